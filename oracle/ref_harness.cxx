@@ -1,0 +1,195 @@
+// TEST INFRASTRUCTURE ONLY -- not part of the shipped engine, never on the product path.
+//
+// C-callable harness around the UNMODIFIED reference sources (zivy/LSQRRecipes), compiled
+// from where they lie under /root/reference against oracle/vnl_shim (VNL is absent from the
+// image; see vnl_shim_core.h for what that implies).  Built by oracle/Makefile into
+// oracle/_ref/libref_oracle.so.  No reference source is copied into this repository: this
+// file only #includes the reference headers and calls their public API.
+//
+// Used (a) to pin the plain-C restatement in oracle/lsqr_oracle.c, (b) to mint the golden
+// fixtures in tests/golden/, (c) as the "reference" CPU baseline in bench.py.
+//
+// Data crosses this boundary as packed doubles, D per datum (see ref_model_info).
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <utility>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "Point2D.h"
+#include "Point3D.h"
+#include "Frame.h"
+#include "Ray3D.h"
+#include "RANSAC.h"
+#include "PlaneParametersEstimator.h"
+#include "LineParametersEstimator.h"
+#include "Line2DParametersEstimator.h"
+#include "SphereParametersEstimator.h"
+#include "AbsoluteOrientationParametersEstimator.h"
+#include "RayIntersectionParametersEstimator.h"
+#include "PivotCalibrationParametersEstimator.h"
+
+using namespace lsqrRecipes;
+
+enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8 };
+
+namespace {
+
+typedef std::pair<Point3D, Point3D> PointPair;
+
+template <class T> struct Marshal;
+template <unsigned n> struct Marshal<Point<double, n> > {
+  enum { D = n };
+  static Point<double, n> get(const double* p) { Point<double, n> r; for (unsigned i = 0; i < n; i++) r[i] = p[i]; return r; }
+};
+template <> struct Marshal<PointPair> {
+  enum { D = 6 };
+  static PointPair get(const double* p) { PointPair r; for (int i = 0; i < 3; i++) { r.first[i] = p[i]; r.second[i] = p[3 + i]; } return r; }
+};
+template <> struct Marshal<Ray3D> {
+  enum { D = 6 };
+  static Ray3D get(const double* p) { Ray3D r; for (int i = 0; i < 3; i++) { r.p[i] = p[i]; r.n[i] = p[3 + i]; } return r; }
+};
+template <> struct Marshal<Frame> {
+  enum { D = 12 };
+  static Frame get(const double* p) {
+    double R[3][3], t[3];
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) R[i][j] = p[3 * i + j]; t[i] = p[9 + i]; }
+    return Frame(R, t);
+  }
+};
+
+template <class T> void unpack(const double* data, size_t n, std::vector<T>& out) {
+  out.clear(); out.reserve(n);
+  for (size_t i = 0; i < n; i++) out.push_back(Marshal<T>::get(data + i * Marshal<T>::D));
+}
+
+struct Cfg { int model; double delta; double aux; int ls_type; };
+
+// Calls f(estimator*, (T*)0) with the concrete reference estimator for cfg.model.
+template <class F> int dispatch(const Cfg& c, F& f) {
+  switch (c.model) {
+    case M_PLANE3: { PlaneParametersEstimator<3> e(c.delta); return f(&e, (Point3D*)0); }
+    case M_LINE2D: { Line2DParametersEstimator e(c.delta); return f(&e, (Point2D*)0); }
+    case M_LINE2: { LineParametersEstimator<2> e(c.delta); return f(&e, (Point2D*)0); }
+    case M_LINE3: { LineParametersEstimator<3> e(c.delta); return f(&e, (Point3D*)0); }
+    case M_CIRCLE2: { SphereParametersEstimator<2> e(c.delta, c.ls_type == 0 ? SphereParametersEstimator<2>::ALGEBRAIC : SphereParametersEstimator<2>::GEOMETRIC); return f(&e, (Point2D*)0); }
+    case M_SPHERE3: { SphereParametersEstimator<3> e(c.delta, c.ls_type == 0 ? SphereParametersEstimator<3>::ALGEBRAIC : SphereParametersEstimator<3>::GEOMETRIC); return f(&e, (Point3D*)0); }
+    case M_ABSOR: { AbsoluteOrientationParametersEstimator e(c.delta); return f(&e, (PointPair*)0); }
+    case M_RAY: { if (c.aux > 0) { RayIntersectionParametersEstimator e(c.delta, c.aux); return f(&e, (Ray3D*)0); } RayIntersectionParametersEstimator e(c.delta); return f(&e, (Ray3D*)0); }
+    case M_PIVOT: { PivotCalibrationEstimator e(c.delta); return f(&e, (Frame*)0); }
+  }
+  return -1;
+}
+
+struct EstimateOp {
+  const double* data; size_t n; double* params;
+  template <class T> int operator()(ParametersEstimator<T, double>* e, T*) {
+    std::vector<T> d; unpack(data, n, d);
+    std::vector<double> p; e->estimate(d, p);
+    for (size_t i = 0; i < p.size(); i++) params[i] = p[i];
+    return (int)p.size();
+  }
+};
+struct LsqOp {
+  const double* data; size_t n; double* params;
+  template <class T> int operator()(ParametersEstimator<T, double>* e, T*) {
+    std::vector<T> d; unpack(data, n, d);
+    std::vector<double> p; e->leastSquaresEstimate(d, p);
+    for (size_t i = 0; i < p.size(); i++) params[i] = p[i];
+    return (int)p.size();
+  }
+};
+struct AgreeOp {
+  const double* params; int np; const double* data; size_t n; uint8_t* out;
+  template <class T> int operator()(ParametersEstimator<T, double>* e, T*) {
+    std::vector<T> d; unpack(data, n, d);
+    std::vector<double> p(params, params + np);
+    int c = 0;
+    for (size_t i = 0; i < n; i++) { bool a = e->agree(p, d[i]); if (out) out[i] = a; c += a; }
+    return c;
+  }
+};
+// Full (no early exit) scoring of an ordered subset list: the per-subset body of the
+// reference's exhaustive driver (RANSAC.hxx:217-249), hypotheses parallelised with OpenMP.
+struct ScoreOp {
+  const double* data; size_t n; const int32_t* subsets; size_t H; int k; int P;
+  uint32_t* counts; double* params_out; int nthreads;
+  template <class T> int operator()(ParametersEstimator<T, double>* e, T*) {
+    std::vector<T> d; unpack(data, n, d);
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads > 0 ? nthreads : omp_get_max_threads())
+#endif
+    for (long long h = 0; h < (long long)H; h++) {
+      std::vector<T*> sub(k);
+      for (int j = 0; j < k; j++) sub[j] = &d[subsets[h * k + j]];
+      std::vector<double> p;
+      e->estimate(sub, p);
+      uint32_t c = 0;
+      if (!p.empty()) for (size_t m = 0; m < n; m++) if (e->agree(p, d[m])) c++;
+      if (counts) counts[h] = c;
+      if (params_out) for (int j = 0; j < P; j++) params_out[h * P + j] = p.empty() ? nan : p[j];
+    }
+    return 0;
+  }
+};
+struct RansacOp {
+  const double* data; size_t n; double prob; bool exhaustive; double* params; uint8_t* mask; double* fraction;
+  template <class T> int operator()(ParametersEstimator<T, double>* e, T*) {
+    std::vector<T> d; unpack(data, n, d);
+    std::vector<double> p; std::vector<bool> cs;
+    double f = exhaustive ? RANSAC<T, double>::compute(p, e, d, &cs) : RANSAC<T, double>::compute(p, e, d, prob, &cs);
+    *fraction = f;
+    for (size_t i = 0; i < p.size(); i++) params[i] = p[i];
+    if (mask) for (size_t i = 0; i < n; i++) mask[i] = (i < cs.size() && cs[i]) ? 1 : 0;
+    return (int)p.size();
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int ref_model_info(int model, int* D, int* P, int* k) {
+  static const int tab[9][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}};
+  if (model < 0 || model > 8) return -1;
+  *D = tab[model][0]; *P = tab[model][1]; *k = tab[model][2];
+  return 0;
+}
+
+int ref_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+// estimate() on n data (n >= k); returns number of parameters written (0 = degenerate).
+int ref_estimate(int model, double delta, double aux, const double* data, size_t n, double* params) {
+  Cfg c = {model, delta, aux, 1}; EstimateOp op = {data, n, params}; return dispatch(c, op);
+}
+int ref_least_squares(int model, double delta, double aux, int ls_type, const double* data, size_t n, double* params) {
+  Cfg c = {model, delta, aux, ls_type}; LsqOp op = {data, n, params}; return dispatch(c, op);
+}
+// agree() of one parameter vector against n data; returns the inlier count, fills out[n] if non-null.
+int ref_agree(int model, double delta, double aux, const double* params, int np, const double* data, size_t n, uint8_t* out) {
+  Cfg c = {model, delta, aux, 1}; AgreeOp op = {params, np, data, n, out}; return dispatch(c, op);
+}
+int ref_score_subsets(int model, double delta, double aux, const double* data, size_t n, const int32_t* subsets, size_t H,
+                      uint32_t* counts, double* params_out, int nthreads) {
+  int D, P, k; if (ref_model_info(model, &D, &P, &k)) return -1;
+  Cfg c = {model, delta, aux, 1}; ScoreOp op = {data, n, subsets, H, k, P, counts, params_out, nthreads}; return dispatch(c, op);
+}
+// The reference's own RANSAC<T,S>::compute: exhaustive (RANSAC.hxx:150-192) or randomized (:4-145).
+int ref_ransac(int model, double delta, double aux, int ls_type, const double* data, size_t n, int exhaustive, double prob,
+               double* params, uint8_t* mask, double* fraction) {
+  Cfg c = {model, delta, aux, ls_type}; RansacOp op = {data, n, prob, exhaustive != 0, params, mask, fraction}; return dispatch(c, op);
+}
+
+}  // extern "C"
