@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- hypothesis x point agree() evaluations per second (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch of synthetic input: minimal solve +
+consensus scoring + arg-max of H Philox-sampled hypotheses against N points resident in HBM
+(workload = BASELINE.json configs[1]: 3D plane, 10 M points, 40 % outliers, 1 M hypotheses per
+GPU, fp32 fast mode).  `value` is whole-job evals/s with inputs resident; `e2e` is the same
+metric through the C ABI with HOST buffers: upload (H2D) + score + consensus set (D2H mask) +
+least-squares refine inside the timed region.  Multi-GPU: points replicated, hypotheses
+partitioned (weak scaling: H per GPU fixed), one all-reduce(MAX) on the packed (count,index) key.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_EVAL = {"plane3": 6, "sphere3": 8, "line2d": 4, "absor": 26}   # FFMA = 2 flop, minimal fused form
+LANEOPS_PER_EVAL = {"plane3": 3, "sphere3": 6, "line2d": 2, "absor": 15}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="plane3", choices=list(FLOP_PER_EVAL))
+    ap.add_argument("--points", type=int, default=10_000_000)
+    ap.add_argument("--hyps", type=int, default=1_000_000, help="hypotheses per GPU")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--cpu-sample-hyps", type=int, default=0, help="hypotheses in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_data(model, n):
+    from lsqrrecipes_b200 import synth
+    data, true = synth.GENERATORS[model](n, seed=synth.SEED)
+    return data, synth.DELTAS[model]
+
+
+def cpu_reference_run(model, data, delta, n_hyps, threads=0):
+    """Times the reference's own estimate()+agree() loop (oracle/_ref when built, else the C port)
+    on the host cores over n_hyps Philox-free random subsets x all points."""
+    from lsqrrecipes_b200 import synth
+    from oracle import pyoracle
+    kind = "ref" if pyoracle.available("ref") else "port"
+    if kind == "port" and not pyoracle.available("port"):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
+    orc = pyoracle.Oracle(kind)
+    m = pyoracle.MODELS[model]
+    k = pyoracle.INFO[m][2]
+    subs = synth.random_subsets(data.shape[0], k, n_hyps, seed=123)
+    t0 = time.perf_counter()
+    counts, _ = orc.score_subsets(m, delta, data, subs, nthreads=threads, want_params=False)
+    dt = time.perf_counter() - t0
+    return {"kind": "reference" if kind == "ref" else "port", "cores": orc.num_threads() if threads == 0 else threads,
+            "seconds": dt, "evals": float(n_hyps) * data.shape[0], "best": int(counts.max())}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    data, delta = make_data(args.model, args.points)
+    cores = os.cpu_count() or 1
+    n_hyps = args.cpu_sample_hyps or max(cores * 2, 16)
+    for _ in range(args.warmup):
+        cpu_reference_run(args.model, data, delta, max(cores, 4))
+    times, info = [], None
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        info = cpu_reference_run(args.model, data, delta, n_hyps)
+        times.append(info["seconds"])
+    total = time.perf_counter() - t_all
+    value = info["evals"] * args.steps / sum(times)
+    line = {
+        "impl": "reference", "metric": "hypothesis x point agree() evals/sec", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.model} RANSAC consensus, {args.points} synthetic points, 40% outliers (BASELINE.json configs[1])",
+                   "sample": f"{n_hyps} hypotheses x {args.points} points per step"},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": info["cores"], "kind": info["kind"],
+                         "sample": f"{n_hyps} hypotheses x {args.points} points per step, estimate()+agree() loop of RANSAC.hxx:217-249, OpenMP over hypotheses"},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": total,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from lsqrrecipes_b200 import FP32, FP64, SAMPLE_PHILOX, Engine
+    from lsqrrecipes_b200.dist import install_hooks
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    precision = FP32 if args.precision == "fp32" else FP64
+    model = args.model
+    N, Hper = args.points, args.hyps
+    Hglobal = Hper * world
+
+    data, delta = make_data(model, N)
+    host = torch.from_numpy(data).pin_memory()                 # host buffer for the e2e leg
+    eng = Engine(model, delta, device=local)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    if world > 1:
+        install_hooks(eng, rank, world)
+    eng.upload_ptr(host.data_ptr(), N, data.shape[1] * 8)       # untimed: inputs resident in HBM
+
+    # measured pipe peaks for the roofline (same device, same moment)
+    ffma, _ = eng.microbench_fma(0, 8192)
+    ffma2, _ = eng.microbench_fma(1, 8192)
+    dfma, _ = eng.microbench_fma(2, 2048)
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def step(seed):
+        flush.zero_()
+        return eng.score(count=Hglobal, sampler=SAMPLE_PHILOX, precision=precision, seed=seed)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        step(1000 + w)
+    launches0 = eng.kernel_launches
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cons_ms = []
+    with ClockSampler(local) as clk:
+        ev0.record()
+        for s in range(args.steps):
+            r = step(s)
+            cons_ms.append(r["consensus_ms"])
+        ev1.record()
+        barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = eng.kernel_launches - launches0
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    evals_per_step = float(Hglobal) * float(N)
+    value = evals_per_step * args.steps / (elapsed_ms * 1e-3)
+
+    # roofline of the dominant kernel (consensus), from CUDA events on its own stream inside the library
+    kern_ms = float(np.mean(cons_ms))
+    kern_evals = float(Hper) * float(N)
+    if precision == FP32:
+        achieved = kern_evals * FLOP_PER_EVAL[model] / (kern_ms * 1e-3) / 1e12
+        peak = ffma * 2 / 1e12
+        bound = "fp32_pipe"
+    else:
+        achieved = kern_evals * 9 / (kern_ms * 1e-3) / 1e12    # as-written 3 DSUB + 4 DMUL + 2 DADD, no FMA
+        peak = dfma / 1e12                                       # one lane-op per cycle per fp64 lane
+        bound = "fp64_pipe"
+    roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "consensus_kernel", "kernel_ms": kern_ms,
+                "peak_source": "measured live: register-resident FFMA chain (lsqr_microbench_fma); not in MEASURED_PEAKS.json",
+                "ffma_tflops": ffma * 2 / 1e12, "ffma2_tflops": ffma2 * 2 / 1e12, "dfma_tflops": dfma * 2 / 1e12,
+                "algorithmic_flop_per_eval": FLOP_PER_EVAL[model] if precision == FP32 else 9}
+
+    # e2e: host buffers in, mask + parameters out, everything inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step(seed):
+            eng.upload_ptr(host.data_ptr(), N, data.shape[1] * 8)
+            r = eng.score(count=Hglobal, sampler=SAMPLE_PHILOX, precision=precision, seed=seed)
+            cnt = eng.consensus(r["best_params"])
+            mask = eng.get_mask()
+            prm = eng.refine()
+            return cnt, mask, prm
+        e2e_step(77)
+        barrier()
+        t0 = time.perf_counter()
+        ke = max(1, min(args.steps, 3))
+        for s in range(ke):
+            cnt, mask, prm = e2e_step(s)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        rs = eng.last_refine_stats()
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            hbm_peak = 6650.0
+        e2e = {"value": evals_per_step * ke / dt, "unit": "evals/s", "h2d_bytes_per_step": int(N * data.shape[1] * 8),
+               "d2h_bytes_per_step": int(N + 8 * 16), "ms_per_step": 1e3 * dt / ke, "steps": ke,
+               "inlier_fraction": cnt / N, "params": [float(x) for x in prm]}
+        roofline_refine = {"bound": "hbm", "achieved": rs["bytes"] / (rs["kernel_ms"] * 1e-3) / 1e9 if rs["kernel_ms"] > 0 else None,
+                           "peak": hbm_peak, "unit": "GB/s", "kernel": "mask_moments_kernel", "kernel_ms": rs["kernel_ms"],
+                           "traffic": None}
+        if roofline_refine["achieved"]:
+            roofline_refine["frac"] = roofline_refine["achieved"] / hbm_peak
+    else:
+        roofline_refine = None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_hyps = args.cpu_sample_hyps or max(4 * cores, 64)
+        info = cpu_reference_run(model, data, delta, n_hyps)
+        cpu = {"value": info["evals"] / info["seconds"], "unit": "evals/s", "cores": info["cores"], "kind": info["kind"],
+               "sample": f"{n_hyps} hypotheses x {N} points, estimate()+agree() loop (RANSAC.hxx:217-249), OpenMP over hypotheses, {info['seconds']:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "hypothesis x point agree() evals/sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if precision == FP32 else "f64", "data": "synthetic",
+            "config": {"workload": f"{model} RANSAC (BASELINE.json configs[1]): {N} synthetic points, 40% outliers, {Hper} Philox hypotheses per GPU, delta={delta}",
+                       "points": N, "hypotheses_per_gpu": Hper, "hypotheses_total": Hglobal, "precision": args.precision,
+                       "parallelism": f"points replicated, hypotheses partitioned x{world}, 1 all-reduce(max) on the packed key",
+                       "l2": "256 MB flush buffer written between steps"},
+            "roofline": roofline, "roofline_refine": roofline_refine, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clk.summary(),
+            "best_count": int(r["best_count"]),
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,199 @@
+/* lsqr_b200.h -- C ABI of the B200-native RANSAC / least-squares engine.
+ *
+ * This is the drop-in boundary for ONE path of zivy/LSQRRecipes: the RANSAC driver
+ * (parametersEstimators/RANSAC.h:75-79 randomized compute, :111-113 exhaustive compute,
+ * bodies RANSAC.hxx:4-249) together with the estimate / agree / leastSquaresEstimate
+ * bodies of the estimators it calls through ParametersEstimator<T,S>
+ * (parametersEstimators/ParametersEstimator.h:41-61).  The re-authored C++ headers in
+ * include/lsqrRecipes/ keep the reference's class names and signatures and forward here;
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Plain pointers and sizes only; no C++ or torch types.  All entry points return 0 on
+ * success or a negative lsqr_status; lsqr_last_error() gives the text.  Nothing throws
+ * across this boundary.  One context per host thread; calls are synchronous at return.
+ * There is NO CPU fallback: without a CUDA device every call fails with LSQR_ERR_CUDA.
+ *
+ * Data layouts are the reference's host layouts: a datum is `dim` doubles
+ * at the start of each `stride`-byte record:
+ *   Point<double,n>   n doubles                 (common/Point.h:127)       stride 8n
+ *   pair<Point3D,Point3D>  first[3], second[3]  (std::pair)                stride 48
+ *   Ray3D             p[3], n[3]                (common/Ray3D.h:23-24)     stride 48
+ *   Frame             rotation[3][3], translation[3] (common/Frame.h:30-31) stride 104
+ */
+#ifndef LSQR_B200_H
+#define LSQR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lsqr_ctx lsqr_ctx;
+
+/* Estimator behind the context.  Replaces the virtual dispatch of
+ * ParametersEstimator<T,S> (ParametersEstimator.h:26-64) for the listed classes. */
+typedef enum lsqr_model {
+  LSQR_PLANE3 = 0,  /* PlaneParametersEstimator<3>            PlaneParametersEstimator.hxx:36-203 */
+  LSQR_LINE2D = 1,  /* Line2DParametersEstimator              Line2DParametersEstimator.cxx:11-123 */
+  LSQR_LINE2 = 2,   /* LineParametersEstimator<2>             LineParametersEstimator.hxx:23-150 */
+  LSQR_LINE3 = 3,   /* LineParametersEstimator<3> */
+  LSQR_CIRCLE2 = 4, /* SphereParametersEstimator<2>           SphereParametersEstimator.hxx:80-109,255-338 */
+  LSQR_SPHERE3 = 5, /* SphereParametersEstimator<3>           SphereParametersEstimator.hxx:115-163,255-338 */
+  LSQR_ABSOR = 6,   /* AbsoluteOrientationParametersEstimator AbsoluteOrientationParametersEstimator.cxx:14-327 */
+  LSQR_RAY = 7,     /* RayIntersectionParametersEstimator     RayIntersectionParametersEstimator.cxx:23-179 */
+  LSQR_PIVOT = 8,   /* PivotCalibrationEstimator              PivotCalibrationParametersEstimator.cxx:9-123 */
+  LSQR_NUM_MODELS = 9
+} lsqr_model;
+
+typedef enum lsqr_status {
+  LSQR_OK = 0,
+  LSQR_ERR_ARG = -1,     /* bad argument / unsupported combination */
+  LSQR_ERR_CUDA = -2,    /* CUDA runtime failure (including: no device) */
+  LSQR_ERR_STATE = -3,   /* call out of order (e.g. score before upload) */
+  LSQR_ERR_COMM = -4     /* collective hook failed */
+} lsqr_status;
+
+typedef enum lsqr_precision {
+  LSQR_FP64 = 0, /* validation mode: the reference's operation order, no FMA contraction; bit-exact counts */
+  LSQR_FP32 = 1  /* fast mode: hoisted constants, fused multiply-add */
+} lsqr_precision;
+
+typedef enum lsqr_sampler {
+  LSQR_SAMPLE_PHILOX = 0,     /* on-device Philox4x32-10, counter = global hypothesis index (replaces RANSAC.hxx:44-79) */
+  LSQR_SAMPLE_EXHAUSTIVE = 1, /* lexicographic unranking, the order of RANSAC.hxx:197-213 */
+  LSQR_SAMPLE_LIST = 2,       /* caller-supplied ordered subsets, int32 [H][k] */
+  LSQR_SAMPLE_PARAMS = 3      /* caller-supplied hypothesis parameters, double [H][P] (agree() only) */
+} lsqr_sampler;
+
+/* SphereParametersEstimator::LeastSquaresType (SphereParametersEstimator.h:43) */
+typedef enum lsqr_ls_type { LSQR_LS_ALGEBRAIC = 0, LSQR_LS_GEOMETRIC = 1 } lsqr_ls_type;
+
+#define LSQR_MAX_PARAMS 8
+#define LSQR_MAX_SUBSET 4
+
+/* ---- model table ------------------------------------------------------------------ */
+/* dim = doubles per datum, nparams = length of the parameter vector, k = numForEstimate()
+ * (ParametersEstimator.h:61). */
+int lsqr_model_info(int model, int* dim, int* nparams, int* k);
+
+/* ---- context ---------------------------------------------------------------------- */
+int lsqr_ctx_create(lsqr_ctx** out, int device);
+void lsqr_ctx_destroy(lsqr_ctx* ctx);
+const char* lsqr_last_error(const lsqr_ctx* ctx);
+/* Run every kernel of this context on an existing CUDA stream (cudaStream_t passed as void*). */
+int lsqr_ctx_set_stream(lsqr_ctx* ctx, void* cuda_stream);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t lsqr_kernel_launches(const lsqr_ctx* ctx);
+
+/* Estimator configuration: the constructor arguments of the reference classes
+ * (delta: e.g. PlaneParametersEstimator.h:31; aux: RayIntersectionParametersEstimator.h:34-35
+ * minimalAngularDeviation, <=0 selects the reference default of 1 degree;
+ * ls_type: SphereParametersEstimator.h:37). */
+int lsqr_set_estimator(lsqr_ctx* ctx, int model, double delta, double aux, int ls_type);
+
+/* Copy n data records (host memory, reference AoS layout, see top) to the device and build
+ * the SoA fp64 / fp32 working layouts.  Replaces the `std::vector<T>& data` argument of
+ * RANSAC::compute (RANSAC.h:77).  The input is not retained. */
+int lsqr_upload(lsqr_ctx* ctx, const void* aos, size_t n, size_t stride_bytes);
+/* Same, for a buffer that already lives in device memory (packed doubles, dim per record). */
+int lsqr_upload_device(lsqr_ctx* ctx, const double* dev_packed, size_t n);
+
+/* Multi-GPU sharding: this context scores hypotheses [rank*H/world, (rank+1)*H/world) of every
+ * request and refines the points [rank*N/world, (rank+1)*N/world).  The two exchange steps go
+ * through caller-supplied hooks operating IN PLACE on device memory (NCCL all-reduce over
+ * NVLink in bench.py).  Hooks must be stream-ordered on `cuda_stream`. */
+typedef int (*lsqr_allreduce_max_u64_fn)(void* user, uint64_t* dev_key, void* cuda_stream);
+typedef int (*lsqr_allreduce_sum_f64_fn)(void* user, double* dev_vals, int count, void* cuda_stream);
+int lsqr_set_shard(lsqr_ctx* ctx, int rank, int world, lsqr_allreduce_max_u64_fn max_fn,
+                   lsqr_allreduce_sum_f64_fn sum_fn, void* user);
+
+/* ---- scoring: minimal solve + consensus for a batch of hypotheses ------------------- */
+typedef struct lsqr_score_args {
+  int sampler;           /* lsqr_sampler */
+  int precision;         /* lsqr_precision */
+  uint64_t seed;         /* Philox key */
+  uint64_t first;        /* global index of the first hypothesis (Philox counter / lexicographic rank) */
+  uint64_t count;        /* H: number of hypotheses in this request (global, before sharding) */
+  const int32_t* subsets;/* LSQR_SAMPLE_LIST: host int32 [H][k] */
+  const double* params;  /* LSQR_SAMPLE_PARAMS: host double [H][P]; NaN row = degenerate */
+  uint32_t* out_counts;  /* optional host [H]: full inlier count per hypothesis (no early exit, RANSAC.hxx:239-244) */
+  double* out_params;    /* optional host [H][P]: estimate() output per hypothesis, NaN row if degenerate */
+} lsqr_score_args;
+
+typedef struct lsqr_score_result {
+  uint64_t best_index;   /* global index of the winner; ties -> lowest index (strict '>' of RANSAC.hxx:100,245) */
+  uint32_t best_count;   /* its inlier count; 0 = no valid hypothesis */
+  uint32_t n_valid;      /* hypotheses whose minimal subset was not degenerate (this rank) */
+  int32_t best_subset[LSQR_MAX_SUBSET];
+  double best_params[LSQR_MAX_PARAMS];
+  double score_ms;       /* device time of solve + consensus + arg-max (CUDA events) */
+  double consensus_ms;   /* device time of the consensus kernel(s) alone */
+} lsqr_score_result;
+
+int lsqr_score(lsqr_ctx* ctx, const lsqr_score_args* args, lsqr_score_result* res);
+
+/* ---- consensus set + least-squares refine ------------------------------------------ */
+/* agree() of `params` against every uploaded datum in fp64 reference arithmetic
+ * (e.g. PlaneParametersEstimator.hxx:196-203): stores the consensus set on the device,
+ * returns its size.  Replaces RANSAC.hxx:129-137. */
+int lsqr_consensus(lsqr_ctx* ctx, const double* params, uint32_t* out_count);
+/* Copy the stored consensus set to the host, one byte per datum (std::vector<bool> order). */
+int lsqr_get_mask(lsqr_ctx* ctx, uint8_t* out_bytes);
+/* leastSquaresEstimate() over the stored consensus set (RANSAC.hxx:138), or over all data
+ * when use_mask == 0.  *n_params = 0 means the reference's "empty parameters" (degenerate). */
+int lsqr_refine(lsqr_ctx* ctx, int use_mask, double* out_params, int* n_params);
+
+/* ---- whole calls -------------------------------------------------------------------- */
+typedef struct lsqr_compute_result {
+  double params[LSQR_MAX_PARAMS];
+  int n_params;          /* 0 = empty parameter vector (reference error convention, RANSAC.h:53-63) */
+  double fraction;       /* return value of RANSAC::compute: |consensus set| / N */
+  uint32_t best_count;
+  uint64_t best_index;
+  uint64_t tries;        /* hypotheses actually scored */
+  double device_ms;      /* sum of device time over all kernels of the call */
+} lsqr_compute_result;
+
+/* RANSAC<T,S>::compute(parameters, estimator, data, desiredProbabilityForNoOutliers,
+ * consensusSet) -- RANSAC.h:75-79 / RANSAC.hxx:4-145.  Rounds of Philox-sampled hypotheses;
+ * the stop rule of RANSAC.hxx:107-110 is re-evaluated between rounds.  Invalid input
+ * (N < k, prob outside (0,1)) returns LSQR_OK with fraction = 0, n_params = 0. */
+int lsqr_ransac(lsqr_ctx* ctx, double prob, int precision, uint64_t seed, uint8_t* out_mask_bytes,
+                lsqr_compute_result* res);
+/* The brute-force overload, RANSAC.h:111-113 / RANSAC.hxx:150-249: all C(N,k) subsets in
+ * lexicographic order, first maximum wins. */
+int lsqr_ransac_exhaustive(lsqr_ctx* ctx, int precision, uint8_t* out_mask_bytes, lsqr_compute_result* res);
+
+/* Many independent small problems, one thread block per problem (a host loop of
+ * RANSAC::compute calls in the reference).  data: host packed doubles, problems back to
+ * back; `offsets` [n_problems+1] in records.  exhaustive != 0 enumerates all C(n,k) subsets
+ * of each problem (RANSAC.hxx:150-249); otherwise rounds of Philox hypotheses with the stop
+ * rule of RANSAC.hxx:107-110 for `prob` (prob <= 0: exactly max_tries hypotheses), capped at
+ * max_tries.  Outputs per problem: params [n_problems][P] (NaN row = empty), counts
+ * [n_problems], optional masks (bytes, same indexing as data). */
+int lsqr_ransac_batch(lsqr_ctx* ctx, const double* data, const uint64_t* offsets, uint64_t n_problems,
+                      int exhaustive, double prob, uint32_t max_tries, uint64_t seed,
+                      double* out_params, uint32_t* out_counts, uint8_t* out_masks, double* device_ms);
+
+/* ---- the estimator's own methods, for callers that use them directly ---------------- */
+/* estimate() on k (or more) data in host memory; *n_params = 0 when degenerate. */
+int lsqr_estimate(lsqr_ctx* ctx, const double* packed, size_t n, double* out_params, int* n_params);
+/* agree() of one parameter vector against n packed data; out[n] bytes. */
+int lsqr_agree(lsqr_ctx* ctx, const double* params, const double* packed, size_t n, uint8_t* out);
+/* leastSquaresEstimate() on n packed data in host memory. */
+int lsqr_least_squares(lsqr_ctx* ctx, const double* packed, size_t n, double* out_params, int* n_params);
+
+/* ---- measurement helpers ------------------------------------------------------------ */
+/* Register-resident FMA-chain microbenchmarks: returns lane-FMA/s of the fp32 (kind 0),
+ * packed fp32x2 (kind 1) or fp64 (kind 2) pipe on the context's device.  Used by bench.py
+ * to state the consensus kernel's roofline against a MEASURED pipe peak. */
+int lsqr_microbench_fma(lsqr_ctx* ctx, int kind, int iters, double* out_fma_per_s, double* out_ms);
+/* Time of the last refine's streaming moment kernel and the bytes it had to read. */
+int lsqr_last_refine_stats(const lsqr_ctx* ctx, double* kernel_ms, double* algorithmic_bytes, int* lm_iterations);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSQR_B200_H */

@@ -1,0 +1,743 @@
+// Consensus set + least-squares refine (RANSAC.hxx:129-138 and the estimators'
+// leastSquaresEstimate bodies).
+//
+// One streaming pass per refine: every datum is read once from the fp64 SoA arrays, agree() is
+// evaluated in reference arithmetic against the winning hypothesis, the consensus bit is written
+// (one 32-bit word per warp via ballot) and -- in the same pass -- the estimator's least-squares
+// moments are accumulated over the inliers in fp64.  The kernel is HBM-bound: D*8 bytes read per
+// datum, 1 bit written.  Per-block partial sums are combined in a fixed order (reproducible), and a
+// single-thread kernel turns the moments into parameters with small Jacobi eigen / pseudo-inverse
+// solves.  The sphere's geometric fit runs Levenberg-Marquardt with one such pass per function
+// evaluation (J^T J, J^T r and the cost in one sweep) and an on-device controller.
+//
+// All position components are accumulated relative to dv.center (shift-invariant scatter / normal
+// equations), which keeps the fp64 sums well conditioned for coordinates far from the origin.
+#include "engine.h"
+
+namespace lsqr {
+
+// number of accumulated doubles per model (index 0 is always the inlier count)
+__host__ __device__ inline int n_moments(int model, bool lm) {
+  switch (model) {
+    case PLANE3: case LINE3: return 10;
+    case LINE2D: case LINE2: return 6;
+    case CIRCLE2: return lm ? 11 : 9;
+    case SPHERE3: return lm ? 16 : 14;
+    case ABSOR: return 16;
+    case RAY: return 10;
+    case PIVOT: return 22;
+  }
+  return 0;
+}
+int moments_count(int model, bool lm) { return n_moments(model, lm); }
+
+template <int M> struct Mom { static constexpr int N = 0, NLM = 0; };
+template <> struct Mom<PLANE3>  { static constexpr int N = 10, NLM = 0; };
+template <> struct Mom<LINE3>   { static constexpr int N = 10, NLM = 0; };
+template <> struct Mom<LINE2D>  { static constexpr int N = 6,  NLM = 0; };
+template <> struct Mom<LINE2>   { static constexpr int N = 6,  NLM = 0; };
+template <> struct Mom<CIRCLE2> { static constexpr int N = 9,  NLM = 11; };
+template <> struct Mom<SPHERE3> { static constexpr int N = 14, NLM = 16; };
+template <> struct Mom<ABSOR>   { static constexpr int N = 16, NLM = 0; };
+template <> struct Mom<RAY>     { static constexpr int N = 10, NLM = 0; };
+template <> struct Mom<PIVOT>   { static constexpr int N = 22, NLM = 0; };
+
+// q = centred datum.  acc[0] counts.
+template <int DIM> __device__ __forceinline__ void acc_scatter(const double* q, double* acc) {
+  acc[0] += 1.0;
+  int o = 1;
+#pragma unroll
+  for (int j = 0; j < DIM; j++) acc[o++] += q[j];
+#pragma unroll
+  for (int j = 0; j < DIM; j++)
+#pragma unroll
+    for (int k = j; k < DIM; k++) acc[o++] += q[j] * q[k];
+}
+template <int DIM> __device__ __forceinline__ void acc_sphere_alg(const double* q, double* acc) {
+  double s = 0;
+#pragma unroll
+  for (int j = 0; j < DIM; j++) s += q[j] * q[j];
+  acc_scatter<DIM>(q, acc);
+  int o = 1 + DIM + DIM * (DIM + 1) / 2;
+#pragma unroll
+  for (int j = 0; j < DIM; j++) acc[o++] += s * q[j];
+  acc[o] += s;
+}
+// residual / Jacobian of SphereParametersEstimator.hxx:394-431 at x = (centre', r)
+template <int DIM> __device__ __forceinline__ void acc_sphere_lm(const double* q, const double* x, double* acc) {
+  double J[DIM + 1], s = 0;
+#pragma unroll
+  for (int j = 0; j < DIM; j++) s += (q[j] - x[j]) * (q[j] - x[j]);
+  const double sv = sqrt(s), r = sv - x[DIM];
+#pragma unroll
+  for (int j = 0; j < DIM; j++) J[j] = (x[j] - q[j]) / sv;
+  J[DIM] = -1.0;
+  acc[0] += 1.0;
+  int o = 1;
+#pragma unroll
+  for (int a = 0; a <= DIM; a++)
+#pragma unroll
+    for (int b = a; b <= DIM; b++) acc[o++] += J[a] * J[b];
+#pragma unroll
+  for (int a = 0; a <= DIM; a++) acc[o++] += J[a] * r;
+  acc[o] += r * r;
+}
+
+template <int M> __device__ __forceinline__ void accumulate(const double* q, double* acc);
+template <> __device__ __forceinline__ void accumulate<PLANE3>(const double* q, double* acc) { acc_scatter<3>(q, acc); }
+template <> __device__ __forceinline__ void accumulate<LINE3>(const double* q, double* acc) { acc_scatter<3>(q, acc); }
+template <> __device__ __forceinline__ void accumulate<LINE2D>(const double* q, double* acc) { acc_scatter<2>(q, acc); }
+template <> __device__ __forceinline__ void accumulate<LINE2>(const double* q, double* acc) { acc_scatter<2>(q, acc); }
+template <> __device__ __forceinline__ void accumulate<CIRCLE2>(const double* q, double* acc) { acc_sphere_alg<2>(q, acc); }
+template <> __device__ __forceinline__ void accumulate<SPHERE3>(const double* q, double* acc) { acc_sphere_alg<3>(q, acc); }
+// AbsoluteOrientationParametersEstimator.cxx:134-166: sums of both point sets and of p1 p2^T
+template <> __device__ __forceinline__ void accumulate<ABSOR>(const double* q, double* acc) {
+  acc[0] += 1.0;
+#pragma unroll
+  for (int j = 0; j < 6; j++) acc[1 + j] += q[j];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) acc[7 + r * 3 + c] += q[r] * q[3 + c];
+}
+// RayIntersectionParametersEstimator.cxx:108-123
+template <> __device__ __forceinline__ void accumulate<RAY>(const double* q, double* acc) {
+  const double* n = q + 3;
+  acc[0] += 1.0;
+  acc[1] += n[0] * n[0]; acc[2] += n[0] * n[1]; acc[3] += n[0] * n[2];
+  acc[4] += n[1] * n[1]; acc[5] += n[1] * n[2]; acc[6] += n[2] * n[2];
+  const double s = n[0] * q[0] + n[1] * q[1] + n[2] * q[2];
+  acc[7] += q[0] - s * n[0]; acc[8] += q[1] - s * n[1]; acc[9] += q[2] - s * n[2];
+}
+// Normal equations of the rows [R | -I] x = -t (PivotCalibrationParametersEstimator.cxx:77-83)
+template <> __device__ __forceinline__ void accumulate<PIVOT>(const double* q, double* acc) {
+  acc[0] += 1.0;
+  int o = 1;
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = a; b < 3; b++) acc[o++] += q[a] * q[b] + q[3 + a] * q[3 + b] + q[6 + a] * q[6 + b];  // (R^T R)_{ab}
+#pragma unroll
+  for (int j = 0; j < 9; j++) acc[o++] += q[j];                                                          // sum R
+#pragma unroll
+  for (int a = 0; a < 3; a++) acc[o++] += q[a] * q[9] + q[3 + a] * q[10] + q[6 + a] * q[11];            // R^T t
+#pragma unroll
+  for (int a = 0; a < 3; a++) acc[o++] += q[9 + a];                                                      // sum t
+}
+
+__host__ __device__ inline bool centred_comp(int model, int d) {
+  switch (model) {
+    case RAY: return d < 3;
+    case PIVOT: return d >= 9;
+    default: return true;
+  }
+}
+
+// MODE 0: every datum counts; 1: evaluate agree() and write the consensus bits; 2: read stored bits.
+template <int M, int MODE, bool LM>
+__global__ void __launch_bounds__(256) mask_moments_kernel(DataView dv, uint32_t begin, uint32_t end, const double* __restrict__ params_dev,
+                                                            const double* __restrict__ lm_state, EstCfg cfg, uint32_t* __restrict__ maskbits,
+                                                            double* __restrict__ partials) {
+  constexpr int D = Model<M>::D, P = Model<M>::P, HQ = Model<M>::HQ;
+  constexpr int NM = LM ? Mom<M>::NLM : Mom<M>::N;
+  double acc[NM > 0 ? NM : 1];
+#pragma unroll
+  for (int j = 0; j < NM; j++) acc[j] = 0.0;
+  double hq[HQ];
+  if (MODE == 1) {
+    double prm[P];
+#pragma unroll
+    for (int j = 0; j < P; j++) prm[j] = params_dev[j];
+    prepare<M>(prm, hq);
+  }
+  double lmx[4] = {0, 0, 0, 0};
+  if (LM) {
+    // lm_state[9] selects the evaluation point: 0 -> x (state[0..3]), 1 -> trial (state[10..13])
+    const int off = (lm_state[9] != 0.0) ? 10 : 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) lmx[j] = lm_state[off + j];
+  }
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  for (uint64_t base = (uint64_t)begin + (uint64_t)warp * 32; base < end; base += (uint64_t)warps_total * 32) {
+    const uint64_t i = base + lane;
+    double x[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) x[d] = dv.soa64[(size_t)d * dv.ld + i];  // padded with NaN beyond n: never agrees
+    bool in;
+    if (MODE == 0) in = i < end;
+    else if (MODE == 1) {
+      in = (i < end) && agree<M>(hq, x, cfg);
+      const unsigned bits = __ballot_sync(0xffffffffu, in);
+      if (lane == 0) maskbits[base >> 5] = bits;
+    } else in = (i < end) && ((maskbits[base >> 5] >> lane) & 1u);
+    if (in) {
+      double q[D];
+#pragma unroll
+      for (int d = 0; d < D; d++) q[d] = centred_comp(M, d) ? x[d] - dv.center[d] : x[d];
+      if (LM) {
+        if constexpr (M == CIRCLE2) acc_sphere_lm<2>(q, lmx, acc);
+        if constexpr (M == SPHERE3) acc_sphere_lm<3>(q, lmx, acc);
+      } else accumulate<M>(q, acc);
+    }
+  }
+  // block reduction: shuffle within warps, shared memory across the 8 warps
+  __shared__ double sh[8][kMaxMoments];
+#pragma unroll
+  for (int j = 0; j < NM; j++) {
+    double v = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[threadIdx.x >> 5][j] = v;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < NM) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) v += sh[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * kMaxMoments + threadIdx.x] = v;
+  }
+}
+
+void launch_mask_moments(int model, const DataView& dv, uint32_t begin, uint32_t end, const double* params_dev, int mask_mode,
+                         const double* lm_state, const EstCfg& cfg, const RefineBuffers& rb, cudaStream_t s) {
+  const int blocks = rb.blocks;
+#define LAUNCH(MM, MODE, LMV) mask_moments_kernel<MM, MODE, LMV><<<blocks, 256, 0, s>>>(dv, begin, end, params_dev, lm_state, cfg, rb.maskbits, rb.partials)
+#define BYMODE(MM, LMV)                                   \
+  if (mask_mode == 0) LAUNCH(MM, 0, LMV);                 \
+  else if (mask_mode == 1) LAUNCH(MM, 1, LMV);            \
+  else LAUNCH(MM, 2, LMV)
+  if (lm_state) {
+    if (model == CIRCLE2) { BYMODE(CIRCLE2, true); }
+    else if (model == SPHERE3) { BYMODE(SPHERE3, true); }
+    return;
+  }
+  switch (model) {
+    case PLANE3: { BYMODE(PLANE3, false); break; }
+    case LINE2D: { BYMODE(LINE2D, false); break; }
+    case LINE2: { BYMODE(LINE2, false); break; }
+    case LINE3: { BYMODE(LINE3, false); break; }
+    case CIRCLE2: { BYMODE(CIRCLE2, false); break; }
+    case SPHERE3: { BYMODE(SPHERE3, false); break; }
+    case ABSOR: { BYMODE(ABSOR, false); break; }
+    case RAY: { BYMODE(RAY, false); break; }
+    case PIVOT: { BYMODE(PIVOT, false); break; }
+  }
+#undef BYMODE
+#undef LAUNCH
+}
+
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, int blocks, int nm, double* __restrict__ moments) {
+  const int j = threadIdx.x;
+  if (j >= nm) return;
+  double v = 0.0;
+  for (int b = 0; b < blocks; b++) v += partials[(size_t)b * kMaxMoments + j];
+  moments[j] = v;
+}
+void launch_reduce_partials(const RefineBuffers& rb, int nm, cudaStream_t s) {
+  reduce_partials_kernel<<<1, 32, 0, s>>>(rb.partials, rb.blocks, nm, rb.moments);
+}
+
+// ---------------------------------------------------------------------------------------
+// moments -> parameters
+// ---------------------------------------------------------------------------------------
+
+// Symmetric positive semi-definite solve through the eigen-decomposition of the diagonally
+// scaled matrix; eigenvalues below 1e-13 of the largest are dropped.  Returns the rank.
+// Stands in for vnl_matrix_inverse on the normal equations of the reference's tall systems.
+template <int N>
+__device__ int sym_pinv_solve(const double* A, const double* b, double* x) {
+  double S[N * N], V[N * N], ev[N], sc[N], y[N];
+  for (int i = 0; i < N; i++) sc[i] = A[i * N + i] > 0 ? 1.0 / sqrt(A[i * N + i]) : 1.0;
+  for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) S[i * N + j] = A[i * N + j] * sc[i] * sc[j];
+  sym_eig<N>(S, V, ev);
+  const double tol = 1e-13 * fabs(ev[N - 1]);
+  int rank = 0;
+  for (int k = 0; k < N; k++) {
+    double d = 0;
+    for (int i = 0; i < N; i++) d += V[i * N + k] * (b[i] * sc[i]);
+    if (ev[k] > tol) { y[k] = d / ev[k]; rank++; } else y[k] = 0.0;
+  }
+  for (int i = 0; i < N; i++) { double s = 0; for (int k = 0; k < N; k++) s += V[i * N + k] * y[k]; x[i] = s * sc[i]; }
+  return rank;
+}
+
+// PlaneParametersEstimator.hxx:141-171 (col 0) / LineParametersEstimator.hxx:80-110 (col DIM-1)
+template <int DIM> __device__ int solve_scatter(const double* m, const double* c, int col, double* out) {
+  const double n = m[0];
+  if (n < 1.0) return 0;
+  double C[DIM * DIM], V[DIM * DIM], ev[DIM];
+  int o = 1 + DIM;
+  for (int j = 0; j < DIM; j++) for (int k = j; k < DIM; k++) { const double v = m[o++] - m[1 + j] * m[1 + k] / n; C[j * DIM + k] = v; C[k * DIM + j] = v; }
+  sym_eig<DIM>(C, V, ev);
+  for (int j = 0; j < DIM; j++) out[j] = V[j * DIM + col];
+  for (int j = 0; j < DIM; j++) out[DIM + j] = m[1 + j] / n + c[j];
+  return 2 * DIM;
+}
+// Line2DParametersEstimator.cxx:50-100
+__device__ int solve_line2d(const double* m, const double* c, double* out) {
+  const double n = m[0];
+  if (n < 1.0) return 0;
+  const double mx = m[1] / n, my = m[2] / n;
+  const double c11 = m[3] - n * mx * mx, c12 = m[4] - n * mx * my, c22 = m[5] - n * my * my;
+  double nx, ny;
+  if (c11 < 1e-12) {
+    nx = 1.0; ny = 0.0;
+    if (c22 < 1e-12) return 0;
+  } else {
+    const double lambda1 = (c11 + c22 + sqrt((c11 - c22) * (c11 - c22) + 4 * c12 * c12)) / 2.0;
+    nx = -c12; ny = lambda1 - c22;
+    const double norm = sqrt(nx * nx + ny * ny);
+    nx /= norm; ny /= norm;
+  }
+  out[0] = nx; out[1] = ny; out[2] = mx + c[0]; out[3] = my + c[1];
+  return 4;
+}
+// SphereParametersEstimator.hxx:267-307 through the normal equations of [-2p, 1] x = -|p|^2.
+// Result in centred coordinates: out = (centre', r).
+template <int DIM> __device__ int solve_sphere_alg(const double* m, double* out) {
+  constexpr int NP = DIM + 1;
+  const double n = m[0];
+  if (n < (double)NP) return 0;
+  double A[NP * NP], b[NP], x[NP];
+  int o = 1 + DIM;
+  for (int j = 0; j < DIM; j++) for (int k = j; k < DIM; k++) { const double v = 4.0 * m[o++]; A[j * NP + k] = v; A[k * NP + j] = v; }
+  for (int j = 0; j < DIM; j++) { A[j * NP + DIM] = -2.0 * m[1 + j]; A[DIM * NP + j] = -2.0 * m[1 + j]; }
+  A[DIM * NP + DIM] = n;
+  for (int j = 0; j < DIM; j++) b[j] = 2.0 * m[o++];
+  b[DIM] = -m[o];
+  if (sym_pinv_solve<NP>(A, b, x) < NP) return 0;
+  double r2 = -x[DIM];
+  for (int j = 0; j < DIM; j++) { out[j] = x[j]; r2 += x[j] * x[j]; }
+  if (!(r2 > 0)) return 0;
+  out[DIM] = sqrt(r2);
+  return NP;
+}
+// AbsoluteOrientationParametersEstimator.cxx:134-205 (Horn): M = sum p1 p2^T - N mu1 mu2^T, 4x4 N matrix,
+// eigenvector of the largest eigenvalue, t = mu2 - R mu1 with the normalised quaternion.
+__device__ int solve_absor(const double* m, const double* c, double* out) {
+  const double n = m[0];
+  if (n < 3.0) return 0;
+  double mu1[3], mu2[3], Mm[9], Nm[16], V[16], ev[4], R[9];
+  for (int j = 0; j < 3; j++) { mu1[j] = m[1 + j] / n; mu2[j] = m[4 + j] / n; }
+  for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) Mm[r * 3 + cc] = m[7 + r * 3 + cc] - n * mu1[r] * mu2[cc];
+  const double tr = Mm[0] + Mm[4] + Mm[8];
+  const double A12 = Mm[5] - Mm[7], A20 = Mm[6] - Mm[2], A01 = Mm[1] - Mm[3];
+  for (int i = 0; i < 16; i++) Nm[i] = 0.0;
+  Nm[0] = tr; Nm[1] = A12; Nm[2] = A20; Nm[3] = A01; Nm[4] = A12; Nm[8] = A20; Nm[12] = A01;
+  for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) Nm[(r + 1) * 4 + cc + 1] = ((r == cc) ? -tr : 0.0) + (Mm[r * 3 + cc] + Mm[cc * 3 + r]);
+  sym_eig<4>(Nm, V, ev);
+  double q[4];
+  for (int r = 0; r < 4; r++) { q[r] = V[r * 4 + 3]; out[r] = q[r]; }
+  const double norm = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  quat_to_rot(q[0] / norm, q[1] / norm, q[2] / norm, q[3] / norm, R);
+  for (int r = 0; r < 3; r++) {
+    const double f = R[3 * r] * (mu1[0] + c[0]) + R[3 * r + 1] * (mu1[1] + c[1]) + R[3 * r + 2] * (mu1[2] + c[2]);
+    out[4 + r] = (mu2[r] + c[3 + r]) - f;
+  }
+  return 7;
+}
+// RayIntersectionParametersEstimator.cxx:124-143
+__device__ int solve_ray(const double* m, const double* c, double* out) {
+  const double n = m[0];
+  double A[9], x[3];
+  A[0] = n - m[1]; A[1] = -m[2]; A[2] = -m[3];
+  A[3] = A[1]; A[4] = n - m[4]; A[5] = -m[5];
+  A[6] = A[2]; A[7] = A[5]; A[8] = n - m[6];
+  if (n < 1.0 || sym_pinv_solve<3>(A, m + 7, x) < 3) return 0;
+  for (int j = 0; j < 3; j++) out[j] = x[j] + c[j];
+  return 3;
+}
+// PivotCalibrationParametersEstimator.cxx:63-96 through the 6x6 normal equations
+__device__ int solve_pivot(const double* m, const double* c, double* out) {
+  const double n = m[0];
+  if (n < 3.0) return 0;
+  double A[36], b[6], x[6];
+  int o = 1;
+  for (int a = 0; a < 3; a++) for (int bb = a; bb < 3; bb++) { const double v = m[o++]; A[a * 6 + bb] = v; A[bb * 6 + a] = v; }
+  const double* SR = m + 7;  // sum R, row-major
+  for (int a = 0; a < 3; a++) for (int bb = 0; bb < 3; bb++) {
+    A[a * 6 + 3 + bb] = -SR[bb * 3 + a];  // -(sum R)^T
+    A[(3 + bb) * 6 + a] = -SR[bb * 3 + a];
+    A[(3 + a) * 6 + 3 + bb] = (a == bb) ? n : 0.0;
+  }
+  for (int a = 0; a < 3; a++) { b[a] = -m[16 + a]; b[3 + a] = m[19 + a]; }
+  if (sym_pinv_solve<6>(A, b, x) < 6) return 0;
+  for (int j = 0; j < 3; j++) { out[j] = x[j]; out[3 + j] = x[3 + j] + c[9 + j]; }
+  return 6;
+}
+
+// out[0] = number of parameters (0 = the reference's empty vector), out[1..] = parameters.
+// For CIRCLE2/SPHERE3 the parameters stay in centred coordinates when keep_centred != 0 (LM start).
+__global__ void solve_moments_kernel(int model, DataView dv, const double* __restrict__ m, int keep_centred, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double p[8];
+  int np = 0;
+  const double* c = dv.center;
+  switch (model) {
+    case PLANE3: np = solve_scatter<3>(m, c, 0, p); break;
+    case LINE3: np = solve_scatter<3>(m, c, 2, p); break;
+    case LINE2: np = solve_scatter<2>(m, c, 1, p); break;
+    case LINE2D: np = solve_line2d(m, c, p); break;
+    case CIRCLE2: np = solve_sphere_alg<2>(m, p); if (np && !keep_centred) { p[0] += c[0]; p[1] += c[1]; } break;
+    case SPHERE3: np = solve_sphere_alg<3>(m, p); if (np && !keep_centred) { p[0] += c[0]; p[1] += c[1]; p[2] += c[2]; } break;
+    case ABSOR: np = solve_absor(m, c, p); break;
+    case RAY: np = solve_ray(m, c, p); break;
+    case PIVOT: np = solve_pivot(m, c, p); break;
+  }
+  out[0] = (double)np;
+  for (int j = 0; j < np; j++) out[1 + j] = p[j];
+}
+void launch_solve_moments(int model, const DataView& dv, const double* moments, int keep_centred, double* out_dev, cudaStream_t s) {
+  solve_moments_kernel<<<1, 32, 0, s>>>(model, dv, moments, keep_centred, out_dev);
+}
+
+// ---------------------------------------------------------------------------------------
+// Levenberg-Marquardt controller (SphereParametersEstimator.hxx:310-338: xtol = gtol = 1e-15,
+// ftol = VNL default 1e-10, at most 500 function evaluations, result only if converged).
+// state: [0..3] x, [4] cost, [5] lambda, [6] nu, [7] status (0 run, 1 converged, 2 failed),
+//        [8] evals, [9] phase (0 = evaluate x, 1 = evaluate trial), [10..13] trial,
+//        [14..29] A = J^T J at x, [30..33] g = J^T r at x, [34] pred, [35] |h|^2, [36] |x|^2
+// ---------------------------------------------------------------------------------------
+template <int NP> __device__ bool chol_solve(const double* Ain, const double* b, double* x) {
+  double M[NP * NP];
+  for (int i = 0; i < NP * NP; i++) M[i] = Ain[i];
+  for (int j = 0; j < NP; j++) {
+    double s = M[j * NP + j];
+    for (int k = 0; k < j; k++) s -= M[j * NP + k] * M[j * NP + k];
+    if (!(s > 0)) return false;
+    M[j * NP + j] = sqrt(s);
+    for (int i = j + 1; i < NP; i++) { double t = M[i * NP + j]; for (int k = 0; k < j; k++) t -= M[i * NP + k] * M[j * NP + k]; M[i * NP + j] = t / M[j * NP + j]; }
+  }
+  for (int i = 0; i < NP; i++) { double t = b[i]; for (int k = 0; k < i; k++) t -= M[i * NP + k] * x[k]; x[i] = t / M[i * NP + i]; }
+  for (int i = NP - 1; i >= 0; i--) { double t = x[i]; for (int k = i + 1; k < NP; k++) t -= M[k * NP + i] * x[k]; x[i] = t / M[i * NP + i]; }
+  return true;
+}
+
+template <int NP> __device__ void lm_load_normal(const double* m, double* A, double* g, double* cost) {
+  int o = 1;
+  for (int a = 0; a < NP; a++) for (int b = a; b < NP; b++) { const double v = m[o++]; A[a * 4 + b] = v; A[b * 4 + a] = v; }
+  for (int a = 0; a < NP; a++) g[a] = m[o++];
+  *cost = m[o];
+}
+// Computes the next trial point from (A, g, lambda); grows lambda until the damped system is SPD.
+template <int NP> __device__ void lm_make_trial(double* st) {
+  double* A = st + 14; double* g = st + 30;
+  for (int it = 0; it < 64; it++) {
+    double Mx[NP * NP], h[NP];
+    for (int a = 0; a < NP; a++) for (int b = 0; b < NP; b++) Mx[a * NP + b] = A[a * 4 + b] + (a == b ? st[5] : 0.0);
+    if (chol_solve<NP>(Mx, g, h)) {
+      double hn = 0, xn = 0, pred = 0;
+      for (int a = 0; a < NP; a++) { h[a] = -h[a]; st[10 + a] = st[a] + h[a]; hn += h[a] * h[a]; xn += st[a] * st[a]; pred += h[a] * (st[5] * h[a] - g[a]); }
+      st[34] = pred; st[35] = hn; st[36] = xn;
+      st[9] = 1.0;
+      return;
+    }
+    st[5] *= st[6]; st[6] *= 2;
+  }
+  st[7] = 2.0;
+}
+template <int NP> __device__ bool lm_gradient_converged(const double* st) {
+  const double gtol = 10e-16;
+  const double* A = st + 14; const double* g = st + 30;
+  const double fnorm = sqrt(st[4]);
+  double gmax = 0;
+  for (int a = 0; a < NP; a++) { const double cn = sqrt(A[a * 4 + a]); if (cn > 0 && fnorm > 0) { const double v = fabs(g[a]) / (cn * fnorm); if (v > gmax) gmax = v; } }
+  return gmax <= gtol || st[4] == 0.0;
+}
+template <int NP> __device__ void lm_update(const double* m, double* st) {
+  const double xtol = 10e-16, ftol = 1e-8 * 0.01;
+  const int maxfev = 500;
+  if (st[7] != 0.0) return;
+  if (st[9] == 0.0) {  // first evaluation at x
+    lm_load_normal<NP>(m, st + 14, st + 30, st + 4);
+    st[8] = 1.0;
+    if (lm_gradient_converged<NP>(st)) { st[7] = 1.0; return; }
+    double dmax = 0;
+    for (int a = 0; a < NP; a++) if (st[14 + a * 4 + a] > dmax) dmax = st[14 + a * 4 + a];
+    st[5] = 1e-3 * dmax; st[6] = 2.0;
+    lm_make_trial<NP>(st);
+    return;
+  }
+  double An[16], gn[4], cnew;
+  lm_load_normal<NP>(m, An, gn, &cnew);
+  st[8] += 1.0;
+  const double cost = st[4], pred = st[34], hn = st[35], xn = st[36];
+  const double actred = cost - cnew;
+  if (pred > 0 && actred > 0) {
+    const double rho = actred / pred, t = 2 * rho - 1, f = 1 - t * t * t;
+    const bool fconv = actred <= ftol * cost && pred <= ftol * cost;
+    for (int a = 0; a < NP; a++) st[a] = st[10 + a];
+    for (int i = 0; i < 16; i++) st[14 + i] = An[i];
+    for (int i = 0; i < 4; i++) st[30 + i] = gn[i];
+    st[5] *= (f > 1.0 / 3.0 ? f : 1.0 / 3.0); st[6] = 2.0;
+    st[4] = cnew;
+    if (fconv || sqrt(hn) <= xtol * sqrt(xn)) { st[7] = 1.0; return; }
+    if (lm_gradient_converged<NP>(st)) { st[7] = 1.0; return; }
+  } else {
+    if (sqrt(hn) <= xtol * sqrt(xn)) { st[7] = 1.0; return; }
+    if (fabs(actred) <= ftol * cost && pred <= ftol * cost) { st[7] = 1.0; return; }
+    st[5] *= st[6]; st[6] *= 2;
+  }
+  if (st[8] >= (double)maxfev) { st[7] = 2.0; return; }
+  lm_make_trial<NP>(st);
+}
+
+__global__ void lm_init_kernel(const double* __restrict__ alg_out, double* __restrict__ st) {
+  if (threadIdx.x != 0) return;
+  for (int i = 0; i < 64; i++) st[i] = 0.0;
+  const int np = (int)alg_out[0];
+  if (np == 0) { st[7] = 2.0; return; }
+  for (int j = 0; j < np; j++) st[j] = alg_out[1 + j];
+}
+__global__ void lm_update_kernel(int model, const double* __restrict__ m, double* __restrict__ st) {
+  if (threadIdx.x != 0) return;
+  if (model == CIRCLE2) lm_update<3>(m, st); else lm_update<4>(m, st);
+}
+__global__ void lm_finish_kernel(int model, DataView dv, const double* __restrict__ st, double* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  const int dim = (model == CIRCLE2) ? 2 : 3;
+  if (st[7] != 1.0) { out[0] = 0.0; return; }
+  out[0] = dim + 1;
+  for (int j = 0; j < dim; j++) out[1 + j] = st[j] + dv.center[j];
+  out[1 + dim] = st[dim];
+}
+void launch_lm_init(const double* alg_out_dev, double* state, cudaStream_t s) { lm_init_kernel<<<1, 32, 0, s>>>(alg_out_dev, state); }
+void launch_lm_update(int model, const double* moments, double* state, cudaStream_t s) { lm_update_kernel<<<1, 32, 0, s>>>(model, moments, state); }
+void launch_lm_finish(int model, const DataView& dv, const double* state, double* out_dev, cudaStream_t s) { lm_finish_kernel<<<1, 32, 0, s>>>(model, dv, state, out_dev); }
+
+// ---------------------------------------------------------------------------------------
+__global__ void expand_mask_kernel(const uint32_t* __restrict__ bits, uint32_t n, uint8_t* __restrict__ bytes) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) bytes[i] = (bits[i >> 5] >> (i & 31)) & 1u;
+}
+void launch_expand_mask(const uint32_t* bits, uint32_t n, uint8_t* bytes, cudaStream_t s) {
+  if (n) expand_mask_kernel<<<(n + 255) / 256, 256, 0, s>>>(bits, n, bytes);
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Batched small problems: one thread block per problem (BASELINE.json config 5; in the
+// reference this is a host loop of RANSAC<T,S>::compute calls).  Everything -- subset
+// generation, minimal solve, consensus, arg-max, consensus set, least-squares refine -- happens
+// inside the block with the problem's points resident in shared memory, in fp64 reference
+// arithmetic.  Exhaustive mode enumerates all C(n,k) subsets (RANSAC.hxx:150-249); otherwise
+// rounds of blockDim.x Philox hypotheses with the stop rule of RANSAC.hxx:107-110 between rounds.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, unsigned long long* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  unsigned long long r = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) r = sh[w] > r ? sh[w] : r;
+  return r;
+}
+
+template <int M>
+__device__ void block_moments(const double* pts, uint32_t n, uint32_t ldp, const double* hq, const EstCfg& cfg, const double* lmx, bool lm,
+                              int use_mask, uint8_t* mask_out, double* sh_part, double* sh_mom) {
+  constexpr int D = Model<M>::D;
+  constexpr int NMA = Mom<M>::N, NML = Mom<M>::NLM;
+  double acc[kMaxMoments];
+  const int nm = lm ? NML : NMA;
+  for (int j = 0; j < kMaxMoments; j++) acc[j] = 0.0;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    double x[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) x[d] = pts[d * ldp + i];
+    const bool in = use_mask ? agree<M>(hq, x, cfg) : true;
+    if (mask_out) mask_out[i] = in ? 1 : 0;
+    if (in) {
+      if (lm) {
+        if constexpr (M == CIRCLE2) acc_sphere_lm<2>(x, lmx, acc);
+        if constexpr (M == SPHERE3) acc_sphere_lm<3>(x, lmx, acc);
+      } else accumulate<M>(x, acc);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  for (int j = 0; j < nm; j++) {
+    double v = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh_part[warp * kMaxMoments + j] = v;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nm) { double v = 0; for (int w = 0; w < nw; w++) v += sh_part[w * kMaxMoments + threadIdx.x]; sh_mom[threadIdx.x] = v; }
+  __syncthreads();
+}
+
+template <int M>
+__global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int ls_type) {
+  constexpr int D = Model<M>::D, P = Model<M>::P, K = Model<M>::K, HQ = Model<M>::HQ;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* pts = reinterpret_cast<double*>(smem_raw);  // [D][ldp]
+  const uint32_t ldp = a.max_n;
+  __shared__ unsigned long long sh_key[8];
+  __shared__ double sh_part[8 * kMaxMoments];
+  __shared__ double sh_mom[kMaxMoments];
+  __shared__ double sh_prm[16];
+  __shared__ double sh_state[64];
+  __shared__ unsigned long long sh_best;
+  __shared__ unsigned long long sh_tries;
+  __shared__ int sh_ok;
+
+  const uint32_t b = blockIdx.x;
+  const uint64_t off = a.offsets[b];
+  const uint32_t n = (uint32_t)(a.offsets[b + 1] - off);
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  for (uint32_t i = threadIdx.x; i < n * D; i += blockDim.x) pts[(i % D) * ldp + (i / D)] = a.data[off * D + i];
+  if (threadIdx.x == 0) {
+    sh_best = 0ull;
+    unsigned long long all = 0xFFFFFFFFull;  // RANSAC::choose saturates at UINT_MAX (RANSAC.hxx:254-280)
+    if (n >= (uint32_t)K) { const uint64_t c = binom(n, K); all = c < all ? c : all; } else all = 0;
+    sh_tries = a.exhaustive ? all : (all < a.tries ? all : (unsigned long long)a.tries);
+  }
+  __syncthreads();
+
+  unsigned long long best = 0ull;
+  const double log1mp = log(1.0 - a.prob);
+  for (unsigned long long done = 0; done < sh_tries; done += blockDim.x) {
+    const unsigned long long h = done + threadIdx.x;
+    unsigned long long key = 0ull;
+    if (h < sh_tries) {
+      int32_t sub[K];
+      if (a.exhaustive) unrank_lex<K>(h, n, sub); else sample_subset<K>(((uint64_t)b << 32) | h, a.seed, n, sub);
+      double sp[K * D], prm[P], hq[HQ];
+#pragma unroll
+      for (int j = 0; j < K; j++)
+#pragma unroll
+        for (int d = 0; d < D; d++) sp[j * D + d] = pts[d * ldp + sub[j]];
+      if (estimate<M>(sp, cfg, prm)) {
+        prepare<M>(prm, hq);
+        uint32_t c = 0;
+        for (uint32_t i = 0; i < n; i++) {
+          double x[D];
+#pragma unroll
+          for (int d = 0; d < D; d++) x[d] = pts[d * ldp + i];
+          c += agree<M>(hq, x, cfg) ? 1u : 0u;
+        }
+        key = ((unsigned long long)c << 32) | (0xFFFFFFFFull - h);
+      }
+    }
+    const unsigned long long round_best = block_max_u64(key, sh_key);
+    if (round_best > best) {
+      best = round_best;
+      if (!a.exhaustive && threadIdx.x == 0) {  // stop rule, RANSAC.hxx:104-110
+        const uint32_t c = (uint32_t)(best >> 32);
+        unsigned long long cap = sh_tries;
+        if (c == n) cap = 0;
+        else if (a.prob > 0.0 && a.prob < 1.0) {
+          const double den = log(1.0 - pow((double)c / (double)n, (double)K));
+          const double t = log1mp / den + 0.5;
+          const unsigned long long nt = t >= 4294967295.0 ? 0xFFFFFFFFull : (unsigned long long)(long long)t;
+          cap = nt < cap ? nt : cap;
+        }
+        sh_tries = cap;
+      }
+    }
+    __syncthreads();
+  }
+
+  // winner -> consensus set -> least squares (RANSAC.hxx:129-138)
+  const uint32_t best_count = (uint32_t)(best >> 32);
+  if (threadIdx.x == 0) {
+    sh_ok = 0;
+    if (best_count > 0) {
+      const unsigned long long h = 0xFFFFFFFFull - (best & 0xFFFFFFFFull);
+      int32_t sub[K];
+      if (a.exhaustive) unrank_lex<K>(h, n, sub); else sample_subset<K>(((uint64_t)b << 32) | h, a.seed, n, sub);
+      double sp[K * D], prm[P];
+      for (int j = 0; j < K; j++) for (int d = 0; d < D; d++) sp[j * D + d] = pts[d * ldp + sub[j]];
+      if (estimate<M>(sp, cfg, prm)) { prepare<M>(prm, sh_prm); sh_ok = 1; }
+    }
+  }
+  __syncthreads();
+  uint8_t* mask_out = a.out_masks ? a.out_masks + off : nullptr;
+  if (threadIdx.x == 0) a.out_counts[b] = best_count;
+  if (!sh_ok) {
+    for (uint32_t i = threadIdx.x; i < (uint32_t)P; i += blockDim.x) a.out_params[(size_t)b * P + i] = nan;
+    if (mask_out) for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) mask_out[i] = 0;
+    return;
+  }
+  double hq[HQ];
+#pragma unroll
+  for (int j = 0; j < HQ; j++) hq[j] = sh_prm[j];
+  block_moments<M>(pts, n, ldp, hq, cfg, nullptr, false, 1, mask_out, sh_part, sh_mom);
+  DataView zero;
+  for (int j = 0; j < 12; j++) zero.center[j] = 0.0;
+  __shared__ double sh_out[12];
+  if (threadIdx.x == 0) {
+    double p[8];
+    int np = 0;
+    const double* m = sh_mom;
+    const double* c = zero.center;
+    switch (M) {
+      case PLANE3: np = solve_scatter<3>(m, c, 0, p); break;
+      case LINE3: np = solve_scatter<3>(m, c, 2, p); break;
+      case LINE2: np = solve_scatter<2>(m, c, 1, p); break;
+      case LINE2D: np = solve_line2d(m, c, p); break;
+      case CIRCLE2: np = solve_sphere_alg<2>(m, p); break;
+      case SPHERE3: np = solve_sphere_alg<3>(m, p); break;
+      case ABSOR: np = solve_absor(m, c, p); break;
+      case RAY: np = solve_ray(m, c, p); break;
+      case PIVOT: np = solve_pivot(m, c, p); break;
+    }
+    sh_out[0] = np;
+    for (int j = 0; j < np; j++) sh_out[1 + j] = p[j];
+  }
+  __syncthreads();
+  if constexpr (M == CIRCLE2 || M == SPHERE3) {
+    if (ls_type == 1) {  // geometric: Levenberg-Marquardt from the algebraic fit
+      if (threadIdx.x == 0) {
+        for (int i = 0; i < 64; i++) sh_state[i] = 0.0;
+        const int np = (int)sh_out[0];
+        if (np == 0) sh_state[7] = 2.0;
+        for (int j = 0; j < np; j++) sh_state[j] = sh_out[1 + j];
+      }
+      __syncthreads();
+      while (sh_state[7] == 0.0) {
+        double lmx[4];
+        const int o = (sh_state[9] != 0.0) ? 10 : 0;
+        for (int j = 0; j < 4; j++) lmx[j] = sh_state[o + j];
+        block_moments<M>(pts, n, ldp, hq, cfg, lmx, true, 1, nullptr, sh_part, sh_mom);
+        if (threadIdx.x == 0) { if (M == CIRCLE2) lm_update<3>(sh_mom, sh_state); else lm_update<4>(sh_mom, sh_state); }
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) {
+        if (sh_state[7] != 1.0) sh_out[0] = 0.0;
+        else for (int j = 0; j < P; j++) sh_out[1 + j] = sh_state[j];
+      }
+      __syncthreads();
+    }
+  }
+  const int np = (int)sh_out[0];
+  for (uint32_t i = threadIdx.x; i < (uint32_t)P; i += blockDim.x) a.out_params[(size_t)b * P + i] = np ? sh_out[1 + i] : nan;
+}
+
+int launch_batch(const BatchArgs& a, const EstCfg& cfg, int ls_type, cudaStream_t s) {
+  if (a.n_problems == 0) return 0;
+  const int D = model_info(a.model).D;
+  const size_t smem = (size_t)D * a.max_n * sizeof(double);
+  if (smem > 200 * 1024) return -1;
+#define CALL(MM)                                                                                                    {                                                                                                                   auto kern = batch_kernel<MM>;                                                                                     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                              kern<<<a.n_problems, 256, smem, s>>>(a, cfg, ls_type);                                                          }
+  switch (a.model) {
+    case PLANE3: CALL(PLANE3) break;
+    case LINE2D: CALL(LINE2D) break;
+    case LINE2: CALL(LINE2) break;
+    case LINE3: CALL(LINE3) break;
+    case CIRCLE2: CALL(CIRCLE2) break;
+    case SPHERE3: CALL(SPHERE3) break;
+    case ABSOR: CALL(ABSOR) break;
+    case RAY: CALL(RAY) break;
+    case PIVOT: CALL(PIVOT) break;
+    default: return -1;
+  }
+#undef CALL
+  return 1;
+}
+
+}  // namespace lsqr

@@ -1,0 +1,510 @@
+// Scoring path: ingest -> (sample + minimal solve) -> hoist -> consensus -> arg-max.
+//
+// The consensus kernel is the hot path (RANSAC.hxx:94-99 / :239-244 in the reference: N virtual
+// agree() calls per hypothesis).  Layout of the work:
+//   * grid.x = blocks of THREADS*R hypotheses, grid.y = chunks of the point set.  Each thread
+//     keeps R prepared hypotheses in registers for the whole kernel.
+//   * The point chunk is streamed through shared memory in SoA tiles of TILE points, staged by
+//     TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) in a 2-deep ring, one copy per
+//     component per tile, issued by one elected thread.
+//   * Inside a tile every thread reads the same point (shared-memory broadcast, vector loads of
+//     UNR consecutive points) and evaluates agree() for its R hypotheses.
+//   * Per-hypothesis counts go to global memory with one atomicAdd per (hypothesis, chunk).
+// fp64 mode evaluates models.cuh's reference-order agree(); fp32 mode evaluates the fused,
+// constant-hoisted forms below (fmaf explicit; the TU is built with -fmad=false).
+// Tensor cores are deliberately unused: the contraction depth is <= 4 (BASELINE.json north_star).
+#include "engine.h"
+
+#include <cstdio>
+
+namespace lsqr {
+
+// ---------------------------------------------------------------------------------------
+// mbarrier / TMA-bulk helpers (sm_90+ PTX; SASS: SYNCS / UBLKCP)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// Ingest
+// ---------------------------------------------------------------------------------------
+__global__ void ingest_kernel(int D, const unsigned char* __restrict__ aos, size_t stride, uint32_t n, double* __restrict__ soa, size_t ld) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ld) return;
+  if (i < n) {
+    const double* rec = reinterpret_cast<const double*>(aos + i * stride);
+    for (int d = 0; d < D; d++) soa[(size_t)d * ld + i] = rec[d];
+  } else {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int d = 0; d < D; d++) soa[(size_t)d * ld + i] = nan;
+  }
+}
+void launch_ingest(int D, const unsigned char* aos, size_t stride, uint32_t n, double* soa64, size_t ld, cudaStream_t s) {
+  ingest_kernel<<<(unsigned)((ld + 255) / 256), 256, 0, s>>>(D, aos, stride, n, soa64, ld);
+}
+
+// Which components are positions (get centred) for each model; directions / rotations are not.
+__host__ __device__ inline bool centred_component(int model, int d) {
+  switch (model) {
+    case RAY: return d < 3;
+    case PIVOT: return d >= 9;
+    default: return true;
+  }
+}
+
+constexpr int kCenterBlocks = 256;
+__global__ void center_partial_kernel(int D, const double* __restrict__ soa, size_t ld, uint32_t n, double* __restrict__ partials) {
+  __shared__ double sh[256];
+  for (int d = 0; d < D; d++) {
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc += soa[(size_t)d * ld + i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) partials[(size_t)blockIdx.x * 12 + d] = sh[0];
+    __syncthreads();
+  }
+}
+__global__ void center_final_kernel(int model, int D, uint32_t n, const double* __restrict__ partials, double* __restrict__ center) {
+  const int d = threadIdx.x;
+  if (d >= 12) return;
+  double acc = 0.0;
+  if (d < D && centred_component(model, d)) {
+    for (int b = 0; b < kCenterBlocks; b++) acc += partials[(size_t)b * 12 + d];
+    acc = (n > 0) ? acc / (double)n : 0.0;
+    if (!(acc == acc) || fabs(acc) > 1e300) acc = 0.0;
+  }
+  center[d] = acc;
+}
+void launch_center(int model, const double* soa64, size_t ld, uint32_t n, double* partials, double* center_dev, cudaStream_t s) {
+  const int D = model_info(model).D;
+  center_partial_kernel<<<kCenterBlocks, 256, 0, s>>>(D, soa64, ld, n, partials);
+  center_final_kernel<<<1, 32, 0, s>>>(model, D, n, partials, center_dev);
+}
+__global__ void make32_kernel(int D, const double* __restrict__ soa64, const double* __restrict__ center, float* __restrict__ soa32, size_t ld) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ld) return;
+  for (int d = 0; d < D; d++) soa32[(size_t)d * ld + i] = (float)(soa64[(size_t)d * ld + i] - center[d]);
+}
+void launch_make32(int D, const double* soa64, const double* center_dev, float* soa32, size_t ld, cudaStream_t s) {
+  make32_kernel<<<(unsigned)((ld + 255) / 256), 256, 0, s>>>(D, soa64, center_dev, soa32, ld);
+}
+
+// ---------------------------------------------------------------------------------------
+// Sample + minimal solve: one hypothesis per thread
+// ---------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(128) solve_kernel(SolveArgs a, const double* __restrict__ soa, size_t ld, uint32_t n, EstCfg cfg) {
+  constexpr int D = Model<M>::D, P = Model<M>::P, K = Model<M>::K;
+  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= a.H) return;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  double prm[P];
+  bool ok;
+  int32_t sub[K];
+  if (a.sampler == 3) {  // LSQR_SAMPLE_PARAMS
+#pragma unroll
+    for (int j = 0; j < P; j++) prm[j] = a.params_in[(size_t)h * P + j];
+    ok = (prm[0] == prm[0]);
+#pragma unroll
+    for (int j = 0; j < K; j++) sub[j] = -1;
+  } else {
+    const uint64_t g = a.first + h;
+    if (a.sampler == 0) sample_subset<K>(g, a.seed, n, sub);
+    else if (a.sampler == 1) unrank_lex<K>(g, n, sub);
+    else {
+#pragma unroll
+      for (int j = 0; j < K; j++) sub[j] = a.list[(size_t)h * K + j];
+    }
+    double pts[K * D];
+    bool in_range = true;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      in_range = in_range && sub[j] >= 0 && (uint32_t)sub[j] < n;
+      const size_t idx = in_range ? (size_t)sub[j] : 0;
+#pragma unroll
+      for (int d = 0; d < D; d++) pts[j * D + d] = soa[(size_t)d * ld + idx];
+    }
+    ok = in_range && estimate<M>(pts, cfg, prm);
+  }
+#pragma unroll
+  for (int j = 0; j < K; j++) a.subsets[(size_t)j * a.hld + h] = sub[j];
+#pragma unroll
+  for (int j = 0; j < P; j++) a.hyp64[(size_t)j * a.hld + h] = ok ? prm[j] : nan;
+  const unsigned ballot = __ballot_sync(__activemask(), ok);
+  if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1) && ballot) atomicAdd(a.n_valid, __popc(ballot));
+}
+
+#define LSQR_DISPATCH_MODEL(model, CALL)      \
+  switch (model) {                            \
+    case PLANE3: { CALL(PLANE3); break; }     \
+    case LINE2D: { CALL(LINE2D); break; }     \
+    case LINE2: { CALL(LINE2); break; }       \
+    case LINE3: { CALL(LINE3); break; }       \
+    case CIRCLE2: { CALL(CIRCLE2); break; }   \
+    case SPHERE3: { CALL(SPHERE3); break; }   \
+    case ABSOR: { CALL(ABSOR); break; }       \
+    case RAY: { CALL(RAY); break; }           \
+    case PIVOT: { CALL(PIVOT); break; }       \
+    default: break;                           \
+  }
+
+void launch_solve(const SolveArgs& a, const DataView& dv, const EstCfg& cfg, cudaStream_t s) {
+  if (a.H == 0) return;
+  const unsigned blocks = (a.H + 127) / 128;
+#define CALL(MM) solve_kernel<MM><<<blocks, 128, 0, s>>>(a, dv.soa64, dv.ld, dv.n, cfg)
+  LSQR_DISPATCH_MODEL(a.model, CALL)
+#undef CALL
+}
+
+// ---------------------------------------------------------------------------------------
+// fp32 fast forms.  A hoisted hypothesis is Q32 floats computed once in fp64 from the raw
+// parameters and the data centre c (positions are stored as x - c in fp32):
+//   PLANE3   (nx,ny,nz, -n.(a-c))             |fma chain| < delta            3 FFMA
+//   LINE2D   (nx,ny, -n.(a-c))                                                2 FFMA
+//   LINE2/3  (dir, a-c)                       |v - (v.n)n|^2 < delta^2
+//   CIRCLE/SPHERE (ctr-c, m, w)               | |x-ctr|^2 - m | < w  with m = r^2+delta^2, w = 2 r delta
+//                                             (sqrt-free two-sided test of |d - r| < delta)
+//   ABSOR    (R[9], R c1 + t - c2)            |R x1 + t' - x2|^2 < delta^2
+//   RAY      (x - c)                          t >= 0 && |x - p - t n|^2 < delta^2
+//   PIVOT    (tDRF, tW - c)                   |R tDRF + t - tW|^2 < delta^2
+// ---------------------------------------------------------------------------------------
+template <int M> __device__ __forceinline__ void hoist32(const double* prm, const double* c, const EstCfg& cfg, float* q);
+template <> __device__ __forceinline__ void hoist32<PLANE3>(const double* p, const double* c, const EstCfg&, float* q) {
+  q[0] = (float)p[0]; q[1] = (float)p[1]; q[2] = (float)p[2];
+  q[3] = (float)(-(p[0] * (p[3] - c[0]) + p[1] * (p[4] - c[1]) + p[2] * (p[5] - c[2])));
+}
+template <> __device__ __forceinline__ void hoist32<LINE2D>(const double* p, const double* c, const EstCfg&, float* q) {
+  q[0] = (float)p[0]; q[1] = (float)p[1];
+  q[2] = (float)(-(p[0] * (p[2] - c[0]) + p[1] * (p[3] - c[1])));
+}
+template <> __device__ __forceinline__ void hoist32<LINE2>(const double* p, const double* c, const EstCfg&, float* q) {
+  q[0] = (float)p[0]; q[1] = (float)p[1]; q[2] = (float)(p[2] - c[0]); q[3] = (float)(p[3] - c[1]);
+}
+template <> __device__ __forceinline__ void hoist32<LINE3>(const double* p, const double* c, const EstCfg&, float* q) {
+  for (int i = 0; i < 3; i++) { q[i] = (float)p[i]; q[3 + i] = (float)(p[3 + i] - c[i]); }
+}
+template <int DIM> __device__ __forceinline__ void hoist_sphere(const double* p, const double* c, const EstCfg& cfg, float* q) {
+  for (int i = 0; i < DIM; i++) q[i] = (float)(p[i] - c[i]);
+  const double r = p[DIM], dl = cfg.delta;
+  double m, w;
+  if (r >= dl) { m = r * r + dl * dl; w = 2.0 * r * dl; }
+  else { const double hi = (r + dl) * (r + dl); m = (hi - 1.0) * 0.5; w = (hi + 1.0) * 0.5; }  // interval (-1, hi): no lower bound on d^2 >= 0
+  q[DIM] = (float)m; q[DIM + 1] = (float)w;
+}
+template <> __device__ __forceinline__ void hoist32<CIRCLE2>(const double* p, const double* c, const EstCfg& cfg, float* q) { hoist_sphere<2>(p, c, cfg, q); }
+template <> __device__ __forceinline__ void hoist32<SPHERE3>(const double* p, const double* c, const EstCfg& cfg, float* q) { hoist_sphere<3>(p, c, cfg, q); }
+template <> __device__ __forceinline__ void hoist32<ABSOR>(const double* p, const double* c, const EstCfg&, float* q) {
+  double R[9];
+  quat_to_rot(p[0], p[1], p[2], p[3], R);
+  for (int i = 0; i < 9; i++) q[i] = (float)R[i];
+  for (int i = 0; i < 3; i++) q[9 + i] = (float)(R[3 * i] * c[0] + R[3 * i + 1] * c[1] + R[3 * i + 2] * c[2] + p[4 + i] - c[3 + i]);
+}
+template <> __device__ __forceinline__ void hoist32<RAY>(const double* p, const double* c, const EstCfg&, float* q) {
+  for (int i = 0; i < 3; i++) q[i] = (float)(p[i] - c[i]);
+}
+template <> __device__ __forceinline__ void hoist32<PIVOT>(const double* p, const double* c, const EstCfg&, float* q) {
+  for (int i = 0; i < 3; i++) { q[i] = (float)p[i]; q[3 + i] = (float)(p[3 + i] - c[9 + i]); }
+}
+
+template <int M>
+__global__ void hoist32_kernel(const double* __restrict__ hyp64, size_t hld, uint32_t H, DataView dv, EstCfg cfg, float* __restrict__ hyp32) {
+  constexpr int P = Model<M>::P, Q = Model<M>::Q32;
+  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  double prm[P], c[12];
+  float q[Q];
+#pragma unroll
+  for (int j = 0; j < P; j++) prm[j] = hyp64[(size_t)j * hld + h];
+#pragma unroll
+  for (int j = 0; j < 12; j++) c[j] = dv.center[j];
+  hoist32<M>(prm, c, cfg, q);
+  const bool ok = prm[0] == prm[0];
+#pragma unroll
+  for (int j = 0; j < Q; j++) hyp32[(size_t)j * hld + h] = ok ? q[j] : __int_as_float(0x7fc00000);
+}
+void launch_hoist32(int model, const double* hyp64, size_t hld, uint32_t H, const DataView& dv, const EstCfg& cfg, float* hyp32, cudaStream_t s) {
+  if (H == 0) return;
+  const unsigned blocks = (H + 255) / 256;
+#define CALL(MM) hoist32_kernel<MM><<<blocks, 256, 0, s>>>(hyp64, hld, H, dv, cfg, hyp32)
+  LSQR_DISPATCH_MODEL(model, CALL)
+#undef CALL
+}
+
+// fp32 thresholds handed to the kernel
+struct Thr32 { float delta, delta2; };
+
+template <int M> __device__ __forceinline__ bool agree32(const float* q, const float* x, const Thr32& t);
+template <> __device__ __forceinline__ bool agree32<PLANE3>(const float* q, const float* x, const Thr32& t) {
+  const float s = fmaf(q[0], x[0], fmaf(q[1], x[1], fmaf(q[2], x[2], q[3])));
+  return fabsf(s) < t.delta;
+}
+template <> __device__ __forceinline__ bool agree32<LINE2D>(const float* q, const float* x, const Thr32& t) {
+  const float s = fmaf(q[0], x[0], fmaf(q[1], x[1], q[2]));
+  return fabsf(s) < t.delta;
+}
+template <int DIM> __device__ __forceinline__ bool agree32_line(const float* q, const float* x, const Thr32& t) {
+  float v[DIM], vn = 0.f, ds = 0.f;
+#pragma unroll
+  for (int i = 0; i < DIM; i++) { v[i] = x[i] - q[DIM + i]; vn = fmaf(v[i], q[i], vn); }
+#pragma unroll
+  for (int i = 0; i < DIM; i++) { const float w = fmaf(-vn, q[i], v[i]); ds = fmaf(w, w, ds); }
+  return ds < t.delta2;
+}
+template <> __device__ __forceinline__ bool agree32<LINE2>(const float* q, const float* x, const Thr32& t) { return agree32_line<2>(q, x, t); }
+template <> __device__ __forceinline__ bool agree32<LINE3>(const float* q, const float* x, const Thr32& t) { return agree32_line<3>(q, x, t); }
+template <int DIM> __device__ __forceinline__ bool agree32_sphere(const float* q, const float* x, const Thr32&) {
+  float d2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < DIM; i++) { const float w = x[i] - q[i]; d2 = fmaf(w, w, d2); }
+  return fabsf(d2 - q[DIM]) < q[DIM + 1];
+}
+template <> __device__ __forceinline__ bool agree32<CIRCLE2>(const float* q, const float* x, const Thr32& t) { return agree32_sphere<2>(q, x, t); }
+template <> __device__ __forceinline__ bool agree32<SPHERE3>(const float* q, const float* x, const Thr32& t) { return agree32_sphere<3>(q, x, t); }
+template <> __device__ __forceinline__ bool agree32<ABSOR>(const float* q, const float* x, const Thr32& t) {
+  const float dx = fmaf(q[0], x[0], fmaf(q[1], x[1], fmaf(q[2], x[2], q[9]))) - x[3];
+  const float dy = fmaf(q[3], x[0], fmaf(q[4], x[1], fmaf(q[5], x[2], q[10]))) - x[4];
+  const float dz = fmaf(q[6], x[0], fmaf(q[7], x[1], fmaf(q[8], x[2], q[11]))) - x[5];
+  return fmaf(dx, dx, fmaf(dy, dy, dz * dz)) < t.delta2;
+}
+template <> __device__ __forceinline__ bool agree32<RAY>(const float* q, const float* x, const Thr32& t) {
+  const float vx = q[0] - x[0], vy = q[1] - x[1], vz = q[2] - x[2];
+  const float tt = fmaf(x[3], vx, fmaf(x[4], vy, x[5] * vz));
+  const float dx = fmaf(-tt, x[3], vx), dy = fmaf(-tt, x[4], vy), dz = fmaf(-tt, x[5], vz);
+  return tt >= 0.f && fmaf(dx, dx, fmaf(dy, dy, dz * dz)) < t.delta2;
+}
+template <> __device__ __forceinline__ bool agree32<PIVOT>(const float* q, const float* x, const Thr32& t) {
+  const float dx = fmaf(x[0], q[0], fmaf(x[1], q[1], fmaf(x[2], q[2], x[9]))) - q[3];
+  const float dy = fmaf(x[3], q[0], fmaf(x[4], q[1], fmaf(x[5], q[2], x[10]))) - q[4];
+  const float dz = fmaf(x[6], q[0], fmaf(x[7], q[1], fmaf(x[8], q[2], x[11]))) - q[5];
+  return fmaf(dx, dx, fmaf(dy, dy, dz * dz)) < t.delta2;
+}
+
+// Traits binding the generic consensus kernel to one (model, precision).
+template <int M> struct Exact {
+  using real = double;
+  using thr_t = EstCfg;
+  static constexpr int D = Model<M>::D, NIN = Model<M>::P, HQ = Model<M>::HQ, UNR = 2;
+  __device__ static __forceinline__ void load(const double* raw, double* hq) { prepare<M>(raw, hq); }
+  __device__ static __forceinline__ bool test(const double* hq, const double* x, const EstCfg& t) { return agree<M>(hq, x, t); }
+};
+template <int M> struct Fast {
+  using real = float;
+  using thr_t = Thr32;
+  static constexpr int D = Model<M>::D, NIN = Model<M>::Q32, HQ = Model<M>::Q32, UNR = 4;
+  __device__ static __forceinline__ void load(const float* raw, float* hq) {
+#pragma unroll
+    for (int i = 0; i < HQ; i++) hq[i] = raw[i];
+  }
+  __device__ static __forceinline__ bool test(const float* hq, const float* x, const Thr32& t) { return agree32<M>(hq, x, t); }
+};
+
+template <class T, int R, int THREADS, int TILE>
+__global__ void __launch_bounds__(THREADS) consensus_kernel(const typename T::real* __restrict__ soa, size_t ld, uint32_t tiles_total, uint32_t tiles_per_chunk,
+                                                             const typename T::real* __restrict__ hyp, size_t hld, uint32_t H, typename T::thr_t thr,
+                                                             uint32_t* __restrict__ counts) {
+  using real = typename T::real;
+  constexpr int D = T::D, UNR = T::UNR;
+  constexpr uint32_t kTileBytes = (uint32_t)(TILE * sizeof(real));
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  real* tile0 = reinterpret_cast<real*>(smem_raw);
+  real* tile1 = tile0 + D * TILE;
+  __shared__ __align__(8) uint64_t bars[2];
+
+  const int tid = threadIdx.x;
+  const uint32_t hbase = blockIdx.x * (THREADS * R);
+  real hq[R][T::HQ];
+  uint32_t cnt[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const uint32_t h = hbase + r * THREADS + tid;
+    real raw[T::NIN];
+#pragma unroll
+    for (int j = 0; j < T::NIN; j++) raw[j] = (h < H) ? hyp[(size_t)j * hld + h] : (real)NAN;
+    T::load(raw, hq[r]);
+    cnt[r] = 0;
+  }
+
+  const uint32_t t0 = blockIdx.y * tiles_per_chunk;
+  const uint32_t t1 = min(t0 + tiles_per_chunk, tiles_total);
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
+  __syncthreads();
+  auto issue = [&](uint32_t t, int buf) {
+    real* dst = buf ? tile1 : tile0;
+    mbar_expect_tx(&bars[buf], kTileBytes * D);
+#pragma unroll
+    for (int d = 0; d < D; d++) tma_bulk_g2s(dst + d * TILE, soa + (size_t)d * ld + (size_t)t * TILE, kTileBytes, &bars[buf]);
+  };
+  if (tid == 0 && t0 < t1) issue(t0, 0);
+  uint32_t phase0 = 0, phase1 = 0;
+  for (uint32_t t = t0; t < t1; t++) {
+    const int buf = (t - t0) & 1;
+    if (tid == 0 && t + 1 < t1) issue(t + 1, buf ^ 1);
+    if (buf) { mbar_wait(&bars[1], phase1); phase1 ^= 1; } else { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
+    const real* tl = buf ? tile1 : tile0;
+#pragma unroll 1
+    for (int i = 0; i < TILE; i += UNR) {
+      real x[UNR][D];
+#pragma unroll
+      for (int d = 0; d < D; d++) {
+        if constexpr (sizeof(real) == 4) {
+          const float4 v = *reinterpret_cast<const float4*>(tl + d * TILE + i);
+          x[0][d] = v.x; x[1][d] = v.y; x[2][d] = v.z; x[3][d] = v.w;
+        } else {
+          const double2 v = *reinterpret_cast<const double2*>(tl + d * TILE + i);
+          x[0][d] = v.x; x[1][d] = v.y;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+#pragma unroll
+        for (int u = 0; u < UNR; u++) cnt[r] += T::test(hq[r], x[u], thr) ? 1u : 0u;
+      }
+    }
+    __syncthreads();  // everyone is done with this buffer before it is refilled
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const uint32_t h = hbase + r * THREADS + tid;
+    if (h < H && cnt[r]) atomicAdd(&counts[h], cnt[r]);
+  }
+}
+
+template <class T, int R, int THREADS, int TILE>
+static int run_consensus(const typename T::real* soa, size_t ld, const typename T::real* hyp, size_t hld, uint32_t H, const typename T::thr_t& thr,
+                         uint32_t* counts, int num_sms, cudaStream_t s) {
+  using real = typename T::real;
+  const uint32_t tiles_total = (uint32_t)(ld / TILE);
+  const uint32_t hyp_blocks = (H + THREADS * R - 1) / (THREADS * R);
+  // enough (hypothesis block x point chunk) work items for ~16 CTAs per SM, chunks not below 4 tiles
+  uint32_t want = (uint32_t)num_sms * 16;
+  uint32_t chunks = (want + hyp_blocks - 1) / hyp_blocks;
+  uint32_t max_chunks = (tiles_total + 3) / 4;
+  if (max_chunks == 0) max_chunks = 1;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks > 65535) chunks = 65535;
+  if (chunks == 0) chunks = 1;
+  const uint32_t tiles_per_chunk = (tiles_total + chunks - 1) / chunks;
+  chunks = (tiles_total + tiles_per_chunk - 1) / tiles_per_chunk;
+  const size_t smem = 2 * (size_t)T::D * TILE * sizeof(real);
+  auto kern = consensus_kernel<T, R, THREADS, TILE>;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  dim3 grid(hyp_blocks, chunks);
+  kern<<<grid, THREADS, smem, s>>>(soa, ld, tiles_total, tiles_per_chunk, hyp, hld, H, thr, counts);
+  return 1;
+}
+
+int launch_consensus(int model, int precision, const DataView& dv, const double* hyp64, const float* hyp32, size_t hld, uint32_t H,
+                     const EstCfg& cfg, uint32_t* counts, int num_sms, cudaStream_t s) {
+  if (H == 0 || dv.n == 0) return 0;
+  if (precision == 0) {
+#define CALL(MM)                                                                                                             \
+  if (H <= 4096) return run_consensus<Exact<MM>, 1, 128, 256>(dv.soa64, dv.ld, hyp64, hld, H, cfg, counts, num_sms, s);       \
+  return run_consensus<Exact<MM>, (Model<MM>::HQ >= 12 ? 2 : 4), 128, 256>(dv.soa64, dv.ld, hyp64, hld, H, cfg, counts, num_sms, s)
+    LSQR_DISPATCH_MODEL(model, CALL)
+#undef CALL
+  } else {
+    Thr32 t;
+    t.delta = (float)cfg.delta;
+    t.delta2 = (float)cfg.delta2;
+#define CALL(MM)                                                                                                             \
+  if (H <= 8192) return run_consensus<Fast<MM>, 1, 128, 512>(dv.soa32, dv.ld, hyp32, hld, H, t, counts, num_sms, s);          \
+  return run_consensus<Fast<MM>, (Model<MM>::Q32 >= 12 ? 4 : 8), 256, 512>(dv.soa32, dv.ld, hyp32, hld, H, t, counts, num_sms, s)
+    LSQR_DISPATCH_MODEL(model, CALL)
+#undef CALL
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Arg-max over a packed (count, index) key: larger count wins, ties go to the SMALLER index
+// (strict '>' of RANSAC.hxx:100 and :245 keeps the first maximum).
+// ---------------------------------------------------------------------------------------
+__global__ void argmax_kernel(const uint32_t* __restrict__ counts, uint32_t H, uint32_t index_base, unsigned long long* __restrict__ key) {
+  unsigned long long best = 0ull;
+  for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < H; h += gridDim.x * blockDim.x) {
+    const unsigned long long k = ((unsigned long long)counts[h] << 32) | (unsigned long long)(0xFFFFFFFFu - (index_base + h));
+    best = k > best ? k : best;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, best, o); best = v > best ? v : best; }
+  __shared__ unsigned long long sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    best = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0ull;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, best, o); best = v > best ? v : best; }
+    if (threadIdx.x == 0 && best) atomicMax(key, best);
+  }
+}
+void launch_argmax(const uint32_t* counts, uint32_t H, uint32_t index_base, unsigned long long* key, cudaStream_t s) {
+  if (H == 0) return;
+  unsigned blocks = (H + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  argmax_kernel<<<blocks, 256, 0, s>>>(counts, H, index_base, key);
+}
+
+
+// ---------------------------------------------------------------------------------------
+// The estimator's own estimate() / agree() for callers that use them directly
+// (ParametersEstimator.h:41-55); same device functions as the batched path.
+// ---------------------------------------------------------------------------------------
+template <int M>
+__global__ void estimate_one_kernel(const double* __restrict__ packed, EstCfg cfg, double* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  constexpr int D = Model<M>::D, P = Model<M>::P, K = Model<M>::K;
+  double pts[K * D], prm[P];
+  for (int i = 0; i < K * D; i++) pts[i] = packed[i];
+  const bool ok = estimate<M>(pts, cfg, prm);
+  out[0] = ok ? (double)P : 0.0;
+  for (int j = 0; j < P; j++) out[1 + j] = ok ? prm[j] : 0.0;
+}
+void launch_estimate_one(int model, const double* packed_dev, const EstCfg& cfg, double* out_dev, cudaStream_t s) {
+#define CALL(MM) estimate_one_kernel<MM><<<1, 32, 0, s>>>(packed_dev, cfg, out_dev)
+  LSQR_DISPATCH_MODEL(model, CALL)
+#undef CALL
+}
+template <int M>
+__global__ void agree_many_kernel(const double* __restrict__ params, const double* __restrict__ packed, uint32_t n, EstCfg cfg, uint8_t* __restrict__ out) {
+  constexpr int D = Model<M>::D, P = Model<M>::P, HQ = Model<M>::HQ;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double prm[P], hq[HQ], x[D];
+#pragma unroll
+  for (int j = 0; j < P; j++) prm[j] = params[j];
+  prepare<M>(prm, hq);
+#pragma unroll
+  for (int d = 0; d < D; d++) x[d] = packed[(size_t)i * D + d];
+  out[i] = agree<M>(hq, x, cfg) ? 1 : 0;
+}
+void launch_agree_many(int model, const double* params_dev, const double* packed_dev, uint32_t n, const EstCfg& cfg, uint8_t* out, cudaStream_t s) {
+  if (n == 0) return;
+  const unsigned blocks = (n + 255) / 256;
+#define CALL(MM) agree_many_kernel<MM><<<blocks, 256, 0, s>>>(params_dev, packed_dev, n, cfg, out)
+  LSQR_DISPATCH_MODEL(model, CALL)
+#undef CALL
+}
+
+}  // namespace lsqr

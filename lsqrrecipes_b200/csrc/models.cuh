@@ -1,0 +1,467 @@
+// Device-side estimator arithmetic in fp64 "validation" form: the reference's operation order,
+// one rounding per operation.  Every translation unit that includes this header is compiled
+// with -fmad=false so that nvcc never contracts a*b+c into an FMA; sqrt and / are IEEE
+// correctly rounded for double on sm_100a, which makes these bodies round exactly like the
+// reference built with g++ -O2 -ffp-contract=off on x86-64 (SURVEY.md section 7 "hard parts").
+//
+// Hot-path pieces are split in two so the per-hypothesis work is hoisted out of the point
+// loop without changing a single rounding: prepare<M>() runs once per hypothesis (e.g. the
+// quaternion -> rotation matrix that the reference redoes on every agree() call,
+// AbsoluteOrientationParametersEstimator.cxx:318-319), agree<M>() runs per (hypothesis, datum).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lsqr {
+
+enum : int { PLANE3 = 0, LINE2D = 1, LINE2 = 2, LINE3 = 3, CIRCLE2 = 4, SPHERE3 = 5, ABSOR = 6, RAY = 7, PIVOT = 8, NUM_MODELS = 9 };
+
+// dim = doubles per datum, P = parameters, K = minimal subset, HQ = doubles of a prepared
+// fp64 hypothesis, Q32 = floats of a hoisted fp32 hypothesis.
+template <int M> struct Model;
+template <> struct Model<PLANE3>  { static constexpr int D = 3,  P = 6, K = 3, HQ = 6,  Q32 = 4;  };
+template <> struct Model<LINE2D>  { static constexpr int D = 2,  P = 4, K = 2, HQ = 4,  Q32 = 3;  };
+template <> struct Model<LINE2>   { static constexpr int D = 2,  P = 4, K = 2, HQ = 4,  Q32 = 4;  };
+template <> struct Model<LINE3>   { static constexpr int D = 3,  P = 6, K = 2, HQ = 6,  Q32 = 6;  };
+template <> struct Model<CIRCLE2> { static constexpr int D = 2,  P = 3, K = 3, HQ = 3,  Q32 = 4;  };
+template <> struct Model<SPHERE3> { static constexpr int D = 3,  P = 4, K = 4, HQ = 4,  Q32 = 5;  };
+template <> struct Model<ABSOR>   { static constexpr int D = 6,  P = 7, K = 3, HQ = 12, Q32 = 12; };
+template <> struct Model<RAY>     { static constexpr int D = 6,  P = 3, K = 2, HQ = 3,  Q32 = 3;  };
+template <> struct Model<PIVOT>   { static constexpr int D = 12, P = 6, K = 3, HQ = 6,  Q32 = 6;  };
+
+struct ModelInfo { int D, P, K, HQ, Q32; };
+__host__ __device__ inline ModelInfo model_info(int m) {
+  switch (m) {
+    case PLANE3:  return {3, 6, 3, 6, 4};
+    case LINE2D:  return {2, 4, 2, 4, 3};
+    case LINE2:   return {2, 4, 2, 4, 4};
+    case LINE3:   return {3, 6, 2, 6, 6};
+    case CIRCLE2: return {2, 3, 3, 3, 4};
+    case SPHERE3: return {3, 4, 4, 4, 5};
+    case ABSOR:   return {6, 7, 3, 12, 12};
+    case RAY:     return {6, 3, 2, 3, 3};
+    case PIVOT:   return {12, 6, 3, 6, 6};
+  }
+  return {0, 0, 0, 0, 0};
+}
+
+// Thresholds of one estimator instance (what the reference keeps in private members).
+struct EstCfg {
+  double delta;      // SphereParametersEstimator.h / PivotCalibrationParametersEstimator.h: compared against a distance
+  double delta2;     // delta*delta, e.g. PlaneParametersEstimator.hxx:17 -- compared against a squared distance
+  double cross_eps;  // RayIntersectionParametersEstimator.cxx:14-15: sin(minimalAngularDeviation)^2
+};
+
+constexpr double kEps = 2.220446049250313e-016;      // common/Epsilon.h:19
+constexpr double kSphereEps = 1e-9;                  // SphereParametersEstimator.hxx:11
+constexpr double kSmallAngle = 0.008726535498373935; // common/Frame.cxx:8
+constexpr double kHalfPi = 3.14159265358979323846 / 2.0;  // common/Frame.cxx:10
+
+// ---------------------------------------------------------------------------------------
+// Small dense helpers shared by solvers and refine
+// ---------------------------------------------------------------------------------------
+
+// Frame(x,y,z,s,qx,qy,qz) rotation entries, common/Frame.cxx:188-198.
+__device__ __forceinline__ void quat_to_rot(double s, double qx, double qy, double qz, double* R) {
+  R[0] = 1 - 2 * (qy * qy + qz * qz);
+  R[1] = 2 * (qx * qy - s * qz);
+  R[2] = 2 * (qx * qz + s * qy);
+  R[3] = 2 * (qx * qy + s * qz);
+  R[4] = 1 - 2 * (qx * qx + qz * qz);
+  R[5] = 2 * (qy * qz - s * qx);
+  R[6] = 2 * (qx * qz - s * qy);
+  R[7] = 2 * (qy * qz + s * qx);
+  R[8] = 1 - 2 * (qx * qx + qy * qy);
+}
+
+// Frame::getRotationQuaternion, common/Frame.cxx:952-988.
+__device__ inline void rot_to_quat(const double* R, double* q) {
+  const double lo = kHalfPi - kSmallAngle, hi = kHalfPi + kSmallAngle;
+  q[0] = 0.5 * sqrt(R[0] + R[4] + R[8] + 1);
+  const double half_theta = acos(q[0]);
+  if (!(half_theta > lo && half_theta < hi)) {
+    const double denom = 4 * q[0];
+    q[1] = (R[7] - R[5]) / denom;
+    q[2] = (R[2] - R[6]) / denom;
+    q[3] = (R[3] - R[1]) / denom;
+  } else {
+    int i = 0;
+    if (R[4] > R[i * 3 + i]) i = 1;
+    if (R[8] > R[i * 3 + i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    const double w = sqrt(R[i * 3 + i] - R[j * 3 + j] - R[k * 3 + k] + 1);
+    q[i + 1] = w / 2.0;
+    q[j + 1] = (R[i * 3 + j] + R[j * 3 + i]) / (2 * w);
+    q[k + 1] = (R[i * 3 + k] + R[k * 3 + i]) / (2 * w);
+  }
+}
+
+// Cyclic Jacobi, symmetric n x n (row-major a, destroyed); d ascending, eigenvectors in the
+// columns of v.  Stands in for vnl_symmetric_eigensystem (PlaneParametersEstimator.hxx:163).
+template <int N>
+__device__ inline void sym_eig(double* a, double* v, double* d) {
+  for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) v[i * N + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 100; sweep++) {
+    double off = 0.0;
+    for (int p = 0; p < N; p++) for (int q = p + 1; q < N; q++) off += a[p * N + q] * a[p * N + q];
+    if (off == 0.0) break;
+    for (int p = 0; p < N; p++) {
+      for (int q = p + 1; q < N; q++) {
+        const double apq = a[p * N + q];
+        if (apq == 0.0) continue;
+        const double theta = (a[q * N + q] - a[p * N + p]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < N; k++) { const double x = a[k * N + p], y = a[k * N + q]; a[k * N + p] = c * x - s * y; a[k * N + q] = s * x + c * y; }
+        for (int k = 0; k < N; k++) { const double x = a[p * N + k], y = a[q * N + k]; a[p * N + k] = c * x - s * y; a[q * N + k] = s * x + c * y; }
+        for (int k = 0; k < N; k++) { const double x = v[k * N + p], y = v[k * N + q]; v[k * N + p] = c * x - s * y; v[k * N + q] = s * x + c * y; }
+      }
+    }
+  }
+  for (int i = 0; i < N; i++) d[i] = a[i * N + i];
+  for (int i = 0; i + 1 < N; i++) {
+    int m = i;
+    for (int j = i + 1; j < N; j++) if (d[j] < d[m]) m = j;
+    if (m != i) {
+      double t = d[i]; d[i] = d[m]; d[m] = t;
+      for (int k = 0; k < N; k++) { t = v[k * N + i]; v[k * N + i] = v[k * N + m]; v[k * N + m] = t; }
+    }
+  }
+}
+
+// x = pinv(A) b, A (MR x NC, row-major, destroyed), singular values <= tol dropped; returns
+// the rank.  One-sided Jacobi.  Stands in for vnl_matrix_inverse + zero_out_absolute + rank
+// (PivotCalibrationParametersEstimator.cxx:40-47).
+template <int MR, int NC>
+__device__ inline int pinv_solve(double* A, const double* b, double tol, double* x) {
+  double V[NC * NC], y[NC];
+  for (int i = 0; i < NC; i++) for (int j = 0; j < NC; j++) V[i * NC + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; sweep++) {
+    bool rotated = false;
+    for (int p = 0; p < NC; p++) {
+      for (int q = p + 1; q < NC; q++) {
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int k = 0; k < MR; k++) { const double ap = A[k * NC + p], aq = A[k * NC + q]; alpha += ap * ap; beta += aq * aq; gamma += ap * aq; }
+        if (gamma == 0.0 || fabs(gamma) <= 1e-16 * sqrt(alpha * beta)) continue;
+        rotated = true;
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        for (int k = 0; k < MR; k++) { const double xk = A[k * NC + p], yk = A[k * NC + q]; A[k * NC + p] = c * xk - s * yk; A[k * NC + q] = s * xk + c * yk; }
+        for (int k = 0; k < NC; k++) { const double xk = V[k * NC + p], yk = V[k * NC + q]; V[k * NC + p] = c * xk - s * yk; V[k * NC + q] = s * xk + c * yk; }
+      }
+    }
+    if (!rotated) break;
+  }
+  int rank = 0;
+  for (int j = 0; j < NC; j++) {
+    double s2 = 0, ub = 0;
+    for (int k = 0; k < MR; k++) { const double a = A[k * NC + j]; s2 += a * a; ub += a * b[k]; }
+    if (sqrt(s2) <= tol) y[j] = 0.0; else { y[j] = ub / s2; rank++; }
+  }
+  for (int i = 0; i < NC; i++) { double s = 0; for (int j = 0; j < NC; j++) s += V[i * NC + j] * y[j]; x[i] = s; }
+  return rank;
+}
+
+// ---------------------------------------------------------------------------------------
+// estimate(): minimal solvers, one hypothesis per thread.  pts = K data of D doubles in
+// subset order.  Returns false for a degenerate subset (reference: empty parameter vector).
+// ---------------------------------------------------------------------------------------
+template <int M> __device__ bool estimate(const double* pts, const EstCfg& cfg, double* prm);
+
+// PlaneParametersEstimator.hxx:48-69, :107-108
+template <> __device__ inline bool estimate<PLANE3>(const double* d, const EstCfg&, double* prm) {
+  const double *p0 = d, *p1 = d + 3, *p2 = d + 6;
+  const double v10 = p1[0] - p0[0], v11 = p1[1] - p0[1], v12 = p1[2] - p0[2];
+  const double v20 = p2[0] - p0[0], v21 = p2[1] - p0[1], v22 = p2[2] - p0[2];
+  const double nx = v11 * v22 - v12 * v21;
+  const double ny = v12 * v20 - v10 * v22;
+  const double nz = v10 * v21 - v11 * v20;
+  const double norm = sqrt(nx * nx + ny * ny + nz * nz);
+  if (norm < kEps) return false;
+  prm[0] = nx / norm; prm[1] = ny / norm; prm[2] = nz / norm;
+  prm[3] = p0[0]; prm[4] = p0[1]; prm[5] = p0[2];
+  return true;
+}
+
+// Line2DParametersEstimator.cxx:11-32
+template <> __device__ inline bool estimate<LINE2D>(const double* d, const EstCfg& cfg, double* prm) {
+  const double *p0 = d, *p1 = d + 2;
+  const double nx = p1[1] - p0[1];
+  const double ny = p0[0] - p1[0];
+  const double norm_squared = nx * nx + ny * ny;
+  if (norm_squared < cfg.delta2) return false;
+  const double norm = sqrt(nx * nx + ny * ny);
+  prm[0] = nx / norm; prm[1] = ny / norm; prm[2] = p0[0]; prm[3] = p0[1];
+  return true;
+}
+
+// LineParametersEstimator.hxx:23-48 (separation test through Point::distanceSquared, Point.h:72-74)
+template <int DIM> __device__ inline bool estimate_line(const double* d, const EstCfg& cfg, double* prm) {
+  const double *p0 = d, *p1 = d + DIM;
+  double ds = 0;
+  for (int i = 0; i < DIM; i++) { const double t = p0[i] - p1[i]; ds += t * t; }
+  if (ds < cfg.delta2) return false;
+  double dir_norm = 0.0;
+  for (int i = 0; i < DIM; i++) { prm[i] = p0[i] - p1[i]; dir_norm += prm[i] * prm[i]; prm[DIM + i] = p0[i]; }
+  dir_norm = sqrt(dir_norm);
+  for (int i = 0; i < DIM; i++) prm[i] /= dir_norm;
+  return true;
+}
+template <> __device__ inline bool estimate<LINE2>(const double* d, const EstCfg& c, double* prm) { return estimate_line<2>(d, c, prm); }
+template <> __device__ inline bool estimate<LINE3>(const double* d, const EstCfg& c, double* prm) { return estimate_line<3>(d, c, prm); }
+
+// SphereParametersEstimator.hxx:80-109
+template <> __device__ inline bool estimate<CIRCLE2>(const double* d, const EstCfg&, double* prm) {
+  const double *p0 = d, *p1 = d + 2, *p2 = d + 4;
+  const double A00 = p0[0] - p1[0], A01 = p0[1] - p1[1];
+  const double A10 = p0[0] - p2[0], A11 = p0[1] - p2[1];
+  double detA = (A00 * A11 - A01 * A10);
+  if (fabs(detA) < kSphereEps) return false;
+  detA *= 2.0;
+  const double b0 = A00 * (p0[0] + p1[0]) + A01 * (p0[1] + p1[1]);
+  const double b1 = A10 * (p0[0] + p2[0]) + A11 * (p0[1] + p2[1]);
+  prm[0] = (A11 * b0 - A01 * b1) / detA;
+  prm[1] = (A00 * b1 - A10 * b0) / detA;
+  prm[2] = sqrt((p0[0] - prm[0]) * (p0[0] - prm[0]) + (p0[1] - prm[1]) * (p0[1] - prm[1]));
+  return true;
+}
+
+// SphereParametersEstimator.hxx:115-163
+template <> __device__ inline bool estimate<SPHERE3>(const double* d, const EstCfg&, double* prm) {
+  const double *p0 = d, *p1 = d + 3, *p2 = d + 6, *p3 = d + 9;
+  const double A00 = p0[0] - p1[0], A01 = p0[1] - p1[1], A02 = p0[2] - p1[2];
+  const double A10 = p0[0] - p2[0], A11 = p0[1] - p2[1], A12 = p0[2] - p2[2];
+  const double A20 = p0[0] - p3[0], A21 = p0[1] - p3[1], A22 = p0[2] - p3[2];
+  const double CT00 = A11 * A22 - A12 * A21;
+  const double CT10 = A12 * A20 - A10 * A22;
+  const double CT20 = A10 * A21 - A11 * A20;
+  double detA = A00 * CT00 + A01 * CT10 + A02 * CT20;
+  if (fabs(detA) < kSphereEps) return false;
+  detA *= 2;
+  const double CT01 = A02 * A21 - A01 * A22;
+  const double CT11 = A00 * A22 - A02 * A20;
+  const double CT21 = A01 * A20 - A00 * A21;
+  const double CT02 = A01 * A12 - A02 * A11;
+  const double CT12 = A02 * A10 - A00 * A12;
+  const double CT22 = A00 * A11 - A01 * A10;
+  const double b0 = A00 * (p0[0] + p1[0]) + A01 * (p0[1] + p1[1]) + A02 * (p0[2] + p1[2]);
+  const double b1 = A10 * (p0[0] + p2[0]) + A11 * (p0[1] + p2[1]) + A12 * (p0[2] + p2[2]);
+  const double b2 = A20 * (p0[0] + p3[0]) + A21 * (p0[1] + p3[1]) + A22 * (p0[2] + p3[2]);
+  prm[0] = (CT00 * b0 + CT01 * b1 + CT02 * b2) / detA;
+  prm[1] = (CT10 * b0 + CT11 * b1 + CT12 * b2) / detA;
+  prm[2] = (CT20 * b0 + CT21 * b1 + CT22 * b2) / detA;
+  prm[3] = sqrt(((p0[0] - prm[0]) * (p0[0] - prm[0])) + ((p0[1] - prm[1]) * (p0[1] - prm[1])) + ((p0[2] - prm[2]) * (p0[2] - prm[2])));
+  return true;
+}
+
+// One side of the orthonormal-triad construction, AbsoluteOrientationParametersEstimator.cxx:24-51 / :53-81.
+// VNL helpers as published: normalize() scales by 1/sqrt(sum x^2); dot_product / magnitude sum left to right.
+__device__ inline bool triad(const double* P0, const double* P1, const double* P2, double* Rm, double* mean) {
+  double x[3], y[3], z[3];
+  for (int i = 0; i < 3; i++) mean[i] = (P0[i] + P1[i] + P2[i]) / 3.0;
+  for (int i = 0; i < 3; i++) x[i] = P0[i] - mean[i];
+  double s = 0.0; for (int i = 0; i < 3; i++) s += x[i] * x[i];
+  if (s != 0.0) { const double inv = 1.0 / sqrt(s); for (int i = 0; i < 3; i++) x[i] = inv * x[i]; }
+  for (int i = 0; i < 3; i++) y[i] = P1[i] - mean[i];
+  double dot = 0.0; for (int i = 0; i < 3; i++) dot += y[i] * x[i];
+  for (int i = 0; i < 3; i++) y[i] = y[i] - x[i] * dot;
+  s = 0.0; for (int i = 0; i < 3; i++) s += y[i] * y[i];
+  if (s != 0.0) { const double inv = 1.0 / sqrt(s); for (int i = 0; i < 3; i++) y[i] = inv * y[i]; }
+  z[0] = x[1] * y[2] - x[2] * y[1];
+  z[1] = x[2] * y[0] - x[0] * y[2];
+  z[2] = x[0] * y[1] - x[1] * y[0];
+  s = 0.0; for (int i = 0; i < 3; i++) s += z[i] * z[i];
+  if (sqrt(s) < kEps) return false;
+  for (int i = 0; i < 3; i++) { Rm[i * 3 + 0] = x[i]; Rm[i * 3 + 1] = y[i]; Rm[i * 3 + 2] = z[i]; }
+  return true;
+}
+
+// AbsoluteOrientationParametersEstimator.cxx:14-101 (triad construction, NOT Horn -- SURVEY.md 8a-8)
+template <> __device__ inline bool estimate<ABSOR>(const double* d, const EstCfg&, double* prm) {
+  double R1[9], R2[9], R[9], m1[3], m2[3], q[4];
+  if (!triad(d + 0, d + 6, d + 12, R1, m1)) return false;
+  if (!triad(d + 3, d + 9, d + 15, R2, m2)) return false;
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < 3; k++) { double s = 0.0; for (int j = 0; j < 3; j++) s += R2[i * 3 + j] * R1[k * 3 + j]; R[i * 3 + k] = s; }
+  for (int i = 0; i < 3; i++) { double s = 0.0; for (int j = 0; j < 3; j++) s += R[i * 3 + j] * m1[j]; prm[4 + i] = m2[i] - s; }
+  rot_to_quat(R, q);
+  prm[0] = q[0]; prm[1] = q[1]; prm[2] = q[2]; prm[3] = q[3];
+  return true;
+}
+
+// RayIntersectionParametersEstimator.cxx:23-70
+template <> __device__ inline bool estimate<RAY>(const double* d, const EstCfg& cfg, double* prm) {
+  const double *p1 = d, *n1 = d + 3, *p2 = d + 6, *n2 = d + 9;
+  const double p210 = p2[0] - p1[0], p211 = p2[1] - p1[1], p212 = p2[2] - p1[2];
+  const double c0 = n1[1] * n2[2] - n1[2] * n2[1];
+  const double c1 = n1[2] * n2[0] - n1[0] * n2[2];
+  const double c2 = n1[0] * n2[1] - n1[1] * n2[0];
+  const double denominator = c0 * c0 + c1 * c1 + c2 * c2;
+  if (denominator < cfg.cross_eps) return false;
+  const double t1 = (c0 * (p211 * n2[2] - p212 * n2[1]) - c1 * (p210 * n2[2] - p212 * n2[0]) + c2 * (p210 * n2[1] - p211 * n2[0])) / denominator;
+  const double t2 = (c0 * (p211 * n1[2] - p212 * n1[1]) - c1 * (p210 * n1[2] - p212 * n1[0]) + c2 * (p210 * n1[1] - p211 * n1[0])) / denominator;
+  if (t1 < 0 || t2 < 0) return false;
+  prm[0] = (p1[0] + t1 * n1[0] + p2[0] + t2 * n2[0]) / 2.0;
+  prm[1] = (p1[1] + t1 * n1[1] + p2[1] + t2 * n2[1]) / 2.0;
+  prm[2] = (p1[2] + t1 * n1[2] + p2[2] + t2 * n2[2]) / 2.0;
+  return true;
+}
+
+// PivotCalibrationParametersEstimator.cxx:9-51: rows [R_i | -I], rhs -t_i, pseudo-inverse, rank < 6 fails.
+template <> __device__ inline bool estimate<PIVOT>(const double* d, const EstCfg&, double* prm) {
+  double A[9 * 6], b[9];
+  for (int i = 0; i < 54; i++) A[i] = 0.0;
+  for (int i = 0; i < 3; i++) {
+    const double* f = d + 12 * i;
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) A[(3 * i + r) * 6 + c] = f[3 * r + c];
+      A[(3 * i + r) * 6 + 3 + r] = -1.0;
+      b[3 * i + r] = -f[9 + r];
+    }
+  }
+  return pinv_solve<9, 6>(A, b, kEps, prm) >= 6;
+}
+
+// ---------------------------------------------------------------------------------------
+// agree(): prepare once per hypothesis, test once per (hypothesis, datum)
+// ---------------------------------------------------------------------------------------
+template <int M> __device__ __forceinline__ void prepare(const double* prm, double* hq) {
+#pragma unroll
+  for (int i = 0; i < Model<M>::P; i++) hq[i] = prm[i];
+}
+template <> __device__ __forceinline__ void prepare<ABSOR>(const double* prm, double* hq) {
+  quat_to_rot(prm[0], prm[1], prm[2], prm[3], hq);
+  hq[9] = prm[4]; hq[10] = prm[5]; hq[11] = prm[6];
+}
+
+template <int M> __device__ __forceinline__ bool agree(const double* hq, const double* x, const EstCfg& cfg);
+
+// PlaneParametersEstimator.hxx:196-203
+template <> __device__ __forceinline__ bool agree<PLANE3>(const double* h, const double* x, const EstCfg& cfg) {
+  double sd = 0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) sd += h[i] * (x[i] - h[3 + i]);
+  return (sd * sd) < cfg.delta2;
+}
+// Line2DParametersEstimator.cxx:119-123
+template <> __device__ __forceinline__ bool agree<LINE2D>(const double* h, const double* x, const EstCfg& cfg) {
+  const double sd = h[0] * (x[0] - h[2]) + h[1] * (x[1] - h[3]);
+  return (sd * sd) < cfg.delta2;
+}
+// LineParametersEstimator.hxx:135-150
+template <int DIM> __device__ __forceinline__ bool agree_line(const double* h, const double* x, const EstCfg& cfg) {
+  double v[DIM], v_dot_n = 0.0, ds = 0.0;
+#pragma unroll
+  for (int i = 0; i < DIM; i++) { v[i] = x[i] - h[DIM + i]; v_dot_n += v[i] * h[i]; }
+#pragma unroll
+  for (int i = 0; i < DIM; i++) ds += (v[i] - v_dot_n * h[i]) * (v[i] - v_dot_n * h[i]);
+  return ds < cfg.delta2;
+}
+template <> __device__ __forceinline__ bool agree<LINE2>(const double* h, const double* x, const EstCfg& c) { return agree_line<2>(h, x, c); }
+template <> __device__ __forceinline__ bool agree<LINE3>(const double* h, const double* x, const EstCfg& c) { return agree_line<3>(h, x, c); }
+// SphereParametersEstimator.hxx:255-264 (a distance against delta, not squared)
+template <int DIM> __device__ __forceinline__ bool agree_sphere(const double* h, const double* x, const EstCfg& cfg) {
+  double dl = 0;
+#pragma unroll
+  for (int i = 0; i < DIM; i++) dl += ((x[i] - h[i]) * (x[i] - h[i]));
+  dl = fabs(sqrt(dl) - h[DIM]);
+  return dl < cfg.delta;
+}
+template <> __device__ __forceinline__ bool agree<CIRCLE2>(const double* h, const double* x, const EstCfg& c) { return agree_sphere<2>(h, x, c); }
+template <> __device__ __forceinline__ bool agree<SPHERE3>(const double* h, const double* x, const EstCfg& c) { return agree_sphere<3>(h, x, c); }
+// AbsoluteOrientationParametersEstimator.cxx:316-327 with Frame::apply, common/Frame.cxx:229-248
+template <> __device__ __forceinline__ bool agree<ABSOR>(const double* h, const double* x, const EstCfg& cfg) {
+  const double qx = h[0] * x[0] + h[1] * x[1] + h[2] * x[2] + h[9];
+  const double qy = h[3] * x[0] + h[4] * x[1] + h[5] * x[2] + h[10];
+  const double qz = h[6] * x[0] + h[7] * x[1] + h[8] * x[2] + h[11];
+  const double dx = qx - x[3], dy = qy - x[4], dz = qz - x[5];
+  return (dx * dx + dy * dy + dz * dz) < cfg.delta2;
+}
+// RayIntersectionParametersEstimator.cxx:164-179
+template <> __device__ __forceinline__ bool agree<RAY>(const double* h, const double* x, const EstCfg& cfg) {
+  const double* p = x; const double* n = x + 3;
+  const double t = n[0] * (h[0] - p[0]) + n[1] * (h[1] - p[1]) + n[2] * (h[2] - p[2]);
+  const double dx = h[0] - p[0] - t * n[0];
+  const double dy = h[1] - p[1] - t * n[1];
+  const double dz = h[2] - p[2] - t * n[2];
+  return t >= 0 && (dx * dx + dy * dy + dz * dz < cfg.delta2);
+}
+// PivotCalibrationParametersEstimator.cxx:108-123 (Frame::apply then Vector::l2Norm, common/Vector.h:134-139)
+template <> __device__ __forceinline__ bool agree<PIVOT>(const double* h, const double* x, const EstCfg& cfg) {
+  const double qx = x[0] * h[0] + x[1] * h[1] + x[2] * h[2] + x[9];
+  const double qy = x[3] * h[0] + x[4] * h[1] + x[5] * h[2] + x[10];
+  const double qz = x[6] * h[0] + x[7] * h[1] + x[8] * h[2] + x[11];
+  const double rx = qx - h[3], ry = qy - h[4], rz = qz - h[5];
+  double s = 0;
+  s += rx * rx; s += ry * ry; s += rz * rz;
+  return sqrt(s) < cfg.delta;
+}
+
+// ---------------------------------------------------------------------------------------
+// Subset generation
+// ---------------------------------------------------------------------------------------
+
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so hypothesis h's subset depends only
+// on (seed, h) -- independent of how hypotheses are split over thread blocks or GPUs.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+// K distinct indices in [0, n), in draw order (the reference also hands estimate() its subset
+// in draw order, RANSAC.hxx:56-68).  Draw j picks uniformly among the n-j indices not yet taken.
+template <int K>
+__device__ __forceinline__ void sample_subset(uint64_t gidx, uint64_t seed, uint32_t n, int32_t* out) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t rnd[4] = {r.x, r.y, r.z, r.w};
+  uint32_t sorted[K];
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    uint32_t v = __umulhi(rnd[j], n - j);  // uniform in [0, n-j)
+#pragma unroll
+    for (int i = 0; i < j; i++) if (v >= sorted[i]) v++;  // skip taken indices, ascending
+    out[j] = (int32_t)v;
+    int pos = j;
+#pragma unroll
+    for (int i = j - 1; i >= 0; i--) if (sorted[i] > v) { sorted[i + 1] = sorted[i]; pos = i; }
+    sorted[pos] = v;
+  }
+}
+
+__device__ __forceinline__ uint64_t binom(uint32_t n, int k) {
+  if ((uint32_t)k > n) return 0;
+  uint64_t r = 1;
+  for (int i = 0; i < k; i++) r = r * (n - i) / (i + 1);
+  return r;
+}
+
+// Subset with lexicographic rank `rank` among ascending K-tuples of {0..n-1}: the enumeration
+// order of RANSAC<T,S>::computeAllChoices (RANSAC.hxx:197-213).  Tuples whose j-th element is
+// below c (given the earlier elements) number C(n-lo, K-j) - C(n-c, K-j); binary search on c.
+template <int K>
+__device__ inline void unrank_lex(uint64_t rank, uint32_t n, int32_t* out) {
+  uint32_t lo = 0;
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    const int kk = K - j;
+    const uint64_t total = binom(n - lo, kk);
+    // largest c in [lo, n-kk] with  total - C(n-c, kk) <= rank
+    uint32_t a = lo, b = n - kk;
+    while (a < b) {
+      const uint32_t mid = a + (b - a + 1) / 2;
+      if (total - binom(n - mid, kk) <= rank) a = mid; else b = mid - 1;
+    }
+    rank -= total - binom(n - a, kk);
+    out[j] = (int32_t)a;
+    lo = a + 1;
+  }
+}
+
+}  // namespace lsqr

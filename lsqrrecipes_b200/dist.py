@@ -1,0 +1,81 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink / NVSwitch).
+
+The path shards like this: points REPLICATED on every GPU, hypotheses PARTITIONED
+by global index (rank r owns [r*H/W, (r+1)*H/W); Philox counters and lexicographic ranks are
+global, so results do not depend on W), and exactly two exchange steps:
+  1. one all-reduce(MAX) on the packed 64-bit key (count << 32) | (0xFFFFFFFF - index): largest
+     count wins, ties go to the smallest index -- the strict '>' of RANSAC.hxx:100,245;
+  2. one all-reduce(SUM) of <= 32 doubles per refine pass (per LM iteration for the sphere):
+     the least-squares moments of the point shards.
+Both run in place on device memory through the hooks of lsqr_set_shard.  The helpers below are
+pure functions so that the N>1 logic is testable with gloo on CPU.
+"""
+import ctypes
+
+import numpy as np
+
+INDEX_MASK = 0xFFFFFFFF
+
+
+def hypothesis_shard(count, rank, world):
+    """[lo, hi) of the hypotheses of one request owned by `rank` (same formula as engine.cu)."""
+    return count * rank // world, count * (rank + 1) // world
+
+
+def point_shard(n, rank, world):
+    """[begin, end) of the data refined by `rank`; boundaries fall on 32-datum words (engine.cu shard_range)."""
+    if world <= 1:
+        return 0, n
+    words = (n + 31) // 32
+    return min(words * rank // world * 32, n), min(words * (rank + 1) // world * 32, n)
+
+
+def pack_key(count, index):
+    return (int(count) << 32) | (INDEX_MASK - int(index))
+
+
+def unpack_key(key):
+    return int(key) >> 32, INDEX_MASK - (int(key) & INDEX_MASK)
+
+
+def best_key(counts, index_base=0):
+    """arg-max of a count vector as a packed key (first maximum wins)."""
+    counts = np.asarray(counts)
+    if counts.size == 0:
+        return 0
+    i = int(np.argmax(counts))  # numpy returns the first maximum
+    return pack_key(counts[i], index_base + i)
+
+
+class _DevArray:
+    """Wraps a raw device pointer for torch.as_tensor via __cuda_array_interface__."""
+
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def install_hooks(engine, rank, world, group=None):
+    """Registers NCCL all-reduce hooks on an Engine.  The keys are < 2^63 (counts < 2^31), so the
+    MAX over int64 equals the MAX over uint64."""
+    import torch
+    import torch.distributed as dist
+
+    def max_hook(user, dev_key, stream):
+        try:
+            t = torch.as_tensor(_DevArray(dev_key, 1, "<i8"), device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            return 0
+        except Exception as e:  # never raise across the C ABI
+            print("max all-reduce hook failed:", e)
+            return 1
+
+    def sum_hook(user, dev_vals, count, stream):
+        try:
+            t = torch.as_tensor(_DevArray(dev_vals, count, "<f8"), device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            return 0
+        except Exception as e:
+            print("sum all-reduce hook failed:", e)
+            return 1
+
+    engine.set_shard(rank, world, max_hook, sum_hook)

@@ -1,0 +1,58 @@
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def port():
+    """The plain-C restatement (oracle/liboracle.so); built on demand with gcc."""
+    from oracle import pyoracle
+    if not pyoracle.available("port"):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
+    return pyoracle.Oracle("port")
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The reference's own sources (oracle/_ref); present only where it was built."""
+    from oracle import pyoracle
+    if not pyoracle.available("ref"):
+        if os.path.isdir("/root/reference/parametersEstimators"):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
+        else:
+            pytest.skip("oracle/_ref not built and /root/reference absent")
+    return pyoracle.Oracle("ref")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def same_up_to_sign(a, b, idx, tol):
+    """Eigenvector-derived entries (normals, directions, quaternions) are defined up to sign."""
+    a, b = np.array(a, dtype=float), np.array(b, dtype=float)
+    if a.shape != b.shape:
+        return False
+    if len(idx) and np.dot(a[idx], b[idx]) < 0:
+        a = a.copy()
+        a[idx] = -a[idx]
+    scale = np.maximum(np.abs(b), 1.0)
+    return bool(np.all(np.abs(a - b) <= tol * scale))
+
+
+# parameter entries that carry an arbitrary sign after leastSquaresEstimate
+SIGN_IDX = {"plane3": [0, 1, 2], "line2d": [0, 1], "line2": [0, 1], "line3": [0, 1, 2], "circle2": [], "sphere3": [],
+            "absor": [0, 1, 2, 3], "ray": [], "pivot": []}

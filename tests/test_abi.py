@@ -1,0 +1,83 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/lsqr_b200.h declares, and fails loudly (no fallback) when there is no GPU.  No compute."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from lsqrrecipes_b200 import api
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "lsqr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lsqr_[a-z0-9_]+)\s*\(", text)) - {"lsqr_allreduce_max_u64_fn", "lsqr_allreduce_sum_f64_fn"})
+
+
+def test_library_exports_every_declared_symbol():
+    path = api.lib_path()
+    assert os.path.exists(path), "liblsqr_b200.so must be built in-tree (__graft_entry__.build())"
+    lib = ctypes.CDLL(path)
+    declared = _declared_functions()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/lsqr_b200.h but not exported"
+    assert sorted(api.EXPORTED_SYMBOLS) == declared, "python binding and header must list the same entry points"
+
+
+def test_model_table_matches_reference_shapes():
+    lib = api.load_library()
+    for name, m in api.MODELS.items():
+        d, p, k = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        assert lib.lsqr_model_info(m, ctypes.byref(d), ctypes.byref(p), ctypes.byref(k)) == 0
+        assert (d.value, p.value, k.value) == api.MODEL_INFO[m]
+    assert lib.lsqr_model_info(99, None, None, None) != 0
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(api.LsqrError):
+        api.Engine("plane3", 0.5)
+
+
+def test_library_is_sm100a_only():
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run(["cuobjdump", "-lelf", api.lib_path()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under lsqrrecipes_b200/ or include/ may reference it."""
+    bad = []
+    for base in ("lsqrrecipes_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                    text = open(os.path.join(dirpath, f), errors="ignore").read()
+                    if re.search(r"pyoracle|liboracle|lsqr_oracle|libref_oracle|from oracle|import oracle", text):
+                        bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
+
+
+def test_host_guards_need_no_gpu():
+    """RANSAC.hxx:16-19: invalid input returns 0 and leaves `parameters` untouched (randomized overload);
+    the exhaustive overload clears first (RANSAC.hxx:165-169).  Both return before any device work."""
+    from lsqrrecipes_b200 import PlaneParametersEstimator, RANSAC
+    est = PlaneParametersEstimator(0.5)
+    assert est.numForEstimate() == 3
+    params = [1.0, 2.0]
+    assert RANSAC.compute(params, est, [[0, 0, 0], [1, 1, 1]], 0.99) == 0.0 and params == [1.0, 2.0]
+    assert RANSAC.compute(params, est, [[0, 0, 0]] * 5, 1.0) == 0.0 and params == [1.0, 2.0]
+    assert RANSAC.compute(params, est, [[0, 0, 0]] * 5, 0.0) == 0.0 and params == [1.0, 2.0]
+    assert RANSAC.compute(params, est, [[0, 0, 0], [1, 1, 1]]) == 0.0 and params == []
+    out = [9.0]
+    est.estimate([[0, 0, 0], [1, 0, 0]], out)   # fewer than k points: cleared, nothing computed
+    assert out == []

@@ -1,0 +1,323 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs and the same ordered subset lists, and against the committed golden fixtures
+minted by the reference.  Bars (BASELINE.json north_star):
+  * fp64 validation mode: per-hypothesis inlier counts, the chosen best subset and the consensus
+    mask are BIT-EXACT; estimate() parameters bit-exact where the reference's arithmetic is plain
+    double (all models but pivot, whose 9x6 pseudo-inverse goes through an SVD stand-in);
+  * fp32 fast mode: per-point decisions may differ only within the fp32 rounding band of the
+    threshold (stated below), refined parameters within 1e-4 relative;
+  * refined parameters: 1e-6 relative (fp64), modulo the sign of eigenvector-derived entries.
+"""
+import numpy as np
+import pytest
+
+from conftest import SIGN_IDX, golden, same_up_to_sign
+from lsqrrecipes_b200 import FP32, FP64, SAMPLE_EXHAUSTIVE, SAMPLE_LIST, SAMPLE_PARAMS, Engine, synth
+from oracle.pyoracle import INFO, MODELS
+
+pytestmark = pytest.mark.gpu
+ALL = list(MODELS.items())
+REFINE_TOL = 1e-6
+
+
+def _ls_types(name):
+    return [0, 1] if name in ("circle2", "sphere3") else [1]
+
+
+@pytest.mark.parametrize("name,m", ALL)
+def test_fp64_counts_bit_exact_vs_reference_fixture(name, m):
+    """Subset list from the fixture -> device minimal solve + fp64 consensus == what the reference returned."""
+    g = golden(name)
+    eng = Engine(name, float(g["delta"]))
+    eng.upload(g["data"])
+    r = eng.score(sampler=SAMPLE_LIST, subsets=g["subsets"], precision=FP64, want_counts=True, want_params=True)
+    assert np.array_equal(r["counts"], g["counts"])
+    assert np.array_equal(np.isnan(r["params"]), np.isnan(g["params"]))
+    if name == "pivot":
+        assert np.allclose(np.nan_to_num(r["params"]), np.nan_to_num(g["params"]), rtol=1e-9, atol=1e-9)
+    else:
+        assert np.array_equal(np.nan_to_num(r["params"]), np.nan_to_num(g["params"])), "device estimate() must round like the reference"
+    b = int(np.argmax(g["counts"]))  # first maximum: strict '>' of RANSAC.hxx:245
+    assert r["best_index"] == b and r["best_count"] == g["counts"][b]
+    assert np.array_equal(r["best_subset"], g["subsets"][b])
+    eng.close()
+
+
+@pytest.mark.parametrize("name,m", ALL)
+def test_fp64_counts_bit_exact_vs_oracle_large(port, name, m):
+    """Same, at a size where tiles, chunks and atomics are all exercised, against the oracle."""
+    D, P, k = INFO[m]
+    n, H = 20011, 3000
+    data, _ = synth.GENERATORS[name](n, seed=777 + m)
+    delta = synth.DELTAS[name]
+    subs = synth.random_subsets(n, k, H, seed=31 + m)
+    c_ref, p_ref = port.score_subsets(m, delta, data, subs)
+    eng = Engine(name, delta)
+    eng.upload(data)
+    r = eng.score(sampler=SAMPLE_LIST, subsets=subs, precision=FP64, want_counts=True, want_params=True)
+    assert np.array_equal(r["counts"], c_ref)
+    # agree() alone, on the oracle's own hypotheses (covers pivot bit-exactly as well)
+    r2 = eng.score(sampler=SAMPLE_PARAMS, params=p_ref, precision=FP64, want_counts=True)
+    assert np.array_equal(r2["counts"], c_ref)
+    assert r2["best_index"] == int(np.argmax(c_ref))
+    eng.close()
+
+
+@pytest.mark.parametrize("name,m", ALL)
+def test_exhaustive_compute_vs_reference_fixture(name, m):
+    """RANSAC<T,S>::compute, brute-force overload (RANSAC.hxx:150-249), on the fixture's small problem."""
+    g = golden(name)
+    for ls in _ls_types(name):
+        eng = Engine(name, float(g["delta"]), ls_type=ls)
+        eng.upload(g["small"])
+        r = eng.ransac_exhaustive(precision=FP64)
+        assert np.array_equal(r["mask"], g[f"ex_mask_ls{ls}"]), "consensus set must be bit-exact"
+        assert r["fraction"] == float(g[f"ex_fraction_ls{ls}"])
+        assert same_up_to_sign(r["params"], g[f"ex_params_ls{ls}"], SIGN_IDX[name], REFINE_TOL)
+        eng.close()
+
+
+def test_config1_plane23_exhaustive(port):
+    """BASELINE.json configs[0] restated."""
+    g = golden("config1_plane23")
+    eng = Engine("plane3", 0.5)
+    eng.upload(g["data"])
+    s = eng.score(count=1771, sampler=SAMPLE_EXHAUSTIVE, precision=FP64, want_counts=True, want_params=True)
+    assert np.array_equal(s["counts"], g["all_counts"])
+    assert np.array_equal(s["params"], g["all_params"])
+    assert s["best_index"] == int(np.argmax(g["all_counts"]))
+    r = eng.ransac_exhaustive(precision=FP64)
+    assert np.array_equal(r["mask"], g["mask"]) and r["fraction"] == float(g["fraction"])
+    assert same_up_to_sign(r["params"], g["params"], [0, 1, 2], REFINE_TOL)
+    # the on-device unranking follows the reference's enumeration order
+    for rank in (0, 5, 1014, 1770):
+        s1 = eng.score(count=1, first=rank, sampler=SAMPLE_EXHAUSTIVE, precision=FP64)
+        assert np.array_equal(s1["best_subset"], port.unrank_lex(rank, 23, 3)) or s1["best_count"] == 0
+    eng.close()
+
+
+def test_pivot_file_known_answers():
+    """The reference's one file-based known-answer test (PivotCalibrationParametersEstimatorTest.cxx)."""
+    g = golden("pivot_file")
+    frames = g["frames"]
+    n = len(frames)
+    eng = Engine("pivot", 1.0)
+    exact = eng.estimate(frames[[0, int(n / 2.0), n - 1]])
+    assert len(exact) == 6 and np.all(np.abs(exact - g["known_exact"]) < 1.0)
+    assert np.allclose(exact, g["exact"], rtol=1e-9, atol=1e-9)
+    assert eng.agree(exact, frames[[0, int(n / 2.0), n - 1]]).sum() == 3
+    ls = eng.least_squares(frames)
+    assert len(ls) == 6 and np.all(np.abs(ls - g["known_ls"]) < 1.0)
+    assert np.allclose(ls, g["ls"], rtol=1e-8, atol=1e-8)
+    eng.close()
+
+
+def test_circle_agree_literals():
+    """testing/SphereParametersEstimatorTest.cxx:280-296"""
+    eng = Engine("circle2", 0.5)
+    out = eng.agree([0.0, 0.0, 2.0], np.array([[0, 0], [1.75, 0], [2.25, 0], [4, 0.]]))
+    assert out.tolist() == [0, 1, 1, 0]
+    eng.close()
+
+
+@pytest.mark.parametrize("name,m", ALL)
+def test_consensus_mask_and_refine_vs_oracle(port, name, m):
+    D, P, k = INFO[m]
+    n = 50021
+    data, _ = synth.GENERATORS[name](n, seed=1234 + m)
+    delta = synth.DELTAS[name]
+    subs = synth.random_subsets(n, k, 64, seed=5 + m)
+    c_ref, p_ref = port.score_subsets(m, delta, data, subs)
+    b = int(np.argmax(c_ref))
+    cnt_ref, mask_ref = port.agree(m, delta, p_ref[b], data)
+    for ls in _ls_types(name):
+        eng = Engine(name, delta, ls_type=ls)
+        eng.upload(data)
+        cnt = eng.consensus(p_ref[b])
+        assert cnt == cnt_ref
+        assert np.array_equal(eng.get_mask(), mask_ref), "agree() mask must be bit-exact in fp64"
+        prm = eng.refine()
+        want = port.least_squares(m, delta, data[mask_ref.astype(bool)], ls)
+        assert same_up_to_sign(prm, want, SIGN_IDX[name], REFINE_TOL), (prm, want)
+        # leastSquaresEstimate() called directly on the inliers gives the same answer
+        direct = eng.least_squares(data[mask_ref.astype(bool)])
+        assert same_up_to_sign(direct, want, SIGN_IDX[name], REFINE_TOL)
+        eng.close()
+
+
+def _fp32_band(name, data, prm, delta):
+    """Half-width (in residual units) of the band around the threshold inside which an fp32
+    decision may legitimately differ: 1e-6 relative to the magnitude of the terms that are
+    summed to form the residual (SURVEY.md / DESIGN.md 'fp32 fast mode')."""
+    scale = np.abs(data).max() + np.abs(prm).max() + 1.0
+    return 1e-6 * scale * (4.0 if name in ("absor", "pivot", "ray", "line3", "line2") else 2.0)
+
+
+def _residual64(name, prm, data, delta):
+    """|residual| in float64 numpy, and the threshold it is compared with (distance units)."""
+    p = np.asarray(prm)
+    if name in ("plane3",):
+        return np.abs((data - p[3:6]) @ p[0:3]), delta
+    if name == "line2d":
+        return np.abs((data - p[2:4]) @ p[0:2]), delta
+    if name in ("line2", "line3"):
+        d = data.shape[1]
+        v = data - p[d:]
+        w = v - (v @ p[:d])[:, None] * p[:d]
+        return np.linalg.norm(w, axis=1), delta
+    if name in ("circle2", "sphere3"):
+        d = data.shape[1]
+        return np.abs(np.linalg.norm(data - p[:d], axis=1) - p[d]), delta
+    if name == "absor":
+        R = synth.quat_to_matrix(*p[:4])
+        return np.linalg.norm(data[:, :3] @ R.T + p[4:7] - data[:, 3:], axis=1), delta
+    if name == "ray":
+        v = p[:3] - data[:, :3]
+        t = np.sum(v * data[:, 3:], axis=1)
+        r = np.linalg.norm(v - t[:, None] * data[:, 3:], axis=1)
+        r[t < 0] = np.inf
+        return r, delta
+    if name == "pivot":
+        R = data[:, :9].reshape(-1, 3, 3)
+        return np.linalg.norm(np.einsum("nij,j->ni", R, p[:3]) + data[:, 9:] - p[3:6], axis=1), delta
+    raise AssertionError(name)
+
+
+@pytest.mark.parametrize("name,m", ALL)
+def test_fp32_fast_mode_differs_only_near_threshold(port, name, m):
+    D, P, k = INFO[m]
+    n, H = 30011, 512
+    data, _ = synth.GENERATORS[name](n, seed=900 + m)
+    delta = synth.DELTAS[name]
+    subs = synth.random_subsets(n, k, H, seed=77 + m)
+    c64, p64 = port.score_subsets(m, delta, data, subs)
+    eng = Engine(name, delta)
+    eng.upload(data)
+    r = eng.score(sampler=SAMPLE_LIST, subsets=subs, precision=FP32, want_counts=True)
+    c32 = r["counts"].astype(np.int64)
+    diff = np.abs(c32 - c64.astype(np.int64))
+    # every count difference must be explained by points inside the rounding band of the threshold
+    worst = np.argsort(-diff)[:8]
+    for h in worst:
+        if np.isnan(p64[h, 0]):
+            assert c32[h] == 0
+            continue
+        res, thr = _residual64(name, p64[h], data, delta)
+        band = _fp32_band(name, data, p64[h], delta)
+        near = int(np.sum(np.abs(res - thr) <= band))
+        assert diff[h] <= near, (name, h, diff[h], near)
+    assert diff.sum() <= 1e-3 * c64.sum() + 16
+    eng.close()
+
+
+@pytest.mark.parametrize("name,m", ALL)
+@pytest.mark.parametrize("precision", [FP64, FP32])
+def test_randomized_compute_end_to_end(port, name, m, precision):
+    """RANSAC<T,S>::compute(parameters, estimator, data, 0.999, &consensusSet): the result must be the
+    least-squares fit of a consensus set that the oracle reproduces from the chosen hypothesis."""
+    D, P, k = INFO[m]
+    n = 20000
+    data, true = synth.GENERATORS[name](n, seed=2024 + m)
+    delta = synth.DELTAS[name]
+    eng = Engine(name, delta)
+    eng.upload(data)
+    r = eng.ransac(0.999, precision=precision, seed=11)
+    assert r["fraction"] > 0.4 and r["tries"] >= 1
+    mask = r["mask"].astype(bool)
+    assert mask.sum() == r["best_count"] and abs(r["fraction"] - mask.sum() / n) < 1e-15
+    want = port.least_squares(m, delta, data[mask], 1)
+    assert same_up_to_sign(r["params"], want, SIGN_IDX[name], REFINE_TOL if precision == FP64 else 1e-4)
+    # and the refined model explains the generating model's inliers
+    cnt, _ = port.agree(m, delta, r["params"], data)
+    assert cnt >= 0.9 * mask.sum()
+    eng.close()
+
+
+def test_philox_sampler_is_partition_independent():
+    """Hypothesis h depends only on (seed, h): scoring [0,H) in one request or in pieces gives the same counts."""
+    data, _ = synth.plane(5000, seed=3)
+    eng = Engine("plane3", 0.5)
+    eng.upload(data)
+    whole = eng.score(count=4096, seed=5, precision=FP64, want_counts=True)
+    parts = [eng.score(count=1024, first=f, seed=5, precision=FP64, want_counts=True)["counts"] for f in (0, 1024, 2048, 3072)]
+    assert np.array_equal(whole["counts"], np.concatenate(parts))
+    assert whole["n_valid"] == 4096
+    other = eng.score(count=4096, seed=6, precision=FP64, want_counts=True)
+    assert not np.array_equal(whole["counts"], other["counts"])
+    # subsets are distinct, in range
+    s = eng.score(count=1, first=123, seed=5, precision=FP64)
+    assert len(set(s["best_subset"].tolist())) == 3 and s["best_subset"].min() >= 0 and s["best_subset"].max() < 5000
+    eng.close()
+
+
+def test_edge_cases_match_reference_conventions():
+    eng = Engine("plane3", 0.5)
+    # fewer data than the minimal subset (RANSAC.hxx:16-19 / :168-169)
+    eng.upload(np.zeros((2, 3)))
+    r = eng.ransac(0.99)
+    assert r["fraction"] == 0.0 and len(r["params"]) == 0
+    r = eng.ransac_exhaustive()
+    assert r["fraction"] == 0.0 and len(r["params"]) == 0
+    # all subsets degenerate -> empty parameters, return 0
+    eng.upload(np.ones((8, 3)))
+    r = eng.ransac_exhaustive()
+    assert r["fraction"] == 0.0 and len(r["params"]) == 0 and r["best_count"] == 0
+    # probability outside (0,1)
+    data, _ = synth.plane(100, seed=1)
+    eng.upload(data)
+    assert eng.ransac(1.0)["fraction"] == 0.0 and eng.ransac(0.0)["fraction"] == 0.0
+    # all inliers: terminates on the first perfect hypothesis (RANSAC.hxx:104-105)
+    flat = np.random.default_rng(0).uniform(-10, 10, (1000, 3))
+    flat[:, 2] = 0.0
+    eng.upload(flat)
+    r = eng.ransac(0.99, precision=FP64)
+    assert r["fraction"] == 1.0 and r["best_count"] == 1000
+    # estimate(): degenerate -> empty
+    assert len(eng.estimate(np.array([[0, 0, 0], [1, 1, 1], [2, 2, 2.]]))) == 0
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["line2d", "plane3", "sphere3"])
+def test_batched_small_problems_vs_oracle(port, name):
+    """BASELINE.json configs[4]: many independent small problems, one thread block each.  Exhaustive mode is
+    bit-comparable with the reference's brute-force driver run per problem."""
+    m = MODELS[name]
+    D, P, k = INFO[m]
+    delta = synth.DELTAS[name]
+    nprob = 24
+    sizes = [20 + (7 * i) % 13 for i in range(nprob)]
+    sizes[3] = 1   # ragged: fewer points than the minimal subset
+    sizes[5] = k
+    chunks = [synth.GENERATORS[name](max(s, k + 1), seed=50 + i)[0][:s] for i, s in enumerate(sizes)]
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    eng = Engine(name, delta, ls_type=1)
+    out = eng.ransac_batch(np.concatenate(chunks), offsets, exhaustive=True, want_masks=True)
+    for i, ch in enumerate(chunks):
+        prm, mask, frac, cnt, rank = port.ransac_exhaustive(m, delta, ch, ls_type=1)
+        assert out["counts"][i] == cnt
+        got_mask = out["masks"][int(offsets[i]):int(offsets[i + 1])]
+        assert np.array_equal(got_mask, mask)
+        if len(prm) == 0:
+            assert np.isnan(out["params"][i]).all()
+        else:
+            assert same_up_to_sign(out["params"][i], prm, SIGN_IDX[name], REFINE_TOL)
+    # randomized mode: consensus at least as large as the generating inlier set minus noise tail
+    out2 = eng.ransac_batch(np.concatenate(chunks), offsets, exhaustive=False, prob=0.999, max_tries=4096, seed=9)
+    ok = [i for i, s in enumerate(sizes) if s > 2 * k]
+    assert np.mean(out2["counts"][ok] >= 0.8 * out["counts"][ok]) > 0.9
+    eng.close()
+
+
+def test_python_operator_interface_mirrors_reference():
+    """Reads like examples/planeEstimation.cxx:112-118."""
+    from lsqrrecipes_b200 import PlaneParametersEstimator, RANSAC
+    data, true = synth.plane(1000, outlier_frac=0.1, seed=8)
+    est = PlaneParametersEstimator(0.5)
+    params, consensus = [], []
+    frac = RANSAC.compute(params, est, data.tolist(), 0.999, consensus)
+    assert len(params) == 6 and len(consensus) == 1000 and abs(frac - sum(consensus) / 1000) < 1e-12
+    assert abs(abs(np.dot(params[:3], true[:3])) - 1) < 1e-3
+    assert est.agree(params, data[consensus.index(True)])
+    ls = []
+    est.leastSquaresEstimate(data[np.array(consensus)], ls)
+    assert same_up_to_sign(ls, params, [0, 1, 2], 1e-9)
