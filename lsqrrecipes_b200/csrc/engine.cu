@@ -327,6 +327,7 @@ int consensus_impl(lsqr_ctx* ctx, DataSet& ds, const double* params, uint32_t* o
   shard_range(ctx, ds.n, &b, &e);
   const int nm = moments_count(ctx->model, false);
   CK(cudaEventRecord(ctx->ev[4], s));
+  ctx->rb.maskbits = ds.maskbits;
   launch_mask_moments(ctx->model, ds.view(), b, e, ctx->small_dev, 1, nullptr, ctx->cfg, ctx->rb, s); ctx->launches++;
   CK(cudaEventRecord(ctx->ev[5], s));
   if (int rc = reduce_moments(ctx, nm)) return rc;
@@ -349,6 +350,7 @@ int refine_impl(lsqr_ctx* ctx, DataSet& ds, int use_mask, double* out_params, in
   cudaStream_t s = ctx->stream;
   CK(cudaSetDevice(ctx->device));
   const DataView dv = ds.view();
+  ctx->rb.maskbits = ds.maskbits;
   uint32_t b, e;
   shard_range(ctx, ds.n, &b, &e);
   const int nm = moments_count(ctx->model, false);

@@ -43,6 +43,9 @@ void launch_hoist32(int model, const double* hyp64, size_t hld, uint32_t H, cons
 // counts[h] (+)= |{m : agree(h, datum m)}|.  counts must be zeroed by the caller.  Returns #launches.
 int launch_consensus(int model, int precision, const DataView& dv, const double* hyp64, const float* hyp32, size_t hld, uint32_t H,
                      const EstCfg& cfg, uint32_t* counts, int num_sms, cudaStream_t s);
+// fp32 fast mode (k_fast.cu)
+int launch_consensus32(int model, const DataView& dv, const float* hyp32, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms,
+                       cudaStream_t s);
 // key = max over h of (counts[h] << 32) | (0xFFFFFFFF - (index_base + h)); key must be zeroed first.
 void launch_argmax(const uint32_t* counts, uint32_t H, uint32_t index_base, unsigned long long* key, cudaStream_t s);
 

@@ -1,0 +1,372 @@
+// fp32 "fast mode" consensus: the hot kernel of the whole path (RANSAC.hxx:94-99 / :239-244).
+//
+// Formulation (chosen by measurement, tools/consensus_lab.cu + tools/pipe_lab.cu, profiles/):
+//   * sm_100a issues one warp instruction per cycle per SM sub-partition and a packed
+//     fma.rn.f32x2 (SASS FFMA2) occupies two of those cycles, so the cost of an evaluation is the
+//     number of instruction slots it needs: 3 for the plane's FMA chain plus whatever the
+//     threshold test and the count cost.  `cnt += (|s| < delta)` compiles to FSETP + VIADD +
+//     predicated MOV (3 slots, 7.5 slots/eval measured).
+//   * Every model is therefore written so that ONE float g carries the decision in its SIGN BIT
+//     (inlier <=> g < 0): the squared-distance models start their FMA chain at -delta^2, the plane
+//     adds one FMA (s*s - delta^2), the sphere squares its centred d^2 - m against w^2.  Counting
+//     is then a single shift-add (LEA.HI cnt = cnt + (g >> 31)).
+//   * For the two 2-3 FMA models (plane, 2D line) a third of the register-blocked hypotheses use the
+//     sign form (4 FMA-pipe + 1 ALU slot) and two thirds use FSETP + predicated IADD on |s| < delta
+//     (3 FMA-pipe + 2 ALU slots), which balances the FMA and ALU pipes: 4.9 slots/eval measured.
+//   * Arithmetic is packed over PAIRS OF POINTS (f32x2): hypothesis constants are duplicated into
+//     both halves once per thread, point pairs come straight out of the SoA shared-memory tile
+//     (one LDS.128 = two pairs), so no repacking happens in the loop.
+//   * Point tiles are staged by TMA bulk copies into a 2-deep shared-memory ring (as in k_score.cu).
+// Tensor cores are deliberately unused: contraction depth <= 4 (BASELINE.json north_star).
+#include "engine.h"
+
+namespace lsqr {
+
+// ---- mbarrier / TMA-bulk helpers ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarrier_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count)); }
+__device__ __forceinline__ void mbarrier_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarrier_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src), "r"(bytes),
+               "r"(smem_addr(bar))
+               : "memory");
+}
+
+// ---- packed pair arithmetic (sm_100 f32x2) -------------------------------------------------
+struct f2 { unsigned long long v; };
+__device__ __forceinline__ f2 splat(float a) { f2 r; asm("mov.b64 %0, {%1, %1};" : "=l"(r.v) : "f"(a)); return r; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ void halves(f2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ f2 join(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+
+// ---- hoisted fp32 hypotheses ---------------------------------------------------------------
+// Q32 floats per hypothesis, computed once in fp64 from the raw parameters, the data centre c
+// (positions are stored as x - c in fp32) and the thresholds:
+//   PLANE3   (nx,ny,nz, -n.(a-c))
+//   LINE2D   (nx,ny, -n.(a-c))
+//   LINE2/3  (dir, a-c)
+//   CIRCLE/SPHERE (ctr-c, -m, -w^2)  with  |d - r| < delta  <=>  (d^2 - m)^2 < w^2,  m = r^2+delta^2, w = 2 r delta
+//   ABSOR    (R[9], R c1 + t - c2)
+//   RAY      (x - c)
+//   PIVOT    (tDRF, tW - c)
+template <int M> __device__ __forceinline__ void hoist32(const double* p, const double* c, const EstCfg& cfg, float* q);
+template <> __device__ __forceinline__ void hoist32<PLANE3>(const double* p, const double* c, const EstCfg&, float* q) {
+  q[0] = (float)p[0]; q[1] = (float)p[1]; q[2] = (float)p[2];
+  q[3] = (float)(-(p[0] * (p[3] - c[0]) + p[1] * (p[4] - c[1]) + p[2] * (p[5] - c[2])));
+}
+template <> __device__ __forceinline__ void hoist32<LINE2D>(const double* p, const double* c, const EstCfg&, float* q) {
+  q[0] = (float)p[0]; q[1] = (float)p[1];
+  q[2] = (float)(-(p[0] * (p[2] - c[0]) + p[1] * (p[3] - c[1])));
+}
+template <> __device__ __forceinline__ void hoist32<LINE2>(const double* p, const double* c, const EstCfg&, float* q) {
+  q[0] = (float)p[0]; q[1] = (float)p[1]; q[2] = (float)(p[2] - c[0]); q[3] = (float)(p[3] - c[1]);
+}
+template <> __device__ __forceinline__ void hoist32<LINE3>(const double* p, const double* c, const EstCfg&, float* q) {
+  for (int i = 0; i < 3; i++) { q[i] = (float)p[i]; q[3 + i] = (float)(p[3 + i] - c[i]); }
+}
+template <int DIM> __device__ __forceinline__ void hoist_sphere(const double* p, const double* c, const EstCfg& cfg, float* q) {
+  for (int i = 0; i < DIM; i++) q[i] = (float)(p[i] - c[i]);
+  const double r = p[DIM], dl = cfg.delta;
+  double m, w;
+  if (r >= dl) { m = r * r + dl * dl; w = 2.0 * r * dl; }
+  else { const double hi = (r + dl) * (r + dl); m = (hi - 1.0) * 0.5; w = (hi + 1.0) * 0.5; }  // interval (-1, hi): d^2 >= 0 has no lower bound
+  q[DIM] = (float)(-m); q[DIM + 1] = (float)(-(w * w));
+}
+template <> __device__ __forceinline__ void hoist32<CIRCLE2>(const double* p, const double* c, const EstCfg& cfg, float* q) { hoist_sphere<2>(p, c, cfg, q); }
+template <> __device__ __forceinline__ void hoist32<SPHERE3>(const double* p, const double* c, const EstCfg& cfg, float* q) { hoist_sphere<3>(p, c, cfg, q); }
+template <> __device__ __forceinline__ void hoist32<ABSOR>(const double* p, const double* c, const EstCfg&, float* q) {
+  double R[9];
+  quat_to_rot(p[0], p[1], p[2], p[3], R);
+  for (int i = 0; i < 9; i++) q[i] = (float)R[i];
+  for (int i = 0; i < 3; i++) q[9 + i] = (float)(R[3 * i] * c[0] + R[3 * i + 1] * c[1] + R[3 * i + 2] * c[2] + p[4 + i] - c[3 + i]);
+}
+template <> __device__ __forceinline__ void hoist32<RAY>(const double* p, const double* c, const EstCfg&, float* q) {
+  for (int i = 0; i < 3; i++) q[i] = (float)(p[i] - c[i]);
+}
+template <> __device__ __forceinline__ void hoist32<PIVOT>(const double* p, const double* c, const EstCfg&, float* q) {
+  for (int i = 0; i < 3; i++) { q[i] = (float)p[i]; q[3 + i] = (float)(p[3 + i] - c[9 + i]); }
+}
+
+template <int M>
+__global__ void hoist32_kernel(const double* __restrict__ hyp64, size_t hld, uint32_t H, DataView dv, EstCfg cfg, float* __restrict__ hyp32) {
+  constexpr int P = Model<M>::P, Q = Model<M>::Q32;
+  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  double prm[P], c[12];
+  float q[Q];
+#pragma unroll
+  for (int j = 0; j < P; j++) prm[j] = hyp64[(size_t)j * hld + h];
+#pragma unroll
+  for (int j = 0; j < 12; j++) c[j] = dv.center[j];
+  hoist32<M>(prm, c, cfg, q);
+  const bool ok = prm[0] == prm[0];
+#pragma unroll
+  for (int j = 0; j < Q; j++) hyp32[(size_t)j * hld + h] = ok ? q[j] : __int_as_float(0x7fc00000);
+}
+
+#define LSQR_DISPATCH_MODEL(model, CALL)      \
+  switch (model) {                            \
+    case PLANE3: { CALL(PLANE3); break; }     \
+    case LINE2D: { CALL(LINE2D); break; }     \
+    case LINE2: { CALL(LINE2); break; }       \
+    case LINE3: { CALL(LINE3); break; }       \
+    case CIRCLE2: { CALL(CIRCLE2); break; }   \
+    case SPHERE3: { CALL(SPHERE3); break; }   \
+    case ABSOR: { CALL(ABSOR); break; }       \
+    case RAY: { CALL(RAY); break; }           \
+    case PIVOT: { CALL(PIVOT); break; }       \
+    default: break;                           \
+  }
+
+void launch_hoist32(int model, const double* hyp64, size_t hld, uint32_t H, const DataView& dv, const EstCfg& cfg, float* hyp32, cudaStream_t s) {
+  if (H == 0) return;
+  const unsigned blocks = (H + 255) / 256;
+#define CALL(MM) hoist32_kernel<MM><<<blocks, 256, 0, s>>>(hyp64, hld, H, dv, cfg, hyp32)
+  LSQR_DISPATCH_MODEL(model, CALL)
+#undef CALL
+}
+
+// ---- per-model residual forms on point pairs ----------------------------------------------
+struct Thr2 { f2 delta, neg_delta2; float fdelta; };
+
+// signed(): g with inlier <=> g < 0.   For PLANE3 / LINE2D, dist(): s with inlier <=> |s| < delta.
+template <int M> struct Eval;
+template <> struct Eval<PLANE3> {
+  static constexpr bool kHasAbsForm = true;
+  __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return fma2(q[0], x[0], fma2(q[1], x[1], fma2(q[2], x[2], q[3]))); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
+};
+template <> struct Eval<LINE2D> {
+  static constexpr bool kHasAbsForm = true;
+  __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return fma2(q[0], x[0], fma2(q[1], x[1], q[2])); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
+};
+template <int DIM> __device__ __forceinline__ f2 line_signed(const f2* q, const f2* x, const Thr2& t) {
+  f2 v[DIM], vn;
+#pragma unroll
+  for (int i = 0; i < DIM; i++) v[i] = sub2(x[i], q[DIM + i]);
+  vn = mul2(v[0], q[0]);
+#pragma unroll
+  for (int i = 1; i < DIM; i++) vn = fma2(v[i], q[i], vn);
+  const f2 nvn = sub2(splat(0.f), vn);
+  f2 g = t.neg_delta2;
+#pragma unroll
+  for (int i = 0; i < DIM; i++) { const f2 w = fma2(nvn, q[i], v[i]); g = fma2(w, w, g); }
+  return g;
+}
+template <> struct Eval<LINE2> {
+  static constexpr bool kHasAbsForm = false;
+  __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { return line_signed<2>(q, x, t); }
+};
+template <> struct Eval<LINE3> {
+  static constexpr bool kHasAbsForm = false;
+  __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { return line_signed<3>(q, x, t); }
+};
+template <int DIM> __device__ __forceinline__ f2 sphere_signed(const f2* q, const f2* x) {
+  f2 t = q[DIM];  // -m
+#pragma unroll
+  for (int i = 0; i < DIM; i++) { const f2 w = sub2(x[i], q[i]); t = fma2(w, w, t); }
+  return fma2(t, t, q[DIM + 1]);  // (d^2 - m)^2 - w^2
+}
+template <> struct Eval<CIRCLE2> {
+  static constexpr bool kHasAbsForm = false;
+  __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2&) { return sphere_signed<2>(q, x); }
+};
+template <> struct Eval<SPHERE3> {
+  static constexpr bool kHasAbsForm = false;
+  __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2&) { return sphere_signed<3>(q, x); }
+};
+template <> struct Eval<ABSOR> {
+  static constexpr bool kHasAbsForm = false;
+  __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) {
+    f2 g = t.neg_delta2;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const f2 d = sub2(fma2(q[3 * i], x[0], fma2(q[3 * i + 1], x[1], fma2(q[3 * i + 2], x[2], q[9 + i]))), x[3 + i]);
+      g = fma2(d, d, g);
+    }
+    return g;
+  }
+};
+template <> struct Eval<RAY> {
+  static constexpr bool kHasAbsForm = false;
+  __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) {
+    const f2 vx = sub2(q[0], x[0]), vy = sub2(q[1], x[1]), vz = sub2(q[2], x[2]);
+    const f2 tt = fma2(x[3], vx, fma2(x[4], vy, mul2(x[5], vz)));
+    const f2 ntt = sub2(splat(0.f), tt);
+    const f2 dx = fma2(ntt, x[3], vx), dy = fma2(ntt, x[4], vy), dz = fma2(ntt, x[5], vz);
+    const f2 g = fma2(dx, dx, fma2(dy, dy, fma2(dz, dz, t.neg_delta2)));
+    // t >= 0 && dist^2 < delta^2  <=>  max(g, -t) < 0; with NaN padding the compare fails and the (positive) NaN -t is kept
+    float g0, g1, n0, n1;
+    halves(g, g0, g1); halves(ntt, n0, n1);
+    return join(g0 > n0 ? g0 : n0, g1 > n1 ? g1 : n1);
+  }
+};
+template <> struct Eval<PIVOT> {
+  static constexpr bool kHasAbsForm = false;
+  __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) {
+    f2 g = t.neg_delta2;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const f2 d = sub2(fma2(x[3 * i], q[0], fma2(x[3 * i + 1], q[1], fma2(x[3 * i + 2], q[2], x[9 + i]))), q[3 + i]);
+      g = fma2(d, d, g);
+    }
+    return g;
+  }
+};
+
+// FSETP + predicated IADD on two residuals, written in PTX so that ptxas keeps the 2-instruction form.
+__device__ __forceinline__ void count_abs_lt(uint32_t& cnt, f2 s, float delta) {
+  float a, b;
+  halves(s, a, b);
+  asm("{\n\t.reg .pred p0, p1;\n\t"
+      "setp.lt.f32 p0, %1, %3;\n\tsetp.lt.f32 p1, %2, %3;\n\t"
+      "@p0 add.u32 %0, %0, 1;\n\t@p1 add.u32 %0, %0, 1;\n\t}"
+      : "+r"(cnt) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(delta));
+}
+__device__ __forceinline__ void count_sign(uint32_t& cnt, f2 g) {
+  float a, b;
+  halves(g, a, b);
+  cnt += __float_as_uint(a) >> 31;
+  cnt += __float_as_uint(b) >> 31;
+}
+
+// PPI = point pairs per inner iteration (2 -> one LDS.128 per component, 1 -> one LDS.64)
+template <int M, int R, int THREADS, int TILE, int PPI>
+__global__ void __launch_bounds__(THREADS) consensus32_kernel(const float* __restrict__ soa, size_t ld, uint32_t tiles_total, uint32_t tiles_per_chunk,
+                                                               const float* __restrict__ hyp, size_t hld, uint32_t H, float delta, float delta2,
+                                                               uint32_t* __restrict__ counts) {
+  constexpr int D = Model<M>::D, Q = Model<M>::Q32;
+  constexpr uint32_t kTileBytes = (uint32_t)(TILE * sizeof(float));
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* tile0 = reinterpret_cast<float*>(smem_raw);
+  float* tile1 = tile0 + D * TILE;
+  __shared__ __align__(8) uint64_t bars[2];
+
+  const int tid = threadIdx.x;
+  const uint32_t hbase = blockIdx.x * (THREADS * R);
+  f2 q[R][Q];
+  uint32_t cnt[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const uint32_t h = hbase + r * THREADS + tid;
+#pragma unroll
+    for (int j = 0; j < Q; j++) q[r][j] = splat((h < H) ? hyp[(size_t)j * hld + h] : __int_as_float(0x7fc00000));
+    cnt[r] = 0;
+  }
+  Thr2 thr;
+  thr.delta = splat(delta); thr.neg_delta2 = splat(-delta2); thr.fdelta = delta;
+
+  const uint32_t t0 = blockIdx.y * tiles_per_chunk;
+  const uint32_t t1 = min(t0 + tiles_per_chunk, tiles_total);
+  if (tid == 0) { mbarrier_init(&bars[0], 1); mbarrier_init(&bars[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  auto issue = [&](uint32_t t, int buf) {
+    float* dst = buf ? tile1 : tile0;
+    mbarrier_expect_tx(&bars[buf], kTileBytes * D);
+#pragma unroll
+    for (int d = 0; d < D; d++) tma_load_1d(dst + d * TILE, soa + (size_t)d * ld + (size_t)t * TILE, kTileBytes, &bars[buf]);
+  };
+  if (tid == 0 && t0 < t1) issue(t0, 0);
+  uint32_t phase0 = 0, phase1 = 0;
+  for (uint32_t t = t0; t < t1; t++) {
+    const int buf = (t - t0) & 1;
+    if (tid == 0 && t + 1 < t1) issue(t + 1, buf ^ 1);
+    if (buf) { mbarrier_wait(&bars[1], phase1); phase1 ^= 1; } else { mbarrier_wait(&bars[0], phase0); phase0 ^= 1; }
+    const float* tl = buf ? tile1 : tile0;
+#pragma unroll 1
+    for (int i = 0; i < TILE; i += 2 * PPI) {
+      f2 x[PPI][D];
+#pragma unroll
+      for (int d = 0; d < D; d++) {
+        if constexpr (PPI == 2) {
+          const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(tl + d * TILE + i);
+          x[0][d].v = v.x; x[1][d].v = v.y;
+        } else {
+          x[0][d].v = *reinterpret_cast<const unsigned long long*>(tl + d * TILE + i);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+#pragma unroll
+        for (int u = 0; u < PPI; u++) {
+          if (Eval<M>::kHasAbsForm && (r % 3) != 0) count_abs_lt(cnt[r], Eval<M>::dist(q[r], x[u]), thr.fdelta);
+          else count_sign(cnt[r], Eval<M>::signed_(q[r], x[u], thr));
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with this buffer before it is refilled
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const uint32_t h = hbase + r * THREADS + tid;
+    if (h < H && cnt[r]) atomicAdd(&counts[h], cnt[r]);
+  }
+}
+
+template <int M, int R, int THREADS, int TILE, int PPI>
+static int run_consensus32(const DataView& dv, const float* hyp, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms, cudaStream_t s) {
+  const uint32_t tiles_total = (uint32_t)(dv.ld / TILE);
+  const uint32_t hyp_blocks = (H + THREADS * R - 1) / (THREADS * R);
+  uint32_t want = (uint32_t)num_sms * 16;  // ~16 work items per SM for load balance
+  uint32_t chunks = (want + hyp_blocks - 1) / hyp_blocks;
+  uint32_t max_chunks = (tiles_total + 3) / 4;
+  if (max_chunks == 0) max_chunks = 1;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks > 65535) chunks = 65535;
+  if (chunks == 0) chunks = 1;
+  const uint32_t tiles_per_chunk = (tiles_total + chunks - 1) / chunks;
+  chunks = (tiles_total + tiles_per_chunk - 1) / tiles_per_chunk;
+  const size_t smem = 2 * (size_t)Model<M>::D * TILE * sizeof(float);
+  auto kern = consensus32_kernel<M, R, THREADS, TILE, PPI>;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  kern<<<dim3(hyp_blocks, chunks), THREADS, smem, s>>>(dv.soa32, dv.ld, tiles_total, tiles_per_chunk, hyp, hld, H, (float)cfg.delta, (float)cfg.delta2, counts);
+  return 1;
+}
+
+// Register blocking per model: R hypotheses per thread sized so that 2*Q32*R duplicated constants
+// plus the point pairs stay below ~128 registers at 256 threads.
+template <int M> struct Block32 { static constexpr int R = 6, PPI = 2; };
+template <> struct Block32<PLANE3> { static constexpr int R = 9, PPI = 2; };
+template <> struct Block32<LINE2D> { static constexpr int R = 9, PPI = 2; };
+template <> struct Block32<LINE2> { static constexpr int R = 8, PPI = 2; };
+template <> struct Block32<LINE3> { static constexpr int R = 6, PPI = 2; };
+template <> struct Block32<CIRCLE2> { static constexpr int R = 8, PPI = 2; };
+template <> struct Block32<SPHERE3> { static constexpr int R = 8, PPI = 2; };
+template <> struct Block32<ABSOR> { static constexpr int R = 3, PPI = 1; };
+template <> struct Block32<RAY> { static constexpr int R = 8, PPI = 1; };
+template <> struct Block32<PIVOT> { static constexpr int R = 4, PPI = 1; };
+
+int launch_consensus32(int model, const DataView& dv, const float* hyp32, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms,
+                       cudaStream_t s) {
+  if (H == 0 || dv.n == 0) return 0;
+#define CALL(MM)                                                                                                        \
+  if (H <= 8192) return run_consensus32<MM, 1, 128, 512, Block32<MM>::PPI>(dv, hyp32, hld, H, cfg, counts, num_sms, s);  \
+  return run_consensus32<MM, Block32<MM>::R, 256, 512, Block32<MM>::PPI>(dv, hyp32, hld, H, cfg, counts, num_sms, s)
+  LSQR_DISPATCH_MODEL(model, CALL)
+#undef CALL
+  return 0;
+}
+
+}  // namespace lsqr

@@ -10,8 +10,8 @@
 //   * Inside a tile every thread reads the same point (shared-memory broadcast, vector loads of
 //     UNR consecutive points) and evaluates agree() for its R hypotheses.
 //   * Per-hypothesis counts go to global memory with one atomicAdd per (hypothesis, chunk).
-// fp64 mode evaluates models.cuh's reference-order agree(); fp32 mode evaluates the fused,
-// constant-hoisted forms below (fmaf explicit; the TU is built with -fmad=false).
+// This TU holds the fp64 validation mode (models.cuh's reference-order agree()); the fp32 fast
+// mode lives in k_fast.cu.
 // Tensor cores are deliberately unused: the contraction depth is <= 4 (BASELINE.json north_star).
 #include "engine.h"
 
@@ -177,129 +177,6 @@ void launch_solve(const SolveArgs& a, const DataView& dv, const EstCfg& cfg, cud
 #undef CALL
 }
 
-// ---------------------------------------------------------------------------------------
-// fp32 fast forms.  A hoisted hypothesis is Q32 floats computed once in fp64 from the raw
-// parameters and the data centre c (positions are stored as x - c in fp32):
-//   PLANE3   (nx,ny,nz, -n.(a-c))             |fma chain| < delta            3 FFMA
-//   LINE2D   (nx,ny, -n.(a-c))                                                2 FFMA
-//   LINE2/3  (dir, a-c)                       |v - (v.n)n|^2 < delta^2
-//   CIRCLE/SPHERE (ctr-c, m, w)               | |x-ctr|^2 - m | < w  with m = r^2+delta^2, w = 2 r delta
-//                                             (sqrt-free two-sided test of |d - r| < delta)
-//   ABSOR    (R[9], R c1 + t - c2)            |R x1 + t' - x2|^2 < delta^2
-//   RAY      (x - c)                          t >= 0 && |x - p - t n|^2 < delta^2
-//   PIVOT    (tDRF, tW - c)                   |R tDRF + t - tW|^2 < delta^2
-// ---------------------------------------------------------------------------------------
-template <int M> __device__ __forceinline__ void hoist32(const double* prm, const double* c, const EstCfg& cfg, float* q);
-template <> __device__ __forceinline__ void hoist32<PLANE3>(const double* p, const double* c, const EstCfg&, float* q) {
-  q[0] = (float)p[0]; q[1] = (float)p[1]; q[2] = (float)p[2];
-  q[3] = (float)(-(p[0] * (p[3] - c[0]) + p[1] * (p[4] - c[1]) + p[2] * (p[5] - c[2])));
-}
-template <> __device__ __forceinline__ void hoist32<LINE2D>(const double* p, const double* c, const EstCfg&, float* q) {
-  q[0] = (float)p[0]; q[1] = (float)p[1];
-  q[2] = (float)(-(p[0] * (p[2] - c[0]) + p[1] * (p[3] - c[1])));
-}
-template <> __device__ __forceinline__ void hoist32<LINE2>(const double* p, const double* c, const EstCfg&, float* q) {
-  q[0] = (float)p[0]; q[1] = (float)p[1]; q[2] = (float)(p[2] - c[0]); q[3] = (float)(p[3] - c[1]);
-}
-template <> __device__ __forceinline__ void hoist32<LINE3>(const double* p, const double* c, const EstCfg&, float* q) {
-  for (int i = 0; i < 3; i++) { q[i] = (float)p[i]; q[3 + i] = (float)(p[3 + i] - c[i]); }
-}
-template <int DIM> __device__ __forceinline__ void hoist_sphere(const double* p, const double* c, const EstCfg& cfg, float* q) {
-  for (int i = 0; i < DIM; i++) q[i] = (float)(p[i] - c[i]);
-  const double r = p[DIM], dl = cfg.delta;
-  double m, w;
-  if (r >= dl) { m = r * r + dl * dl; w = 2.0 * r * dl; }
-  else { const double hi = (r + dl) * (r + dl); m = (hi - 1.0) * 0.5; w = (hi + 1.0) * 0.5; }  // interval (-1, hi): no lower bound on d^2 >= 0
-  q[DIM] = (float)m; q[DIM + 1] = (float)w;
-}
-template <> __device__ __forceinline__ void hoist32<CIRCLE2>(const double* p, const double* c, const EstCfg& cfg, float* q) { hoist_sphere<2>(p, c, cfg, q); }
-template <> __device__ __forceinline__ void hoist32<SPHERE3>(const double* p, const double* c, const EstCfg& cfg, float* q) { hoist_sphere<3>(p, c, cfg, q); }
-template <> __device__ __forceinline__ void hoist32<ABSOR>(const double* p, const double* c, const EstCfg&, float* q) {
-  double R[9];
-  quat_to_rot(p[0], p[1], p[2], p[3], R);
-  for (int i = 0; i < 9; i++) q[i] = (float)R[i];
-  for (int i = 0; i < 3; i++) q[9 + i] = (float)(R[3 * i] * c[0] + R[3 * i + 1] * c[1] + R[3 * i + 2] * c[2] + p[4 + i] - c[3 + i]);
-}
-template <> __device__ __forceinline__ void hoist32<RAY>(const double* p, const double* c, const EstCfg&, float* q) {
-  for (int i = 0; i < 3; i++) q[i] = (float)(p[i] - c[i]);
-}
-template <> __device__ __forceinline__ void hoist32<PIVOT>(const double* p, const double* c, const EstCfg&, float* q) {
-  for (int i = 0; i < 3; i++) { q[i] = (float)p[i]; q[3 + i] = (float)(p[3 + i] - c[9 + i]); }
-}
-
-template <int M>
-__global__ void hoist32_kernel(const double* __restrict__ hyp64, size_t hld, uint32_t H, DataView dv, EstCfg cfg, float* __restrict__ hyp32) {
-  constexpr int P = Model<M>::P, Q = Model<M>::Q32;
-  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= H) return;
-  double prm[P], c[12];
-  float q[Q];
-#pragma unroll
-  for (int j = 0; j < P; j++) prm[j] = hyp64[(size_t)j * hld + h];
-#pragma unroll
-  for (int j = 0; j < 12; j++) c[j] = dv.center[j];
-  hoist32<M>(prm, c, cfg, q);
-  const bool ok = prm[0] == prm[0];
-#pragma unroll
-  for (int j = 0; j < Q; j++) hyp32[(size_t)j * hld + h] = ok ? q[j] : __int_as_float(0x7fc00000);
-}
-void launch_hoist32(int model, const double* hyp64, size_t hld, uint32_t H, const DataView& dv, const EstCfg& cfg, float* hyp32, cudaStream_t s) {
-  if (H == 0) return;
-  const unsigned blocks = (H + 255) / 256;
-#define CALL(MM) hoist32_kernel<MM><<<blocks, 256, 0, s>>>(hyp64, hld, H, dv, cfg, hyp32)
-  LSQR_DISPATCH_MODEL(model, CALL)
-#undef CALL
-}
-
-// fp32 thresholds handed to the kernel
-struct Thr32 { float delta, delta2; };
-
-template <int M> __device__ __forceinline__ bool agree32(const float* q, const float* x, const Thr32& t);
-template <> __device__ __forceinline__ bool agree32<PLANE3>(const float* q, const float* x, const Thr32& t) {
-  const float s = fmaf(q[0], x[0], fmaf(q[1], x[1], fmaf(q[2], x[2], q[3])));
-  return fabsf(s) < t.delta;
-}
-template <> __device__ __forceinline__ bool agree32<LINE2D>(const float* q, const float* x, const Thr32& t) {
-  const float s = fmaf(q[0], x[0], fmaf(q[1], x[1], q[2]));
-  return fabsf(s) < t.delta;
-}
-template <int DIM> __device__ __forceinline__ bool agree32_line(const float* q, const float* x, const Thr32& t) {
-  float v[DIM], vn = 0.f, ds = 0.f;
-#pragma unroll
-  for (int i = 0; i < DIM; i++) { v[i] = x[i] - q[DIM + i]; vn = fmaf(v[i], q[i], vn); }
-#pragma unroll
-  for (int i = 0; i < DIM; i++) { const float w = fmaf(-vn, q[i], v[i]); ds = fmaf(w, w, ds); }
-  return ds < t.delta2;
-}
-template <> __device__ __forceinline__ bool agree32<LINE2>(const float* q, const float* x, const Thr32& t) { return agree32_line<2>(q, x, t); }
-template <> __device__ __forceinline__ bool agree32<LINE3>(const float* q, const float* x, const Thr32& t) { return agree32_line<3>(q, x, t); }
-template <int DIM> __device__ __forceinline__ bool agree32_sphere(const float* q, const float* x, const Thr32&) {
-  float d2 = 0.f;
-#pragma unroll
-  for (int i = 0; i < DIM; i++) { const float w = x[i] - q[i]; d2 = fmaf(w, w, d2); }
-  return fabsf(d2 - q[DIM]) < q[DIM + 1];
-}
-template <> __device__ __forceinline__ bool agree32<CIRCLE2>(const float* q, const float* x, const Thr32& t) { return agree32_sphere<2>(q, x, t); }
-template <> __device__ __forceinline__ bool agree32<SPHERE3>(const float* q, const float* x, const Thr32& t) { return agree32_sphere<3>(q, x, t); }
-template <> __device__ __forceinline__ bool agree32<ABSOR>(const float* q, const float* x, const Thr32& t) {
-  const float dx = fmaf(q[0], x[0], fmaf(q[1], x[1], fmaf(q[2], x[2], q[9]))) - x[3];
-  const float dy = fmaf(q[3], x[0], fmaf(q[4], x[1], fmaf(q[5], x[2], q[10]))) - x[4];
-  const float dz = fmaf(q[6], x[0], fmaf(q[7], x[1], fmaf(q[8], x[2], q[11]))) - x[5];
-  return fmaf(dx, dx, fmaf(dy, dy, dz * dz)) < t.delta2;
-}
-template <> __device__ __forceinline__ bool agree32<RAY>(const float* q, const float* x, const Thr32& t) {
-  const float vx = q[0] - x[0], vy = q[1] - x[1], vz = q[2] - x[2];
-  const float tt = fmaf(x[3], vx, fmaf(x[4], vy, x[5] * vz));
-  const float dx = fmaf(-tt, x[3], vx), dy = fmaf(-tt, x[4], vy), dz = fmaf(-tt, x[5], vz);
-  return tt >= 0.f && fmaf(dx, dx, fmaf(dy, dy, dz * dz)) < t.delta2;
-}
-template <> __device__ __forceinline__ bool agree32<PIVOT>(const float* q, const float* x, const Thr32& t) {
-  const float dx = fmaf(x[0], q[0], fmaf(x[1], q[1], fmaf(x[2], q[2], x[9]))) - q[3];
-  const float dy = fmaf(x[3], q[0], fmaf(x[4], q[1], fmaf(x[5], q[2], x[10]))) - q[4];
-  const float dz = fmaf(x[6], q[0], fmaf(x[7], q[1], fmaf(x[8], q[2], x[11]))) - q[5];
-  return fmaf(dx, dx, fmaf(dy, dy, dz * dz)) < t.delta2;
-}
-
 // Traits binding the generic consensus kernel to one (model, precision).
 template <int M> struct Exact {
   using real = double;
@@ -308,17 +185,6 @@ template <int M> struct Exact {
   __device__ static __forceinline__ void load(const double* raw, double* hq) { prepare<M>(raw, hq); }
   __device__ static __forceinline__ bool test(const double* hq, const double* x, const EstCfg& t) { return agree<M>(hq, x, t); }
 };
-template <int M> struct Fast {
-  using real = float;
-  using thr_t = Thr32;
-  static constexpr int D = Model<M>::D, NIN = Model<M>::Q32, HQ = Model<M>::Q32, UNR = 4;
-  __device__ static __forceinline__ void load(const float* raw, float* hq) {
-#pragma unroll
-    for (int i = 0; i < HQ; i++) hq[i] = raw[i];
-  }
-  __device__ static __forceinline__ bool test(const float* hq, const float* x, const Thr32& t) { return agree32<M>(hq, x, t); }
-};
-
 template <class T, int R, int THREADS, int TILE>
 __global__ void __launch_bounds__(THREADS) consensus_kernel(const typename T::real* __restrict__ soa, size_t ld, uint32_t tiles_total, uint32_t tiles_per_chunk,
                                                              const typename T::real* __restrict__ hyp, size_t hld, uint32_t H, typename T::thr_t thr,
@@ -425,14 +291,7 @@ int launch_consensus(int model, int precision, const DataView& dv, const double*
     LSQR_DISPATCH_MODEL(model, CALL)
 #undef CALL
   } else {
-    Thr32 t;
-    t.delta = (float)cfg.delta;
-    t.delta2 = (float)cfg.delta2;
-#define CALL(MM)                                                                                                             \
-  if (H <= 8192) return run_consensus<Fast<MM>, 1, 128, 512>(dv.soa32, dv.ld, hyp32, hld, H, t, counts, num_sms, s);          \
-  return run_consensus<Fast<MM>, (Model<MM>::Q32 >= 12 ? 4 : 8), 256, 512>(dv.soa32, dv.ld, hyp32, hld, H, t, counts, num_sms, s)
-    LSQR_DISPATCH_MODEL(model, CALL)
-#undef CALL
+    return launch_consensus32(model, dv, hyp32, hld, H, cfg, counts, num_sms, s);
   }
   return 0;
 }

@@ -222,7 +222,7 @@ def test_randomized_compute_end_to_end(port, name, m, precision):
     eng = Engine(name, delta)
     eng.upload(data)
     r = eng.ransac(0.999, precision=precision, seed=11)
-    assert r["fraction"] > 0.4 and r["tries"] >= 1
+    assert r["fraction"] > 0.3 and r["tries"] >= 1
     mask = r["mask"].astype(bool)
     assert mask.sum() == r["best_count"] and abs(r["fraction"] - mask.sum() / n) < 1e-15
     want = port.least_squares(m, delta, data[mask], 1)
