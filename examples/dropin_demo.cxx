@@ -1,0 +1,236 @@
+// Exercises the drop-in C++ headers (include/lsqrRecipes/) the way the reference's examples and tests
+// use the originals (e.g. examples/planeEstimation.cxx:105-118, testing/PlaneParametersEstimatorTest.cxx):
+// build an estimator, call estimate / agree / leastSquaresEstimate directly, then
+// RANSAC<T,double>::compute(parameters, &estimator, data, 0.999, &consensus) and the exhaustive overload.
+// Everything runs on the GPU through liblsqr_b200.so.  Exit code 0 = every check passed.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <utility>
+#include <vector>
+
+#include "lsqrRecipes/AbsoluteOrientationParametersEstimator.h"
+#include "lsqrRecipes/Line2DParametersEstimator.h"
+#include "lsqrRecipes/LineParametersEstimator.h"
+#include "lsqrRecipes/PivotCalibrationParametersEstimator.h"
+#include "lsqrRecipes/PlaneParametersEstimator.h"
+#include "lsqrRecipes/RANSAC.h"
+#include "lsqrRecipes/RayIntersectionParametersEstimator.h"
+#include "lsqrRecipes/SphereParametersEstimator.h"
+
+using namespace lsqrRecipes;
+
+static int failures = 0;
+#define CHECK(cond, what)                                                        \
+  do {                                                                           \
+    if (!(cond)) { std::printf("  FAIL: %s (%s)\n", what, b200LastError()); failures++; } \
+  } while (0)
+
+static std::mt19937_64 rng(20261017);
+static double uni(double a, double b) { return std::uniform_real_distribution<double>(a, b)(rng); }
+static double gauss(double s) { return std::normal_distribution<double>(0.0, s)(rng); }
+
+static void planeCase() {
+  std::printf("PlaneParametersEstimator<3>\n");
+  double n[3] = {uni(0, 1), uni(0, 1), uni(0, 1)};
+  const double nn = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+  for (int i = 0; i < 3; i++) n[i] /= nn;
+  double a[3] = {uni(-1000, 1000), uni(-1000, 1000), uni(-1000, 1000)};
+  std::vector<Point3D> data;
+  for (int i = 0; i < 100000; i++) {
+    Point3D p;
+    for (int j = 0; j < 3; j++) p[j] = uni(-1000, 1000);
+    if (i % 10 < 6) {  // 60% inliers: project on the plane, add noise
+      double s = 0;
+      for (int j = 0; j < 3; j++) s += (p[j] - a[j]) * n[j];
+      for (int j = 0; j < 3; j++) p[j] += -s * n[j] + gauss(0.4);
+    }
+    data.push_back(p);
+  }
+  PlaneParametersEstimator<3> est(0.5);
+  std::vector<double> prm;
+  std::vector<Point3D> three(data.begin(), data.begin() + 3);
+  est.estimate(three, prm);
+  CHECK(prm.size() == 6, "estimate() returns 6 parameters");
+  CHECK(est.agree(prm, three[0]) && est.agree(prm, three[2]), "defining points agree with the exact estimate");
+  std::vector<Point3D> two(data.begin(), data.begin() + 2);
+  est.estimate(two, prm);
+  CHECK(prm.empty(), "too few points -> empty parameters");
+  std::vector<bool> consensus;
+  const double frac = RANSAC<Point3D, double>::compute(prm, &est, data, 0.999, &consensus);
+  CHECK(prm.size() == 6 && consensus.size() == data.size(), "RANSAC::compute fills parameters and consensus set");
+  if (prm.size() != 6) return;
+  const double dot = std::fabs(prm[0] * n[0] + prm[1] * n[1] + prm[2] * n[2]);
+  double off = 0;
+  for (int j = 0; j < 3; j++) off += (prm[3 + j] - a[j]) * n[j];
+  std::printf("  fraction %.4f  |n.n_true| %.9f  point offset %.4g\n", frac, dot, off);
+  CHECK(frac > 0.45 && frac < 0.50, "inlier fraction near 0.6 * P(|N(0,0.4)| < 0.5)");
+  CHECK(dot > 1 - 1e-6 && std::fabs(off) < 0.1, "refined plane matches the generating plane");
+  // invalid input: returns 0 and leaves the vector untouched (RANSAC.hxx:16-19)
+  std::vector<double> keep(2, 7.0);
+  CHECK((RANSAC<Point3D, double>::compute(keep, &est, data, 1.5) == 0.0) && keep.size() == 2, "probability outside (0,1) -> 0, parameters untouched");
+  CHECK((RANSAC<Point3D, double>::compute(keep, &est, two, 0.9) == 0.0) && keep.size() == 2, "too few data -> 0, parameters untouched");
+  // exhaustive overload on a small subset
+  std::vector<Point3D> small(data.begin(), data.begin() + 40);
+  std::vector<double> prm2;
+  const double f2 = RANSAC<Point3D, double>::compute(prm2, &est, small, &consensus);
+  CHECK(prm2.size() == 6 && f2 > 0.3, "exhaustive overload");
+}
+
+static void line2dCase() {
+  std::printf("Line2DParametersEstimator / LineParametersEstimator<2>\n");
+  const double ang = uni(0, 3.1), dx = std::cos(ang), dy = std::sin(ang), ax = uni(-100, 100), ay = uni(-100, 100);
+  std::vector<Point2D> data;
+  for (int i = 0; i < 20000; i++) {
+    Point2D p;
+    if (i % 10 < 7) { const double s = uni(-1000, 1000); p[0] = ax + s * dx + gauss(0.3); p[1] = ay + s * dy + gauss(0.3); }
+    else { p[0] = uni(-1000, 1000); p[1] = uni(-1000, 1000); }
+    data.push_back(p);
+  }
+  Line2DParametersEstimator est(0.5);
+  std::vector<double> prm;
+  double frac = RANSAC<Point2D, double>::compute(prm, &est, data, 0.999);
+  CHECK(prm.size() == 4 && frac > 0.5, "Line2D RANSAC");
+  if (prm.size() == 4) CHECK(std::fabs(prm[0] * dx + prm[1] * dy) < 1e-4, "normal is perpendicular to the generating direction");
+  LineParametersEstimator<2> est2(0.5);
+  frac = RANSAC<Point2D, double>::compute(prm, &est2, data, 0.999);
+  CHECK(prm.size() == 4 && frac > 0.5, "Line<2> RANSAC");
+  if (prm.size() == 4) CHECK(std::fabs(std::fabs(prm[0] * dx + prm[1] * dy) - 1) < 1e-6, "direction matches");
+}
+
+static void sphereCase() {
+  std::printf("SphereParametersEstimator<3>\n");
+  const double c[3] = {uni(-500, 500), uni(-500, 500), uni(-500, 500)}, r = uni(100, 500);
+  std::vector<Point3D> data;
+  for (int i = 0; i < 50000; i++) {
+    Point3D p;
+    if (i % 10 < 6) {
+      double u[3] = {uni(-1, 1), uni(-1, 1), uni(-1, 1)};
+      const double un = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+      for (int j = 0; j < 3; j++) p[j] = c[j] + r * u[j] / un + gauss(0.4);
+    } else for (int j = 0; j < 3; j++) p[j] = uni(-1000, 1000);
+    data.push_back(p);
+  }
+  for (int geo = 0; geo < 2; geo++) {
+    SphereParametersEstimator<3> est(0.5, geo ? SphereParametersEstimator<3>::GEOMETRIC : SphereParametersEstimator<3>::ALGEBRAIC);
+    std::vector<double> prm;
+    const double frac = RANSAC<Point3D, double>::compute(prm, &est, data, 0.999);
+    CHECK(prm.size() == 4 && frac > 0.2, geo ? "sphere RANSAC, geometric LS (Levenberg-Marquardt)" : "sphere RANSAC, algebraic LS");
+    if (prm.size() == 4) {
+      const double e = std::fabs(prm[0] - c[0]) + std::fabs(prm[1] - c[1]) + std::fabs(prm[2] - c[2]) + std::fabs(prm[3] - r);
+      std::printf("  %s: fraction %.4f  |error|_1 %.4g\n", geo ? "geometric" : "algebraic", frac, e);
+      CHECK(e < 0.5, "refined sphere matches the generating sphere");
+    }
+  }
+  bool threw = false;
+  try { SphereParametersEstimator<3> bad(0.5, static_cast<SphereParametersEstimator<3>::LeastSquaresType>(7)); } catch (std::exception&) { threw = true; }
+  CHECK(threw, "invalid least-squares type throws from the constructor (SphereParametersEstimator.hxx:17-18)");
+}
+
+static void absorCase() {
+  std::printf("AbsoluteOrientationParametersEstimator\n");
+  Frame T(uni(-1000, 1000), uni(-1000, 1000), uni(-1000, 1000), 0.5, 0.5, -0.5, 0.5, true);
+  typedef std::pair<Point3D, Point3D> Pair;
+  std::vector<Pair> data;
+  for (int i = 0; i < 30000; i++) {
+    Pair pr;
+    for (int j = 0; j < 3; j++) pr.first[j] = uni(-100, 100);
+    T.apply(pr.first, pr.second);
+    for (int j = 0; j < 3; j++) pr.second[j] += gauss(1.0);
+    if (i % 10 >= 7) for (int j = 0; j < 3; j++) pr.second[j] = uni(-1100, 1100);
+    data.push_back(pr);
+  }
+  AbsoluteOrientationParametersEstimator est(2.0);
+  std::vector<double> prm;
+  const double frac = RANSAC<Pair, double>::compute(prm, &est, data, 0.999);
+  CHECK(prm.size() == 7 && frac > 0.3, "absolute orientation RANSAC");
+  if (prm.size() == 7) {
+    Frame E(prm[4], prm[5], prm[6], prm[0], prm[1], prm[2], prm[3], true);
+    double worst = 0;
+    for (int i = 0; i < 100; i++) {
+      Point3D a, b;
+      T.apply(data[i].first, a);
+      E.apply(data[i].first, b);
+      worst = std::fmax(worst, std::sqrt(a.distanceSquared(b)));
+    }
+    std::printf("  fraction %.4f  max target registration error %.4g\n", frac, worst);
+    CHECK(worst < 0.5, "estimated transformation maps points like the generating one");
+  }
+}
+
+static void rayCase() {
+  std::printf("RayIntersectionParametersEstimator\n");
+  const double x[3] = {uni(-50, 50), uni(-50, 50), uni(-50, 50)};
+  std::vector<Ray3D> data;
+  for (int i = 0; i < 20000; i++) {
+    Ray3D ray;
+    double t[3];
+    for (int j = 0; j < 3; j++) { ray.p[j] = uni(-1000, 1000); t[j] = (i % 10 < 7) ? x[j] + gauss(0.3) : uni(-1000, 1000); }
+    double nn = 0;
+    for (int j = 0; j < 3; j++) { ray.n[j] = t[j] - ray.p[j]; nn += ray.n[j] * ray.n[j]; }
+    for (int j = 0; j < 3; j++) ray.n[j] /= std::sqrt(nn);
+    data.push_back(ray);
+  }
+  RayIntersectionParametersEstimator est(1.0);
+  std::vector<double> prm;
+  const double frac = RANSAC<Ray3D, double>::compute(prm, &est, data, 0.999);
+  CHECK(prm.size() == 3 && frac > 0.5, "ray intersection RANSAC");
+  if (prm.size() == 3) CHECK(std::fabs(prm[0] - x[0]) + std::fabs(prm[1] - x[1]) + std::fabs(prm[2] - x[2]) < 0.05, "intersection point recovered");
+}
+
+static void pivotCase() {
+  std::printf("PivotCalibrationEstimator\n");
+  const double tdrf[3] = {uni(-200, 200), uni(-200, 200), uni(-200, 200)}, tw[3] = {uni(-1000, 1000), uni(-1000, 1000), uni(-1000, 1000)};
+  std::vector<Frame> data;
+  for (int i = 0; i < 5000; i++) {
+    double q[4] = {gauss(1), gauss(1), gauss(1), gauss(1)};
+    Frame f(0, 0, 0, q[0], q[1], q[2], q[3], true);
+    Point3D p, rp;
+    for (int j = 0; j < 3; j++) p[j] = tdrf[j];
+    f.apply(p, rp);  // R tDRF
+    double t[3];
+    for (int j = 0; j < 3; j++) t[j] = tw[j] - rp[j] + gauss(0.2) + ((i % 10 >= 8) ? uni(-50, 50) : 0.0);
+    f.setTranslation(t);
+    data.push_back(f);
+  }
+  PivotCalibrationEstimator est(1.0);
+  std::vector<double> prm;
+  const double frac = RANSAC<Frame, double>::compute(prm, &est, data, 0.999);
+  CHECK(prm.size() == 6 && frac > 0.6, "pivot calibration RANSAC");
+  if (prm.size() == 6) {
+    double e = 0;
+    for (int j = 0; j < 3; j++) e += std::fabs(prm[j] - tdrf[j]) + std::fabs(prm[3 + j] - tw[j]);
+    std::printf("  fraction %.4f  |error|_1 %.4g\n", frac, e);
+    CHECK(e < 0.2, "pivot translations recovered");
+  }
+}
+
+// A user-defined estimator has no GPU path: same failure convention as a degenerate data set.
+class UserEstimator : public ParametersEstimator<Point2D, double> {
+ public:
+  UserEstimator() : ParametersEstimator<Point2D, double>(2) {}
+  virtual void estimate(std::vector<Point2D*>&, std::vector<double>& p) { p.clear(); }
+  virtual void estimate(std::vector<Point2D>&, std::vector<double>& p) { p.clear(); }
+  virtual void leastSquaresEstimate(std::vector<Point2D*>&, std::vector<double>& p) { p.clear(); }
+  virtual void leastSquaresEstimate(std::vector<Point2D>&, std::vector<double>& p) { p.clear(); }
+  virtual bool agree(std::vector<double>&, Point2D&) { return false; }
+};
+
+int main() {
+  if (!b200::context()) { std::printf("no GPU context: %s\n", b200LastError()); return 2; }
+  planeCase();
+  line2dCase();
+  sphereCase();
+  absorCase();
+  rayCase();
+  pivotCase();
+  std::printf("user-defined estimator\n");
+  UserEstimator user;
+  std::vector<Point2D> pts(10);
+  std::vector<double> prm(1, 3.0);
+  CHECK((RANSAC<Point2D, double>::compute(prm, &user, pts, 0.9) == 0.0) && prm.empty(), "no GPU path -> 0 and empty parameters, no fallback");
+  std::printf("  (%s)\n", b200LastError());
+  std::printf(failures ? "FAILED: %d check(s)\n" : "ALL CHECKS PASSED\n", failures);
+  return failures ? EXIT_FAILURE : EXIT_SUCCESS;
+}

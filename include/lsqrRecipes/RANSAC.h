@@ -1,0 +1,83 @@
+// Drop-in counterpart of parametersEstimators/RANSAC.{h,hxx} of zivy/LSQRRecipes (re-authored).
+// Same namespace, class template and the same two static entry points (RANSAC.h:75-79 and
+// :111-113); the bodies (RANSAC.hxx:4-249) are replaced by calls into liblsqr_b200.so:
+//
+//   reference (host, one thread)                 here (B200)
+//   ------------------------------------------   ------------------------------------------------
+//   srand/rand subset draw + std::set dedupe      Philox4x32-10 counter sampler on the device
+//   estimator->estimate()   per try               one minimal solve per thread
+//   N x estimator->agree()  per try               consensus kernel, R hypotheses x point tiles
+//   strict '>' best update                        packed (count, ~index) arg-max
+//   numTries update after each improvement        same rule, re-evaluated between rounds
+//   leastSquaresEstimate(inliers)                 fused mask + moment pass, on-device eigen / LM
+//
+// Error convention kept: invalid input returns 0 (the randomized overload returns BEFORE clearing
+// `parameters`, RANSAC.hxx:16-19 vs :43; the exhaustive overload clears first, :165-169); a
+// degenerate data set leaves `parameters` empty.  Estimators without a GPU path (user-defined
+// classes that do not override b200Describe) produce the same "empty parameters, return 0"
+// result and b200LastError() explains; there is no CPU fallback.
+#ifndef LSQR_B200_RANSAC_H
+#define LSQR_B200_RANSAC_H
+
+#include <vector>
+
+#include "ParametersEstimator.h"
+
+namespace lsqrRecipes {
+
+// Process-wide knobs that the reference does not have (its random path is time-seeded).
+struct B200RansacOptions {
+  int precision;        // LSQR_FP32 (default) or LSQR_FP64 for the consensus scoring
+  unsigned long long seed;
+  B200RansacOptions() : precision(LSQR_FP32), seed(0) {}
+};
+inline B200RansacOptions& b200Options() { static B200RansacOptions o; return o; }
+
+template <class T, class S>
+class RANSAC {
+ public:
+  // Randomized RANSAC; returns the fraction of the data used for the least-squares estimate.
+  static double compute(std::vector<S>& parameters, ParametersEstimator<T, S>* paramEstimator, std::vector<T>& data,
+                        double desiredProbabilityForNoOutliers, std::vector<bool>* consensusSet = NULL) {
+    const unsigned int numDataObjects = static_cast<unsigned int>(data.size());
+    if (numDataObjects < paramEstimator->numForEstimate() || desiredProbabilityForNoOutliers >= 1.0 || desiredProbabilityForNoOutliers <= 0.0) return 0;
+    parameters.clear();
+    return run(parameters, paramEstimator, data, false, desiredProbabilityForNoOutliers, consensusSet);
+  }
+
+  // Brute force over all C(n,k) subsets in lexicographic order; use only when that number is small.
+  static double compute(std::vector<S>& parameters, ParametersEstimator<T, S>* paramEstimator, std::vector<T>& data,
+                        std::vector<bool>* consensusSet = NULL) {
+    parameters.clear();
+    if (data.size() < paramEstimator->numForEstimate()) return 0;
+    return run(parameters, paramEstimator, data, true, 0.0, consensusSet);
+  }
+
+ private:
+  static double run(std::vector<S>& parameters, ParametersEstimator<T, S>* paramEstimator, std::vector<T>& data, bool exhaustive, double prob,
+                    std::vector<bool>* consensusSet) {
+    B200EstimatorDesc d;
+    if (!paramEstimator->b200Describe(d)) {
+      b200::lastErrorStorage() = "this ParametersEstimator has no GPU path (b200Describe not overridden); lsqr_b200 has no CPU fallback";
+      return 0;
+    }
+    lsqr_ctx* ctx = b200::configured(d);
+    if (!ctx) return 0;
+    if (!b200::check(ctx, lsqr_upload(ctx, data.data(), data.size(), sizeof(T)))) return 0;
+    std::vector<uint8_t> mask(consensusSet ? data.size() : 0);
+    lsqr_compute_result r;
+    const int rc = exhaustive ? lsqr_ransac_exhaustive(ctx, LSQR_FP64, consensusSet ? mask.data() : NULL, &r)
+                              : lsqr_ransac(ctx, prob, b200Options().precision, b200Options().seed, consensusSet ? mask.data() : NULL, &r);
+    if (!b200::check(ctx, rc)) return 0;
+    if (r.best_count == 0) return 0;
+    if (consensusSet) {
+      consensusSet->clear();
+      consensusSet->insert(consensusSet->begin(), mask.begin(), mask.end());
+    }
+    for (int i = 0; i < r.n_params; i++) parameters.push_back(static_cast<S>(r.params[i]));
+    return r.fraction;
+  }
+};
+
+}  // namespace lsqrRecipes
+#endif

@@ -175,18 +175,19 @@ int upload_to(lsqr_ctx* ctx, DataSet& ds, const void* aos, size_t n, size_t stri
   return build_layouts(ctx, ds, src, stride);
 }
 
-// RANSAC::choose, RANSAC.hxx:254-280 (double arithmetic, saturates at UINT_MAX)
+// Number of subsets as the reference counts them (RANSAC::choose, RANSAC.hxx:254-280): the binomial
+// coefficient evaluated in double precision as a ratio of two running products, saturating at
+// UINT_MAX when either the result or an intermediate does not fit.  The stop rule clamps the
+// number of tries with this value (RANSAC.hxx:41,110), so the same saturation must happen here.
 unsigned int choose_ref(unsigned int n, unsigned int m) {
-  double denominatorEnd, numeratorStart, numerator, denominator, i, result;
-  if ((n - m) > m) { numeratorStart = n - m + 1; denominatorEnd = m; }
-  else { numeratorStart = m + 1; denominatorEnd = n - m; }
-  for (i = numeratorStart, numerator = 1; i <= n; i++) numerator *= i;
-  for (i = 1, denominator = 1; i <= denominatorEnd; i++) denominator *= i;
-  result = numerator / denominator;
-  if (denominator > std::numeric_limits<double>::max() || numerator > std::numeric_limits<double>::max() ||
-      static_cast<double>(std::numeric_limits<unsigned int>::max()) < result)
-    return std::numeric_limits<unsigned int>::max();
-  return static_cast<unsigned int>(result);
+  const unsigned int small = std::min(m, n - m);         // multiply the shorter run of factors
+  double num = 1.0, den = 1.0;
+  for (unsigned int f = n - small + 1; f <= n && f != 0; f++) num *= static_cast<double>(f);
+  for (unsigned int f = 1; f <= small; f++) den *= static_cast<double>(f);
+  const double c = num / den;
+  const double dmax = std::numeric_limits<double>::max(), umax = static_cast<double>(std::numeric_limits<unsigned int>::max());
+  if (num > dmax || den > dmax || c > umax) return std::numeric_limits<unsigned int>::max();
+  return static_cast<unsigned int>(c);
 }
 
 uint64_t choose_exact(uint64_t n, uint64_t k) {

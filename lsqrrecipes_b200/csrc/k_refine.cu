@@ -228,15 +228,19 @@ void launch_mask_moments(int model, const DataView& dv, uint32_t begin, uint32_t
 #undef LAUNCH
 }
 
+// One warp per moment; lanes stride over the blocks, then a fixed-order shuffle tree: the summation
+// order depends only on the launch geometry, so results are reproducible run to run.
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int blocks, int nm, double* __restrict__ moments) {
-  const int j = threadIdx.x;
+  const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (j >= nm) return;
   double v = 0.0;
-  for (int b = 0; b < blocks; b++) v += partials[(size_t)b * kMaxMoments + j];
-  moments[j] = v;
+  for (int b = lane; b < blocks; b += 32) v += partials[(size_t)b * kMaxMoments + j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) moments[j] = v;
 }
 void launch_reduce_partials(const RefineBuffers& rb, int nm, cudaStream_t s) {
-  reduce_partials_kernel<<<1, 32, 0, s>>>(rb.partials, rb.blocks, nm, rb.moments);
+  reduce_partials_kernel<<<1, 32 * kMaxMoments, 0, s>>>(rb.partials, rb.blocks, nm, rb.moments);
 }
 
 // ---------------------------------------------------------------------------------------

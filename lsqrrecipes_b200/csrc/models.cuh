@@ -102,9 +102,9 @@ template <int N>
 __device__ inline void sym_eig(double* a, double* v, double* d) {
   for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) v[i * N + j] = (i == j) ? 1.0 : 0.0;
   for (int sweep = 0; sweep < 100; sweep++) {
-    double off = 0.0;
-    for (int p = 0; p < N; p++) for (int q = p + 1; q < N; q++) off += a[p * N + q] * a[p * N + q];
-    if (off == 0.0) break;
+    double off = 0.0, diag = 0.0;
+    for (int p = 0; p < N; p++) { diag += a[p * N + p] * a[p * N + p]; for (int q = p + 1; q < N; q++) off += a[p * N + q] * a[p * N + q]; }
+    if (off <= 1e-34 * diag) break;  // off-diagonal mass below fp64 resolution of the spectrum (also catches off == 0)
     for (int p = 0; p < N; p++) {
       for (int q = p + 1; q < N; q++) {
         const double apq = a[p * N + q];

@@ -15,6 +15,7 @@ typedef unsigned long long u64;
 __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ u64 fmul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ u64 pack2(float lo, float hi) { u64 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi)); return d; }
+__device__ __forceinline__ u64 pack2_opaque(float lo, float hi) { u64 d; asm volatile("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi)); return d; }
 __device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ uint32_t set_lt(float a, float b) { uint32_t m; asm("set.lt.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(a), "f"(b)); return m; }
 
@@ -46,8 +47,13 @@ __global__ void __launch_bounds__(THREADS) lab_kernel(const float* __restrict__ 
     const float c = (VARIANT == 3) ? 1.41421356237f / delta : 1.0f;
 #pragma unroll
     for (int r = 0; r < R; r++) {
+      if (VARIANT == 12) {
+        hx2[r] = pack2_opaque(h[r].x, h[r].x); hy2[r] = pack2_opaque(h[r].y, h[r].y);
+        hz2[r] = pack2_opaque(h[r].z, h[r].z); hd2[r] = pack2_opaque(h[r].w, h[r].w);
+      } else {
       hx2[r] = pack2(h[r].x * c, h[r].x * c); hy2[r] = pack2(h[r].y * c, h[r].y * c);
       hz2[r] = pack2(h[r].z * c, h[r].z * c); hd2[r] = pack2(h[r].w * c, h[r].w * c);
+      }
     }
   }
   if (VARIANT == 11) {
@@ -64,7 +70,7 @@ __global__ void __launch_bounds__(THREADS) lab_kernel(const float* __restrict__ 
     __syncthreads();
 #pragma unroll 1
     for (int i = 0; i < TILE; i += 4) {
-      if (VARIANT <= 1 || VARIANT >= 8) {
+      if (VARIANT <= 1 || (VARIANT >= 8 && VARIANT <= 11)) {
         const float4 x = *reinterpret_cast<const float4*>(sx + i), y = *reinterpret_cast<const float4*>(sy + i), z = *reinterpret_cast<const float4*>(sz + i);
         const float xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w}, zs[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
@@ -130,7 +136,7 @@ __global__ void __launch_bounds__(THREADS) lab_kernel(const float* __restrict__ 
                   : "+r"(c0) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)), "f"(fabsf(d)), "f"(delta));
               cnt[r] = c0;
             }
-          } else if (VARIANT == 5 || (VARIANT == 7 && (r % 3) != 0)) {
+          } else if (VARIANT == 5 || ((VARIANT == 7 || VARIANT == 12) && (r % 3) != 0)) {
             // FSETP + predicated IADD, forced through PTX so that ptxas cannot turn it into add+select
             float a, b, c, d;
             unpack2(s01, a, b); unpack2(s23, c, d);
@@ -140,7 +146,7 @@ __global__ void __launch_bounds__(THREADS) lab_kernel(const float* __restrict__ 
                 "@p0 add.u32 %0, %0, 1;\n\t@p1 add.u32 %0, %0, 1;\n\t@p2 add.u32 %0, %0, 1;\n\t@p3 add.u32 %0, %0, 1;\n\t}"
                 : "+r"(c0) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)), "f"(fabsf(d)), "f"(delta));
             cnt[r] = c0;
-          } else if (VARIANT == 6 || VARIANT == 7) {
+          } else if (VARIANT == 6 || VARIANT == 7 || VARIANT == 12) {
             // w = s^2 - delta^2 on the FMA pipe; the sign bit of w is the inlier flag: cnt += bits(w) >> 31
             const u64 md2 = pack2(-delta * delta, -delta * delta);
             const u64 w01 = ffma2(s01, s01, md2), w23 = ffma2(s23, s23, md2);
@@ -249,6 +255,9 @@ int main(int argc, char** argv) {
   run<7, 9, 256>("v7 hybrid 1/3 sign, 2/3 setp", px, py, pz, N, hyp, H, delta, counts, got, false); check("v7");
   run<7, 6, 256>("v7 hybrid 1/3 sign, 2/3 setp", px, py, pz, N, hyp, H, delta, counts, got, false);
   run<7, 9, 128>("v7 hybrid 1/3 sign, 2/3 setp", px, py, pz, N, hyp, H, delta, counts, got, false);
+  run<12, 9, 256>("v12 hybrid, packed (non-bcast) hyps", px, py, pz, N, hyp, H, delta, counts, got, false); check("v12");
+  run<12, 6, 256>("v12 hybrid, packed (non-bcast) hyps", px, py, pz, N, hyp, H, delta, counts, got, false);
+  run<12, 9, 128>("v12 hybrid, packed (non-bcast) hyps", px, py, pz, N, hyp, H, delta, counts, got, false);
   run<8, 8, 256>("v8 scalar, setp + @p add", px, py, pz, N, hyp, H, delta, counts, got, false); check("v8");
   run<8, 16, 128>("v8 scalar, setp + @p add", px, py, pz, N, hyp, H, delta, counts, got, false);
   run<8, 16, 256>("v8 scalar, setp + @p add", px, py, pz, N, hyp, H, delta, counts, got, false);

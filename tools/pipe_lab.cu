@@ -11,7 +11,7 @@ __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm volatile(
 
 // per loop iteration: NF2 FFMA2 (distinct 3-register-pair operands), NF1 scalar FFMA (3 distinct regs),
 // NLEA shift-adds (acc += x >> 31), NSP (FSETP + predicated add) pairs.
-template <int NF2, int NF1, int NLEA, int NSP>
+template <int NF2, int NF1, int NLEA, int NSP, bool BCAST = false>
 __global__ void __launch_bounds__(256) pipe_kernel(int iters, float* sink, float seedf) {
   u64 a2[16], b2[8], c2[16];
   float a1[16], b1[8], c1[16];
@@ -29,7 +29,10 @@ __global__ void __launch_bounds__(256) pipe_kernel(int iters, float* sink, float
 #pragma unroll
     for (int u = 0; u < 4; u++) {
 #pragma unroll
-      for (int i = 0; i < NF2; i++) a2[i % 16] = ffma2(a2[i % 16], b2[i % 8], c2[(i + u) % 16]);
+      for (int i = 0; i < NF2; i++) {
+        if (BCAST) { u64 bb; asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b1[i % 8])); a2[i % 16] = ffma2(bb, a2[i % 16], c2[(i + u) % 16]); }
+        else a2[i % 16] = ffma2(a2[i % 16], b2[i % 8], c2[(i + u) % 16]);
+      }
 #pragma unroll
       for (int i = 0; i < NF1; i++) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a1[i % 16]) : "f"(b1[i % 8]), "f"(c1[(i + u) % 16]));
 #pragma unroll
@@ -46,14 +49,14 @@ __global__ void __launch_bounds__(256) pipe_kernel(int iters, float* sink, float
   if (r == 123.456f) sink[0] = r;
 }
 
-template <int NF2, int NF1, int NLEA, int NSP>
+template <int NF2, int NF1, int NLEA, int NSP, bool BCAST = false>
 void run(const char* name, float* sink) {
   const int iters = 2048, blocks = 148 * 8;
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   float best = 1e30f;
   for (int rep = 0; rep < 3; rep++) {
     CK(cudaEventRecord(e0));
-    pipe_kernel<NF2, NF1, NLEA, NSP><<<blocks, 256>>>(iters, sink, 1.0f);
+    pipe_kernel<NF2, NF1, NLEA, NSP, BCAST><<<blocks, 256>>>(iters, sink, 1.0f);
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
     if (ms < best) best = ms;
@@ -68,6 +71,7 @@ void run(const char* name, float* sink) {
 int main() {
   float* sink; CK(cudaMalloc(&sink, 64));
   run<12, 0, 0, 0>("FFMA2 only", sink);
+  run<12, 0, 0, 0, true>("FFMA2 with one .F32 broadcast operand", sink);
   run<0, 12, 0, 0>("FFMA (3 distinct regs) only", sink);
   run<0, 0, 8, 0>("LEA/shift-add only", sink);
   run<0, 0, 0, 8>("FSETP+@P ADD only", sink);
