@@ -17,8 +17,17 @@
 //     both halves once per thread, point pairs come straight out of the SoA shared-memory tile
 //     (one LDS.128 = two pairs), so no repacking happens in the loop.
 //   * Point tiles are staged by TMA bulk copies into a 2-deep shared-memory ring (as in k_score.cu).
+//   * Large requests (H >= kCbMinHyps) take the CONSTANT-BANK kernel at the end of this file.  The
+//     register file of an SM sub-partition delivers two 32-bit operands per cycle
+//     (tools/ptx_lab, profiles/r01_ptx_lab_rf_model.txt): an FFMA2 whose point pair comes out of
+//     shared memory into registers reads 5-6 of them and is RF-bound at 2.5-3 cycles instead of the
+//     2 cycles its pipe needs.  With the points of one launch in the 64 KB constant bank the pair is a
+//     UNIFORM-register operand (LDCU.128 -> `FFMA2 R, R.F32, UR.F32x2, R.F32x2`), 2-3 register reads,
+//     and the FMA-heavy pipe becomes the limit (ncu: 90 % busy) -- 8.0 instead of 6.6 T evals/s.
 // Tensor cores are deliberately unused: contraction depth <= 4 (BASELINE.json north_star).
 #include "engine.h"
+
+#include <mutex>
 
 namespace lsqr {
 
@@ -244,6 +253,16 @@ __device__ __forceinline__ void count_abs_lt(uint32_t& cnt, f2 s, float delta) {
       "@p0 add.u32 %0, %0, 1;\n\t@p1 add.u32 %0, %0, 1;\n\t}"
       : "+r"(cnt) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(delta));
 }
+// Four residuals (two point pairs) at once.
+__device__ __forceinline__ void count_abs_lt4(uint32_t& cnt, f2 s01, f2 s23, float delta) {
+  float a, b, c, d;
+  halves(s01, a, b);
+  halves(s23, c, d);
+  asm("{\n\t.reg .pred p0, p1, p2, p3;\n\t"
+      "setp.lt.f32 p0, %1, %5;\n\tsetp.lt.f32 p1, %2, %5;\n\tsetp.lt.f32 p2, %3, %5;\n\tsetp.lt.f32 p3, %4, %5;\n\t"
+      "@p0 add.u32 %0, %0, 1;\n\t@p1 add.u32 %0, %0, 1;\n\t@p2 add.u32 %0, %0, 1;\n\t@p3 add.u32 %0, %0, 1;\n\t}"
+      : "+r"(cnt) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)), "f"(fabsf(d)), "f"(delta));
+}
 __device__ __forceinline__ void count_sign(uint32_t& cnt, f2 g) {
   float a, b;
   halves(g, a, b);
@@ -345,6 +364,125 @@ static int run_consensus32(const DataView& dv, const float* hyp, size_t hld, uin
   return 1;
 }
 
+
+// ---- constant-bank variant ---------------------------------------------------------------------
+// One launch scores ALL hypotheses of the request against the `cp` points whose components sit in
+// the constant bank ([D][cp] floats, cp a multiple of 16, copied there device-to-device before the
+// launch).  grid = (hypothesis blocks) x (point sub-chunks of `sub` points); every thread keeps R
+// hypotheses as scalars (broadcast .F32 operands), the point pairs are uniform registers.
+constexpr int kCbFloats = 16320;              // 65280 B of the 64 KB bank
+constexpr uint32_t kCbMinHyps = 98304;        // below this the per-launch overhead outweighs the gain
+__constant__ float4 c_tile[kCbFloats / 4];
+static std::mutex g_cb_mutex[16];             // the bank is per device, not per context
+
+template <int M, int R, int THREADS, int PPI>
+__global__ void __launch_bounds__(THREADS) consensus_cb_kernel(uint32_t cp, uint32_t npts, uint32_t sub, const float* __restrict__ hyp, size_t hld, uint32_t H,
+                                                                float delta, float delta2, uint32_t* __restrict__ counts) {
+  constexpr int D = Model<M>::D, Q = Model<M>::Q32;
+  const int tid = threadIdx.x;
+  const uint32_t hbase = blockIdx.x * (THREADS * R);
+  float qf[R][Q];
+  uint32_t cnt[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const uint32_t h = hbase + r * THREADS + tid;
+#pragma unroll
+    for (int j = 0; j < Q; j++) qf[r][j] = (h < H) ? hyp[(size_t)j * hld + h] : __int_as_float(0x7fc00000);
+    cnt[r] = 0;
+  }
+  Thr2 thr;
+  thr.delta = splat(delta); thr.neg_delta2 = splat(-delta2); thr.fdelta = delta;
+  const uint32_t p0 = blockIdx.y * sub, p1 = min(p0 + sub, npts);
+#pragma unroll 1
+  for (uint32_t i = p0; i < p1; i += 2 * PPI) {
+    f2 x[PPI][D];
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+      if constexpr (PPI == 2) {
+        const float4 v = c_tile[(d * cp + i) >> 2];
+        x[0][d] = join(v.x, v.y); x[1][d] = join(v.z, v.w);
+      } else {
+        const float2 v = reinterpret_cast<const float2*>(c_tile)[(d * cp + i) >> 1];
+        x[0][d] = join(v.x, v.y);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      f2 q[Q];
+#pragma unroll
+      for (int j = 0; j < Q; j++) q[j] = splat(qf[r][j]);
+      if constexpr (Eval<M>::kHasAbsForm && PPI == 2) {
+        count_abs_lt4(cnt[r], Eval<M>::dist(q, x[0]), Eval<M>::dist(q, x[1]), thr.fdelta);
+      } else {
+#pragma unroll
+        for (int u = 0; u < PPI; u++) count_sign(cnt[r], Eval<M>::signed_(q, x[u], thr));
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const uint32_t h = hbase + r * THREADS + tid;
+    if (h < H && cnt[r]) atomicAdd(&counts[h], cnt[r]);
+  }
+}
+
+// Hypotheses per thread / point pairs per iteration of the constant-bank kernel (128 threads, <= 80 registers).
+template <int M> struct BlockCB { static constexpr int R = 8, PPI = 2; };
+template <> struct BlockCB<PLANE3> { static constexpr int R = 12, PPI = 2; };
+template <> struct BlockCB<LINE2D> { static constexpr int R = 12, PPI = 2; };
+template <> struct BlockCB<LINE2> { static constexpr int R = 10, PPI = 2; };
+template <> struct BlockCB<LINE3> { static constexpr int R = 8, PPI = 2; };
+template <> struct BlockCB<CIRCLE2> { static constexpr int R = 12, PPI = 2; };
+template <> struct BlockCB<SPHERE3> { static constexpr int R = 10, PPI = 2; };
+template <> struct BlockCB<ABSOR> { static constexpr int R = 4, PPI = 2; };
+template <> struct BlockCB<RAY> { static constexpr int R = 8, PPI = 2; };
+template <> struct BlockCB<PIVOT> { static constexpr int R = 6, PPI = 1; };
+
+template <int M>
+static int run_consensus_cb(const DataView& dv, const float* hyp, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms, cudaStream_t s) {
+  constexpr int D = Model<M>::D, R = BlockCB<M>::R, PPI = BlockCB<M>::PPI, THREADS = 128;
+  constexpr uint32_t cp = (uint32_t)(kCbFloats / D / 16 * 16);   // points per launch
+  auto kern = consensus_cb_kernel<M, R, THREADS, PPI>;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static int occ[16] = {0};
+  if (!occ[dev & 15]) {
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, THREADS, 0) != cudaSuccess || o < 1) o = 4;
+    occ[dev & 15] = o;
+  }
+  void* bank = nullptr;
+  if (cudaGetSymbolAddress(&bank, c_tile) != cudaSuccess) return -1;
+  const uint32_t hyp_blocks = (H + THREADS * R - 1) / (THREADS * R);
+  const uint32_t slots = (uint32_t)num_sms * (uint32_t)occ[dev & 15];
+  // sub-chunks per launch: fill the last wave (the launches of one request serialise on the bank)
+  auto pick_sub = [&](uint32_t npts) {
+    uint32_t best_sub = npts; double best_eff = 0.0;
+    for (uint32_t nsub = 1; nsub <= 64; nsub++) {
+      uint32_t sub = ((npts + nsub - 1) / nsub + 15) / 16 * 16;
+      if (sub < 128 && nsub > 1) break;
+      const uint32_t ny = (npts + sub - 1) / sub;
+      const double waves = (double)hyp_blocks * ny / slots;
+      const double eff = waves / (double)(uint64_t)(waves + 0.999999);
+      if (eff > best_eff + 0.01) { best_eff = eff; best_sub = sub; }
+    }
+    return best_sub;
+  };
+  std::lock_guard<std::mutex> lock(g_cb_mutex[dev & 15]);
+  int launches = 0;
+  for (size_t base = 0; base < dv.ld; base += cp) {
+    const uint32_t npts = (uint32_t)((dv.ld - base < cp) ? (dv.ld - base) : cp);   // ld is a multiple of 1024, cp of 16
+    if (base >= dv.n) break;                                                        // only NaN padding left
+    if (cudaMemcpy2DAsync(bank, sizeof(float) * cp, dv.soa32 + base, sizeof(float) * dv.ld, sizeof(float) * npts, D, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return -1;
+    const uint32_t sub = pick_sub(npts);
+    kern<<<dim3(hyp_blocks, (npts + sub - 1) / sub), THREADS, 0, s>>>(cp, npts, sub, hyp, hld, H, (float)cfg.delta, (float)cfg.delta2, counts);
+    launches += 2;
+  }
+  // the bank is shared by every context on this device: finish before another request may refill it
+  if (cudaStreamSynchronize(s) != cudaSuccess) return -1;
+  return launches;
+}
+
 // Register blocking per model: R hypotheses per thread sized so that 2*Q32*R duplicated constants
 // plus the point pairs stay below ~128 registers at 256 threads.
 template <int M> struct Block32 { static constexpr int R = 6, PPI = 2; };
@@ -361,6 +499,11 @@ template <> struct Block32<PIVOT> { static constexpr int R = 4, PPI = 1; };
 int launch_consensus32(int model, const DataView& dv, const float* hyp32, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms,
                        cudaStream_t s) {
   if (H == 0 || dv.n == 0) return 0;
+  if (H >= kCbMinHyps) {
+#define CALL(MM) return run_consensus_cb<MM>(dv, hyp32, hld, H, cfg, counts, num_sms, s)
+    LSQR_DISPATCH_MODEL(model, CALL)
+#undef CALL
+  }
 #define CALL(MM)                                                                                                        \
   if (H <= 8192) return run_consensus32<MM, 1, 128, 512, Block32<MM>::PPI>(dv, hyp32, hld, H, cfg, counts, num_sms, s);  \
   return run_consensus32<MM, Block32<MM>::R, 256, 512, Block32<MM>::PPI>(dv, hyp32, hld, H, cfg, counts, num_sms, s)

@@ -211,6 +211,28 @@ def test_fp32_fast_mode_differs_only_near_threshold(port, name, m):
 
 
 @pytest.mark.parametrize("name,m", ALL)
+def test_fp32_constant_bank_kernel_matches_shared_memory_kernel(name, m):
+    """Requests of >= 98304 hypotheses take the constant-bank kernel (k_fast.cu), smaller ones the
+    shared-memory kernel.  Both evaluate the same fp32 expressions, so one large request and the same
+    hypotheses scored in small pieces must give identical counts; the data size is chosen so that the
+    last constant-bank launch is partial and the last sub-chunk ragged."""
+    n, H, piece = 7001, 100352, 25088
+    data, _ = synth.GENERATORS[name](n, seed=4100 + m)
+    eng = Engine(name, synth.DELTAS[name])
+    eng.upload(data)
+    whole = eng.score(count=H, seed=9, precision=FP32, want_counts=True)
+    parts = [eng.score(count=piece, first=f, seed=9, precision=FP32, want_counts=True) for f in range(0, H, piece)]
+    c_parts = np.concatenate([p["counts"] for p in parts])
+    assert np.array_equal(whole["counts"], c_parts)
+    b = int(np.argmax(c_parts))
+    assert whole["best_index"] == b and whole["best_count"] == c_parts[b]
+    # and the fp32 counts stay within a whisker of the bit-exact fp64 ones
+    c64 = eng.score(count=4096, seed=9, precision=FP64, want_counts=True)["counts"].astype(np.int64)
+    assert np.abs(whole["counts"][:4096].astype(np.int64) - c64).sum() <= 1e-3 * c64.sum() + 16
+    eng.close()
+
+
+@pytest.mark.parametrize("name,m", ALL)
 @pytest.mark.parametrize("precision", [FP64, FP32])
 def test_randomized_compute_end_to_end(port, name, m, precision):
     """RANSAC<T,S>::compute(parameters, estimator, data, 0.999, &consensusSet): the result must be the

@@ -63,6 +63,9 @@ __global__ void __launch_bounds__(THREADS) lab_kernel(const float* __restrict__ 
   uint32_t total[R];
 #pragma unroll
   for (int r = 0; r < R; r++) total[r] = 0;
+  uint32_t opaque_one, opaque_msb;
+  asm volatile("mov.u32 %0, 1;" : "=r"(opaque_one));
+  asm volatile("mov.u32 %0, 0x80000000;" : "=r"(opaque_msb));
   const uint32_t t0 = blockIdx.y * tiles_per_chunk, t1 = min(t0 + tiles_per_chunk, n_tiles);
   for (uint32_t t = t0; t < t1; t++) {
     __syncthreads();
@@ -136,6 +139,22 @@ __global__ void __launch_bounds__(THREADS) lab_kernel(const float* __restrict__ 
                   : "+r"(c0) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)), "f"(fabsf(d)), "f"(delta));
               cnt[r] = c0;
             }
+          } else if ((VARIANT == 13 || VARIANT == 14) && (r % 3) != 0) {
+            float a, b, c, d;
+            unpack2(s01, a, b); unpack2(s23, c, d);
+            uint32_t c0 = cnt[r];
+            if (VARIANT == 13) {
+              asm("{\n\t.reg .pred p0, p1, p2, p3;\n\t"
+                  "setp.lt.f32 p0, %1, %5;\n\tsetp.lt.f32 p1, %2, %5;\n\tsetp.lt.f32 p2, %3, %5;\n\tsetp.lt.f32 p3, %4, %5;\n\t"
+                  "@p0 add.u32 %0, %0, %6;\n\t@p1 add.u32 %0, %0, %6;\n\t@p2 add.u32 %0, %0, %6;\n\t@p3 add.u32 %0, %0, %6;\n\t}"
+                  : "+r"(c0) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)), "f"(fabsf(d)), "f"(delta), "r"(opaque_one));
+            } else {
+              asm("{\n\t.reg .pred p0, p1, p2, p3;\n\t.reg .u32 t;\n\t"
+                  "setp.lt.f32 p0, %1, %5;\n\tsetp.lt.f32 p1, %2, %5;\n\tsetp.lt.f32 p2, %3, %5;\n\tsetp.lt.f32 p3, %4, %5;\n\t"
+                  "@p0 shf.l.wrap.b32 t, %6, %0, 1;\n\t@p0 mov.u32 %0, t;\n\t}"
+                  : "+r"(c0) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)), "f"(fabsf(d)), "f"(delta), "r"(opaque_msb));
+            }
+            cnt[r] = c0;
           } else if (VARIANT == 5 || ((VARIANT == 7 || VARIANT == 12) && (r % 3) != 0)) {
             // FSETP + predicated IADD, forced through PTX so that ptxas cannot turn it into add+select
             float a, b, c, d;
@@ -146,7 +165,7 @@ __global__ void __launch_bounds__(THREADS) lab_kernel(const float* __restrict__ 
                 "@p0 add.u32 %0, %0, 1;\n\t@p1 add.u32 %0, %0, 1;\n\t@p2 add.u32 %0, %0, 1;\n\t@p3 add.u32 %0, %0, 1;\n\t}"
                 : "+r"(c0) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)), "f"(fabsf(d)), "f"(delta));
             cnt[r] = c0;
-          } else if (VARIANT == 6 || VARIANT == 7 || VARIANT == 12) {
+          } else if (VARIANT == 6 || VARIANT == 7 || VARIANT == 12 || VARIANT == 13 || VARIANT == 14) {
             // w = s^2 - delta^2 on the FMA pipe; the sign bit of w is the inlier flag: cnt += bits(w) >> 31
             const u64 md2 = pack2(-delta * delta, -delta * delta);
             const u64 w01 = ffma2(s01, s01, md2), w23 = ffma2(s23, s23, md2);
@@ -255,6 +274,9 @@ int main(int argc, char** argv) {
   run<7, 9, 256>("v7 hybrid 1/3 sign, 2/3 setp", px, py, pz, N, hyp, H, delta, counts, got, false); check("v7");
   run<7, 6, 256>("v7 hybrid 1/3 sign, 2/3 setp", px, py, pz, N, hyp, H, delta, counts, got, false);
   run<7, 9, 128>("v7 hybrid 1/3 sign, 2/3 setp", px, py, pz, N, hyp, H, delta, counts, got, false);
+  run<13, 9, 256>("v13 hybrid, @p add opaque reg", px, py, pz, N, hyp, H, delta, counts, got, false); check("v13");
+  run<13, 9, 128>("v13 hybrid, @p add opaque reg", px, py, pz, N, hyp, H, delta, counts, got, false);
+  run<13, 12, 128>("v13 hybrid, @p add opaque reg", px, py, pz, N, hyp, H, delta, counts, got, false);
   run<12, 9, 256>("v12 hybrid, packed (non-bcast) hyps", px, py, pz, N, hyp, H, delta, counts, got, false); check("v12");
   run<12, 6, 256>("v12 hybrid, packed (non-bcast) hyps", px, py, pz, N, hyp, H, delta, counts, got, false);
   run<12, 9, 128>("v12 hybrid, packed (non-bcast) hyps", px, py, pz, N, hyp, H, delta, counts, got, false);
