@@ -122,8 +122,29 @@ __global__ void hoist32_kernel(const double* __restrict__ hyp64, size_t hld, uin
   for (int j = 0; j < 12; j++) c[j] = dv.center[j];
   hoist32<M>(prm, c, cfg, q);
   const bool ok = prm[0] == prm[0];
+  // layout: groups of four constants, [ceil(Q/4)][hld] float4 -> one 16-byte load per group in the consensus kernels
+  float4* out = reinterpret_cast<float4*>(hyp32);
 #pragma unroll
-  for (int j = 0; j < Q; j++) hyp32[(size_t)j * hld + h] = ok ? q[j] : __int_as_float(0x7fc00000);
+  for (int g = 0; g < (Q + 3) / 4; g++) {
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) v[c] = (ok && 4 * g + c < Q) ? q[4 * g + c] : __int_as_float(0x7fc00000);
+    out[(size_t)g * hld + h] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// Reads the Q hoisted constants of hypothesis h (NaN for h >= H: never agrees).
+template <int Q>
+__device__ __forceinline__ void load_hyp32(const float* __restrict__ hyp, size_t hld, uint32_t h, uint32_t H, float* q) {
+  const float4* in = reinterpret_cast<const float4*>(hyp);
+  const float nan = __int_as_float(0x7fc00000);
+#pragma unroll
+  for (int g = 0; g < (Q + 3) / 4; g++) {
+    const float4 v = (h < H) ? __ldg(in + (size_t)g * hld + h) : make_float4(nan, nan, nan, nan);
+    const float t[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int c = 0; c < 4; c++) if (4 * g + c < Q) q[4 * g + c] = t[c];
+  }
 }
 
 #define LSQR_DISPATCH_MODEL(model, CALL)      \
@@ -263,6 +284,19 @@ __device__ __forceinline__ void count_abs_lt4(uint32_t& cnt, f2 s01, f2 s23, flo
       "@p0 add.u32 %0, %0, 1;\n\t@p1 add.u32 %0, %0, 1;\n\t@p2 add.u32 %0, %0, 1;\n\t@p3 add.u32 %0, %0, 1;\n\t}"
       : "+r"(cnt) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)), "f"(fabsf(d)), "f"(delta));
 }
+// Same test with two ALU instructions per residual and nothing on the FMA-heavy pipe: FSET.BF writes
+// 1.0f (0x3F800000) or 0, whose top three bits are the count increment (LEA.HI cnt += f >> 29).
+__device__ __forceinline__ void count_abs_lt4_alu(uint32_t& cnt, f2 s01, f2 s23, float delta) {
+  float a, b, c, d;
+  halves(s01, a, b);
+  halves(s23, c, d);
+  asm("{\n\t.reg .f32 f0, f1, f2, f3;\n\t.reg .b32 t0, t1, t2, t3;\n\t"
+      "set.lt.f32.f32 f0, %1, %5;\n\tset.lt.f32.f32 f1, %2, %5;\n\tset.lt.f32.f32 f2, %3, %5;\n\tset.lt.f32.f32 f3, %4, %5;\n\t"
+      "mov.b32 t0, f0;\n\tmov.b32 t1, f1;\n\tmov.b32 t2, f2;\n\tmov.b32 t3, f3;\n\t"
+      "shr.u32 t0, t0, 29;\n\tshr.u32 t1, t1, 29;\n\tshr.u32 t2, t2, 29;\n\tshr.u32 t3, t3, 29;\n\t"
+      "add.u32 %0, %0, t0;\n\tadd.u32 %0, %0, t1;\n\tadd.u32 %0, %0, t2;\n\tadd.u32 %0, %0, t3;\n\t}"
+      : "+r"(cnt) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)), "f"(fabsf(d)), "f"(delta));
+}
 __device__ __forceinline__ void count_sign(uint32_t& cnt, f2 g) {
   float a, b;
   halves(g, a, b);
@@ -289,8 +323,10 @@ __global__ void __launch_bounds__(THREADS) consensus32_kernel(const float* __res
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const uint32_t h = hbase + r * THREADS + tid;
+    float qs[Q];
+    load_hyp32<Q>(hyp, hld, h, H, qs);
 #pragma unroll
-    for (int j = 0; j < Q; j++) q[r][j] = splat((h < H) ? hyp[(size_t)j * hld + h] : __int_as_float(0x7fc00000));
+    for (int j = 0; j < Q; j++) q[r][j] = splat(qs[j]);
     cnt[r] = 0;
   }
   Thr2 thr;
@@ -375,19 +411,26 @@ constexpr uint32_t kCbMinHyps = 98304;        // below this the per-launch overh
 __constant__ float4 c_tile[kCbFloats / 4];
 static std::mutex g_cb_mutex[16];             // the bank is per device, not per context
 
+#ifndef LSQR_CB_MINBLOCKS
+#define LSQR_CB_MINBLOCKS 5
+#endif
+#ifndef LSQR_CB_MIX
+#define LSQR_CB_MIX 3
+#endif
+template <int M> constexpr uint32_t cb_points() { return (uint32_t)(kCbFloats / Model<M>::D / 16 * 16); }   // points per launch
+
 template <int M, int R, int THREADS, int PPI>
-__global__ void __launch_bounds__(THREADS) consensus_cb_kernel(uint32_t cp, uint32_t npts, uint32_t sub, const float* __restrict__ hyp, size_t hld, uint32_t H,
+__global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kernel(uint32_t npts, uint32_t sub, const float* __restrict__ hyp, size_t hld, uint32_t H,
                                                                 float delta, float delta2, uint32_t* __restrict__ counts) {
   constexpr int D = Model<M>::D, Q = Model<M>::Q32;
+  constexpr uint32_t cp = cb_points<M>();
   const int tid = threadIdx.x;
   const uint32_t hbase = blockIdx.x * (THREADS * R);
   float qf[R][Q];
   uint32_t cnt[R];
 #pragma unroll
   for (int r = 0; r < R; r++) {
-    const uint32_t h = hbase + r * THREADS + tid;
-#pragma unroll
-    for (int j = 0; j < Q; j++) qf[r][j] = (h < H) ? hyp[(size_t)j * hld + h] : __int_as_float(0x7fc00000);
+    load_hyp32<Q>(hyp, hld, hbase + r * THREADS + tid, H, qf[r]);
     cnt[r] = 0;
   }
   Thr2 thr;
@@ -412,7 +455,10 @@ __global__ void __launch_bounds__(THREADS) consensus_cb_kernel(uint32_t cp, uint
 #pragma unroll
       for (int j = 0; j < Q; j++) q[j] = splat(qf[r][j]);
       if constexpr (Eval<M>::kHasAbsForm && PPI == 2) {
-        count_abs_lt4(cnt[r], Eval<M>::dist(q, x[0]), Eval<M>::dist(q, x[1]), thr.fdelta);
+        // ptxas puts most predicated adds on the FMA-heavy pipe (VIADD), which the FFMA2s need: one
+        // hypothesis in LSQR_CB_MIX counts that way, the others with two ALU instructions
+        if (r % LSQR_CB_MIX == 0) count_abs_lt4(cnt[r], Eval<M>::dist(q, x[0]), Eval<M>::dist(q, x[1]), thr.fdelta);
+        else count_abs_lt4_alu(cnt[r], Eval<M>::dist(q, x[0]), Eval<M>::dist(q, x[1]), thr.fdelta);
       } else {
 #pragma unroll
         for (int u = 0; u < PPI; u++) count_sign(cnt[r], Eval<M>::signed_(q, x[u], thr));
@@ -427,8 +473,14 @@ __global__ void __launch_bounds__(THREADS) consensus_cb_kernel(uint32_t cp, uint
 }
 
 // Hypotheses per thread / point pairs per iteration of the constant-bank kernel (128 threads, <= 80 registers).
+#ifndef LSQR_CB_THREADS
+#define LSQR_CB_THREADS 128
+#endif
+#ifndef LSQR_CB_R_PLANE
+#define LSQR_CB_R_PLANE 12
+#endif
 template <int M> struct BlockCB { static constexpr int R = 8, PPI = 2; };
-template <> struct BlockCB<PLANE3> { static constexpr int R = 12, PPI = 2; };
+template <> struct BlockCB<PLANE3> { static constexpr int R = LSQR_CB_R_PLANE, PPI = 2; };
 template <> struct BlockCB<LINE2D> { static constexpr int R = 12, PPI = 2; };
 template <> struct BlockCB<LINE2> { static constexpr int R = 10, PPI = 2; };
 template <> struct BlockCB<LINE3> { static constexpr int R = 8, PPI = 2; };
@@ -440,8 +492,8 @@ template <> struct BlockCB<PIVOT> { static constexpr int R = 6, PPI = 1; };
 
 template <int M>
 static int run_consensus_cb(const DataView& dv, const float* hyp, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms, cudaStream_t s) {
-  constexpr int D = Model<M>::D, R = BlockCB<M>::R, PPI = BlockCB<M>::PPI, THREADS = 128;
-  constexpr uint32_t cp = (uint32_t)(kCbFloats / D / 16 * 16);   // points per launch
+  constexpr int D = Model<M>::D, R = BlockCB<M>::R, PPI = BlockCB<M>::PPI, THREADS = LSQR_CB_THREADS;
+  constexpr uint32_t cp = cb_points<M>();
   auto kern = consensus_cb_kernel<M, R, THREADS, PPI>;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -475,7 +527,7 @@ static int run_consensus_cb(const DataView& dv, const float* hyp, size_t hld, ui
     if (base >= dv.n) break;                                                        // only NaN padding left
     if (cudaMemcpy2DAsync(bank, sizeof(float) * cp, dv.soa32 + base, sizeof(float) * dv.ld, sizeof(float) * npts, D, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return -1;
     const uint32_t sub = pick_sub(npts);
-    kern<<<dim3(hyp_blocks, (npts + sub - 1) / sub), THREADS, 0, s>>>(cp, npts, sub, hyp, hld, H, (float)cfg.delta, (float)cfg.delta2, counts);
+    kern<<<dim3(hyp_blocks, (npts + sub - 1) / sub), THREADS, 0, s>>>(npts, sub, hyp, hld, H, (float)cfg.delta, (float)cfg.delta2, counts);
     launches += 2;
   }
   // the bank is shared by every context on this device: finish before another request may refill it

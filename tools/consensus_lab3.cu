@@ -28,6 +28,8 @@ __constant__ float4 c_pts[3 * CPTS / 4];   // [x: CPTS][y: CPTS][z: CPTS]
 // COUNT 4: low half FSETP, high half DSETP on the register pair viewed as a double (monotone bit patterns), predicated add.u32
 // COUNT 5: as 4, counting with predicated DADD
 // COUNT 6: FSETP x2, one add.u32 + one DADD per pair
+// COUNT 7: FSET.BF (1.0f / 0) + LEA.HI cnt += f >> 29          (two ALU ops, nothing on the FMA-heavy pipe)
+// COUNT 8/9/10: hybrid, every 3rd / 4th / 2nd hypothesis FSETP + @p add (mostly VIADD = FMA-heavy), the rest as 7
 template <int R, int THREADS, int COUNT, int SUB>
 __global__ void __launch_bounds__(THREADS) cb_kernel(const float4* __restrict__ hyp, uint32_t H, float delta, uint32_t* __restrict__ counts) {
   const int tid = threadIdx.x;
@@ -54,7 +56,18 @@ __global__ void __launch_bounds__(THREADS) cb_kernel(const float4* __restrict__ 
       const u64 hx = pack2(h[r].x, h[r].x), hy = pack2(h[r].y, h[r].y), hz = pack2(h[r].z, h[r].z), hd = pack2(h[r].w, h[r].w);
       const u64 s01 = ffma2(hx, x01, ffma2(hy, y01, ffma2(hz, z01, hd)));
       const u64 s23 = ffma2(hx, x23, ffma2(hy, y23, ffma2(hz, z23, hd)));
-      if (COUNT == 0 || (COUNT == 2 && (r % 3) != 0)) {
+      if (COUNT == 7 || (COUNT == 8 && (r % 3) != 0) || (COUNT == 9 && (r % 4) != 0) || (COUNT == 10 && (r % 2) != 0)) {
+        float a, b, c, d;
+        unpack2(s01, a, b); unpack2(s23, c, d);
+        uint32_t c0 = cnt[r];
+        asm("{\n\t.reg .f32 f0, f1, f2, f3;\n\t.reg .b32 t0, t1, t2, t3;\n\t"
+            "set.lt.f32.f32 f0, %1, %5;\n\tset.lt.f32.f32 f1, %2, %5;\n\tset.lt.f32.f32 f2, %3, %5;\n\tset.lt.f32.f32 f3, %4, %5;\n\t"
+            "mov.b32 t0, f0;\n\tmov.b32 t1, f1;\n\tmov.b32 t2, f2;\n\tmov.b32 t3, f3;\n\t"
+            "shr.u32 t0, t0, 29;\n\tshr.u32 t1, t1, 29;\n\tshr.u32 t2, t2, 29;\n\tshr.u32 t3, t3, 29;\n\t"
+            "add.u32 %0, %0, t0;\n\tadd.u32 %0, %0, t1;\n\tadd.u32 %0, %0, t2;\n\tadd.u32 %0, %0, t3;\n\t}"
+            : "+r"(c0) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)), "f"(fabsf(d)), "f"(delta));
+        cnt[r] = c0;
+      } else if (COUNT == 0 || COUNT == 8 || COUNT == 9 || COUNT == 10 || (COUNT == 2 && (r % 3) != 0)) {
         float a, b, c, d;
         unpack2(s01, a, b); unpack2(s23, c, d);
         uint32_t c0 = cnt[r];
@@ -191,18 +204,14 @@ int main() {
   std::vector<uint32_t> ref(HREF);
   CK(cudaMemcpy(ref.data(), refc, 4 * HREF, cudaMemcpyDeviceToHost));
   run<12, 128, 0, 272>("const-bank, setp", dch, N, hyp, H, delta, counts, ref);
-  run<12, 128, 0, 544>("const-bank, setp", dch, N, hyp, H, delta, counts, ref);
-  run<12, 128, 3, 272>("const-bank, setp+DADD", dch, N, hyp, H, delta, counts, ref);
-  run<12, 128, 4, 272>("const-bank, FSETP/DSETP", dch, N, hyp, H, delta, counts, ref);
-  run<12, 128, 5, 272>("const-bank, FSETP/DSETP+DADD", dch, N, hyp, H, delta, counts, ref);
-  run<12, 128, 6, 272>("const-bank, setp, add/DADD", dch, N, hyp, H, delta, counts, ref);
-  run<8, 128, 3, 272>("const-bank, setp+DADD", dch, N, hyp, H, delta, counts, ref);
-  run<8, 128, 4, 272>("const-bank, FSETP/DSETP", dch, N, hyp, H, delta, counts, ref);
-  run<8, 128, 5, 272>("const-bank, FSETP/DSETP+DADD", dch, N, hyp, H, delta, counts, ref);
-  run<8, 128, 6, 272>("const-bank, setp, add/DADD", dch, N, hyp, H, delta, counts, ref);
-  run<10, 128, 4, 272>("const-bank, FSETP/DSETP", dch, N, hyp, H, delta, counts, ref);
-  run<10, 128, 6, 272>("const-bank, setp, add/DADD", dch, N, hyp, H, delta, counts, ref);
-  run<12, 256, 4, 272>("const-bank, FSETP/DSETP", dch, N, hyp, H, delta, counts, ref);
-  run<12, 256, 6, 272>("const-bank, setp, add/DADD", dch, N, hyp, H, delta, counts, ref);
+  run<12, 128, 7, 272>("const-bank, fset+lea", dch, N, hyp, H, delta, counts, ref);
+  run<12, 128, 8, 272>("const-bank, 1/3 padd 2/3 fset", dch, N, hyp, H, delta, counts, ref);
+  run<12, 128, 9, 272>("const-bank, 1/4 padd 3/4 fset", dch, N, hyp, H, delta, counts, ref);
+  run<12, 128, 10, 272>("const-bank, 1/2 padd 1/2 fset", dch, N, hyp, H, delta, counts, ref);
+  run<9, 128, 8, 272>("const-bank, 1/3 padd 2/3 fset", dch, N, hyp, H, delta, counts, ref);
+  run<8, 128, 9, 272>("const-bank, 1/4 padd 3/4 fset", dch, N, hyp, H, delta, counts, ref);
+  run<8, 128, 10, 272>("const-bank, 1/2 padd 1/2 fset", dch, N, hyp, H, delta, counts, ref);
+  run<12, 256, 8, 272>("const-bank, 1/3 padd 2/3 fset", dch, N, hyp, H, delta, counts, ref);
+  run<15, 128, 8, 272>("const-bank, 1/3 padd 2/3 fset", dch, N, hyp, H, delta, counts, ref);
   return 0;
 }
