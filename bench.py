@@ -90,6 +90,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def load_traffic():
+    """DRAM bytes per launch from the committed ncu --set full captures (profiles/r01_traffic.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    except Exception:
+        return {}
+
+
+def workload_config(model, N, Hper, world, precision, delta):
+    """The `config` object both arms print: BASELINE.json configs[1] unless overridden on the command line."""
+    return {"workload": f"{model} RANSAC (BASELINE.json configs[1]): {N} synthetic points, 40% outliers, {Hper} Philox hypotheses per GPU, delta={delta}",
+            "points": N, "hypotheses_per_gpu": Hper, "hypotheses_total": Hper * world, "precision": precision,
+            "parallelism": f"points replicated, hypotheses partitioned x{world}, 1 all-reduce(max) on the packed key",
+            "l2": "256 MB flush buffer written between steps"}
+
+
 def make_data(model, n):
     from lsqrrecipes_b200 import synth
     data, true = synth.GENERATORS[model](n, seed=synth.SEED)
@@ -121,9 +137,10 @@ def run_reference_arm(args):
         return
     data, delta = make_data(args.model, args.points)
     cores = os.cpu_count() or 1
-    n_hyps = args.cpu_sample_hyps or max(cores * 2, 16)
+    # ~5 s of host work per step at the ~2e9 evals/s the 16-core GPU box reaches on 10 M points
+    n_hyps = args.cpu_sample_hyps or max(1, int(64 * cores * 10_000_000 / max(args.points, 1)))
     for _ in range(args.warmup):
-        cpu_reference_run(args.model, data, delta, max(cores, 4))
+        cpu_reference_run(args.model, data, delta, max(n_hyps // 8, 1))
     times, info = [], None
     t_all = time.perf_counter()
     for _ in range(args.steps):
@@ -135,8 +152,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "hypothesis x point agree() evals/sec", "value": value, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.model} RANSAC consensus, {args.points} synthetic points, 40% outliers (BASELINE.json configs[1])",
-                   "sample": f"{n_hyps} hypotheses x {args.points} points per step"},
+        "config": dict(workload_config(args.model, args.points, args.hyps, args.gpus, args.precision, delta),
+                       sample=f"each step times {n_hyps} of the hypotheses x all {args.points} points on the host cores (fp64, the reference's arithmetic)"),
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": info["cores"], "kind": info["kind"],
                          "sample": f"{n_hyps} hypotheses x {args.points} points per step, estimate()+agree() loop of RANSAC.hxx:217-249, OpenMP over hypotheses"},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -226,8 +243,16 @@ def main():
         achieved = kern_evals * 9 / (kern_ms * 1e-3) / 1e12    # as-written 3 DSUB + 4 DMUL + 2 DADD, no FMA
         peak = dfma / 1e12                                       # one lane-op per cycle per fp64 lane
         bound = "fp64_pipe"
-    roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "consensus_kernel", "kernel_ms": kern_ms,
+    traffic = load_traffic()
+    tr = traffic.get("consensus_cb_kernel", {})
+    cb_match = precision == FP32 and tr.get("config") == {"model": model, "points": N, "hyps": Hper}
+    n_kernel_launches = -(-N // tr["points_per_launch"]) if cb_match else None
+    roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": tr["bytes_per_launch"] if cb_match else None,
+                "kernel": "consensus_cb_kernel" if (precision == FP32 and Hper >= 98304) else "consensus_kernel", "kernel_ms": kern_ms,
+                "launches_per_step": n_kernel_launches,
+                "algorithmic_flop_per_launch": (float(Hper) * tr["points_per_launch"] * FLOP_PER_EVAL[model]) if cb_match else None,
+                "avg_launch_ms": (kern_ms / n_kernel_launches) if cb_match else None,
                 "peak_source": "measured live: register-resident FFMA chain (lsqr_microbench_fma); not in MEASURED_PEAKS.json",
                 "ffma_tflops": ffma * 2 / 1e12, "ffma2_tflops": ffma2 * 2 / 1e12, "dfma_tflops": dfma * 2 / 1e12,
                 "algorithmic_flop_per_eval": FLOP_PER_EVAL[model] if precision == FP32 else 9}
@@ -263,9 +288,11 @@ def main():
         e2e = {"value": evals_per_step * ke / dt, "unit": "evals/s", "h2d_bytes_per_step": int(N * data.shape[1] * 8),
                "d2h_bytes_per_step": int(N + 8 * 16), "ms_per_step": 1e3 * dt / ke, "steps": ke,
                "inlier_fraction": cnt / N, "params": [float(x) for x in prm]}
+        trm = traffic.get("mask_moments_kernel", {})
         roofline_refine = {"bound": "hbm", "achieved": rs["bytes"] / (rs["kernel_ms"] * 1e-3) / 1e9 if rs["kernel_ms"] > 0 else None,
                            "peak": hbm_peak, "unit": "GB/s", "kernel": "mask_moments_kernel", "kernel_ms": rs["kernel_ms"],
-                           "traffic": None}
+                           "algorithmic_bytes": rs["bytes"],
+                           "traffic": trm.get("bytes_per_launch") if trm.get("config") == {"model": model, "points": N} else None}
         if roofline_refine["achieved"]:
             roofline_refine["frac"] = roofline_refine["achieved"] / hbm_peak
     else:
@@ -274,7 +301,8 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_hyps = args.cpu_sample_hyps or max(4 * cores, 64)
+        # bounded sample: ~20 s of host work (SURVEY.md 8d measured ~1.5e8 evals/s per core)
+        n_hyps = args.cpu_sample_hyps or max(1, int(256 * cores * 10_000_000 / max(N, 1)))
         info = cpu_reference_run(model, data, delta, n_hyps)
         cpu = {"value": info["evals"] / info["seconds"], "unit": "evals/s", "cores": info["cores"], "kind": info["kind"],
                "sample": f"{n_hyps} hypotheses x {N} points, estimate()+agree() loop (RANSAC.hxx:217-249), OpenMP over hypotheses, {info['seconds']:.1f} s"}
@@ -284,10 +312,7 @@ def main():
             "metric": "hypothesis x point agree() evals/sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if precision == FP32 else "f64", "data": "synthetic",
-            "config": {"workload": f"{model} RANSAC (BASELINE.json configs[1]): {N} synthetic points, 40% outliers, {Hper} Philox hypotheses per GPU, delta={delta}",
-                       "points": N, "hypotheses_per_gpu": Hper, "hypotheses_total": Hglobal, "precision": args.precision,
-                       "parallelism": f"points replicated, hypotheses partitioned x{world}, 1 all-reduce(max) on the packed key",
-                       "l2": "256 MB flush buffer written between steps"},
+            "config": workload_config(model, N, Hper, world, args.precision, delta),
             "roofline": roofline, "roofline_refine": roofline_refine, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clk.summary(),
             "best_count": int(r["best_count"]),

@@ -70,6 +70,8 @@ struct lsqr_ctx {
   RefineBuffers rb{};
   // pinned host scratch
   double* pin = nullptr;                  // 64 doubles
+  uint8_t* mask_dev = nullptr; size_t mask_dev_cap = 0;   // consensus set, one byte per datum (device)
+  uint8_t* mask_pin = nullptr; size_t mask_pin_cap = 0;   // pinned bounce buffer for its download
   cudaEvent_t ev[6]{};
 
   // sharding
@@ -395,12 +397,19 @@ int refine_impl(lsqr_ctx* ctx, DataSet& ds, int use_mask, double* out_params, in
 int get_mask_impl(lsqr_ctx* ctx, DataSet& ds, uint8_t* out_bytes) {
   if (!ds.mask_valid) return fail(ctx, LSQR_ERR_STATE, "no consensus set stored");
   if (!out_bytes || ds.n == 0) return LSQR_OK;
-  uint8_t* tmp = nullptr;
-  CK(cudaMalloc((void**)&tmp, ds.n));
-  launch_expand_mask(ds.maskbits, ds.n, tmp, ctx->stream); ctx->launches++;
-  cudaError_t e1 = cudaMemcpyAsync(out_bytes, tmp, ds.n, cudaMemcpyDeviceToHost, ctx->stream);
+  // persistent device + pinned buffers: a cudaMalloc/cudaFree pair per call costs up to 0.3 s after the
+  // thousands of launches of a large request, and a pageable destination is staged by the driver
+  if (int rc = ensure(ctx, &ctx->mask_dev, &ctx->mask_dev_cap, (size_t)ds.n)) return rc;
+  if (ctx->mask_pin_cap < ds.n) {
+    if (ctx->mask_pin) cudaFreeHost(ctx->mask_pin);
+    ctx->mask_pin = nullptr; ctx->mask_pin_cap = 0;
+    CK(cudaMallocHost((void**)&ctx->mask_pin, ds.n));
+    ctx->mask_pin_cap = ds.n;
+  }
+  launch_expand_mask(ds.maskbits, ds.n, ctx->mask_dev, ctx->stream); ctx->launches++;
+  cudaError_t e1 = cudaMemcpyAsync(ctx->mask_pin, ctx->mask_dev, ds.n, cudaMemcpyDeviceToHost, ctx->stream);
   cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-  cudaFree(tmp);
+  if (e1 == cudaSuccess && e2 == cudaSuccess) memcpy(out_bytes, ctx->mask_pin, ds.n);
   if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(ctx, LSQR_ERR_CUDA, "mask download failed");
   return LSQR_OK;
 }
@@ -448,7 +457,7 @@ int lsqr_ctx_create(lsqr_ctx** out, int device) {
   ctx->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(LSQR_ERR_CUDA);
   ctx->own_stream = true;
-  ctx->rb.blocks = ctx->num_sms * 8;
+  ctx->rb.blocks = ctx->num_sms * mask_moments_ctas_per_sm();   // one wave of resident CTAs
   bool ok = cudaMalloc((void**)&ctx->key_dev, 4 * sizeof(unsigned long long)) == cudaSuccess &&
             cudaMalloc((void**)&ctx->small_dev, 256 * sizeof(double)) == cudaSuccess &&
             cudaMalloc((void**)&ctx->center_dev, 12 * sizeof(double)) == cudaSuccess &&
@@ -467,6 +476,7 @@ void lsqr_ctx_destroy(lsqr_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (DataSet* ds : {&ctx->main, &ctx->scratch}) { cudaFree(ds->soa64); cudaFree(ds->soa32); cudaFree(ds->maskbits); }
+  cudaFree(ctx->mask_dev); if (ctx->mask_pin) cudaFreeHost(ctx->mask_pin);
   cudaFree(ctx->staging); cudaFree(ctx->subsets); cudaFree(ctx->hyp64); cudaFree(ctx->hyp32); cudaFree(ctx->counts);
   cudaFree(ctx->list_dev); cudaFree(ctx->params_in_dev); cudaFree(ctx->key_dev); cudaFree(ctx->small_dev);
   cudaFree(ctx->center_dev); cudaFree(ctx->center_partials); cudaFree(ctx->rb.partials); cudaFree(ctx->rb.moments);

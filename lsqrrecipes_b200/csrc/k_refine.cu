@@ -29,6 +29,13 @@ __host__ __device__ inline int n_moments(int model, bool lm) {
   }
   return 0;
 }
+#ifndef LSQR_MM_CTAS
+#define LSQR_MM_CTAS 2
+#endif
+#ifndef LSQR_MM_U
+#define LSQR_MM_U 8
+#endif
+int mask_moments_ctas_per_sm() { return LSQR_MM_CTAS; }
 int moments_count(int model, bool lm) { return n_moments(model, lm); }
 
 template <int M> struct Mom { static constexpr int N = 0, NLM = 0; };
@@ -134,12 +141,16 @@ __host__ __device__ inline bool centred_comp(int model, int d) {
 }
 
 // MODE 0: every datum counts; 1: evaluate agree() and write the consensus bits; 2: read stored bits.
+// HBM-bound streaming pass.  Two resident CTAs per SM (grid = 2 x SMs, one wave); every warp keeps
+// U rows of 32 data (U*D 8-byte loads per lane, ~48 registers) in flight before it touches them, so
+// that ~100 KB per SM are outstanding -- what a 6.5 TB/s stream needs at ~600 ns latency.
 template <int M, int MODE, bool LM>
-__global__ void __launch_bounds__(256) mask_moments_kernel(DataView dv, uint32_t begin, uint32_t end, const double* __restrict__ params_dev,
-                                                            const double* __restrict__ lm_state, EstCfg cfg, uint32_t* __restrict__ maskbits,
-                                                            double* __restrict__ partials) {
+__global__ void __launch_bounds__(256, LSQR_MM_CTAS) mask_moments_kernel(DataView dv, uint32_t begin, uint32_t end, const double* __restrict__ params_dev,
+                                                               const double* __restrict__ lm_state, EstCfg cfg, uint32_t* __restrict__ maskbits,
+                                                               double* __restrict__ partials) {
   constexpr int D = Model<M>::D, P = Model<M>::P, HQ = Model<M>::HQ;
   constexpr int NM = LM ? Mom<M>::NLM : Mom<M>::N;
+  constexpr int U = LM ? 4 : (D <= 3 ? LSQR_MM_U : (D <= 6 ? 4 : 2));
   double acc[NM > 0 ? NM : 1];
 #pragma unroll
   for (int j = 0; j < NM; j++) acc[j] = 0.0;
@@ -160,26 +171,38 @@ __global__ void __launch_bounds__(256) mask_moments_kernel(DataView dv, uint32_t
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  for (uint64_t base = (uint64_t)begin + (uint64_t)warp * 32; base < end; base += (uint64_t)warps_total * 32) {
-    const uint64_t i = base + lane;
-    double x[D];
+  for (uint64_t base = (uint64_t)begin + (uint64_t)warp * (32 * U); base < end; base += (uint64_t)warps_total * (32 * U)) {
+    double x[U][D];
+    uint32_t stored[U];
 #pragma unroll
-    for (int d = 0; d < D; d++) x[d] = dv.soa64[(size_t)d * dv.ld + i];  // padded with NaN beyond n: never agrees
-    bool in;
-    if (MODE == 0) in = i < end;
-    else if (MODE == 1) {
-      in = (i < end) && agree<M>(hq, x, cfg);
-      const unsigned bits = __ballot_sync(0xffffffffu, in);
-      if (lane == 0) maskbits[base >> 5] = bits;
-    } else in = (i < end) && ((maskbits[base >> 5] >> lane) & 1u);
-    if (in) {
-      double q[D];
+    for (int u = 0; u < U; u++) {
+      const uint64_t row = base + 32 * u;   // rows start on multiples of 32; the arrays are NaN-padded to ld >= end rounded up to 1024
+      if (row < end) {
 #pragma unroll
-      for (int d = 0; d < D; d++) q[d] = centred_comp(M, d) ? x[d] - dv.center[d] : x[d];
-      if (LM) {
-        if constexpr (M == CIRCLE2) acc_sphere_lm<2>(q, lmx, acc);
-        if constexpr (M == SPHERE3) acc_sphere_lm<3>(q, lmx, acc);
-      } else accumulate<M>(q, acc);
+        for (int d = 0; d < D; d++) x[u][d] = __ldcs(dv.soa64 + (size_t)d * dv.ld + row + lane);
+        if (MODE == 2) stored[u] = maskbits[row >> 5];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t row = base + 32 * u, i = row + lane;
+      if (row >= end) break;
+      bool in;
+      if (MODE == 0) in = i < end;
+      else if (MODE == 1) {
+        in = (i < end) && agree<M>(hq, x[u], cfg);   // NaN padding beyond n never agrees
+        const unsigned bits = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) maskbits[row >> 5] = bits;
+      } else in = (i < end) && ((stored[u] >> lane) & 1u);
+      if (in) {
+        double q[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) q[d] = centred_comp(M, d) ? x[u][d] - dv.center[d] : x[u][d];
+        if (LM) {
+          if constexpr (M == CIRCLE2) acc_sphere_lm<2>(q, lmx, acc);
+          if constexpr (M == SPHERE3) acc_sphere_lm<3>(q, lmx, acc);
+        } else accumulate<M>(q, acc);
+      }
     }
   }
   // block reduction: shuffle within warps, shared memory across the 8 warps
