@@ -14,6 +14,7 @@
 #include "lsqrRecipes/Line2DParametersEstimator.h"
 #include "lsqrRecipes/LineParametersEstimator.h"
 #include "lsqrRecipes/PivotCalibrationParametersEstimator.h"
+#include "lsqrRecipes/DenseLinearEquationSystemParametersEstimator.h"
 #include "lsqrRecipes/PlaneParametersEstimator.h"
 #include "lsqrRecipes/RANSAC.h"
 #include "lsqrRecipes/RayIntersectionParametersEstimator.h"
@@ -206,6 +207,34 @@ static void pivotCase() {
   }
 }
 
+// examples/linearEquationSystemSolver.cxx: a consistent 5-column system with gross outliers
+static void denseCase() {
+  std::printf("DenseLinearEquationSystemParametersEstimator<double,5>\n");
+  const unsigned int n = 5;
+  double x[n];
+  for (unsigned int j = 0; j < n; j++) x[j] = uni(-100, 100);
+  std::vector<AugmentedRow<double, n> > rows;
+  for (int i = 0; i < 4000; i++) {
+    double r[n + 1];
+    r[n] = gauss(0.03);
+    for (unsigned int j = 0; j < n; j++) { r[j] = uni(-100, 100); r[n] += r[j] * x[j]; }
+    if (i % 10 >= 7) r[n] += uni(5, 5000);   // 30 % outliers
+    rows.push_back(AugmentedRow<double, n>(r));
+  }
+  DenseLinearEquationSystemParametersEstimator<double, n> est(0.2);
+  std::vector<double> prm;
+  std::vector<bool> cs;
+  const double frac = RANSAC<AugmentedRow<double, n>, double>::compute(prm, &est, rows, 0.999, &cs);
+  CHECK(prm.size() == n && frac > 0.65, "linear system RANSAC");
+  if (prm.size() == n) {
+    double e = 0;
+    for (unsigned int j = 0; j < n; j++) e += std::fabs(prm[j] - x[j]);
+    std::printf("  fraction %.4f  |error|_1 %.4g\n", frac, e);
+    CHECK(e < 1e-3, "solution recovered");
+    CHECK(est.agree(prm, rows[0]) && !est.agree(prm, rows[7]), "agree() on an inlier row and on an outlier row");
+  }
+}
+
 // A user-defined estimator has no GPU path: same failure convention as a degenerate data set.
 class UserEstimator : public ParametersEstimator<Point2D, double> {
  public:
@@ -225,6 +254,7 @@ int main() {
   absorCase();
   rayCase();
   pivotCase();
+  denseCase();
   std::printf("user-defined estimator\n");
   UserEstimator user;
   std::vector<Point2D> pts(10);

@@ -44,7 +44,9 @@ typedef enum lsqr_model {
   LSQR_ABSOR = 6,   /* AbsoluteOrientationParametersEstimator AbsoluteOrientationParametersEstimator.cxx:14-327 */
   LSQR_RAY = 7,     /* RayIntersectionParametersEstimator     RayIntersectionParametersEstimator.cxx:23-179 */
   LSQR_PIVOT = 8,   /* PivotCalibrationEstimator              PivotCalibrationParametersEstimator.cxx:9-123 */
-  LSQR_NUM_MODELS = 9
+  LSQR_DENSE5 = 9,  /* DenseLinearEquationSystemParametersEstimator<double,5>   DenseLinearEquationSystemParametersEstimator.hxx:17-119 */
+  LSQR_DENSE6 = 10, /* DenseLinearEquationSystemParametersEstimator<double,6>   (datum = AugmentedRow: n coefficients, right-hand side) */
+  LSQR_NUM_MODELS = 11
 } lsqr_model;
 
 typedef enum lsqr_status {
@@ -71,7 +73,7 @@ typedef enum lsqr_sampler {
 typedef enum lsqr_ls_type { LSQR_LS_ALGEBRAIC = 0, LSQR_LS_GEOMETRIC = 1 } lsqr_ls_type;
 
 #define LSQR_MAX_PARAMS 8
-#define LSQR_MAX_SUBSET 4
+#define LSQR_MAX_SUBSET 6
 
 /* ---- model table ------------------------------------------------------------------ */
 /* dim = doubles per datum, nparams = length of the parameter vector, k = numForEstimate()

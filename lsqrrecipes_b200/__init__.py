@@ -32,11 +32,12 @@ from .estimators import (  # noqa: F401
     AbsoluteOrientationParametersEstimator,
     RayIntersectionParametersEstimator,
     PivotCalibrationEstimator,
+    DenseLinearEquationSystemParametersEstimator,
 )
 
 __all__ = [
     "Engine", "LsqrError", "MODELS", "MODEL_INFO", "FP32", "FP64", "RANSAC",
     "PlaneParametersEstimator", "LineParametersEstimator", "Line2DParametersEstimator",
     "SphereParametersEstimator", "AbsoluteOrientationParametersEstimator",
-    "RayIntersectionParametersEstimator", "PivotCalibrationEstimator",
+    "RayIntersectionParametersEstimator", "PivotCalibrationEstimator", "DenseLinearEquationSystemParametersEstimator",
 ]

@@ -71,6 +71,7 @@ __device__ __forceinline__ f2 join(float lo, float hi) { f2 r; asm("mov.b64 %0, 
 //   ABSOR    (R[9], R c1 + t - c2)
 //   RAY      (x - c)
 //   PIVOT    (tDRF, tW - c)
+//   DENSE n  (x[n], -1): a.x - b as n+1 FMAs over the (uncentred) augmented row
 template <int M> __device__ __forceinline__ void hoist32(const double* p, const double* c, const EstCfg& cfg, float* q);
 template <> __device__ __forceinline__ void hoist32<PLANE3>(const double* p, const double* c, const EstCfg&, float* q) {
   q[0] = (float)p[0]; q[1] = (float)p[1]; q[2] = (float)p[2];
@@ -108,6 +109,13 @@ template <> __device__ __forceinline__ void hoist32<RAY>(const double* p, const 
 template <> __device__ __forceinline__ void hoist32<PIVOT>(const double* p, const double* c, const EstCfg&, float* q) {
   for (int i = 0; i < 3; i++) { q[i] = (float)p[i]; q[3 + i] = (float)(p[3 + i] - c[9 + i]); }
 }
+
+template <int N> __device__ __forceinline__ void hoist_dense(const double* p, float* q) {
+  for (int i = 0; i < N; i++) q[i] = (float)p[i];
+  q[N] = -1.0f;
+}
+template <> __device__ __forceinline__ void hoist32<DENSE5>(const double* p, const double*, const EstCfg&, float* q) { hoist_dense<5>(p, q); }
+template <> __device__ __forceinline__ void hoist32<DENSE6>(const double* p, const double*, const EstCfg&, float* q) { hoist_dense<6>(p, q); }
 
 template <int M>
 __global__ void hoist32_kernel(const double* __restrict__ hyp64, size_t hld, uint32_t H, DataView dv, EstCfg cfg, float* __restrict__ hyp32) {
@@ -158,6 +166,8 @@ __device__ __forceinline__ void load_hyp32(const float* __restrict__ hyp, size_t
     case ABSOR: { CALL(ABSOR); break; }       \
     case RAY: { CALL(RAY); break; }           \
     case PIVOT: { CALL(PIVOT); break; }       \
+    case DENSE5: { CALL(DENSE5); break; }     \
+    case DENSE6: { CALL(DENSE6); break; }     \
     default: break;                           \
   }
 
@@ -263,6 +273,24 @@ template <> struct Eval<PIVOT> {
     }
     return g;
   }
+};
+
+// |a.x - b| < delta: n+1 FMAs, the last constant is -1 (DenseLinearEquationSystemParametersEstimator.hxx:111-119)
+template <int N> __device__ __forceinline__ f2 dense_dist(const f2* q, const f2* x) {
+  f2 s = mul2(q[N], x[N]);
+#pragma unroll
+  for (int i = N - 1; i >= 0; i--) s = fma2(q[i], x[i], s);
+  return s;
+}
+template <> struct Eval<DENSE5> {
+  static constexpr bool kHasAbsForm = true;
+  __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return dense_dist<5>(q, x); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
+};
+template <> struct Eval<DENSE6> {
+  static constexpr bool kHasAbsForm = true;
+  __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return dense_dist<6>(q, x); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
 };
 
 // FSETP + predicated IADD on two residuals, written in PTX so that ptxas keeps the 2-instruction form.
@@ -489,6 +517,8 @@ template <> struct BlockCB<SPHERE3> { static constexpr int R = 10, PPI = 2; };
 template <> struct BlockCB<ABSOR> { static constexpr int R = 4, PPI = 2; };
 template <> struct BlockCB<RAY> { static constexpr int R = 8, PPI = 2; };
 template <> struct BlockCB<PIVOT> { static constexpr int R = 6, PPI = 1; };
+template <> struct BlockCB<DENSE5> { static constexpr int R = 8, PPI = 2; };
+template <> struct BlockCB<DENSE6> { static constexpr int R = 8, PPI = 2; };
 
 template <int M>
 static int run_consensus_cb(const DataView& dv, const float* hyp, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms, cudaStream_t s) {
@@ -547,6 +577,8 @@ template <> struct Block32<SPHERE3> { static constexpr int R = 8, PPI = 2; };
 template <> struct Block32<ABSOR> { static constexpr int R = 3, PPI = 1; };
 template <> struct Block32<RAY> { static constexpr int R = 8, PPI = 1; };
 template <> struct Block32<PIVOT> { static constexpr int R = 4, PPI = 1; };
+template <> struct Block32<DENSE5> { static constexpr int R = 6, PPI = 2; };
+template <> struct Block32<DENSE6> { static constexpr int R = 6, PPI = 2; };
 
 int launch_consensus32(int model, const DataView& dv, const float* hyp32, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms,
                        cudaStream_t s) {

@@ -26,6 +26,8 @@ __host__ __device__ inline int n_moments(int model, bool lm) {
     case ABSOR: return 16;
     case RAY: return 10;
     case PIVOT: return 22;
+    case DENSE5: return 21;   // count, A^T A upper triangle (15), A^T b (5)
+    case DENSE6: return 28;   // count, 21, 6
   }
   return 0;
 }
@@ -48,6 +50,8 @@ template <> struct Mom<SPHERE3> { static constexpr int N = 14, NLM = 16; };
 template <> struct Mom<ABSOR>   { static constexpr int N = 16, NLM = 0; };
 template <> struct Mom<RAY>     { static constexpr int N = 10, NLM = 0; };
 template <> struct Mom<PIVOT>   { static constexpr int N = 22, NLM = 0; };
+template <> struct Mom<DENSE5>  { static constexpr int N = 21, NLM = 0; };
+template <> struct Mom<DENSE6>  { static constexpr int N = 28, NLM = 0; };
 
 // q = centred datum.  acc[0] counts.
 template <int DIM> __device__ __forceinline__ void acc_scatter(const double* q, double* acc) {
@@ -132,10 +136,25 @@ template <> __device__ __forceinline__ void accumulate<PIVOT>(const double* q, d
   for (int a = 0; a < 3; a++) acc[o++] += q[9 + a];                                                      // sum t
 }
 
+// Normal equations of the rows a.x = b (DenseLinearEquationSystemParametersEstimator.hxx:64-96)
+template <int N> __device__ __forceinline__ void acc_dense(const double* q, double* acc) {
+  acc[0] += 1.0;
+  int o = 1;
+#pragma unroll
+  for (int a = 0; a < N; a++)
+#pragma unroll
+    for (int b = a; b < N; b++) acc[o++] += q[a] * q[b];
+#pragma unroll
+  for (int a = 0; a < N; a++) acc[o++] += q[a] * q[N];
+}
+template <> __device__ __forceinline__ void accumulate<DENSE5>(const double* q, double* acc) { acc_dense<5>(q, acc); }
+template <> __device__ __forceinline__ void accumulate<DENSE6>(const double* q, double* acc) { acc_dense<6>(q, acc); }
+
 __host__ __device__ inline bool centred_comp(int model, int d) {
   switch (model) {
     case RAY: return d < 3;
     case PIVOT: return d >= 9;
+    case DENSE5: case DENSE6: return false;
     default: return true;
   }
 }
@@ -246,6 +265,8 @@ void launch_mask_moments(int model, const DataView& dv, uint32_t begin, uint32_t
     case ABSOR: { BYMODE(ABSOR, false); break; }
     case RAY: { BYMODE(RAY, false); break; }
     case PIVOT: { BYMODE(PIVOT, false); break; }
+    case DENSE5: { BYMODE(DENSE5, false); break; }
+    case DENSE6: { BYMODE(DENSE6, false); break; }
   }
 #undef BYMODE
 #undef LAUNCH
@@ -395,6 +416,16 @@ __device__ int solve_pivot(const double* m, const double* c, double* out) {
   return 6;
 }
 
+// DenseLinearEquationSystemParametersEstimator.hxx:64-96 through the n x n normal equations; rank < n -> no solution
+template <int N> __device__ int solve_dense(const double* m, double* out) {
+  if (m[0] < (double)N) return 0;
+  double A[N * N], b[N];
+  int o = 1;
+  for (int a = 0; a < N; a++) for (int bb = a; bb < N; bb++) { const double v = m[o++]; A[a * N + bb] = v; A[bb * N + a] = v; }
+  for (int a = 0; a < N; a++) b[a] = m[o++];
+  return sym_pinv_solve<N>(A, b, out) < N ? 0 : N;
+}
+
 // out[0] = number of parameters (0 = the reference's empty vector), out[1..] = parameters.
 // For CIRCLE2/SPHERE3 the parameters stay in centred coordinates when keep_centred != 0 (LM start).
 __global__ void solve_moments_kernel(int model, DataView dv, const double* __restrict__ m, int keep_centred, double* __restrict__ out) {
@@ -412,6 +443,8 @@ __global__ void solve_moments_kernel(int model, DataView dv, const double* __res
     case ABSOR: np = solve_absor(m, c, p); break;
     case RAY: np = solve_ray(m, c, p); break;
     case PIVOT: np = solve_pivot(m, c, p); break;
+    case DENSE5: np = solve_dense<5>(m, p); break;
+    case DENSE6: np = solve_dense<6>(m, p); break;
   }
   out[0] = (double)np;
   for (int j = 0; j < np; j++) out[1 + j] = p[j];
@@ -712,6 +745,8 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
       case ABSOR: np = solve_absor(m, c, p); break;
       case RAY: np = solve_ray(m, c, p); break;
       case PIVOT: np = solve_pivot(m, c, p); break;
+      case DENSE5: np = solve_dense<5>(m, p); break;
+      case DENSE6: np = solve_dense<6>(m, p); break;
     }
     sh_out[0] = np;
     for (int j = 0; j < np; j++) sh_out[1 + j] = p[j];
@@ -761,6 +796,8 @@ int launch_batch(const BatchArgs& a, const EstCfg& cfg, int ls_type, cudaStream_
     case ABSOR: CALL(ABSOR) break;
     case RAY: CALL(RAY) break;
     case PIVOT: CALL(PIVOT) break;
+    case DENSE5: CALL(DENSE5) break;
+    case DENSE6: CALL(DENSE6) break;
     default: return -1;
   }
 #undef CALL

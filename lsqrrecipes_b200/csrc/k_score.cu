@@ -68,6 +68,7 @@ __host__ __device__ inline bool centred_component(int model, int d) {
   switch (model) {
     case RAY: return d < 3;
     case PIVOT: return d >= 9;
+    case DENSE5: case DENSE6: return false;   // rows of a linear system: a shift would change the solution
     default: return true;
   }
 }
@@ -166,6 +167,8 @@ __global__ void __launch_bounds__(128) solve_kernel(SolveArgs a, const double* _
     case ABSOR: { CALL(ABSOR); break; }       \
     case RAY: { CALL(RAY); break; }           \
     case PIVOT: { CALL(PIVOT); break; }       \
+    case DENSE5: { CALL(DENSE5); break; }     \
+    case DENSE6: { CALL(DENSE6); break; }     \
     default: break;                           \
   }
 

@@ -14,7 +14,7 @@
 
 namespace lsqr {
 
-enum : int { PLANE3 = 0, LINE2D = 1, LINE2 = 2, LINE3 = 3, CIRCLE2 = 4, SPHERE3 = 5, ABSOR = 6, RAY = 7, PIVOT = 8, NUM_MODELS = 9 };
+enum : int { PLANE3 = 0, LINE2D = 1, LINE2 = 2, LINE3 = 3, CIRCLE2 = 4, SPHERE3 = 5, ABSOR = 6, RAY = 7, PIVOT = 8, DENSE5 = 9, DENSE6 = 10, NUM_MODELS = 11 };
 
 // dim = doubles per datum, P = parameters, K = minimal subset, HQ = doubles of a prepared
 // fp64 hypothesis, Q32 = floats of a hoisted fp32 hypothesis.
@@ -28,6 +28,9 @@ template <> struct Model<SPHERE3> { static constexpr int D = 3,  P = 4, K = 4, H
 template <> struct Model<ABSOR>   { static constexpr int D = 6,  P = 7, K = 3, HQ = 12, Q32 = 12; };
 template <> struct Model<RAY>     { static constexpr int D = 6,  P = 3, K = 2, HQ = 3,  Q32 = 3;  };
 template <> struct Model<PIVOT>   { static constexpr int D = 12, P = 6, K = 3, HQ = 6,  Q32 = 6;  };
+// DenseLinearEquationSystemParametersEstimator<double, n>: datum = AugmentedRow (n coefficients, right-hand side)
+template <> struct Model<DENSE5>  { static constexpr int D = 6,  P = 5, K = 5, HQ = 5,  Q32 = 6;  };
+template <> struct Model<DENSE6>  { static constexpr int D = 7,  P = 6, K = 6, HQ = 6,  Q32 = 7;  };
 
 struct ModelInfo { int D, P, K, HQ, Q32; };
 __host__ __device__ inline ModelInfo model_info(int m) {
@@ -41,6 +44,8 @@ __host__ __device__ inline ModelInfo model_info(int m) {
     case ABSOR:   return {6, 7, 3, 12, 12};
     case RAY:     return {6, 3, 2, 3, 3};
     case PIVOT:   return {12, 6, 3, 6, 6};
+    case DENSE5:  return {6, 5, 5, 5, 6};
+    case DENSE6:  return {7, 6, 6, 6, 7};
   }
   return {0, 0, 0, 0, 0};
 }
@@ -323,6 +328,16 @@ template <> __device__ inline bool estimate<PIVOT>(const double* d, const EstCfg
   return pinv_solve<9, 6>(A, b, kEps, prm) >= 6;
 }
 
+// DenseLinearEquationSystemParametersEstimator.hxx:17-49: n rows -> A x = b through the pseudo-inverse,
+// singular values <= EPS zeroed, rank < n fails.
+template <int N> __device__ inline bool estimate_dense(const double* d, double* prm) {
+  double A[N * N], b[N];
+  for (int i = 0; i < N; i++) { for (int j = 0; j < N; j++) A[i * N + j] = d[i * (N + 1) + j]; b[i] = d[i * (N + 1) + N]; }
+  return pinv_solve<N, N>(A, b, kEps, prm) >= N;
+}
+template <> __device__ inline bool estimate<DENSE5>(const double* d, const EstCfg&, double* prm) { return estimate_dense<5>(d, prm); }
+template <> __device__ inline bool estimate<DENSE6>(const double* d, const EstCfg&, double* prm) { return estimate_dense<6>(d, prm); }
+
 // ---------------------------------------------------------------------------------------
 // agree(): prepare once per hypothesis, test once per (hypothesis, datum)
 // ---------------------------------------------------------------------------------------
@@ -398,6 +413,17 @@ template <> __device__ __forceinline__ bool agree<PIVOT>(const double* h, const 
   return sqrt(s) < cfg.delta;
 }
 
+// DenseLinearEquationSystemParametersEstimator.hxx:111-119
+template <int N> __device__ __forceinline__ bool agree_dense(const double* h, const double* x, const EstCfg& cfg) {
+  double sum = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; i++) sum += x[i] * h[i];
+  sum -= x[N];
+  return fabs(sum) < cfg.delta;
+}
+template <> __device__ __forceinline__ bool agree<DENSE5>(const double* h, const double* x, const EstCfg& c) { return agree_dense<5>(h, x, c); }
+template <> __device__ __forceinline__ bool agree<DENSE6>(const double* h, const double* x, const EstCfg& c) { return agree_dense<6>(h, x, c); }
+
 // ---------------------------------------------------------------------------------------
 // Subset generation
 // ---------------------------------------------------------------------------------------
@@ -420,7 +446,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 template <int K>
 __device__ __forceinline__ void sample_subset(uint64_t gidx, uint64_t seed, uint32_t n, int32_t* out) {
   const uint4 r = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  const uint32_t rnd[4] = {r.x, r.y, r.z, r.w};
+  uint32_t rnd[K > 4 ? 8 : 4] = {r.x, r.y, r.z, r.w};
+  if constexpr (K > 4) {   // second counter block for the 5th..8th draw
+    const uint4 r2 = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), 1u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    rnd[4] = r2.x; rnd[5] = r2.y; rnd[6] = r2.z; rnd[7] = r2.w;
+  }
   uint32_t sorted[K];
 #pragma unroll
   for (int j = 0; j < K; j++) {

@@ -140,6 +140,17 @@ class PivotCalibrationEstimator(ParametersEstimator):
         parameters.extend(self.engine().least_squares(d).tolist())
 
 
+class DenseLinearEquationSystemParametersEstimator(ParametersEstimator):
+    """DenseLinearEquationSystemParametersEstimator<double, n> (n = 5 or 6); datum = AugmentedRow as n+1 doubles
+    [a_0..a_{n-1}, b]; parameters = the solution x (DenseLinearEquationSystemParametersEstimator.hxx:17-119)."""
+
+    def __init__(self, delta, n):
+        if n not in (5, 6):
+            raise ValueError("dense linear systems are instantiated for n = 5 and n = 6 (the sizes the reference exercises)")
+        self._model = f"dense{n}"
+        super().__init__(n, delta)
+
+
 class RANSAC:
     """RANSAC<T,S> (RANSAC.h:47-151): two static compute() overloads."""
 

@@ -139,6 +139,19 @@ def pivot_frames(n, outlier_frac=0.2, seed=SEED, sigma=0.2):
     return out, np.concatenate([t_drf, t_w])
 
 
+def dense_rows(n, nc, outlier_frac=0.3, seed=SEED, sigma=0.03):
+    """Augmented rows [a | b] of a consistent system a.x = b: coefficients and solution ~ U(-100, 100) as in
+    examples/linearEquationSystemSolver.cxx:58-66, small noise on b, gross outliers in b."""
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-100, 100, nc)
+    A = rng.uniform(-100, 100, (n, nc))
+    b = A @ x + rng.normal(0, sigma, n)
+    n_out = int(round(n * outlier_frac))
+    idx = rng.permutation(n)[:n_out]
+    b[idx] += rng.uniform(5, 5000, n_out) * rng.choice([-1.0, 1.0], n_out)
+    return np.ascontiguousarray(np.concatenate([A, b[:, None]], axis=1)), x
+
+
 def frames_from_quat_file(path):
     """Rows 'x y z qx qy qz qs' (testing/Data/pivotCalibrationData.txt) -> packed frames,
     following testing/PivotCalibrationParametersEstimatorTest.cxx:29-33."""
@@ -160,8 +173,11 @@ GENERATORS = {
     "absor": lambda n, seed=SEED: absolute_orientation(n, seed=seed),
     "ray": lambda n, seed=SEED: rays(n, seed=seed),
     "pivot": lambda n, seed=SEED: pivot_frames(n, seed=seed),
+    "dense5": lambda n, seed=SEED: dense_rows(n, 5, seed=seed),
+    "dense6": lambda n, seed=SEED: dense_rows(n, 6, seed=seed),
 }
-DELTAS = {"plane3": 0.5, "line2d": 0.5, "line2": 0.5, "line3": 0.5, "circle2": 0.5, "sphere3": 0.5, "absor": 2.0, "ray": 1.0, "pivot": 1.0}
+DELTAS = {"plane3": 0.5, "line2d": 0.5, "line2": 0.5, "line3": 0.5, "circle2": 0.5, "sphere3": 0.5, "absor": 2.0, "ray": 1.0, "pivot": 1.0,
+          "dense5": 0.2, "dense6": 0.2}
 
 
 def random_subsets(n, k, H, seed=SEED):

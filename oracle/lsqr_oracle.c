@@ -21,7 +21,7 @@
 #include <omp.h>
 #endif
 
-enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8 };
+enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10 };
 
 /* common/Epsilon.h:19 */
 static const double EPS = 2.220446049250313e-016;
@@ -32,8 +32,8 @@ static const double FRAME_SMALL_ANGLE = 0.008726535498373935;
 static const double FRAME_HALF_PI = 3.14159265358979323846 / 2.0;
 
 int orc_model_info(int model, int* D, int* P, int* k) {
-  static const int tab[9][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}};
-  if (model < 0 || model > 8) return -1;
+  static const int tab[11][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}, {6, 5, 5}, {7, 6, 6}};
+  if (model < 0 || model > 10) return -1;
   *D = tab[model][0]; *P = tab[model][1]; *k = tab[model][2];
   return 0;
 }
@@ -359,6 +359,18 @@ static int pivot_solve(const double* d, size_t n, double* prm) {
   return rank < 6 ? 0 : 6;
 }
 
+/* Rows [a_i | b_i]: DenseLinearEquationSystemParametersEstimator.hxx:17-49 (rows = nc) and :64-96 (rows >= nc):
+ * x = pinv(A) b with singular values <= EPS zeroed, rank < nc -> no solution */
+static int dense_solve(int nc, const double* d, size_t rows, double* prm) {
+  size_t i; int j, rank;
+  double* A = (double*)malloc(rows * nc * sizeof(double));
+  double* b = (double*)malloc(rows * sizeof(double));
+  for (i = 0; i < rows; i++) { for (j = 0; j < nc; j++) A[i * nc + j] = d[i * (nc + 1) + j]; b[i] = d[i * (nc + 1) + nc]; }
+  rank = pinv_solve((int)rows, nc, A, b, EPS, prm);
+  free(A); free(b);
+  return rank < nc ? 0 : nc;
+}
+
 static double ray_cross_eps(double aux) {
   double a = aux > 0 ? aux : 0.017453292519943295769236907684886; /* RayIntersectionParametersEstimator.h:35 */
   double s = sin(a);
@@ -379,6 +391,8 @@ int orc_estimate(int model, double delta, double aux, const double* data, size_t
     case M_ABSOR: return absor_estimate(data, params);
     case M_RAY: return ray_estimate(data, ray_cross_eps(aux), params);
     case M_PIVOT: return pivot_solve(data, 3, params);
+    case M_DENSE5: return dense_solve(5, data, 5, params);
+    case M_DENSE6: return dense_solve(6, data, 6, params);
   }
   return -1;
 }
@@ -435,6 +449,14 @@ static int agree1(int model, double delta, const double* prm, const double* x) {
       for (i = 0; i < 3; i++) r[i] = q[i] - prm[3 + i];
       for (i = 0; i < 3; i++) s += r[i] * r[i];
       return sqrt(s) < delta;
+    }
+    case M_DENSE5:
+    case M_DENSE6: { /* DenseLinearEquationSystemParametersEstimator.hxx:111-119 */
+      const int nc = (model == M_DENSE5) ? 5 : 6;
+      double sum = 0.0; int i;
+      for (i = 0; i < nc; i++) sum += x[i] * prm[i];
+      sum -= x[nc];
+      return fabs(sum) < delta;
     }
   }
   return 0;
@@ -657,6 +679,8 @@ int orc_least_squares(int model, double delta, double aux, int ls_type, const do
     case M_ABSOR: return absor_lsq(data, n, params);
     case M_RAY: return ray_lsq(data, n, params);
     case M_PIVOT: return pivot_solve(data, n, params);
+    case M_DENSE5: return dense_solve(5, data, n, params);
+    case M_DENSE6: return dense_solve(6, data, n, params);
   }
   return -1;
 }
@@ -668,7 +692,7 @@ int orc_least_squares(int model, double delta, double aux, int ls_type, const do
 /* RANSAC.hxx:217-249 body for one subset (full scoring, no early exit). */
 static uint32_t score_one(int model, int D, int k, double delta, double aux, const double* data, size_t n,
                           const int32_t* sub, double* prm, int* nprm) {
-  double pts[4 * 12];
+  double pts[6 * 12];
   int j; size_t m; uint32_t c = 0;
   for (j = 0; j < k; j++) memcpy(pts + j * D, data + (size_t)sub[j] * D, sizeof(double) * D);
   *nprm = orc_estimate(model, delta, aux, pts, (size_t)k, prm);
@@ -740,7 +764,7 @@ unsigned int orc_num_tries(double prob, unsigned int votes, unsigned int n, unsi
 int orc_ransac_exhaustive(int model, double delta, double aux, int ls_type, const double* data, size_t n,
                           double* params, uint8_t* mask, double* fraction, uint32_t* best_count, uint64_t* best_rank) {
   int D, P, k, np = 0, j;
-  int32_t sub[4];
+  int32_t sub[6];
   uint32_t best = 0; uint64_t rank = 0, brank = 0; double bprm[8], prm[8];
   size_t m, nin = 0;
   double* inl;

@@ -32,10 +32,11 @@
 #include "AbsoluteOrientationParametersEstimator.h"
 #include "RayIntersectionParametersEstimator.h"
 #include "PivotCalibrationParametersEstimator.h"
+#include "DenseLinearEquationSystemParametersEstimator.h"
 
 using namespace lsqrRecipes;
 
-enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8 };
+enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10 };
 
 namespace {
 
@@ -63,6 +64,11 @@ template <> struct Marshal<Frame> {
   }
 };
 
+template <unsigned n> struct Marshal<AugmentedRow<double, n> > {
+  enum { D = n + 1 };
+  static AugmentedRow<double, n> get(const double* p) { double tmp[n + 1]; for (unsigned i = 0; i <= n; i++) tmp[i] = p[i]; return AugmentedRow<double, n>(tmp); }
+};
+
 template <class T> void unpack(const double* data, size_t n, std::vector<T>& out) {
   out.clear(); out.reserve(n);
   for (size_t i = 0; i < n; i++) out.push_back(Marshal<T>::get(data + i * Marshal<T>::D));
@@ -82,6 +88,8 @@ template <class F> int dispatch(const Cfg& c, F& f) {
     case M_ABSOR: { AbsoluteOrientationParametersEstimator e(c.delta); return f(&e, (PointPair*)0); }
     case M_RAY: { if (c.aux > 0) { RayIntersectionParametersEstimator e(c.delta, c.aux); return f(&e, (Ray3D*)0); } RayIntersectionParametersEstimator e(c.delta); return f(&e, (Ray3D*)0); }
     case M_PIVOT: { PivotCalibrationEstimator e(c.delta); return f(&e, (Frame*)0); }
+    case M_DENSE5: { DenseLinearEquationSystemParametersEstimator<double, 5> e(c.delta); return f(&e, (AugmentedRow<double, 5>*)0); }
+    case M_DENSE6: { DenseLinearEquationSystemParametersEstimator<double, 6> e(c.delta); return f(&e, (AugmentedRow<double, 6>*)0); }
   }
   return -1;
 }
@@ -156,8 +164,8 @@ struct RansacOp {
 extern "C" {
 
 int ref_model_info(int model, int* D, int* P, int* k) {
-  static const int tab[9][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}};
-  if (model < 0 || model > 8) return -1;
+  static const int tab[11][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}, {6, 5, 5}, {7, 6, 6}};
+  if (model < 0 || model > 10) return -1;
   *D = tab[model][0]; *P = tab[model][1]; *k = tab[model][2];
   return 0;
 }

@@ -155,6 +155,8 @@ class vnl_matrix {
   }
   vnl_matrix& set_column(unsigned j, vnl_vector<T> const& v) { for (unsigned i = 0; i < r_; i++) (*this)(i, j) = v[i]; return *this; }
   vnl_matrix& set_row(unsigned i, vnl_vector<T> const& v) { for (unsigned j = 0; j < c_; j++) (*this)(i, j) = v[j]; return *this; }
+  vnl_matrix& set_row(unsigned i, T const* v) { for (unsigned j = 0; j < c_; j++) (*this)(i, j) = v[j]; return *this; }   // DenseLinearEquationSystemParametersEstimator.hxx:34
+  vnl_matrix& set_column(unsigned j, T const* v) { for (unsigned i = 0; i < r_; i++) (*this)(i, j) = v[i]; return *this; }
   vnl_vector<T> get_row(unsigned i) const { vnl_vector<T> v(c_); for (unsigned j = 0; j < c_; j++) v[j] = (*this)(i, j); return v; }
   vnl_vector<T> get_column(unsigned j) const { vnl_vector<T> v(r_); for (unsigned i = 0; i < r_; i++) v[i] = (*this)(i, j); return v; }
 

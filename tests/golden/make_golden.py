@@ -2,7 +2,7 @@
 
 Run in the build container (needs /root/reference and oracle/_ref built by oracle/Makefile):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [model ...]      (no arguments: every model and the file-based cases)
 
 For every model it stores seeded inputs and what the reference's own classes return for them
 through oracle/_ref/libref_oracle.so (reference sources compiled unmodified against the VNL
@@ -27,7 +27,10 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 
 def main():
     ref = Oracle("ref")
+    only = sys.argv[1:]
     for name, m in MODELS.items():
+        if only and name not in only:
+            continue
         D, P, k = INFO[m]
         delta = synth.DELTAS[name]
         n = 96
@@ -49,6 +52,18 @@ def main():
             fx[f"lsq_ls{ls_type}"] = ref.least_squares(m, delta, data[bm.astype(bool)], ls_type)
         np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **fx)
         print(name, "best", counts.max(), "valid", int((~np.isnan(params[:, 0])).sum()), "exhaustive fraction", fx["ex_fraction_ls1"])
+
+    # the reference's second file-based known answer: DenseLinearEquationSystemParametersEstimatorTest.cxx:153-213
+    # (least squares over testing/Data/augmentedMatrix.txt against a 17-digit solution, tolerance 0.5)
+    if not only or "dense6" in only:
+        rows = np.loadtxt("/root/reference/testing/Data/augmentedMatrix.txt")
+        ls = ref.least_squares(MODELS["dense6"], 0.5, rows)
+        known = np.array([-1.777985584409468e+001, 1.111302171667757e+000, -1.568653413096010e+002, 1.469013927556186e+002,
+                          -6.296891425314718e+001, -1.042139650090033e+003])
+        np.savez_compressed(os.path.join(OUT, "dense_file.npz"), rows=rows, ls=ls, known_ls=known)
+        print("dense file: ls", ls, "max |ls - known|", np.abs(ls - known).max())
+    if only:
+        return
 
     # configs[0] restated: PlaneParametersEstimatorTest's data shape --
     # 3 exact + 20 noisy points, bounds +-1000, sigma 1, delta 0.5 -- seeded, exhaustive C(23,3)=1771.

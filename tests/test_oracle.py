@@ -10,6 +10,7 @@ from lsqrrecipes_b200 import synth
 from oracle.pyoracle import INFO, MODELS
 
 ALL = list(MODELS.items())
+PINV_MODELS = ("pivot", "dense5", "dense6")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
 
 
 # ---- the reference's own literal test vectors -------------------------------------------
@@ -41,6 +42,16 @@ def test_pivot_known_answers(port):
     assert np.allclose(ls, g["ls"], rtol=0, atol=1e-9)
 
 
+def test_dense_file_known_answer(port):
+    """testing/DenseLinearEquationSystemParametersEstimatorTest.cxx:153-213 on testing/Data/augmentedMatrix.txt
+    (rows stored in the fixture): least squares within 0.5 of the 17-digit solution."""
+    g = golden("dense_file")
+    assert g["rows"].shape == (1443, 7)
+    ls = port.least_squares(MODELS["dense6"], 0.5, g["rows"])
+    assert len(ls) == 6 and np.all(np.abs(ls - g["known_ls"]) < 0.5)
+    assert np.allclose(ls, g["ls"], rtol=1e-9, atol=1e-9)
+
+
 # ---- fixtures minted by the reference ---------------------------------------------------
 @pytest.mark.parametrize("name,m", ALL)
 def test_port_matches_reference_fixture(port, name, m):
@@ -48,7 +59,7 @@ def test_port_matches_reference_fixture(port, name, m):
     counts, params = port.score_subsets(m, float(g["delta"]), g["data"], g["subsets"])
     assert np.array_equal(counts, g["counts"]), "per-hypothesis inlier counts must be bit-exact"
     assert np.array_equal(np.isnan(params), np.isnan(g["params"])), "same degenerate subsets"
-    if name == "pivot":  # 9x6 pseudo-inverse goes through the SVD stand-in: rounding-level agreement
+    if name in PINV_MODELS:  # 9x6 / n x n pseudo-inverse goes through the SVD stand-in: rounding-level agreement
         assert np.allclose(np.nan_to_num(params), np.nan_to_num(g["params"]), rtol=1e-9, atol=1e-9)
     else:
         assert np.array_equal(np.nan_to_num(params), np.nan_to_num(g["params"])), "estimate() must be bit-exact"
@@ -93,7 +104,9 @@ def test_port_matches_reference_live(port, ref, name, m):
     c2, p2 = ref.score_subsets(m, delta, data, subs)
     assert np.array_equal(c1, c2)
     assert np.array_equal(np.isnan(p1), np.isnan(p2))
-    if name != "pivot":
+    if name in PINV_MODELS:
+        assert np.allclose(np.nan_to_num(p1), np.nan_to_num(p2), rtol=1e-9, atol=1e-9)
+    else:
         assert np.array_equal(np.nan_to_num(p1), np.nan_to_num(p2))
 
 

@@ -17,6 +17,7 @@ from oracle.pyoracle import INFO, MODELS
 
 pytestmark = pytest.mark.gpu
 ALL = list(MODELS.items())
+PINV_MODELS = ("pivot", "dense5", "dense6")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
 REFINE_TOL = 1e-6
 
 
@@ -33,7 +34,7 @@ def test_fp64_counts_bit_exact_vs_reference_fixture(name, m):
     r = eng.score(sampler=SAMPLE_LIST, subsets=g["subsets"], precision=FP64, want_counts=True, want_params=True)
     assert np.array_equal(r["counts"], g["counts"])
     assert np.array_equal(np.isnan(r["params"]), np.isnan(g["params"]))
-    if name == "pivot":
+    if name in PINV_MODELS:
         assert np.allclose(np.nan_to_num(r["params"]), np.nan_to_num(g["params"]), rtol=1e-9, atol=1e-9)
     else:
         assert np.array_equal(np.nan_to_num(r["params"]), np.nan_to_num(g["params"])), "device estimate() must round like the reference"
@@ -112,6 +113,19 @@ def test_pivot_file_known_answers():
     eng.close()
 
 
+def test_dense_file_known_answer():
+    """DenseLinearEquationSystemParametersEstimatorTest.cxx:153-213: least squares over
+    testing/Data/augmentedMatrix.txt (1443 rows x 7) against the 17-digit solution, tolerance 0.5 there."""
+    g = golden("dense_file")
+    eng = Engine("dense6", 0.5)
+    ls = eng.least_squares(g["rows"])
+    assert np.all(np.abs(ls - g["known_ls"]) < 0.5)          # the reference's own criterion
+    assert np.allclose(ls, g["ls"], rtol=1e-9, atol=1e-9)    # and what the reference itself returns
+    eng.upload(g["rows"])
+    assert eng.consensus(g["known_ls"]) == int(np.sum(np.abs(g["rows"][:, :6] @ g["known_ls"] - g["rows"][:, 6]) < 0.5))
+    eng.close()
+
+
 def test_circle_agree_literals():
     """testing/SphereParametersEstimatorTest.cxx:280-296"""
     eng = Engine("circle2", 0.5)
@@ -149,6 +163,10 @@ def _fp32_band(name, data, prm, delta):
     """Half-width (in residual units) of the band around the threshold inside which an fp32
     decision may legitimately differ: 1e-6 relative to the magnitude of the terms that are
     summed to form the residual (SURVEY.md / DESIGN.md 'fp32 fast mode')."""
+    if name in ("dense5", "dense6"):   # the summed terms are the products a_i x_i and b
+        nc = data.shape[1] - 1
+        scale = np.abs(data[:, :nc]).max() * np.abs(prm).max() * nc + np.abs(data[:, nc]).max() + 1.0
+        return 1e-6 * scale
     scale = np.abs(data).max() + np.abs(prm).max() + 1.0
     return 1e-6 * scale * (4.0 if name in ("absor", "pivot", "ray", "line3", "line2") else 2.0)
 
@@ -180,6 +198,9 @@ def _residual64(name, prm, data, delta):
     if name == "pivot":
         R = data[:, :9].reshape(-1, 3, 3)
         return np.linalg.norm(np.einsum("nij,j->ni", R, p[:3]) + data[:, 9:] - p[3:6], axis=1), delta
+    if name in ("dense5", "dense6"):
+        nc = data.shape[1] - 1
+        return np.abs(data[:, :nc] @ p[:nc] - data[:, nc]), delta
     raise AssertionError(name)
 
 
@@ -299,7 +320,7 @@ def test_edge_cases_match_reference_conventions():
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["line2d", "plane3", "sphere3"])
+@pytest.mark.parametrize("name", ["line2d", "plane3", "sphere3", "dense5"])
 def test_batched_small_problems_vs_oracle(port, name):
     """BASELINE.json configs[4]: many independent small problems, one thread block each.  Exhaustive mode is
     bit-comparable with the reference's brute-force driver run per problem."""
