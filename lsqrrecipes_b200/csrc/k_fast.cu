@@ -463,17 +463,19 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
   }
   Thr2 thr;
   thr.delta = splat(delta); thr.neg_delta2 = splat(-delta2); thr.fdelta = delta;
+  // one induction variable in units of 2*PPI points; the component offsets are immediates (cp is a multiple of 16)
   const uint32_t p0 = blockIdx.y * sub, p1 = min(p0 + sub, npts);
+  const int g0 = (int)(p0 / (2 * PPI)), g1 = (int)(p1 / (2 * PPI));
 #pragma unroll 1
-  for (uint32_t i = p0; i < p1; i += 2 * PPI) {
+  for (int g = g0; g < g1; g++) {
     f2 x[PPI][D];
 #pragma unroll
     for (int d = 0; d < D; d++) {
       if constexpr (PPI == 2) {
-        const float4 v = c_tile[(d * cp + i) >> 2];
+        const float4 v = c_tile[d * (int)(cp / 4) + g];
         x[0][d] = join(v.x, v.y); x[1][d] = join(v.z, v.w);
       } else {
-        const float2 v = reinterpret_cast<const float2*>(c_tile)[(d * cp + i) >> 1];
+        const float2 v = reinterpret_cast<const float2*>(c_tile)[d * (int)(cp / 2) + g];
         x[0][d] = join(v.x, v.y);
       }
     }
