@@ -292,7 +292,7 @@ def main():
         roofline_refine = {"bound": "hbm", "achieved": rs["bytes"] / (rs["kernel_ms"] * 1e-3) / 1e9 if rs["kernel_ms"] > 0 else None,
                            "peak": hbm_peak, "unit": "GB/s", "kernel": "mask_moments_kernel", "kernel_ms": rs["kernel_ms"],
                            "algorithmic_bytes": rs["bytes"],
-                           "traffic": trm.get("bytes_per_launch") if trm.get("config") == {"model": model, "points": N} else None}
+                           "traffic": trm.get("bytes_per_launch") if (world == 1 and trm.get("config") == {"model": model, "points": N}) else None}
         if roofline_refine["achieved"]:
             roofline_refine["frac"] = roofline_refine["achieved"] / hbm_peak
     else:
