@@ -280,6 +280,20 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         rs = eng.last_refine_stats()
+        # the second half of BASELINE.json's metric: wall time of RANSAC<T,S>::compute(parameters, estimator, data, 0.999,
+        # &consensusSet) through the library -- upload from pinned host memory, adaptive rounds, consensus set, refine
+        comp_ms, comp = [], None
+        for s in range(4):
+            barrier()
+            t0 = time.perf_counter()
+            eng.upload_ptr(host.data_ptr(), N, data.shape[1] * 8)
+            comp = eng.ransac(0.999, precision=precision, seed=100 + s)
+            comp_ms.append(1e3 * (time.perf_counter() - t0))
+        tc = torch.tensor([float(np.median(comp_ms[1:]))], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        compute_e2e = {"ms": float(tc.item()), "desired_probability": 0.999, "tries": int(comp["tries"]), "inlier_fraction": float(comp["fraction"]),
+                       "device_ms": float(comp["device_ms"]), "n_params": int(len(comp["params"]))}
         hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -297,6 +311,7 @@ def main():
             roofline_refine["frac"] = roofline_refine["achieved"] / hbm_peak
     else:
         roofline_refine = None
+        compute_e2e = None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -313,7 +328,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if precision == FP32 else "f64", "data": "synthetic",
             "config": workload_config(model, N, Hper, world, args.precision, delta),
-            "roofline": roofline, "roofline_refine": roofline_refine, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "roofline_refine": roofline_refine, "cpu_baseline": cpu, "e2e": e2e, "compute_e2e": compute_e2e,
             "gpu_launches": int(launches), "clocks": clk.summary(),
             "best_count": int(r["best_count"]),
         }

@@ -186,6 +186,9 @@ int lsqr_estimate(lsqr_ctx* ctx, const double* packed, size_t n, double* out_par
 int lsqr_agree(lsqr_ctx* ctx, const double* params, const double* packed, size_t n, uint8_t* out);
 /* leastSquaresEstimate() on n packed data in host memory. */
 int lsqr_least_squares(lsqr_ctx* ctx, const double* packed, size_t n, double* out_params, int* n_params);
+/* AbsoluteOrientationParametersEstimator::weightedLeastSquaresEstimate (AbsoluteOrientationParametersEstimator.cxx:208-297):
+ * Horn's method with one weight per pair; LSQR_ABSOR contexts only; *n_params = 0 for fewer than 3 pairs. */
+int lsqr_weighted_least_squares(lsqr_ctx* ctx, const double* packed, size_t n, const double* weights, double* out_params, int* n_params);
 
 /* ---- measurement helpers ------------------------------------------------------------ */
 /* Register-resident FMA-chain microbenchmarks: returns lane-FMA/s of the fp32 (kind 0),

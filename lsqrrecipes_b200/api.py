@@ -84,6 +84,7 @@ def load_library():
         "lsqr_estimate": (c.c_int, [c.c_void_p, _dp, c.c_size_t, _dp, c.POINTER(c.c_int)]),
         "lsqr_agree": (c.c_int, [c.c_void_p, _dp, _dp, c.c_size_t, _u8p]),
         "lsqr_least_squares": (c.c_int, [c.c_void_p, _dp, c.c_size_t, _dp, c.POINTER(c.c_int)]),
+        "lsqr_weighted_least_squares": (c.c_int, [c.c_void_p, _dp, c.c_size_t, _dp, _dp, c.POINTER(c.c_int)]),
         "lsqr_microbench_fma": (c.c_int, [c.c_void_p, c.c_int, c.c_int, _dp, _dp]),
         "lsqr_last_refine_stats": (c.c_int, [c.c_void_p, _dp, _dp, c.POINTER(c.c_int)]),
     }
@@ -99,7 +100,7 @@ EXPORTED_SYMBOLS = [
     "lsqr_model_info", "lsqr_ctx_create", "lsqr_ctx_destroy", "lsqr_last_error", "lsqr_ctx_set_stream", "lsqr_kernel_launches",
     "lsqr_set_estimator", "lsqr_upload", "lsqr_upload_device", "lsqr_set_shard", "lsqr_score", "lsqr_consensus", "lsqr_get_mask",
     "lsqr_refine", "lsqr_ransac", "lsqr_ransac_exhaustive", "lsqr_ransac_batch", "lsqr_estimate", "lsqr_agree", "lsqr_least_squares",
-    "lsqr_microbench_fma", "lsqr_last_refine_stats",
+    "lsqr_microbench_fma", "lsqr_last_refine_stats", "lsqr_weighted_least_squares",
 ]
 
 
@@ -270,6 +271,17 @@ class Engine:
         out = np.zeros(8)
         n = ctypes.c_int(0)
         self._ck(self.lib.lsqr_least_squares(self.h, _ptr(d, _dp), d.shape[0], _ptr(out, _dp), ctypes.byref(n)))
+        return out[: n.value].copy()
+
+    def weighted_least_squares(self, data, weights):
+        """AbsoluteOrientationParametersEstimator::weightedLeastSquaresEstimate (absolute orientation only)."""
+        d = np.ascontiguousarray(data, dtype=np.float64).reshape(-1, self.dim)
+        w = np.ascontiguousarray(weights, dtype=np.float64).reshape(-1)
+        if len(w) != d.shape[0]:
+            raise ValueError("one weight per datum")
+        out = np.zeros(8)
+        n = ctypes.c_int(0)
+        self._ck(self.lib.lsqr_weighted_least_squares(self.h, _ptr(d, _dp), d.shape[0], _ptr(w, _dp), _ptr(out, _dp), ctypes.byref(n)))
         return out[: n.value].copy()
 
     # -- measurement ------------------------------------------------------------------

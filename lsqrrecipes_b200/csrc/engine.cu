@@ -70,6 +70,7 @@ struct lsqr_ctx {
   RefineBuffers rb{};
   // pinned host scratch
   double* pin = nullptr;                  // 64 doubles
+  double* weights_dev = nullptr; size_t weights_cap = 0;   // lsqr_weighted_least_squares
   uint8_t* mask_dev = nullptr; size_t mask_dev_cap = 0;   // consensus set, one byte per datum (device)
   uint8_t* mask_pin = nullptr; size_t mask_pin_cap = 0;   // pinned bounce buffer for its download
   cudaEvent_t ev[6]{};
@@ -476,7 +477,7 @@ void lsqr_ctx_destroy(lsqr_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (DataSet* ds : {&ctx->main, &ctx->scratch}) { cudaFree(ds->soa64); cudaFree(ds->soa32); cudaFree(ds->maskbits); }
-  cudaFree(ctx->mask_dev); if (ctx->mask_pin) cudaFreeHost(ctx->mask_pin);
+  cudaFree(ctx->weights_dev); cudaFree(ctx->mask_dev); if (ctx->mask_pin) cudaFreeHost(ctx->mask_pin);
   cudaFree(ctx->staging); cudaFree(ctx->subsets); cudaFree(ctx->hyp64); cudaFree(ctx->hyp32); cudaFree(ctx->counts);
   cudaFree(ctx->list_dev); cudaFree(ctx->params_in_dev); cudaFree(ctx->key_dev); cudaFree(ctx->small_dev);
   cudaFree(ctx->center_dev); cudaFree(ctx->center_partials); cudaFree(ctx->rb.partials); cudaFree(ctx->rb.moments);
@@ -708,6 +709,33 @@ int lsqr_least_squares(lsqr_ctx* ctx, const double* packed, size_t n, double* ou
   if (!rc) rc = refine_impl(ctx, ctx->scratch, 0, out_params, n_params);
   ctx->world = world; ctx->rank = rank;
   return rc;
+}
+
+int lsqr_weighted_least_squares(lsqr_ctx* ctx, const double* packed, size_t n, const double* weights, double* out_params, int* n_params) {
+  if (!ctx || !out_params || !n_params || !weights) return LSQR_ERR_ARG;
+  if (ctx->model != ABSOR) return fail(ctx, LSQR_ERR_ARG, "weighted least squares exists for the absolute-orientation estimator only");
+  *n_params = 0;
+  if (n < 3) return LSQR_OK;   // AbsoluteOrientationParametersEstimator.cxx:214-215
+  const int world = ctx->world, rank = ctx->rank;
+  ctx->world = 1; ctx->rank = 0;
+  int rc = upload_to(ctx, ctx->scratch, packed, n, sizeof(double) * 6, false);
+  ctx->world = world; ctx->rank = rank;
+  if (rc) return rc;
+  cudaStream_t s = ctx->stream;
+  if (int rc2 = ensure(ctx, &ctx->weights_dev, &ctx->weights_cap, n)) return rc2;
+  CK(cudaMemcpyAsync(ctx->weights_dev, weights, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+  const DataView dv = ctx->scratch.view();
+  launch_weighted_absor_moments(dv, ctx->weights_dev, ctx->rb, s);
+  launch_reduce_partials(ctx->rb, 16, s);
+  launch_solve_weighted_absor(dv, ctx->rb.moments, ctx->small_dev + 16, s); ctx->launches += 3;
+  CKL();
+  CK(cudaMemcpyAsync(ctx->pin, ctx->small_dev + 16, sizeof(double) * (1 + LSQR_MAX_PARAMS), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const int np = (int)ctx->pin[0];
+  for (int j = 0; j < np; j++) out_params[j] = ctx->pin[1 + j];
+  *n_params = np;
+  ctx->scratch.moments_valid = false;
+  return LSQR_OK;
 }
 
 int lsqr_microbench_fma(lsqr_ctx* ctx, int kind, int iters, double* out_fma_per_s, double* out_ms) {

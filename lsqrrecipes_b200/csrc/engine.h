@@ -71,6 +71,9 @@ void launch_solve_moments(int model, const DataView& dv, const double* moments, 
 void launch_lm_init(const double* alg_out_dev, double* state, cudaStream_t s);
 void launch_lm_update(int model, const double* moments, double* state, cudaStream_t s);
 void launch_lm_finish(int model, const DataView& dv, const double* state, double* out_dev, cudaStream_t s);
+// Weighted Horn (AbsoluteOrientationParametersEstimator.cxx:208-297): weighted moments of all n pairs, then the 4x4 eigen solve.
+void launch_weighted_absor_moments(const DataView& dv, const double* weights_dev, const RefineBuffers& rb, cudaStream_t s);
+void launch_solve_weighted_absor(const DataView& dv, const double* moments, double* out_dev, cudaStream_t s);
 int moments_count(int model, bool lm);
 int mask_moments_ctas_per_sm();   // grid of launch_mask_moments = this x SMs (one wave)
 void launch_expand_mask(const uint32_t* bits, uint32_t n, uint8_t* bytes, cudaStream_t s);

@@ -272,6 +272,47 @@ void launch_mask_moments(int model, const DataView& dv, uint32_t begin, uint32_t
 #undef LAUNCH
 }
 
+// Weighted Horn moments (AbsoluteOrientationParametersEstimator.cxx:217-261): sum w, sum w p1, sum w p2,
+// sum w p1 p2^T over all n pairs, relative to dv.center.  Same partials layout as mask_moments_kernel.
+__global__ void __launch_bounds__(256) weighted_absor_moments_kernel(DataView dv, const double* __restrict__ w, double* __restrict__ partials) {
+  constexpr int NM = 16;
+  double acc[NM];
+#pragma unroll
+  for (int j = 0; j < NM; j++) acc[j] = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < dv.n; i += (size_t)gridDim.x * blockDim.x) {
+    double q[6];
+#pragma unroll
+    for (int d = 0; d < 6; d++) q[d] = dv.soa64[(size_t)d * dv.ld + i] - dv.center[d];
+    const double wi = w[i];
+    acc[0] += wi;
+#pragma unroll
+    for (int j = 0; j < 6; j++) acc[1 + j] += q[j] * wi;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) acc[7 + r * 3 + c] += (q[r] * q[3 + c]) * wi;
+  }
+  __shared__ double sh[8][kMaxMoments];
+  const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < NM; j++) {
+    double v = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[threadIdx.x >> 5][j] = v;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < NM) {
+    double v = 0.0;
+#pragma unroll
+    for (int wp = 0; wp < 8; wp++) v += sh[wp][threadIdx.x];
+    partials[(size_t)blockIdx.x * kMaxMoments + threadIdx.x] = v;
+  }
+}
+void launch_weighted_absor_moments(const DataView& dv, const double* weights_dev, const RefineBuffers& rb, cudaStream_t s) {
+  weighted_absor_moments_kernel<<<rb.blocks, 256, 0, s>>>(dv, weights_dev, rb.partials);
+}
+
 // One warp per moment; lanes stride over the blocks, then a fixed-order shuffle tree: the summation
 // order depends only on the launch geometry, so results are reproducible run to run.
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int blocks, int nm, double* __restrict__ moments) {
@@ -364,9 +405,12 @@ template <int DIM> __device__ int solve_sphere_alg(const double* m, double* out)
 }
 // AbsoluteOrientationParametersEstimator.cxx:134-205 (Horn): M = sum p1 p2^T - N mu1 mu2^T, 4x4 N matrix,
 // eigenvector of the largest eigenvalue, t = mu2 - R mu1 with the normalised quaternion.
-__device__ int solve_absor(const double* m, const double* c, double* out) {
+// m[0] is the number of pairs, or the sum of the weights for the weighted variant (:208-297), whose
+// size guard is on the number of pairs and is applied by the caller.
+__device__ int solve_absor(const double* m, const double* c, double* out, bool weighted = false) {
   const double n = m[0];
-  if (n < 3.0) return 0;
+  if (!weighted && n < 3.0) return 0;
+  if (weighted && !(n == n && n != 0.0)) return 0;
   double mu1[3], mu2[3], Mm[9], Nm[16], V[16], ev[4], R[9];
   for (int j = 0; j < 3; j++) { mu1[j] = m[1 + j] / n; mu2[j] = m[4 + j] / n; }
   for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) Mm[r * 3 + cc] = m[7 + r * 3 + cc] - n * mu1[r] * mu2[cc];
@@ -448,6 +492,16 @@ __global__ void solve_moments_kernel(int model, DataView dv, const double* __res
   }
   out[0] = (double)np;
   for (int j = 0; j < np; j++) out[1 + j] = p[j];
+}
+__global__ void solve_weighted_absor_kernel(DataView dv, const double* __restrict__ m, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double p[8];
+  const int np = solve_absor(m, dv.center, p, true);
+  out[0] = (double)np;
+  for (int j = 0; j < np; j++) out[1 + j] = p[j];
+}
+void launch_solve_weighted_absor(const DataView& dv, const double* moments, double* out_dev, cudaStream_t s) {
+  solve_weighted_absor_kernel<<<1, 32, 0, s>>>(dv, moments, out_dev);
 }
 void launch_solve_moments(int model, const DataView& dv, const double* moments, int keep_centred, double* out_dev, cudaStream_t s) {
   solve_moments_kernel<<<1, 32, 0, s>>>(model, dv, moments, keep_centred, out_dev);

@@ -111,6 +111,14 @@ class AbsoluteOrientationParametersEstimator(ParametersEstimator):
     def __init__(self, delta):
         super().__init__(3, delta)
 
+    def weightedLeastSquaresEstimate(self, data, weights, parameters):
+        """AbsoluteOrientationParametersEstimator.cxx:208-297: Horn's method with one weight per pair."""
+        parameters.clear()
+        d = np.asarray(data, dtype=np.float64).reshape(-1, 6)
+        if d.shape[0] < self.minForEstimate:
+            return
+        parameters.extend(self.engine().weighted_least_squares(d, weights).tolist())
+
 
 class RayIntersectionParametersEstimator(ParametersEstimator):
     """RayIntersectionParametersEstimator; datum = Ray3D (p, n) as 6 doubles; parameters [x,y,z]."""

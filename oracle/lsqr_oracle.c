@@ -647,6 +647,32 @@ static int absor_lsq(const double* d, size_t n, double* prm) {
   return 7;
 }
 
+/* AbsoluteOrientationParametersEstimator.cxx:208-297: Horn's method with one weight per pair */
+int orc_weighted_absor(const double* d, size_t n, const double* w, double* prm) {
+  double mF[3] = {0, 0, 0}, mS[3] = {0, 0, 0}, mu[9], M[9] = {0}, N[16] = {0}, tmp[9], V[16], ev[4], R[9], tF[3], zero[3] = {0, 0, 0};
+  double A12, A20, A01, traceM = 0.0, sumWeights = 0.0;
+  size_t i; int r, c;
+  if (n < 3) return 0;
+  for (i = 0; i < n; i++) sumWeights += w[i];
+  for (i = 0; i < n; i++) for (r = 0; r < 3; r++) { mF[r] += d[6 * i + r] * w[i]; mS[r] += d[6 * i + 3 + r] * w[i]; }
+  for (r = 0; r < 3; r++) { mF[r] /= sumWeights; mS[r] /= sumWeights; }
+  for (r = 0; r < 3; r++) for (c = 0; c < 3; c++) mu[r * 3 + c] = mF[r] * mS[c];
+  for (i = 0; i < n; i++) for (r = 0; r < 3; r++) for (c = 0; c < 3; c++) M[r * 3 + c] += (d[6 * i + r] * d[6 * i + 3 + c]) * w[i];
+  for (r = 0; r < 9; r++) M[r] += mu[r] * (-sumWeights);
+  for (r = 0; r < 3; r++) traceM += M[r * 3 + r];
+  for (r = 0; r < 3; r++) for (c = 0; c < 3; c++) tmp[r * 3 + c] = ((r == c) ? -traceM : 0.0) + (M[r * 3 + c] + M[c * 3 + r]);
+  A12 = M[5] - M[7]; A20 = M[6] - M[2]; A01 = M[1] - M[3];
+  N[0] = traceM; N[1] = A12; N[2] = A20; N[3] = A01;
+  N[4] = A12; N[8] = A20; N[12] = A01;
+  for (r = 0; r < 3; r++) for (c = 0; c < 3; c++) N[(r + 1) * 4 + c + 1] = tmp[r * 3 + c];
+  sym_eig(4, N, V, ev);
+  for (r = 0; r < 4; r++) prm[r] = V[r * 4 + 3];
+  quat_to_matrix(prm[0], prm[1], prm[2], prm[3], 1, R);
+  frame_apply(R, zero, mF, tF);
+  for (r = 0; r < 3; r++) prm[4 + r] = mS[r] - tF[r];
+  return 7;
+}
+
 /* RayIntersectionParametersEstimator.cxx:100-144 */
 static int ray_lsq(const double* d, size_t m, double* prm) {
   double A[9] = {0}, b[3] = {0, 0, 0};

@@ -35,6 +35,8 @@ int orc_num_threads(void);
 /* estimate(): data = n>=k data in subset order; returns #params written (0 = degenerate). */
 int orc_estimate(int model, double delta, double aux, const double* data, size_t n, double* params);
 int orc_least_squares(int model, double delta, double aux, int ls_type, const double* data, size_t n, double* params);
+/* AbsoluteOrientationParametersEstimator::weightedLeastSquaresEstimate (.cxx:208-297); returns 7 or 0 */
+int orc_weighted_absor(const double* data, size_t n, const double* weights, double* params);
 /* agree() of one parameter vector against n data; returns inlier count; out[n] optional. */
 int orc_agree(int model, double delta, double aux, const double* params, int np, const double* data, size_t n, uint8_t* out);
 /* Full scoring (no early exit) of an ordered subset list: RANSAC.hxx:217-249 per subset. */

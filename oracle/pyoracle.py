@@ -47,6 +47,7 @@ class Oracle:
         f("agree", ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_double, _dp, ctypes.c_int, _dp, ctypes.c_size_t, _u8p])
         f("score_subsets", ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_double, _dp, ctypes.c_size_t, _i32p, ctypes.c_size_t, _u32p, _dp, ctypes.c_int])
         f("num_threads", ctypes.c_int, [])
+        f("weighted_absor", ctypes.c_int, [_dp, ctypes.c_size_t, _dp, _dp])
         if kind == "port":
             f("ransac_exhaustive", ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, _dp, ctypes.c_size_t, _dp, _u8p, _dp, _u32p, ctypes.POINTER(ctypes.c_uint64)])
             f("choose", ctypes.c_uint, [ctypes.c_uint, ctypes.c_uint])
@@ -79,6 +80,15 @@ class Oracle:
         d = self._data(model, data)
         out = np.zeros(16)
         n = self._least_squares(model, delta, aux, ls_type, _ptr(d, _dp), d.shape[0], _ptr(out, _dp))
+        return out[:max(n, 0)].copy()
+
+    def weighted_absor(self, data, weights):
+        """AbsoluteOrientationParametersEstimator::weightedLeastSquaresEstimate"""
+        d = np.ascontiguousarray(data, dtype=np.float64).reshape(-1, 6)
+        w = np.ascontiguousarray(weights, dtype=np.float64).reshape(-1)
+        assert len(w) == d.shape[0]
+        out = np.zeros(16)
+        n = self._weighted_absor(_ptr(d, _dp), d.shape[0], _ptr(w, _dp), _ptr(out, _dp))
         return out[:max(n, 0)].copy()
 
     def agree(self, model, delta, params, data, aux=0.0):

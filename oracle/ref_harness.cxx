@@ -194,6 +194,17 @@ int ref_score_subsets(int model, double delta, double aux, const double* data, s
   int D, P, k; if (ref_model_info(model, &D, &P, &k)) return -1;
   Cfg c = {model, delta, aux, 1}; ScoreOp op = {data, n, subsets, H, k, P, counts, params_out, nthreads}; return dispatch(c, op);
 }
+// AbsoluteOrientationParametersEstimator::weightedLeastSquaresEstimate (AbsoluteOrientationParametersEstimator.cxx:208-297)
+int ref_weighted_absor(const double* data, size_t n, const double* weights, double* params) {
+  std::vector<PointPair> d; unpack(data, n, d);
+  std::vector<double> w(weights, weights + n), p;
+  AbsoluteOrientationParametersEstimator e(1.0);
+  std::vector<PointPair*> ptrs(d.size());
+  for (size_t i = 0; i < d.size(); i++) ptrs[i] = &d[i];
+  e.weightedLeastSquaresEstimate(ptrs, w, p);   // the reference has the pointer overload only (.h:86-89)
+  for (size_t i = 0; i < p.size(); i++) params[i] = p[i];
+  return (int)p.size();
+}
 // The reference's own RANSAC<T,S>::compute: exhaustive (RANSAC.hxx:150-192) or randomized (:4-145).
 int ref_ransac(int model, double delta, double aux, int ls_type, const double* data, size_t n, int exhaustive, double prob,
                double* params, uint8_t* mask, double* fraction) {

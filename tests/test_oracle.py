@@ -110,6 +110,23 @@ def test_port_matches_reference_live(port, ref, name, m):
         assert np.array_equal(np.nan_to_num(p1), np.nan_to_num(p2))
 
 
+def test_weighted_horn_port_matches_reference(port, ref):
+    """AbsoluteOrientationParametersEstimator::weightedLeastSquaresEstimate (.cxx:208-297): restatement vs the
+    reference itself; unit weights reproduce the unweighted Horn solve; zero weights remove pairs."""
+    data, true = synth.absolute_orientation(500, seed=77, outlier_frac=0.0)
+    rng = np.random.default_rng(5)
+    w = rng.uniform(0.1, 3.0, 500)
+    a, b = port.weighted_absor(data, w), ref.weighted_absor(data, w)
+    assert len(a) == 7 and same_up_to_sign(a, b, SIGN_IDX["absor"], 1e-10)
+    assert same_up_to_sign(port.weighted_absor(data, np.ones(500)), port.least_squares(MODELS["absor"], 2.0, data), SIGN_IDX["absor"], 1e-9)
+    bad = data.copy()
+    bad[::5, 3:] += 500.0
+    w0 = np.ones(500)
+    w0[::5] = 0.0
+    assert same_up_to_sign(port.weighted_absor(bad, w0), port.least_squares(MODELS["absor"], 2.0, data[w0 > 0]), SIGN_IDX["absor"], 1e-9)
+    assert len(port.weighted_absor(data[:2], np.ones(2))) == 0
+
+
 def test_ragged_and_empty_inputs(port):
     """Edge cases the reference guards: too few data, degenerate subsets, empty consensus."""
     m = MODELS["plane3"]

@@ -126,6 +126,24 @@ def test_dense_file_known_answer():
     eng.close()
 
 
+def test_weighted_horn_vs_oracle(port):
+    """lsqr_weighted_least_squares == AbsoluteOrientationParametersEstimator::weightedLeastSquaresEstimate (.cxx:208-297)."""
+    data, true = synth.absolute_orientation(20000, seed=91)
+    rng = np.random.default_rng(6)
+    w = rng.uniform(0.0, 2.0, 20000)
+    eng = Engine("absor", 2.0)
+    got = eng.weighted_least_squares(data, w)
+    assert same_up_to_sign(got, port.weighted_absor(data, w), SIGN_IDX["absor"], REFINE_TOL)
+    assert same_up_to_sign(eng.weighted_least_squares(data, np.ones(20000)), eng.least_squares(data), SIGN_IDX["absor"], 1e-9)
+    assert len(eng.weighted_least_squares(data[:2], np.ones(2))) == 0
+    eng.close()
+    from lsqrrecipes_b200 import AbsoluteOrientationParametersEstimator
+    est = AbsoluteOrientationParametersEstimator(2.0)
+    prm = []
+    est.weightedLeastSquaresEstimate(data, w, prm)
+    assert same_up_to_sign(prm, port.weighted_absor(data, w), SIGN_IDX["absor"], REFINE_TOL)
+
+
 def test_circle_agree_literals():
     """testing/SphereParametersEstimatorTest.cxx:280-296"""
     eng = Engine("circle2", 0.5)
