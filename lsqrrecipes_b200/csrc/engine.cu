@@ -71,6 +71,10 @@ struct lsqr_ctx {
   // pinned host scratch
   double* pin = nullptr;                  // 64 doubles
   double* weights_dev = nullptr; size_t weights_cap = 0;   // lsqr_weighted_least_squares
+  double* bt_data = nullptr; size_t bt_data_cap = 0;       // lsqr_ransac_batch: packed problems, offsets, results
+  uint64_t* bt_off = nullptr; size_t bt_off_cap = 0;
+  double* bt_prm = nullptr; size_t bt_prm_cap = 0;
+  uint32_t* bt_cnt = nullptr; size_t bt_cnt_cap = 0;
   uint8_t* mask_dev = nullptr; size_t mask_dev_cap = 0;   // consensus set, one byte per datum (device)
   uint8_t* mask_pin = nullptr; size_t mask_pin_cap = 0;   // pinned bounce buffer for its download
   cudaEvent_t ev[6]{};
@@ -477,6 +481,7 @@ void lsqr_ctx_destroy(lsqr_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (DataSet* ds : {&ctx->main, &ctx->scratch}) { cudaFree(ds->soa64); cudaFree(ds->soa32); cudaFree(ds->maskbits); }
+  cudaFree(ctx->bt_data); cudaFree(ctx->bt_off); cudaFree(ctx->bt_prm); cudaFree(ctx->bt_cnt);
   cudaFree(ctx->weights_dev); cudaFree(ctx->mask_dev); if (ctx->mask_pin) cudaFreeHost(ctx->mask_pin);
   cudaFree(ctx->staging); cudaFree(ctx->subsets); cudaFree(ctx->hyp64); cudaFree(ctx->hyp32); cudaFree(ctx->counts);
   cudaFree(ctx->list_dev); cudaFree(ctx->params_in_dev); cudaFree(ctx->key_dev); cudaFree(ctx->small_dev);
@@ -625,14 +630,16 @@ int lsqr_ransac_batch(lsqr_ctx* ctx, const double* data, const uint64_t* offsets
   }
   if ((size_t)max_n * mi.D * sizeof(double) > 200 * 1024) return fail(ctx, LSQR_ERR_ARG, "a problem does not fit in shared memory; use lsqr_ransac for large problems");
   cudaStream_t s = ctx->stream;
-  double* d_data = nullptr; uint64_t* d_off = nullptr; double* d_prm = nullptr; uint32_t* d_cnt = nullptr; uint8_t* d_mask = nullptr;
-  auto cleanup = [&]() { cudaFree(d_data); cudaFree(d_off); cudaFree(d_prm); cudaFree(d_cnt); cudaFree(d_mask); };
+  // persistent buffers (a cudaMalloc/cudaFree set per call cost more than the kernel)
+  if (int rc = ensure(ctx, &ctx->bt_data, &ctx->bt_data_cap, (size_t)std::max<uint64_t>(total, 1) * mi.D)) return rc;
+  if (int rc = ensure(ctx, &ctx->bt_off, &ctx->bt_off_cap, (size_t)n_problems + 1)) return rc;
+  if (int rc = ensure(ctx, &ctx->bt_prm, &ctx->bt_prm_cap, (size_t)n_problems * mi.P)) return rc;
+  if (int rc = ensure(ctx, &ctx->bt_cnt, &ctx->bt_cnt_cap, (size_t)n_problems)) return rc;
+  if (out_masks) if (int rc = ensure(ctx, &ctx->mask_dev, &ctx->mask_dev_cap, (size_t)std::max<uint64_t>(total, 1))) return rc;
+  double* d_data = ctx->bt_data; uint64_t* d_off = ctx->bt_off; double* d_prm = ctx->bt_prm; uint32_t* d_cnt = ctx->bt_cnt;
+  uint8_t* d_mask = out_masks ? ctx->mask_dev : nullptr;
+  auto cleanup = [&]() {};
 #define CKB(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail(ctx, LSQR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } } while (0)
-  CKB(cudaMalloc((void**)&d_data, sizeof(double) * std::max<uint64_t>(total, 1) * mi.D));
-  CKB(cudaMalloc((void**)&d_off, sizeof(uint64_t) * (n_problems + 1)));
-  CKB(cudaMalloc((void**)&d_prm, sizeof(double) * n_problems * mi.P));
-  CKB(cudaMalloc((void**)&d_cnt, sizeof(uint32_t) * n_problems));
-  if (out_masks) CKB(cudaMalloc((void**)&d_mask, std::max<uint64_t>(total, 1)));
   CKB(cudaMemcpyAsync(d_data, data, sizeof(double) * total * mi.D, cudaMemcpyHostToDevice, s));
   CKB(cudaMemcpyAsync(d_off, offsets, sizeof(uint64_t) * (n_problems + 1), cudaMemcpyHostToDevice, s));
   BatchArgs ba{};
