@@ -72,7 +72,7 @@ typedef enum lsqr_sampler {
 /* SphereParametersEstimator::LeastSquaresType (SphereParametersEstimator.h:43) */
 typedef enum lsqr_ls_type { LSQR_LS_ALGEBRAIC = 0, LSQR_LS_GEOMETRIC = 1 } lsqr_ls_type;
 
-#define LSQR_MAX_PARAMS 8
+#define LSQR_MAX_PARAMS 20
 #define LSQR_MAX_SUBSET 6
 
 /* ---- model table ------------------------------------------------------------------ */

@@ -32,12 +32,12 @@ class ScoreArgs(ctypes.Structure):
 
 class ScoreResult(ctypes.Structure):
     _fields_ = [("best_index", ctypes.c_uint64), ("best_count", ctypes.c_uint32), ("n_valid", ctypes.c_uint32),
-                ("best_subset", ctypes.c_int32 * 6), ("best_params", ctypes.c_double * 8),
+                ("best_subset", ctypes.c_int32 * 6), ("best_params", ctypes.c_double * 20),
                 ("score_ms", ctypes.c_double), ("consensus_ms", ctypes.c_double)]
 
 
 class ComputeResult(ctypes.Structure):
-    _fields_ = [("params", ctypes.c_double * 8), ("n_params", ctypes.c_int), ("fraction", ctypes.c_double),
+    _fields_ = [("params", ctypes.c_double * 20), ("n_params", ctypes.c_int), ("fraction", ctypes.c_double),
                 ("best_count", ctypes.c_uint32), ("best_index", ctypes.c_uint64), ("tries", ctypes.c_uint64),
                 ("device_ms", ctypes.c_double)]
 
@@ -217,7 +217,7 @@ class Engine:
         return m
 
     def refine(self, use_mask=True):
-        out = np.zeros(8)
+        out = np.zeros(20)
         n = ctypes.c_int(0)
         self._ck(self.lib.lsqr_refine(self.h, 1 if use_mask else 0, _ptr(out, _dp), ctypes.byref(n)))
         return out[: n.value].copy()
@@ -254,7 +254,7 @@ class Engine:
     # -- the estimator's own methods ---------------------------------------------------
     def estimate(self, data):
         d = np.ascontiguousarray(data, dtype=np.float64).reshape(-1, self.dim)
-        out = np.zeros(8)
+        out = np.zeros(20)
         n = ctypes.c_int(0)
         self._ck(self.lib.lsqr_estimate(self.h, _ptr(d, _dp), d.shape[0], _ptr(out, _dp), ctypes.byref(n)))
         return out[: n.value].copy()
@@ -268,7 +268,7 @@ class Engine:
 
     def least_squares(self, data):
         d = np.ascontiguousarray(data, dtype=np.float64).reshape(-1, self.dim)
-        out = np.zeros(8)
+        out = np.zeros(20)
         n = ctypes.c_int(0)
         self._ck(self.lib.lsqr_least_squares(self.h, _ptr(d, _dp), d.shape[0], _ptr(out, _dp), ctypes.byref(n)))
         return out[: n.value].copy()
@@ -279,7 +279,7 @@ class Engine:
         w = np.ascontiguousarray(weights, dtype=np.float64).reshape(-1)
         if len(w) != d.shape[0]:
             raise ValueError("one weight per datum")
-        out = np.zeros(8)
+        out = np.zeros(20)
         n = ctypes.c_int(0)
         self._ck(self.lib.lsqr_weighted_least_squares(self.h, _ptr(d, _dp), d.shape[0], _ptr(w, _dp), _ptr(out, _dp), ctypes.byref(n)))
         return out[: n.value].copy()

@@ -20,6 +20,10 @@
 using namespace lsqr;
 
 namespace {
+constexpr int kSmall = 1024, kSmIn = 0, kSmOut = 32, kSmLm = 64, kSmEst = 640, kSmSink = 800;   // layout of lsqr_ctx::small_dev
+}
+
+namespace {
 
 struct DataSet {
   double* soa64 = nullptr;
@@ -63,7 +67,7 @@ struct lsqr_ctx {
   int32_t* list_dev = nullptr; size_t list_cap = 0;
   double* params_in_dev = nullptr; size_t params_in_cap = 0;
   unsigned long long* key_dev = nullptr;  // [0] key, [1] n_valid (as u32 in low half)
-  double* small_dev = nullptr;            // 256 doubles: [0..15] params in, [16..47] solve out, [64..127] LM state, [128..] misc
+  double* small_dev = nullptr;            // kSmall doubles: parameters in @kSmIn, solve out @kSmOut, LM state @kSmLm, estimate() input @kSmEst, sink @kSmSink
   double* center_dev = nullptr;           // 12 doubles
   double* center_partials = nullptr;      // 256*12
   // refine
@@ -330,13 +334,13 @@ int consensus_impl(lsqr_ctx* ctx, DataSet& ds, const double* params, uint32_t* o
   cudaStream_t s = ctx->stream;
   CK(cudaSetDevice(ctx->device));
   for (int j = 0; j < mi.P; j++) ctx->pin[32 + j] = params[j];
-  CK(cudaMemcpyAsync(ctx->small_dev, ctx->pin + 32, sizeof(double) * mi.P, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->small_dev + kSmIn, ctx->pin + 32, sizeof(double) * mi.P, cudaMemcpyHostToDevice, s));
   uint32_t b, e;
   shard_range(ctx, ds.n, &b, &e);
   const int nm = moments_count(ctx->model, false);
   CK(cudaEventRecord(ctx->ev[4], s));
   ctx->rb.maskbits = ds.maskbits;
-  launch_mask_moments(ctx->model, ds.view(), b, e, ctx->small_dev, 1, nullptr, ctx->cfg, ctx->rb, s); ctx->launches++;
+  launch_mask_moments(ctx->model, ds.view(), b, e, ctx->small_dev + kSmIn, 1, nullptr, ctx->cfg, ctx->rb, s); ctx->launches++;
   CK(cudaEventRecord(ctx->ev[5], s));
   if (int rc = reduce_moments(ctx, nm)) return rc;
   CKL();
@@ -370,12 +374,12 @@ int refine_impl(lsqr_ctx* ctx, DataSet& ds, int use_mask, double* out_params, in
     if (int rc = reduce_moments(ctx, nm)) return rc;
     ds.moments_valid = false;
   }
-  double* out_dev = ctx->small_dev + 16;
+  double* out_dev = ctx->small_dev + kSmOut;
   const bool geometric = (ctx->model == CIRCLE2 || ctx->model == SPHERE3) && ctx->ls_type == LSQR_LS_GEOMETRIC;
   launch_solve_moments(ctx->model, dv, ctx->rb.moments, geometric ? 1 : 0, out_dev, s); ctx->launches++;
   if (geometric) {
     // SphereParametersEstimator.hxx:224-230: algebraic fit as the start, then Levenberg-Marquardt.
-    double* st = ctx->small_dev + 64;
+    double* st = ctx->small_dev + kSmLm;
     const int nlm = moments_count(ctx->model, true);
     launch_lm_init(out_dev, st, s); ctx->launches++;
     ds.moments_valid = false;
@@ -464,7 +468,7 @@ int lsqr_ctx_create(lsqr_ctx** out, int device) {
   ctx->own_stream = true;
   ctx->rb.blocks = ctx->num_sms * mask_moments_ctas_per_sm();   // one wave of resident CTAs
   bool ok = cudaMalloc((void**)&ctx->key_dev, 4 * sizeof(unsigned long long)) == cudaSuccess &&
-            cudaMalloc((void**)&ctx->small_dev, 256 * sizeof(double)) == cudaSuccess &&
+            cudaMalloc((void**)&ctx->small_dev, kSmall * sizeof(double)) == cudaSuccess &&
             cudaMalloc((void**)&ctx->center_dev, 12 * sizeof(double)) == cudaSuccess &&
             cudaMalloc((void**)&ctx->center_partials, 256 * 12 * sizeof(double)) == cudaSuccess &&
             cudaMalloc((void**)&ctx->rb.partials, sizeof(double) * kMaxMoments * ctx->rb.blocks) == cudaSuccess &&
@@ -671,11 +675,11 @@ int lsqr_estimate(lsqr_ctx* ctx, const double* packed, size_t n, double* out_par
   if (n < (size_t)mi.K) return LSQR_OK;  // e.g. PlaneParametersEstimator.hxx:45-46
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
-  double* in_dev = ctx->small_dev + 128;  // K*D <= 48 doubles
+  double* in_dev = ctx->small_dev + kSmEst;  // K*D <= 64 doubles
   CK(cudaMemcpyAsync(in_dev, packed, sizeof(double) * mi.K * mi.D, cudaMemcpyHostToDevice, s));
-  launch_estimate_one(ctx->model, in_dev, ctx->cfg, ctx->small_dev + 16, s); ctx->launches++;
+  launch_estimate_one(ctx->model, in_dev, ctx->cfg, ctx->small_dev + kSmOut, s); ctx->launches++;
   CKL();
-  CK(cudaMemcpyAsync(ctx->pin, ctx->small_dev + 16, sizeof(double) * (1 + LSQR_MAX_PARAMS), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(ctx->pin, ctx->small_dev + kSmOut, sizeof(double) * (1 + LSQR_MAX_PARAMS), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   *n_params = (int)ctx->pin[0];
   for (int j = 0; j < *n_params; j++) out_params[j] = ctx->pin[1 + j];
@@ -694,8 +698,8 @@ int lsqr_agree(lsqr_ctx* ctx, const double* params, const double* packed, size_t
   double* d_in = reinterpret_cast<double*>(ctx->staging);
   uint8_t* d_out = ctx->staging + n * mi.D * sizeof(double);
   CK(cudaMemcpyAsync(d_in, packed, sizeof(double) * n * mi.D, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(ctx->small_dev, params, sizeof(double) * mi.P, cudaMemcpyHostToDevice, s));
-  launch_agree_many(ctx->model, ctx->small_dev, d_in, (uint32_t)n, ctx->cfg, d_out, s); ctx->launches++;
+  CK(cudaMemcpyAsync(ctx->small_dev + kSmIn, params, sizeof(double) * mi.P, cudaMemcpyHostToDevice, s));
+  launch_agree_many(ctx->model, ctx->small_dev + kSmIn, d_in, (uint32_t)n, ctx->cfg, d_out, s); ctx->launches++;
   CKL();
   CK(cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -734,9 +738,9 @@ int lsqr_weighted_least_squares(lsqr_ctx* ctx, const double* packed, size_t n, c
   const DataView dv = ctx->scratch.view();
   launch_weighted_absor_moments(dv, ctx->weights_dev, ctx->rb, s);
   launch_reduce_partials(ctx->rb, 16, s);
-  launch_solve_weighted_absor(dv, ctx->rb.moments, ctx->small_dev + 16, s); ctx->launches += 3;
+  launch_solve_weighted_absor(dv, ctx->rb.moments, ctx->small_dev + kSmOut, s); ctx->launches += 3;
   CKL();
-  CK(cudaMemcpyAsync(ctx->pin, ctx->small_dev + 16, sizeof(double) * (1 + LSQR_MAX_PARAMS), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(ctx->pin, ctx->small_dev + kSmOut, sizeof(double) * (1 + LSQR_MAX_PARAMS), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   const int np = (int)ctx->pin[0];
   for (int j = 0; j < np; j++) out_params[j] = ctx->pin[1 + j];
@@ -749,7 +753,7 @@ int lsqr_microbench_fma(lsqr_ctx* ctx, int kind, int iters, double* out_fma_per_
   if (!ctx || kind < 0 || kind > 2 || iters <= 0) return LSQR_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
-  float* sink = reinterpret_cast<float*>(ctx->small_dev + 200);
+  float* sink = reinterpret_cast<float*>(ctx->small_dev + kSmSink);
   const int blocks = ctx->num_sms * 8, threads = 256;
   launch_fma_bench(kind, 16, blocks, threads, sink, s);  // warm-up
   CK(cudaEventRecord(ctx->ev[0], s));

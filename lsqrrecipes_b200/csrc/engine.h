@@ -9,7 +9,7 @@
 namespace lsqr {
 
 constexpr int kTilePad = 1024;   // leading dimension of the SoA point arrays is a multiple of this
-constexpr int kMaxMoments = 32;  // doubles accumulated per thread by the refine reductions
+constexpr int kMaxMoments = 96;  // upper bound on the doubles accumulated per thread by the refine reductions (cross-wire US calibration: 91)
 
 // Device-resident description of the uploaded data.
 struct DataView {

@@ -13,6 +13,7 @@
 // All position components are accumulated relative to dv.center (shift-invariant scatter / normal
 // equations), which keeps the fp64 sums well conditioned for coordinates far from the origin.
 #include "engine.h"
+#include "../../include/lsqr_b200.h"
 
 namespace lsqr {
 
@@ -316,7 +317,7 @@ void launch_weighted_absor_moments(const DataView& dv, const double* weights_dev
 // One warp per moment; lanes stride over the blocks, then a fixed-order shuffle tree: the summation
 // order depends only on the launch geometry, so results are reproducible run to run.
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int blocks, int nm, double* __restrict__ moments) {
-  const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (j >= nm) return;
   double v = 0.0;
   for (int b = lane; b < blocks; b += 32) v += partials[(size_t)b * kMaxMoments + j];
@@ -325,7 +326,7 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
   if (lane == 0) moments[j] = v;
 }
 void launch_reduce_partials(const RefineBuffers& rb, int nm, cudaStream_t s) {
-  reduce_partials_kernel<<<1, 32 * kMaxMoments, 0, s>>>(rb.partials, rb.blocks, nm, rb.moments);
+  reduce_partials_kernel<<<(nm + 7) / 8, 256, 0, s>>>(rb.partials, rb.blocks, nm, rb.moments);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -474,7 +475,7 @@ template <int N> __device__ int solve_dense(const double* m, double* out) {
 // For CIRCLE2/SPHERE3 the parameters stay in centred coordinates when keep_centred != 0 (LM start).
 __global__ void solve_moments_kernel(int model, DataView dv, const double* __restrict__ m, int keep_centred, double* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double p[8];
+  double p[LSQR_MAX_PARAMS];
   int np = 0;
   const double* c = dv.center;
   switch (model) {
@@ -693,7 +694,7 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
   __shared__ unsigned long long sh_key[8];
   __shared__ double sh_part[8 * kMaxMoments];
   __shared__ double sh_mom[kMaxMoments];
-  __shared__ double sh_prm[16];
+  __shared__ double sh_prm[LSQR_MAX_PARAMS + 4];
   __shared__ double sh_state[64];
   __shared__ unsigned long long sh_best;
   __shared__ unsigned long long sh_tries;
@@ -783,9 +784,9 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
   block_moments<M>(pts, n, ldp, hq, cfg, nullptr, false, 1, mask_out, sh_part, sh_mom);
   DataView zero;
   for (int j = 0; j < 12; j++) zero.center[j] = 0.0;
-  __shared__ double sh_out[12];
+  __shared__ double sh_out[LSQR_MAX_PARAMS + 4];
   if (threadIdx.x == 0) {
-    double p[8];
+    double p[LSQR_MAX_PARAMS];
     int np = 0;
     const double* m = sh_mom;
     const double* c = zero.center;
