@@ -152,6 +152,45 @@ def dense_rows(n, nc, outlier_frac=0.3, seed=SEED, sigma=0.03):
     return np.ascontiguousarray(np.concatenate([A, b[:, None]], axis=1)), x
 
 
+def euler_zyx(oz, oy, ox):
+    """R = Rz(oz) Ry(oy) Rx(ox), the parametrisation of SinglePointTargetUSCalibrationParametersEstimator.cxx:430-441."""
+    cz, sz, cy, sy, cx, sx = np.cos(oz), np.sin(oz), np.cos(oy), np.sin(oy), np.cos(ox), np.sin(ox)
+    return np.array([[cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx],
+                     [sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx],
+                     [-sy, cy * sx, cy * cx]])
+
+
+def crosswire(n, outlier_frac=0.3, seed=SEED, sigma=1.0):
+    """Cross-wire phantom US calibration data in the shape of testing/SinglePointTargetUSCalibration
+    ParametersEstimatorTest.cxx:556-650: a fixed point t1 seen in n tracked images.  Datum = [R2 (9), t2 (3), u, v]
+    with  R2 (T3 (u, v, 0, 1)) + t2 = t1;  pixel noise sigma, gross outliers in (u, v).
+    Returns the data and the 20 reference parameters
+    [t1, t3, omega_z, omega_y, omega_x, m_x, m_y, m_x R3(:,1), m_y R3(:,2), R3(:,3)]."""
+    rng = np.random.default_rng(seed)
+    m_x, m_y = 0.143, 0.139
+    ox, oy, oz = rng.uniform(0.2, 1.3, 3)           # away from the gimbal lock of the Euler extraction
+    R3 = euler_zyx(oz, oy, ox)
+    t3 = rng.uniform(-100, 100, 3)
+    t1 = rng.uniform(-100, 100, 3)
+    out = np.zeros((n, 14))
+    n_out = int(round(n * outlier_frac))
+    bad = np.zeros(n, dtype=bool)
+    bad[rng.permutation(n)[:n_out]] = True
+    for i in range(n):
+        u, v = rng.uniform(0, 640), rng.uniform(0, 480)
+        p = R3 @ np.array([m_x * u, m_y * v, 0.0]) + t3           # point in the US reference frame
+        R2 = quat_to_matrix(*_unit(rng.normal(0, 1, 4)))
+        t2 = t1 - R2 @ p
+        un, vn = u + rng.normal(0, sigma), v + rng.normal(0, sigma)
+        if bad[i]:
+            un, vn = rng.uniform(0, 640), rng.uniform(0, 480)
+        out[i, :9] = R2.ravel()
+        out[i, 9:12] = t2
+        out[i, 12:] = (un, vn)
+    prm = np.concatenate([t1, t3, [oz, oy, ox, m_x, m_y], m_x * R3[:, 0], m_y * R3[:, 1], R3[:, 2]])
+    return out, prm
+
+
 def frames_from_quat_file(path):
     """Rows 'x y z qx qy qz qs' (testing/Data/pivotCalibrationData.txt) -> packed frames,
     following testing/PivotCalibrationParametersEstimatorTest.cxx:29-33."""
@@ -175,9 +214,10 @@ GENERATORS = {
     "pivot": lambda n, seed=SEED: pivot_frames(n, seed=seed),
     "dense5": lambda n, seed=SEED: dense_rows(n, 5, seed=seed),
     "dense6": lambda n, seed=SEED: dense_rows(n, 6, seed=seed),
+    "usxw": lambda n, seed=SEED: crosswire(n, seed=seed),
 }
 DELTAS = {"plane3": 0.5, "line2d": 0.5, "line2": 0.5, "line3": 0.5, "circle2": 0.5, "sphere3": 0.5, "absor": 2.0, "ray": 1.0, "pivot": 1.0,
-          "dense5": 0.2, "dense6": 0.2}
+          "dense5": 0.2, "dense6": 0.2, "usxw": 1.0}
 
 
 def random_subsets(n, k, H, seed=SEED):

@@ -21,7 +21,7 @@
 #include <omp.h>
 #endif
 
-enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10 };
+enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10, M_USXW = 11 };
 
 /* common/Epsilon.h:19 */
 static const double EPS = 2.220446049250313e-016;
@@ -32,8 +32,8 @@ static const double FRAME_SMALL_ANGLE = 0.008726535498373935;
 static const double FRAME_HALF_PI = 3.14159265358979323846 / 2.0;
 
 int orc_model_info(int model, int* D, int* P, int* k) {
-  static const int tab[11][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}, {6, 5, 5}, {7, 6, 6}};
-  if (model < 0 || model > 10) return -1;
+  static const int tab[12][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}, {6, 5, 5}, {7, 6, 6}, {14, 20, 4}};
+  if (model < 0 || model > 11) return -1;
   *D = tab[model][0]; *P = tab[model][1]; *k = tab[model][2];
   return 0;
 }
@@ -371,6 +371,206 @@ static int dense_solve(int nc, const double* d, size_t rows, double* prm) {
   return rank < nc ? 0 : nc;
 }
 
+
+static int chol_solve(double* M, const double* b, double* x, int p);
+
+/* ------------------------------------------------------------------------------------ */
+/* Cross-wire (single unknown point target) ultrasound calibration                      */
+/* SinglePointTargetUSCalibrationParametersEstimator.cxx:10-329, 415-658                */
+/* datum = [R2 row-major (9), t2 (3), u, v]; parameters (20) =                          */
+/* [t1, t3, omega_z, omega_y, omega_x, m_x, m_y, m_x R3(:,1), m_y R3(:,2), R3(:,3)]     */
+/* ------------------------------------------------------------------------------------ */
+
+/* R <- U V^T of its SVD (the closest rotation in the Frobenius norm, .cxx:226-229), computed as the
+ * orthogonal polar factor R (R^T R)^(-1/2) */
+static void us_closest_rotation(double R[9]) {
+  double S[9], V[9], ev[3], W[9], out[9];
+  int i, j, k;
+  for (i = 0; i < 3; i++) for (j = 0; j < 3; j++) { double s = 0; for (k = 0; k < 3; k++) s += R[k * 3 + i] * R[k * 3 + j]; S[i * 3 + j] = s; }
+  sym_eig(3, S, V, ev);
+  for (i = 0; i < 3; i++) for (j = 0; j < 3; j++) { double s = 0; for (k = 0; k < 3; k++) s += V[i * 3 + k] * V[j * 3 + k] / sqrt(ev[k]); W[i * 3 + j] = s; }
+  for (i = 0; i < 3; i++) for (j = 0; j < 3; j++) { double s = 0; for (k = 0; k < 3; k++) s += R[i * 3 + k] * W[k * 3 + j]; out[i * 3 + j] = s; }
+  memcpy(R, out, sizeof(out));
+}
+
+/* .cxx:204-268: scale factors, re-orthonormalised rotation, Euler angles, the 20 output parameters */
+static int us_post(const double x[12], double prm[20]) {
+  const double smallAngle = 0.008726535498373935, halfPI = 1.5707963267948966192313216916398;
+  double r1[3], r2[3], r3[3], R3[9], m_x, m_y, inv, omega_z, omega_y, omega_x;
+  int i;
+  for (i = 0; i < 3; i++) { r1[i] = x[i]; r2[i] = x[3 + i]; }
+  m_x = sqrt(r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2]);
+  inv = 1.0 / m_x; for (i = 0; i < 3; i++) r1[i] = inv * r1[i];
+  m_y = sqrt(r2[0] * r2[0] + r2[1] * r2[1] + r2[2] * r2[2]);
+  inv = 1.0 / m_y; for (i = 0; i < 3; i++) r2[i] = inv * r2[i];
+  r3[0] = r1[1] * r2[2] - r1[2] * r2[1];
+  r3[1] = r1[2] * r2[0] - r1[0] * r2[2];
+  r3[2] = r1[0] * r2[1] - r1[1] * r2[0];
+  for (i = 0; i < 3; i++) { R3[i * 3 + 0] = r1[i]; R3[i * 3 + 1] = r2[i]; R3[i * 3 + 2] = r3[i]; }
+  us_closest_rotation(R3);
+  omega_y = atan2(-R3[6], sqrt(R3[0] * R3[0] + R3[3] * R3[3]));
+  if (fabs(omega_y - halfPI) > smallAngle && fabs(omega_y + halfPI) > smallAngle) {
+    double cy = cos(omega_y);
+    omega_z = atan2(R3[3] / cy, R3[0] / cy);
+    omega_x = atan2(R3[7] / cy, R3[8] / cy);
+  } else {
+    omega_z = 0;
+    omega_x = atan2(R3[1], R3[4]);
+  }
+  prm[0] = x[9]; prm[1] = x[10]; prm[2] = x[11];
+  prm[3] = x[6]; prm[4] = x[7]; prm[5] = x[8];
+  prm[6] = omega_z; prm[7] = omega_y; prm[8] = omega_x; prm[9] = m_x; prm[10] = m_y;
+  prm[11] = m_x * R3[0]; prm[12] = m_x * R3[3]; prm[13] = m_x * R3[6];
+  prm[14] = m_y * R3[1]; prm[15] = m_y * R3[4]; prm[16] = m_y * R3[7];
+  prm[17] = R3[2]; prm[18] = R3[5]; prm[19] = R3[8];
+  for (i = 0; i < 20; i++) if (!(prm[i] == prm[i])) return 0;
+  return 20;
+}
+
+/* analyticLeastSquaresEstimate, .cxx:120-270: rows [u R2, v R2, R2, -I] x = -t2, pseudo-inverse with singular
+ * values <= FLT_EPSILON zeroed, rank < 12 -> no solution */
+static int usxw_analytic(const double* d, size_t n, double* prm) {
+  size_t i; int r, c, rank;
+  double x[12];
+  double* A = (double*)calloc(3 * n * 12, sizeof(double));
+  double* b = (double*)malloc(3 * n * sizeof(double));
+  for (i = 0; i < n; i++) {
+    const double* f = d + 14 * i;
+    const double ui = f[12], vi = f[13];
+    for (r = 0; r < 3; r++) {
+      double* row = A + (3 * i + r) * 12;
+      for (c = 0; c < 3; c++) { row[c] = f[3 * r + c] * ui; row[3 + c] = f[3 * r + c] * vi; row[6 + c] = f[3 * r + c]; }
+      row[9 + r] = -1.0;
+      b[3 * i + r] = -f[9 + r];
+    }
+  }
+  rank = pinv_solve((int)(3 * n), 12, A, b, 1.192092896e-07, x);
+  free(A); free(b);
+  if (rank < 12) return 0;
+  return us_post(x, prm);
+}
+
+/* e = R2 (u c1 + v c2 + t3) + t2 - t1 for the LM parameters x[11] (f(), .cxx:415-507) and, when J != NULL,
+ * its 3 x 11 Jacobian (row-major).  The reference minimises sum |e|^2 through the scalar residuals |e_i|
+ * (gradf, .cxx:510-658); the minimiser here works on the vector residuals, same objective, same minimum. */
+static void us_residual(const double* f, const double* x, double e[3], double* J) {
+  const double sz = sin(x[6]), cz = cos(x[6]), sy = sin(x[7]), cy = cos(x[7]), sx = sin(x[8]), cx = cos(x[8]);
+  const double mx = x[9], my = x[10], u = f[12], v = f[13];
+  const double c1[3] = {cz * cy, sz * cy, -sy};
+  const double c2[3] = {cz * sy * sx - sz * cx, sz * sy * sx + cz * cx, cy * sx};
+  double w[3];
+  int r, k;
+  for (k = 0; k < 3; k++) w[k] = u * mx * c1[k] + v * my * c2[k] + x[3 + k];
+  for (r = 0; r < 3; r++) e[r] = f[3 * r] * w[0] + f[3 * r + 1] * w[1] + f[3 * r + 2] * w[2] + f[9 + r] - x[r];
+  if (J) {
+    /* d c1 / d omega_z, omega_y, omega_x and the same for c2 */
+    const double dc1[3][3] = {{-sz * cy, cz * cy, 0}, {-cz * sy, -sz * sy, -cy}, {0, 0, 0}};
+    const double dc2[3][3] = {{-sz * sy * sx - cz * cx, cz * sy * sx - sz * cx, 0}, {cz * cy * sx, sz * cy * sx, -sy * sx},
+                              {cz * sy * cx + sz * sx, sz * sy * cx - cz * sx, cy * cx}};
+    double dw[11][3];
+    int p;
+    memset(dw, 0, sizeof(dw));
+    for (k = 0; k < 3; k++) {
+      dw[3 + k][k] = 1.0;
+      for (p = 0; p < 3; p++) dw[6 + p][k] = u * mx * dc1[p][k] + v * my * dc2[p][k];
+      dw[9][k] = u * c1[k];
+      dw[10][k] = v * c2[k];
+    }
+    for (r = 0; r < 3; r++)
+      for (p = 0; p < 11; p++) J[r * 11 + p] = (p < 3) ? ((p == r) ? -1.0 : 0.0) : f[3 * r] * dw[p][0] + f[3 * r + 1] * dw[p][1] + f[3 * r + 2] * dw[p][2];
+  }
+}
+
+static double us_cost(const double* d, size_t n, const double* x, double* JtJ, double* Jtr) {
+  size_t i; int a, b2, r; double cost = 0;
+  if (JtJ) { memset(JtJ, 0, sizeof(double) * 121); memset(Jtr, 0, sizeof(double) * 11); }
+  for (i = 0; i < n; i++) {
+    double e[3], J[33];
+    us_residual(d + 14 * i, x, e, JtJ ? J : NULL);
+    cost += e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+    if (JtJ) for (r = 0; r < 3; r++) for (a = 0; a < 11; a++) { Jtr[a] += J[r * 11 + a] * e[r]; for (b2 = a; b2 < 11; b2++) JtJ[a * 11 + b2] += J[r * 11 + a] * J[r * 11 + b2]; }
+  }
+  if (JtJ) for (a = 0; a < 11; a++) for (b2 = 0; b2 < a; b2++) JtJ[a * 11 + b2] = JtJ[b2 * 11 + a];
+  return cost;
+}
+
+/* iterativeLeastSquaresEstimate, .cxx:272-329: Levenberg-Marquardt from the analytic estimate, all tolerances
+ * 1e-15, at most 5000 function evaluations, parameters returned only on convergence; entries 11..19 rebuilt
+ * from the angles and scales. */
+static int usxw_iterative(const double* d, size_t n, const double* init, double* prm) {
+  const double xtol = 10e-16, gtol = 10e-16, ftol = 10e-16;
+  const int maxfev = 5000, p = 11;
+  int a, evals = 1, ok = 0;
+  double x[11], xn[11], A[121], g[11], M[121], h[11], dsc[11], cost, lambda = -1, nu = 2;
+  for (a = 0; a < p; a++) x[a] = init[a];
+  cost = us_cost(d, n, x, NULL, NULL);
+  while (evals < maxfev && !ok) {
+    double gmax = 0, fnorm = sqrt(cost);
+    int accepted = 0;
+    us_cost(d, n, x, A, g);
+    for (a = 0; a < p; a++) { double cn = sqrt(A[a * p + a]); if (cn > 0 && fnorm > 0) { double v = fabs(g[a]) / (cn * fnorm); if (v > gmax) gmax = v; } }
+    if (gmax <= gtol || cost == 0.0) { ok = 1; break; }
+    { double dmax = 0; for (a = 0; a < p; a++) if (A[a * p + a] > dmax) dmax = A[a * p + a]; for (a = 0; a < p; a++) dsc[a] = A[a * p + a] > 1e-30 * dmax + 1e-300 ? A[a * p + a] : 1e-30 * dmax + 1e-300; }
+    if (lambda < 0) lambda = 1e-3;   /* Marquardt scaling: damping lambda * diag(J^T J), as MINPACK's mode 1 */
+    while (!accepted && evals < maxfev) {
+      double hn = 0, xnorm = 0, pred = 0, cnew, actred;
+      memcpy(M, A, sizeof(double) * p * p);
+      for (a = 0; a < p; a++) M[a * p + a] += lambda * dsc[a];
+      if (!chol_solve(M, g, h, p)) { lambda *= nu; nu *= 2; continue; }
+      for (a = 0; a < p; a++) { h[a] = -h[a]; xn[a] = x[a] + h[a]; hn += h[a] * h[a]; xnorm += x[a] * x[a]; pred += h[a] * (lambda * dsc[a] * h[a] - g[a]); }
+      cnew = us_cost(d, n, xn, NULL, NULL); evals++;
+      actred = cost - cnew;
+      if (pred > 0 && actred > 0) {
+        double rho = actred / pred, t = 2 * rho - 1, f = 1 - t * t * t;
+        int fconv = actred <= ftol * cost && pred <= ftol * cost;
+        for (a = 0; a < p; a++) x[a] = xn[a];
+        lambda *= (f > 1.0 / 3.0 ? f : 1.0 / 3.0); nu = 2;
+        cost = cnew; accepted = 1;
+        if (fconv || sqrt(hn) <= xtol * sqrt(xnorm)) ok = 1;
+      } else {
+        if (sqrt(hn) <= xtol * sqrt(xnorm)) { ok = 1; break; }
+        if (fabs(actred) <= ftol * cost && pred <= ftol * cost) { ok = 1; break; }
+        lambda *= nu; nu *= 2;
+        if (!(lambda < 1e300)) { ok = 1; break; }   /* the step has shrunk below resolution: stationary to rounding */
+      }
+    }
+  }
+  if (!ok) return 0;
+  for (a = 0; a < p; a++) prm[a] = x[a];
+  {
+    const double cz = cos(x[6]), sz = sin(x[6]), cy = cos(x[7]), sy = sin(x[7]), cx = cos(x[8]), sx = sin(x[8]);
+    prm[11] = x[9] * cz * cy; prm[12] = x[9] * sz * cy; prm[13] = -x[9] * sy;
+    prm[14] = x[10] * (cz * sy * sx - sz * cx); prm[15] = x[10] * (sz * sy * sx + cz * cx); prm[16] = x[10] * cy * sx;
+    prm[17] = cz * sy * cx + sz * sx; prm[18] = sz * sy * cx - cz * sx; prm[19] = cy * cx;
+  }
+  return 20;
+}
+
+/* leastSquaresEstimate, .cxx:36-59 */
+static int usxw_lsq(int ls_type, const double* d, size_t n, double* prm) {
+  double init[20];
+  if (ls_type == 0) return usxw_analytic(d, n, prm);
+  if (!usxw_analytic(d, n, init)) return 0;
+  return usxw_iterative(d, n, init, prm);
+}
+
+/* agree, .cxx:71-107: qInT = (T2*T3)*q with VNL's left-to-right accumulation (terms that multiply the
+ * constant 0 / 1 entries of the homogeneous matrices are exact and left out) */
+static int usxw_agree(const double* prm, const double* f, double delta) {
+  const double u = f[12], v = f[13];
+  double err[3], s = 0;
+  int i;
+  for (i = 0; i < 3; i++) {
+    const double a = f[3 * i], b = f[3 * i + 1], c = f[3 * i + 2];
+    const double M0 = a * prm[11] + b * prm[12] + c * prm[13];
+    const double M1 = a * prm[14] + b * prm[15] + c * prm[16];
+    const double M3 = a * prm[3] + b * prm[4] + c * prm[5] + f[9 + i];
+    err[i] = (M0 * u + M1 * v + M3) - prm[i];
+  }
+  s = err[0] * err[0] + err[1] * err[1] + err[2] * err[2];
+  return s < delta * delta;
+}
+
 static double ray_cross_eps(double aux) {
   double a = aux > 0 ? aux : 0.017453292519943295769236907684886; /* RayIntersectionParametersEstimator.h:35 */
   double s = sin(a);
@@ -393,6 +593,7 @@ int orc_estimate(int model, double delta, double aux, const double* data, size_t
     case M_PIVOT: return pivot_solve(data, 3, params);
     case M_DENSE5: return dense_solve(5, data, 5, params);
     case M_DENSE6: return dense_solve(6, data, 6, params);
+    case M_USXW: return (n == 4) ? usxw_analytic(data, 4, params) : 0;   /* estimate() insists on exactly 4 data (.cxx:21-22) */
   }
   return -1;
 }
@@ -450,6 +651,7 @@ static int agree1(int model, double delta, const double* prm, const double* x) {
       for (i = 0; i < 3; i++) s += r[i] * r[i];
       return sqrt(s) < delta;
     }
+    case M_USXW: return usxw_agree(prm, x, delta);
     case M_DENSE5:
     case M_DENSE6: { /* DenseLinearEquationSystemParametersEstimator.hxx:111-119 */
       const int nc = (model == M_DENSE5) ? 5 : 6;
@@ -578,7 +780,7 @@ static int sphere_geometric(int dim, const double* d, size_t n, const double* in
   const double xtol = 10e-16, gtol = 10e-16, ftol = 1e-8 * 0.01;
   const int maxfev = 500;
   int p = dim + 1, a, evals = 1, ok = 0;
-  double x[4], xn[4], A[16], g[4], M[16], h[4], cost, lambda = -1, nu = 2;
+  double x[4], xn[4], A[16], g[4], M[16], h[4], dsc[4], cost, lambda = -1, nu = 2;
   for (a = 0; a < p; a++) x[a] = init[a];
   cost = sphere_cost(dim, d, n, x, NULL, NULL);
   while (evals < maxfev && !ok) {
@@ -587,13 +789,14 @@ static int sphere_geometric(int dim, const double* d, size_t n, const double* in
     sphere_cost(dim, d, n, x, A, g);
     for (a = 0; a < p; a++) { double cn = sqrt(A[a * p + a]); if (cn > 0 && fnorm > 0) { double v = fabs(g[a]) / (cn * fnorm); if (v > gmax) gmax = v; } }
     if (gmax <= gtol || cost == 0.0) { ok = 1; break; }
-    if (lambda < 0) { double dmax = 0; for (a = 0; a < p; a++) if (A[a * p + a] > dmax) dmax = A[a * p + a]; lambda = 1e-3 * dmax; }
+    { double dmax = 0; for (a = 0; a < p; a++) if (A[a * p + a] > dmax) dmax = A[a * p + a]; for (a = 0; a < p; a++) dsc[a] = A[a * p + a] > 1e-30 * dmax + 1e-300 ? A[a * p + a] : 1e-30 * dmax + 1e-300; }
+    if (lambda < 0) lambda = 1e-3;   /* Marquardt scaling: damping lambda * diag(J^T J), as MINPACK's mode 1 */
     while (!accepted && evals < maxfev) {
       double hn = 0, xnorm = 0, pred = 0, cnew, actred;
       memcpy(M, A, sizeof(double) * p * p);
-      for (a = 0; a < p; a++) M[a * p + a] += lambda;
+      for (a = 0; a < p; a++) M[a * p + a] += lambda * dsc[a];
       if (!chol_solve(M, g, h, p)) { lambda *= nu; nu *= 2; continue; }
-      for (a = 0; a < p; a++) { h[a] = -h[a]; xn[a] = x[a] + h[a]; hn += h[a] * h[a]; xnorm += x[a] * x[a]; pred += h[a] * (lambda * h[a] - g[a]); }
+      for (a = 0; a < p; a++) { h[a] = -h[a]; xn[a] = x[a] + h[a]; hn += h[a] * h[a]; xnorm += x[a] * x[a]; pred += h[a] * (lambda * dsc[a] * h[a] - g[a]); }
       cnew = sphere_cost(dim, d, n, xn, NULL, NULL); evals++;
       actred = cost - cnew;
       if (pred > 0 && actred > 0) {
@@ -707,6 +910,7 @@ int orc_least_squares(int model, double delta, double aux, int ls_type, const do
     case M_PIVOT: return pivot_solve(data, n, params);
     case M_DENSE5: return dense_solve(5, data, n, params);
     case M_DENSE6: return dense_solve(6, data, n, params);
+    case M_USXW: return usxw_lsq(ls_type, data, n, params);
   }
   return -1;
 }
@@ -718,7 +922,7 @@ int orc_least_squares(int model, double delta, double aux, int ls_type, const do
 /* RANSAC.hxx:217-249 body for one subset (full scoring, no early exit). */
 static uint32_t score_one(int model, int D, int k, double delta, double aux, const double* data, size_t n,
                           const int32_t* sub, double* prm, int* nprm) {
-  double pts[6 * 12];
+  double pts[6 * 14];
   int j; size_t m; uint32_t c = 0;
   for (j = 0; j < k; j++) memcpy(pts + j * D, data + (size_t)sub[j] * D, sizeof(double) * D);
   *nprm = orc_estimate(model, delta, aux, pts, (size_t)k, prm);
@@ -736,7 +940,7 @@ int orc_score_subsets(int model, double delta, double aux, const double* data, s
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
 #endif
   for (h = 0; h < (long long)H; h++) {
-    double prm[8]; int np, j;
+    double prm[20]; int np, j;
     uint32_t c = score_one(model, D, k, delta, aux, data, n, subsets + h * k, prm, &np);
     if (counts) counts[h] = c;
     if (params_out) for (j = 0; j < P; j++) params_out[h * P + j] = (np > 0) ? prm[j] : NAN;
@@ -791,7 +995,7 @@ int orc_ransac_exhaustive(int model, double delta, double aux, int ls_type, cons
                           double* params, uint8_t* mask, double* fraction, uint32_t* best_count, uint64_t* best_rank) {
   int D, P, k, np = 0, j;
   int32_t sub[6];
-  uint32_t best = 0; uint64_t rank = 0, brank = 0; double bprm[8], prm[8];
+  uint32_t best = 0; uint64_t rank = 0, brank = 0; double bprm[20], prm[20];
   size_t m, nin = 0;
   double* inl;
   if (orc_model_info(model, &D, &P, &k)) return -1;

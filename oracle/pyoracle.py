@@ -18,10 +18,10 @@ _u32p = ctypes.POINTER(ctypes.c_uint32)
 _i32p = ctypes.POINTER(ctypes.c_int32)
 
 MODELS = {"plane3": 0, "line2d": 1, "line2": 2, "line3": 3, "circle2": 4, "sphere3": 5, "absor": 6, "ray": 7, "pivot": 8,
-          "dense5": 9, "dense6": 10}
+          "dense5": 9, "dense6": 10, "usxw": 11}
 # model -> (D doubles per datum, P params, k minimal subset)
 INFO = {0: (3, 6, 3), 1: (2, 4, 2), 2: (2, 4, 2), 3: (3, 6, 2), 4: (2, 3, 3), 5: (3, 4, 4), 6: (6, 7, 3), 7: (6, 3, 2), 8: (12, 6, 3),
-        9: (6, 5, 5), 10: (7, 6, 6)}
+        9: (6, 5, 5), 10: (7, 6, 6), 11: (14, 20, 4)}
 
 
 def lib_path(kind):
@@ -72,13 +72,13 @@ class Oracle:
 
     def estimate(self, model, delta, data, aux=0.0):
         d = self._data(model, data)
-        out = np.zeros(16)
+        out = np.zeros(24)
         n = self._estimate(model, delta, aux, _ptr(d, _dp), d.shape[0], _ptr(out, _dp))
         return out[:max(n, 0)].copy()
 
     def least_squares(self, model, delta, data, ls_type=1, aux=0.0):
         d = self._data(model, data)
-        out = np.zeros(16)
+        out = np.zeros(24)
         n = self._least_squares(model, delta, aux, ls_type, _ptr(d, _dp), d.shape[0], _ptr(out, _dp))
         return out[:max(n, 0)].copy()
 
@@ -87,7 +87,7 @@ class Oracle:
         d = np.ascontiguousarray(data, dtype=np.float64).reshape(-1, 6)
         w = np.ascontiguousarray(weights, dtype=np.float64).reshape(-1)
         assert len(w) == d.shape[0]
-        out = np.zeros(16)
+        out = np.zeros(24)
         n = self._weighted_absor(_ptr(d, _dp), d.shape[0], _ptr(w, _dp), _ptr(out, _dp))
         return out[:max(n, 0)].copy()
 
@@ -110,7 +110,7 @@ class Oracle:
 
     def ransac_exhaustive(self, model, delta, data, ls_type=1, aux=0.0):
         d = self._data(model, data)
-        out = np.zeros(16)
+        out = np.zeros(24)
         mask = np.zeros(d.shape[0], dtype=np.uint8)
         frac = ctypes.c_double(0)
         if self.kind == "port":
@@ -124,7 +124,7 @@ class Oracle:
     def ransac_random(self, model, delta, data, prob, ls_type=1, aux=0.0):
         assert self.kind == "ref"
         d = self._data(model, data)
-        out = np.zeros(16)
+        out = np.zeros(24)
         mask = np.zeros(d.shape[0], dtype=np.uint8)
         frac = ctypes.c_double(0)
         n = self._ransac(model, delta, aux, ls_type, _ptr(d, _dp), d.shape[0], 0, prob, _ptr(out, _dp), _ptr(mask, _u8p), ctypes.byref(frac))

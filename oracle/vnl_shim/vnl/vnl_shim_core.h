@@ -337,14 +337,18 @@ class vnl_levenberg_marquardt {
       double gmax = 0, fnorm = std::sqrt(cost);
       for (unsigned a = 0; a < p; a++) { double cn = std::sqrt(A[a * p + a]); if (cn > 0 && fnorm > 0) gmax = std::max(gmax, std::fabs(g[a]) / (cn * fnorm)); }
       if (gmax <= gtol_ || cost == 0.0) return true;  // MINPACK info 4
-      if (lambda < 0) { double dmax = 0; for (unsigned a = 0; a < p; a++) dmax = std::max(dmax, A[a * p + a]); lambda = 1e-3 * dmax; }
+      // Marquardt scaling like MINPACK's mode 1: damping lambda * diag(J^T J), so that angles, scales and
+      // translations of very different magnitude are damped alike
+      std::vector<double> dsc(p);
+      { double dmax = 0; for (unsigned a = 0; a < p; a++) dmax = std::max(dmax, A[a * p + a]); for (unsigned a = 0; a < p; a++) dsc[a] = std::max(A[a * p + a], 1e-30 * dmax + 1e-300); }
+      if (lambda < 0) lambda = 1e-3;
       bool accepted = false;
       while (!accepted && num_evals_ < maxfev_) {
         std::vector<double> M(A), h(p);
-        for (unsigned a = 0; a < p; a++) M[a * p + a] += lambda;
+        for (unsigned a = 0; a < p; a++) M[a * p + a] += lambda * dsc[a];
         if (!chol_solve(M, g, h, p)) { lambda *= nu; nu *= 2; continue; }
         double hn = 0, xn = 0, pred = 0;
-        for (unsigned a = 0; a < p; a++) { h[a] = -h[a]; xnew[a] = x[a] + h[a]; hn += h[a] * h[a]; xn += x[a] * x[a]; pred += h[a] * (lambda * h[a] - g[a]); }
+        for (unsigned a = 0; a < p; a++) { h[a] = -h[a]; xnew[a] = x[a] + h[a]; hn += h[a] * h[a]; xn += x[a] * x[a]; pred += h[a] * (lambda * dsc[a] * h[a] - g[a]); }
         f_->f(xnew, fnew); ++num_evals_;
         double cnew = fnew.squared_magnitude();
         double actred = cost - cnew;
@@ -360,6 +364,7 @@ class vnl_levenberg_marquardt {
           if (std::sqrt(hn) <= xtol_ * std::sqrt(xn)) return true;  // step below resolution
           if (std::fabs(actred) <= ftol_ * cost && pred <= ftol_ * cost) return true;
           lambda *= nu; nu *= 2;
+          if (!(lambda < 1e300)) return true;   // the step has shrunk below resolution: stationary to rounding
         }
       }
     }

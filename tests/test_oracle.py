@@ -10,7 +10,7 @@ from lsqrrecipes_b200 import synth
 from oracle.pyoracle import INFO, MODELS
 
 ALL = list(MODELS.items())
-PINV_MODELS = ("pivot", "dense5", "dense6")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
+PINV_MODELS = ("pivot", "dense5", "dense6", "usxw")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
 
 
 # ---- the reference's own literal test vectors -------------------------------------------
@@ -68,15 +68,18 @@ def test_port_matches_reference_fixture(port, name, m):
 @pytest.mark.parametrize("name,m", ALL)
 def test_port_exhaustive_and_lsq_fixture(port, name, m):
     g = golden(name)
-    for ls_type in ([0, 1] if name in ("circle2", "sphere3") else [1]):
+    for ls_type in ([0, 1] if name in ("circle2", "sphere3", "usxw") else [1]):
+        # the cross-wire LM runs on vector residuals here and on the reference's scalar |e_i| residuals there:
+        # same minimum, compared at the north star's 1e-6 relative for converged Levenberg-Marquardt results
+        tol = 1e-6 if (name == "usxw" and ls_type == 1) else 1e-8
         prm, mask, frac, cnt, rank = port.ransac_exhaustive(m, float(g["delta"]), g["small"], ls_type=ls_type)
         assert np.array_equal(mask, g[f"ex_mask_ls{ls_type}"])
         assert frac == float(g[f"ex_fraction_ls{ls_type}"])
-        assert same_up_to_sign(prm, g[f"ex_params_ls{ls_type}"], SIGN_IDX[name], 1e-8)
+        assert same_up_to_sign(prm, g[f"ex_params_ls{ls_type}"], SIGN_IDX[name], tol)
         b = int(np.argmax(g["counts"]))
         _, bm = port.agree(m, float(g["delta"]), g["params"][b], g["data"])
         ls = port.least_squares(m, float(g["delta"]), g["data"][bm.astype(bool)], ls_type)
-        assert same_up_to_sign(ls, g[f"lsq_ls{ls_type}"], SIGN_IDX[name], 1e-8)
+        assert same_up_to_sign(ls, g[f"lsq_ls{ls_type}"], SIGN_IDX[name], tol)
 
 
 def test_config1_plane23(port):

@@ -16,13 +16,15 @@ from lsqrrecipes_b200 import FP32, FP64, SAMPLE_EXHAUSTIVE, SAMPLE_LIST, SAMPLE_
 from oracle.pyoracle import INFO, MODELS
 
 pytestmark = pytest.mark.gpu
-ALL = list(MODELS.items())
-PINV_MODELS = ("pivot", "dense5", "dense6")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
+from lsqrrecipes_b200 import MODELS as ENGINE_MODELS
+
+ALL = [(n, m) for n, m in MODELS.items() if n in ENGINE_MODELS]   # every estimator the engine implements
+PINV_MODELS = ("pivot", "dense5", "dense6", "usxw")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
 REFINE_TOL = 1e-6
 
 
 def _ls_types(name):
-    return [0, 1] if name in ("circle2", "sphere3") else [1]
+    return [0, 1] if name in ("circle2", "sphere3", "usxw") else [1]
 
 
 @pytest.mark.parametrize("name,m", ALL)
