@@ -46,7 +46,9 @@ typedef enum lsqr_model {
   LSQR_PIVOT = 8,   /* PivotCalibrationEstimator              PivotCalibrationParametersEstimator.cxx:9-123 */
   LSQR_DENSE5 = 9,  /* DenseLinearEquationSystemParametersEstimator<double,5>   DenseLinearEquationSystemParametersEstimator.hxx:17-119 */
   LSQR_DENSE6 = 10, /* DenseLinearEquationSystemParametersEstimator<double,6>   (datum = AugmentedRow: n coefficients, right-hand side) */
-  LSQR_NUM_MODELS = 11
+  LSQR_USXW = 11,   /* SingleUnknownPointTargetUSCalibrationParametersEstimator (cross-wire phantom)   SinglePointTargetUSCalibrationParametersEstimator.cxx:10-329
+                     * datum = 14 doubles [R2 row-major, t2, u, v]; ls_type 0 = ANALYTIC, 1 = ITERATIVE (Levenberg-Marquardt) */
+  LSQR_NUM_MODELS = 12
 } lsqr_model;
 
 typedef enum lsqr_status {

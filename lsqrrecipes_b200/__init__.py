@@ -33,11 +33,12 @@ from .estimators import (  # noqa: F401
     RayIntersectionParametersEstimator,
     PivotCalibrationEstimator,
     DenseLinearEquationSystemParametersEstimator,
+    SingleUnknownPointTargetUSCalibrationParametersEstimator,
 )
 
 __all__ = [
     "Engine", "LsqrError", "MODELS", "MODEL_INFO", "FP32", "FP64", "RANSAC",
     "PlaneParametersEstimator", "LineParametersEstimator", "Line2DParametersEstimator",
     "SphereParametersEstimator", "AbsoluteOrientationParametersEstimator",
-    "RayIntersectionParametersEstimator", "PivotCalibrationEstimator", "DenseLinearEquationSystemParametersEstimator",
+    "RayIntersectionParametersEstimator", "PivotCalibrationEstimator", "DenseLinearEquationSystemParametersEstimator", "SingleUnknownPointTargetUSCalibrationParametersEstimator",
 ]

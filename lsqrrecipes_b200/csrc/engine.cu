@@ -375,7 +375,8 @@ int refine_impl(lsqr_ctx* ctx, DataSet& ds, int use_mask, double* out_params, in
     ds.moments_valid = false;
   }
   double* out_dev = ctx->small_dev + kSmOut;
-  const bool geometric = (ctx->model == CIRCLE2 || ctx->model == SPHERE3) && ctx->ls_type == LSQR_LS_GEOMETRIC;
+  // iterative refinement: geometric circle / sphere fit, iterative cross-wire calibration (ls_type 1 in both)
+  const bool geometric = (ctx->model == CIRCLE2 || ctx->model == SPHERE3 || ctx->model == USXW) && ctx->ls_type == LSQR_LS_GEOMETRIC;
   launch_solve_moments(ctx->model, dv, ctx->rb.moments, geometric ? 1 : 0, out_dev, s); ctx->launches++;
   if (geometric) {
     // SphereParametersEstimator.hxx:224-230: algebraic fit as the start, then Levenberg-Marquardt.
@@ -383,8 +384,8 @@ int refine_impl(lsqr_ctx* ctx, DataSet& ds, int use_mask, double* out_params, in
     const int nlm = moments_count(ctx->model, true);
     launch_lm_init(out_dev, st, s); ctx->launches++;
     ds.moments_valid = false;
-    for (int it = 0; it < 520; it++) {
-      CK(cudaMemcpyAsync(ctx->pin, st + 7, sizeof(double), cudaMemcpyDeviceToHost, s));
+    for (int it = 0; it < 5200; it++) {   // the controller stops itself (500 / 5000 evaluations); this is only a safety bound
+      CK(cudaMemcpyAsync(ctx->pin, st + lm_status_offset(), sizeof(double), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
       if (ctx->pin[0] != 0.0) break;
       launch_mask_moments(ctx->model, dv, b, e, nullptr, use_mask ? 2 : 0, st, ctx->cfg, ctx->rb, s); ctx->launches++;
@@ -673,6 +674,7 @@ int lsqr_estimate(lsqr_ctx* ctx, const double* packed, size_t n, double* out_par
   const ModelInfo mi = model_info(ctx->model);
   *n_params = 0;
   if (n < (size_t)mi.K) return LSQR_OK;  // e.g. PlaneParametersEstimator.hxx:45-46
+  if (ctx->model == USXW && n != (size_t)mi.K) return LSQR_OK;  // SinglePointTargetUSCalibrationParametersEstimator.cxx:21-22: exactly four
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   double* in_dev = ctx->small_dev + kSmEst;  // K*D <= 64 doubles

@@ -9,6 +9,7 @@
 namespace lsqr {
 
 constexpr int kTilePad = 1024;   // leading dimension of the SoA point arrays is a multiple of this
+constexpr int kLmStateDoubles = 192;  // device scratch reserved for the Levenberg-Marquardt controller state
 constexpr int kMaxMoments = 96;  // upper bound on the doubles accumulated per thread by the refine reductions (cross-wire US calibration: 91)
 
 // Device-resident description of the uploaded data.
@@ -75,6 +76,7 @@ void launch_lm_finish(int model, const DataView& dv, const double* state, double
 void launch_weighted_absor_moments(const DataView& dv, const double* weights_dev, const RefineBuffers& rb, cudaStream_t s);
 void launch_solve_weighted_absor(const DataView& dv, const double* moments, double* out_dev, cudaStream_t s);
 int moments_count(int model, bool lm);
+int lm_status_offset();   // index of the status word (0 run, 1 converged, 2 failed) in the LM state
 int mask_moments_ctas_per_sm();   // grid of launch_mask_moments = this x SMs (one wave)
 void launch_expand_mask(const uint32_t* bits, uint32_t n, uint8_t* bytes, cudaStream_t s);
 

@@ -72,6 +72,7 @@ __device__ __forceinline__ f2 join(float lo, float hi) { f2 r; asm("mov.b64 %0, 
 //   RAY      (x - c)
 //   PIVOT    (tDRF, tW - c)
 //   DENSE n  (x[n], -1): a.x - b as n+1 FMAs over the (uncentred) augmented row
+//   USXW     (m_x R3(:,1), m_y R3(:,2), t3, t1 - c)
 template <int M> __device__ __forceinline__ void hoist32(const double* p, const double* c, const EstCfg& cfg, float* q);
 template <> __device__ __forceinline__ void hoist32<PLANE3>(const double* p, const double* c, const EstCfg&, float* q) {
   q[0] = (float)p[0]; q[1] = (float)p[1]; q[2] = (float)p[2];
@@ -116,6 +117,11 @@ template <int N> __device__ __forceinline__ void hoist_dense(const double* p, fl
 }
 template <> __device__ __forceinline__ void hoist32<DENSE5>(const double* p, const double*, const EstCfg&, float* q) { hoist_dense<5>(p, q); }
 template <> __device__ __forceinline__ void hoist32<DENSE6>(const double* p, const double*, const EstCfg&, float* q) { hoist_dense<6>(p, q); }
+
+template <> __device__ __forceinline__ void hoist32<USXW>(const double* p, const double* c, const EstCfg&, float* q) {
+  for (int i = 0; i < 6; i++) q[i] = (float)p[11 + i];
+  for (int i = 0; i < 3; i++) { q[6 + i] = (float)p[3 + i]; q[9 + i] = (float)(p[i] - c[9 + i]); }
+}
 
 template <int M>
 __global__ void hoist32_kernel(const double* __restrict__ hyp64, size_t hld, uint32_t H, DataView dv, EstCfg cfg, float* __restrict__ hyp32) {
@@ -168,6 +174,7 @@ __device__ __forceinline__ void load_hyp32(const float* __restrict__ hyp, size_t
     case PIVOT: { CALL(PIVOT); break; }       \
     case DENSE5: { CALL(DENSE5); break; }     \
     case DENSE6: { CALL(DENSE6); break; }     \
+    case USXW: { CALL(USXW); break; }         \
     default: break;                           \
   }
 
@@ -291,6 +298,24 @@ template <> struct Eval<DENSE6> {
   static constexpr bool kHasAbsForm = true;
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return dense_dist<6>(q, x); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
+};
+
+// cross-wire: e = R2 (u c1 + v c2 + t3) + t2 - t1, |e|^2 - delta^2   (21 FMA-pipe operations)
+template <> struct Eval<USXW> {
+  static constexpr bool kHasAbsForm = false;
+  __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) {
+    f2 w[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) w[k] = fma2(x[12], q[k], fma2(x[13], q[3 + k], q[6 + k]));
+    f2 g = t.neg_delta2;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const f2 e = sub2(fma2(x[3 * r], w[0], fma2(x[3 * r + 1], w[1], fma2(x[3 * r + 2], w[2], x[9 + r]))), q[9 + r]);
+      g = fma2(e, e, g);
+    }
+    return g;
+  }
 };
 
 // FSETP + predicated IADD on two residuals, written in PTX so that ptxas keeps the 2-instruction form.
@@ -521,6 +546,7 @@ template <> struct BlockCB<RAY> { static constexpr int R = 8, PPI = 2; };
 template <> struct BlockCB<PIVOT> { static constexpr int R = 6, PPI = 1; };
 template <> struct BlockCB<DENSE5> { static constexpr int R = 8, PPI = 2; };
 template <> struct BlockCB<DENSE6> { static constexpr int R = 8, PPI = 2; };
+template <> struct BlockCB<USXW> { static constexpr int R = 4, PPI = 1; };
 
 template <int M>
 static int run_consensus_cb(const DataView& dv, const float* hyp, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms, cudaStream_t s) {
@@ -581,6 +607,7 @@ template <> struct Block32<RAY> { static constexpr int R = 8, PPI = 1; };
 template <> struct Block32<PIVOT> { static constexpr int R = 4, PPI = 1; };
 template <> struct Block32<DENSE5> { static constexpr int R = 6, PPI = 2; };
 template <> struct Block32<DENSE6> { static constexpr int R = 6, PPI = 2; };
+template <> struct Block32<USXW> { static constexpr int R = 3, PPI = 1; };
 
 int launch_consensus32(int model, const DataView& dv, const float* hyp32, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms,
                        cudaStream_t s) {

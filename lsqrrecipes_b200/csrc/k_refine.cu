@@ -29,9 +29,26 @@ __host__ __device__ inline int n_moments(int model, bool lm) {
     case PIVOT: return 22;
     case DENSE5: return 21;   // count, A^T A upper triangle (15), A^T b (5)
     case DENSE6: return 28;   // count, 21, 6
+    case USXW: return lm ? 79 : 91;   // LM: count, J^T J (66), J^T e (11), cost; analytic: count, A^T A (78), A^T b (12)
   }
   return 0;
 }
+// Layout of the Levenberg-Marquardt state (see the controller further down)
+constexpr int kLmMaxP = 11;
+enum : int {
+  LM_X = 0,                      // [kLmMaxP] current point
+  LM_COST = 11, LM_LAMBDA = 12, LM_NU = 13,
+  LM_STATUS = 14,                // 0 run, 1 converged, 2 failed
+  LM_EVALS = 15,
+  LM_PHASE = 16,                 // 0 = evaluate x, 1 = evaluate trial
+  LM_TRIAL = 17,                 // [kLmMaxP]
+  LM_PRED = 28, LM_HN = 29, LM_XN = 30,
+  LM_A = 32,                     // [kLmMaxP * kLmMaxP] J^T J at x
+  LM_G = 153,                    // [kLmMaxP] J^T r at x
+  LM_SIZE = 176
+};
+static_assert(kLmStateDoubles >= LM_SIZE, "engine.h: LM state buffer too small");
+
 #ifndef LSQR_MM_CTAS
 #define LSQR_MM_CTAS 2
 #endif
@@ -41,18 +58,19 @@ __host__ __device__ inline int n_moments(int model, bool lm) {
 int mask_moments_ctas_per_sm() { return LSQR_MM_CTAS; }
 int moments_count(int model, bool lm) { return n_moments(model, lm); }
 
-template <int M> struct Mom { static constexpr int N = 0, NLM = 0; };
-template <> struct Mom<PLANE3>  { static constexpr int N = 10, NLM = 0; };
-template <> struct Mom<LINE3>   { static constexpr int N = 10, NLM = 0; };
-template <> struct Mom<LINE2D>  { static constexpr int N = 6,  NLM = 0; };
-template <> struct Mom<LINE2>   { static constexpr int N = 6,  NLM = 0; };
-template <> struct Mom<CIRCLE2> { static constexpr int N = 9,  NLM = 11; };
-template <> struct Mom<SPHERE3> { static constexpr int N = 14, NLM = 16; };
-template <> struct Mom<ABSOR>   { static constexpr int N = 16, NLM = 0; };
-template <> struct Mom<RAY>     { static constexpr int N = 10, NLM = 0; };
-template <> struct Mom<PIVOT>   { static constexpr int N = 22, NLM = 0; };
-template <> struct Mom<DENSE5>  { static constexpr int N = 21, NLM = 0; };
-template <> struct Mom<DENSE6>  { static constexpr int N = 28, NLM = 0; };
+template <int M> struct Mom { static constexpr int N = 0, NLM = 0, NPLM = 1; };   // NPLM = parameters of the LM problem
+template <> struct Mom<PLANE3>  { static constexpr int N = 10, NLM = 0, NPLM = 1; };
+template <> struct Mom<LINE3>   { static constexpr int N = 10, NLM = 0, NPLM = 1; };
+template <> struct Mom<LINE2D>  { static constexpr int N = 6,  NLM = 0, NPLM = 1; };
+template <> struct Mom<LINE2>   { static constexpr int N = 6,  NLM = 0, NPLM = 1; };
+template <> struct Mom<CIRCLE2> { static constexpr int N = 9,  NLM = 11, NPLM = 3; };
+template <> struct Mom<SPHERE3> { static constexpr int N = 14, NLM = 16, NPLM = 4; };
+template <> struct Mom<ABSOR>   { static constexpr int N = 16, NLM = 0, NPLM = 1; };
+template <> struct Mom<RAY>     { static constexpr int N = 10, NLM = 0, NPLM = 1; };
+template <> struct Mom<PIVOT>   { static constexpr int N = 22, NLM = 0, NPLM = 1; };
+template <> struct Mom<DENSE5>  { static constexpr int N = 21, NLM = 0, NPLM = 1; };
+template <> struct Mom<DENSE6>  { static constexpr int N = 28, NLM = 0, NPLM = 1; };
+template <> struct Mom<USXW>    { static constexpr int N = 91, NLM = 79, NPLM = 11; };
 
 // q = centred datum.  acc[0] counts.
 template <int DIM> __device__ __forceinline__ void acc_scatter(const double* q, double* acc) {
@@ -151,10 +169,73 @@ template <int N> __device__ __forceinline__ void acc_dense(const double* q, doub
 template <> __device__ __forceinline__ void accumulate<DENSE5>(const double* q, double* acc) { acc_dense<5>(q, acc); }
 template <> __device__ __forceinline__ void accumulate<DENSE6>(const double* q, double* acc) { acc_dense<6>(q, acc); }
 
+// Normal equations of the rows [u R2, v R2, R2, -I] x = -t2 (SinglePointTargetUSCalibrationParametersEstimator.cxx:137-189)
+template <> __device__ __forceinline__ void accumulate<USXW>(const double* q, double* acc) {
+  acc[0] += 1.0;
+  const double u = q[12], v = q[13];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    double row[12];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { row[c] = q[3 * r + c] * u; row[3 + c] = q[3 * r + c] * v; row[6 + c] = q[3 * r + c]; row[9 + c] = (c == r) ? -1.0 : 0.0; }
+    const double b = -q[9 + r];
+    int o = 1;
+#pragma unroll
+    for (int a = 0; a < 12; a++)
+#pragma unroll
+      for (int bb = a; bb < 12; bb++) acc[o++] += row[a] * row[bb];
+#pragma unroll
+    for (int a = 0; a < 12; a++) acc[o++] += row[a] * b;
+  }
+}
+// Levenberg-Marquardt pass of the cross-wire calibration at x[11] = [t1, t3, omega_z, omega_y, omega_x, m_x, m_y]:
+// e = R2 (u m_x c1 + v m_y c2 + t3) + t2 - t1 and its 3 x 11 Jacobian (f / gradf of .cxx:415-658 minimise the same
+// sum |e|^2 through the scalar residuals |e_i|).
+__device__ __forceinline__ void acc_us_lm(const double* q, const double* x, double* acc) {
+  const double sz = sin(x[6]), cz = cos(x[6]), sy = sin(x[7]), cy = cos(x[7]), sx = sin(x[8]), cx = cos(x[8]);
+  const double mx = x[9], my = x[10], u = q[12], v = q[13];
+  const double c1[3] = {cz * cy, sz * cy, -sy};
+  const double c2[3] = {cz * sy * sx - sz * cx, sz * sy * sx + cz * cx, cy * sx};
+  const double dc1[3][3] = {{-sz * cy, cz * cy, 0}, {-cz * sy, -sz * sy, -cy}, {0, 0, 0}};
+  const double dc2[3][3] = {{-sz * sy * sx - cz * cx, cz * sy * sx - sz * cx, 0}, {cz * cy * sx, sz * cy * sx, -sy * sx},
+                            {cz * sy * cx + sz * sx, sz * sy * cx - cz * sx, cy * cx}};
+  double w[3], dw[8][3];   // d w / d (t3 (3), omega (3), m_x, m_y)
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    w[k] = u * mx * c1[k] + v * my * c2[k] + x[3 + k];
+#pragma unroll
+    for (int p = 0; p < 3; p++) { dw[p][k] = (p == k) ? 1.0 : 0.0; dw[3 + p][k] = u * mx * dc1[p][k] + v * my * dc2[p][k]; }
+    dw[6][k] = u * c1[k];
+    dw[7][k] = v * c2[k];
+  }
+  acc[0] += 1.0;
+  double cost = 0;
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const double a = q[3 * r], b = q[3 * r + 1], c = q[3 * r + 2];
+    const double e = a * w[0] + b * w[1] + c * w[2] + q[9 + r] - x[r];
+    double J[11];
+#pragma unroll
+    for (int p = 0; p < 3; p++) J[p] = (p == r) ? -1.0 : 0.0;
+#pragma unroll
+    for (int p = 0; p < 8; p++) J[3 + p] = a * dw[p][0] + b * dw[p][1] + c * dw[p][2];
+    int o = 1;
+#pragma unroll
+    for (int i = 0; i < 11; i++)
+#pragma unroll
+      for (int j = i; j < 11; j++) acc[o++] += J[i] * J[j];
+#pragma unroll
+    for (int i = 0; i < 11; i++) acc[o++] += J[i] * e;
+    cost += e * e;
+  }
+  acc[78] += cost;
+}
+
 __host__ __device__ inline bool centred_comp(int model, int d) {
   switch (model) {
     case RAY: return d < 3;
     case PIVOT: return d >= 9;
+    case USXW: return d >= 9 && d < 12;
     case DENSE5: case DENSE6: return false;
     default: return true;
   }
@@ -181,12 +262,12 @@ __global__ void __launch_bounds__(256, LSQR_MM_CTAS) mask_moments_kernel(DataVie
     for (int j = 0; j < P; j++) prm[j] = params_dev[j];
     prepare<M>(prm, hq);
   }
-  double lmx[4] = {0, 0, 0, 0};
+  double lmx[LM ? Mom<M>::NPLM : 1] = {0};
   if (LM) {
-    // lm_state[9] selects the evaluation point: 0 -> x (state[0..3]), 1 -> trial (state[10..13])
-    const int off = (lm_state[9] != 0.0) ? 10 : 0;
+    // the phase selects the evaluation point: x or the trial point
+    const int off = (lm_state[LM_PHASE] != 0.0) ? LM_TRIAL : LM_X;
 #pragma unroll
-    for (int j = 0; j < 4; j++) lmx[j] = lm_state[off + j];
+    for (int j = 0; j < Mom<M>::NPLM; j++) lmx[j] = lm_state[off + j];
   }
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
@@ -221,6 +302,7 @@ __global__ void __launch_bounds__(256, LSQR_MM_CTAS) mask_moments_kernel(DataVie
         if (LM) {
           if constexpr (M == CIRCLE2) acc_sphere_lm<2>(q, lmx, acc);
           if constexpr (M == SPHERE3) acc_sphere_lm<3>(q, lmx, acc);
+          if constexpr (M == USXW) acc_us_lm(q, lmx, acc);
         } else accumulate<M>(q, acc);
       }
     }
@@ -254,6 +336,7 @@ void launch_mask_moments(int model, const DataView& dv, uint32_t begin, uint32_t
   if (lm_state) {
     if (model == CIRCLE2) { BYMODE(CIRCLE2, true); }
     else if (model == SPHERE3) { BYMODE(SPHERE3, true); }
+    else if (model == USXW) { BYMODE(USXW, true); }
     return;
   }
   switch (model) {
@@ -268,6 +351,7 @@ void launch_mask_moments(int model, const DataView& dv, uint32_t begin, uint32_t
     case PIVOT: { BYMODE(PIVOT, false); break; }
     case DENSE5: { BYMODE(DENSE5, false); break; }
     case DENSE6: { BYMODE(DENSE6, false); break; }
+    case USXW: { BYMODE(USXW, false); break; }
   }
 #undef BYMODE
 #undef LAUNCH
@@ -471,6 +555,34 @@ template <int N> __device__ int solve_dense(const double* m, double* out) {
   return sym_pinv_solve<N>(A, b, out) < N ? 0 : N;
 }
 
+// Analytic cross-wire calibration (SinglePointTargetUSCalibrationParametersEstimator.cxx:120-270) through the
+// 12 x 12 normal equations; t1 comes back relative to the centre of the t2 components.
+__device__ int solve_us(const double* m, const double* c, double* out) {
+  if (m[0] < 4.0) return 0;
+  // diagonally scaled Cholesky of the 12 x 12 normal equations; a pivot below 1e-13 of the unit diagonal means
+  // rank < 12 (the reference's "points do not yield a solution", .cxx:195-196)
+  double S[144], sc[12], y[12], x[12];
+  {
+    int o = 1;
+    for (int a = 0; a < 12; a++) for (int bb = a; bb < 12; bb++) { const double v = m[o++]; S[a * 12 + bb] = v; S[bb * 12 + a] = v; }
+    for (int a = 0; a < 12; a++) y[a] = m[o++];
+  }
+  for (int i = 0; i < 12; i++) { if (!(S[i * 12 + i] > 0)) return 0; sc[i] = 1.0 / sqrt(S[i * 12 + i]); }
+  for (int i = 0; i < 12; i++) { for (int j = 0; j < 12; j++) S[i * 12 + j] *= sc[i] * sc[j]; y[i] *= sc[i]; }
+  for (int j = 0; j < 12; j++) {
+    double d = S[j * 12 + j];
+    for (int k = 0; k < j; k++) d -= S[j * 12 + k] * S[j * 12 + k];
+    if (!(d > 1e-13)) return 0;
+    S[j * 12 + j] = sqrt(d);
+    for (int i = j + 1; i < 12; i++) { double t = S[i * 12 + j]; for (int k = 0; k < j; k++) t -= S[i * 12 + k] * S[j * 12 + k]; S[i * 12 + j] = t / S[j * 12 + j]; }
+  }
+  for (int i = 0; i < 12; i++) { double t = y[i]; for (int k = 0; k < i; k++) t -= S[i * 12 + k] * x[k]; x[i] = t / S[i * 12 + i]; }
+  for (int i = 11; i >= 0; i--) { double t = x[i]; for (int k = i + 1; k < 12; k++) t -= S[k * 12 + i] * x[k]; x[i] = t / S[i * 12 + i]; }
+  for (int i = 0; i < 12; i++) x[i] *= sc[i];
+  if (c) for (int j = 0; j < 3; j++) x[9 + j] += c[9 + j];
+  return us_post(x, out) ? 20 : 0;
+}
+
 // out[0] = number of parameters (0 = the reference's empty vector), out[1..] = parameters.
 // For CIRCLE2/SPHERE3 the parameters stay in centred coordinates when keep_centred != 0 (LM start).
 __global__ void solve_moments_kernel(int model, DataView dv, const double* __restrict__ m, int keep_centred, double* __restrict__ out) {
@@ -490,6 +602,7 @@ __global__ void solve_moments_kernel(int model, DataView dv, const double* __res
     case PIVOT: np = solve_pivot(m, c, p); break;
     case DENSE5: np = solve_dense<5>(m, p); break;
     case DENSE6: np = solve_dense<6>(m, p); break;
+    case USXW: np = solve_us(m, keep_centred ? nullptr : c, p); break;   // LM start: t1 stays relative to the centre
   }
   out[0] = (double)np;
   for (int j = 0; j < np; j++) out[1 + j] = p[j];
@@ -509,12 +622,15 @@ void launch_solve_moments(int model, const DataView& dv, const double* moments, 
 }
 
 // ---------------------------------------------------------------------------------------
-// Levenberg-Marquardt controller (SphereParametersEstimator.hxx:310-338: xtol = gtol = 1e-15,
-// ftol = VNL default 1e-10, at most 500 function evaluations, result only if converged).
-// state: [0..3] x, [4] cost, [5] lambda, [6] nu, [7] status (0 run, 1 converged, 2 failed),
-//        [8] evals, [9] phase (0 = evaluate x, 1 = evaluate trial), [10..13] trial,
-//        [14..29] A = J^T J at x, [30..33] g = J^T r at x, [34] pred, [35] |h|^2, [36] |x|^2
+// Levenberg-Marquardt controller, shared by the geometric circle / sphere fit
+// (SphereParametersEstimator.hxx:310-338: xtol = gtol = 1e-15, ftol = VNL default 1e-10, at most 500
+// function evaluations) and the iterative cross-wire calibration
+// (SinglePointTargetUSCalibrationParametersEstimator.cxx:272-329: all tolerances 1e-15, 5000 evaluations).
+// Result only if converged.  Marquardt scaling (damping lambda * diag(J^T J)) like MINPACK's mode 1.
+// One pass of mask_moments_kernel delivers J^T J, J^T r and the cost at the point the state asks for.
 // ---------------------------------------------------------------------------------------
+
+
 template <int NP> __device__ bool chol_solve(const double* Ain, const double* b, double* x) {
   double M[NP * NP];
   for (int i = 0; i < NP * NP; i++) M[i] = Ain[i];
@@ -530,97 +646,129 @@ template <int NP> __device__ bool chol_solve(const double* Ain, const double* b,
   return true;
 }
 
+// moments layout of an LM pass: [0] count, J^T J upper triangle, J^T r, cost
 template <int NP> __device__ void lm_load_normal(const double* m, double* A, double* g, double* cost) {
   int o = 1;
-  for (int a = 0; a < NP; a++) for (int b = a; b < NP; b++) { const double v = m[o++]; A[a * 4 + b] = v; A[b * 4 + a] = v; }
+  for (int a = 0; a < NP; a++) for (int b = a; b < NP; b++) { const double v = m[o++]; A[a * NP + b] = v; A[b * NP + a] = v; }
   for (int a = 0; a < NP; a++) g[a] = m[o++];
   *cost = m[o];
 }
+template <int NP> __device__ double lm_scale(const double* A, int a) {
+  double dmax = 0;
+  for (int i = 0; i < NP; i++) if (A[i * NP + i] > dmax) dmax = A[i * NP + i];
+  const double floor_ = 1e-30 * dmax + 1e-300;
+  return A[a * NP + a] > floor_ ? A[a * NP + a] : floor_;
+}
 // Computes the next trial point from (A, g, lambda); grows lambda until the damped system is SPD.
 template <int NP> __device__ void lm_make_trial(double* st) {
-  double* A = st + 14; double* g = st + 30;
+  const double* A = st + LM_A; const double* g = st + LM_G;
+  double dsc[NP];
+  for (int a = 0; a < NP; a++) dsc[a] = lm_scale<NP>(A, a);
   for (int it = 0; it < 64; it++) {
     double Mx[NP * NP], h[NP];
-    for (int a = 0; a < NP; a++) for (int b = 0; b < NP; b++) Mx[a * NP + b] = A[a * 4 + b] + (a == b ? st[5] : 0.0);
+    for (int a = 0; a < NP; a++) for (int b = 0; b < NP; b++) Mx[a * NP + b] = A[a * NP + b] + (a == b ? st[LM_LAMBDA] * dsc[a] : 0.0);
     if (chol_solve<NP>(Mx, g, h)) {
       double hn = 0, xn = 0, pred = 0;
-      for (int a = 0; a < NP; a++) { h[a] = -h[a]; st[10 + a] = st[a] + h[a]; hn += h[a] * h[a]; xn += st[a] * st[a]; pred += h[a] * (st[5] * h[a] - g[a]); }
-      st[34] = pred; st[35] = hn; st[36] = xn;
-      st[9] = 1.0;
+      for (int a = 0; a < NP; a++) {
+        h[a] = -h[a]; st[LM_TRIAL + a] = st[LM_X + a] + h[a];
+        hn += h[a] * h[a]; xn += st[LM_X + a] * st[LM_X + a]; pred += h[a] * (st[LM_LAMBDA] * dsc[a] * h[a] - g[a]);
+      }
+      st[LM_PRED] = pred; st[LM_HN] = hn; st[LM_XN] = xn;
+      st[LM_PHASE] = 1.0;
       return;
     }
-    st[5] *= st[6]; st[6] *= 2;
+    st[LM_LAMBDA] *= st[LM_NU]; st[LM_NU] *= 2;
   }
-  st[7] = 2.0;
+  st[LM_STATUS] = 2.0;
 }
 template <int NP> __device__ bool lm_gradient_converged(const double* st) {
   const double gtol = 10e-16;
-  const double* A = st + 14; const double* g = st + 30;
-  const double fnorm = sqrt(st[4]);
+  const double* A = st + LM_A; const double* g = st + LM_G;
+  const double fnorm = sqrt(st[LM_COST]);
   double gmax = 0;
-  for (int a = 0; a < NP; a++) { const double cn = sqrt(A[a * 4 + a]); if (cn > 0 && fnorm > 0) { const double v = fabs(g[a]) / (cn * fnorm); if (v > gmax) gmax = v; } }
-  return gmax <= gtol || st[4] == 0.0;
+  for (int a = 0; a < NP; a++) { const double cn = sqrt(A[a * NP + a]); if (cn > 0 && fnorm > 0) { const double v = fabs(g[a]) / (cn * fnorm); if (v > gmax) gmax = v; } }
+  return gmax <= gtol || st[LM_COST] == 0.0;
 }
-template <int NP> __device__ void lm_update(const double* m, double* st) {
-  const double xtol = 10e-16, ftol = 1e-8 * 0.01;
-  const int maxfev = 500;
-  if (st[7] != 0.0) return;
-  if (st[9] == 0.0) {  // first evaluation at x
-    lm_load_normal<NP>(m, st + 14, st + 30, st + 4);
-    st[8] = 1.0;
-    if (lm_gradient_converged<NP>(st)) { st[7] = 1.0; return; }
-    double dmax = 0;
-    for (int a = 0; a < NP; a++) if (st[14 + a * 4 + a] > dmax) dmax = st[14 + a * 4 + a];
-    st[5] = 1e-3 * dmax; st[6] = 2.0;
+template <int NP> __device__ void lm_update(const double* m, double* st, double ftol, int maxfev) {
+  const double xtol = 10e-16;
+  if (st[LM_STATUS] != 0.0) return;
+  if (st[LM_PHASE] == 0.0) {  // first evaluation at x
+    lm_load_normal<NP>(m, st + LM_A, st + LM_G, st + LM_COST);
+    st[LM_EVALS] = 1.0;
+    if (lm_gradient_converged<NP>(st)) { st[LM_STATUS] = 1.0; return; }
+    st[LM_LAMBDA] = 1e-3; st[LM_NU] = 2.0;
     lm_make_trial<NP>(st);
     return;
   }
-  double An[16], gn[4], cnew;
+  double An[NP * NP], gn[NP], cnew;
   lm_load_normal<NP>(m, An, gn, &cnew);
-  st[8] += 1.0;
-  const double cost = st[4], pred = st[34], hn = st[35], xn = st[36];
+  st[LM_EVALS] += 1.0;
+  const double cost = st[LM_COST], pred = st[LM_PRED], hn = st[LM_HN], xn = st[LM_XN];
   const double actred = cost - cnew;
   if (pred > 0 && actred > 0) {
     const double rho = actred / pred, t = 2 * rho - 1, f = 1 - t * t * t;
     const bool fconv = actred <= ftol * cost && pred <= ftol * cost;
-    for (int a = 0; a < NP; a++) st[a] = st[10 + a];
-    for (int i = 0; i < 16; i++) st[14 + i] = An[i];
-    for (int i = 0; i < 4; i++) st[30 + i] = gn[i];
-    st[5] *= (f > 1.0 / 3.0 ? f : 1.0 / 3.0); st[6] = 2.0;
-    st[4] = cnew;
-    if (fconv || sqrt(hn) <= xtol * sqrt(xn)) { st[7] = 1.0; return; }
-    if (lm_gradient_converged<NP>(st)) { st[7] = 1.0; return; }
+    for (int a = 0; a < NP; a++) st[LM_X + a] = st[LM_TRIAL + a];
+    for (int i = 0; i < NP * NP; i++) st[LM_A + i] = An[i];
+    for (int i = 0; i < NP; i++) st[LM_G + i] = gn[i];
+    st[LM_LAMBDA] *= (f > 1.0 / 3.0 ? f : 1.0 / 3.0); st[LM_NU] = 2.0;
+    st[LM_COST] = cnew;
+    if (fconv || sqrt(hn) <= xtol * sqrt(xn)) { st[LM_STATUS] = 1.0; return; }
+    if (lm_gradient_converged<NP>(st)) { st[LM_STATUS] = 1.0; return; }
   } else {
-    if (sqrt(hn) <= xtol * sqrt(xn)) { st[7] = 1.0; return; }
-    if (fabs(actred) <= ftol * cost && pred <= ftol * cost) { st[7] = 1.0; return; }
-    st[5] *= st[6]; st[6] *= 2;
+    if (sqrt(hn) <= xtol * sqrt(xn)) { st[LM_STATUS] = 1.0; return; }
+    if (fabs(actred) <= ftol * cost && pred <= ftol * cost) { st[LM_STATUS] = 1.0; return; }
+    st[LM_LAMBDA] *= st[LM_NU]; st[LM_NU] *= 2;
+    if (!(st[LM_LAMBDA] < 1e300)) { st[LM_STATUS] = 1.0; return; }   // the step has shrunk below resolution: stationary to rounding
   }
-  if (st[8] >= (double)maxfev) { st[7] = 2.0; return; }
+  if (st[LM_EVALS] >= (double)maxfev) { st[LM_STATUS] = 2.0; return; }
   lm_make_trial<NP>(st);
+}
+__device__ void lm_update_model(int model, const double* m, double* st) {
+  if (model == CIRCLE2) lm_update<3>(m, st, 1e-8 * 0.01, 500);
+  else if (model == SPHERE3) lm_update<4>(m, st, 1e-8 * 0.01, 500);
+  else if (model == USXW) lm_update<11>(m, st, 10e-16, 5000);
 }
 
 __global__ void lm_init_kernel(const double* __restrict__ alg_out, double* __restrict__ st) {
   if (threadIdx.x != 0) return;
-  for (int i = 0; i < 64; i++) st[i] = 0.0;
+  for (int i = 0; i < LM_SIZE; i++) st[i] = 0.0;
   const int np = (int)alg_out[0];
-  if (np == 0) { st[7] = 2.0; return; }
-  for (int j = 0; j < np; j++) st[j] = alg_out[1 + j];
+  if (np == 0) { st[LM_STATUS] = 2.0; return; }
+  for (int j = 0; j < np && j < kLmMaxP; j++) st[LM_X + j] = alg_out[1 + j];   // cross-wire: the first 11 of its 20 parameters
 }
 __global__ void lm_update_kernel(int model, const double* __restrict__ m, double* __restrict__ st) {
   if (threadIdx.x != 0) return;
-  if (model == CIRCLE2) lm_update<3>(m, st); else lm_update<4>(m, st);
+  lm_update_model(model, m, st);
+}
+// .cxx:305-327: entries 11..19 rebuilt from the optimised angles and scales
+__device__ void us_expand(const double* x, double* prm) {
+  for (int j = 0; j < 11; j++) prm[j] = x[j];
+  const double cz = cos(x[6]), sz = sin(x[6]), cy = cos(x[7]), sy = sin(x[7]), cx = cos(x[8]), sx = sin(x[8]);
+  prm[11] = x[9] * cz * cy; prm[12] = x[9] * sz * cy; prm[13] = -x[9] * sy;
+  prm[14] = x[10] * (cz * sy * sx - sz * cx); prm[15] = x[10] * (sz * sy * sx + cz * cx); prm[16] = x[10] * cy * sx;
+  prm[17] = cz * sy * cx + sz * sx; prm[18] = sz * sy * cx - cz * sx; prm[19] = cy * cx;
 }
 __global__ void lm_finish_kernel(int model, DataView dv, const double* __restrict__ st, double* __restrict__ out) {
   if (threadIdx.x != 0) return;
+  if (st[LM_STATUS] != 1.0) { out[0] = 0.0; return; }
+  if (model == USXW) {
+    double x[11];
+    for (int j = 0; j < 11; j++) x[j] = st[LM_X + j];
+    for (int j = 0; j < 3; j++) x[j] += dv.center[9 + j];   // t1 was estimated relative to the centre of the t2 components
+    out[0] = 20;
+    us_expand(x, out + 1);
+    return;
+  }
   const int dim = (model == CIRCLE2) ? 2 : 3;
-  if (st[7] != 1.0) { out[0] = 0.0; return; }
   out[0] = dim + 1;
-  for (int j = 0; j < dim; j++) out[1 + j] = st[j] + dv.center[j];
-  out[1 + dim] = st[dim];
+  for (int j = 0; j < dim; j++) out[1 + j] = st[LM_X + j] + dv.center[j];
+  out[1 + dim] = st[LM_X + dim];
 }
 void launch_lm_init(const double* alg_out_dev, double* state, cudaStream_t s) { lm_init_kernel<<<1, 32, 0, s>>>(alg_out_dev, state); }
 void launch_lm_update(int model, const double* moments, double* state, cudaStream_t s) { lm_update_kernel<<<1, 32, 0, s>>>(model, moments, state); }
 void launch_lm_finish(int model, const DataView& dv, const double* state, double* out_dev, cudaStream_t s) { lm_finish_kernel<<<1, 32, 0, s>>>(model, dv, state, out_dev); }
+int lm_status_offset() { return LM_STATUS; }
 
 // ---------------------------------------------------------------------------------------
 __global__ void expand_mask_kernel(const uint32_t* __restrict__ bits, uint32_t n, uint8_t* __restrict__ bytes) {
@@ -695,7 +843,7 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
   __shared__ double sh_part[8 * kMaxMoments];
   __shared__ double sh_mom[kMaxMoments];
   __shared__ double sh_prm[LSQR_MAX_PARAMS + 4];
-  __shared__ double sh_state[64];
+  __shared__ double sh_state[LM_SIZE];
   __shared__ unsigned long long sh_best;
   __shared__ unsigned long long sh_tries;
   __shared__ int sh_ok;
@@ -810,23 +958,23 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
   if constexpr (M == CIRCLE2 || M == SPHERE3) {
     if (ls_type == 1) {  // geometric: Levenberg-Marquardt from the algebraic fit
       if (threadIdx.x == 0) {
-        for (int i = 0; i < 64; i++) sh_state[i] = 0.0;
+        for (int i = 0; i < LM_SIZE; i++) sh_state[i] = 0.0;
         const int np = (int)sh_out[0];
-        if (np == 0) sh_state[7] = 2.0;
-        for (int j = 0; j < np; j++) sh_state[j] = sh_out[1 + j];
+        if (np == 0) sh_state[LM_STATUS] = 2.0;
+        for (int j = 0; j < np; j++) sh_state[LM_X + j] = sh_out[1 + j];
       }
       __syncthreads();
-      while (sh_state[7] == 0.0) {
+      while (sh_state[LM_STATUS] == 0.0) {
         double lmx[4];
-        const int o = (sh_state[9] != 0.0) ? 10 : 0;
+        const int o = (sh_state[LM_PHASE] != 0.0) ? LM_TRIAL : LM_X;
         for (int j = 0; j < 4; j++) lmx[j] = sh_state[o + j];
         block_moments<M>(pts, n, ldp, hq, cfg, lmx, true, 1, nullptr, sh_part, sh_mom);
-        if (threadIdx.x == 0) { if (M == CIRCLE2) lm_update<3>(sh_mom, sh_state); else lm_update<4>(sh_mom, sh_state); }
+        if (threadIdx.x == 0) lm_update_model(M, sh_mom, sh_state);
         __syncthreads();
       }
       if (threadIdx.x == 0) {
-        if (sh_state[7] != 1.0) sh_out[0] = 0.0;
-        else for (int j = 0; j < P; j++) sh_out[1 + j] = sh_state[j];
+        if (sh_state[LM_STATUS] != 1.0) sh_out[0] = 0.0;
+        else for (int j = 0; j < P; j++) sh_out[1 + j] = sh_state[LM_X + j];
       }
       __syncthreads();
     }

@@ -68,6 +68,7 @@ __host__ __device__ inline bool centred_component(int model, int d) {
   switch (model) {
     case RAY: return d < 3;
     case PIVOT: return d >= 9;
+    case USXW: return d >= 9 && d < 12;       // t2; rotation entries and pixel coordinates stay
     case DENSE5: case DENSE6: return false;   // rows of a linear system: a shift would change the solution
     default: return true;
   }
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(128) solve_kernel(SolveArgs a, const double* _
     case PIVOT: { CALL(PIVOT); break; }       \
     case DENSE5: { CALL(DENSE5); break; }     \
     case DENSE6: { CALL(DENSE6); break; }     \
+    case USXW: { CALL(USXW); break; }         \
     default: break;                           \
   }
 

@@ -14,7 +14,7 @@
 
 namespace lsqr {
 
-enum : int { PLANE3 = 0, LINE2D = 1, LINE2 = 2, LINE3 = 3, CIRCLE2 = 4, SPHERE3 = 5, ABSOR = 6, RAY = 7, PIVOT = 8, DENSE5 = 9, DENSE6 = 10, NUM_MODELS = 11 };
+enum : int { PLANE3 = 0, LINE2D = 1, LINE2 = 2, LINE3 = 3, CIRCLE2 = 4, SPHERE3 = 5, ABSOR = 6, RAY = 7, PIVOT = 8, DENSE5 = 9, DENSE6 = 10, USXW = 11, NUM_MODELS = 12 };
 
 // dim = doubles per datum, P = parameters, K = minimal subset, HQ = doubles of a prepared
 // fp64 hypothesis, Q32 = floats of a hoisted fp32 hypothesis.
@@ -31,6 +31,9 @@ template <> struct Model<PIVOT>   { static constexpr int D = 12, P = 6, K = 3, H
 // DenseLinearEquationSystemParametersEstimator<double, n>: datum = AugmentedRow (n coefficients, right-hand side)
 template <> struct Model<DENSE5>  { static constexpr int D = 6,  P = 5, K = 5, HQ = 5,  Q32 = 6;  };
 template <> struct Model<DENSE6>  { static constexpr int D = 7,  P = 6, K = 6, HQ = 6,  Q32 = 7;  };
+// SingleUnknownPointTargetUSCalibrationParametersEstimator (cross-wire phantom): datum = [R2 (9), t2 (3), u, v],
+// parameters [t1, t3, omega_z, omega_y, omega_x, m_x, m_y, m_x R3(:,1), m_y R3(:,2), R3(:,3)]
+template <> struct Model<USXW>    { static constexpr int D = 14, P = 20, K = 4, HQ = 12, Q32 = 12; };
 
 struct ModelInfo { int D, P, K, HQ, Q32; };
 __host__ __device__ inline ModelInfo model_info(int m) {
@@ -46,6 +49,7 @@ __host__ __device__ inline ModelInfo model_info(int m) {
     case PIVOT:   return {12, 6, 3, 6, 6};
     case DENSE5:  return {6, 5, 5, 5, 6};
     case DENSE6:  return {7, 6, 6, 6, 7};
+    case USXW:    return {14, 20, 4, 12, 12};
   }
   return {0, 0, 0, 0, 0};
 }
@@ -338,6 +342,72 @@ template <int N> __device__ inline bool estimate_dense(const double* d, double* 
 template <> __device__ inline bool estimate<DENSE5>(const double* d, const EstCfg&, double* prm) { return estimate_dense<5>(d, prm); }
 template <> __device__ inline bool estimate<DENSE6>(const double* d, const EstCfg&, double* prm) { return estimate_dense<6>(d, prm); }
 
+// R <- U V^T of its SVD (closest rotation in the Frobenius norm, SinglePointTargetUSCalibrationParametersEstimator
+// .cxx:226-229), as the orthogonal polar factor R (R^T R)^(-1/2).
+__device__ inline void closest_rotation(double* R) {
+  double S[9], V[9], ev[3], W[9], out[9];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double s = 0; for (int k = 0; k < 3; k++) s += R[k * 3 + i] * R[k * 3 + j]; S[i * 3 + j] = s; }
+  sym_eig<3>(S, V, ev);
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double s = 0; for (int k = 0; k < 3; k++) s += V[i * 3 + k] * V[j * 3 + k] / sqrt(ev[k]); W[i * 3 + j] = s; }
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double s = 0; for (int k = 0; k < 3; k++) s += R[i * 3 + k] * W[k * 3 + j]; out[i * 3 + j] = s; }
+  for (int i = 0; i < 9; i++) R[i] = out[i];
+}
+
+// SinglePointTargetUSCalibrationParametersEstimator.cxx:204-268: the solution x[12] of the linear system ->
+// scale factors, re-orthonormalised rotation, Euler angles, the 20 parameters.
+__device__ inline bool us_post(const double* x, double* prm) {
+  const double smallAngle = 0.008726535498373935, halfPI = 1.5707963267948966192313216916398;
+  double r1[3], r2[3], r3[3], R3[9];
+  for (int i = 0; i < 3; i++) { r1[i] = x[i]; r2[i] = x[3 + i]; }
+  const double m_x = sqrt(r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2]);
+  double inv = 1.0 / m_x; for (int i = 0; i < 3; i++) r1[i] = inv * r1[i];
+  const double m_y = sqrt(r2[0] * r2[0] + r2[1] * r2[1] + r2[2] * r2[2]);
+  inv = 1.0 / m_y; for (int i = 0; i < 3; i++) r2[i] = inv * r2[i];
+  r3[0] = r1[1] * r2[2] - r1[2] * r2[1];
+  r3[1] = r1[2] * r2[0] - r1[0] * r2[2];
+  r3[2] = r1[0] * r2[1] - r1[1] * r2[0];
+  for (int i = 0; i < 3; i++) { R3[i * 3 + 0] = r1[i]; R3[i * 3 + 1] = r2[i]; R3[i * 3 + 2] = r3[i]; }
+  closest_rotation(R3);
+  double omega_z, omega_x;
+  const double omega_y = atan2(-R3[6], sqrt(R3[0] * R3[0] + R3[3] * R3[3]));
+  if (fabs(omega_y - halfPI) > smallAngle && fabs(omega_y + halfPI) > smallAngle) {
+    const double cy = cos(omega_y);
+    omega_z = atan2(R3[3] / cy, R3[0] / cy);
+    omega_x = atan2(R3[7] / cy, R3[8] / cy);
+  } else {
+    omega_z = 0;
+    omega_x = atan2(R3[1], R3[4]);
+  }
+  prm[0] = x[9]; prm[1] = x[10]; prm[2] = x[11];
+  prm[3] = x[6]; prm[4] = x[7]; prm[5] = x[8];
+  prm[6] = omega_z; prm[7] = omega_y; prm[8] = omega_x; prm[9] = m_x; prm[10] = m_y;
+  prm[11] = m_x * R3[0]; prm[12] = m_x * R3[3]; prm[13] = m_x * R3[6];
+  prm[14] = m_y * R3[1]; prm[15] = m_y * R3[4]; prm[16] = m_y * R3[7];
+  prm[17] = R3[2]; prm[18] = R3[5]; prm[19] = R3[8];
+  bool ok = true;
+  for (int i = 0; i < 20; i++) ok = ok && (prm[i] == prm[i]);
+  return ok;
+}
+
+// SinglePointTargetUSCalibrationParametersEstimator.cxx:120-270 with four data: rows [u R2, v R2, R2, -I] x = -t2,
+// pseudo-inverse with singular values <= FLT_EPSILON zeroed, rank < 12 fails.
+template <> __device__ inline bool estimate<USXW>(const double* d, const EstCfg&, double* prm) {
+  double A[144], b[12], x[12];
+  for (int i = 0; i < 144; i++) A[i] = 0.0;
+  for (int i = 0; i < 4; i++) {
+    const double* f = d + 14 * i;
+    const double ui = f[12], vi = f[13];
+    for (int r = 0; r < 3; r++) {
+      double* row = A + (3 * i + r) * 12;
+      for (int c = 0; c < 3; c++) { row[c] = f[3 * r + c] * ui; row[3 + c] = f[3 * r + c] * vi; row[6 + c] = f[3 * r + c]; }
+      row[9 + r] = -1.0;
+      b[3 * i + r] = -f[9 + r];
+    }
+  }
+  if (pinv_solve<12, 12>(A, b, 1.192092896e-07, x) < 12) return false;
+  return us_post(x, prm);
+}
+
 // ---------------------------------------------------------------------------------------
 // agree(): prepare once per hypothesis, test once per (hypothesis, datum)
 // ---------------------------------------------------------------------------------------
@@ -348,6 +418,14 @@ template <int M> __device__ __forceinline__ void prepare(const double* prm, doub
 template <> __device__ __forceinline__ void prepare<ABSOR>(const double* prm, double* hq) {
   quat_to_rot(prm[0], prm[1], prm[2], prm[3], hq);
   hq[9] = prm[4]; hq[10] = prm[5]; hq[11] = prm[6];
+}
+
+// cross-wire: the twelve entries agree() reads -- m_x R3(:,1), m_y R3(:,2), t3, t1
+template <> __device__ __forceinline__ void prepare<USXW>(const double* prm, double* hq) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) hq[i] = prm[11 + i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) { hq[6 + i] = prm[3 + i]; hq[9 + i] = prm[i]; }
 }
 
 template <int M> __device__ __forceinline__ bool agree(const double* hq, const double* x, const EstCfg& cfg);
@@ -411,6 +489,24 @@ template <> __device__ __forceinline__ bool agree<PIVOT>(const double* h, const 
   double s = 0;
   s += rx * rx; s += ry * ry; s += rz * rz;
   return sqrt(s) < cfg.delta;
+}
+
+// SinglePointTargetUSCalibrationParametersEstimator.cxx:71-107: qInT = (T2*T3)*q with VNL's left-to-right
+// accumulation; products with the constant 0 / 1 entries of the homogeneous matrices are exact and left out.
+template <> __device__ __forceinline__ bool agree<USXW>(const double* h, const double* x, const EstCfg& cfg) {
+  const double u = x[12], v = x[13];
+  double s = 0;
+  double err[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double a = x[3 * i], b = x[3 * i + 1], c = x[3 * i + 2];
+    const double M0 = a * h[0] + b * h[1] + c * h[2];
+    const double M1 = a * h[3] + b * h[4] + c * h[5];
+    const double M3 = a * h[6] + b * h[7] + c * h[8] + x[9 + i];
+    err[i] = (M0 * u + M1 * v + M3) - h[9 + i];
+  }
+  s = err[0] * err[0] + err[1] * err[1] + err[2] * err[2];
+  return s < cfg.delta2;
 }
 
 // DenseLinearEquationSystemParametersEstimator.hxx:111-119

@@ -159,6 +159,28 @@ class DenseLinearEquationSystemParametersEstimator(ParametersEstimator):
         super().__init__(n, delta)
 
 
+class SingleUnknownPointTargetUSCalibrationParametersEstimator(ParametersEstimator):
+    """SingleUnknownPointTargetUSCalibrationParametersEstimator (cross-wire phantom ultrasound calibration,
+    SinglePointTargetUSCalibrationParametersEstimator.cxx:10-329); datum = (Frame T2, Point2D q) as 14 doubles
+    [R2 row-major, t2, u, v]; 20 parameters [t1, t3, omega_z, omega_y, omega_x, m_x, m_y, m_x R3(:,1), m_y R3(:,2), R3(:,3)]."""
+    _model = "usxw"
+    ANALYTIC, ITERATIVE = 0, 1
+
+    def __init__(self, delta, lsType=1):
+        super().__init__(4, delta, ls_type=lsType)
+
+    def setLeastSquaresType(self, lsType):
+        self._ls_type = int(lsType)
+        self._reconfigure()
+
+    def estimate(self, data, parameters):
+        parameters.clear()
+        d = np.asarray(data, dtype=np.float64).reshape(-1, 14)
+        if d.shape[0] != self.minForEstimate:      # exactly four (.cxx:21-22)
+            return
+        parameters.extend(self.engine().estimate(d).tolist())
+
+
 class RANSAC:
     """RANSAC<T,S> (RANSAC.h:47-151): two static compute() overloads."""
 

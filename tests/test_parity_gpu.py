@@ -183,6 +183,9 @@ def _fp32_band(name, data, prm, delta):
     """Half-width (in residual units) of the band around the threshold inside which an fp32
     decision may legitimately differ: 1e-6 relative to the magnitude of the terms that are
     summed to form the residual (SURVEY.md / DESIGN.md 'fp32 fast mode')."""
+    if name == "usxw":                 # the summed terms: pixel * scaled rotation column, t3, t2, t1
+        scale = np.abs(data[:, 12:]).max() * np.abs(prm[11:17]).max() * 2 + np.abs(prm[:6]).max() * 2 + np.abs(data[:, 9:12]).max() + 1.0
+        return 4e-6 * scale
     if name in ("dense5", "dense6"):   # the summed terms are the products a_i x_i and b
         nc = data.shape[1] - 1
         scale = np.abs(data[:, :nc]).max() * np.abs(prm).max() * nc + np.abs(data[:, nc]).max() + 1.0
@@ -221,6 +224,10 @@ def _residual64(name, prm, data, delta):
     if name in ("dense5", "dense6"):
         nc = data.shape[1] - 1
         return np.abs(data[:, :nc] @ p[:nc] - data[:, nc]), delta
+    if name == "usxw":
+        R2 = data[:, :9].reshape(-1, 3, 3)
+        w = np.outer(data[:, 12], p[11:14]) + np.outer(data[:, 13], p[14:17]) + p[3:6]
+        return np.linalg.norm(np.einsum("nij,nj->ni", R2, w) + data[:, 9:12] - p[0:3], axis=1), delta
     raise AssertionError(name)
 
 
