@@ -15,6 +15,7 @@
 #include "lsqrRecipes/LineParametersEstimator.h"
 #include "lsqrRecipes/PivotCalibrationParametersEstimator.h"
 #include "lsqrRecipes/DenseLinearEquationSystemParametersEstimator.h"
+#include "lsqrRecipes/SinglePointTargetUSCalibrationParametersEstimator.h"
 #include "lsqrRecipes/PlaneParametersEstimator.h"
 #include "lsqrRecipes/RANSAC.h"
 #include "lsqrRecipes/RayIntersectionParametersEstimator.h"
@@ -235,6 +236,52 @@ static void denseCase() {
   }
 }
 
+// testing/SinglePointTargetUSCalibrationParametersEstimatorTest.cxx:556-650: a cross-wire phantom seen in tracked images
+static void crossWireCase() {
+  std::printf("SingleUnknownPointTargetUSCalibrationParametersEstimator\n");
+  typedef SingleUnknownPointTargetUSCalibrationParametersEstimator Est;
+  const double mx = 0.143, my = 0.139, oz = uni(0.2, 1.3), oy = uni(0.2, 1.3), ox = uni(0.2, 1.3);
+  const double cz = std::cos(oz), sz = std::sin(oz), cy = std::cos(oy), sy = std::sin(oy), cx = std::cos(ox), sx = std::sin(ox);
+  const double R3[3][3] = {{cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx}, {sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx}, {-sy, cy * sx, cy * cx}};
+  const double t3[3] = {uni(-100, 100), uni(-100, 100), uni(-100, 100)}, t1[3] = {uni(-100, 100), uni(-100, 100), uni(-100, 100)};
+  std::vector<Est::DataType> data;
+  for (int i = 0; i < 3000; i++) {
+    const double u = uni(0, 640), v = uni(0, 480);
+    double p[3];
+    for (int r = 0; r < 3; r++) p[r] = R3[r][0] * mx * u + R3[r][1] * my * v + t3[r];
+    double q[4] = {gauss(1), gauss(1), gauss(1), gauss(1)};
+    Frame f(0, 0, 0, q[0], q[1], q[2], q[3], true);
+    Point3D pp, rp;
+    for (int j = 0; j < 3; j++) pp[j] = p[j];
+    f.apply(pp, rp);   // R2 p
+    double t2[3];
+    for (int j = 0; j < 3; j++) t2[j] = t1[j] - rp[j];
+    f.setTranslation(t2);
+    Est::DataType d;
+    d.T2 = f;
+    d.q[0] = u + gauss(1.0); d.q[1] = v + gauss(1.0);
+    if (i % 10 >= 7) { d.q[0] = uni(0, 640); d.q[1] = uni(0, 480); }   // 30 % outliers
+    data.push_back(d);
+  }
+  Est est(1.0);
+  std::vector<double> prm;
+  const double frac = RANSAC<Est::DataType, double>::compute(prm, &est, data, 0.999);
+  CHECK(prm.size() == 20 && frac > 0.6, "cross-wire calibration RANSAC (iterative refine)");
+  if (prm.size() == 20) {
+    double e = 0;
+    for (int j = 0; j < 3; j++) e += std::fabs(prm[j] - t1[j]) + std::fabs(prm[3 + j] - t3[j]);
+    std::printf("  fraction %.4f  |t1,t3 error|_1 %.4g  m_x %.5f m_y %.5f\n", frac, e, prm[9], prm[10]);
+    CHECK(e < 0.5 && std::fabs(prm[9] - mx) < 1e-3 && std::fabs(prm[10] - my) < 1e-3, "calibration recovered");
+    CHECK(est.agree(prm, data[0]), "agree() on an inlier image");
+  }
+  est.setLeastSquaresType(Est::ANALYTIC);
+  std::vector<Est::DataType> four(data.begin(), data.begin() + 4), five(data.begin(), data.begin() + 5);
+  std::vector<double> p4, p5(1, 1.0);
+  est.estimate(four, p4);
+  est.estimate(five, p5);
+  CHECK(p4.size() == 20 && p5.empty(), "estimate() wants exactly four images");
+}
+
 // A user-defined estimator has no GPU path: same failure convention as a degenerate data set.
 class UserEstimator : public ParametersEstimator<Point2D, double> {
  public:
@@ -255,6 +302,7 @@ int main() {
   rayCase();
   pivotCase();
   denseCase();
+  crossWireCase();
   std::printf("user-defined estimator\n");
   UserEstimator user;
   std::vector<Point2D> pts(10);

@@ -95,6 +95,9 @@ class ParametersEstimator {
 
   // GPU path hook (see the header comment).  false = this estimator has no GPU path.
   virtual bool b200Describe(B200EstimatorDesc& /*desc*/) const { return false; }
+  // Data types whose leading doubles are NOT the engine's datum (members separated by padding, e.g. the
+  // ultrasound-calibration records {Frame T2; Point2D q;}) write the packed datum to `out` and return true.
+  virtual bool b200PackDatum(const T& /*datum*/, double* /*out*/) const { return false; }
 
  protected:
   unsigned int minForEstimate;
@@ -138,7 +141,9 @@ class B200Estimator : public ParametersEstimator<T, double> {
     lsqr_model_info(d.model, &dim, &np, &k);
     parameters.at(np - 1);  // the reference indexes past the end of a short vector; fail loudly instead
     uint8_t out = 0;
-    if (!b200::check(ctx, lsqr_agree(ctx, parameters.data(), reinterpret_cast<const double*>(&data), 1, &out))) return false;
+    double packed[32];
+    const double* datum = this->b200PackDatum(data, packed) ? packed : reinterpret_cast<const double*>(&data);
+    if (!b200::check(ctx, lsqr_agree(ctx, parameters.data(), datum, 1, &out))) return false;
     return out != 0;
   }
 
@@ -155,6 +160,7 @@ class B200Estimator : public ParametersEstimator<T, double> {
     int dim = 0;
     lsqr_model_info(d.model, &dim, NULL, NULL);
     b200::gather(data, dim, packed);
+    for (size_t i = 0; i < data.size(); i++) if (!this->b200PackDatum(*data[i], &packed[i * dim])) break;   // custom layouts overwrite the raw copy
     return packed.data();
   }
   void runEstimate(const double* packed, size_t n, std::vector<double>& parameters) const {

@@ -63,7 +63,15 @@ class RANSAC {
     }
     lsqr_ctx* ctx = b200::configured(d);
     if (!ctx) return 0;
-    if (!b200::check(ctx, lsqr_upload(ctx, data.data(), data.size(), sizeof(T)))) return 0;
+    double probe[32];
+    if (!data.empty() && paramEstimator->b200PackDatum(data[0], probe)) {
+      // record layout differs from the engine's datum: pack on the host, then upload packed doubles
+      int dim = 0;
+      lsqr_model_info(d.model, &dim, NULL, NULL);
+      std::vector<double> packed(data.size() * static_cast<size_t>(dim));
+      for (size_t i = 0; i < data.size(); i++) paramEstimator->b200PackDatum(data[i], &packed[i * dim]);
+      if (!b200::check(ctx, lsqr_upload(ctx, packed.data(), data.size(), sizeof(double) * dim))) return 0;
+    } else if (!b200::check(ctx, lsqr_upload(ctx, data.data(), data.size(), sizeof(T)))) return 0;
     std::vector<uint8_t> mask(consensusSet ? data.size() : 0);
     lsqr_compute_result r;
     const int rc = exhaustive ? lsqr_ransac_exhaustive(ctx, LSQR_FP64, consensusSet ? mask.data() : NULL, &r)

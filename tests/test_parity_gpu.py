@@ -146,6 +146,32 @@ def test_weighted_horn_vs_oracle(port):
     assert same_up_to_sign(prm, port.weighted_absor(data, w), SIGN_IDX["absor"], REFINE_TOL)
 
 
+def test_crosswire_operator_interface(port):
+    """SingleUnknownPointTargetUSCalibrationParametersEstimator through the Python mirror of the reference API:
+    estimate() wants exactly four data (.cxx:21-22), ANALYTIC / ITERATIVE least squares, RANSAC::compute."""
+    from lsqrrecipes_b200 import RANSAC, SingleUnknownPointTargetUSCalibrationParametersEstimator as Est
+    data, true = synth.crosswire(4000, seed=12)
+    m = MODELS["usxw"]
+    est = Est(1.0)
+    p4, p5 = [], [1.0]
+    est.estimate(data[:4], p4)
+    est.estimate(data[:5], p5)
+    assert len(p4) == 20 and p5 == []
+    assert np.allclose(p4, port.estimate(m, 1.0, data[:4]), rtol=1e-6, atol=1e-6)
+    cnt, flags = port.agree(m, 1.0, true, data)
+    inl = data[flags.astype(bool)]
+    for ls_type in (Est.ANALYTIC, Est.ITERATIVE):
+        est.setLeastSquaresType(ls_type)
+        prm = []
+        est.leastSquaresEstimate(inl, prm)
+        assert same_up_to_sign(prm, port.least_squares(m, 1.0, inl, ls_type), [], REFINE_TOL)
+    assert est.agree(list(true), data[flags.astype(bool)][0]) and not est.agree(list(true), data[~flags.astype(bool)][0])
+    prm, cs = [], []
+    frac = RANSAC.compute(prm, est, data, 0.999, cs)
+    assert frac > 0.6 and len(prm) == 20 and sum(cs) == round(frac * len(data))
+    assert np.abs(np.array(prm[:6]) - true[:6]).max() < 0.5 and abs(prm[9] - 0.143) < 1e-3 and abs(prm[10] - 0.139) < 1e-3
+
+
 def test_circle_agree_literals():
     """testing/SphereParametersEstimatorTest.cxx:280-296"""
     eng = Engine("circle2", 0.5)

@@ -125,6 +125,11 @@ def main():
     scoring("absor", 1_000_000, 100_000 if q else 1_000_000, FP32, "configs[3] absolute orientation scoring", cpu_hyps=64)
     compute_e2e("absor", 1_000_000, 1, "configs[3] absolute orientation compute()", cpu_n=200_000)
     compute_e2e("plane3", N, 1, "configs[1] plane compute()", cpu_n=200_000)
+    # next rows of SURVEY.md 8f: dense linear systems and the cross-wire ultrasound calibration (LM over 11 parameters)
+    scoring("dense6", 1_000_000, 100_000 if q else 1_000_000, FP32, "8f-2 dense linear system (n = 6) scoring", cpu_hyps=32)
+    compute_e2e("dense6", 1_000_000, 1, "8f-2 dense linear system (n = 6) compute()", cpu_n=200_000)
+    scoring("usxw", 200_000, 100_000 if q else 1_000_000, FP32, "8f-3 cross-wire US calibration scoring", cpu_hyps=32)
+    compute_e2e("usxw", 200_000, 1, "8f-3 cross-wire US calibration compute() + LM refine (11 parameters)", cpu_n=20_000)
     nprob = 4096 if q else 65536
     batched("line2d", nprob, 256, "configs[4] batched 2D line", cpu_problems=256)
     batched("plane3", nprob, 256, "configs[4] batched 3D plane", cpu_problems=256)
