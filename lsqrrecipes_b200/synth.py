@@ -191,6 +191,37 @@ def crosswire(n, outlier_frac=0.3, seed=SEED, sigma=1.0):
     return out, prm
 
 
+def calibrated_pointer(n, outlier_frac=0.3, seed=SEED, sigma=1.0):
+    """Calibrated-pointer US calibration data (testing/SinglePointTargetUSCalibrationParametersEstimatorTest.cxx,
+    generateCalibratedPointerData): the pointer tip p_i (tracker coordinates) is seen at pixel (u, v) of image i.
+    Datum = [R2 (9), t2 (3), u, v, p (3)] with R2 (T3 (u, v, 0, 1)) + t2 = p.  Returns the data and the 17 reference
+    parameters [t3, omega_z, omega_y, omega_x, m_x, m_y, m_x R3(:,1), m_y R3(:,2), R3(:,3)]."""
+    rng = np.random.default_rng(seed)
+    m_x, m_y = 0.143, 0.139
+    ox, oy, oz = rng.uniform(0.2, 1.3, 3)
+    R3 = euler_zyx(oz, oy, ox)
+    t3 = rng.uniform(-100, 100, 3)
+    out = np.zeros((n, 17))
+    n_out = int(round(n * outlier_frac))
+    bad = np.zeros(n, dtype=bool)
+    bad[rng.permutation(n)[:n_out]] = True
+    for i in range(n):
+        u, v = rng.uniform(0, 640), rng.uniform(0, 480)
+        pus = R3 @ np.array([m_x * u, m_y * v, 0.0]) + t3
+        R2 = quat_to_matrix(*_unit(rng.normal(0, 1, 4)))
+        t2 = rng.uniform(-300, 300, 3)
+        p = R2 @ pus + t2
+        un, vn = u + rng.normal(0, sigma), v + rng.normal(0, sigma)
+        if bad[i]:
+            un, vn = rng.uniform(0, 640), rng.uniform(0, 480)
+        out[i, :9] = R2.ravel()
+        out[i, 9:12] = t2
+        out[i, 12:14] = (un, vn)
+        out[i, 14:] = p
+    prm = np.concatenate([t3, [oz, oy, ox, m_x, m_y], m_x * R3[:, 0], m_y * R3[:, 1], R3[:, 2]])
+    return out, prm
+
+
 def frames_from_quat_file(path):
     """Rows 'x y z qx qy qz qs' (testing/Data/pivotCalibrationData.txt) -> packed frames,
     following testing/PivotCalibrationParametersEstimatorTest.cxx:29-33."""
@@ -215,9 +246,10 @@ GENERATORS = {
     "dense5": lambda n, seed=SEED: dense_rows(n, 5, seed=seed),
     "dense6": lambda n, seed=SEED: dense_rows(n, 6, seed=seed),
     "usxw": lambda n, seed=SEED: crosswire(n, seed=seed),
+    "uscp": lambda n, seed=SEED: calibrated_pointer(n, seed=seed),
 }
 DELTAS = {"plane3": 0.5, "line2d": 0.5, "line2": 0.5, "line3": 0.5, "circle2": 0.5, "sphere3": 0.5, "absor": 2.0, "ray": 1.0, "pivot": 1.0,
-          "dense5": 0.2, "dense6": 0.2, "usxw": 1.0}
+          "dense5": 0.2, "dense6": 0.2, "usxw": 1.0, "uscp": 1.0}
 
 
 def random_subsets(n, k, H, seed=SEED):

@@ -21,7 +21,7 @@
 #include <omp.h>
 #endif
 
-enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10, M_USXW = 11 };
+enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10, M_USXW = 11, M_USCP = 12 };
 
 /* common/Epsilon.h:19 */
 static const double EPS = 2.220446049250313e-016;
@@ -32,8 +32,8 @@ static const double FRAME_SMALL_ANGLE = 0.008726535498373935;
 static const double FRAME_HALF_PI = 3.14159265358979323846 / 2.0;
 
 int orc_model_info(int model, int* D, int* P, int* k) {
-  static const int tab[12][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}, {6, 5, 5}, {7, 6, 6}, {14, 20, 4}};
-  if (model < 0 || model > 11) return -1;
+  static const int tab[13][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}, {6, 5, 5}, {7, 6, 6}, {14, 20, 4}, {17, 17, 3}};
+  if (model < 0 || model > 12) return -1;
   *D = tab[model][0]; *P = tab[model][1]; *k = tab[model][2];
   return 0;
 }
@@ -393,8 +393,10 @@ static void us_closest_rotation(double R[9]) {
   memcpy(R, out, sizeof(out));
 }
 
-/* .cxx:204-268: scale factors, re-orthonormalised rotation, Euler angles, the 20 output parameters */
-static int us_post(const double x[12], double prm[20]) {
+/* .cxx:204-250 (and :862-900): scale factors, re-orthonormalised rotation and Euler angles from the first six
+ * unknowns [m_x R3(:,1), m_y R3(:,2)] of the linear solution; out = [omega_z, omega_y, omega_x, m_x, m_y, m_x R3(:,1),
+ * m_y R3(:,2), R3(:,3)] (14 values) */
+static void us_rotation_part(const double x[6], double out[14]) {
   const double smallAngle = 0.008726535498373935, halfPI = 1.5707963267948966192313216916398;
   double r1[3], r2[3], r3[3], R3[9], m_x, m_y, inv, omega_z, omega_y, omega_x;
   int i;
@@ -417,12 +419,18 @@ static int us_post(const double x[12], double prm[20]) {
     omega_z = 0;
     omega_x = atan2(R3[1], R3[4]);
   }
+  out[0] = omega_z; out[1] = omega_y; out[2] = omega_x; out[3] = m_x; out[4] = m_y;
+  out[5] = m_x * R3[0]; out[6] = m_x * R3[3]; out[7] = m_x * R3[6];
+  out[8] = m_y * R3[1]; out[9] = m_y * R3[4]; out[10] = m_y * R3[7];
+  out[11] = R3[2]; out[12] = R3[5]; out[13] = R3[8];
+}
+
+/* cross-wire: x = [m_x R3(:,1), m_y R3(:,2), t3, t1] -> the 20 parameters (.cxx:251-268) */
+static int us_post(const double x[12], double prm[20]) {
+  int i;
   prm[0] = x[9]; prm[1] = x[10]; prm[2] = x[11];
   prm[3] = x[6]; prm[4] = x[7]; prm[5] = x[8];
-  prm[6] = omega_z; prm[7] = omega_y; prm[8] = omega_x; prm[9] = m_x; prm[10] = m_y;
-  prm[11] = m_x * R3[0]; prm[12] = m_x * R3[3]; prm[13] = m_x * R3[6];
-  prm[14] = m_y * R3[1]; prm[15] = m_y * R3[4]; prm[16] = m_y * R3[7];
-  prm[17] = R3[2]; prm[18] = R3[5]; prm[19] = R3[8];
+  us_rotation_part(x, prm + 6);
   for (i = 0; i < 20; i++) if (!(prm[i] == prm[i])) return 0;
   return 20;
 }
@@ -571,6 +579,138 @@ static int usxw_agree(const double* prm, const double* f, double delta) {
   return s < delta * delta;
 }
 
+/* ------------------------------------------------------------------------------------ */
+/* Calibrated-pointer ultrasound calibration                                            */
+/* SinglePointTargetUSCalibrationParametersEstimator.cxx:663-985                        */
+/* datum = [R2 (9), t2 (3), u, v, p (3)]; parameters (17) =                             */
+/* [t3, omega_z, omega_y, omega_x, m_x, m_y, m_x R3(:,1), m_y R3(:,2), R3(:,3)]         */
+/* ------------------------------------------------------------------------------------ */
+
+/* analyticLeastSquaresEstimate, .cxx:789-920: rows [u R2, v R2, R2] x = p - t2, singular values <= FLT_EPSILON
+ * zeroed, rank < 9 -> no solution */
+static int uscp_analytic(const double* d, size_t n, double* prm) {
+  size_t i; int r, c, rank;
+  double x[9];
+  double* A = (double*)calloc(3 * n * 9, sizeof(double));
+  double* b = (double*)malloc(3 * n * sizeof(double));
+  for (i = 0; i < n; i++) {
+    const double* f = d + 17 * i;
+    const double ui = f[12], vi = f[13];
+    for (r = 0; r < 3; r++) {
+      double* row = A + (3 * i + r) * 9;
+      for (c = 0; c < 3; c++) { row[c] = f[3 * r + c] * ui; row[3 + c] = f[3 * r + c] * vi; row[6 + c] = f[3 * r + c]; }
+      b[3 * i + r] = f[14 + r] - f[9 + r];
+    }
+  }
+  rank = pinv_solve((int)(3 * n), 9, A, b, 1.192092896e-07, x);
+  free(A); free(b);
+  if (rank < 9) return 0;
+  prm[0] = x[6]; prm[1] = x[7]; prm[2] = x[8];
+  us_rotation_part(x, prm + 3);
+  for (r = 0; r < 17; r++) if (!(prm[r] == prm[r])) return 0;
+  return 17;
+}
+
+/* e = R2 (u m_x c1 + v m_y c2 + t3) + t2 - p at x[8] = [t3, omega_z, omega_y, omega_x, m_x, m_y] and its 3 x 8
+ * Jacobian: the cross-wire residual with t1 replaced by the measured p and no unknown for it */
+static void uscp_residual(const double* f, const double* x, double e[3], double* J) {
+  double xx[11], ee[3], JJ[33];
+  int r, p;
+  xx[0] = f[14]; xx[1] = f[15]; xx[2] = f[16];
+  for (p = 0; p < 8; p++) xx[3 + p] = x[p];
+  us_residual(f, xx, ee, J ? JJ : NULL);
+  for (r = 0; r < 3; r++) { e[r] = ee[r]; if (J) for (p = 0; p < 8; p++) J[r * 8 + p] = JJ[r * 11 + 3 + p]; }
+}
+
+static double uscp_cost(const double* d, size_t n, const double* x, double* JtJ, double* Jtr) {
+  size_t i; int a, b2, r; double cost = 0;
+  if (JtJ) { memset(JtJ, 0, sizeof(double) * 64); memset(Jtr, 0, sizeof(double) * 8); }
+  for (i = 0; i < n; i++) {
+    double e[3], J[24];
+    uscp_residual(d + 17 * i, x, e, JtJ ? J : NULL);
+    cost += e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+    if (JtJ) for (r = 0; r < 3; r++) for (a = 0; a < 8; a++) { Jtr[a] += J[r * 8 + a] * e[r]; for (b2 = a; b2 < 8; b2++) JtJ[a * 8 + b2] += J[r * 8 + a] * J[r * 8 + b2]; }
+  }
+  if (JtJ) for (a = 0; a < 8; a++) for (b2 = 0; b2 < a; b2++) JtJ[a * 8 + b2] = JtJ[b2 * 8 + a];
+  return cost;
+}
+
+/* iterativeLeastSquaresEstimate, .cxx:922-985.  The reference stops MINPACK at tolerances 1e-7, i.e. somewhere within
+ * ~1e-4 relative of the minimiser of sum |e_i|^2 depending on the minimiser's internals (the stand-in of the VNL shim
+ * returns the analytic start).  This restatement iterates to the minimiser itself (1e-15), which is what the engine is
+ * compared with; against the reference the test tolerance is 1e-3 and the cost must not be larger. */
+static int uscp_iterative(const double* d, size_t n, const double* init, double* prm) {
+  const double xtol = 10e-16, gtol = 10e-16, ftol = 10e-16;
+  const int maxfev = 5000, p = 8;
+  int a, evals = 1, ok = 0;
+  double x[8], xn[8], A[64], g[8], M[64], h[8], dsc[8], cost, lambda = -1, nu = 2;
+  for (a = 0; a < p; a++) x[a] = init[a];
+  cost = uscp_cost(d, n, x, NULL, NULL);
+  while (evals < maxfev && !ok) {
+    double gmax = 0, fnorm = sqrt(cost);
+    int accepted = 0;
+    uscp_cost(d, n, x, A, g);
+    for (a = 0; a < p; a++) { double cn = sqrt(A[a * p + a]); if (cn > 0 && fnorm > 0) { double v = fabs(g[a]) / (cn * fnorm); if (v > gmax) gmax = v; } }
+    if (gmax <= gtol || cost == 0.0) { ok = 1; break; }
+    { double dmax = 0; for (a = 0; a < p; a++) if (A[a * p + a] > dmax) dmax = A[a * p + a]; for (a = 0; a < p; a++) dsc[a] = A[a * p + a] > 1e-30 * dmax + 1e-300 ? A[a * p + a] : 1e-30 * dmax + 1e-300; }
+    if (lambda < 0) lambda = 1e-3;
+    while (!accepted && evals < maxfev) {
+      double hn = 0, xnorm = 0, pred = 0, cnew, actred;
+      memcpy(M, A, sizeof(double) * p * p);
+      for (a = 0; a < p; a++) M[a * p + a] += lambda * dsc[a];
+      if (!chol_solve(M, g, h, p)) { lambda *= nu; nu *= 2; continue; }
+      for (a = 0; a < p; a++) { h[a] = -h[a]; xn[a] = x[a] + h[a]; hn += h[a] * h[a]; xnorm += x[a] * x[a]; pred += h[a] * (lambda * dsc[a] * h[a] - g[a]); }
+      cnew = uscp_cost(d, n, xn, NULL, NULL); evals++;
+      actred = cost - cnew;
+      if (pred > 0 && actred > 0) {
+        double rho = actred / pred, t = 2 * rho - 1, f = 1 - t * t * t;
+        int fconv = actred <= ftol * cost && pred <= ftol * cost;
+        for (a = 0; a < p; a++) x[a] = xn[a];
+        lambda *= (f > 1.0 / 3.0 ? f : 1.0 / 3.0); nu = 2;
+        cost = cnew; accepted = 1;
+        if (fconv || sqrt(hn) <= xtol * sqrt(xnorm)) ok = 1;
+      } else {
+        if (sqrt(hn) <= xtol * sqrt(xnorm)) { ok = 1; break; }
+        if (fabs(actred) <= ftol * cost && pred <= ftol * cost) { ok = 1; break; }
+        lambda *= nu; nu *= 2;
+        if (!(lambda < 1e300)) { ok = 1; break; }
+      }
+    }
+  }
+  if (!ok) return 0;
+  for (a = 0; a < p; a++) prm[a] = x[a];
+  {
+    const double cz = cos(x[3]), sz = sin(x[3]), cy = cos(x[4]), sy = sin(x[4]), cx = cos(x[5]), sx = sin(x[5]);
+    prm[8] = x[6] * cz * cy; prm[9] = x[6] * sz * cy; prm[10] = -x[6] * sy;
+    prm[11] = x[7] * (cz * sy * sx - sz * cx); prm[12] = x[7] * (sz * sy * sx + cz * cx); prm[13] = x[7] * cy * sx;
+    prm[14] = cz * sy * cx + sz * sx; prm[15] = sz * sy * cx - cz * sx; prm[16] = cy * cx;
+  }
+  return 17;
+}
+
+static int uscp_lsq(int ls_type, const double* d, size_t n, double* prm) {
+  double init[17];
+  if (ls_type == 0) return uscp_analytic(d, n, prm);
+  if (!uscp_analytic(d, n, init)) return 0;
+  return uscp_iterative(d, n, init, prm);
+}
+
+/* agree, .cxx:726-761 */
+static int uscp_agree(const double* prm, const double* f, double delta) {
+  const double u = f[12], v = f[13];
+  double err[3], s;
+  int i;
+  for (i = 0; i < 3; i++) {
+    const double a = f[3 * i], b = f[3 * i + 1], c = f[3 * i + 2];
+    const double M0 = a * prm[8] + b * prm[9] + c * prm[10];
+    const double M1 = a * prm[11] + b * prm[12] + c * prm[13];
+    const double M3 = a * prm[0] + b * prm[1] + c * prm[2] + f[9 + i];
+    err[i] = (M0 * u + M1 * v + M3) - f[14 + i];
+  }
+  s = err[0] * err[0] + err[1] * err[1] + err[2] * err[2];
+  return s < delta * delta;
+}
+
 static double ray_cross_eps(double aux) {
   double a = aux > 0 ? aux : 0.017453292519943295769236907684886; /* RayIntersectionParametersEstimator.h:35 */
   double s = sin(a);
@@ -594,6 +734,7 @@ int orc_estimate(int model, double delta, double aux, const double* data, size_t
     case M_DENSE5: return dense_solve(5, data, 5, params);
     case M_DENSE6: return dense_solve(6, data, 6, params);
     case M_USXW: return (n == 4) ? usxw_analytic(data, 4, params) : 0;   /* estimate() insists on exactly 4 data (.cxx:21-22) */
+    case M_USCP: return (n == 3) ? uscp_analytic(data, 3, params) : 0;   /* exactly 3 (.cxx:674-675) */
   }
   return -1;
 }
@@ -652,6 +793,7 @@ static int agree1(int model, double delta, const double* prm, const double* x) {
       return sqrt(s) < delta;
     }
     case M_USXW: return usxw_agree(prm, x, delta);
+    case M_USCP: return uscp_agree(prm, x, delta);
     case M_DENSE5:
     case M_DENSE6: { /* DenseLinearEquationSystemParametersEstimator.hxx:111-119 */
       const int nc = (model == M_DENSE5) ? 5 : 6;
@@ -911,6 +1053,7 @@ int orc_least_squares(int model, double delta, double aux, int ls_type, const do
     case M_DENSE5: return dense_solve(5, data, n, params);
     case M_DENSE6: return dense_solve(6, data, n, params);
     case M_USXW: return usxw_lsq(ls_type, data, n, params);
+    case M_USCP: return uscp_lsq(ls_type, data, n, params);
   }
   return -1;
 }
@@ -922,7 +1065,7 @@ int orc_least_squares(int model, double delta, double aux, int ls_type, const do
 /* RANSAC.hxx:217-249 body for one subset (full scoring, no early exit). */
 static uint32_t score_one(int model, int D, int k, double delta, double aux, const double* data, size_t n,
                           const int32_t* sub, double* prm, int* nprm) {
-  double pts[6 * 14];
+  double pts[6 * 17];
   int j; size_t m; uint32_t c = 0;
   for (j = 0; j < k; j++) memcpy(pts + j * D, data + (size_t)sub[j] * D, sizeof(double) * D);
   *nprm = orc_estimate(model, delta, aux, pts, (size_t)k, prm);

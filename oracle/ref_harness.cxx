@@ -37,7 +37,7 @@
 
 using namespace lsqrRecipes;
 
-enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10, M_USXW = 11 };
+enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10, M_USXW = 11, M_USCP = 12 };
 
 namespace {
 
@@ -83,6 +83,20 @@ template <> struct Marshal<CrossWireDatum> {
   }
 };
 
+typedef CalibratedPointerTargetUSCalibrationParametersEstimator::DataType PointerDatum;
+template <> struct Marshal<PointerDatum> {
+  enum { D = 17 };
+  static PointerDatum get(const double* p) {
+    double R[3][3], t[3];
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) R[i][j] = p[3 * i + j]; t[i] = p[9 + i]; }
+    PointerDatum d;
+    d.T2 = Frame(R, t);
+    d.q[0] = p[12]; d.q[1] = p[13];
+    for (int i = 0; i < 3; i++) d.p[i] = p[14 + i];
+    return d;
+  }
+};
+
 template <class T> void unpack(const double* data, size_t n, std::vector<T>& out) {
   out.clear(); out.reserve(n);
   for (size_t i = 0; i < n; i++) out.push_back(Marshal<T>::get(data + i * Marshal<T>::D));
@@ -108,6 +122,11 @@ template <class F> int dispatch(const Cfg& c, F& f) {
       SingleUnknownPointTargetUSCalibrationParametersEstimator e(c.delta, c.ls_type == 0 ? SingleUnknownPointTargetUSCalibrationParametersEstimator::ANALYTIC
                                                                                          : SingleUnknownPointTargetUSCalibrationParametersEstimator::ITERATIVE);
       return f(&e, (CrossWireDatum*)0);
+    }
+    case M_USCP: {
+      CalibratedPointerTargetUSCalibrationParametersEstimator e(c.delta, c.ls_type == 0 ? CalibratedPointerTargetUSCalibrationParametersEstimator::ANALYTIC
+                                                                                        : CalibratedPointerTargetUSCalibrationParametersEstimator::ITERATIVE);
+      return f(&e, (PointerDatum*)0);
     }
   }
   return -1;
@@ -183,8 +202,8 @@ struct RansacOp {
 extern "C" {
 
 int ref_model_info(int model, int* D, int* P, int* k) {
-  static const int tab[12][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}, {6, 5, 5}, {7, 6, 6}, {14, 20, 4}};
-  if (model < 0 || model > 11) return -1;
+  static const int tab[13][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}, {6, 5, 5}, {7, 6, 6}, {14, 20, 4}, {17, 17, 3}};
+  if (model < 0 || model > 12) return -1;
   *D = tab[model][0]; *P = tab[model][1]; *k = tab[model][2];
   return 0;
 }

@@ -10,7 +10,10 @@ from lsqrrecipes_b200 import synth
 from oracle.pyoracle import INFO, MODELS
 
 ALL = list(MODELS.items())
-PINV_MODELS = ("pivot", "dense5", "dense6", "usxw")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
+PINV_MODELS = ("pivot", "dense5", "dense6", "usxw", "uscp")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
+# ... where "rounding level" scales with the conditioning of the minimal system (the 9x9 / 12x12 calibration systems of
+# random subsets reach 1e7)
+PINV_TOL = {"pivot": 1e-9, "dense5": 1e-9, "dense6": 1e-9, "usxw": 1e-6, "uscp": 1e-6}
 
 
 # ---- the reference's own literal test vectors -------------------------------------------
@@ -60,7 +63,7 @@ def test_port_matches_reference_fixture(port, name, m):
     assert np.array_equal(counts, g["counts"]), "per-hypothesis inlier counts must be bit-exact"
     assert np.array_equal(np.isnan(params), np.isnan(g["params"])), "same degenerate subsets"
     if name in PINV_MODELS:  # 9x6 / n x n pseudo-inverse goes through the SVD stand-in: rounding-level agreement
-        assert np.allclose(np.nan_to_num(params), np.nan_to_num(g["params"]), rtol=1e-9, atol=1e-9)
+        assert np.allclose(np.nan_to_num(params), np.nan_to_num(g["params"]), rtol=PINV_TOL[name], atol=PINV_TOL[name])
     else:
         assert np.array_equal(np.nan_to_num(params), np.nan_to_num(g["params"])), "estimate() must be bit-exact"
 
@@ -68,10 +71,12 @@ def test_port_matches_reference_fixture(port, name, m):
 @pytest.mark.parametrize("name,m", ALL)
 def test_port_exhaustive_and_lsq_fixture(port, name, m):
     g = golden(name)
-    for ls_type in ([0, 1] if name in ("circle2", "sphere3", "usxw") else [1]):
+    for ls_type in ([0, 1] if name in ("circle2", "sphere3", "usxw", "uscp") else [1]):
         # the cross-wire LM runs on vector residuals here and on the reference's scalar |e_i| residuals there:
         # same minimum, compared at the north star's 1e-6 relative for converged Levenberg-Marquardt results
         tol = 1e-6 if (name == "usxw" and ls_type == 1) else 1e-8
+        if name == "uscp" and ls_type == 1:   # the reference stops at tolerance 1e-7 (see uscp_iterative in lsqr_oracle.c):
+            tol = 1e-2                         # its stand-in minimiser returns the analytic start, a few 1e-3 from the minimiser
         prm, mask, frac, cnt, rank = port.ransac_exhaustive(m, float(g["delta"]), g["small"], ls_type=ls_type)
         assert np.array_equal(mask, g[f"ex_mask_ls{ls_type}"])
         assert frac == float(g[f"ex_fraction_ls{ls_type}"])
@@ -80,6 +85,14 @@ def test_port_exhaustive_and_lsq_fixture(port, name, m):
         _, bm = port.agree(m, float(g["delta"]), g["params"][b], g["data"])
         ls = port.least_squares(m, float(g["delta"]), g["data"][bm.astype(bool)], ls_type)
         assert same_up_to_sign(ls, g[f"lsq_ls{ls_type}"], SIGN_IDX[name], tol)
+        if name == "uscp" and ls_type == 1:   # ... and the restatement's answer is at least as good a minimum of sum |e_i|^2
+            inl = g["data"][bm.astype(bool)]
+
+            def cost(p):
+                R2 = inl[:, :9].reshape(-1, 3, 3)
+                w = np.outer(inl[:, 12], p[8:11]) + np.outer(inl[:, 13], p[11:14]) + p[0:3]
+                return float(np.sum((np.einsum("nij,nj->ni", R2, w) + inl[:, 9:12] - inl[:, 14:17]) ** 2))
+            assert cost(ls) <= cost(g[f"lsq_ls{ls_type}"]) * (1 + 1e-12)
 
 
 def test_config1_plane23(port):
@@ -108,7 +121,7 @@ def test_port_matches_reference_live(port, ref, name, m):
     assert np.array_equal(c1, c2)
     assert np.array_equal(np.isnan(p1), np.isnan(p2))
     if name in PINV_MODELS:
-        assert np.allclose(np.nan_to_num(p1), np.nan_to_num(p2), rtol=1e-9, atol=1e-9)
+        assert np.allclose(np.nan_to_num(p1), np.nan_to_num(p2), rtol=PINV_TOL[name], atol=PINV_TOL[name])
     else:
         assert np.array_equal(np.nan_to_num(p1), np.nan_to_num(p2))
 

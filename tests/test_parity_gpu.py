@@ -19,12 +19,15 @@ pytestmark = pytest.mark.gpu
 from lsqrrecipes_b200 import MODELS as ENGINE_MODELS
 
 ALL = [(n, m) for n, m in MODELS.items() if n in ENGINE_MODELS]   # every estimator the engine implements
-PINV_MODELS = ("pivot", "dense5", "dense6", "usxw")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
+PINV_MODELS = ("pivot", "dense5", "dense6", "usxw", "uscp")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
+# ... where "rounding level" scales with the conditioning of the minimal system (the 9x9 / 12x12 calibration systems of
+# random subsets reach 1e7)
+PINV_TOL = {"pivot": 1e-9, "dense5": 1e-9, "dense6": 1e-9, "usxw": 1e-6, "uscp": 1e-6}
 REFINE_TOL = 1e-6
 
 
 def _ls_types(name):
-    return [0, 1] if name in ("circle2", "sphere3", "usxw") else [1]
+    return [0, 1] if name in ("circle2", "sphere3", "usxw", "uscp") else [1]
 
 
 @pytest.mark.parametrize("name,m", ALL)
@@ -37,7 +40,7 @@ def test_fp64_counts_bit_exact_vs_reference_fixture(name, m):
     assert np.array_equal(r["counts"], g["counts"])
     assert np.array_equal(np.isnan(r["params"]), np.isnan(g["params"]))
     if name in PINV_MODELS:
-        assert np.allclose(np.nan_to_num(r["params"]), np.nan_to_num(g["params"]), rtol=1e-9, atol=1e-9)
+        assert np.allclose(np.nan_to_num(r["params"]), np.nan_to_num(g["params"]), rtol=PINV_TOL[name], atol=PINV_TOL[name])
     else:
         assert np.array_equal(np.nan_to_num(r["params"]), np.nan_to_num(g["params"])), "device estimate() must round like the reference"
     b = int(np.argmax(g["counts"]))  # first maximum: strict '>' of RANSAC.hxx:245
