@@ -48,7 +48,9 @@ typedef enum lsqr_model {
   LSQR_DENSE6 = 10, /* DenseLinearEquationSystemParametersEstimator<double,6>   (datum = AugmentedRow: n coefficients, right-hand side) */
   LSQR_USXW = 11,   /* SingleUnknownPointTargetUSCalibrationParametersEstimator (cross-wire phantom)   SinglePointTargetUSCalibrationParametersEstimator.cxx:10-329
                      * datum = 14 doubles [R2 row-major, t2, u, v]; ls_type 0 = ANALYTIC, 1 = ITERATIVE (Levenberg-Marquardt) */
-  LSQR_NUM_MODELS = 12
+  LSQR_USCP = 12,   /* CalibratedPointerTargetUSCalibrationParametersEstimator   SinglePointTargetUSCalibrationParametersEstimator.cxx:663-985
+                     * datum = 17 doubles [R2 row-major, t2, u, v, p]; ls_type as for LSQR_USXW */
+  LSQR_NUM_MODELS = 13
 } lsqr_model;
 
 typedef enum lsqr_status {

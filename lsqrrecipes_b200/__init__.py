@@ -34,11 +34,12 @@ from .estimators import (  # noqa: F401
     PivotCalibrationEstimator,
     DenseLinearEquationSystemParametersEstimator,
     SingleUnknownPointTargetUSCalibrationParametersEstimator,
+    CalibratedPointerTargetUSCalibrationParametersEstimator,
 )
 
 __all__ = [
     "Engine", "LsqrError", "MODELS", "MODEL_INFO", "FP32", "FP64", "RANSAC",
     "PlaneParametersEstimator", "LineParametersEstimator", "Line2DParametersEstimator",
     "SphereParametersEstimator", "AbsoluteOrientationParametersEstimator",
-    "RayIntersectionParametersEstimator", "PivotCalibrationEstimator", "DenseLinearEquationSystemParametersEstimator", "SingleUnknownPointTargetUSCalibrationParametersEstimator",
+    "RayIntersectionParametersEstimator", "PivotCalibrationEstimator", "DenseLinearEquationSystemParametersEstimator", "SingleUnknownPointTargetUSCalibrationParametersEstimator", "CalibratedPointerTargetUSCalibrationParametersEstimator",
 ]

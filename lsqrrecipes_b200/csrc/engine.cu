@@ -32,13 +32,13 @@ struct DataSet {
   size_t ld = 0, cap = 0;   // cap = allocated leading dimension
   uint32_t n = 0;
   int D = 0, capD = 0;
-  double center[12] = {0};
+  double center[kMaxDim] = {0};
   bool moments_valid = false;  // rb.moments holds the LS moments of the stored consensus set
   bool mask_valid = false;
   DataView view() const {
     DataView v;
     v.soa64 = soa64; v.soa32 = soa32; v.ld = ld; v.n = n;
-    for (int i = 0; i < 12; i++) v.center[i] = center[i];
+    for (int i = 0; i < kMaxDim; i++) v.center[i] = center[i];
     return v;
   }
 };
@@ -68,8 +68,8 @@ struct lsqr_ctx {
   double* params_in_dev = nullptr; size_t params_in_cap = 0;
   unsigned long long* key_dev = nullptr;  // [0] key, [1] n_valid (as u32 in low half)
   double* small_dev = nullptr;            // kSmall doubles: parameters in @kSmIn, solve out @kSmOut, LM state @kSmLm, estimate() input @kSmEst, sink @kSmSink
-  double* center_dev = nullptr;           // 12 doubles
-  double* center_partials = nullptr;      // 256*12
+  double* center_dev = nullptr;           // kMaxDim doubles
+  double* center_partials = nullptr;      // 256 * kMaxDim
   // refine
   RefineBuffers rb{};
   // pinned host scratch
@@ -163,9 +163,9 @@ int build_layouts(lsqr_ctx* ctx, DataSet& ds, const unsigned char* aos_dev, size
   launch_make32(ds.D, ds.soa64, ctx->center_dev, ds.soa32, ds.ld, ctx->stream); ctx->launches++;
   CKL();
   CK(cudaMemsetAsync(ds.maskbits, 0, sizeof(uint32_t) * (ds.ld / 32), ctx->stream));
-  CK(cudaMemcpyAsync(ctx->pin, ctx->center_dev, sizeof(double) * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->pin, ctx->center_dev, sizeof(double) * kMaxDim, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  for (int i = 0; i < 12; i++) ds.center[i] = ctx->pin[i];
+  for (int i = 0; i < kMaxDim; i++) ds.center[i] = ctx->pin[i];
   return 0;
 }
 
@@ -376,7 +376,7 @@ int refine_impl(lsqr_ctx* ctx, DataSet& ds, int use_mask, double* out_params, in
   }
   double* out_dev = ctx->small_dev + kSmOut;
   // iterative refinement: geometric circle / sphere fit, iterative cross-wire calibration (ls_type 1 in both)
-  const bool geometric = (ctx->model == CIRCLE2 || ctx->model == SPHERE3 || ctx->model == USXW) && ctx->ls_type == LSQR_LS_GEOMETRIC;
+  const bool geometric = (ctx->model == CIRCLE2 || ctx->model == SPHERE3 || ctx->model == USXW || ctx->model == USCP) && ctx->ls_type == LSQR_LS_GEOMETRIC;
   launch_solve_moments(ctx->model, dv, ctx->rb.moments, geometric ? 1 : 0, out_dev, s); ctx->launches++;
   if (geometric) {
     // SphereParametersEstimator.hxx:224-230: algebraic fit as the start, then Levenberg-Marquardt.
@@ -470,8 +470,8 @@ int lsqr_ctx_create(lsqr_ctx** out, int device) {
   ctx->rb.blocks = ctx->num_sms * mask_moments_ctas_per_sm();   // one wave of resident CTAs
   bool ok = cudaMalloc((void**)&ctx->key_dev, 4 * sizeof(unsigned long long)) == cudaSuccess &&
             cudaMalloc((void**)&ctx->small_dev, kSmall * sizeof(double)) == cudaSuccess &&
-            cudaMalloc((void**)&ctx->center_dev, 12 * sizeof(double)) == cudaSuccess &&
-            cudaMalloc((void**)&ctx->center_partials, 256 * 12 * sizeof(double)) == cudaSuccess &&
+            cudaMalloc((void**)&ctx->center_dev, kMaxDim * sizeof(double)) == cudaSuccess &&
+            cudaMalloc((void**)&ctx->center_partials, 256 * kMaxDim * sizeof(double)) == cudaSuccess &&
             cudaMalloc((void**)&ctx->rb.partials, sizeof(double) * kMaxMoments * ctx->rb.blocks) == cudaSuccess &&
             cudaMalloc((void**)&ctx->rb.moments, sizeof(double) * kMaxMoments) == cudaSuccess &&
             cudaMallocHost((void**)&ctx->pin, 64 * sizeof(double)) == cudaSuccess;
@@ -674,7 +674,7 @@ int lsqr_estimate(lsqr_ctx* ctx, const double* packed, size_t n, double* out_par
   const ModelInfo mi = model_info(ctx->model);
   *n_params = 0;
   if (n < (size_t)mi.K) return LSQR_OK;  // e.g. PlaneParametersEstimator.hxx:45-46
-  if (ctx->model == USXW && n != (size_t)mi.K) return LSQR_OK;  // SinglePointTargetUSCalibrationParametersEstimator.cxx:21-22: exactly four
+  if ((ctx->model == USXW || ctx->model == USCP) && n != (size_t)mi.K) return LSQR_OK;  // SinglePointTargetUSCalibrationParametersEstimator.cxx:21-22, :674-675: exactly k
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   double* in_dev = ctx->small_dev + kSmEst;  // K*D <= 64 doubles

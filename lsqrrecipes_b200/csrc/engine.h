@@ -9,6 +9,7 @@
 namespace lsqr {
 
 constexpr int kTilePad = 1024;   // leading dimension of the SoA point arrays is a multiple of this
+constexpr int kMaxDim = 20;           // doubles per datum, upper bound (calibrated-pointer US calibration: 17)
 constexpr int kLmStateDoubles = 192;  // device scratch reserved for the Levenberg-Marquardt controller state
 constexpr int kMaxMoments = 96;  // upper bound on the doubles accumulated per thread by the refine reductions (cross-wire US calibration: 91)
 
@@ -18,7 +19,7 @@ struct DataView {
   const float* soa32;   // [D][ld], centred (soa64 - center), padded with NaN
   size_t ld;
   uint32_t n;
-  double center[12];    // per-component shift used for soa32 and for the refine moments
+  double center[kMaxDim];  // per-component shift used for soa32 and for the refine moments
 };
 
 // ---- k_score.cu -------------------------------------------------------------------------

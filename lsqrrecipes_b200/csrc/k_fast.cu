@@ -73,6 +73,7 @@ __device__ __forceinline__ f2 join(float lo, float hi) { f2 r; asm("mov.b64 %0, 
 //   PIVOT    (tDRF, tW - c)
 //   DENSE n  (x[n], -1): a.x - b as n+1 FMAs over the (uncentred) augmented row
 //   USXW     (m_x R3(:,1), m_y R3(:,2), t3, t1 - c)
+//   USCP     (m_x R3(:,1), m_y R3(:,2), t3)
 template <int M> __device__ __forceinline__ void hoist32(const double* p, const double* c, const EstCfg& cfg, float* q);
 template <> __device__ __forceinline__ void hoist32<PLANE3>(const double* p, const double* c, const EstCfg&, float* q) {
   q[0] = (float)p[0]; q[1] = (float)p[1]; q[2] = (float)p[2];
@@ -123,17 +124,22 @@ template <> __device__ __forceinline__ void hoist32<USXW>(const double* p, const
   for (int i = 0; i < 3; i++) { q[6 + i] = (float)p[3 + i]; q[9 + i] = (float)(p[i] - c[9 + i]); }
 }
 
+template <> __device__ __forceinline__ void hoist32<USCP>(const double* p, const double*, const EstCfg&, float* q) {
+  for (int i = 0; i < 6; i++) q[i] = (float)p[8 + i];
+  for (int i = 0; i < 3; i++) q[6 + i] = (float)p[i];
+}
+
 template <int M>
 __global__ void hoist32_kernel(const double* __restrict__ hyp64, size_t hld, uint32_t H, DataView dv, EstCfg cfg, float* __restrict__ hyp32) {
   constexpr int P = Model<M>::P, Q = Model<M>::Q32;
   const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= H) return;
-  double prm[P], c[12];
+  double prm[P], c[kMaxDim];
   float q[Q];
 #pragma unroll
   for (int j = 0; j < P; j++) prm[j] = hyp64[(size_t)j * hld + h];
 #pragma unroll
-  for (int j = 0; j < 12; j++) c[j] = dv.center[j];
+  for (int j = 0; j < kMaxDim; j++) c[j] = dv.center[j];
   hoist32<M>(prm, c, cfg, q);
   const bool ok = prm[0] == prm[0];
   // layout: groups of four constants, [ceil(Q/4)][hld] float4 -> one 16-byte load per group in the consensus kernels
@@ -175,6 +181,7 @@ __device__ __forceinline__ void load_hyp32(const float* __restrict__ hyp, size_t
     case DENSE5: { CALL(DENSE5); break; }     \
     case DENSE6: { CALL(DENSE6); break; }     \
     case USXW: { CALL(USXW); break; }         \
+    case USCP: { CALL(USCP); break; }         \
     default: break;                           \
   }
 
@@ -312,6 +319,24 @@ template <> struct Eval<USXW> {
 #pragma unroll
     for (int r = 0; r < 3; r++) {
       const f2 e = sub2(fma2(x[3 * r], w[0], fma2(x[3 * r + 1], w[1], fma2(x[3 * r + 2], w[2], x[9 + r]))), q[9 + r]);
+      g = fma2(e, e, g);
+    }
+    return g;
+  }
+};
+
+// calibrated pointer: e = R2 (u c1 + v c2 + t3) + t2 - p
+template <> struct Eval<USCP> {
+  static constexpr bool kHasAbsForm = false;
+  __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) {
+    f2 w[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) w[k] = fma2(x[12], q[k], fma2(x[13], q[3 + k], q[6 + k]));
+    f2 g = t.neg_delta2;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const f2 e = sub2(fma2(x[3 * r], w[0], fma2(x[3 * r + 1], w[1], fma2(x[3 * r + 2], w[2], x[9 + r]))), x[14 + r]);
       g = fma2(e, e, g);
     }
     return g;
@@ -547,6 +572,7 @@ template <> struct BlockCB<PIVOT> { static constexpr int R = 6, PPI = 1; };
 template <> struct BlockCB<DENSE5> { static constexpr int R = 8, PPI = 2; };
 template <> struct BlockCB<DENSE6> { static constexpr int R = 8, PPI = 2; };
 template <> struct BlockCB<USXW> { static constexpr int R = 4, PPI = 1; };
+template <> struct BlockCB<USCP> { static constexpr int R = 4, PPI = 1; };
 
 template <int M>
 static int run_consensus_cb(const DataView& dv, const float* hyp, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms, cudaStream_t s) {
@@ -608,6 +634,7 @@ template <> struct Block32<PIVOT> { static constexpr int R = 4, PPI = 1; };
 template <> struct Block32<DENSE5> { static constexpr int R = 6, PPI = 2; };
 template <> struct Block32<DENSE6> { static constexpr int R = 6, PPI = 2; };
 template <> struct Block32<USXW> { static constexpr int R = 3, PPI = 1; };
+template <> struct Block32<USCP> { static constexpr int R = 3, PPI = 1; };
 
 int launch_consensus32(int model, const DataView& dv, const float* hyp32, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms,
                        cudaStream_t s) {

@@ -30,6 +30,7 @@ __host__ __device__ inline int n_moments(int model, bool lm) {
     case DENSE5: return 21;   // count, A^T A upper triangle (15), A^T b (5)
     case DENSE6: return 28;   // count, 21, 6
     case USXW: return lm ? 79 : 91;   // LM: count, J^T J (66), J^T e (11), cost; analytic: count, A^T A (78), A^T b (12)
+    case USCP: return lm ? 46 : 55;   // LM: count, 36, 8, cost; analytic: count, 45, 9
   }
   return 0;
 }
@@ -71,6 +72,7 @@ template <> struct Mom<PIVOT>   { static constexpr int N = 22, NLM = 0, NPLM = 1
 template <> struct Mom<DENSE5>  { static constexpr int N = 21, NLM = 0, NPLM = 1; };
 template <> struct Mom<DENSE6>  { static constexpr int N = 28, NLM = 0, NPLM = 1; };
 template <> struct Mom<USXW>    { static constexpr int N = 91, NLM = 79, NPLM = 11; };
+template <> struct Mom<USCP>    { static constexpr int N = 55, NLM = 46, NPLM = 8; };
 
 // q = centred datum.  acc[0] counts.
 template <int DIM> __device__ __forceinline__ void acc_scatter(const double* q, double* acc) {
@@ -231,11 +233,71 @@ __device__ __forceinline__ void acc_us_lm(const double* q, const double* x, doub
   acc[78] += cost;
 }
 
+// Normal equations of the rows [u R2, v R2, R2] x = p - t2 (SinglePointTargetUSCalibrationParametersEstimator.cxx:806-846)
+template <> __device__ __forceinline__ void accumulate<USCP>(const double* q, double* acc) {
+  acc[0] += 1.0;
+  const double u = q[12], v = q[13];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    double row[9];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { row[c] = q[3 * r + c] * u; row[3 + c] = q[3 * r + c] * v; row[6 + c] = q[3 * r + c]; }
+    const double b = q[14 + r] - q[9 + r];
+    int o = 1;
+#pragma unroll
+    for (int a = 0; a < 9; a++)
+#pragma unroll
+      for (int bb = a; bb < 9; bb++) acc[o++] += row[a] * row[bb];
+#pragma unroll
+    for (int a = 0; a < 9; a++) acc[o++] += row[a] * b;
+  }
+}
+// Levenberg-Marquardt pass of the calibrated-pointer calibration at x[8] = [t3, omega_z, omega_y, omega_x, m_x, m_y]:
+// e = R2 (u m_x c1 + v m_y c2 + t3) + t2 - p
+__device__ __forceinline__ void acc_uscp_lm(const double* q, const double* x, double* acc) {
+  const double sz = sin(x[3]), cz = cos(x[3]), sy = sin(x[4]), cy = cos(x[4]), sx = sin(x[5]), cx = cos(x[5]);
+  const double mx = x[6], my = x[7], u = q[12], v = q[13];
+  const double c1[3] = {cz * cy, sz * cy, -sy};
+  const double c2[3] = {cz * sy * sx - sz * cx, sz * sy * sx + cz * cx, cy * sx};
+  const double dc1[3][3] = {{-sz * cy, cz * cy, 0}, {-cz * sy, -sz * sy, -cy}, {0, 0, 0}};
+  const double dc2[3][3] = {{-sz * sy * sx - cz * cx, cz * sy * sx - sz * cx, 0}, {cz * cy * sx, sz * cy * sx, -sy * sx},
+                            {cz * sy * cx + sz * sx, sz * sy * cx - cz * sx, cy * cx}};
+  double w[3], dw[8][3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    w[k] = u * mx * c1[k] + v * my * c2[k] + x[k];
+#pragma unroll
+    for (int p = 0; p < 3; p++) { dw[p][k] = (p == k) ? 1.0 : 0.0; dw[3 + p][k] = u * mx * dc1[p][k] + v * my * dc2[p][k]; }
+    dw[6][k] = u * c1[k];
+    dw[7][k] = v * c2[k];
+  }
+  acc[0] += 1.0;
+  double cost = 0;
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const double a = q[3 * r], b = q[3 * r + 1], c = q[3 * r + 2];
+    const double e = a * w[0] + b * w[1] + c * w[2] + q[9 + r] - q[14 + r];
+    double J[8];
+#pragma unroll
+    for (int p = 0; p < 8; p++) J[p] = a * dw[p][0] + b * dw[p][1] + c * dw[p][2];
+    int o = 1;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = i; j < 8; j++) acc[o++] += J[i] * J[j];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[o++] += J[i] * e;
+    cost += e * e;
+  }
+  acc[45] += cost;
+}
+
 __host__ __device__ inline bool centred_comp(int model, int d) {
   switch (model) {
     case RAY: return d < 3;
     case PIVOT: return d >= 9;
     case USXW: return d >= 9 && d < 12;
+    case USCP: return false;
     case DENSE5: case DENSE6: return false;
     default: return true;
   }
@@ -303,6 +365,7 @@ __global__ void __launch_bounds__(256, LSQR_MM_CTAS) mask_moments_kernel(DataVie
           if constexpr (M == CIRCLE2) acc_sphere_lm<2>(q, lmx, acc);
           if constexpr (M == SPHERE3) acc_sphere_lm<3>(q, lmx, acc);
           if constexpr (M == USXW) acc_us_lm(q, lmx, acc);
+          if constexpr (M == USCP) acc_uscp_lm(q, lmx, acc);
         } else accumulate<M>(q, acc);
       }
     }
@@ -337,6 +400,7 @@ void launch_mask_moments(int model, const DataView& dv, uint32_t begin, uint32_t
     if (model == CIRCLE2) { BYMODE(CIRCLE2, true); }
     else if (model == SPHERE3) { BYMODE(SPHERE3, true); }
     else if (model == USXW) { BYMODE(USXW, true); }
+    else if (model == USCP) { BYMODE(USCP, true); }
     return;
   }
   switch (model) {
@@ -352,6 +416,7 @@ void launch_mask_moments(int model, const DataView& dv, uint32_t begin, uint32_t
     case DENSE5: { BYMODE(DENSE5, false); break; }
     case DENSE6: { BYMODE(DENSE6, false); break; }
     case USXW: { BYMODE(USXW, false); break; }
+    case USCP: { BYMODE(USCP, false); break; }
   }
 #undef BYMODE
 #undef LAUNCH
@@ -583,6 +648,30 @@ __device__ int solve_us(const double* m, const double* c, double* out) {
   return us_post(x, out) ? 20 : 0;
 }
 
+// Analytic calibrated-pointer calibration (.cxx:789-920) through the 9 x 9 normal equations (scaled Cholesky as above)
+__device__ int solve_uscp(const double* m, double* out) {
+  if (m[0] < 3.0) return 0;
+  double S[81], sc[9], y[9], x[9];
+  {
+    int o = 1;
+    for (int a = 0; a < 9; a++) for (int bb = a; bb < 9; bb++) { const double v = m[o++]; S[a * 9 + bb] = v; S[bb * 9 + a] = v; }
+    for (int a = 0; a < 9; a++) y[a] = m[o++];
+  }
+  for (int i = 0; i < 9; i++) { if (!(S[i * 9 + i] > 0)) return 0; sc[i] = 1.0 / sqrt(S[i * 9 + i]); }
+  for (int i = 0; i < 9; i++) { for (int j = 0; j < 9; j++) S[i * 9 + j] *= sc[i] * sc[j]; y[i] *= sc[i]; }
+  for (int j = 0; j < 9; j++) {
+    double d = S[j * 9 + j];
+    for (int k = 0; k < j; k++) d -= S[j * 9 + k] * S[j * 9 + k];
+    if (!(d > 1e-13)) return 0;
+    S[j * 9 + j] = sqrt(d);
+    for (int i = j + 1; i < 9; i++) { double t = S[i * 9 + j]; for (int k = 0; k < j; k++) t -= S[i * 9 + k] * S[j * 9 + k]; S[i * 9 + j] = t / S[j * 9 + j]; }
+  }
+  for (int i = 0; i < 9; i++) { double t = y[i]; for (int k = 0; k < i; k++) t -= S[i * 9 + k] * x[k]; x[i] = t / S[i * 9 + i]; }
+  for (int i = 8; i >= 0; i--) { double t = x[i]; for (int k = i + 1; k < 9; k++) t -= S[k * 9 + i] * x[k]; x[i] = t / S[i * 9 + i]; }
+  for (int i = 0; i < 9; i++) x[i] *= sc[i];
+  return uscp_post(x, out) ? 17 : 0;
+}
+
 // out[0] = number of parameters (0 = the reference's empty vector), out[1..] = parameters.
 // For CIRCLE2/SPHERE3 the parameters stay in centred coordinates when keep_centred != 0 (LM start).
 __global__ void solve_moments_kernel(int model, DataView dv, const double* __restrict__ m, int keep_centred, double* __restrict__ out) {
@@ -603,6 +692,7 @@ __global__ void solve_moments_kernel(int model, DataView dv, const double* __res
     case DENSE5: np = solve_dense<5>(m, p); break;
     case DENSE6: np = solve_dense<6>(m, p); break;
     case USXW: np = solve_us(m, keep_centred ? nullptr : c, p); break;   // LM start: t1 stays relative to the centre
+    case USCP: np = solve_uscp(m, p); break;
   }
   out[0] = (double)np;
   for (int j = 0; j < np; j++) out[1 + j] = p[j];
@@ -728,6 +818,7 @@ __device__ void lm_update_model(int model, const double* m, double* st) {
   if (model == CIRCLE2) lm_update<3>(m, st, 1e-8 * 0.01, 500);
   else if (model == SPHERE3) lm_update<4>(m, st, 1e-8 * 0.01, 500);
   else if (model == USXW) lm_update<11>(m, st, 10e-16, 5000);
+  else if (model == USCP) lm_update<8>(m, st, 10e-16, 5000);   // iterated to the minimiser (the reference stops at 1e-7)
 }
 
 __global__ void lm_init_kernel(const double* __restrict__ alg_out, double* __restrict__ st) {
@@ -758,6 +849,15 @@ __global__ void lm_finish_kernel(int model, DataView dv, const double* __restric
     for (int j = 0; j < 3; j++) x[j] += dv.center[9 + j];   // t1 was estimated relative to the centre of the t2 components
     out[0] = 20;
     us_expand(x, out + 1);
+    return;
+  }
+  if (model == USCP) {   // .cxx:958-983: entries 8..16 rebuilt from the optimised angles and scales
+    double x[11], full[20];
+    x[0] = x[1] = x[2] = 0.0;
+    for (int j = 0; j < 8; j++) x[3 + j] = st[LM_X + j];
+    us_expand(x, full);
+    out[0] = 17;
+    for (int j = 0; j < 17; j++) out[1 + j] = full[3 + j];
     return;
   }
   const int dim = (model == CIRCLE2) ? 2 : 3;
@@ -931,7 +1031,7 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
   for (int j = 0; j < HQ; j++) hq[j] = sh_prm[j];
   block_moments<M>(pts, n, ldp, hq, cfg, nullptr, false, 1, mask_out, sh_part, sh_mom);
   DataView zero;
-  for (int j = 0; j < 12; j++) zero.center[j] = 0.0;
+  for (int j = 0; j < kMaxDim; j++) zero.center[j] = 0.0;
   __shared__ double sh_out[LSQR_MAX_PARAMS + 4];
   if (threadIdx.x == 0) {
     double p[LSQR_MAX_PARAMS];

@@ -69,6 +69,7 @@ __host__ __device__ inline bool centred_component(int model, int d) {
     case RAY: return d < 3;
     case PIVOT: return d >= 9;
     case USXW: return d >= 9 && d < 12;       // t2; rotation entries and pixel coordinates stay
+    case USCP: return false;                  // t2 and p enter as p - t2 with no free translation to absorb a shift
     case DENSE5: case DENSE6: return false;   // rows of a linear system: a shift would change the solution
     default: return true;
   }
@@ -83,16 +84,16 @@ __global__ void center_partial_kernel(int D, const double* __restrict__ soa, siz
     sh[threadIdx.x] = acc;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
-    if (threadIdx.x == 0) partials[(size_t)blockIdx.x * 12 + d] = sh[0];
+    if (threadIdx.x == 0) partials[(size_t)blockIdx.x * kMaxDim + d] = sh[0];
     __syncthreads();
   }
 }
 __global__ void center_final_kernel(int model, int D, uint32_t n, const double* __restrict__ partials, double* __restrict__ center) {
   const int d = threadIdx.x;
-  if (d >= 12) return;
+  if (d >= kMaxDim) return;
   double acc = 0.0;
   if (d < D && centred_component(model, d)) {
-    for (int b = 0; b < kCenterBlocks; b++) acc += partials[(size_t)b * 12 + d];
+    for (int b = 0; b < kCenterBlocks; b++) acc += partials[(size_t)b * kMaxDim + d];
     acc = (n > 0) ? acc / (double)n : 0.0;
     if (!(acc == acc) || fabs(acc) > 1e300) acc = 0.0;
   }
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(128) solve_kernel(SolveArgs a, const double* _
     case DENSE5: { CALL(DENSE5); break; }     \
     case DENSE6: { CALL(DENSE6); break; }     \
     case USXW: { CALL(USXW); break; }         \
+    case USCP: { CALL(USCP); break; }         \
     default: break;                           \
   }
 

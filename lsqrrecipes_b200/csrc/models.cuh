@@ -14,7 +14,7 @@
 
 namespace lsqr {
 
-enum : int { PLANE3 = 0, LINE2D = 1, LINE2 = 2, LINE3 = 3, CIRCLE2 = 4, SPHERE3 = 5, ABSOR = 6, RAY = 7, PIVOT = 8, DENSE5 = 9, DENSE6 = 10, USXW = 11, NUM_MODELS = 12 };
+enum : int { PLANE3 = 0, LINE2D = 1, LINE2 = 2, LINE3 = 3, CIRCLE2 = 4, SPHERE3 = 5, ABSOR = 6, RAY = 7, PIVOT = 8, DENSE5 = 9, DENSE6 = 10, USXW = 11, USCP = 12, NUM_MODELS = 13 };
 
 // dim = doubles per datum, P = parameters, K = minimal subset, HQ = doubles of a prepared
 // fp64 hypothesis, Q32 = floats of a hoisted fp32 hypothesis.
@@ -34,6 +34,9 @@ template <> struct Model<DENSE6>  { static constexpr int D = 7,  P = 6, K = 6, H
 // SingleUnknownPointTargetUSCalibrationParametersEstimator (cross-wire phantom): datum = [R2 (9), t2 (3), u, v],
 // parameters [t1, t3, omega_z, omega_y, omega_x, m_x, m_y, m_x R3(:,1), m_y R3(:,2), R3(:,3)]
 template <> struct Model<USXW>    { static constexpr int D = 14, P = 20, K = 4, HQ = 12, Q32 = 12; };
+// CalibratedPointerTargetUSCalibrationParametersEstimator: datum = [R2 (9), t2 (3), u, v, p (3)],
+// parameters [t3, omega_z, omega_y, omega_x, m_x, m_y, m_x R3(:,1), m_y R3(:,2), R3(:,3)]
+template <> struct Model<USCP>    { static constexpr int D = 17, P = 17, K = 3, HQ = 9,  Q32 = 9;  };
 
 struct ModelInfo { int D, P, K, HQ, Q32; };
 __host__ __device__ inline ModelInfo model_info(int m) {
@@ -50,6 +53,7 @@ __host__ __device__ inline ModelInfo model_info(int m) {
     case DENSE5:  return {6, 5, 5, 5, 6};
     case DENSE6:  return {7, 6, 6, 6, 7};
     case USXW:    return {14, 20, 4, 12, 12};
+    case USCP:    return {17, 17, 3, 9, 9};
   }
   return {0, 0, 0, 0, 0};
 }
@@ -353,9 +357,10 @@ __device__ inline void closest_rotation(double* R) {
   for (int i = 0; i < 9; i++) R[i] = out[i];
 }
 
-// SinglePointTargetUSCalibrationParametersEstimator.cxx:204-268: the solution x[12] of the linear system ->
-// scale factors, re-orthonormalised rotation, Euler angles, the 20 parameters.
-__device__ inline bool us_post(const double* x, double* prm) {
+// SinglePointTargetUSCalibrationParametersEstimator.cxx:204-250 (and :862-900): scale factors, re-orthonormalised
+// rotation and Euler angles from the first six unknowns [m_x R3(:,1), m_y R3(:,2)] of the linear solution;
+// out = [omega_z, omega_y, omega_x, m_x, m_y, m_x R3(:,1), m_y R3(:,2), R3(:,3)] (14 values).
+__device__ inline void us_rotation_part(const double* x, double* out) {
   const double smallAngle = 0.008726535498373935, halfPI = 1.5707963267948966192313216916398;
   double r1[3], r2[3], r3[3], R3[9];
   for (int i = 0; i < 3; i++) { r1[i] = x[i]; r2[i] = x[3 + i]; }
@@ -378,14 +383,26 @@ __device__ inline bool us_post(const double* x, double* prm) {
     omega_z = 0;
     omega_x = atan2(R3[1], R3[4]);
   }
+  out[0] = omega_z; out[1] = omega_y; out[2] = omega_x; out[3] = m_x; out[4] = m_y;
+  out[5] = m_x * R3[0]; out[6] = m_x * R3[3]; out[7] = m_x * R3[6];
+  out[8] = m_y * R3[1]; out[9] = m_y * R3[4]; out[10] = m_y * R3[7];
+  out[11] = R3[2]; out[12] = R3[5]; out[13] = R3[8];
+}
+// cross-wire: x = [m_x R3(:,1), m_y R3(:,2), t3, t1] -> the 20 parameters (.cxx:251-268)
+__device__ inline bool us_post(const double* x, double* prm) {
   prm[0] = x[9]; prm[1] = x[10]; prm[2] = x[11];
   prm[3] = x[6]; prm[4] = x[7]; prm[5] = x[8];
-  prm[6] = omega_z; prm[7] = omega_y; prm[8] = omega_x; prm[9] = m_x; prm[10] = m_y;
-  prm[11] = m_x * R3[0]; prm[12] = m_x * R3[3]; prm[13] = m_x * R3[6];
-  prm[14] = m_y * R3[1]; prm[15] = m_y * R3[4]; prm[16] = m_y * R3[7];
-  prm[17] = R3[2]; prm[18] = R3[5]; prm[19] = R3[8];
+  us_rotation_part(x, prm + 6);
   bool ok = true;
   for (int i = 0; i < 20; i++) ok = ok && (prm[i] == prm[i]);
+  return ok;
+}
+// calibrated pointer: x = [m_x R3(:,1), m_y R3(:,2), t3] -> the 17 parameters (.cxx:903-920)
+__device__ inline bool uscp_post(const double* x, double* prm) {
+  prm[0] = x[6]; prm[1] = x[7]; prm[2] = x[8];
+  us_rotation_part(x, prm + 3);
+  bool ok = true;
+  for (int i = 0; i < 17; i++) ok = ok && (prm[i] == prm[i]);
   return ok;
 }
 
@@ -408,6 +425,23 @@ template <> __device__ inline bool estimate<USXW>(const double* d, const EstCfg&
   return us_post(x, prm);
 }
 
+// SinglePointTargetUSCalibrationParametersEstimator.cxx:789-920 with three data: rows [u R2, v R2, R2] x = p - t2,
+// singular values <= FLT_EPSILON zeroed, rank < 9 fails.
+template <> __device__ inline bool estimate<USCP>(const double* d, const EstCfg&, double* prm) {
+  double A[81], b[9], x[9];
+  for (int i = 0; i < 3; i++) {
+    const double* f = d + 17 * i;
+    const double ui = f[12], vi = f[13];
+    for (int r = 0; r < 3; r++) {
+      double* row = A + (3 * i + r) * 9;
+      for (int c = 0; c < 3; c++) { row[c] = f[3 * r + c] * ui; row[3 + c] = f[3 * r + c] * vi; row[6 + c] = f[3 * r + c]; }
+      b[3 * i + r] = f[14 + r] - f[9 + r];
+    }
+  }
+  if (pinv_solve<9, 9>(A, b, 1.192092896e-07, x) < 9) return false;
+  return uscp_post(x, prm);
+}
+
 // ---------------------------------------------------------------------------------------
 // agree(): prepare once per hypothesis, test once per (hypothesis, datum)
 // ---------------------------------------------------------------------------------------
@@ -426,6 +460,14 @@ template <> __device__ __forceinline__ void prepare<USXW>(const double* prm, dou
   for (int i = 0; i < 6; i++) hq[i] = prm[11 + i];
 #pragma unroll
   for (int i = 0; i < 3; i++) { hq[6 + i] = prm[3 + i]; hq[9 + i] = prm[i]; }
+}
+
+// calibrated pointer: m_x R3(:,1), m_y R3(:,2), t3
+template <> __device__ __forceinline__ void prepare<USCP>(const double* prm, double* hq) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) hq[i] = prm[8 + i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) hq[6 + i] = prm[i];
 }
 
 template <int M> __device__ __forceinline__ bool agree(const double* hq, const double* x, const EstCfg& cfg);
@@ -506,6 +548,22 @@ template <> __device__ __forceinline__ bool agree<USXW>(const double* h, const d
     err[i] = (M0 * u + M1 * v + M3) - h[9 + i];
   }
   s = err[0] * err[0] + err[1] * err[1] + err[2] * err[2];
+  return s < cfg.delta2;
+}
+
+// SinglePointTargetUSCalibrationParametersEstimator.cxx:726-761: the same product, compared with the measured pointer tip
+template <> __device__ __forceinline__ bool agree<USCP>(const double* h, const double* x, const EstCfg& cfg) {
+  const double u = x[12], v = x[13];
+  double err[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double a = x[3 * i], b = x[3 * i + 1], c = x[3 * i + 2];
+    const double M0 = a * h[0] + b * h[1] + c * h[2];
+    const double M1 = a * h[3] + b * h[4] + c * h[5];
+    const double M3 = a * h[6] + b * h[7] + c * h[8] + x[9 + i];
+    err[i] = (M0 * u + M1 * v + M3) - x[14 + i];
+  }
+  const double s = err[0] * err[0] + err[1] * err[1] + err[2] * err[2];
   return s < cfg.delta2;
 }
 

@@ -181,6 +181,28 @@ class SingleUnknownPointTargetUSCalibrationParametersEstimator(ParametersEstimat
         parameters.extend(self.engine().estimate(d).tolist())
 
 
+class CalibratedPointerTargetUSCalibrationParametersEstimator(ParametersEstimator):
+    """CalibratedPointerTargetUSCalibrationParametersEstimator (SinglePointTargetUSCalibrationParametersEstimator.cxx:663-985);
+    datum = (Frame T2, Point2D q, Point3D p) as 17 doubles [R2 row-major, t2, u, v, p]; 17 parameters
+    [t3, omega_z, omega_y, omega_x, m_x, m_y, m_x R3(:,1), m_y R3(:,2), R3(:,3)]."""
+    _model = "uscp"
+    ANALYTIC, ITERATIVE = 0, 1
+
+    def __init__(self, delta, lsType=1):
+        super().__init__(3, delta, ls_type=lsType)
+
+    def setLeastSquaresType(self, lsType):
+        self._ls_type = int(lsType)
+        self._reconfigure()
+
+    def estimate(self, data, parameters):
+        parameters.clear()
+        d = np.asarray(data, dtype=np.float64).reshape(-1, 17)
+        if d.shape[0] != self.minForEstimate:      # exactly three (.cxx:674-675)
+            return
+        parameters.extend(self.engine().estimate(d).tolist())
+
+
 class RANSAC:
     """RANSAC<T,S> (RANSAC.h:47-151): two static compute() overloads."""
 
