@@ -1064,13 +1064,23 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
         for (int j = 0; j < np; j++) sh_state[LM_X + j] = sh_out[1 + j];
       }
       __syncthreads();
-      while (sh_state[LM_STATUS] == 0.0) {
+      // The controller state is touched by thread 0 only; what the block needs per pass (status, evaluation
+      // point) goes through sh_bcast, with a barrier on either side of every read.
+      __shared__ double sh_bcast[6];
+      for (;;) {
+        if (threadIdx.x == 0) {
+          sh_bcast[0] = sh_state[LM_STATUS];
+          const int o = (sh_state[LM_PHASE] != 0.0) ? LM_TRIAL : LM_X;
+          for (int j = 0; j < 4; j++) sh_bcast[1 + j] = sh_state[o + j];
+        }
+        __syncthreads();
         double lmx[4];
-        const int o = (sh_state[LM_PHASE] != 0.0) ? LM_TRIAL : LM_X;
-        for (int j = 0; j < 4; j++) lmx[j] = sh_state[o + j];
+        const double status = sh_bcast[0];
+        for (int j = 0; j < 4; j++) lmx[j] = sh_bcast[1 + j];
+        __syncthreads();
+        if (status != 0.0) break;
         block_moments<M>(pts, n, ldp, hq, cfg, lmx, true, 1, nullptr, sh_part, sh_mom);
         if (threadIdx.x == 0) lm_update_model(M, sh_mom, sh_state);
-        __syncthreads();
       }
       if (threadIdx.x == 0) {
         if (sh_state[LM_STATUS] != 1.0) sh_out[0] = 0.0;

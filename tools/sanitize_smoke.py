@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Small pass over every model and entry point, meant to run under compute-sanitizer (memcheck / racecheck)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lsqrrecipes_b200 import FP32, FP64, SAMPLE_EXHAUSTIVE, Engine, MODELS, synth  # noqa: E402
+
+big = "--big" in sys.argv
+for name in MODELS:
+    n = 3000
+    data, true = synth.GENERATORS[name](n, seed=5)
+    for ls in ([0, 1] if name in ("circle2", "sphere3", "usxw", "uscp") else [1]):
+        eng = Engine(name, synth.DELTAS[name], ls_type=ls)
+        eng.upload(data)
+        r64 = eng.score(count=700, precision=FP64, seed=1, want_counts=True, want_params=True)
+        r32 = eng.score(count=700, precision=FP32, seed=1, want_counts=True)
+        if big:
+            eng.score(count=98304 + 128, precision=FP32, seed=2)       # constant-bank kernel
+        eng.consensus(r64["best_params"])
+        eng.get_mask()
+        prm = eng.refine()
+        out = eng.ransac(0.99, precision=FP32, seed=3)
+        eng.estimate(data[: eng.k])
+        eng.agree(r64["best_params"], data[:100])
+        eng.least_squares(data[:500])
+        if name in ("plane3", "line2d", "sphere3", "dense5"):
+            off = np.arange(0, 9) * 200
+            eng.ransac_batch(data[:1600], off, max_tries=256)
+        small = eng
+        small.upload(data[:12])
+        small.ransac_exhaustive()
+        eng.close()
+        print(name, ls, "ok", r64["best_count"], r32["best_count"], len(prm), flush=True)
+eng = Engine("absor", 2.0)
+d, _ = synth.absolute_orientation(2000, seed=1)
+eng.weighted_least_squares(d, np.ones(2000))
+eng.close()
+print("done")
