@@ -521,7 +521,10 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
     f2 x[PPI][D];
 #pragma unroll
     for (int d = 0; d < D; d++) {
-      if constexpr (PPI == 2) {
+      if constexpr (PPI == 4) {
+        const float4 v = c_tile[d * (int)(cp / 4) + 2 * g], w = c_tile[d * (int)(cp / 4) + 2 * g + 1];
+        x[0][d] = join(v.x, v.y); x[1][d] = join(v.z, v.w); x[2][d] = join(w.x, w.y); x[3][d] = join(w.z, w.w);
+      } else if constexpr (PPI == 2) {
         const float4 v = c_tile[d * (int)(cp / 4) + g];
         x[0][d] = join(v.x, v.y); x[1][d] = join(v.z, v.w);
       } else {
@@ -534,11 +537,14 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
       f2 q[Q];
 #pragma unroll
       for (int j = 0; j < Q; j++) q[j] = splat(qf[r][j]);
-      if constexpr (Eval<M>::kHasAbsForm && PPI == 2) {
+      if constexpr (Eval<M>::kHasAbsForm && PPI >= 2) {
         // ptxas puts most predicated adds on the FMA-heavy pipe (VIADD), which the FFMA2s need: one
         // hypothesis in LSQR_CB_MIX counts that way, the others with two ALU instructions
-        if (r % LSQR_CB_MIX == 0) count_abs_lt4(cnt[r], Eval<M>::dist(q, x[0]), Eval<M>::dist(q, x[1]), thr.fdelta);
-        else count_abs_lt4_alu(cnt[r], Eval<M>::dist(q, x[0]), Eval<M>::dist(q, x[1]), thr.fdelta);
+#pragma unroll
+        for (int u = 0; u < PPI; u += 2) {
+          if (r % LSQR_CB_MIX == 0) count_abs_lt4(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), thr.fdelta);
+          else count_abs_lt4_alu(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), thr.fdelta);
+        }
       } else {
 #pragma unroll
         for (int u = 0; u < PPI; u++) count_sign(cnt[r], Eval<M>::signed_(q, x[u], thr));
@@ -557,11 +563,14 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
 #define LSQR_CB_THREADS 128
 #endif
 #ifndef LSQR_CB_R_PLANE
-#define LSQR_CB_R_PLANE 12
+#define LSQR_CB_R_PLANE 10
 #endif
 template <int M> struct BlockCB { static constexpr int R = 8, PPI = 2; };
-template <> struct BlockCB<PLANE3> { static constexpr int R = LSQR_CB_R_PLANE, PPI = 2; };
-template <> struct BlockCB<LINE2D> { static constexpr int R = 12, PPI = 2; };
+#ifndef LSQR_CB_PPI_PLANE
+#define LSQR_CB_PPI_PLANE 4
+#endif
+template <> struct BlockCB<PLANE3> { static constexpr int R = LSQR_CB_R_PLANE, PPI = LSQR_CB_PPI_PLANE; };
+template <> struct BlockCB<LINE2D> { static constexpr int R = 10, PPI = 4; };
 template <> struct BlockCB<LINE2> { static constexpr int R = 10, PPI = 2; };
 template <> struct BlockCB<LINE3> { static constexpr int R = 8, PPI = 2; };
 template <> struct BlockCB<CIRCLE2> { static constexpr int R = 12, PPI = 2; };
