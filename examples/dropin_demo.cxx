@@ -282,6 +282,41 @@ static void crossWireCase() {
   CHECK(p4.size() == 20 && p5.empty(), "estimate() wants exactly four images");
 }
 
+// the same calibration with the target position measured by a tracked pointer (generateCalibratedPointerData of the reference's test)
+static void calibratedPointerCase() {
+  std::printf("CalibratedPointerTargetUSCalibrationParametersEstimator\n");
+  typedef CalibratedPointerTargetUSCalibrationParametersEstimator Est;
+  const double mx = 0.143, my = 0.139, oz = uni(0.2, 1.3), oy = uni(0.2, 1.3), ox = uni(0.2, 1.3);
+  const double cz = std::cos(oz), sz = std::sin(oz), cy = std::cos(oy), sy = std::sin(oy), cx = std::cos(ox), sx = std::sin(ox);
+  const double R3[3][3] = {{cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx}, {sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx}, {-sy, cy * sx, cy * cx}};
+  const double t3[3] = {uni(-100, 100), uni(-100, 100), uni(-100, 100)};
+  std::vector<Est::DataType> data;
+  for (int i = 0; i < 3000; i++) {
+    const double u = uni(0, 640), v = uni(0, 480);
+    Point3D pus, rp;
+    for (int r = 0; r < 3; r++) pus[r] = R3[r][0] * mx * u + R3[r][1] * my * v + t3[r];
+    double q[4] = {gauss(1), gauss(1), gauss(1), gauss(1)};
+    Frame f(uni(-300, 300), uni(-300, 300), uni(-300, 300), q[0], q[1], q[2], q[3], true);
+    f.apply(pus, rp);   // R2 p + t2: the pointer tip in tracker coordinates
+    Est::DataType d;
+    d.T2 = f;
+    d.q[0] = u + gauss(1.0); d.q[1] = v + gauss(1.0);
+    for (int j = 0; j < 3; j++) d.p[j] = rp[j];
+    if (i % 10 >= 7) { d.q[0] = uni(0, 640); d.q[1] = uni(0, 480); }
+    data.push_back(d);
+  }
+  Est est(1.0);
+  std::vector<double> prm;
+  const double frac = RANSAC<Est::DataType, double>::compute(prm, &est, data, 0.999);
+  CHECK(prm.size() == 17 && frac > 0.6, "calibrated-pointer calibration RANSAC (iterative refine)");
+  if (prm.size() == 17) {
+    double e = 0;
+    for (int j = 0; j < 3; j++) e += std::fabs(prm[j] - t3[j]);
+    std::printf("  fraction %.4f  |t3 error|_1 %.4g  m_x %.5f m_y %.5f\n", frac, e, prm[6], prm[7]);
+    CHECK(e < 0.5 && std::fabs(prm[6] - mx) < 1e-3 && std::fabs(prm[7] - my) < 1e-3, "calibration recovered");
+  }
+}
+
 // A user-defined estimator has no GPU path: same failure convention as a degenerate data set.
 class UserEstimator : public ParametersEstimator<Point2D, double> {
  public:
@@ -303,6 +338,7 @@ int main() {
   pivotCase();
   denseCase();
   crossWireCase();
+  calibratedPointerCase();
   std::printf("user-defined estimator\n");
   UserEstimator user;
   std::vector<Point2D> pts(10);
