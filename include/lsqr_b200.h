@@ -50,7 +50,8 @@ typedef enum lsqr_model {
                      * datum = 14 doubles [R2 row-major, t2, u, v]; ls_type 0 = ANALYTIC, 1 = ITERATIVE (Levenberg-Marquardt) */
   LSQR_USCP = 12,   /* CalibratedPointerTargetUSCalibrationParametersEstimator   SinglePointTargetUSCalibrationParametersEstimator.cxx:663-985
                      * datum = 17 doubles [R2 row-major, t2, u, v, p]; ls_type as for LSQR_USXW */
-  LSQR_NUM_MODELS = 13
+  LSQR_SPHERE4 = 13, /* SphereParametersEstimator<4>: the generic-dimension minimal solver (pseudo-inverse, rank test)   SphereParametersEstimator.hxx:169-202 */
+  LSQR_NUM_MODELS = 14
 } lsqr_model;
 
 typedef enum lsqr_status {

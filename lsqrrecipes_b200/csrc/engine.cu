@@ -376,7 +376,7 @@ int refine_impl(lsqr_ctx* ctx, DataSet& ds, int use_mask, double* out_params, in
   }
   double* out_dev = ctx->small_dev + kSmOut;
   // iterative refinement: geometric circle / sphere fit, iterative cross-wire calibration (ls_type 1 in both)
-  const bool geometric = (ctx->model == CIRCLE2 || ctx->model == SPHERE3 || ctx->model == USXW || ctx->model == USCP) && ctx->ls_type == LSQR_LS_GEOMETRIC;
+  const bool geometric = (ctx->model == CIRCLE2 || ctx->model == SPHERE3 || ctx->model == SPHERE4 || ctx->model == USXW || ctx->model == USCP) && ctx->ls_type == LSQR_LS_GEOMETRIC;
   launch_solve_moments(ctx->model, dv, ctx->rb.moments, geometric ? 1 : 0, out_dev, s); ctx->launches++;
   if (geometric) {
     // SphereParametersEstimator.hxx:224-230: algebraic fit as the start, then Levenberg-Marquardt.

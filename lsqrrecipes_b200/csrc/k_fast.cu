@@ -99,6 +99,7 @@ template <int DIM> __device__ __forceinline__ void hoist_sphere(const double* p,
 }
 template <> __device__ __forceinline__ void hoist32<CIRCLE2>(const double* p, const double* c, const EstCfg& cfg, float* q) { hoist_sphere<2>(p, c, cfg, q); }
 template <> __device__ __forceinline__ void hoist32<SPHERE3>(const double* p, const double* c, const EstCfg& cfg, float* q) { hoist_sphere<3>(p, c, cfg, q); }
+template <> __device__ __forceinline__ void hoist32<SPHERE4>(const double* p, const double* c, const EstCfg& cfg, float* q) { hoist_sphere<4>(p, c, cfg, q); }
 template <> __device__ __forceinline__ void hoist32<ABSOR>(const double* p, const double* c, const EstCfg&, float* q) {
   double R[9];
   quat_to_rot(p[0], p[1], p[2], p[3], R);
@@ -182,6 +183,7 @@ __device__ __forceinline__ void load_hyp32(const float* __restrict__ hyp, size_t
     case DENSE6: { CALL(DENSE6); break; }     \
     case USXW: { CALL(USXW); break; }         \
     case USCP: { CALL(USCP); break; }         \
+    case SPHERE4: { CALL(SPHERE4); break; }   \
     default: break;                           \
   }
 
@@ -246,6 +248,11 @@ template <> struct Eval<SPHERE3> {
   static constexpr bool kHasAbsForm = false;
   __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2&) { return sphere_signed<3>(q, x); }
+};
+template <> struct Eval<SPHERE4> {
+  static constexpr bool kHasAbsForm = false;
+  __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2&) { return sphere_signed<4>(q, x); }
 };
 template <> struct Eval<ABSOR> {
   static constexpr bool kHasAbsForm = false;
@@ -582,6 +589,7 @@ template <> struct BlockCB<DENSE5> { static constexpr int R = 8, PPI = 2; };
 template <> struct BlockCB<DENSE6> { static constexpr int R = 8, PPI = 2; };
 template <> struct BlockCB<USXW> { static constexpr int R = 4, PPI = 1; };
 template <> struct BlockCB<USCP> { static constexpr int R = 4, PPI = 1; };
+template <> struct BlockCB<SPHERE4> { static constexpr int R = 8, PPI = 2; };
 
 template <int M>
 static int run_consensus_cb(const DataView& dv, const float* hyp, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms, cudaStream_t s) {
@@ -644,6 +652,7 @@ template <> struct Block32<DENSE5> { static constexpr int R = 6, PPI = 2; };
 template <> struct Block32<DENSE6> { static constexpr int R = 6, PPI = 2; };
 template <> struct Block32<USXW> { static constexpr int R = 3, PPI = 1; };
 template <> struct Block32<USCP> { static constexpr int R = 3, PPI = 1; };
+template <> struct Block32<SPHERE4> { static constexpr int R = 6, PPI = 2; };
 
 int launch_consensus32(int model, const DataView& dv, const float* hyp32, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms,
                        cudaStream_t s) {

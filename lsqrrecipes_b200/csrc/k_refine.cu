@@ -24,6 +24,7 @@ __host__ __device__ inline int n_moments(int model, bool lm) {
     case LINE2D: case LINE2: return 6;
     case CIRCLE2: return lm ? 11 : 9;
     case SPHERE3: return lm ? 16 : 14;
+    case SPHERE4: return lm ? 22 : 20;
     case ABSOR: return 16;
     case RAY: return 10;
     case PIVOT: return 22;
@@ -66,6 +67,7 @@ template <> struct Mom<LINE2D>  { static constexpr int N = 6,  NLM = 0, NPLM = 1
 template <> struct Mom<LINE2>   { static constexpr int N = 6,  NLM = 0, NPLM = 1; };
 template <> struct Mom<CIRCLE2> { static constexpr int N = 9,  NLM = 11, NPLM = 3; };
 template <> struct Mom<SPHERE3> { static constexpr int N = 14, NLM = 16, NPLM = 4; };
+template <> struct Mom<SPHERE4> { static constexpr int N = 20, NLM = 22, NPLM = 5; };
 template <> struct Mom<ABSOR>   { static constexpr int N = 16, NLM = 0, NPLM = 1; };
 template <> struct Mom<RAY>     { static constexpr int N = 10, NLM = 0, NPLM = 1; };
 template <> struct Mom<PIVOT>   { static constexpr int N = 22, NLM = 0, NPLM = 1; };
@@ -122,6 +124,7 @@ template <> __device__ __forceinline__ void accumulate<LINE2D>(const double* q, 
 template <> __device__ __forceinline__ void accumulate<LINE2>(const double* q, double* acc) { acc_scatter<2>(q, acc); }
 template <> __device__ __forceinline__ void accumulate<CIRCLE2>(const double* q, double* acc) { acc_sphere_alg<2>(q, acc); }
 template <> __device__ __forceinline__ void accumulate<SPHERE3>(const double* q, double* acc) { acc_sphere_alg<3>(q, acc); }
+template <> __device__ __forceinline__ void accumulate<SPHERE4>(const double* q, double* acc) { acc_sphere_alg<4>(q, acc); }
 // AbsoluteOrientationParametersEstimator.cxx:134-166: sums of both point sets and of p1 p2^T
 template <> __device__ __forceinline__ void accumulate<ABSOR>(const double* q, double* acc) {
   acc[0] += 1.0;
@@ -364,6 +367,7 @@ __global__ void __launch_bounds__(256, LSQR_MM_CTAS) mask_moments_kernel(DataVie
         if (LM) {
           if constexpr (M == CIRCLE2) acc_sphere_lm<2>(q, lmx, acc);
           if constexpr (M == SPHERE3) acc_sphere_lm<3>(q, lmx, acc);
+          if constexpr (M == SPHERE4) acc_sphere_lm<4>(q, lmx, acc);
           if constexpr (M == USXW) acc_us_lm(q, lmx, acc);
           if constexpr (M == USCP) acc_uscp_lm(q, lmx, acc);
         } else accumulate<M>(q, acc);
@@ -399,6 +403,7 @@ void launch_mask_moments(int model, const DataView& dv, uint32_t begin, uint32_t
   if (lm_state) {
     if (model == CIRCLE2) { BYMODE(CIRCLE2, true); }
     else if (model == SPHERE3) { BYMODE(SPHERE3, true); }
+    else if (model == SPHERE4) { BYMODE(SPHERE4, true); }
     else if (model == USXW) { BYMODE(USXW, true); }
     else if (model == USCP) { BYMODE(USCP, true); }
     return;
@@ -417,6 +422,7 @@ void launch_mask_moments(int model, const DataView& dv, uint32_t begin, uint32_t
     case DENSE6: { BYMODE(DENSE6, false); break; }
     case USXW: { BYMODE(USXW, false); break; }
     case USCP: { BYMODE(USCP, false); break; }
+    case SPHERE4: { BYMODE(SPHERE4, false); break; }
   }
 #undef BYMODE
 #undef LAUNCH
@@ -686,6 +692,7 @@ __global__ void solve_moments_kernel(int model, DataView dv, const double* __res
     case LINE2D: np = solve_line2d(m, c, p); break;
     case CIRCLE2: np = solve_sphere_alg<2>(m, p); if (np && !keep_centred) { p[0] += c[0]; p[1] += c[1]; } break;
     case SPHERE3: np = solve_sphere_alg<3>(m, p); if (np && !keep_centred) { p[0] += c[0]; p[1] += c[1]; p[2] += c[2]; } break;
+    case SPHERE4: np = solve_sphere_alg<4>(m, p); if (np && !keep_centred) { p[0] += c[0]; p[1] += c[1]; p[2] += c[2]; p[3] += c[3]; } break;
     case ABSOR: np = solve_absor(m, c, p); break;
     case RAY: np = solve_ray(m, c, p); break;
     case PIVOT: np = solve_pivot(m, c, p); break;
@@ -817,6 +824,7 @@ template <int NP> __device__ void lm_update(const double* m, double* st, double 
 __device__ void lm_update_model(int model, const double* m, double* st) {
   if (model == CIRCLE2) lm_update<3>(m, st, 1e-8 * 0.01, 500);
   else if (model == SPHERE3) lm_update<4>(m, st, 1e-8 * 0.01, 500);
+  else if (model == SPHERE4) lm_update<5>(m, st, 1e-8 * 0.01, 500);
   else if (model == USXW) lm_update<11>(m, st, 10e-16, 5000);
   else if (model == USCP) lm_update<8>(m, st, 10e-16, 5000);   // iterated to the minimiser (the reference stops at 1e-7)
 }
@@ -860,7 +868,7 @@ __global__ void lm_finish_kernel(int model, DataView dv, const double* __restric
     for (int j = 0; j < 17; j++) out[1 + j] = full[3 + j];
     return;
   }
-  const int dim = (model == CIRCLE2) ? 2 : 3;
+  const int dim = (model == CIRCLE2) ? 2 : (model == SPHERE3 ? 3 : 4);
   out[0] = dim + 1;
   for (int j = 0; j < dim; j++) out[1 + j] = st[LM_X + j] + dv.center[j];
   out[1 + dim] = st[LM_X + dim];
@@ -917,6 +925,7 @@ __device__ void block_moments(const double* pts, uint32_t n, uint32_t ldp, const
       if (lm) {
         if constexpr (M == CIRCLE2) acc_sphere_lm<2>(x, lmx, acc);
         if constexpr (M == SPHERE3) acc_sphere_lm<3>(x, lmx, acc);
+        if constexpr (M == SPHERE4) acc_sphere_lm<4>(x, lmx, acc);
       } else accumulate<M>(x, acc);
     }
   }
@@ -1045,6 +1054,7 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
       case LINE2D: np = solve_line2d(m, c, p); break;
       case CIRCLE2: np = solve_sphere_alg<2>(m, p); break;
       case SPHERE3: np = solve_sphere_alg<3>(m, p); break;
+      case SPHERE4: np = solve_sphere_alg<4>(m, p); break;
       case ABSOR: np = solve_absor(m, c, p); break;
       case RAY: np = solve_ray(m, c, p); break;
       case PIVOT: np = solve_pivot(m, c, p); break;
@@ -1055,7 +1065,7 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
     for (int j = 0; j < np; j++) sh_out[1 + j] = p[j];
   }
   __syncthreads();
-  if constexpr (M == CIRCLE2 || M == SPHERE3) {
+  if constexpr (M == CIRCLE2 || M == SPHERE3 || M == SPHERE4) {
     if (ls_type == 1) {  // geometric: Levenberg-Marquardt from the algebraic fit
       if (threadIdx.x == 0) {
         for (int i = 0; i < LM_SIZE; i++) sh_state[i] = 0.0;
@@ -1071,12 +1081,12 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
         if (threadIdx.x == 0) {
           sh_bcast[0] = sh_state[LM_STATUS];
           const int o = (sh_state[LM_PHASE] != 0.0) ? LM_TRIAL : LM_X;
-          for (int j = 0; j < 4; j++) sh_bcast[1 + j] = sh_state[o + j];
+          for (int j = 0; j < 5; j++) sh_bcast[1 + j] = sh_state[o + j];
         }
         __syncthreads();
-        double lmx[4];
+        double lmx[5];
         const double status = sh_bcast[0];
-        for (int j = 0; j < 4; j++) lmx[j] = sh_bcast[1 + j];
+        for (int j = 0; j < 5; j++) lmx[j] = sh_bcast[1 + j];
         __syncthreads();
         if (status != 0.0) break;
         block_moments<M>(pts, n, ldp, hq, cfg, lmx, true, 1, nullptr, sh_part, sh_mom);
@@ -1106,6 +1116,7 @@ int launch_batch(const BatchArgs& a, const EstCfg& cfg, int ls_type, cudaStream_
     case LINE3: CALL(LINE3) break;
     case CIRCLE2: CALL(CIRCLE2) break;
     case SPHERE3: CALL(SPHERE3) break;
+    case SPHERE4: CALL(SPHERE4) break;
     case ABSOR: CALL(ABSOR) break;
     case RAY: CALL(RAY) break;
     case PIVOT: CALL(PIVOT) break;

@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(128) solve_kernel(SolveArgs a, const double* _
     case DENSE6: { CALL(DENSE6); break; }     \
     case USXW: { CALL(USXW); break; }         \
     case USCP: { CALL(USCP); break; }         \
+    case SPHERE4: { CALL(SPHERE4); break; }   \
     default: break;                           \
   }
 

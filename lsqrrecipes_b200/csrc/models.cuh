@@ -14,7 +14,7 @@
 
 namespace lsqr {
 
-enum : int { PLANE3 = 0, LINE2D = 1, LINE2 = 2, LINE3 = 3, CIRCLE2 = 4, SPHERE3 = 5, ABSOR = 6, RAY = 7, PIVOT = 8, DENSE5 = 9, DENSE6 = 10, USXW = 11, USCP = 12, NUM_MODELS = 13 };
+enum : int { PLANE3 = 0, LINE2D = 1, LINE2 = 2, LINE3 = 3, CIRCLE2 = 4, SPHERE3 = 5, ABSOR = 6, RAY = 7, PIVOT = 8, DENSE5 = 9, DENSE6 = 10, USXW = 11, USCP = 12, SPHERE4 = 13, NUM_MODELS = 14 };
 
 // dim = doubles per datum, P = parameters, K = minimal subset, HQ = doubles of a prepared
 // fp64 hypothesis, Q32 = floats of a hoisted fp32 hypothesis.
@@ -37,6 +37,7 @@ template <> struct Model<USXW>    { static constexpr int D = 14, P = 20, K = 4, 
 // CalibratedPointerTargetUSCalibrationParametersEstimator: datum = [R2 (9), t2 (3), u, v, p (3)],
 // parameters [t3, omega_z, omega_y, omega_x, m_x, m_y, m_x R3(:,1), m_y R3(:,2), R3(:,3)]
 template <> struct Model<USCP>    { static constexpr int D = 17, P = 17, K = 3, HQ = 9,  Q32 = 9;  };
+template <> struct Model<SPHERE4> { static constexpr int D = 4,  P = 5, K = 5, HQ = 5,  Q32 = 6;  };
 
 struct ModelInfo { int D, P, K, HQ, Q32; };
 __host__ __device__ inline ModelInfo model_info(int m) {
@@ -54,6 +55,7 @@ __host__ __device__ inline ModelInfo model_info(int m) {
     case DENSE6:  return {7, 6, 6, 6, 7};
     case USXW:    return {14, 20, 4, 12, 12};
     case USCP:    return {17, 17, 3, 9, 9};
+    case SPHERE4: return {4, 5, 5, 5, 6};
   }
   return {0, 0, 0, 0, 0};
 }
@@ -425,6 +427,21 @@ template <> __device__ inline bool estimate<USXW>(const double* d, const EstCfg&
   return us_post(x, prm);
 }
 
+// SphereParametersEstimator.hxx:169-202 (estimateND, every dimension other than 2 and 3): rows p0 - p_i, pseudo-inverse
+// with singular values <= EPS zeroed; rank < dim means the points lie in a hyperplane.
+template <> __device__ inline bool estimate<SPHERE4>(const double* d, const EstCfg&, double* prm) {
+  double A[16], b[4], x[4];
+  for (int i = 0; i < 4; i++) {
+    b[i] = 0.0;
+    for (int j = 0; j < 4; j++) { A[i * 4 + j] = d[j] - d[(i + 1) * 4 + j]; b[i] += A[i * 4 + j] * (d[j] + d[(i + 1) * 4 + j]); }
+  }
+  if (pinv_solve<4, 4>(A, b, kSphereEps, x) < 4) return false;
+  double rSquared = 0.0;
+  for (int i = 0; i < 4; i++) { prm[i] = x[i] * 0.5; rSquared += (d[i] - prm[i]) * (d[i] - prm[i]); }
+  prm[4] = sqrt(rSquared);
+  return true;
+}
+
 // SinglePointTargetUSCalibrationParametersEstimator.cxx:789-920 with three data: rows [u R2, v R2, R2] x = p - t2,
 // singular values <= FLT_EPSILON zeroed, rank < 9 fails.
 template <> __device__ inline bool estimate<USCP>(const double* d, const EstCfg&, double* prm) {
@@ -505,6 +522,7 @@ template <int DIM> __device__ __forceinline__ bool agree_sphere(const double* h,
 }
 template <> __device__ __forceinline__ bool agree<CIRCLE2>(const double* h, const double* x, const EstCfg& c) { return agree_sphere<2>(h, x, c); }
 template <> __device__ __forceinline__ bool agree<SPHERE3>(const double* h, const double* x, const EstCfg& c) { return agree_sphere<3>(h, x, c); }
+template <> __device__ __forceinline__ bool agree<SPHERE4>(const double* h, const double* x, const EstCfg& c) { return agree_sphere<4>(h, x, c); }
 // AbsoluteOrientationParametersEstimator.cxx:316-327 with Frame::apply, common/Frame.cxx:229-248
 template <> __device__ __forceinline__ bool agree<ABSOR>(const double* h, const double* x, const EstCfg& cfg) {
   const double qx = h[0] * x[0] + h[1] * x[1] + h[2] * x[2] + h[9];

@@ -88,15 +88,15 @@ class Line2DParametersEstimator(ParametersEstimator):
 
 
 class SphereParametersEstimator(ParametersEstimator):
-    """SphereParametersEstimator<dimension> for dimension 2 (circle) or 3 (SphereParametersEstimator.h:29-190)."""
+    """SphereParametersEstimator<dimension> for dimension 2 (circle), 3 or 4 (SphereParametersEstimator.h:29-190)."""
     ALGEBRAIC, GEOMETRIC = api.LS_ALGEBRAIC, api.LS_GEOMETRIC
 
     def __init__(self, delta, lsType=api.LS_GEOMETRIC, dimension=3):
         if lsType not in (self.ALGEBRAIC, self.GEOMETRIC):
             raise ValueError("lsType must be ALGEBRAIC or GEOMETRIC")  # SphereParametersEstimator.hxx:17-18 throws
-        if dimension not in (2, 3):
-            raise NotImplementedError("hyperspheres are accelerated for d = 2, 3")
-        self._model = "circle2" if dimension == 2 else "sphere3"
+        if dimension not in (2, 3, 4):
+            raise NotImplementedError("hyperspheres are accelerated for d = 2, 3, 4")
+        self._model = {2: "circle2", 3: "sphere3", 4: "sphere4"}[dimension]
         super().__init__(dimension + 1, delta, ls_type=lsType)
 
     def setLeastSquaresType(self, lsType):

@@ -21,7 +21,7 @@
 #include <omp.h>
 #endif
 
-enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10, M_USXW = 11, M_USCP = 12 };
+enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10, M_USXW = 11, M_USCP = 12, M_SPHERE4 = 13 };
 
 /* common/Epsilon.h:19 */
 static const double EPS = 2.220446049250313e-016;
@@ -32,8 +32,8 @@ static const double FRAME_SMALL_ANGLE = 0.008726535498373935;
 static const double FRAME_HALF_PI = 3.14159265358979323846 / 2.0;
 
 int orc_model_info(int model, int* D, int* P, int* k) {
-  static const int tab[13][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}, {6, 5, 5}, {7, 6, 6}, {14, 20, 4}, {17, 17, 3}};
-  if (model < 0 || model > 12) return -1;
+  static const int tab[14][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}, {6, 5, 5}, {7, 6, 6}, {14, 20, 4}, {17, 17, 3}, {4, 5, 5}};
+  if (model < 0 || model > 13) return -1;
   *D = tab[model][0]; *P = tab[model][1]; *k = tab[model][2];
   return 0;
 }
@@ -308,6 +308,20 @@ static int triad(const double* P0, const double* P1, const double* P2, double Rm
 }
 
 /* AbsoluteOrientationParametersEstimator.cxx:14-101 */
+/* SphereParametersEstimator.hxx:169-202 (estimateND, dimensions other than 2 and 3): rows p0 - p_i, pseudo-inverse with
+ * singular values <= EPS zeroed, rank < dim -> coplanar points */
+static int sphere_nd_estimate(int dim, const double* d, double* prm) {
+  double A[36], b[6] = {0, 0, 0, 0, 0, 0}, x[6], rSquared = 0.0;
+  int i, j, rank;
+  for (i = 0; i < dim; i++)
+    for (j = 0; j < dim; j++) { A[i * dim + j] = d[j] - d[(i + 1) * dim + j]; b[i] += A[i * dim + j] * (d[j] + d[(i + 1) * dim + j]); }
+  rank = pinv_solve(dim, dim, A, b, EPS, x);
+  if (rank < dim) return 0;
+  for (i = 0; i < dim; i++) { x[i] = x[i] * 0.5; prm[i] = x[i]; rSquared += (d[i] - x[i]) * (d[i] - x[i]); }
+  prm[dim] = sqrt(rSquared);
+  return dim + 1;
+}
+
 static int absor_estimate(const double* d, double* prm) {
   double R1[9], R2[9], R[9], m1[3], m2[3], t[3], q[4];
   int i, j, k;
@@ -728,6 +742,7 @@ int orc_estimate(int model, double delta, double aux, const double* data, size_t
     case M_LINE3: return line_estimate(3, data, delta * delta, params);
     case M_CIRCLE2: return circle_estimate(data, params);
     case M_SPHERE3: return sphere3_estimate(data, params);
+    case M_SPHERE4: return sphere_nd_estimate(4, data, params);
     case M_ABSOR: return absor_estimate(data, params);
     case M_RAY: return ray_estimate(data, ray_cross_eps(aux), params);
     case M_PIVOT: return pivot_solve(data, 3, params);
@@ -763,8 +778,9 @@ static int agree1(int model, double delta, const double* prm, const double* x) {
       return ds < delta * delta;
     }
     case M_CIRCLE2:
-    case M_SPHERE3: { /* SphereParametersEstimator.hxx:255-264 (distance vs delta, not squared) */
-      int dim = (model == M_CIRCLE2) ? 2 : 3, i;
+    case M_SPHERE3:
+    case M_SPHERE4: { /* SphereParametersEstimator.hxx:255-264 (distance vs delta, not squared) */
+      int dim = (model == M_CIRCLE2) ? 2 : (model == M_SPHERE3 ? 3 : 4), i;
       double dl = 0;
       for (i = 0; i < dim; i++) dl += ((x[i] - prm[i]) * (x[i] - prm[i]));
       dl = fabs(sqrt(dl) - prm[dim]);
@@ -864,7 +880,7 @@ static int line2d_lsq(const double* d, size_t n, double* prm) {
 static int sphere_algebraic(int dim, const double* d, size_t n, double* prm) {
   int cols = dim + 1, j, rank;
   size_t i;
-  double x[4], rSquared;
+  double x[5], rSquared;
   double* A = (double*)malloc(sizeof(double) * n * cols);
   double* b = (double*)calloc(n, sizeof(double));
   for (i = 0; i < n; i++) {
@@ -900,7 +916,7 @@ static double sphere_cost(int dim, const double* d, size_t n, const double* x, d
   int p = dim + 1, a, b2, j; size_t i; double cost = 0;
   if (JtJ) { memset(JtJ, 0, sizeof(double) * p * p); memset(Jtr, 0, sizeof(double) * p); }
   for (i = 0; i < n; i++) {
-    double sq = 0, sv, r, J[4];
+    double sq = 0, sv, r, J[5];
     for (j = 0; j < dim; j++) sq += (d[i * dim + j] - x[j]) * (d[i * dim + j] - x[j]);
     sv = sqrt(sq);
     r = sv - x[dim];
@@ -922,7 +938,7 @@ static int sphere_geometric(int dim, const double* d, size_t n, const double* in
   const double xtol = 10e-16, gtol = 10e-16, ftol = 1e-8 * 0.01;
   const int maxfev = 500;
   int p = dim + 1, a, evals = 1, ok = 0;
-  double x[4], xn[4], A[16], g[4], M[16], h[4], dsc[4], cost, lambda = -1, nu = 2;
+  double x[5], xn[5], A[25], g[5], M[25], h[5], dsc[5], cost, lambda = -1, nu = 2;
   for (a = 0; a < p; a++) x[a] = init[a];
   cost = sphere_cost(dim, d, n, x, NULL, NULL);
   while (evals < maxfev && !ok) {
@@ -962,7 +978,7 @@ static int sphere_geometric(int dim, const double* d, size_t n, const double* in
 
 /* SphereParametersEstimator.hxx:209-232 */
 static int sphere_lsq(int dim, int ls_type, const double* d, size_t n, double* prm) {
-  double init[4];
+  double init[5];
   if (ls_type == 0) return sphere_algebraic(dim, d, n, prm);
   if (!sphere_algebraic(dim, d, n, init)) return 0;
   return sphere_geometric(dim, d, n, init, prm);
@@ -1047,6 +1063,7 @@ int orc_least_squares(int model, double delta, double aux, int ls_type, const do
     case M_LINE3: return cov_eig_estimate(3, 2, data, n, params);
     case M_CIRCLE2: return sphere_lsq(2, ls_type, data, n, params);
     case M_SPHERE3: return sphere_lsq(3, ls_type, data, n, params);
+    case M_SPHERE4: return sphere_lsq(4, ls_type, data, n, params);
     case M_ABSOR: return absor_lsq(data, n, params);
     case M_RAY: return ray_lsq(data, n, params);
     case M_PIVOT: return pivot_solve(data, n, params);

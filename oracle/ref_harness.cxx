@@ -37,7 +37,7 @@
 
 using namespace lsqrRecipes;
 
-enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10, M_USXW = 11, M_USCP = 12 };
+enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10, M_USXW = 11, M_USCP = 12, M_SPHERE4 = 13 };
 
 namespace {
 
@@ -113,6 +113,7 @@ template <class F> int dispatch(const Cfg& c, F& f) {
     case M_LINE3: { LineParametersEstimator<3> e(c.delta); return f(&e, (Point3D*)0); }
     case M_CIRCLE2: { SphereParametersEstimator<2> e(c.delta, c.ls_type == 0 ? SphereParametersEstimator<2>::ALGEBRAIC : SphereParametersEstimator<2>::GEOMETRIC); return f(&e, (Point2D*)0); }
     case M_SPHERE3: { SphereParametersEstimator<3> e(c.delta, c.ls_type == 0 ? SphereParametersEstimator<3>::ALGEBRAIC : SphereParametersEstimator<3>::GEOMETRIC); return f(&e, (Point3D*)0); }
+    case M_SPHERE4: { typedef Point<double, 4> Point4D; SphereParametersEstimator<4> e(c.delta, c.ls_type == 0 ? SphereParametersEstimator<4>::ALGEBRAIC : SphereParametersEstimator<4>::GEOMETRIC); return f(&e, (Point4D*)0); }
     case M_ABSOR: { AbsoluteOrientationParametersEstimator e(c.delta); return f(&e, (PointPair*)0); }
     case M_RAY: { if (c.aux > 0) { RayIntersectionParametersEstimator e(c.delta, c.aux); return f(&e, (Ray3D*)0); } RayIntersectionParametersEstimator e(c.delta); return f(&e, (Ray3D*)0); }
     case M_PIVOT: { PivotCalibrationEstimator e(c.delta); return f(&e, (Frame*)0); }
@@ -202,8 +203,8 @@ struct RansacOp {
 extern "C" {
 
 int ref_model_info(int model, int* D, int* P, int* k) {
-  static const int tab[13][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}, {6, 5, 5}, {7, 6, 6}, {14, 20, 4}, {17, 17, 3}};
-  if (model < 0 || model > 12) return -1;
+  static const int tab[14][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}, {6, 5, 5}, {7, 6, 6}, {14, 20, 4}, {17, 17, 3}, {4, 5, 5}};
+  if (model < 0 || model > 13) return -1;
   *D = tab[model][0]; *P = tab[model][1]; *k = tab[model][2];
   return 0;
 }

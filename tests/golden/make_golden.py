@@ -41,7 +41,7 @@ def main():
         ns = 28
         small, _ = synth.GENERATORS[name](ns, seed=synth.SEED + 200 + m)
         fx = {"data": data, "delta": delta, "subsets": subsets, "counts": counts, "params": params, "true": true, "small": small}
-        for ls_type in ([0, 1] if name in ("circle2", "sphere3", "usxw", "uscp") else [1]):
+        for ls_type in ([0, 1] if name in ("circle2", "sphere3", "sphere4", "usxw", "uscp") else [1]):
             prm, mask, frac, cnt, _ = ref.ransac_exhaustive(m, delta, small, ls_type=ls_type)
             fx[f"ex_params_ls{ls_type}"] = prm
             fx[f"ex_mask_ls{ls_type}"] = mask

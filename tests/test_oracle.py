@@ -10,10 +10,10 @@ from lsqrrecipes_b200 import synth
 from oracle.pyoracle import INFO, MODELS
 
 ALL = list(MODELS.items())
-PINV_MODELS = ("pivot", "dense5", "dense6", "usxw", "uscp")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
+PINV_MODELS = ("pivot", "dense5", "dense6", "usxw", "uscp", "sphere4")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
 # ... where "rounding level" scales with the conditioning of the minimal system (the 9x9 / 12x12 calibration systems of
 # random subsets reach 1e7)
-PINV_TOL = {"pivot": 1e-9, "dense5": 1e-9, "dense6": 1e-9, "usxw": 1e-6, "uscp": 1e-6}
+PINV_TOL = {"pivot": 1e-9, "dense5": 1e-9, "dense6": 1e-9, "usxw": 1e-6, "uscp": 1e-6, "sphere4": 1e-6}
 
 
 # ---- the reference's own literal test vectors -------------------------------------------
@@ -71,7 +71,7 @@ def test_port_matches_reference_fixture(port, name, m):
 @pytest.mark.parametrize("name,m", ALL)
 def test_port_exhaustive_and_lsq_fixture(port, name, m):
     g = golden(name)
-    for ls_type in ([0, 1] if name in ("circle2", "sphere3", "usxw", "uscp") else [1]):
+    for ls_type in ([0, 1] if name in ("circle2", "sphere3", "sphere4", "usxw", "uscp") else [1]):
         # the cross-wire LM runs on vector residuals here and on the reference's scalar |e_i| residuals there:
         # same minimum, compared at the north star's 1e-6 relative for converged Levenberg-Marquardt results
         tol = 1e-6 if (name == "usxw" and ls_type == 1) else 1e-8

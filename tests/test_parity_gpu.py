@@ -19,15 +19,15 @@ pytestmark = pytest.mark.gpu
 from lsqrrecipes_b200 import MODELS as ENGINE_MODELS
 
 ALL = [(n, m) for n, m in MODELS.items() if n in ENGINE_MODELS]   # every estimator the engine implements
-PINV_MODELS = ("pivot", "dense5", "dense6", "usxw", "uscp")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
+PINV_MODELS = ("pivot", "dense5", "dense6", "usxw", "uscp", "sphere4")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
 # ... where "rounding level" scales with the conditioning of the minimal system (the 9x9 / 12x12 calibration systems of
 # random subsets reach 1e7)
-PINV_TOL = {"pivot": 1e-9, "dense5": 1e-9, "dense6": 1e-9, "usxw": 1e-6, "uscp": 1e-6}
+PINV_TOL = {"pivot": 1e-9, "dense5": 1e-9, "dense6": 1e-9, "usxw": 1e-6, "uscp": 1e-6, "sphere4": 1e-6}
 REFINE_TOL = 1e-6
 
 
 def _ls_types(name):
-    return [0, 1] if name in ("circle2", "sphere3", "usxw", "uscp") else [1]
+    return [0, 1] if name in ("circle2", "sphere3", "sphere4", "usxw", "uscp") else [1]
 
 
 @pytest.mark.parametrize("name,m", ALL)
@@ -178,6 +178,37 @@ def test_crosswire_operator_interface(port):
     assert np.abs(np.array(prm[:6]) - true[:6]).max() < 0.5 and abs(prm[9] - 0.143) < 1e-3 and abs(prm[10] - 0.139) < 1e-3
 
 
+def test_hypersphere_4d_as_the_reference_tests_it(port):
+    """testing/SphereParametersEstimatorTest.cxx:379-428 (testnD<4>, "covers all the code for dimensionality greater than
+    3"): 50 points on a random 4-D sphere, coordinates up to 1000, unit noise; the minimal estimate from clean data and
+    both least-squares fits must land within 3 sigma of the known [c, r]."""
+    from lsqrrecipes_b200 import SphereParametersEstimator as Est
+    rng = np.random.default_rng(404)
+    c, r = rng.uniform(-1000, 1000, 4), rng.uniform(0, 1000)
+    u = rng.uniform(-1, 1, (50, 4))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    clean = c + r * u
+    noisy = clean + rng.normal(0, 1.0, (50, 4))
+    true = np.append(c, r)
+    est = Est(0.5, dimension=4)
+    prm = []
+    est.estimate(clean[:5], prm)
+    assert len(prm) == 5 and np.abs(np.array(prm) - true).max() < 3.0
+    assert np.allclose(prm, port.estimate(MODELS["sphere4"], 0.5, clean[:5]), rtol=1e-9, atol=1e-7)
+    for ls_type in (Est.ALGEBRAIC, Est.GEOMETRIC):
+        est.setLeastSquaresType(ls_type)
+        prm = []
+        est.leastSquaresEstimate(noisy, prm)
+        assert len(prm) == 5 and np.abs(np.array(prm) - true).max() < 3.0
+        assert np.allclose(prm, port.least_squares(MODELS["sphere4"], 0.5, noisy, ls_type), rtol=REFINE_TOL, atol=REFINE_TOL)
+    # five points in a hyperplane: rank < 4, no sphere (SphereParametersEstimator.hxx:190-191)
+    flat = clean[:5].copy()
+    flat[:, 3] = 7.0
+    prm = [1.0]
+    est.estimate(flat, prm)
+    assert prm == []
+
+
 def test_circle_agree_literals():
     """testing/SphereParametersEstimatorTest.cxx:280-296"""
     eng = Engine("circle2", 0.5)
@@ -241,7 +272,7 @@ def _residual64(name, prm, data, delta):
         v = data - p[d:]
         w = v - (v @ p[:d])[:, None] * p[:d]
         return np.linalg.norm(w, axis=1), delta
-    if name in ("circle2", "sphere3"):
+    if name in ("circle2", "sphere3", "sphere4"):
         d = data.shape[1]
         return np.abs(np.linalg.norm(data - p[:d], axis=1) - p[d]), delta
     if name == "absor":
@@ -386,7 +417,7 @@ def test_edge_cases_match_reference_conventions():
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["line2d", "plane3", "sphere3", "dense5"])
+@pytest.mark.parametrize("name", ["line2d", "plane3", "sphere3", "sphere4", "dense5"])
 def test_batched_small_problems_vs_oracle(port, name):
     """BASELINE.json configs[4]: many independent small problems, one thread block each.  Exhaustive mode is
     bit-comparable with the reference's brute-force driver run per problem."""
@@ -413,7 +444,8 @@ def test_batched_small_problems_vs_oracle(port, name):
     # randomized mode: consensus at least as large as the generating inlier set minus noise tail
     out2 = eng.ransac_batch(np.concatenate(chunks), offsets, exhaustive=False, prob=0.999, max_tries=4096, seed=9)
     ok = [i for i, s in enumerate(sizes) if s > 2 * k]
-    assert np.mean(out2["counts"][ok] >= 0.8 * out["counts"][ok]) > 0.9
+    # (five noisy points pin a 4-D sphere loosely, so the stopping rule of RANSAC.hxx:121-126 ends further from the optimum)
+    assert np.mean(out2["counts"][ok] >= (0.7 if name == "sphere4" else 0.8) * out["counts"][ok]) > 0.9
     eng.close()
 
 

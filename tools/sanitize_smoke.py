@@ -13,7 +13,7 @@ big = "--big" in sys.argv
 for name in MODELS:
     n = 3000
     data, true = synth.GENERATORS[name](n, seed=5)
-    for ls in ([0, 1] if name in ("circle2", "sphere3", "usxw", "uscp") else [1]):
+    for ls in ([0, 1] if name in ("circle2", "sphere3", "sphere4", "usxw", "uscp") else [1]):
         eng = Engine(name, synth.DELTAS[name], ls_type=ls)
         eng.upload(data)
         r64 = eng.score(count=700, precision=FP64, seed=1, want_counts=True, want_params=True)
