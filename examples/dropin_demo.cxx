@@ -130,6 +130,60 @@ static void sphereCase() {
   CHECK(threw, "invalid least-squares type throws from the constructor (SphereParametersEstimator.hxx:17-18)");
 }
 
+// Dimension 4 takes the reference's generic-dimension branches: pseudo-inverse minimal solver for the hypersphere
+// (SphereParametersEstimator.hxx:169-202, what testing/SphereParametersEstimatorTest.cxx:379-428 exercises) and the
+// null-space solver for the hyperplane (PlaneParametersEstimator.hxx:70-108).
+static void fourDCase() {
+  std::printf("SphereParametersEstimator<4>, PlaneParametersEstimator<4>\n");
+  typedef Point<double, 4> Point4D;
+  const double c[4] = {uni(-500, 500), uni(-500, 500), uni(-500, 500), uni(-500, 500)}, r = uni(100, 500);
+  std::vector<Point4D> data, exact;
+  for (int i = 0; i < 40000; i++) {
+    Point4D p, q;
+    double u[4], un = 0;
+    for (int j = 0; j < 4; j++) { u[j] = uni(-1, 1); un += u[j] * u[j]; }
+    un = std::sqrt(un);
+    for (int j = 0; j < 4; j++) { q[j] = c[j] + r * u[j] / un; p[j] = (i % 10 < 6) ? q[j] + gauss(0.4) : uni(-1000, 1000); }
+    data.push_back(p);
+    if (exact.size() < 5) exact.push_back(q);
+  }
+  SphereParametersEstimator<4> sph(0.5);
+  std::vector<double> prm;
+  sph.estimate(exact, prm);
+  CHECK(prm.size() == 5, "estimate() from five points");
+  if (prm.size() == 5) CHECK(std::fabs(prm[0] - c[0]) + std::fabs(prm[1] - c[1]) + std::fabs(prm[2] - c[2]) + std::fabs(prm[3] - c[3]) + std::fabs(prm[4] - r) < 1e-6, "exact 4-D sphere through noise-free points");
+  const double frac = RANSAC<Point4D, double>::compute(prm, &sph, data, 0.999);
+  CHECK(prm.size() == 5 && frac > 0.2, "4-D sphere RANSAC, geometric LS");
+  if (prm.size() == 5) {
+    const double e = std::fabs(prm[0] - c[0]) + std::fabs(prm[1] - c[1]) + std::fabs(prm[2] - c[2]) + std::fabs(prm[3] - c[3]) + std::fabs(prm[4] - r);
+    std::printf("  sphere: fraction %.4f  |error|_1 %.4g\n", frac, e);
+    CHECK(e < 0.5, "refined 4-D sphere matches the generating sphere");
+  }
+
+  double n[4], nn = 0;
+  for (int j = 0; j < 4; j++) { n[j] = uni(0, 1); nn += n[j] * n[j]; }
+  nn = std::sqrt(nn);
+  for (int j = 0; j < 4; j++) n[j] /= nn;
+  const double a[4] = {uni(-500, 500), uni(-500, 500), uni(-500, 500), uni(-500, 500)};
+  std::vector<Point4D> pdata;
+  for (int i = 0; i < 40000; i++) {
+    Point4D p;
+    double t = 0;
+    for (int j = 0; j < 4; j++) { p[j] = uni(-1000, 1000); t += (p[j] - a[j]) * n[j]; }
+    if (i % 10 < 6) for (int j = 0; j < 4; j++) p[j] += -t * n[j] + gauss(0.2);
+    pdata.push_back(p);
+  }
+  PlaneParametersEstimator<4> pl(0.5);
+  const double pfrac = RANSAC<Point4D, double>::compute(prm, &pl, pdata, 0.999);
+  CHECK(prm.size() == 8 && pfrac > 0.5, "4-D hyperplane RANSAC");
+  if (prm.size() == 8) {
+    double dot = 0, off = 0;
+    for (int j = 0; j < 4; j++) { dot += prm[j] * n[j]; off += (prm[4 + j] - a[j]) * n[j]; }
+    std::printf("  hyperplane: fraction %.4f  |n.n_true| %.8f  offset %.4g\n", pfrac, std::fabs(dot), off);
+    CHECK(std::fabs(std::fabs(dot) - 1) < 1e-6 && std::fabs(off) < 0.05, "refined hyperplane matches the generating one");
+  }
+}
+
 static void absorCase() {
   std::printf("AbsoluteOrientationParametersEstimator\n");
   Frame T(uni(-1000, 1000), uni(-1000, 1000), uni(-1000, 1000), 0.5, 0.5, -0.5, 0.5, true);
@@ -333,6 +387,7 @@ int main() {
   planeCase();
   line2dCase();
   sphereCase();
+  fourDCase();
   absorCase();
   rayCase();
   pivotCase();

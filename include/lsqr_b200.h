@@ -51,7 +51,8 @@ typedef enum lsqr_model {
   LSQR_USCP = 12,   /* CalibratedPointerTargetUSCalibrationParametersEstimator   SinglePointTargetUSCalibrationParametersEstimator.cxx:663-985
                      * datum = 17 doubles [R2 row-major, t2, u, v, p]; ls_type as for LSQR_USXW */
   LSQR_SPHERE4 = 13, /* SphereParametersEstimator<4>: the generic-dimension minimal solver (pseudo-inverse, rank test)   SphereParametersEstimator.hxx:169-202 */
-  LSQR_NUM_MODELS = 14
+  LSQR_PLANE4 = 14,  /* PlaneParametersEstimator<4>: the generic-dimension minimal solver (null space of [p_i, -1])   PlaneParametersEstimator.hxx:70-108 */
+  LSQR_NUM_MODELS = 15
 } lsqr_model;
 
 typedef enum lsqr_status {

@@ -79,6 +79,11 @@ template <> __device__ __forceinline__ void hoist32<PLANE3>(const double* p, con
   q[0] = (float)p[0]; q[1] = (float)p[1]; q[2] = (float)p[2];
   q[3] = (float)(-(p[0] * (p[3] - c[0]) + p[1] * (p[4] - c[1]) + p[2] * (p[5] - c[2])));
 }
+template <> __device__ __forceinline__ void hoist32<PLANE4>(const double* p, const double* c, const EstCfg&, float* q) {
+  double s = 0;
+  for (int i = 0; i < 4; i++) { q[i] = (float)p[i]; s += p[i] * (p[4 + i] - c[i]); }
+  q[4] = (float)(-s);
+}
 template <> __device__ __forceinline__ void hoist32<LINE2D>(const double* p, const double* c, const EstCfg&, float* q) {
   q[0] = (float)p[0]; q[1] = (float)p[1];
   q[2] = (float)(-(p[0] * (p[2] - c[0]) + p[1] * (p[3] - c[1])));
@@ -184,6 +189,7 @@ __device__ __forceinline__ void load_hyp32(const float* __restrict__ hyp, size_t
     case USXW: { CALL(USXW); break; }         \
     case USCP: { CALL(USCP); break; }         \
     case SPHERE4: { CALL(SPHERE4); break; }   \
+    case PLANE4: { CALL(PLANE4); break; }     \
     default: break;                           \
   }
 
@@ -203,6 +209,11 @@ template <int M> struct Eval;
 template <> struct Eval<PLANE3> {
   static constexpr bool kHasAbsForm = true;
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return fma2(q[0], x[0], fma2(q[1], x[1], fma2(q[2], x[2], q[3]))); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
+};
+template <> struct Eval<PLANE4> {
+  static constexpr bool kHasAbsForm = true;
+  __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return fma2(q[0], x[0], fma2(q[1], x[1], fma2(q[2], x[2], fma2(q[3], x[3], q[4])))); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
 };
 template <> struct Eval<LINE2D> {
@@ -590,6 +601,7 @@ template <> struct BlockCB<DENSE6> { static constexpr int R = 8, PPI = 2; };
 template <> struct BlockCB<USXW> { static constexpr int R = 4, PPI = 1; };
 template <> struct BlockCB<USCP> { static constexpr int R = 4, PPI = 1; };
 template <> struct BlockCB<SPHERE4> { static constexpr int R = 8, PPI = 2; };
+template <> struct BlockCB<PLANE4> { static constexpr int R = 8, PPI = 2; };
 
 template <int M>
 static int run_consensus_cb(const DataView& dv, const float* hyp, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms, cudaStream_t s) {
@@ -653,6 +665,7 @@ template <> struct Block32<DENSE6> { static constexpr int R = 6, PPI = 2; };
 template <> struct Block32<USXW> { static constexpr int R = 3, PPI = 1; };
 template <> struct Block32<USCP> { static constexpr int R = 3, PPI = 1; };
 template <> struct Block32<SPHERE4> { static constexpr int R = 6, PPI = 2; };
+template <> struct Block32<PLANE4> { static constexpr int R = 8, PPI = 2; };
 
 int launch_consensus32(int model, const DataView& dv, const float* hyp32, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms,
                        cudaStream_t s) {

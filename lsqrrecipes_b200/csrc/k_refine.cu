@@ -25,6 +25,7 @@ __host__ __device__ inline int n_moments(int model, bool lm) {
     case CIRCLE2: return lm ? 11 : 9;
     case SPHERE3: return lm ? 16 : 14;
     case SPHERE4: return lm ? 22 : 20;
+    case PLANE4: return 15;
     case ABSOR: return 16;
     case RAY: return 10;
     case PIVOT: return 22;
@@ -68,6 +69,7 @@ template <> struct Mom<LINE2>   { static constexpr int N = 6,  NLM = 0, NPLM = 1
 template <> struct Mom<CIRCLE2> { static constexpr int N = 9,  NLM = 11, NPLM = 3; };
 template <> struct Mom<SPHERE3> { static constexpr int N = 14, NLM = 16, NPLM = 4; };
 template <> struct Mom<SPHERE4> { static constexpr int N = 20, NLM = 22, NPLM = 5; };
+template <> struct Mom<PLANE4>  { static constexpr int N = 15, NLM = 0, NPLM = 1; };
 template <> struct Mom<ABSOR>   { static constexpr int N = 16, NLM = 0, NPLM = 1; };
 template <> struct Mom<RAY>     { static constexpr int N = 10, NLM = 0, NPLM = 1; };
 template <> struct Mom<PIVOT>   { static constexpr int N = 22, NLM = 0, NPLM = 1; };
@@ -119,6 +121,7 @@ template <int DIM> __device__ __forceinline__ void acc_sphere_lm(const double* q
 
 template <int M> __device__ __forceinline__ void accumulate(const double* q, double* acc);
 template <> __device__ __forceinline__ void accumulate<PLANE3>(const double* q, double* acc) { acc_scatter<3>(q, acc); }
+template <> __device__ __forceinline__ void accumulate<PLANE4>(const double* q, double* acc) { acc_scatter<4>(q, acc); }
 template <> __device__ __forceinline__ void accumulate<LINE3>(const double* q, double* acc) { acc_scatter<3>(q, acc); }
 template <> __device__ __forceinline__ void accumulate<LINE2D>(const double* q, double* acc) { acc_scatter<2>(q, acc); }
 template <> __device__ __forceinline__ void accumulate<LINE2>(const double* q, double* acc) { acc_scatter<2>(q, acc); }
@@ -423,6 +426,7 @@ void launch_mask_moments(int model, const DataView& dv, uint32_t begin, uint32_t
     case USXW: { BYMODE(USXW, false); break; }
     case USCP: { BYMODE(USCP, false); break; }
     case SPHERE4: { BYMODE(SPHERE4, false); break; }
+    case PLANE4: { BYMODE(PLANE4, false); break; }
   }
 #undef BYMODE
 #undef LAUNCH
@@ -687,6 +691,7 @@ __global__ void solve_moments_kernel(int model, DataView dv, const double* __res
   const double* c = dv.center;
   switch (model) {
     case PLANE3: np = solve_scatter<3>(m, c, 0, p); break;
+    case PLANE4: np = solve_scatter<4>(m, c, 0, p); break;
     case LINE3: np = solve_scatter<3>(m, c, 2, p); break;
     case LINE2: np = solve_scatter<2>(m, c, 1, p); break;
     case LINE2D: np = solve_line2d(m, c, p); break;
@@ -1049,6 +1054,7 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
     const double* c = zero.center;
     switch (M) {
       case PLANE3: np = solve_scatter<3>(m, c, 0, p); break;
+      case PLANE4: np = solve_scatter<4>(m, c, 0, p); break;
       case LINE3: np = solve_scatter<3>(m, c, 2, p); break;
       case LINE2: np = solve_scatter<2>(m, c, 1, p); break;
       case LINE2D: np = solve_line2d(m, c, p); break;
@@ -1117,6 +1123,7 @@ int launch_batch(const BatchArgs& a, const EstCfg& cfg, int ls_type, cudaStream_
     case CIRCLE2: CALL(CIRCLE2) break;
     case SPHERE3: CALL(SPHERE3) break;
     case SPHERE4: CALL(SPHERE4) break;
+    case PLANE4: CALL(PLANE4) break;
     case ABSOR: CALL(ABSOR) break;
     case RAY: CALL(RAY) break;
     case PIVOT: CALL(PIVOT) break;

@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(128) solve_kernel(SolveArgs a, const double* _
     case USXW: { CALL(USXW); break; }         \
     case USCP: { CALL(USCP); break; }         \
     case SPHERE4: { CALL(SPHERE4); break; }   \
+    case PLANE4: { CALL(PLANE4); break; }     \
     default: break;                           \
   }
 

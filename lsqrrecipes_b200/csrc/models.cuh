@@ -14,7 +14,7 @@
 
 namespace lsqr {
 
-enum : int { PLANE3 = 0, LINE2D = 1, LINE2 = 2, LINE3 = 3, CIRCLE2 = 4, SPHERE3 = 5, ABSOR = 6, RAY = 7, PIVOT = 8, DENSE5 = 9, DENSE6 = 10, USXW = 11, USCP = 12, SPHERE4 = 13, NUM_MODELS = 14 };
+enum : int { PLANE3 = 0, LINE2D = 1, LINE2 = 2, LINE3 = 3, CIRCLE2 = 4, SPHERE3 = 5, ABSOR = 6, RAY = 7, PIVOT = 8, DENSE5 = 9, DENSE6 = 10, USXW = 11, USCP = 12, SPHERE4 = 13, PLANE4 = 14, NUM_MODELS = 15 };
 
 // dim = doubles per datum, P = parameters, K = minimal subset, HQ = doubles of a prepared
 // fp64 hypothesis, Q32 = floats of a hoisted fp32 hypothesis.
@@ -38,6 +38,7 @@ template <> struct Model<USXW>    { static constexpr int D = 14, P = 20, K = 4, 
 // parameters [t3, omega_z, omega_y, omega_x, m_x, m_y, m_x R3(:,1), m_y R3(:,2), R3(:,3)]
 template <> struct Model<USCP>    { static constexpr int D = 17, P = 17, K = 3, HQ = 9,  Q32 = 9;  };
 template <> struct Model<SPHERE4> { static constexpr int D = 4,  P = 5, K = 5, HQ = 5,  Q32 = 6;  };
+template <> struct Model<PLANE4>  { static constexpr int D = 4,  P = 8, K = 4, HQ = 8,  Q32 = 5;  };
 
 struct ModelInfo { int D, P, K, HQ, Q32; };
 __host__ __device__ inline ModelInfo model_info(int m) {
@@ -56,6 +57,7 @@ __host__ __device__ inline ModelInfo model_info(int m) {
     case USXW:    return {14, 20, 4, 12, 12};
     case USCP:    return {17, 17, 3, 9, 9};
     case SPHERE4: return {4, 5, 5, 5, 6};
+    case PLANE4:  return {4, 8, 4, 8, 5};
   }
   return {0, 0, 0, 0, 0};
 }
@@ -175,6 +177,43 @@ __device__ inline int pinv_solve(double* A, const double* b, double tol, double*
     if (sqrt(s2) <= tol) y[j] = 0.0; else { y[j] = ub / s2; rank++; }
   }
   for (int i = 0; i < NC; i++) { double s = 0; for (int j = 0; j < NC; j++) s += V[i * NC + j] * y[j]; x[i] = s; }
+  return rank;
+}
+
+// Null vector of A (MR x NC, MR < NC, row-major, destroyed) and the number of singular values above tol.  Stands in
+// for vnl_svd + zero_out_absolute + rank() + nullvector() (PlaneParametersEstimator.hxx:82-90): vnl_svd keeps NC
+// singular values in descending order (the trailing NC-MR are zero) and nullvector() is the last column of V.
+template <int MR, int NC>
+__device__ inline int null_vector(double* A, double tol, double* x) {
+  double V[NC * NC];
+  for (int i = 0; i < NC; i++) for (int j = 0; j < NC; j++) V[i * NC + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; sweep++) {
+    bool rotated = false;
+    for (int p = 0; p < NC; p++) {
+      for (int q = p + 1; q < NC; q++) {
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int k = 0; k < MR; k++) { const double ap = A[k * NC + p], aq = A[k * NC + q]; alpha += ap * ap; beta += aq * aq; gamma += ap * aq; }
+        if (gamma == 0.0 || fabs(gamma) <= 1e-16 * sqrt(alpha * beta)) continue;
+        rotated = true;
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        for (int k = 0; k < MR; k++) { const double xk = A[k * NC + p], yk = A[k * NC + q]; A[k * NC + p] = c * xk - s * yk; A[k * NC + q] = s * xk + c * yk; }
+        for (int k = 0; k < NC; k++) { const double xk = V[k * NC + p], yk = V[k * NC + q]; V[k * NC + p] = c * xk - s * yk; V[k * NC + q] = s * xk + c * yk; }
+      }
+    }
+    if (!rotated) break;
+  }
+  int rank = 0, last = 0;
+  double wlast = 0.0;
+  for (int j = 0; j < NC; j++) {
+    double s2 = 0;
+    for (int k = 0; k < MR; k++) s2 += A[k * NC + j] * A[k * NC + j];
+    const double w = sqrt(s2);
+    if (w > tol) rank++;
+    if (j == 0 || w <= wlast) { last = j; wlast = w; }
+  }
+  for (int i = 0; i < NC; i++) x[i] = V[i * NC + last];
   return rank;
 }
 
@@ -427,6 +466,18 @@ template <> __device__ inline bool estimate<USXW>(const double* d, const EstCfg&
   return us_post(x, prm);
 }
 
+// PlaneParametersEstimator.hxx:70-108 (every dimension other than 3): [n, d] spans the null space of [p_i, -1]
+template <> __device__ inline bool estimate<PLANE4>(const double* d, const EstCfg&, double* prm) {
+  double A[4 * 5], x[5];
+  for (int i = 0; i < 4; i++) { for (int j = 0; j < 4; j++) A[i * 5 + j] = d[i * 4 + j]; A[i * 5 + 4] = -1; }
+  if (null_vector<4, 5>(A, kEps, x) < 4) return false;
+  double norm = 0;
+  for (int i = 0; i < 4; i++) norm += x[i] * x[i];
+  norm = 1.0 / sqrt(norm);
+  for (int i = 0; i < 4; i++) { prm[i] = x[i] * norm; prm[4 + i] = d[i]; }
+  return true;
+}
+
 // SphereParametersEstimator.hxx:169-202 (estimateND, every dimension other than 2 and 3): rows p0 - p_i, pseudo-inverse
 // with singular values <= EPS zeroed; rank < dim means the points lie in a hyperplane.
 template <> __device__ inline bool estimate<SPHERE4>(const double* d, const EstCfg&, double* prm) {
@@ -494,6 +545,12 @@ template <> __device__ __forceinline__ bool agree<PLANE3>(const double* h, const
   double sd = 0;
 #pragma unroll
   for (int i = 0; i < 3; i++) sd += h[i] * (x[i] - h[3 + i]);
+  return (sd * sd) < cfg.delta2;
+}
+template <> __device__ __forceinline__ bool agree<PLANE4>(const double* h, const double* x, const EstCfg& cfg) {
+  double sd = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) sd += h[i] * (x[i] - h[4 + i]);
   return (sd * sd) < cfg.delta2;
 }
 // Line2DParametersEstimator.cxx:119-123

@@ -60,13 +60,13 @@ class ParametersEstimator:
 
 
 class PlaneParametersEstimator(ParametersEstimator):
-    """PlaneParametersEstimator<3> (PlaneParametersEstimator.h:24-91); only dimension 3 is on the GPU path."""
-    _model = "plane3"
+    """PlaneParametersEstimator<dimension> for dimension 3 or 4 (PlaneParametersEstimator.h:24-91)."""
 
     def __init__(self, delta, dimension=3):
-        if dimension != 3:
-            raise NotImplementedError("hyperplanes of dimension != 3 are outside the accelerated path (SURVEY.md 8f-4)")
-        super().__init__(3, delta)
+        if dimension not in (3, 4):
+            raise NotImplementedError("hyperplanes are accelerated for d = 3, 4")
+        self._model = "plane3" if dimension == 3 else "plane4"
+        super().__init__(dimension, delta)
 
 
 class LineParametersEstimator(ParametersEstimator):

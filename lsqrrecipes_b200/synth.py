@@ -246,11 +246,12 @@ GENERATORS = {
     "dense5": lambda n, seed=SEED: dense_rows(n, 5, seed=seed),
     "dense6": lambda n, seed=SEED: dense_rows(n, 6, seed=seed),
     "sphere4": lambda n, seed=SEED: sphere(n, 4, seed=seed),
+    "plane4": lambda n, seed=SEED: plane(n, seed=seed, dim=4),
     "usxw": lambda n, seed=SEED: crosswire(n, seed=seed),
     "uscp": lambda n, seed=SEED: calibrated_pointer(n, seed=seed),
 }
 DELTAS = {"plane3": 0.5, "line2d": 0.5, "line2": 0.5, "line3": 0.5, "circle2": 0.5, "sphere3": 0.5, "absor": 2.0, "ray": 1.0, "pivot": 1.0,
-          "dense5": 0.2, "dense6": 0.2, "usxw": 1.0, "uscp": 1.0, "sphere4": 0.5}
+          "dense5": 0.2, "dense6": 0.2, "usxw": 1.0, "uscp": 1.0, "sphere4": 0.5, "plane4": 0.5}
 
 
 def random_subsets(n, k, H, seed=SEED):

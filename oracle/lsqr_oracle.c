@@ -21,7 +21,7 @@
 #include <omp.h>
 #endif
 
-enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10, M_USXW = 11, M_USCP = 12, M_SPHERE4 = 13 };
+enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10, M_USXW = 11, M_USCP = 12, M_SPHERE4 = 13, M_PLANE4 = 14 };
 
 /* common/Epsilon.h:19 */
 static const double EPS = 2.220446049250313e-016;
@@ -32,8 +32,8 @@ static const double FRAME_SMALL_ANGLE = 0.008726535498373935;
 static const double FRAME_HALF_PI = 3.14159265358979323846 / 2.0;
 
 int orc_model_info(int model, int* D, int* P, int* k) {
-  static const int tab[14][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}, {6, 5, 5}, {7, 6, 6}, {14, 20, 4}, {17, 17, 3}, {4, 5, 5}};
-  if (model < 0 || model > 13) return -1;
+  static const int tab[15][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}, {6, 5, 5}, {7, 6, 6}, {14, 20, 4}, {17, 17, 3}, {4, 5, 5}, {4, 8, 4}};
+  if (model < 0 || model > 14) return -1;
   *D = tab[model][0]; *P = tab[model][1]; *k = tab[model][2];
   return 0;
 }
@@ -124,6 +124,44 @@ static int pinv_solve(int m, int n, const double* Ain, const double* b, double t
   }
   for (i = 0; i < n; i++) { double s = 0; for (j = 0; j < n; j++) s += V[i * n + j] * y[j]; x[i] = s; }
   free(A);
+  return rank;
+}
+
+/* Null vector of A (m x n, m < n, row-major) and the number of singular values above tol: the contract of
+ * vnl_svd + zero_out_absolute + rank() + nullvector() at PlaneParametersEstimator.hxx:82-90.  vnl_svd carries n
+ * singular values (descending, the trailing n-m zero) and an n x n V; nullvector() is V's last column.  Same
+ * one-sided Jacobi as pinv_solve, run on the columns of the wide matrix. */
+static int null_vector(int m, int n, const double* Ain, double tol, double* x) {
+  double A[6 * 7], V[7 * 7], w[7];
+  int i, j, k, p, q, sweep, rank = 0, last = 0;
+  memcpy(A, Ain, sizeof(double) * (size_t)m * n);
+  for (i = 0; i < n; i++) for (j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0 : 0.0;
+  for (sweep = 0; sweep < 60; sweep++) {
+    int rotated = 0;
+    for (p = 0; p < n; p++) {
+      for (q = p + 1; q < n; q++) {
+        double alpha = 0, beta = 0, gamma = 0, zeta, t, c, s;
+        for (k = 0; k < m; k++) { double ap = A[k * n + p], aq = A[k * n + q]; alpha += ap * ap; beta += aq * aq; gamma += ap * aq; }
+        if (gamma == 0.0 || fabs(gamma) <= 1e-16 * sqrt(alpha * beta)) continue;
+        rotated = 1;
+        zeta = (beta - alpha) / (2.0 * gamma);
+        t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        c = 1.0 / sqrt(1.0 + t * t);
+        s = c * t;
+        for (k = 0; k < m; k++) { double xk = A[k * n + p], yk = A[k * n + q]; A[k * n + p] = c * xk - s * yk; A[k * n + q] = s * xk + c * yk; }
+        for (k = 0; k < n; k++) { double xk = V[k * n + p], yk = V[k * n + q]; V[k * n + p] = c * xk - s * yk; V[k * n + q] = s * xk + c * yk; }
+      }
+    }
+    if (!rotated) break;
+  }
+  for (j = 0; j < n; j++) {
+    double s2 = 0;
+    for (k = 0; k < m; k++) s2 += A[k * n + j] * A[k * n + j];
+    w[j] = sqrt(s2);
+    if (w[j] > tol) rank++;
+    if (w[j] <= w[last]) last = j;   /* the column a stable descending sort puts last */
+  }
+  for (i = 0; i < n; i++) x[i] = V[i * n + last];
   return rank;
 }
 
@@ -308,6 +346,21 @@ static int triad(const double* P0, const double* P1, const double* P2, double Rm
 }
 
 /* AbsoluteOrientationParametersEstimator.cxx:14-101 */
+/* PlaneParametersEstimator.hxx:70-108 (dimensions other than 3): the hyperplane normal and offset are the null space of
+ * the k x (k+1) matrix [p_i, -1]; rank < k -> linearly dependent points; the normal is scaled to unit length, the point
+ * on the plane is the first datum */
+static int plane_nd_estimate(int dim, const double* d, double* prm) {
+  double A[6 * 7], x[7], norm = 0;
+  int i, j;
+  for (i = 0; i < dim; i++) { for (j = 0; j < dim; j++) A[i * (dim + 1) + j] = d[i * dim + j]; A[i * (dim + 1) + dim] = -1; }
+  if (null_vector(dim, dim + 1, A, EPS, x) < dim) return 0;
+  for (i = 0; i < dim; i++) { norm += x[i] * x[i]; prm[i] = x[i]; }
+  norm = 1.0 / sqrt(norm);
+  for (i = 0; i < dim; i++) prm[i] *= norm;
+  for (i = 0; i < dim; i++) prm[dim + i] = d[i];
+  return 2 * dim;
+}
+
 /* SphereParametersEstimator.hxx:169-202 (estimateND, dimensions other than 2 and 3): rows p0 - p_i, pseudo-inverse with
  * singular values <= EPS zeroed, rank < dim -> coplanar points */
 static int sphere_nd_estimate(int dim, const double* d, double* prm) {
@@ -743,6 +796,7 @@ int orc_estimate(int model, double delta, double aux, const double* data, size_t
     case M_CIRCLE2: return circle_estimate(data, params);
     case M_SPHERE3: return sphere3_estimate(data, params);
     case M_SPHERE4: return sphere_nd_estimate(4, data, params);
+    case M_PLANE4: return plane_nd_estimate(4, data, params);
     case M_ABSOR: return absor_estimate(data, params);
     case M_RAY: return ray_estimate(data, ray_cross_eps(aux), params);
     case M_PIVOT: return pivot_solve(data, 3, params);
@@ -760,9 +814,11 @@ int orc_estimate(int model, double delta, double aux, const double* data, size_t
 
 static int agree1(int model, double delta, const double* prm, const double* x) {
   switch (model) {
-    case M_PLANE3: { /* PlaneParametersEstimator.hxx:196-203 */
+    case M_PLANE3:
+    case M_PLANE4: { /* PlaneParametersEstimator.hxx:196-203 */
+      const int dim = (model == M_PLANE3) ? 3 : 4;
       double sd = 0; int i;
-      for (i = 0; i < 3; i++) sd += prm[i] * (x[i] - prm[3 + i]);
+      for (i = 0; i < dim; i++) sd += prm[i] * (x[i] - prm[dim + i]);
       return (sd * sd) < delta * delta;
     }
     case M_LINE2D: { /* Line2DParametersEstimator.cxx:119-123 */
@@ -837,7 +893,7 @@ int orc_agree(int model, double delta, double aux, const double* params, int np,
 /* PlaneParametersEstimator.hxx:129-172 (col=0: smallest eigenvalue) and
  * LineParametersEstimator.hxx:68-111 (col=dim-1: largest) share the covariance build. */
 static int cov_eig_estimate(int dim, int col, const double* d, size_t n, double* prm) {
-  double mean[3] = {0, 0, 0}, cov[9] = {0}, meanMat[9], V[9], ev[3], sqrtN = sqrt((double)n);
+  double mean[4] = {0, 0, 0, 0}, cov[16] = {0}, meanMat[16], V[16], ev[4], sqrtN = sqrt((double)n);
   size_t i; int j, k;
   for (i = 0; i < n; i++) for (j = 0; j < dim; j++) mean[j] += d[i * dim + j];
   for (j = 0; j < dim; j++) mean[j] /= sqrtN;
@@ -1058,6 +1114,7 @@ int orc_least_squares(int model, double delta, double aux, int ls_type, const do
   if (n < (size_t)k && model != M_RAY) return 0; /* ray LS has no size guard (:100-144) */
   switch (model) {
     case M_PLANE3: return cov_eig_estimate(3, 0, data, n, params);
+    case M_PLANE4: return cov_eig_estimate(4, 0, data, n, params);
     case M_LINE2D: return line2d_lsq(data, n, params);
     case M_LINE2: return cov_eig_estimate(2, 1, data, n, params);
     case M_LINE3: return cov_eig_estimate(3, 2, data, n, params);

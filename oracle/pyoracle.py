@@ -18,10 +18,10 @@ _u32p = ctypes.POINTER(ctypes.c_uint32)
 _i32p = ctypes.POINTER(ctypes.c_int32)
 
 MODELS = {"plane3": 0, "line2d": 1, "line2": 2, "line3": 3, "circle2": 4, "sphere3": 5, "absor": 6, "ray": 7, "pivot": 8,
-          "dense5": 9, "dense6": 10, "usxw": 11, "uscp": 12, "sphere4": 13}
+          "dense5": 9, "dense6": 10, "usxw": 11, "uscp": 12, "sphere4": 13, "plane4": 14}
 # model -> (D doubles per datum, P params, k minimal subset)
 INFO = {0: (3, 6, 3), 1: (2, 4, 2), 2: (2, 4, 2), 3: (3, 6, 2), 4: (2, 3, 3), 5: (3, 4, 4), 6: (6, 7, 3), 7: (6, 3, 2), 8: (12, 6, 3),
-        9: (6, 5, 5), 10: (7, 6, 6), 11: (14, 20, 4), 12: (17, 17, 3), 13: (4, 5, 5)}
+        9: (6, 5, 5), 10: (7, 6, 6), 11: (14, 20, 4), 12: (17, 17, 3), 13: (4, 5, 5), 14: (4, 8, 4)}
 
 
 def lib_path(kind):

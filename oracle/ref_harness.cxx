@@ -37,7 +37,7 @@
 
 using namespace lsqrRecipes;
 
-enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10, M_USXW = 11, M_USCP = 12, M_SPHERE4 = 13 };
+enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10, M_USXW = 11, M_USCP = 12, M_SPHERE4 = 13, M_PLANE4 = 14 };
 
 namespace {
 
@@ -108,6 +108,7 @@ struct Cfg { int model; double delta; double aux; int ls_type; };
 template <class F> int dispatch(const Cfg& c, F& f) {
   switch (c.model) {
     case M_PLANE3: { PlaneParametersEstimator<3> e(c.delta); return f(&e, (Point3D*)0); }
+    case M_PLANE4: { typedef Point<double, 4> Point4D; PlaneParametersEstimator<4> e(c.delta); return f(&e, (Point4D*)0); }
     case M_LINE2D: { Line2DParametersEstimator e(c.delta); return f(&e, (Point2D*)0); }
     case M_LINE2: { LineParametersEstimator<2> e(c.delta); return f(&e, (Point2D*)0); }
     case M_LINE3: { LineParametersEstimator<3> e(c.delta); return f(&e, (Point3D*)0); }
@@ -203,8 +204,8 @@ struct RansacOp {
 extern "C" {
 
 int ref_model_info(int model, int* D, int* P, int* k) {
-  static const int tab[14][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}, {6, 5, 5}, {7, 6, 6}, {14, 20, 4}, {17, 17, 3}, {4, 5, 5}};
-  if (model < 0 || model > 13) return -1;
+  static const int tab[15][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}, {6, 5, 5}, {7, 6, 6}, {14, 20, 4}, {17, 17, 3}, {4, 5, 5}, {4, 8, 4}};
+  if (model < 0 || model > 14) return -1;
   *D = tab[model][0]; *P = tab[model][1]; *k = tab[model][2];
   return 0;
 }

@@ -206,8 +206,9 @@ class vnl_symmetric_eigensystem {
 };
 
 // ---------------------------------------------------------------------------------------
-// SVD by one-sided Jacobi.  A (m x n, m >= n required by every call site on the scoped
-// path; m < n is handled by decomposing the transpose).  Singular values descending.
+// SVD by one-sided Jacobi on the columns of A (m x n).  As in VNL, W has n entries and V is n x n
+// also when m < n (the trailing singular values are then zero and nullvector(), the last column of V,
+// spans the null space -- PlaneParametersEstimator.hxx:70-90 relies on that).  Singular values descending.
 // ---------------------------------------------------------------------------------------
 template <class T>
 class vnl_svd {
@@ -243,8 +244,8 @@ class vnl_svd {
 
  private:
   void compute(vnl_matrix<T> const& Ain) {
-    const bool tr = Ain.rows() < Ain.cols();
-    vnl_matrix<T> A = tr ? Ain.transpose() : Ain;
+    const bool tr = false;
+    vnl_matrix<T> A = Ain;
     const unsigned m = A.rows(), n = A.cols();
     vnl_matrix<T> V(n, n, T(0));
     for (unsigned i = 0; i < n; i++) V(i, i) = T(1);

@@ -55,4 +55,4 @@ def same_up_to_sign(a, b, idx, tol):
 
 # parameter entries that carry an arbitrary sign after leastSquaresEstimate
 SIGN_IDX = {"plane3": [0, 1, 2], "line2d": [0, 1], "line2": [0, 1], "line3": [0, 1, 2], "circle2": [], "sphere3": [],
-            "absor": [0, 1, 2, 3], "ray": [], "pivot": [], "dense5": [], "dense6": [], "usxw": [], "uscp": [], "sphere4": []}
+            "absor": [0, 1, 2, 3], "ray": [], "pivot": [], "dense5": [], "dense6": [], "usxw": [], "uscp": [], "sphere4": [], "plane4": [0, 1, 2, 3]}

@@ -10,10 +10,10 @@ from lsqrrecipes_b200 import synth
 from oracle.pyoracle import INFO, MODELS
 
 ALL = list(MODELS.items())
-PINV_MODELS = ("pivot", "dense5", "dense6", "usxw", "uscp", "sphere4")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
+PINV_MODELS = ("pivot", "dense5", "dense6", "usxw", "uscp", "sphere4", "plane4")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
 # ... where "rounding level" scales with the conditioning of the minimal system (the 9x9 / 12x12 calibration systems of
 # random subsets reach 1e7)
-PINV_TOL = {"pivot": 1e-9, "dense5": 1e-9, "dense6": 1e-9, "usxw": 1e-6, "uscp": 1e-6, "sphere4": 1e-6}
+PINV_TOL = {"pivot": 1e-9, "dense5": 1e-9, "dense6": 1e-9, "usxw": 1e-6, "uscp": 1e-6, "sphere4": 1e-6, "plane4": 1e-9}
 
 
 # ---- the reference's own literal test vectors -------------------------------------------

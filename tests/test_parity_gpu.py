@@ -19,10 +19,10 @@ pytestmark = pytest.mark.gpu
 from lsqrrecipes_b200 import MODELS as ENGINE_MODELS
 
 ALL = [(n, m) for n, m in MODELS.items() if n in ENGINE_MODELS]   # every estimator the engine implements
-PINV_MODELS = ("pivot", "dense5", "dense6", "usxw", "uscp", "sphere4")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
+PINV_MODELS = ("pivot", "dense5", "dense6", "usxw", "uscp", "sphere4", "plane4")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
 # ... where "rounding level" scales with the conditioning of the minimal system (the 9x9 / 12x12 calibration systems of
 # random subsets reach 1e7)
-PINV_TOL = {"pivot": 1e-9, "dense5": 1e-9, "dense6": 1e-9, "usxw": 1e-6, "uscp": 1e-6, "sphere4": 1e-6}
+PINV_TOL = {"pivot": 1e-9, "dense5": 1e-9, "dense6": 1e-9, "usxw": 1e-6, "uscp": 1e-6, "sphere4": 1e-6, "plane4": 1e-9}
 REFINE_TOL = 1e-6
 
 
@@ -209,6 +209,36 @@ def test_hypersphere_4d_as_the_reference_tests_it(port):
     assert prm == []
 
 
+def test_hyperplane_4d_operator_interface(port):
+    """PlaneParametersEstimator<4> goes through the null-space branch (PlaneParametersEstimator.hxx:70-108) that the
+    reference's own test leaves to "any dimension" (testing/PlaneParametersEstimatorTest.cxx:37): same checks as its
+    3-D test -- exact estimate from k points, least squares on noisy inliers, agree(), and RANSAC::compute."""
+    from lsqrrecipes_b200 import RANSAC, PlaneParametersEstimator as Est
+    data, true = synth.plane(5000, seed=31, dim=4)
+    m = MODELS["plane4"]
+    est = Est(0.5, dimension=4)
+    prm = []
+    est.estimate(data[:4], prm)
+    assert len(prm) == 8 and same_up_to_sign(prm, port.estimate(m, 0.5, data[:4]), SIGN_IDX["plane4"], 1e-9)
+    assert abs(np.linalg.norm(prm[:4]) - 1.0) < 1e-12 and prm[4:] == data[0].tolist()
+    assert np.abs((data[:4] - np.array(prm[4:])) @ np.array(prm[:4])).max() < 1e-9    # the four points lie on it
+    dup = data[[0, 1, 2, 2]]                                                         # linearly dependent rows: rank 3
+    prm = [1.0]
+    est.estimate(dup, prm)
+    assert prm == []
+    cnt, flags = port.agree(m, 0.5, true, data)
+    inl = data[flags.astype(bool)]
+    prm = []
+    est.leastSquaresEstimate(inl, prm)
+    assert same_up_to_sign(prm, port.least_squares(m, 0.5, inl), SIGN_IDX["plane4"], REFINE_TOL)
+    assert est.agree(list(true), inl[0]) and not est.agree(list(true), data[~flags.astype(bool)][0])
+    out, cs = [], []
+    frac = RANSAC.compute(out, est, data, 0.999, cs)
+    assert frac > 0.9 * cnt / len(data) and sum(cs) == round(frac * len(data))
+    n_est, n_true = np.array(out[:4]), true[:4]
+    assert abs(abs(n_est @ n_true) - 1.0) < 1e-6 and abs((np.array(out[4:]) - true[4:]) @ n_true) < 0.1
+
+
 def test_circle_agree_literals():
     """testing/SphereParametersEstimatorTest.cxx:280-296"""
     eng = Engine("circle2", 0.5)
@@ -263,8 +293,9 @@ def _fp32_band(name, data, prm, delta):
 def _residual64(name, prm, data, delta):
     """|residual| in float64 numpy, and the threshold it is compared with (distance units)."""
     p = np.asarray(prm)
-    if name in ("plane3",):
-        return np.abs((data - p[3:6]) @ p[0:3]), delta
+    if name in ("plane3", "plane4"):
+        d = data.shape[1]
+        return np.abs((data - p[d:]) @ p[:d]), delta
     if name == "line2d":
         return np.abs((data - p[2:4]) @ p[0:2]), delta
     if name in ("line2", "line3"):
@@ -417,7 +448,7 @@ def test_edge_cases_match_reference_conventions():
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["line2d", "plane3", "sphere3", "sphere4", "dense5"])
+@pytest.mark.parametrize("name", ["line2d", "plane3", "plane4", "sphere3", "sphere4", "dense5"])
 def test_batched_small_problems_vs_oracle(port, name):
     """BASELINE.json configs[4]: many independent small problems, one thread block each.  Exhaustive mode is
     bit-comparable with the reference's brute-force driver run per problem."""
