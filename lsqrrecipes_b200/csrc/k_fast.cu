@@ -393,6 +393,20 @@ __device__ __forceinline__ void count_abs_lt4_alu(uint32_t& cnt, f2 s01, f2 s23,
       "add.u32 %0, %0, t0;\n\tadd.u32 %0, %0, t1;\n\tadd.u32 %0, %0, t2;\n\tadd.u32 %0, %0, t3;\n\t}"
       : "+r"(cnt) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)), "f"(fabsf(d)), "f"(delta));
 }
+// Three ALU instructions per two residuals: the two FSET.BF results are summed as raw words by one IADD3
+// (raw += 0x3F800000 per inlier).  0x3F800000 = 127 << 23, so raw holds (127 k mod 512) << 23 and k is recovered
+// by cb_raw_decode() as long as no more than 511 inliers were summed since the last decode.
+__device__ __forceinline__ void count_abs_lt4_raw(uint32_t& raw, f2 s01, f2 s23, float delta) {
+  float a, b, c, d;
+  halves(s01, a, b);
+  halves(s23, c, d);
+  asm("{\n\t.reg .f32 f0, f1, f2, f3;\n\t.reg .b32 t0, t1, t2, t3;\n\t"
+      "set.lt.f32.f32 f0, %1, %5;\n\tset.lt.f32.f32 f1, %2, %5;\n\tset.lt.f32.f32 f2, %3, %5;\n\tset.lt.f32.f32 f3, %4, %5;\n\t"
+      "mov.b32 t0, f0;\n\tmov.b32 t1, f1;\n\tmov.b32 t2, f2;\n\tmov.b32 t3, f3;\n\t"
+      "add.u32 t0, t0, t1;\n\tadd.u32 %0, %0, t0;\n\tadd.u32 t2, t2, t3;\n\tadd.u32 %0, %0, t2;\n\t}"
+      : "+r"(raw) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)), "f"(fabsf(d)), "f"(delta));
+}
+__device__ __forceinline__ uint32_t cb_raw_decode(uint32_t raw) { return ((raw >> 23) * 383u) & 511u; }   // 127 * 383 = 1 (mod 512)
 __device__ __forceinline__ void count_sign(uint32_t& cnt, f2 g) {
   float a, b;
   halves(g, a, b);
@@ -513,6 +527,10 @@ static std::mutex g_cb_mutex[16];             // the bank is per device, not per
 #ifndef LSQR_CB_MIX
 #define LSQR_CB_MIX 3
 #endif
+#ifndef LSQR_CB_RAW
+#define LSQR_CB_RAW 1
+#endif
+constexpr uint32_t kCbRawMaxSub = 496;       // <= 511 inliers per raw counter, multiple of 16
 template <int M> constexpr uint32_t cb_points() { return (uint32_t)(kCbFloats / Model<M>::D / 16 * 16); }   // points per launch
 
 template <int M, int R, int THREADS, int PPI>
@@ -534,33 +552,37 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
   // one induction variable in units of 2*PPI points; the component offsets are immediates (cp is a multiple of 16)
   const uint32_t p0 = blockIdx.y * sub, p1 = min(p0 + sub, npts);
   const int g0 = (int)(p0 / (2 * PPI)), g1 = (int)(p1 / (2 * PPI));
-#pragma unroll 1
-  for (int g = g0; g < g1; g++) {
-    f2 x[PPI][D];
+  // raw-sum counting (count_abs_lt4_raw) holds 9 bits: the host keeps sub <= kCbRawMaxSub points per CTA
+  constexpr bool kRaw = LSQR_CB_RAW && Eval<M>::kHasAbsForm && PPI >= 2;
+  // points of group g (2*PPI points) from the constant bank: uniform loads, the values live in uniform registers
+  auto load_group = [&](f2 (&x)[PPI][D], int g) {
 #pragma unroll
     for (int d = 0; d < D; d++) {
-      if constexpr (PPI == 4) {
-        const float4 v = c_tile[d * (int)(cp / 4) + 2 * g], w = c_tile[d * (int)(cp / 4) + 2 * g + 1];
-        x[0][d] = join(v.x, v.y); x[1][d] = join(v.z, v.w); x[2][d] = join(w.x, w.y); x[3][d] = join(w.z, w.w);
-      } else if constexpr (PPI == 2) {
-        const float4 v = c_tile[d * (int)(cp / 4) + g];
-        x[0][d] = join(v.x, v.y); x[1][d] = join(v.z, v.w);
+      if constexpr (PPI % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < PPI / 2; j++) {
+          const float4 v = c_tile[d * (int)(cp / 4) + (PPI / 2) * g + j];
+          x[2 * j][d] = join(v.x, v.y); x[2 * j + 1][d] = join(v.z, v.w);
+        }
       } else {
         const float2 v = reinterpret_cast<const float2*>(c_tile)[d * (int)(cp / 2) + g];
         x[0][d] = join(v.x, v.y);
       }
     }
+  };
+  auto score_group = [&](const f2 (&x)[PPI][D]) {
 #pragma unroll
     for (int r = 0; r < R; r++) {
       f2 q[Q];
 #pragma unroll
       for (int j = 0; j < Q; j++) q[j] = splat(qf[r][j]);
       if constexpr (Eval<M>::kHasAbsForm && PPI >= 2) {
-        // ptxas puts most predicated adds on the FMA-heavy pipe (VIADD), which the FFMA2s need: one
-        // hypothesis in LSQR_CB_MIX counts that way, the others with two ALU instructions
 #pragma unroll
         for (int u = 0; u < PPI; u += 2) {
-          if (r % LSQR_CB_MIX == 0) count_abs_lt4(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), thr.fdelta);
+          // kRaw: 3 ALU instructions per two residuals.  Otherwise FSETP + predicated add, most of which ptxas puts on the
+          // FMA-heavy pipe (VIADD) that the FFMA2s need: one hypothesis in LSQR_CB_MIX counts that way, the others with FSET.BF + LEA.HI
+          if constexpr (kRaw) count_abs_lt4_raw(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), thr.fdelta);
+          else if (r % LSQR_CB_MIX == 0) count_abs_lt4(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), thr.fdelta);
           else count_abs_lt4_alu(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), thr.fdelta);
         }
       } else {
@@ -568,10 +590,17 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
         for (int u = 0; u < PPI; u++) count_sign(cnt[r], Eval<M>::signed_(q, x[u], thr));
       }
     }
+  };
+#pragma unroll 1
+  for (int g = g0; g < g1; g++) {
+    f2 x[PPI][D];
+    load_group(x, g);
+    score_group(x);
   }
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const uint32_t h = hbase + r * THREADS + tid;
+    if constexpr (kRaw) cnt[r] = cb_raw_decode(cnt[r]);
     if (h < H && cnt[r]) atomicAdd(&counts[h], cnt[r]);
   }
 }
@@ -621,10 +650,12 @@ static int run_consensus_cb(const DataView& dv, const float* hyp, size_t hld, ui
   const uint32_t hyp_blocks = (H + THREADS * R - 1) / (THREADS * R);
   const uint32_t slots = (uint32_t)num_sms * (uint32_t)occ[dev & 15];
   // sub-chunks per launch: fill the last wave (the launches of one request serialise on the bank)
+  constexpr bool kRaw = LSQR_CB_RAW && Eval<M>::kHasAbsForm && PPI >= 2;
   auto pick_sub = [&](uint32_t npts) {
-    uint32_t best_sub = npts; double best_eff = 0.0;
+    uint32_t best_sub = kRaw ? std::min(npts, kCbRawMaxSub) : npts; double best_eff = 0.0;
     for (uint32_t nsub = 1; nsub <= 64; nsub++) {
       uint32_t sub = ((npts + nsub - 1) / nsub + 15) / 16 * 16;
+      if (kRaw && sub > kCbRawMaxSub) continue;
       if (sub < 128 && nsub > 1) break;
       const uint32_t ny = (npts + sub - 1) / sub;
       const double waves = (double)hyp_blocks * ny / slots;
