@@ -159,11 +159,33 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": total,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
+
+
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner) write to file descriptor 1 as
+    well, so everything else is pointed at stderr and the line goes to the original descriptor."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_line(line):
+    payload = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(payload.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, payload)
 
 
 def main():
     args = parse()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -332,7 +354,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clk.summary(),
             "best_count": int(r["best_count"]),
         }
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
