@@ -67,7 +67,7 @@ __device__ __forceinline__ f2 join(float lo, float hi) { f2 r; asm("mov.b64 %0, 
 //   PLANE3   (nx,ny,nz, -n.(a-c))
 //   LINE2D   (nx,ny, -n.(a-c))
 //   LINE2/3  (dir, a-c)
-//   CIRCLE/SPHERE (ctr-c, -m, -w^2)  with  |d - r| < delta  <=>  (d^2 - m)^2 < w^2,  m = r^2+delta^2, w = 2 r delta
+//   CIRCLE/SPHERE (ctr-c, -m, w)  with  |d - r| < delta  <=>  |d^2 - m| < w,  m = r^2+delta^2, w = 2 r delta
 //   ABSOR    (R[9], R c1 + t - c2)
 //   RAY      (x - c)
 //   PIVOT    (tDRF, tW - c)
@@ -100,7 +100,7 @@ template <int DIM> __device__ __forceinline__ void hoist_sphere(const double* p,
   double m, w;
   if (r >= dl) { m = r * r + dl * dl; w = 2.0 * r * dl; }
   else { const double hi = (r + dl) * (r + dl); m = (hi - 1.0) * 0.5; w = (hi + 1.0) * 0.5; }  // interval (-1, hi): d^2 >= 0 has no lower bound
-  q[DIM] = (float)(-m); q[DIM + 1] = (float)(-(w * w));
+  q[DIM] = (float)(-m); q[DIM + 1] = (float)w;
 }
 template <> __device__ __forceinline__ void hoist32<CIRCLE2>(const double* p, const double* c, const EstCfg& cfg, float* q) { hoist_sphere<2>(p, c, cfg, q); }
 template <> __device__ __forceinline__ void hoist32<SPHERE3>(const double* p, const double* c, const EstCfg& cfg, float* q) { hoist_sphere<3>(p, c, cfg, q); }
@@ -208,16 +208,19 @@ struct Thr2 { f2 delta, neg_delta2; float fdelta; };
 template <int M> struct Eval;
 template <> struct Eval<PLANE3> {
   static constexpr bool kHasAbsForm = true;
+  static constexpr int kThr = -1;   // threshold = delta for every hypothesis
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return fma2(q[0], x[0], fma2(q[1], x[1], fma2(q[2], x[2], q[3]))); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
 };
 template <> struct Eval<PLANE4> {
   static constexpr bool kHasAbsForm = true;
+  static constexpr int kThr = -1;   // threshold = delta for every hypothesis
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return fma2(q[0], x[0], fma2(q[1], x[1], fma2(q[2], x[2], fma2(q[3], x[3], q[4])))); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
 };
 template <> struct Eval<LINE2D> {
   static constexpr bool kHasAbsForm = true;
+  static constexpr int kThr = -1;   // threshold = delta for every hypothesis
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return fma2(q[0], x[0], fma2(q[1], x[1], q[2])); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
 };
@@ -236,37 +239,35 @@ template <int DIM> __device__ __forceinline__ f2 line_signed(const f2* q, const 
 }
 template <> struct Eval<LINE2> {
   static constexpr bool kHasAbsForm = false;
+  static constexpr int kThr = -1;
   __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { return line_signed<2>(q, x, t); }
 };
 template <> struct Eval<LINE3> {
   static constexpr bool kHasAbsForm = false;
+  static constexpr int kThr = -1;
   __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { return line_signed<3>(q, x, t); }
 };
-template <int DIM> __device__ __forceinline__ f2 sphere_signed(const f2* q, const f2* x) {
+// d^2 - m: the sphere test |d - r| < delta becomes |d^2 - m| < w with a per-hypothesis threshold w (q[DIM + 1])
+template <int DIM> __device__ __forceinline__ f2 sphere_t(const f2* q, const f2* x) {
   f2 t = q[DIM];  // -m
 #pragma unroll
   for (int i = 0; i < DIM; i++) { const f2 w = sub2(x[i], q[i]); t = fma2(w, w, t); }
-  return fma2(t, t, q[DIM + 1]);  // (d^2 - m)^2 - w^2
+  return t;
 }
-template <> struct Eval<CIRCLE2> {
-  static constexpr bool kHasAbsForm = false;
-  __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
-  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2&) { return sphere_signed<2>(q, x); }
+template <int DIM> struct EvalSphere {
+  static constexpr bool kHasAbsForm = true;
+  static constexpr int kThr = DIM + 1;
+  __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return sphere_t<DIM>(q, x); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2&) { const f2 t = sphere_t<DIM>(q, x); return sub2(mul2(t, t), mul2(q[DIM + 1], q[DIM + 1])); }
 };
-template <> struct Eval<SPHERE3> {
-  static constexpr bool kHasAbsForm = false;
-  __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
-  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2&) { return sphere_signed<3>(q, x); }
-};
-template <> struct Eval<SPHERE4> {
-  static constexpr bool kHasAbsForm = false;
-  __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
-  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2&) { return sphere_signed<4>(q, x); }
-};
+template <> struct Eval<CIRCLE2> : EvalSphere<2> {};
+template <> struct Eval<SPHERE3> : EvalSphere<3> {};
+template <> struct Eval<SPHERE4> : EvalSphere<4> {};
 template <> struct Eval<ABSOR> {
   static constexpr bool kHasAbsForm = false;
+  static constexpr int kThr = -1;
   __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) {
     f2 g = t.neg_delta2;
@@ -280,6 +281,7 @@ template <> struct Eval<ABSOR> {
 };
 template <> struct Eval<RAY> {
   static constexpr bool kHasAbsForm = false;
+  static constexpr int kThr = -1;
   __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) {
     const f2 vx = sub2(q[0], x[0]), vy = sub2(q[1], x[1]), vz = sub2(q[2], x[2]);
@@ -295,6 +297,7 @@ template <> struct Eval<RAY> {
 };
 template <> struct Eval<PIVOT> {
   static constexpr bool kHasAbsForm = false;
+  static constexpr int kThr = -1;
   __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) {
     f2 g = t.neg_delta2;
@@ -316,11 +319,13 @@ template <int N> __device__ __forceinline__ f2 dense_dist(const f2* q, const f2*
 }
 template <> struct Eval<DENSE5> {
   static constexpr bool kHasAbsForm = true;
+  static constexpr int kThr = -1;   // threshold = delta for every hypothesis
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return dense_dist<5>(q, x); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
 };
 template <> struct Eval<DENSE6> {
   static constexpr bool kHasAbsForm = true;
+  static constexpr int kThr = -1;   // threshold = delta for every hypothesis
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return dense_dist<6>(q, x); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
 };
@@ -328,6 +333,7 @@ template <> struct Eval<DENSE6> {
 // cross-wire: e = R2 (u c1 + v c2 + t3) + t2 - t1, |e|^2 - delta^2   (21 FMA-pipe operations)
 template <> struct Eval<USXW> {
   static constexpr bool kHasAbsForm = false;
+  static constexpr int kThr = -1;
   __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) {
     f2 w[3];
@@ -346,6 +352,7 @@ template <> struct Eval<USXW> {
 // calibrated pointer: e = R2 (u c1 + v c2 + t3) + t2 - p
 template <> struct Eval<USCP> {
   static constexpr bool kHasAbsForm = false;
+  static constexpr int kThr = -1;
   __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) {
     f2 w[3];
@@ -361,6 +368,14 @@ template <> struct Eval<USCP> {
   }
 };
 
+template <int M> __device__ __forceinline__ float hyp_thr(const f2* q, float delta) {
+  if constexpr (Eval<M>::kThr >= 0) { float lo, hi; halves(q[Eval<M>::kThr], lo, hi); return lo; }
+  else return delta;
+}
+template <int M> __device__ __forceinline__ float hyp_thr(const float* q, float delta) {
+  if constexpr (Eval<M>::kThr >= 0) return q[Eval<M>::kThr];
+  else return delta;
+}
 // FSETP + predicated IADD on two residuals, written in PTX so that ptxas keeps the 2-instruction form.
 __device__ __forceinline__ void count_abs_lt(uint32_t& cnt, f2 s, float delta) {
   float a, b;
@@ -475,7 +490,8 @@ __global__ void __launch_bounds__(THREADS) consensus32_kernel(const float* __res
       for (int r = 0; r < R; r++) {
 #pragma unroll
         for (int u = 0; u < PPI; u++) {
-          if (Eval<M>::kHasAbsForm && (r % 3) != 0) count_abs_lt(cnt[r], Eval<M>::dist(q[r], x[u]), thr.fdelta);
+          // models with a per-hypothesis threshold always take the |.| < thr form (the same predicate as the constant-bank kernel)
+          if (Eval<M>::kHasAbsForm && (Eval<M>::kThr >= 0 || (r % 3) != 0)) count_abs_lt(cnt[r], Eval<M>::dist(q[r], x[u]), hyp_thr<M>(q[r], thr.fdelta));
           else count_sign(cnt[r], Eval<M>::signed_(q[r], x[u], thr));
         }
       }
@@ -581,9 +597,10 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
         for (int u = 0; u < PPI; u += 2) {
           // kRaw: 3 ALU instructions per two residuals.  Otherwise FSETP + predicated add, most of which ptxas puts on the
           // FMA-heavy pipe (VIADD) that the FFMA2s need: one hypothesis in LSQR_CB_MIX counts that way, the others with FSET.BF + LEA.HI
-          if constexpr (kRaw) count_abs_lt4_raw(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), thr.fdelta);
-          else if (r % LSQR_CB_MIX == 0) count_abs_lt4(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), thr.fdelta);
-          else count_abs_lt4_alu(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), thr.fdelta);
+          const float th = hyp_thr<M>(qf[r], thr.fdelta);
+          if constexpr (kRaw) count_abs_lt4_raw(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), th);
+          else if (r % LSQR_CB_MIX == 0) count_abs_lt4(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), th);
+          else count_abs_lt4_alu(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), th);
         }
       } else {
 #pragma unroll
@@ -605,32 +622,41 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
   }
 }
 
-// Hypotheses per thread / point pairs per iteration of the constant-bank kernel (128 threads, <= 80 registers).
+// Hypotheses per thread / point pairs per iteration of the constant-bank kernel (128 threads), from the sweep in
+// profiles/r01_tune_cb_sweep_models.txt.  Few hypotheses per thread (R = 4, 5) on a model with few operations per datum
+// make the uniform constant loads (D per point pair) the limit: 3-8x slower, see the plane4 / dense5 columns there.
 #ifndef LSQR_CB_THREADS
 #define LSQR_CB_THREADS 128
 #endif
 #ifndef LSQR_CB_R_PLANE
 #define LSQR_CB_R_PLANE 10
 #endif
+#ifdef LSQR_CB_SWEEP_R   // R&D builds (tools/build_variants.sh): one blocking for every model that can take it
+template <int M> struct BlockCB { static constexpr int R = LSQR_CB_SWEEP_R, PPI = LSQR_CB_SWEEP_PPI; };
+template <> struct BlockCB<PIVOT> { static constexpr int R = 6, PPI = 1; };
+template <> struct BlockCB<USXW> { static constexpr int R = 4, PPI = 1; };
+template <> struct BlockCB<USCP> { static constexpr int R = 4, PPI = 1; };
+#else
 template <int M> struct BlockCB { static constexpr int R = 8, PPI = 2; };
 #ifndef LSQR_CB_PPI_PLANE
 #define LSQR_CB_PPI_PLANE 4
 #endif
 template <> struct BlockCB<PLANE3> { static constexpr int R = LSQR_CB_R_PLANE, PPI = LSQR_CB_PPI_PLANE; };
 template <> struct BlockCB<LINE2D> { static constexpr int R = 10, PPI = 4; };
-template <> struct BlockCB<LINE2> { static constexpr int R = 10, PPI = 2; };
+template <> struct BlockCB<LINE2> { static constexpr int R = 6, PPI = 4; };
 template <> struct BlockCB<LINE3> { static constexpr int R = 8, PPI = 2; };
 template <> struct BlockCB<CIRCLE2> { static constexpr int R = 12, PPI = 2; };
 template <> struct BlockCB<SPHERE3> { static constexpr int R = 10, PPI = 2; };
-template <> struct BlockCB<ABSOR> { static constexpr int R = 4, PPI = 2; };
-template <> struct BlockCB<RAY> { static constexpr int R = 8, PPI = 2; };
+template <> struct BlockCB<ABSOR> { static constexpr int R = 4, PPI = 4; };
+template <> struct BlockCB<RAY> { static constexpr int R = 8, PPI = 4; };
 template <> struct BlockCB<PIVOT> { static constexpr int R = 6, PPI = 1; };
-template <> struct BlockCB<DENSE5> { static constexpr int R = 8, PPI = 2; };
-template <> struct BlockCB<DENSE6> { static constexpr int R = 8, PPI = 2; };
+template <> struct BlockCB<DENSE5> { static constexpr int R = 8, PPI = 4; };
+template <> struct BlockCB<DENSE6> { static constexpr int R = 8, PPI = 4; };
 template <> struct BlockCB<USXW> { static constexpr int R = 4, PPI = 1; };
 template <> struct BlockCB<USCP> { static constexpr int R = 4, PPI = 1; };
-template <> struct BlockCB<SPHERE4> { static constexpr int R = 8, PPI = 2; };
-template <> struct BlockCB<PLANE4> { static constexpr int R = 8, PPI = 2; };
+template <> struct BlockCB<SPHERE4> { static constexpr int R = 8, PPI = 4; };
+template <> struct BlockCB<PLANE4> { static constexpr int R = 8, PPI = 4; };
+#endif
 
 template <int M>
 static int run_consensus_cb(const DataView& dv, const float* hyp, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms, cudaStream_t s) {
