@@ -385,29 +385,6 @@ __device__ __forceinline__ void count_abs_lt(uint32_t& cnt, f2 s, float delta) {
       "@p0 add.u32 %0, %0, 1;\n\t@p1 add.u32 %0, %0, 1;\n\t}"
       : "+r"(cnt) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(delta));
 }
-// Four residuals (two point pairs) at once.
-__device__ __forceinline__ void count_abs_lt4(uint32_t& cnt, f2 s01, f2 s23, float delta) {
-  float a, b, c, d;
-  halves(s01, a, b);
-  halves(s23, c, d);
-  asm("{\n\t.reg .pred p0, p1, p2, p3;\n\t"
-      "setp.lt.f32 p0, %1, %5;\n\tsetp.lt.f32 p1, %2, %5;\n\tsetp.lt.f32 p2, %3, %5;\n\tsetp.lt.f32 p3, %4, %5;\n\t"
-      "@p0 add.u32 %0, %0, 1;\n\t@p1 add.u32 %0, %0, 1;\n\t@p2 add.u32 %0, %0, 1;\n\t@p3 add.u32 %0, %0, 1;\n\t}"
-      : "+r"(cnt) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)), "f"(fabsf(d)), "f"(delta));
-}
-// Same test with two ALU instructions per residual and nothing on the FMA-heavy pipe: FSET.BF writes
-// 1.0f (0x3F800000) or 0, whose top three bits are the count increment (LEA.HI cnt += f >> 29).
-__device__ __forceinline__ void count_abs_lt4_alu(uint32_t& cnt, f2 s01, f2 s23, float delta) {
-  float a, b, c, d;
-  halves(s01, a, b);
-  halves(s23, c, d);
-  asm("{\n\t.reg .f32 f0, f1, f2, f3;\n\t.reg .b32 t0, t1, t2, t3;\n\t"
-      "set.lt.f32.f32 f0, %1, %5;\n\tset.lt.f32.f32 f1, %2, %5;\n\tset.lt.f32.f32 f2, %3, %5;\n\tset.lt.f32.f32 f3, %4, %5;\n\t"
-      "mov.b32 t0, f0;\n\tmov.b32 t1, f1;\n\tmov.b32 t2, f2;\n\tmov.b32 t3, f3;\n\t"
-      "shr.u32 t0, t0, 29;\n\tshr.u32 t1, t1, 29;\n\tshr.u32 t2, t2, 29;\n\tshr.u32 t3, t3, 29;\n\t"
-      "add.u32 %0, %0, t0;\n\tadd.u32 %0, %0, t1;\n\tadd.u32 %0, %0, t2;\n\tadd.u32 %0, %0, t3;\n\t}"
-      : "+r"(cnt) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)), "f"(fabsf(d)), "f"(delta));
-}
 // Three ALU instructions per two residuals: the two FSET.BF results are summed as raw words by one IADD3
 // (raw += 0x3F800000 per inlier).  0x3F800000 = 127 << 23, so raw holds (127 k mod 512) << 23 and k is recovered
 // by cb_raw_decode() as long as no more than 511 inliers were summed since the last decode.
@@ -540,12 +517,6 @@ static std::mutex g_cb_mutex[16];             // the bank is per device, not per
 #ifndef LSQR_CB_MINBLOCKS
 #define LSQR_CB_MINBLOCKS 5
 #endif
-#ifndef LSQR_CB_MIX
-#define LSQR_CB_MIX 3
-#endif
-#ifndef LSQR_CB_RAW
-#define LSQR_CB_RAW 1
-#endif
 constexpr uint32_t kCbRawMaxSub = 496;       // <= 511 inliers per raw counter, multiple of 16
 template <int M> constexpr uint32_t cb_points() { return (uint32_t)(kCbFloats / Model<M>::D / 16 * 16); }   // points per launch
 
@@ -569,7 +540,7 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
   const uint32_t p0 = blockIdx.y * sub, p1 = min(p0 + sub, npts);
   const int g0 = (int)(p0 / (2 * PPI)), g1 = (int)(p1 / (2 * PPI));
   // raw-sum counting (count_abs_lt4_raw) holds 9 bits: the host keeps sub <= kCbRawMaxSub points per CTA
-  constexpr bool kRaw = LSQR_CB_RAW && Eval<M>::kHasAbsForm && PPI >= 2;
+  constexpr bool kRaw = Eval<M>::kHasAbsForm && PPI >= 2;
   // points of group g (2*PPI points) from the constant bank: uniform loads, the values live in uniform registers
   auto load_group = [&](f2 (&x)[PPI][D], int g) {
 #pragma unroll
@@ -592,16 +563,10 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
       f2 q[Q];
 #pragma unroll
       for (int j = 0; j < Q; j++) q[j] = splat(qf[r][j]);
-      if constexpr (Eval<M>::kHasAbsForm && PPI >= 2) {
+      if constexpr (kRaw) {
+        const float th = hyp_thr<M>(qf[r], thr.fdelta);
 #pragma unroll
-        for (int u = 0; u < PPI; u += 2) {
-          // kRaw: 3 ALU instructions per two residuals.  Otherwise FSETP + predicated add, most of which ptxas puts on the
-          // FMA-heavy pipe (VIADD) that the FFMA2s need: one hypothesis in LSQR_CB_MIX counts that way, the others with FSET.BF + LEA.HI
-          const float th = hyp_thr<M>(qf[r], thr.fdelta);
-          if constexpr (kRaw) count_abs_lt4_raw(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), th);
-          else if (r % LSQR_CB_MIX == 0) count_abs_lt4(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), th);
-          else count_abs_lt4_alu(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), th);
-        }
+        for (int u = 0; u < PPI; u += 2) count_abs_lt4_raw(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), th);
       } else {
 #pragma unroll
         for (int u = 0; u < PPI; u++) count_sign(cnt[r], Eval<M>::signed_(q, x[u], thr));
@@ -676,7 +641,7 @@ static int run_consensus_cb(const DataView& dv, const float* hyp, size_t hld, ui
   const uint32_t hyp_blocks = (H + THREADS * R - 1) / (THREADS * R);
   const uint32_t slots = (uint32_t)num_sms * (uint32_t)occ[dev & 15];
   // sub-chunks per launch: fill the last wave (the launches of one request serialise on the bank)
-  constexpr bool kRaw = LSQR_CB_RAW && Eval<M>::kHasAbsForm && PPI >= 2;
+  constexpr bool kRaw = Eval<M>::kHasAbsForm && PPI >= 2;
   auto pick_sub = [&](uint32_t npts) {
     uint32_t best_sub = kRaw ? std::min(npts, kCbRawMaxSub) : npts; double best_eff = 0.0;
     for (uint32_t nsub = 1; nsub <= 64; nsub++) {
