@@ -383,7 +383,10 @@ def plane(order, R, count, src="lds"):
             X, Y, Z = f"PX{pr}", f"PY{pr}", f"PZ{pr}"
             if order == "hm":
                 for r in range(R):
-                    b.emit(f"mov.b64 W0, {bc(f'hn{4*r+2}')}; mov.b64 W1, {bc(f'hn{4*r+3}')}; fma.rn.f32x2 T{r}, W0, {Z}, W1;")
+                    if count == "chain":
+                        b.emit(f"mov.b64 W0, {bc(f'hn{4*r+2}')}; fma.rn.f32x2 T{r}, W0, {Z}, T{r};")
+                    else:
+                        b.emit(f"mov.b64 W0, {bc(f'hn{4*r+2}')}; mov.b64 W1, {bc(f'hn{4*r+3}')}; fma.rn.f32x2 T{r}, W0, {Z}, W1;")
                     b.emit(f"mov.b64 W0, {bc(f'hn{4*r+1}')}; fma.rn.f32x2 T{r}, W0, {Y}, T{r};")
                     b.emit(f"mov.b64 W0, {bc(f'hn{4*r}')}; fma.rn.f32x2 T{r}, W0, {X}, T{r};")
                     counting(b, r, count, pr)
@@ -400,7 +403,20 @@ def plane(order, R, count, src="lds"):
 
 
 def counting(b, r, count, pr):
+    if count == "chain":
+        return
     b.emit(f"mov.b64 {{sl{r}, sh{r}}}, T{r};")
+    if count == "raw":      # 2 FSET.BF + one 3-input add of the raw words (the product kernel's form)
+        b.emit(f"abs.f32 x0, sl{r}; abs.f32 x1, sh{r}; set.lt.f32.f32 x2, x0, thr; set.lt.f32.f32 x3, x1, thr;")
+        b.emit(f"mov.b32 h0, x2; mov.b32 h1, x3; add.u32 t0, h0, h1; add.u32 cnt{r}, cnt{r}, t0;")
+        return
+    if count == "fset":     # 2 FSET.BF, results consumed by one LOP3 (keeps the ALU count at 3 but with no carry chain)
+        b.emit(f"abs.f32 x0, sl{r}; abs.f32 x1, sh{r}; set.lt.f32.f32 x2, x0, thr; set.lt.f32.f32 x3, x1, thr;")
+        b.emit(f"mov.b32 h0, x2; mov.b32 h1, x3; lop3.b32 cnt{r}, cnt{r}, h0, h1, 0x96;")
+        return
+    if count == "fset1":    # one FSET.BF per pair only (half the compares): where does the time go?
+        b.emit(f"abs.f32 x0, sl{r}; set.lt.f32.f32 x2, x0, thr; mov.b32 h0, x2; mov.b32 h1, sh{r}; add.u32 t0, h0, h1; add.u32 cnt{r}, cnt{r}, t0;")
+        return
     if count == "setp":
         b.emit(f"abs.f32 x0, sl{r}; abs.f32 x1, sh{r}; setp.lt.f32 q0, x0, thr; setp.lt.f32 q1, x1, thr;")
         b.emit(f"@q0 add.u32 cnt{r}, cnt{r}, 1; @q1 add.u32 cnt{r}, cnt{r}, 1;")
@@ -417,6 +433,9 @@ for R in (8,):
     for order in ("hm", "cm"):
         for count in ("none", "setpc", "setp", "sign"):
             VARIANTS[f"pl_{order}_{count}_R{R}"] = (f"plane kernel body, {order}, R={R}, counting={count}: {4*R} evals/slice, {6*R} FFMA2 (+{2*R} for sign)", plane(order, R, count))
+for R in (8, 10):
+    for count in ("chain", "raw", "fset", "fset1"):
+        VARIANTS[f"plc_{count}_R{R}"] = (f"plane body, points from the constant bank (LDCU -> UR operands), R={R}, counting={count}: {4*R} evals/slice", plane("hm", R, count, "const"))
 for R in (8, 12):
     for count in ("none", "setpc", "setp", "sign"):
         VARIANTS[f"plc_{count}_R{R}"] = (f"plane body, points from the constant bank (LDCU -> UR operands), R={R}, counting={count}: {4*R} evals/slice", plane("hm", R, count, "const"))
