@@ -948,7 +948,7 @@ __device__ void block_moments(const double* pts, uint32_t n, uint32_t ldp, const
 }
 
 template <int M>
-__global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int ls_type) {
+__global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int ls_type, uint32_t group) {
   constexpr int D = Model<M>::D, P = Model<M>::P, K = Model<M>::K, HQ = Model<M>::HQ;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* pts = reinterpret_cast<double*>(smem_raw);  // [D][ldp]
@@ -977,8 +977,13 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
 
   unsigned long long best = 0ull;
   const double log1mp = log(1.0 - a.prob);
-  for (unsigned long long done = 0; done < sh_tries; done += blockDim.x) {
-    const unsigned long long h = done + threadIdx.x;
+  // G threads share one hypothesis (each counts every G-th datum).  Randomized mode re-evaluates the stop rule after every
+  // round and ends in a single-thread refit, so it runs small blocks (many resident per SM) with short rounds; exhaustive
+  // mode is throughput-bound and scores one hypothesis per thread (launch_batch picks block size and G).
+  const uint32_t G = group;
+  const uint32_t per_round = blockDim.x / G, sub_lane = threadIdx.x % G;
+  for (unsigned long long done = 0; done < sh_tries; done += per_round) {
+    const unsigned long long h = done + threadIdx.x / G;
     unsigned long long key = 0ull;
     if (h < sh_tries) {
       int32_t sub[K];
@@ -988,17 +993,22 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
       for (int j = 0; j < K; j++)
 #pragma unroll
         for (int d = 0; d < D; d++) sp[j * D + d] = pts[d * ldp + sub[j]];
-      if (estimate<M>(sp, cfg, prm)) {
+      const bool ok = estimate<M>(sp, cfg, prm);   // the same for all G threads of a hypothesis
+      uint32_t c = 0;
+      if (ok) {
         prepare<M>(prm, hq);
-        uint32_t c = 0;
-        for (uint32_t i = 0; i < n; i++) {
+        for (uint32_t i = sub_lane; i < n; i += G) {
           double x[D];
 #pragma unroll
           for (int d = 0; d < D; d++) x[d] = pts[d * ldp + i];
           c += agree<M>(hq, x, cfg) ? 1u : 0u;
         }
-        key = ((unsigned long long)c << 32) | (0xFFFFFFFFull - h);
       }
+      if (G > 1) {   // uniform over the block; the G threads of a hypothesis are adjacent lanes of one warp
+        const unsigned grp = (0xFFFFFFFFu >> (32u - G)) << ((threadIdx.x & 31u) & ~(G - 1u));
+        for (uint32_t o = 1; o < G; o <<= 1) c += __shfl_xor_sync(grp, c, o);
+      }
+      if (ok) key = ((unsigned long long)c << 32) | (0xFFFFFFFFull - h);
     }
     const unsigned long long round_best = block_max_u64(key, sh_key);
     if (round_best > best) {
@@ -1114,7 +1124,14 @@ int launch_batch(const BatchArgs& a, const EstCfg& cfg, int ls_type, cudaStream_
   const int D = model_info(a.model).D;
   const size_t smem = (size_t)D * a.max_n * sizeof(double);
   if (smem > 200 * 1024) return -1;
-#define CALL(MM)                                                                                                    {                                                                                                                   auto kern = batch_kernel<MM>;                                                                                     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                              kern<<<a.n_problems, 256, smem, s>>>(a, cfg, ls_type);                                                          }
+  const int threads = a.exhaustive ? 256 : 64;
+  const uint32_t group = a.exhaustive ? 1u : 2u;
+#define CALL(MM)                                                                                  \
+  {                                                                                               \
+    auto kern = batch_kernel<MM>;                                                                 \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+    kern<<<a.n_problems, threads, smem, s>>>(a, cfg, ls_type, group);                            \
+  }
   switch (a.model) {
     case PLANE3: CALL(PLANE3) break;
     case LINE2D: CALL(LINE2D) break;
