@@ -193,7 +193,7 @@ def main():
     import torch
     import torch.distributed as dist
     from lsqrrecipes_b200 import FP32, FP64, SAMPLE_PHILOX, Engine
-    from lsqrrecipes_b200.dist import install_hooks
+    from lsqrrecipes_b200.dist import install_hooks, upload_replicated
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -282,8 +282,15 @@ def main():
     # e2e: host buffers in, mask + parameters out, everything inside the timed region
     e2e = None
     if not args.no_e2e:
+        def upload_from_host():
+            # N > 1: every rank needs all points; 1/world of the bytes per PCIe link, NCCL all-gather over NVLink for the rest
+            if world > 1:
+                upload_replicated(eng, host, rank, world)
+            else:
+                eng.upload_ptr(host.data_ptr(), N, data.shape[1] * 8)
+
         def e2e_step(seed):
-            eng.upload_ptr(host.data_ptr(), N, data.shape[1] * 8)
+            upload_from_host()
             r = eng.score(count=Hglobal, sampler=SAMPLE_PHILOX, precision=precision, seed=seed)
             cnt = eng.consensus(r["best_params"])
             mask = eng.get_mask()
@@ -308,7 +315,7 @@ def main():
         for s in range(4):
             barrier()
             t0 = time.perf_counter()
-            eng.upload_ptr(host.data_ptr(), N, data.shape[1] * 8)
+            upload_from_host()
             comp = eng.ransac(0.999, precision=precision, seed=100 + s)
             comp_ms.append(1e3 * (time.perf_counter() - t0))
         tc = torch.tensor([float(np.median(comp_ms[1:]))], dtype=torch.float64, device="cuda")

@@ -7,7 +7,9 @@ global, so results do not depend on W), and exactly two exchange steps:
      count wins, ties go to the smallest index -- the strict '>' of RANSAC.hxx:100,245;
   2. one all-reduce(SUM) of <= 32 doubles per refine pass (per LM iteration for the sphere):
      the least-squares moments of the point shards.
-Both run in place on device memory through the hooks of lsqr_set_shard.  The helpers below are
+Both run in place on device memory through the hooks of lsqr_set_shard.  Replicating the points is the one bulk
+transfer: `upload_replicated` moves 1/W of the host buffer over each GPU's PCIe link and lets an NCCL all-gather over
+NVLink / NVSwitch fan it out, instead of W full uploads competing for the host's memory bandwidth.  The helpers below are
 pure functions so that the N>1 logic is testable with gloo on CPU.
 """
 import ctypes
@@ -79,3 +81,43 @@ def install_hooks(engine, rank, world, group=None):
             return 1
 
     engine.set_shard(rank, world, max_hook, sum_hook)
+
+
+def upload_slice(n, rank, world):
+    """[begin, end) of the records that `rank` copies from the host, and the padded slice length used by the all-gather."""
+    per = (n + world - 1) // world
+    return min(rank * per, n), min((rank + 1) * per, n), per
+
+
+_GATHER_CACHE = {}
+
+
+def gather_replicated(host, rank, world, device, group=None):
+    """host: [n, D] float64 tensor holding (at least) this rank's slice.  Returns the full [n, D] tensor on `device`:
+    own slice copied host -> device, the rest by all-gather."""
+    import torch
+    import torch.distributed as dist
+
+    n, d = host.shape
+    lo, hi, per = upload_slice(n, rank, world)
+    key = (str(device), per * world, d)
+    full = _GATHER_CACHE.get(key)
+    if full is None:
+        full = _GATHER_CACHE[key] = torch.empty((per * world, d), dtype=torch.float64, device=device)
+    mine = full[rank * per:(rank + 1) * per]
+    if hi > lo:
+        mine[: hi - lo].copy_(host[lo:hi], non_blocking=True)
+    if world > 1:
+        dist.all_gather_into_tensor(full, mine, group=group) if full.is_cuda else \
+            dist.all_gather(list(full.view(world, per, d).unbind(0)), mine.clone(), group=group)
+    return full[:n]
+
+
+def upload_replicated(engine, host, rank, world, group=None):
+    """RANSAC::compute's `data` argument for W ranks that all need every point: 1/W of the bytes per PCIe link, the rest
+    over NVLink.  `host` is a pinned [n, D] float64 torch tensor (packed records)."""
+    import torch
+
+    full = gather_replicated(host, rank, world, torch.device("cuda", torch.cuda.current_device()), group)
+    engine.upload_device(full.data_ptr(), host.shape[0])
+    return full

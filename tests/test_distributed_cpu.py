@@ -29,6 +29,15 @@ def test_shard_formulas_cover_everything():
             assert all(s[0] % 32 == 0 for s in spans)
 
 
+def test_upload_slices_tile_the_data():
+    for n in (0, 1, 7, 1000, 10_000_000):
+        for world in (1, 2, 3, 8):
+            spans = [ldist.upload_slice(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert all(s[1] - s[0] <= s[2] for s in spans) and len({s[2] for s in spans}) == 1
+
+
 def test_packed_key_orders_like_the_reference():
     # larger count wins; equal counts -> smaller index wins (strict '>' of RANSAC.hxx:100,245)
     assert ldist.pack_key(10, 5) > ldist.pack_key(9, 0)
@@ -62,7 +71,14 @@ def _worker(rank, world, port_no, out_q):
     pts = data[b:e][mask.astype(bool)]
     mom = torch.tensor(np.concatenate([[len(pts)], pts.sum(0), (pts[:, :, None] * pts[:, None, :]).reshape(len(pts), 9).sum(0)]))
     dist.all_reduce(mom, op=dist.ReduceOp.SUM)                      # exchange step 2
-    out_q.put((rank, cnt, idx, mom.numpy()))
+    # replication of the points: each rank contributes its slice, the all-gather rebuilds the whole buffer
+    odd, _ = synth.plane(1001, seed=9)
+    mine = torch.from_numpy(odd.copy())
+    lo_u, hi_u, _ = ldist.upload_slice(len(odd), rank, world)
+    mine[:lo_u] = -1.0                                               # a rank only needs to hold its own slice
+    mine[hi_u:] = -1.0
+    full = ldist.gather_replicated(mine, rank, world, torch.device("cpu"))
+    out_q.put((rank, cnt, idx, mom.numpy(), bool(np.array_equal(full.numpy(), odd))))
     dist.destroy_process_group()
 
 
@@ -88,6 +104,7 @@ def test_two_rank_gloo_matches_single_process(port):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, cnt, idx, mom in results:
+    for rank, cnt, idx, mom, replicated in results:
         assert (cnt, idx) == (int(counts[want_idx]), want_idx)
         assert np.allclose(mom, want_mom, rtol=1e-12, atol=1e-6)
+        assert replicated, "all-gather of the per-rank slices must rebuild the data exactly"
