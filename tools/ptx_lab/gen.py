@@ -130,6 +130,7 @@ class Body:
     def __init__(self):
         self.lines = []
         self.unpacked = set()
+        self.nsrc = 16          # accumulators that the main instructions of the slice keep loop-varying
 
     def emit(self, s):
         self.lines.append("  " + s)
@@ -180,8 +181,8 @@ class Body:
     def src(self, j, scalar):
         """j-th loop-varying float source: halves of the FFMA2 accumulators, or the scalar FFMA accumulators."""
         if scalar:
-            return f"fa{j % 16}"
-        i = (j // 2) % 16
+            return f"fa{j % self.nsrc}"
+        i = (j // 2) % self.nsrc
         self.unpack(i)
         return (f"lo{i}" if j % 2 == 0 else f"hi{i}")
 
@@ -239,6 +240,18 @@ class Body:
         self.emit("min.f32 x4, x0, x1, x2;")
         self.emit("min.f32 x4, x4, x3;")
         self.emit(f"setp.lt.and.f32 p{j % 4}, x4, thr, p{j % 4};")
+
+    def fsetbf(self, j, scalar):   # FSET.BF only; results folded with a 2-input add every other op to keep them live
+        x = self.src(j, scalar)
+        self.emit(f"abs.f32 x0, {x};")
+        self.emit(f"set.lt.f32.f32 x1, x0, thr;")
+        self.emit(f"mov.b32 h0, x1; add.u32 cnt{j % 8}, cnt{j % 8}, h0;")
+
+    def raw3(self, j, scalar):     # the product kernel's counting: 2 FSET.BF + one 3-input add
+        a, b = self.src(2 * j, scalar), self.src(2 * j + 1, scalar)
+        self.emit(f"abs.f32 x0, {a}; abs.f32 x1, {b};")
+        self.emit(f"set.lt.f32.f32 x2, x0, thr; set.lt.f32.f32 x3, x1, thr;")
+        self.emit(f"mov.b32 h0, x2; mov.b32 h1, x3; add.u32 t0, h0, h1; add.u32 cnt{j % 8}, cnt{j % 8}, t0;")
 
     def leahi(self, j, scalar):
         x = self.src(j, scalar)
@@ -312,6 +325,7 @@ def variant(name, desc):
 def simple(name, desc, main, nmain, aux=None, naux=0, scalar=False):
     def fn(b, u):
         m = getattr(b, main)
+        b.nsrc = min(nmain, 16)
         if aux is None:
             for i in range(nmain):
                 m(i, u)
@@ -347,6 +361,14 @@ simple("f2_12_min3_2", "12 FFMA2 + 2 x (min3, min, FSETP chain) over 4 values", 
 simple("f1_12_setpc_4", "12 FFMA + 4 FSETP(pred chain)", "ffma", 12, "setp_chain", 4, True)
 simple("f1_12_sp_4", "12 FFMA + 4 (FSETP + @p add)", "ffma", 12, "setp_padd", 4, True)
 simple("f1_12_leahi_4", "12 FFMA + 4 LEA.HI", "ffma", 12, "leahi", 4, True)
+simple("f1_8_fsetbf_8", "8 FFMA + 8 x (FSET.BF + 2-input add)", "ffma", 8, "fsetbf", 8, True)
+simple("f1_8_raw3_4", "8 FFMA + 4 x (2 FSET.BF + IADD3 with 3 register inputs)", "ffma", 8, "raw3", 4, True)
+simple("f1_8_iadd3_4", "8 FFMA + 4 IADD3 (3 register inputs)", "ffma", 8, "iadd3", 4, True)
+simple("f1_8_leahi_8", "8 FFMA + 8 LEA.HI", "ffma", 8, "leahi", 8, True)
+simple("f1_8_setpc_8", "8 FFMA + 8 FSETP (pred chain)", "ffma", 8, "setp_chain", 8, True)
+simple("f2_8_raw3_4", "8 FFMA2 + 4 x (2 FSET.BF + IADD3)  [2D line ratio 2:2:1]", "ffma2", 8, "raw3", 4)
+simple("f2_12_raw3_4", "12 FFMA2 + 4 x (2 FSET.BF + IADD3)  [plane ratio 3:2:1]", "ffma2", 12, "raw3", 4)
+simple("f2_16_raw3_4", "16 FFMA2 + 4 x (2 FSET.BF + IADD3)  [4:2:1]", "ffma2", 16, "raw3", 4)
 simple("setpc_8", "8 FSETP(pred chain) only (sources: scalar FFMA accumulators, 2 FFMA to keep them varying)", "ffma", 2, "setp_chain", 8, True)
 simple("leahi_8", "8 LEA.HI only (+2 FFMA)", "ffma", 2, "leahi", 8, True)
 simple("sp_8", "8 (FSETP + @p add) only (+2 FFMA)", "ffma", 2, "setp_padd", 8, True)
