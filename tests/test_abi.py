@@ -81,3 +81,28 @@ def test_host_guards_need_no_gpu():
     out = [9.0]
     est.estimate([[0, 0, 0], [1, 0, 0]], out)   # fewer than k points: cleared, nothing computed
     assert out == []
+
+
+def test_estimator_mirrors_keep_the_reference_contracts():
+    """Constructor contracts of the reference's estimator classes, checked without a device: the minimal subset sizes
+    (`numForEstimate`, e.g. PlaneParametersEstimator.h:31 dimension, SphereParametersEstimator.h:37 dimension + 1), the
+    exception for an invalid least-squares type (SphereParametersEstimator.hxx:17-18) and a clear refusal of template
+    arguments that have no GPU path."""
+    import lsqrrecipes_b200 as L
+    want = [(L.PlaneParametersEstimator(0.5), 3), (L.PlaneParametersEstimator(0.5, dimension=4), 4),
+            (L.LineParametersEstimator(0.5, dimension=2), 2), (L.LineParametersEstimator(0.5), 2), (L.Line2DParametersEstimator(0.5), 2),
+            (L.SphereParametersEstimator(0.5, dimension=2), 3), (L.SphereParametersEstimator(0.5), 4),
+            (L.SphereParametersEstimator(0.5, dimension=4), 5), (L.AbsoluteOrientationParametersEstimator(2.0), 3),
+            (L.RayIntersectionParametersEstimator(1.0), 2), (L.PivotCalibrationEstimator(1.0), 3),
+            (L.DenseLinearEquationSystemParametersEstimator(0.5, 5), 5), (L.DenseLinearEquationSystemParametersEstimator(0.5, 6), 6),
+            (L.SingleUnknownPointTargetUSCalibrationParametersEstimator(1.0), 4),
+            (L.CalibratedPointerTargetUSCalibrationParametersEstimator(1.0), 3)]
+    for est, k in want:
+        assert est.numForEstimate() == k, type(est).__name__
+        assert api.MODEL_INFO[api.MODELS[est._model]][2] == k
+    with pytest.raises(ValueError):
+        L.SphereParametersEstimator(0.5, lsType=7)
+    for bad in (lambda: L.PlaneParametersEstimator(0.5, dimension=5), lambda: L.SphereParametersEstimator(0.5, dimension=5),
+                lambda: L.LineParametersEstimator(0.5, dimension=4), lambda: L.DenseLinearEquationSystemParametersEstimator(0.5, 7)):
+        with pytest.raises((NotImplementedError, ValueError)):
+            bad()
