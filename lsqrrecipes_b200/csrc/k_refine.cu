@@ -313,13 +313,16 @@ __host__ __device__ inline bool centred_comp(int model, int d) {
 // HBM-bound streaming pass.  Two resident CTAs per SM (grid = 2 x SMs, one wave); every warp keeps
 // U rows of 32 data (U*D 8-byte loads per lane, ~48 registers) in flight before it touches them, so
 // that ~100 KB per SM are outstanding -- what a 6.5 TB/s stream needs at ~600 ns latency.
+// Models with more than 40 accumulators per thread (the two ultrasound calibrations: 55-91 doubles) get the whole register
+// file of an SM for one CTA; with two resident CTAs their accumulators spill to local memory.
+template <int M, bool LM> constexpr int mm_ctas() { return ((LM ? Mom<M>::NLM : Mom<M>::N) > 40) ? 1 : LSQR_MM_CTAS; }
 template <int M, int MODE, bool LM>
-__global__ void __launch_bounds__(256, LSQR_MM_CTAS) mask_moments_kernel(DataView dv, uint32_t begin, uint32_t end, const double* __restrict__ params_dev,
+__global__ void __launch_bounds__(256, mm_ctas<M, LM>()) mask_moments_kernel(DataView dv, uint32_t begin, uint32_t end, const double* __restrict__ params_dev,
                                                                const double* __restrict__ lm_state, EstCfg cfg, uint32_t* __restrict__ maskbits,
                                                                double* __restrict__ partials) {
   constexpr int D = Model<M>::D, P = Model<M>::P, HQ = Model<M>::HQ;
   constexpr int NM = LM ? Mom<M>::NLM : Mom<M>::N;
-  constexpr int U = LM ? 4 : (D <= 3 ? LSQR_MM_U : (D <= 6 ? 4 : 2));
+  constexpr int U = D > 6 ? (LM ? 1 : 2) : (LM ? 4 : (D <= 3 ? LSQR_MM_U : 4));
   double acc[NM > 0 ? NM : 1];
 #pragma unroll
   for (int j = 0; j < NM; j++) acc[j] = 0.0;
