@@ -14,6 +14,12 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    # a fresh checkout has no built artefacts (they are git-ignored): build once, in-tree, the way the driver does
+    lib = os.path.join(ROOT, "lsqrrecipes_b200", "liblsqr_b200.so")
+    if not os.path.exists(lib):
+        import shutil
+        if shutil.which("nvcc"):
+            subprocess.check_call([sys.executable, "-c", "import __graft_entry__ as g; g.build()"], cwd=ROOT)
 
 
 @pytest.fixture(scope="session")
