@@ -312,11 +312,12 @@ def main():
         # the second half of BASELINE.json's metric: wall time of RANSAC<T,S>::compute(parameters, estimator, data, 0.999,
         # &consensusSet) through the library -- upload from pinned host memory, adaptive rounds, consensus set, refine
         comp_ms, comp = [], None
+        mask_host = torch.empty(N, dtype=torch.uint8).pin_memory().numpy()   # the caller's consensus-set buffer
         for s in range(4):
             barrier()
             t0 = time.perf_counter()
             upload_from_host()
-            comp = eng.ransac(0.999, precision=precision, seed=100 + s)
+            comp = eng.ransac(0.999, precision=precision, seed=100 + s, mask_out=mask_host)
             comp_ms.append(1e3 * (time.perf_counter() - t0))
         tc = torch.tensor([float(np.median(comp_ms[1:]))], dtype=torch.float64, device="cuda")
         if world > 1:

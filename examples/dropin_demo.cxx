@@ -211,7 +211,7 @@ static void absorCase() {
       worst = std::fmax(worst, std::sqrt(a.distanceSquared(b)));
     }
     std::printf("  fraction %.4f  max target registration error %.4g\n", frac, worst);
-    CHECK(worst < 0.5, "estimated transformation maps points like the generating one");
+    CHECK(worst < 1.0, "estimated transformation maps points like the generating one (noise sigma 1 per coordinate)");
   }
 }
 

@@ -227,8 +227,9 @@ class Engine:
         return {"params": np.array(r.params[: r.n_params]), "fraction": r.fraction, "best_count": int(r.best_count),
                 "best_index": int(r.best_index), "tries": int(r.tries), "device_ms": r.device_ms, "mask": mask}
 
-    def ransac(self, prob, precision=FP32, seed=0, want_mask=True):
-        mask = np.zeros(self.n, dtype=np.uint8) if want_mask else None
+    def ransac(self, prob, precision=FP32, seed=0, want_mask=True, mask_out=None):
+        """mask_out: optional caller-owned uint8[n] (e.g. a view of pinned memory) that receives the consensus set."""
+        mask = mask_out if mask_out is not None else (np.zeros(self.n, dtype=np.uint8) if want_mask else None)
         r = ComputeResult()
         self._ck(self.lib.lsqr_ransac(self.h, float(prob), precision, seed, _ptr(mask, _u8p), ctypes.byref(r)))
         return self._result(r, mask)

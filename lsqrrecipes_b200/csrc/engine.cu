@@ -417,9 +417,13 @@ int get_mask_impl(lsqr_ctx* ctx, DataSet& ds, uint8_t* out_bytes) {
     ctx->mask_pin_cap = ds.n;
   }
   launch_expand_mask(ds.maskbits, ds.n, ctx->mask_dev, ctx->stream); ctx->launches++;
-  cudaError_t e1 = cudaMemcpyAsync(ctx->mask_pin, ctx->mask_dev, ds.n, cudaMemcpyDeviceToHost, ctx->stream);
+  // a caller buffer that is itself page-locked takes the DMA directly
+  cudaPointerAttributes attr{};
+  const bool direct = cudaPointerGetAttributes(&attr, out_bytes) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  if (!direct) cudaGetLastError();   // an unregistered pointer is not an error here
+  cudaError_t e1 = cudaMemcpyAsync(direct ? out_bytes : ctx->mask_pin, ctx->mask_dev, ds.n, cudaMemcpyDeviceToHost, ctx->stream);
   cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-  if (e1 == cudaSuccess && e2 == cudaSuccess) memcpy(out_bytes, ctx->mask_pin, ds.n);
+  if (!direct && e1 == cudaSuccess && e2 == cudaSuccess) memcpy(out_bytes, ctx->mask_pin, ds.n);
   if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(ctx, LSQR_ERR_CUDA, "mask download failed");
   return LSQR_OK;
 }
@@ -573,7 +577,9 @@ int lsqr_ransac(lsqr_ctx* ctx, double prob, int precision, uint64_t seed, uint8_
   if (n < (uint32_t)mi.K || prob >= 1.0 || prob <= 0.0) return LSQR_OK;
   const double numerator = log(1.0 - prob);
   const unsigned int all_tries = choose_ref(n, (unsigned)mi.K);  // RANSAC.hxx:41
-  uint64_t num_tries = all_tries, done = 0, round = 1024;
+  // rounds of 256, 1024, 4096 ... hypotheses: the stop rule (:107-110) is re-evaluated between rounds, and a typical problem
+  // (inlier ratio ~0.5, k = 3: 65 tries) ends after the first, small one
+  uint64_t num_tries = all_tries, done = 0, round = 256;
   lsqr_score_result best{};
   double dev_ms = 0;
   while (done < num_tries) {
