@@ -147,7 +147,9 @@ int lsqr_score(lsqr_ctx* ctx, const lsqr_score_args* args, lsqr_score_result* re
  * (e.g. PlaneParametersEstimator.hxx:196-203): stores the consensus set on the device,
  * returns its size.  Replaces RANSAC.hxx:129-137. */
 int lsqr_consensus(lsqr_ctx* ctx, const double* params, uint32_t* out_count);
-/* Copy the stored consensus set to the host, one byte per datum (std::vector<bool> order). */
+/* Copy the stored consensus set to the host, one byte per datum (std::vector<bool> order).  A page-locked
+ * destination (cudaHostAlloc / cudaHostRegister) receives the DMA directly; any other is filled through the
+ * library's own staging buffer. */
 int lsqr_get_mask(lsqr_ctx* ctx, uint8_t* out_bytes);
 /* leastSquaresEstimate() over the stored consensus set (RANSAC.hxx:138), or over all data
  * when use_mask == 0.  *n_params = 0 means the reference's "empty parameters" (degenerate). */
@@ -165,8 +167,9 @@ typedef struct lsqr_compute_result {
 } lsqr_compute_result;
 
 /* RANSAC<T,S>::compute(parameters, estimator, data, desiredProbabilityForNoOutliers,
- * consensusSet) -- RANSAC.h:75-79 / RANSAC.hxx:4-145.  Rounds of Philox-sampled hypotheses;
- * the stop rule of RANSAC.hxx:107-110 is re-evaluated between rounds.  Invalid input
+ * consensusSet) -- RANSAC.h:75-79 / RANSAC.hxx:4-145.  Rounds of 256, 1024, 4096 ... Philox-sampled
+ * hypotheses; the stop rule of RANSAC.hxx:107-110 is re-evaluated between rounds, so at least as many
+ * hypotheses are scored as the reference's loop would try.  Invalid input
  * (N < k, prob outside (0,1)) returns LSQR_OK with fraction = 0, n_params = 0. */
 int lsqr_ransac(lsqr_ctx* ctx, double prob, int precision, uint64_t seed, uint8_t* out_mask_bytes,
                 lsqr_compute_result* res);
