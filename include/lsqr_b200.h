@@ -111,7 +111,10 @@ int lsqr_upload_device(lsqr_ctx* ctx, const double* dev_packed, size_t n);
 /* Multi-GPU sharding: this context scores hypotheses [rank*H/world, (rank+1)*H/world) of every
  * request and refines the points [rank*N/world, (rank+1)*N/world).  The two exchange steps go
  * through caller-supplied hooks operating IN PLACE on device memory (NCCL all-reduce over
- * NVLink in bench.py).  Hooks must be stream-ordered on `cuda_stream`. */
+ * NVLink in bench.py).  Hooks must be stream-ordered on `cuda_stream`.
+ * Counts, fractions and refined parameters are global; the consensus set a rank returns (lsqr_get_mask, the mask
+ * of lsqr_ransac) holds the bits of ITS point shard and zeros elsewhere -- OR the ranks' masks for the full set
+ * (lsqrrecipes_b200/dist.py: full_mask). */
 typedef int (*lsqr_allreduce_max_u64_fn)(void* user, uint64_t* dev_key, void* cuda_stream);
 typedef int (*lsqr_allreduce_sum_f64_fn)(void* user, double* dev_vals, int count, void* cuda_stream);
 int lsqr_set_shard(lsqr_ctx* ctx, int rank, int world, lsqr_allreduce_max_u64_fn max_fn,

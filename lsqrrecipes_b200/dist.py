@@ -121,3 +121,17 @@ def upload_replicated(engine, host, rank, world, group=None):
     full = gather_replicated(host, rank, world, torch.device("cuda", torch.cuda.current_device()), group)
     engine.upload_device(full.data_ptr(), host.shape[0])
     return full
+
+
+def full_mask(mask, group=None):
+    """In sharded mode a rank's consensus set covers its own point shard (zeros elsewhere): OR over the ranks = the set
+    RANSAC::compute returns.  `mask`: uint8[n] from Engine.get_mask() / Engine.ransac()."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return mask
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.from_numpy(np.ascontiguousarray(mask)).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return t.cpu().numpy()

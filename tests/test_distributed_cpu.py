@@ -78,7 +78,12 @@ def _worker(rank, world, port_no, out_q):
     mine[:lo_u] = -1.0                                               # a rank only needs to hold its own slice
     mine[hi_u:] = -1.0
     full = ldist.gather_replicated(mine, rank, world, torch.device("cpu"))
-    out_q.put((rank, cnt, idx, mom.numpy(), bool(np.array_equal(full.numpy(), odd))))
+    # consensus set: every rank holds the bits of its point shard, the OR over ranks is the whole set
+    part = np.zeros(n, dtype=np.uint8)
+    part[b:e] = mask
+    whole = ldist.full_mask(part)
+    _, want_mask = orc.agree(m, 0.5, best, data)
+    out_q.put((rank, cnt, idx, mom.numpy(), bool(np.array_equal(full.numpy(), odd)) and bool(np.array_equal(whole, want_mask))))
     dist.destroy_process_group()
 
 
