@@ -64,8 +64,8 @@ __device__ __forceinline__ f2 join(float lo, float hi) { f2 r; asm("mov.b64 %0, 
 // ---- hoisted fp32 hypotheses ---------------------------------------------------------------
 // Q32 floats per hypothesis, computed once in fp64 from the raw parameters, the data centre c
 // (positions are stored as x - c in fp32) and the thresholds:
-//   PLANE3   (nx,ny,nz, -n.(a-c))
-//   LINE2D   (nx,ny, -n.(a-c))
+//   PLANE3   (nx,ny,nz, delta - n.(a-c))      the kernels form s' = s + delta and test 0 <= s' < 2 delta (see count_carry)
+//   LINE2D   (nx,ny, -n.(a-c))                 |s| < delta (two FFMA2 per pair leave the ALU pipe as the limit either way; measured: the carry form is 4 % slower here)
 //   LINE2/3  (dir, a-c)
 //   CIRCLE/SPHERE (ctr-c, -m, w)  with  |d - r| < delta  <=>  |d^2 - m| < w,  m = r^2+delta^2, w = 2 r delta
 //   ABSOR    (R[9], R c1 + t - c2)
@@ -75,14 +75,14 @@ __device__ __forceinline__ f2 join(float lo, float hi) { f2 r; asm("mov.b64 %0, 
 //   USXW     (m_x R3(:,1), m_y R3(:,2), t3, t1 - c)
 //   USCP     (m_x R3(:,1), m_y R3(:,2), t3)
 template <int M> __device__ __forceinline__ void hoist32(const double* p, const double* c, const EstCfg& cfg, float* q);
-template <> __device__ __forceinline__ void hoist32<PLANE3>(const double* p, const double* c, const EstCfg&, float* q) {
+template <> __device__ __forceinline__ void hoist32<PLANE3>(const double* p, const double* c, const EstCfg& cfg, float* q) {
   q[0] = (float)p[0]; q[1] = (float)p[1]; q[2] = (float)p[2];
-  q[3] = (float)(-(p[0] * (p[3] - c[0]) + p[1] * (p[4] - c[1]) + p[2] * (p[5] - c[2])));
+  q[3] = (float)(cfg.delta - (p[0] * (p[3] - c[0]) + p[1] * (p[4] - c[1]) + p[2] * (p[5] - c[2])));   // shifted residual s + delta
 }
-template <> __device__ __forceinline__ void hoist32<PLANE4>(const double* p, const double* c, const EstCfg&, float* q) {
+template <> __device__ __forceinline__ void hoist32<PLANE4>(const double* p, const double* c, const EstCfg& cfg, float* q) {
   double s = 0;
   for (int i = 0; i < 4; i++) { q[i] = (float)p[i]; s += p[i] * (p[4 + i] - c[i]); }
-  q[4] = (float)(-s);
+  q[4] = (float)(cfg.delta - s);
 }
 template <> __device__ __forceinline__ void hoist32<LINE2D>(const double* p, const double* c, const EstCfg&, float* q) {
   q[0] = (float)p[0]; q[1] = (float)p[1];
@@ -208,19 +208,22 @@ struct Thr2 { f2 delta, neg_delta2; float fdelta; };
 template <int M> struct Eval;
 template <> struct Eval<PLANE3> {
   static constexpr bool kHasAbsForm = true;
-  static constexpr int kThr = -1;   // threshold = delta for every hypothesis
+  static constexpr int kThr = -1;
+  static constexpr bool kShifted = true;   // dist() is s + delta (the hoisted constant carries the shift)
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return fma2(q[0], x[0], fma2(q[1], x[1], fma2(q[2], x[2], q[3]))); }
-  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = sub2(dist(q, x), t.delta); return fma2(s, s, t.neg_delta2); }
 };
 template <> struct Eval<PLANE4> {
   static constexpr bool kHasAbsForm = true;
-  static constexpr int kThr = -1;   // threshold = delta for every hypothesis
+  static constexpr int kThr = -1;
+  static constexpr bool kShifted = true;   // dist() is s + delta (the hoisted constant carries the shift)
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return fma2(q[0], x[0], fma2(q[1], x[1], fma2(q[2], x[2], fma2(q[3], x[3], q[4])))); }
-  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = sub2(dist(q, x), t.delta); return fma2(s, s, t.neg_delta2); }
 };
 template <> struct Eval<LINE2D> {
   static constexpr bool kHasAbsForm = true;
-  static constexpr int kThr = -1;   // threshold = delta for every hypothesis
+  static constexpr int kThr = -1;
+  static constexpr bool kShifted = false;
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return fma2(q[0], x[0], fma2(q[1], x[1], q[2])); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
 };
@@ -240,12 +243,14 @@ template <int DIM> __device__ __forceinline__ f2 line_signed(const f2* q, const 
 template <> struct Eval<LINE2> {
   static constexpr bool kHasAbsForm = false;
   static constexpr int kThr = -1;
+  static constexpr bool kShifted = false;
   __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { return line_signed<2>(q, x, t); }
 };
 template <> struct Eval<LINE3> {
   static constexpr bool kHasAbsForm = false;
   static constexpr int kThr = -1;
+  static constexpr bool kShifted = false;
   __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { return line_signed<3>(q, x, t); }
 };
@@ -259,6 +264,7 @@ template <int DIM> __device__ __forceinline__ f2 sphere_t(const f2* q, const f2*
 template <int DIM> struct EvalSphere {
   static constexpr bool kHasAbsForm = true;
   static constexpr int kThr = DIM + 1;
+  static constexpr bool kShifted = false;
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return sphere_t<DIM>(q, x); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2&) { const f2 t = sphere_t<DIM>(q, x); return sub2(mul2(t, t), mul2(q[DIM + 1], q[DIM + 1])); }
 };
@@ -268,6 +274,7 @@ template <> struct Eval<SPHERE4> : EvalSphere<4> {};
 template <> struct Eval<ABSOR> {
   static constexpr bool kHasAbsForm = false;
   static constexpr int kThr = -1;
+  static constexpr bool kShifted = false;
   __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) {
     f2 g = t.neg_delta2;
@@ -282,6 +289,7 @@ template <> struct Eval<ABSOR> {
 template <> struct Eval<RAY> {
   static constexpr bool kHasAbsForm = false;
   static constexpr int kThr = -1;
+  static constexpr bool kShifted = false;
   __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) {
     const f2 vx = sub2(q[0], x[0]), vy = sub2(q[1], x[1]), vz = sub2(q[2], x[2]);
@@ -298,6 +306,7 @@ template <> struct Eval<RAY> {
 template <> struct Eval<PIVOT> {
   static constexpr bool kHasAbsForm = false;
   static constexpr int kThr = -1;
+  static constexpr bool kShifted = false;
   __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) {
     f2 g = t.neg_delta2;
@@ -320,12 +329,14 @@ template <int N> __device__ __forceinline__ f2 dense_dist(const f2* q, const f2*
 template <> struct Eval<DENSE5> {
   static constexpr bool kHasAbsForm = true;
   static constexpr int kThr = -1;   // threshold = delta for every hypothesis
+  static constexpr bool kShifted = false;
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return dense_dist<5>(q, x); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
 };
 template <> struct Eval<DENSE6> {
   static constexpr bool kHasAbsForm = true;
   static constexpr int kThr = -1;   // threshold = delta for every hypothesis
+  static constexpr bool kShifted = false;
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return dense_dist<6>(q, x); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
 };
@@ -334,6 +345,7 @@ template <> struct Eval<DENSE6> {
 template <> struct Eval<USXW> {
   static constexpr bool kHasAbsForm = false;
   static constexpr int kThr = -1;
+  static constexpr bool kShifted = false;
   __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) {
     f2 w[3];
@@ -353,6 +365,7 @@ template <> struct Eval<USXW> {
 template <> struct Eval<USCP> {
   static constexpr bool kHasAbsForm = false;
   static constexpr int kThr = -1;
+  static constexpr bool kShifted = false;
   __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) {
     f2 w[3];
@@ -384,6 +397,21 @@ __device__ __forceinline__ void count_abs_lt(uint32_t& cnt, f2 s, float delta) {
       "setp.lt.f32 p0, %1, %3;\n\tsetp.lt.f32 p1, %2, %3;\n\t"
       "@p0 add.u32 %0, %0, 1;\n\t@p1 add.u32 %0, %0, 1;\n\t}"
       : "+r"(cnt) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(delta));
+}
+// Outlier counting through the carry chain, for residuals in the shifted form s' = s + delta (inlier <=> 0 <= s' < 2 delta
+// <=> bits(s') < bits(2 delta) as unsigned integers: negative floats, NaN and everything >= 2 delta have larger bit patterns).
+// The counter is the HIGH word of a 64-bit value whose low word is replaced by bits(s') before a 64-bit add of
+// 2^32 - bits(2 delta): the carry out of the low word is the outlier flag.  ptxas turns two such steps into
+//   IADD3 RZ, P0, PT, s0, -K, RZ ;  IADD3 RZ, P1, PT, s1, -K, RZ ;  IADD3.X cnt, PT, PT, RZ, RZ, cnt, P1, P0
+// i.e. three ALU instructions per two residuals with ONE register operand each (no value but the counter is written).
+__device__ __forceinline__ void count_carry(unsigned long long& acc, f2 s, uint32_t negk) {   // negk = 2^32 - bits(2 delta)
+  float a, b;
+  halves(s, a, b);
+  asm("{\n\t.reg .b64 w, k;\n\t.reg .b32 lo, hi;\n\t"
+      "cvt.u64.u32 k, %3;\n\t"
+      "mov.b64 {lo, hi}, %0;\n\tmov.b64 w, {%1, hi};\n\tadd.u64 %0, w, k;\n\t"
+      "mov.b64 {lo, hi}, %0;\n\tmov.b64 w, {%2, hi};\n\tadd.u64 %0, w, k;\n\t}"
+      : "+l"(acc) : "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(negk));
 }
 // Three ALU instructions per two residuals: the two FSET.BF results are summed as raw words by one IADD3
 // (raw += 0x3F800000 per inlier).  0x3F800000 = 127 << 23, so raw holds (127 k mod 512) << 23 and k is recovered
@@ -422,6 +450,7 @@ __global__ void __launch_bounds__(THREADS) consensus32_kernel(const float* __res
   const uint32_t hbase = blockIdx.x * (THREADS * R);
   f2 q[R][Q];
   uint32_t cnt[R];
+  unsigned long long out[R];   // kShifted models: outliers in the high word (count_carry)
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const uint32_t h = hbase + r * THREADS + tid;
@@ -430,9 +459,11 @@ __global__ void __launch_bounds__(THREADS) consensus32_kernel(const float* __res
 #pragma unroll
     for (int j = 0; j < Q; j++) q[r][j] = splat(qs[j]);
     cnt[r] = 0;
+    out[r] = 0ull;
   }
   Thr2 thr;
   thr.delta = splat(delta); thr.neg_delta2 = splat(-delta2); thr.fdelta = delta;
+  const uint32_t negk = 0u - __float_as_uint(2.0f * delta);   // 2^32 - bits(2 delta)
 
   const uint32_t t0 = blockIdx.y * tiles_per_chunk;
   const uint32_t t1 = min(t0 + tiles_per_chunk, tiles_total);
@@ -467,8 +498,10 @@ __global__ void __launch_bounds__(THREADS) consensus32_kernel(const float* __res
       for (int r = 0; r < R; r++) {
 #pragma unroll
         for (int u = 0; u < PPI; u++) {
-          // models with a per-hypothesis threshold always take the |.| < thr form (the same predicate as the constant-bank kernel)
-          if (Eval<M>::kHasAbsForm && (Eval<M>::kThr >= 0 || (r % 3) != 0)) count_abs_lt(cnt[r], Eval<M>::dist(q[r], x[u]), hyp_thr<M>(q[r], thr.fdelta));
+          // the predicate must be the constant-bank kernel's: shifted models count through the carry chain, models with a
+          // per-hypothesis threshold always take the |.| < thr form
+          if constexpr (Eval<M>::kShifted) count_carry(out[r], Eval<M>::dist(q[r], x[u]), negk);
+          else if (Eval<M>::kHasAbsForm && (Eval<M>::kThr >= 0 || (r % 3) != 0)) count_abs_lt(cnt[r], Eval<M>::dist(q[r], x[u]), hyp_thr<M>(q[r], thr.fdelta));
           else count_sign(cnt[r], Eval<M>::signed_(q[r], x[u], thr));
         }
       }
@@ -478,6 +511,7 @@ __global__ void __launch_bounds__(THREADS) consensus32_kernel(const float* __res
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const uint32_t h = hbase + r * THREADS + tid;
+    if constexpr (Eval<M>::kShifted) cnt[r] = (t1 - t0) * (uint32_t)TILE - (uint32_t)(out[r] >> 32);   // NaN padding counts as outliers
     if (h < H && cnt[r]) atomicAdd(&counts[h], cnt[r]);
   }
 }
@@ -529,18 +563,22 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
   const uint32_t hbase = blockIdx.x * (THREADS * R);
   float qf[R][Q];
   uint32_t cnt[R];
+  unsigned long long out[R];   // kShifted models: outliers in the high word (count_carry)
 #pragma unroll
   for (int r = 0; r < R; r++) {
     load_hyp32<Q>(hyp, hld, hbase + r * THREADS + tid, H, qf[r]);
     cnt[r] = 0;
+    out[r] = 0ull;
   }
+  const uint32_t negk = 0u - __float_as_uint(2.0f * delta);   // 2^32 - bits(2 delta)
   Thr2 thr;
   thr.delta = splat(delta); thr.neg_delta2 = splat(-delta2); thr.fdelta = delta;
   // one induction variable in units of 2*PPI points; the component offsets are immediates (cp is a multiple of 16)
   const uint32_t p0 = blockIdx.y * sub, p1 = min(p0 + sub, npts);
   const int g0 = (int)(p0 / (2 * PPI)), g1 = (int)(p1 / (2 * PPI));
   // raw-sum counting (count_abs_lt4_raw) holds 9 bits: the host keeps sub <= kCbRawMaxSub points per CTA
-  constexpr bool kRaw = Eval<M>::kHasAbsForm && PPI >= 2;
+  constexpr bool kCarry = Eval<M>::kShifted;
+  constexpr bool kRaw = Eval<M>::kHasAbsForm && PPI >= 2 && !kCarry;
   // points of group g (2*PPI points) from the constant bank: uniform loads, the values live in uniform registers
   auto load_group = [&](f2 (&x)[PPI][D], int g) {
 #pragma unroll
@@ -563,7 +601,10 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
       f2 q[Q];
 #pragma unroll
       for (int j = 0; j < Q; j++) q[j] = splat(qf[r][j]);
-      if constexpr (kRaw) {
+      if constexpr (kCarry) {
+#pragma unroll
+        for (int u = 0; u < PPI; u++) count_carry(out[r], Eval<M>::dist(q, x[u]), negk);
+      } else if constexpr (kRaw) {
         const float th = hyp_thr<M>(qf[r], thr.fdelta);
 #pragma unroll
         for (int u = 0; u < PPI; u += 2) count_abs_lt4_raw(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), th);
@@ -582,6 +623,7 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const uint32_t h = hbase + r * THREADS + tid;
+    if constexpr (kCarry) cnt[r] = (uint32_t)(g1 - g0) * (2u * PPI) - (uint32_t)(out[r] >> 32);   // NaN padding counts as outliers
     if constexpr (kRaw) cnt[r] = cb_raw_decode(cnt[r]);
     if (h < H && cnt[r]) atomicAdd(&counts[h], cnt[r]);
   }
@@ -641,7 +683,7 @@ static int run_consensus_cb(const DataView& dv, const float* hyp, size_t hld, ui
   const uint32_t hyp_blocks = (H + THREADS * R - 1) / (THREADS * R);
   const uint32_t slots = (uint32_t)num_sms * (uint32_t)occ[dev & 15];
   // sub-chunks per launch: fill the last wave (the launches of one request serialise on the bank)
-  constexpr bool kRaw = Eval<M>::kHasAbsForm && PPI >= 2;
+  constexpr bool kRaw = Eval<M>::kHasAbsForm && PPI >= 2 && !Eval<M>::kShifted;
   auto pick_sub = [&](uint32_t npts) {
     uint32_t best_sub = kRaw ? std::min(npts, kCbRawMaxSub) : npts; double best_eff = 0.0;
     for (uint32_t nsub = 1; nsub <= 64; nsub++) {
