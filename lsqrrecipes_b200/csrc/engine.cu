@@ -521,7 +521,12 @@ int lsqr_set_estimator(lsqr_ctx* ctx, int model, double delta, double aux, int l
     for (DataSet* ds : {&ctx->main, &ctx->scratch}) { cudaFree(ds->soa64); cudaFree(ds->soa32); cudaFree(ds->maskbits); *ds = DataSet(); }
   }
   ctx->model = model; ctx->delta = delta; ctx->aux = aux; ctx->ls_type = ls_type;
-  ctx->cfg.delta = delta;
+  // The reference keeps delta*delta for every estimator but the hypersphere, pivot and dense-system ones (e.g.
+  // PlaneParametersEstimator.hxx:16 vs SphereParametersEstimator.hxx:20), so the sign of delta is immaterial there; the device
+  // code that compares an unsquared residual (fp32 fast mode) gets |delta|.
+  const bool distance_threshold = model == LSQR_CIRCLE2 || model == LSQR_SPHERE3 || model == LSQR_SPHERE4 || model == LSQR_PIVOT ||
+                                  model == LSQR_DENSE5 || model == LSQR_DENSE6;
+  ctx->cfg.delta = distance_threshold ? delta : fabs(delta);
   ctx->cfg.delta2 = delta * delta;
   const double ang = aux > 0 ? aux : 0.017453292519943295769236907684886;  // RayIntersectionParametersEstimator.h:35
   double ce = sin(ang);

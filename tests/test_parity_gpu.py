@@ -239,6 +239,31 @@ def test_hyperplane_4d_operator_interface(port):
     assert abs(abs(n_est @ n_true) - 1.0) < 1e-6 and abs((np.array(out[4:]) - true[4:]) @ n_true) < 0.1
 
 
+def test_sign_of_delta_is_immaterial_where_the_reference_squares_it(port):
+    """PlaneParametersEstimator.hxx:16 stores delta*delta, so -0.5 and 0.5 are the same estimator (also in fp32 fast mode, whose
+    kernels compare an unsquared residual); SphereParametersEstimator.hxx:20 keeps delta itself: a negative one admits nothing."""
+    data, _ = synth.plane(20011, seed=3)
+    subs = synth.random_subsets(len(data), 3, 256, seed=4)
+    want, _ = port.score_subsets(MODELS["plane3"], -0.5, data, subs)
+    assert np.array_equal(want, port.score_subsets(MODELS["plane3"], 0.5, data, subs)[0])
+    pos, neg = Engine("plane3", 0.5), Engine("plane3", -0.5)
+    for eng in (pos, neg):
+        eng.upload(data)
+    for precision in (FP64, FP32):
+        a = pos.score(sampler=SAMPLE_LIST, subsets=subs, precision=precision, want_counts=True)["counts"]
+        b = neg.score(sampler=SAMPLE_LIST, subsets=subs, precision=precision, want_counts=True)["counts"]
+        assert np.array_equal(a, b)
+        if precision == FP64:
+            assert np.array_equal(a, want)
+    pos.close(); neg.close()
+    sdata, strue = synth.sphere(5000, 3, seed=5)
+    eng = Engine("sphere3", -0.5)
+    eng.upload(sdata)
+    for precision in (FP64, FP32):
+        assert eng.score(sampler=SAMPLE_PARAMS, params=strue[None, :], precision=precision, want_counts=True)["counts"][0] == 0
+    eng.close()
+
+
 def test_circle_agree_literals():
     """testing/SphereParametersEstimatorTest.cxx:280-296"""
     eng = Engine("circle2", 0.5)
