@@ -1,0 +1,60 @@
+"""Static checks on the built sm_100a code (cuobjdump, no GPU): the instruction forms DESIGN.md section 3 relies on are what ptxas
+actually emitted.  A compiler change that silently loses one of them would cost throughput, not correctness -- these tests are
+the tripwire."""
+import collections
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from lsqrrecipes_b200 import api
+
+pytestmark = pytest.mark.skipif(not shutil.which("cuobjdump"), reason="cuobjdump not available")
+
+
+@pytest.fixture(scope="module")
+def sass():
+    out = subprocess.run(["cuobjdump", "-sass", api.lib_path()], capture_output=True, text=True, check=True).stdout
+    funcs, name = collections.defaultdict(list), None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(.*?);", line)
+        if m and name:
+            funcs[name].append(m.group(1).strip())
+    return funcs
+
+
+def _one(funcs, pattern):
+    hits = [k for k in funcs if re.search(pattern, k)]
+    assert hits, pattern
+    return funcs[hits[0]]
+
+
+def test_plane_kernel_counts_through_the_carry_chain(sass):
+    """consensus_cb_kernel<PLANE3, 10, 128, 4>: per pair of residuals 3 FFMA2 with a uniform-register point operand, two IADD3 that
+    write only a carry predicate and one IADD3.X that consumes two predicates; no FSET / FSETP / LEA.HI in the loop."""
+    ins = _one(sass, r"consensus_cb_kernelILi0ELi10ELi128ELi4E")
+    ffma2 = [i for i in ins if i.startswith("FFMA2")]
+    assert len(ffma2) >= 120 and sum("UR" in i for i in ffma2) >= 120, "points must come as uniform-register operands"
+    cmp_ = [i for i in ins if re.match(r"IADD3 RZ, P\d, PT, R\d+, UR\d+, RZ", i)]
+    addx = [i for i in ins if re.match(r"IADD3\.X R\d+, PT, PT, RZ, RZ, R\d+, P\d, P\d", i)]
+    assert len(cmp_) >= 80 and len(addx) >= 40, (len(cmp_), len(addx))
+    assert not [i for i in ins if i.startswith(("FSET", "FSETP"))]          # no float compare left in this kernel
+    assert sum(i.startswith("LEA.HI") for i in ins) <= 2                    # (index arithmetic outside the loop)
+    assert sum(i.startswith("LDCU") for i in ins) >= 12, "constant-bank loads"
+
+
+def test_sphere_kernel_uses_the_raw_sum_form(sass):
+    ins = _one(sass, r"consensus_cb_kernelILi5ELi10ELi128ELi2E")
+    assert sum(i.startswith("FSET.BF") for i in ins) >= 40 and sum(i.startswith("FFMA2") for i in ins) >= 60
+    assert sum(i.startswith("FADD2") for i in ins) >= 60
+
+
+def test_shared_memory_kernel_is_fed_by_tma(sass):
+    ins = _one(sass, r"consensus32_kernelILi0ELi9ELi256ELi512ELi2E")
+    assert any(i.startswith("UBLKCP") for i in ins), "cp.async.bulk (TMA) must be present"
+    assert any("SYNCS" in i for i in ins), "mbarrier wait"
