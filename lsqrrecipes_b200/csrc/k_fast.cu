@@ -511,7 +511,8 @@ __global__ void __launch_bounds__(THREADS) consensus32_kernel(const float* __res
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const uint32_t h = hbase + r * THREADS + tid;
-    if constexpr (Eval<M>::kShifted) cnt[r] = (t1 - t0) * (uint32_t)TILE - (uint32_t)(out[r] >> 32);   // NaN padding counts as outliers
+    // NaN padding counts as outliers; delta = 0 (bits(2 delta) = 0: no carry ever) admits nothing, like |s| < 0
+    if constexpr (Eval<M>::kShifted) cnt[r] = negk ? (t1 - t0) * (uint32_t)TILE - (uint32_t)(out[r] >> 32) : 0u;
     if (h < H && cnt[r]) atomicAdd(&counts[h], cnt[r]);
   }
 }
@@ -623,7 +624,8 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const uint32_t h = hbase + r * THREADS + tid;
-    if constexpr (kCarry) cnt[r] = (uint32_t)(g1 - g0) * (2u * PPI) - (uint32_t)(out[r] >> 32);   // NaN padding counts as outliers
+    // NaN padding counts as outliers; delta = 0 (bits(2 delta) = 0: no carry ever) admits nothing, like |s| < 0
+    if constexpr (kCarry) cnt[r] = negk ? (uint32_t)(g1 - g0) * (2u * PPI) - (uint32_t)(out[r] >> 32) : 0u;
     if constexpr (kRaw) cnt[r] = cb_raw_decode(cnt[r]);
     if (h < H && cnt[r]) atomicAdd(&counts[h], cnt[r]);
   }

@@ -256,6 +256,13 @@ def test_sign_of_delta_is_immaterial_where_the_reference_squares_it(port):
         if precision == FP64:
             assert np.array_equal(a, want)
     pos.close(); neg.close()
+    # delta = 0 admits nothing (|s| < 0), in both fp32 kernels and in fp64
+    zero = Engine("plane3", 0.0)
+    zero.upload(data)
+    assert zero.score(sampler=SAMPLE_LIST, subsets=subs, precision=FP32, want_counts=True)["counts"].max() == 0
+    assert zero.score(sampler=SAMPLE_LIST, subsets=subs, precision=FP64, want_counts=True)["counts"].max() == 0
+    assert zero.score(count=98304 + 64, seed=1, precision=FP32)["best_count"] == 0
+    zero.close()
     sdata, strue = synth.sphere(5000, 3, seed=5)
     eng = Engine("sphere3", -0.5)
     eng.upload(sdata)
