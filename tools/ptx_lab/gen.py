@@ -30,7 +30,7 @@ HEADER = """.version 8.8
   .reg .pred p<8>, q<8>, ploop;
   .reg .u32 cnt<16>, t<16>, iters, it, tid, one, msk;
   .reg .b32 h<16>;
-  .reg .b64 coff, cbase, ck0, ck1, gt0, gt1, PX<2>, PY<2>, PZ<2>, T<16>, HD<16>;
+  .reg .b64 coff, cbase, ck0, ck1, gt0, gt1, PX<2>, PY<2>, PZ<2>, T<16>, HD<16>, kneg;
   .reg .f32 hn<48>, sl<16>, sh<16>;
   .reg .u32 saddr, soff;
   .shared .align 16 .b8 tile[6144];
@@ -45,6 +45,9 @@ HEADER = """.version 8.8
   fma.rn.f32 thr, seed, 0f2F000000, 0f3F000000;     // ~0.5, run-time value
   fma.rn.f32 nthr2, seed, 0f2F000000, 0fBE800000;   // ~-0.25
   mov.u32 one, 1;
+  mov.b32 msk, thr;
+  neg.s32 msk, msk;
+  cvt.u64.u32 kneg, msk;                            // 2^32 - bits(thr): the addend of the carry-chain count
   // fill the shared tile (3 components x 512 floats) with run-time values
   mov.u32 saddr, tile;
   shl.b32 soff, tid, 2;
@@ -121,6 +124,7 @@ def consume():
         s.append(f"  selp.u32 t0, 1, 0, p{i}; add.u32 cnt0, cnt0, t0;")
     for i in range(16):
         s.append(f"  mov.b64 {{sl{i}, sh{i}}}, T{i}; mov.b32 t0, sl{i}; add.u32 cnt0, cnt0, t0; mov.b32 t0, sh{i}; add.u32 cnt0, cnt0, t0;")
+        s.append(f"  mov.b64 {{t0, t1}}, HD{i}; add.u32 cnt0, cnt0, t1;")
     return "\n".join(s)
 
 
@@ -432,6 +436,10 @@ def counting(b, r, count, pr):
         b.emit(f"abs.f32 x0, sl{r}; abs.f32 x1, sh{r}; set.lt.f32.f32 x2, x0, thr; set.lt.f32.f32 x3, x1, thr;")
         b.emit(f"mov.b32 h0, x2; mov.b32 h1, x3; add.u32 t0, h0, h1; add.u32 cnt{r}, cnt{r}, t0;")
         return
+    if count == "carry":    # the product kernel's plane form: two carry-only IADD3 + one IADD3.X (64-bit add idiom, high word = counter)
+        for half in ("sl", "sh"):
+            b.emit(f"mov.b32 h0, {half}{r}; mov.b64 {{t0, t1}}, HD{r}; mov.b64 W2, {{h0, t1}}; add.u64 HD{r}, W2, kneg;")
+        return
     if count == "fset":     # 2 FSET.BF, results consumed by one LOP3 (keeps the ALU count at 3 but with no carry chain)
         b.emit(f"abs.f32 x0, sl{r}; abs.f32 x1, sh{r}; set.lt.f32.f32 x2, x0, thr; set.lt.f32.f32 x3, x1, thr;")
         b.emit(f"mov.b32 h0, x2; mov.b32 h1, x3; lop3.b32 cnt{r}, cnt{r}, h0, h1, 0x96;")
@@ -456,7 +464,7 @@ for R in (8,):
         for count in ("none", "setpc", "setp", "sign"):
             VARIANTS[f"pl_{order}_{count}_R{R}"] = (f"plane kernel body, {order}, R={R}, counting={count}: {4*R} evals/slice, {6*R} FFMA2 (+{2*R} for sign)", plane(order, R, count))
 for R in (8, 10):
-    for count in ("chain", "raw", "fset", "fset1"):
+    for count in ("chain", "raw", "carry", "fset", "fset1"):
         VARIANTS[f"plc_{count}_R{R}"] = (f"plane body, points from the constant bank (LDCU -> UR operands), R={R}, counting={count}: {4*R} evals/slice", plane("hm", R, count, "const"))
 for R in (8, 12):
     for count in ("none", "setpc", "setp", "sign"):
