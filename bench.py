@@ -112,23 +112,67 @@ def make_data(model, n):
     return data, synth.DELTAS[model]
 
 
-def cpu_reference_run(model, data, delta, n_hyps, threads=0):
-    """Times the reference's own estimate()+agree() loop (oracle/_ref when built, else the C port)
-    on the host cores over n_hyps Philox-free random subsets x all points."""
-    from lsqrrecipes_b200 import synth
+def host_cores():
+    """Cores this process may use.  torch.distributed.run exports OMP_NUM_THREADS=1 when nproc > 1, so the OpenMP default
+    is useless there: the CPU legs always pass an explicit thread count."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def _oracle():
     from oracle import pyoracle
     kind = "ref" if pyoracle.available("ref") else "port"
     if kind == "port" and not pyoracle.available("port"):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
-    orc = pyoracle.Oracle(kind)
+    return pyoracle, pyoracle.Oracle(kind), kind
+
+
+def cpu_reference_run(model, data, delta, n_hyps, threads=0):
+    """Times the reference's own estimate()+agree() loop (oracle/_ref when built, else the C port)
+    on `threads` host cores over n_hyps random subsets x all points."""
+    from lsqrrecipes_b200 import synth
+    pyoracle, orc, kind = _oracle()
+    threads = threads or host_cores()
     m = pyoracle.MODELS[model]
     k = pyoracle.INFO[m][2]
     subs = synth.random_subsets(data.shape[0], k, n_hyps, seed=123)
     t0 = time.perf_counter()
     counts, _ = orc.score_subsets(m, delta, data, subs, nthreads=threads, want_params=False)
     dt = time.perf_counter() - t0
-    return {"kind": "reference" if kind == "ref" else "port", "cores": orc.num_threads() if threads == 0 else threads,
+    return {"kind": "reference" if kind == "ref" else "port", "cores": threads,
             "seconds": dt, "evals": float(n_hyps) * data.shape[0], "best": int(counts.max())}
+
+
+def cpu_sample_size(model, data, delta, target_s, threads):
+    """Hypotheses per CPU sample so that one sample takes ~target_s: sized from a short probe instead of an assumed rate."""
+    probe = max(threads, 4)
+    info = cpu_reference_run(model, data, delta, probe, threads)
+    rate = probe / max(info["seconds"], 1e-3)
+    return max(threads, int(rate * target_s) // threads * threads)
+
+
+def reference_compute_ms(model, data, delta, prob=0.999, budget_s=60.0):
+    """Wall time of the reference's own RANSAC<T,S>::compute (RANSAC.hxx:4-145: srand/rand subsets, estimate, N agree()
+    calls per try, least squares over the consensus set) on one host thread, as shipped.  Only oracle/_ref has it."""
+    pyoracle, orc, kind = _oracle()
+    if kind != "ref":
+        return None
+    m = pyoracle.MODELS[model]
+    n = data.shape[0]
+    ms, frac = [], None
+    t_all = time.perf_counter()
+    for _ in range(3):
+        t0 = time.perf_counter()
+        prm, mask, frac = orc.ransac_random(m, delta, data, prob)
+        ms.append(1e3 * (time.perf_counter() - t0))
+        if time.perf_counter() - t_all > budget_s / 3:
+            break
+    return {"ms": float(np.median(ms)), "runs_ms": [float(x) for x in ms], "points": int(n), "desired_probability": prob, "threads": 1,
+            "inlier_fraction": float(frac), "n_params": int(len(prm)),
+            "what": "RANSAC<T,S>::compute(parameters, estimator, data, 0.999, &consensusSet) of the reference (oracle/_ref), single-threaded as shipped; "
+                    "the number of tries is time-seeded (RANSAC.hxx:44)"}
 
 
 def run_reference_arm(args):
@@ -136,27 +180,30 @@ def run_reference_arm(args):
     if rank != 0:
         return
     data, delta = make_data(args.model, args.points)
-    cores = os.cpu_count() or 1
-    # ~5 s of host work per step at the ~2e9 evals/s the 16-core GPU box reaches on 10 M points
-    n_hyps = args.cpu_sample_hyps or max(1, int(64 * cores * 10_000_000 / max(args.points, 1)))
+    cores = host_cores()
+    # each step is a bounded sample of the workload; the whole run (warm-up + steps + compute()) stays under ~2 minutes
+    target_s = min(5.0, max(0.5, 60.0 / max(args.steps + args.warmup / 4.0, 1.0)))
+    n_hyps = args.cpu_sample_hyps or cpu_sample_size(args.model, data, delta, target_s, cores)
     for _ in range(args.warmup):
-        cpu_reference_run(args.model, data, delta, max(n_hyps // 8, 1))
+        cpu_reference_run(args.model, data, delta, max(n_hyps // 4, cores), cores)
     times, info = [], None
     t_all = time.perf_counter()
     for _ in range(args.steps):
-        info = cpu_reference_run(args.model, data, delta, n_hyps)
+        info = cpu_reference_run(args.model, data, delta, n_hyps, cores)
         times.append(info["seconds"])
     total = time.perf_counter() - t_all
     value = info["evals"] * args.steps / sum(times)
+    comp = None if args.no_e2e else reference_compute_ms(args.model, data, delta)
     line = {
         "impl": "reference", "metric": "hypothesis x point agree() evals/sec", "value": value, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": dict(workload_config(args.model, args.points, args.hyps, args.gpus, args.precision, delta),
-                       sample=f"each step times {n_hyps} of the hypotheses x all {args.points} points on the host cores (fp64, the reference's arithmetic)"),
+                       sample=f"each step times {n_hyps} of the hypotheses x all {args.points} points on {cores} host cores (fp64, the reference's arithmetic)"),
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": info["cores"], "kind": info["kind"],
                          "sample": f"{n_hyps} hypotheses x {args.points} points per step, estimate()+agree() loop of RANSAC.hxx:217-249, OpenMP over hypotheses"},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "compute_e2e": comp,
         "gpu_launches": 0, "wall_s": total,
     }
     emit_line(line)
@@ -345,10 +392,10 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        # bounded sample: ~20 s of host work (SURVEY.md 8d measured ~1.5e8 evals/s per core)
-        n_hyps = args.cpu_sample_hyps or max(1, int(256 * cores * 10_000_000 / max(N, 1)))
-        info = cpu_reference_run(model, data, delta, n_hyps)
+        cores = host_cores()
+        # bounded sample: ~15 s of host work, sized from a short probe
+        n_hyps = args.cpu_sample_hyps or cpu_sample_size(model, data, delta, 15.0, cores)
+        info = cpu_reference_run(model, data, delta, n_hyps, cores)
         cpu = {"value": info["evals"] / info["seconds"], "unit": "evals/s", "cores": info["cores"], "kind": info["kind"],
                "sample": f"{n_hyps} hypotheses x {N} points, estimate()+agree() loop (RANSAC.hxx:217-249), OpenMP over hypotheses, {info['seconds']:.1f} s"}
 

@@ -384,14 +384,19 @@ int refine_impl(lsqr_ctx* ctx, DataSet& ds, int use_mask, double* out_params, in
     const int nlm = moments_count(ctx->model, true);
     launch_lm_init(out_dev, st, s); ctx->launches++;
     ds.moments_valid = false;
-    for (int it = 0; it < 5200; it++) {   // the controller stops itself (500 / 5000 evaluations); this is only a safety bound
-      CK(cudaMemcpyAsync(ctx->pin, st + lm_status_offset(), sizeof(double), cudaMemcpyDeviceToHost, s));
+    // The controller stops itself (500 / 5000 evaluations at most).  Passes are enqueued kLmAhead evaluations ahead of the
+    // status word, so the host synchronises once per chunk instead of once per evaluation; passes behind a stop are no-ops.
+    constexpr int kLmAhead = 8;
+    for (int it = 0; it < 5200; it += kLmAhead) {
+      for (int k = 0; k < kLmAhead; k++) {
+        launch_mask_moments(ctx->model, dv, b, e, nullptr, use_mask ? 2 : 0, st, ctx->cfg, ctx->rb, s); ctx->launches++;
+        if (int rc = reduce_moments(ctx, nlm)) return rc;
+        launch_lm_update(ctx->model, ctx->rb.moments, st, s); ctx->launches++;
+      }
+      CK(cudaMemcpyAsync(ctx->pin, st + lm_status_offset(), 3 * sizeof(double), cudaMemcpyDeviceToHost, s));   // status, phase, evaluations
       CK(cudaStreamSynchronize(s));
+      ctx->lm_iterations = (int)ctx->pin[2];
       if (ctx->pin[0] != 0.0) break;
-      launch_mask_moments(ctx->model, dv, b, e, nullptr, use_mask ? 2 : 0, st, ctx->cfg, ctx->rb, s); ctx->launches++;
-      if (int rc = reduce_moments(ctx, nlm)) return rc;
-      launch_lm_update(ctx->model, ctx->rb.moments, st, s); ctx->launches++;
-      ctx->lm_iterations++;
     }
     launch_lm_finish(ctx->model, dv, st, out_dev, s); ctx->launches++;
   }

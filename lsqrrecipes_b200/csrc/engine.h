@@ -10,7 +10,7 @@ namespace lsqr {
 
 constexpr int kTilePad = 1024;   // leading dimension of the SoA point arrays is a multiple of this
 constexpr int kMaxDim = 20;           // doubles per datum, upper bound (calibrated-pointer US calibration: 17)
-constexpr int kLmStateDoubles = 192;  // device scratch reserved for the Levenberg-Marquardt controller state
+constexpr int kLmStateDoubles = 256;  // device scratch reserved for the Levenberg-Marquardt controller state
 constexpr int kMaxMoments = 96;  // upper bound on the doubles accumulated per thread by the refine reductions (cross-wire US calibration: 91)
 
 // Device-resident description of the uploaded data.

@@ -529,8 +529,11 @@ static int run_consensus32(const DataView& dv, const float* hyp, size_t hld, uin
   chunks = (tiles_total + tiles_per_chunk - 1) / tiles_per_chunk;
   const size_t smem = 2 * (size_t)Model<M>::D * TILE * sizeof(float);
   auto kern = consensus32_kernel<M, R, THREADS, TILE, PPI>;
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  // the attribute is per device (a multi-device context launches the same kernel on every GPU of the process)
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[dev & 63] = true; }
   kern<<<dim3(hyp_blocks, chunks), THREADS, smem, s>>>(dv.soa32, dv.ld, tiles_total, tiles_per_chunk, hyp, hld, H, (float)cfg.delta, (float)cfg.delta2, counts);
   return 1;
 }

@@ -14,6 +14,7 @@
 // equations), which keeps the fp64 sums well conditioned for coordinates far from the origin.
 #include "engine.h"
 #include "../../include/lsqr_b200.h"
+#include "lm_minpack.cuh"
 
 namespace lsqr {
 
@@ -36,20 +37,6 @@ __host__ __device__ inline int n_moments(int model, bool lm) {
   }
   return 0;
 }
-// Layout of the Levenberg-Marquardt state (see the controller further down)
-constexpr int kLmMaxP = 11;
-enum : int {
-  LM_X = 0,                      // [kLmMaxP] current point
-  LM_COST = 11, LM_LAMBDA = 12, LM_NU = 13,
-  LM_STATUS = 14,                // 0 run, 1 converged, 2 failed
-  LM_EVALS = 15,
-  LM_PHASE = 16,                 // 0 = evaluate x, 1 = evaluate trial
-  LM_TRIAL = 17,                 // [kLmMaxP]
-  LM_PRED = 28, LM_HN = 29, LM_XN = 30,
-  LM_A = 32,                     // [kLmMaxP * kLmMaxP] J^T J at x
-  LM_G = 153,                    // [kLmMaxP] J^T r at x
-  LM_SIZE = 176
-};
 static_assert(kLmStateDoubles >= LM_SIZE, "engine.h: LM state buffer too small");
 
 #ifndef LSQR_MM_CTAS
@@ -196,12 +183,16 @@ template <> __device__ __forceinline__ void accumulate<USXW>(const double* q, do
     for (int a = 0; a < 12; a++) acc[o++] += row[a] * b;
   }
 }
-// Levenberg-Marquardt pass of the cross-wire calibration at x[11] = [t1, t3, omega_z, omega_y, omega_x, m_x, m_y]:
-// e = R2 (u m_x c1 + v m_y c2 + t3) + t2 - t1 and its 3 x 11 Jacobian (f / gradf of .cxx:415-658 minimise the same
-// sum |e|^2 through the scalar residuals |e_i|).
-__device__ __forceinline__ void acc_us_lm(const double* q, const double* x, double* acc) {
-  const double sz = sin(x[6]), cz = cos(x[6]), sy = sin(x[7]), cy = cos(x[7]), sx = sin(x[8]), cx = cos(x[8]);
-  const double mx = x[9], my = x[10], u = q[12], v = q[13];
+// Levenberg-Marquardt pass of the ultrasound calibrations.  The reference hands MINPACK the SCALAR residuals d_i = |e_i| with
+// e_i = R2 (u m_x c1 + v m_y c2 + t3) + t2 - t1 (f, SinglePointTargetUSCalibrationParametersEstimator.cxx:415-507) and the
+// Jacobian rows (e_i^T de_i/dx) / d_i (gradf, :510-658); the iteration path depends on that choice (J^T J of the scalar form is
+// not the one of the vector form), so the same rows are accumulated here: count, J^T J (upper triangle), J^T d, sum d^2.
+// x = [t1 (NT1 = 3, cross-wire only), t3, omega_z, omega_y, omega_x, m_x, m_y]; `tgt` is t1 or the measured pointer tip p.
+template <int NT1> __device__ __forceinline__ void acc_us_lm_rows(const double* q, const double* x, const double* tgt, double* acc) {
+  constexpr int NP = NT1 + 8;
+  const double* y = x + NT1;   // t3, angles, scales
+  const double sz = sin(y[3]), cz = cos(y[3]), sy = sin(y[4]), cy = cos(y[4]), sx = sin(y[5]), cx = cos(y[5]);
+  const double mx = y[6], my = y[7], u = q[12], v = q[13];
   const double c1[3] = {cz * cy, sz * cy, -sy};
   const double c2[3] = {cz * sy * sx - sz * cx, sz * sy * sx + cz * cx, cy * sx};
   const double dc1[3][3] = {{-sz * cy, cz * cy, 0}, {-cz * sy, -sz * sy, -cy}, {0, 0, 0}};
@@ -210,34 +201,37 @@ __device__ __forceinline__ void acc_us_lm(const double* q, const double* x, doub
   double w[3], dw[8][3];   // d w / d (t3 (3), omega (3), m_x, m_y)
 #pragma unroll
   for (int k = 0; k < 3; k++) {
-    w[k] = u * mx * c1[k] + v * my * c2[k] + x[3 + k];
+    w[k] = u * mx * c1[k] + v * my * c2[k] + y[k];
 #pragma unroll
     for (int p = 0; p < 3; p++) { dw[p][k] = (p == k) ? 1.0 : 0.0; dw[3 + p][k] = u * mx * dc1[p][k] + v * my * dc2[p][k]; }
     dw[6][k] = u * c1[k];
     dw[7][k] = v * c2[k];
   }
-  acc[0] += 1.0;
-  double cost = 0;
+  double e[3], J[NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) J[p] = 0.0;
 #pragma unroll
   for (int r = 0; r < 3; r++) {
     const double a = q[3 * r], b = q[3 * r + 1], c = q[3 * r + 2];
-    const double e = a * w[0] + b * w[1] + c * w[2] + q[9 + r] - x[r];
-    double J[11];
+    e[r] = a * w[0] + b * w[1] + c * w[2] + q[9 + r] - tgt[r];
+    if (NT1) J[r] = -e[r];
 #pragma unroll
-    for (int p = 0; p < 3; p++) J[p] = (p == r) ? -1.0 : 0.0;
-#pragma unroll
-    for (int p = 0; p < 8; p++) J[3 + p] = a * dw[p][0] + b * dw[p][1] + c * dw[p][2];
-    int o = 1;
-#pragma unroll
-    for (int i = 0; i < 11; i++)
-#pragma unroll
-      for (int j = i; j < 11; j++) acc[o++] += J[i] * J[j];
-#pragma unroll
-    for (int i = 0; i < 11; i++) acc[o++] += J[i] * e;
-    cost += e * e;
+    for (int p = 0; p < 8; p++) J[NT1 + p] += (a * dw[p][0] + b * dw[p][1] + c * dw[p][2]) * e[r];
   }
-  acc[78] += cost;
+  const double d = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+#pragma unroll
+  for (int p = 0; p < NP; p++) J[p] /= d;
+  acc[0] += 1.0;
+  int o = 1;
+#pragma unroll
+  for (int i = 0; i < NP; i++)
+#pragma unroll
+    for (int j = i; j < NP; j++) acc[o++] += J[i] * J[j];
+#pragma unroll
+  for (int i = 0; i < NP; i++) acc[o++] += J[i] * d;
+  acc[o] += d * d;
 }
+__device__ __forceinline__ void acc_us_lm(const double* q, const double* x, double* acc) { acc_us_lm_rows<3>(q, x, x, acc); }
 
 // Normal equations of the rows [u R2, v R2, R2] x = p - t2 (SinglePointTargetUSCalibrationParametersEstimator.cxx:806-846)
 template <> __device__ __forceinline__ void accumulate<USCP>(const double* q, double* acc) {
@@ -258,45 +252,8 @@ template <> __device__ __forceinline__ void accumulate<USCP>(const double* q, do
     for (int a = 0; a < 9; a++) acc[o++] += row[a] * b;
   }
 }
-// Levenberg-Marquardt pass of the calibrated-pointer calibration at x[8] = [t3, omega_z, omega_y, omega_x, m_x, m_y]:
-// e = R2 (u m_x c1 + v m_y c2 + t3) + t2 - p
-__device__ __forceinline__ void acc_uscp_lm(const double* q, const double* x, double* acc) {
-  const double sz = sin(x[3]), cz = cos(x[3]), sy = sin(x[4]), cy = cos(x[4]), sx = sin(x[5]), cx = cos(x[5]);
-  const double mx = x[6], my = x[7], u = q[12], v = q[13];
-  const double c1[3] = {cz * cy, sz * cy, -sy};
-  const double c2[3] = {cz * sy * sx - sz * cx, sz * sy * sx + cz * cx, cy * sx};
-  const double dc1[3][3] = {{-sz * cy, cz * cy, 0}, {-cz * sy, -sz * sy, -cy}, {0, 0, 0}};
-  const double dc2[3][3] = {{-sz * sy * sx - cz * cx, cz * sy * sx - sz * cx, 0}, {cz * cy * sx, sz * cy * sx, -sy * sx},
-                            {cz * sy * cx + sz * sx, sz * sy * cx - cz * sx, cy * cx}};
-  double w[3], dw[8][3];
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    w[k] = u * mx * c1[k] + v * my * c2[k] + x[k];
-#pragma unroll
-    for (int p = 0; p < 3; p++) { dw[p][k] = (p == k) ? 1.0 : 0.0; dw[3 + p][k] = u * mx * dc1[p][k] + v * my * dc2[p][k]; }
-    dw[6][k] = u * c1[k];
-    dw[7][k] = v * c2[k];
-  }
-  acc[0] += 1.0;
-  double cost = 0;
-#pragma unroll
-  for (int r = 0; r < 3; r++) {
-    const double a = q[3 * r], b = q[3 * r + 1], c = q[3 * r + 2];
-    const double e = a * w[0] + b * w[1] + c * w[2] + q[9 + r] - q[14 + r];
-    double J[8];
-#pragma unroll
-    for (int p = 0; p < 8; p++) J[p] = a * dw[p][0] + b * dw[p][1] + c * dw[p][2];
-    int o = 1;
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-#pragma unroll
-      for (int j = i; j < 8; j++) acc[o++] += J[i] * J[j];
-#pragma unroll
-    for (int i = 0; i < 8; i++) acc[o++] += J[i] * e;
-    cost += e * e;
-  }
-  acc[45] += cost;
-}
+// calibrated pointer: the same rows with the measured tip position p (q[14..16]) in the place of t1 and no unknown for it
+__device__ __forceinline__ void acc_uscp_lm(const double* q, const double* x, double* acc) { acc_us_lm_rows<0>(q, x, q + 14, acc); }
 
 __host__ __device__ inline bool centred_comp(int model, int d) {
   switch (model) {
@@ -335,6 +292,9 @@ __global__ void __launch_bounds__(256, mm_ctas<M, LM>()) mask_moments_kernel(Dat
   }
   double lmx[LM ? Mom<M>::NPLM : 1] = {0};
   if (LM) {
+    // the host enqueues evaluation passes a few iterations ahead of the controller's status word: once the iteration has
+    // stopped, the remaining passes are no-ops (the controller ignores the stale moments)
+    if (lm_state[LM_STATUS] != 0.0) return;
     // the phase selects the evaluation point: x or the trial point
     const int off = (lm_state[LM_PHASE] != 0.0) ? LM_TRIAL : LM_X;
 #pragma unroll
@@ -727,114 +687,17 @@ void launch_solve_moments(int model, const DataView& dv, const double* moments, 
 }
 
 // ---------------------------------------------------------------------------------------
-// Levenberg-Marquardt controller, shared by the geometric circle / sphere fit
-// (SphereParametersEstimator.hxx:310-338: xtol = gtol = 1e-15, ftol = VNL default 1e-10, at most 500
-// function evaluations) and the iterative cross-wire calibration
-// (SinglePointTargetUSCalibrationParametersEstimator.cxx:272-329: all tolerances 1e-15, 5000 evaluations).
-// Result only if converged.  Marquardt scaling (damping lambda * diag(J^T J)) like MINPACK's mode 1.
-// One pass of mask_moments_kernel delivers J^T J, J^T r and the cost at the point the state asks for.
+// Levenberg-Marquardt controller: lm_minpack.cuh (MINPACK's lmder restated on the normal equations, the reference's
+// tolerances per estimator).  Result only if MINPACK would report info 1..4 (vnl_levenberg_marquardt::minimize returns
+// true), else empty parameters.  One pass of mask_moments_kernel delivers J^T J, J^T f and |f|^2 at the point the state
+// asks for.
 // ---------------------------------------------------------------------------------------
-
-
-template <int NP> __device__ bool chol_solve(const double* Ain, const double* b, double* x) {
-  double M[NP * NP];
-  for (int i = 0; i < NP * NP; i++) M[i] = Ain[i];
-  for (int j = 0; j < NP; j++) {
-    double s = M[j * NP + j];
-    for (int k = 0; k < j; k++) s -= M[j * NP + k] * M[j * NP + k];
-    if (!(s > 0)) return false;
-    M[j * NP + j] = sqrt(s);
-    for (int i = j + 1; i < NP; i++) { double t = M[i * NP + j]; for (int k = 0; k < j; k++) t -= M[i * NP + k] * M[j * NP + k]; M[i * NP + j] = t / M[j * NP + j]; }
-  }
-  for (int i = 0; i < NP; i++) { double t = b[i]; for (int k = 0; k < i; k++) t -= M[i * NP + k] * x[k]; x[i] = t / M[i * NP + i]; }
-  for (int i = NP - 1; i >= 0; i--) { double t = x[i]; for (int k = i + 1; k < NP; k++) t -= M[k * NP + i] * x[k]; x[i] = t / M[i * NP + i]; }
-  return true;
-}
-
-// moments layout of an LM pass: [0] count, J^T J upper triangle, J^T r, cost
-template <int NP> __device__ void lm_load_normal(const double* m, double* A, double* g, double* cost) {
-  int o = 1;
-  for (int a = 0; a < NP; a++) for (int b = a; b < NP; b++) { const double v = m[o++]; A[a * NP + b] = v; A[b * NP + a] = v; }
-  for (int a = 0; a < NP; a++) g[a] = m[o++];
-  *cost = m[o];
-}
-template <int NP> __device__ double lm_scale(const double* A, int a) {
-  double dmax = 0;
-  for (int i = 0; i < NP; i++) if (A[i * NP + i] > dmax) dmax = A[i * NP + i];
-  const double floor_ = 1e-30 * dmax + 1e-300;
-  return A[a * NP + a] > floor_ ? A[a * NP + a] : floor_;
-}
-// Computes the next trial point from (A, g, lambda); grows lambda until the damped system is SPD.
-template <int NP> __device__ void lm_make_trial(double* st) {
-  const double* A = st + LM_A; const double* g = st + LM_G;
-  double dsc[NP];
-  for (int a = 0; a < NP; a++) dsc[a] = lm_scale<NP>(A, a);
-  for (int it = 0; it < 64; it++) {
-    double Mx[NP * NP], h[NP];
-    for (int a = 0; a < NP; a++) for (int b = 0; b < NP; b++) Mx[a * NP + b] = A[a * NP + b] + (a == b ? st[LM_LAMBDA] * dsc[a] : 0.0);
-    if (chol_solve<NP>(Mx, g, h)) {
-      double hn = 0, xn = 0, pred = 0;
-      for (int a = 0; a < NP; a++) {
-        h[a] = -h[a]; st[LM_TRIAL + a] = st[LM_X + a] + h[a];
-        hn += h[a] * h[a]; xn += st[LM_X + a] * st[LM_X + a]; pred += h[a] * (st[LM_LAMBDA] * dsc[a] * h[a] - g[a]);
-      }
-      st[LM_PRED] = pred; st[LM_HN] = hn; st[LM_XN] = xn;
-      st[LM_PHASE] = 1.0;
-      return;
-    }
-    st[LM_LAMBDA] *= st[LM_NU]; st[LM_NU] *= 2;
-  }
-  st[LM_STATUS] = 2.0;
-}
-template <int NP> __device__ bool lm_gradient_converged(const double* st) {
-  const double gtol = 10e-16;
-  const double* A = st + LM_A; const double* g = st + LM_G;
-  const double fnorm = sqrt(st[LM_COST]);
-  double gmax = 0;
-  for (int a = 0; a < NP; a++) { const double cn = sqrt(A[a * NP + a]); if (cn > 0 && fnorm > 0) { const double v = fabs(g[a]) / (cn * fnorm); if (v > gmax) gmax = v; } }
-  return gmax <= gtol || st[LM_COST] == 0.0;
-}
-template <int NP> __device__ void lm_update(const double* m, double* st, double ftol, int maxfev) {
-  const double xtol = 10e-16;
-  if (st[LM_STATUS] != 0.0) return;
-  if (st[LM_PHASE] == 0.0) {  // first evaluation at x
-    lm_load_normal<NP>(m, st + LM_A, st + LM_G, st + LM_COST);
-    st[LM_EVALS] = 1.0;
-    if (lm_gradient_converged<NP>(st)) { st[LM_STATUS] = 1.0; return; }
-    st[LM_LAMBDA] = 1e-3; st[LM_NU] = 2.0;
-    lm_make_trial<NP>(st);
-    return;
-  }
-  double An[NP * NP], gn[NP], cnew;
-  lm_load_normal<NP>(m, An, gn, &cnew);
-  st[LM_EVALS] += 1.0;
-  const double cost = st[LM_COST], pred = st[LM_PRED], hn = st[LM_HN], xn = st[LM_XN];
-  const double actred = cost - cnew;
-  if (pred > 0 && actred > 0) {
-    const double rho = actred / pred, t = 2 * rho - 1, f = 1 - t * t * t;
-    const bool fconv = actred <= ftol * cost && pred <= ftol * cost;
-    for (int a = 0; a < NP; a++) st[LM_X + a] = st[LM_TRIAL + a];
-    for (int i = 0; i < NP * NP; i++) st[LM_A + i] = An[i];
-    for (int i = 0; i < NP; i++) st[LM_G + i] = gn[i];
-    st[LM_LAMBDA] *= (f > 1.0 / 3.0 ? f : 1.0 / 3.0); st[LM_NU] = 2.0;
-    st[LM_COST] = cnew;
-    if (fconv || sqrt(hn) <= xtol * sqrt(xn)) { st[LM_STATUS] = 1.0; return; }
-    if (lm_gradient_converged<NP>(st)) { st[LM_STATUS] = 1.0; return; }
-  } else {
-    if (sqrt(hn) <= xtol * sqrt(xn)) { st[LM_STATUS] = 1.0; return; }
-    if (fabs(actred) <= ftol * cost && pred <= ftol * cost) { st[LM_STATUS] = 1.0; return; }
-    st[LM_LAMBDA] *= st[LM_NU]; st[LM_NU] *= 2;
-    if (!(st[LM_LAMBDA] < 1e300)) { st[LM_STATUS] = 1.0; return; }   // the step has shrunk below resolution: stationary to rounding
-  }
-  if (st[LM_EVALS] >= (double)maxfev) { st[LM_STATUS] = 2.0; return; }
-  lm_make_trial<NP>(st);
-}
-__device__ void lm_update_model(int model, const double* m, double* st) {
-  if (model == CIRCLE2) lm_update<3>(m, st, 1e-8 * 0.01, 500);
-  else if (model == SPHERE3) lm_update<4>(m, st, 1e-8 * 0.01, 500);
-  else if (model == SPHERE4) lm_update<5>(m, st, 1e-8 * 0.01, 500);
-  else if (model == USXW) lm_update<11>(m, st, 10e-16, 5000);
-  else if (model == USCP) lm_update<8>(m, st, 10e-16, 5000);   // iterated to the minimiser (the reference stops at 1e-7)
+__host__ __device__ inline void lm_update_model(int model, const double* m, double* st) {
+  if (model == CIRCLE2) lm_update<3>(m, st, lm_tolerances(0));
+  else if (model == SPHERE3) lm_update<4>(m, st, lm_tolerances(0));
+  else if (model == SPHERE4) lm_update<5>(m, st, lm_tolerances(0));
+  else if (model == USXW) lm_update<11>(m, st, lm_tolerances(1));
+  else if (model == USCP) lm_update<8>(m, st, lm_tolerances(2));
 }
 
 __global__ void lm_init_kernel(const double* __restrict__ alg_out, double* __restrict__ st) {

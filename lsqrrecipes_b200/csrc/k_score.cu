@@ -283,8 +283,11 @@ static int run_consensus(const typename T::real* soa, size_t ld, const typename 
   chunks = (tiles_total + tiles_per_chunk - 1) / tiles_per_chunk;
   const size_t smem = 2 * (size_t)T::D * TILE * sizeof(real);
   auto kern = consensus_kernel<T, R, THREADS, TILE>;
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  // the attribute is per device (a multi-device context launches the same kernel on every GPU of the process)
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set[dev & 63] = true; }
   dim3 grid(hyp_blocks, chunks);
   kern<<<grid, THREADS, smem, s>>>(soa, ld, tiles_total, tiles_per_chunk, hyp, hld, H, thr, counts);
   return 1;

@@ -8,10 +8,11 @@
  * The reference delegates eigen / SVD / Levenberg-Marquardt to VNL (third party, absent
  * from /root/reference, un-pinned).  Those three routines are restated here from their
  * published contracts (ascending symmetric eigenvalues with column eigenvectors;
- * pseudo-inverse with singular values <= EPS zeroed; LM with MINPACK-style stopping),
- * so results that pass through them match to rounding level, not bit-for-bit.
+ * pseudo-inverse with singular values <= EPS zeroed; Levenberg-Marquardt = MINPACK's lmder, restated in
+ * minpack_lm.h), so results that pass through them match to rounding level, not bit-for-bit.
  */
 #include "lsqr_oracle.h"
+#include "minpack_lm.h"
 
 #include <limits.h>
 #include <math.h>
@@ -439,7 +440,6 @@ static int dense_solve(int nc, const double* d, size_t rows, double* prm) {
 }
 
 
-static int chol_solve(double* M, const double* b, double* x, int p);
 
 /* ------------------------------------------------------------------------------------ */
 /* Cross-wire (single unknown point target) ultrasound calibration                      */
@@ -526,8 +526,8 @@ static int usxw_analytic(const double* d, size_t n, double* prm) {
 }
 
 /* e = R2 (u c1 + v c2 + t3) + t2 - t1 for the LM parameters x[11] (f(), .cxx:415-507) and, when J != NULL,
- * its 3 x 11 Jacobian (row-major).  The reference minimises sum |e|^2 through the scalar residuals |e_i|
- * (gradf, .cxx:510-658); the minimiser here works on the vector residuals, same objective, same minimum. */
+ * its 3 x 11 Jacobian (row-major); the scalar residuals |e_i| and their gradients that the reference hands to MINPACK
+ * (f, gradf, .cxx:415-658) are formed from these in usxw_lm_fcn. */
 static void us_residual(const double* f, const double* x, double e[3], double* J) {
   const double sz = sin(x[6]), cz = cos(x[6]), sy = sin(x[7]), cy = cos(x[7]), sx = sin(x[8]), cx = cos(x[8]);
   const double mx = x[9], my = x[10], u = f[12], v = f[13];
@@ -556,62 +556,43 @@ static void us_residual(const double* f, const double* x, double e[3], double* J
   }
 }
 
-static double us_cost(const double* d, size_t n, const double* x, double* JtJ, double* Jtr) {
-  size_t i; int a, b2, r; double cost = 0;
-  if (JtJ) { memset(JtJ, 0, sizeof(double) * 121); memset(Jtr, 0, sizeof(double) * 11); }
-  for (i = 0; i < n; i++) {
-    double e[3], J[33];
-    us_residual(d + 14 * i, x, e, JtJ ? J : NULL);
-    cost += e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
-    if (JtJ) for (r = 0; r < 3; r++) for (a = 0; a < 11; a++) { Jtr[a] += J[r * 11 + a] * e[r]; for (b2 = a; b2 < 11; b2++) JtJ[a * 11 + b2] += J[r * 11 + a] * J[r * 11 + b2]; }
+/* The functor the reference hands to vnl_levenberg_marquardt (SumSquaresCalibrationPointsDistanceFunction, .cxx:402-658):
+ * m scalar residuals d_i = |e_i| (f, :415-507) with Jacobian rows (e_i^T de_i/dx) / d_i (gradf, :510-658). */
+typedef struct { const double* d; size_t n; } us_lm_ctx;
+/* MINPACK's info and function-evaluation count of the last Levenberg-Marquardt run on this thread (for tests that need a
+ * case away from the reference's evaluation cap) */
+static __thread int g_lm_info = 0, g_lm_nfev = 0;
+void orc_last_lm(int* info, int* nfev) { if (info) *info = g_lm_info; if (nfev) *nfev = g_lm_nfev; }
+static int usxw_lm_fcn(void* user, int m, int n, const double* x, double* fvec, double* fjac, int ldfjac, int iflag) {
+  const us_lm_ctx* c = (const us_lm_ctx*)user;
+  int i, p, r;
+  (void)n;
+  for (i = 0; i < m; i++) {
+    double e[3], J[33], dist;
+    us_residual(c->d + 14 * (size_t)i, x, e, iflag == 2 ? J : NULL);
+    dist = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+    if (iflag == 1) fvec[i] = dist;
+    else for (p = 0; p < 11; p++) { double t = 0; for (r = 0; r < 3; r++) t += J[r * 11 + p] * e[r]; fjac[i + (size_t)ldfjac * p] = t / dist; }
   }
-  if (JtJ) for (a = 0; a < 11; a++) for (b2 = 0; b2 < a; b2++) JtJ[a * 11 + b2] = JtJ[b2 * 11 + a];
-  return cost;
+  return 0;
 }
 
-/* iterativeLeastSquaresEstimate, .cxx:272-329: Levenberg-Marquardt from the analytic estimate, all tolerances
- * 1e-15, at most 5000 function evaluations, parameters returned only on convergence; entries 11..19 rebuilt
- * from the angles and scales. */
+/* iterativeLeastSquaresEstimate, .cxx:272-329: vnl_levenberg_marquardt (= MINPACK lmder, minpack_lm.h) from the analytic
+ * estimate, all three tolerances 10e-16, at most 5000 function evaluations, parameters returned only if minimize()
+ * reports success (info 1..4); entries 11..19 rebuilt from the angles and scales. */
 static int usxw_iterative(const double* d, size_t n, const double* init, double* prm) {
-  const double xtol = 10e-16, gtol = 10e-16, ftol = 10e-16;
-  const int maxfev = 5000, p = 11;
-  int a, evals = 1, ok = 0;
-  double x[11], xn[11], A[121], g[11], M[121], h[11], dsc[11], cost, lambda = -1, nu = 2;
-  for (a = 0; a < p; a++) x[a] = init[a];
-  cost = us_cost(d, n, x, NULL, NULL);
-  while (evals < maxfev && !ok) {
-    double gmax = 0, fnorm = sqrt(cost);
-    int accepted = 0;
-    us_cost(d, n, x, A, g);
-    for (a = 0; a < p; a++) { double cn = sqrt(A[a * p + a]); if (cn > 0 && fnorm > 0) { double v = fabs(g[a]) / (cn * fnorm); if (v > gmax) gmax = v; } }
-    if (gmax <= gtol || cost == 0.0) { ok = 1; break; }
-    { double dmax = 0; for (a = 0; a < p; a++) if (A[a * p + a] > dmax) dmax = A[a * p + a]; for (a = 0; a < p; a++) dsc[a] = A[a * p + a] > 1e-30 * dmax + 1e-300 ? A[a * p + a] : 1e-30 * dmax + 1e-300; }
-    if (lambda < 0) lambda = 1e-3;   /* Marquardt scaling: damping lambda * diag(J^T J), as MINPACK's mode 1 */
-    while (!accepted && evals < maxfev) {
-      double hn = 0, xnorm = 0, pred = 0, cnew, actred;
-      memcpy(M, A, sizeof(double) * p * p);
-      for (a = 0; a < p; a++) M[a * p + a] += lambda * dsc[a];
-      if (!chol_solve(M, g, h, p)) { lambda *= nu; nu *= 2; continue; }
-      for (a = 0; a < p; a++) { h[a] = -h[a]; xn[a] = x[a] + h[a]; hn += h[a] * h[a]; xnorm += x[a] * x[a]; pred += h[a] * (lambda * dsc[a] * h[a] - g[a]); }
-      cnew = us_cost(d, n, xn, NULL, NULL); evals++;
-      actred = cost - cnew;
-      if (pred > 0 && actred > 0) {
-        double rho = actred / pred, t = 2 * rho - 1, f = 1 - t * t * t;
-        int fconv = actred <= ftol * cost && pred <= ftol * cost;
-        for (a = 0; a < p; a++) x[a] = xn[a];
-        lambda *= (f > 1.0 / 3.0 ? f : 1.0 / 3.0); nu = 2;
-        cost = cnew; accepted = 1;
-        if (fconv || sqrt(hn) <= xtol * sqrt(xnorm)) ok = 1;
-      } else {
-        if (sqrt(hn) <= xtol * sqrt(xnorm)) { ok = 1; break; }
-        if (fabs(actred) <= ftol * cost && pred <= ftol * cost) { ok = 1; break; }
-        lambda *= nu; nu *= 2;
-        if (!(lambda < 1e300)) { ok = 1; break; }   /* the step has shrunk below resolution: stationary to rounding */
-      }
-    }
-  }
-  if (!ok) return 0;
-  for (a = 0; a < p; a++) prm[a] = x[a];
+  us_lm_ctx c;
+  double x[11], *fvec;
+  int a, info;
+  if (n < 11) return 0;   /* vnl_levenberg_marquardt: fewer residuals than unknowns -> failure */
+  c.d = d; c.n = n;
+  for (a = 0; a < 11; a++) x[a] = init[a];
+  fvec = (double*)malloc(sizeof(double) * n);
+  info = mpk_lmder(usxw_lm_fcn, &c, (int)n, 11, x, fvec, 10e-16, 10e-16, 10e-16, 5000, 100.0, &g_lm_nfev, NULL);
+  g_lm_info = info;
+  free(fvec);
+  if (info < 1 || info > 4) return 0;
+  for (a = 0; a < 11; a++) prm[a] = x[a];
   {
     const double cz = cos(x[6]), sz = sin(x[6]), cy = cos(x[7]), sy = sin(x[7]), cx = cos(x[8]), sx = sin(x[8]);
     prm[11] = x[9] * cz * cy; prm[12] = x[9] * sz * cy; prm[13] = -x[9] * sy;
@@ -689,63 +670,36 @@ static void uscp_residual(const double* f, const double* x, double e[3], double*
   for (r = 0; r < 3; r++) { e[r] = ee[r]; if (J) for (p = 0; p < 8; p++) J[r * 8 + p] = JJ[r * 11 + 3 + p]; }
 }
 
-static double uscp_cost(const double* d, size_t n, const double* x, double* JtJ, double* Jtr) {
-  size_t i; int a, b2, r; double cost = 0;
-  if (JtJ) { memset(JtJ, 0, sizeof(double) * 64); memset(Jtr, 0, sizeof(double) * 8); }
-  for (i = 0; i < n; i++) {
-    double e[3], J[24];
-    uscp_residual(d + 17 * i, x, e, JtJ ? J : NULL);
-    cost += e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
-    if (JtJ) for (r = 0; r < 3; r++) for (a = 0; a < 8; a++) { Jtr[a] += J[r * 8 + a] * e[r]; for (b2 = a; b2 < 8; b2++) JtJ[a * 8 + b2] += J[r * 8 + a] * J[r * 8 + b2]; }
+static int uscp_lm_fcn(void* user, int m, int n, const double* x, double* fvec, double* fjac, int ldfjac, int iflag) {
+  const us_lm_ctx* c = (const us_lm_ctx*)user;
+  int i, p, r;
+  (void)n;
+  for (i = 0; i < m; i++) {
+    double e[3], J[24], dist;
+    uscp_residual(c->d + 17 * (size_t)i, x, e, iflag == 2 ? J : NULL);
+    dist = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+    if (iflag == 1) fvec[i] = dist;
+    else for (p = 0; p < 8; p++) { double t = 0; for (r = 0; r < 3; r++) t += J[r * 8 + p] * e[r]; fjac[i + (size_t)ldfjac * p] = t / dist; }
   }
-  if (JtJ) for (a = 0; a < 8; a++) for (b2 = 0; b2 < a; b2++) JtJ[a * 8 + b2] = JtJ[b2 * 8 + a];
-  return cost;
+  return 0;
 }
 
-/* iterativeLeastSquaresEstimate, .cxx:922-985.  The reference stops MINPACK at tolerances 1e-7, i.e. somewhere within
- * ~1e-4 relative of the minimiser of sum |e_i|^2 depending on the minimiser's internals (the stand-in of the VNL shim
- * returns the analytic start).  This restatement iterates to the minimiser itself (1e-15), which is what the engine is
- * compared with; against the reference the test tolerance is 1e-3 and the cost must not be larger. */
+/* iterativeLeastSquaresEstimate, .cxx:916-985: as the cross-wire one with 8 unknowns and all three tolerances 10e-8, so
+ * MINPACK stops as soon as the scaled gradient, the relative step or the relative reductions fall below 1e-7 -- often at
+ * the analytic start itself (info 4). */
 static int uscp_iterative(const double* d, size_t n, const double* init, double* prm) {
-  const double xtol = 10e-16, gtol = 10e-16, ftol = 10e-16;
-  const int maxfev = 5000, p = 8;
-  int a, evals = 1, ok = 0;
-  double x[8], xn[8], A[64], g[8], M[64], h[8], dsc[8], cost, lambda = -1, nu = 2;
-  for (a = 0; a < p; a++) x[a] = init[a];
-  cost = uscp_cost(d, n, x, NULL, NULL);
-  while (evals < maxfev && !ok) {
-    double gmax = 0, fnorm = sqrt(cost);
-    int accepted = 0;
-    uscp_cost(d, n, x, A, g);
-    for (a = 0; a < p; a++) { double cn = sqrt(A[a * p + a]); if (cn > 0 && fnorm > 0) { double v = fabs(g[a]) / (cn * fnorm); if (v > gmax) gmax = v; } }
-    if (gmax <= gtol || cost == 0.0) { ok = 1; break; }
-    { double dmax = 0; for (a = 0; a < p; a++) if (A[a * p + a] > dmax) dmax = A[a * p + a]; for (a = 0; a < p; a++) dsc[a] = A[a * p + a] > 1e-30 * dmax + 1e-300 ? A[a * p + a] : 1e-30 * dmax + 1e-300; }
-    if (lambda < 0) lambda = 1e-3;
-    while (!accepted && evals < maxfev) {
-      double hn = 0, xnorm = 0, pred = 0, cnew, actred;
-      memcpy(M, A, sizeof(double) * p * p);
-      for (a = 0; a < p; a++) M[a * p + a] += lambda * dsc[a];
-      if (!chol_solve(M, g, h, p)) { lambda *= nu; nu *= 2; continue; }
-      for (a = 0; a < p; a++) { h[a] = -h[a]; xn[a] = x[a] + h[a]; hn += h[a] * h[a]; xnorm += x[a] * x[a]; pred += h[a] * (lambda * dsc[a] * h[a] - g[a]); }
-      cnew = uscp_cost(d, n, xn, NULL, NULL); evals++;
-      actred = cost - cnew;
-      if (pred > 0 && actred > 0) {
-        double rho = actred / pred, t = 2 * rho - 1, f = 1 - t * t * t;
-        int fconv = actred <= ftol * cost && pred <= ftol * cost;
-        for (a = 0; a < p; a++) x[a] = xn[a];
-        lambda *= (f > 1.0 / 3.0 ? f : 1.0 / 3.0); nu = 2;
-        cost = cnew; accepted = 1;
-        if (fconv || sqrt(hn) <= xtol * sqrt(xnorm)) ok = 1;
-      } else {
-        if (sqrt(hn) <= xtol * sqrt(xnorm)) { ok = 1; break; }
-        if (fabs(actred) <= ftol * cost && pred <= ftol * cost) { ok = 1; break; }
-        lambda *= nu; nu *= 2;
-        if (!(lambda < 1e300)) { ok = 1; break; }
-      }
-    }
-  }
-  if (!ok) return 0;
-  for (a = 0; a < p; a++) prm[a] = x[a];
+  us_lm_ctx c;
+  double x[8], *fvec;
+  int a, info;
+  if (n < 8) return 0;
+  c.d = d; c.n = n;
+  for (a = 0; a < 8; a++) x[a] = init[a];
+  fvec = (double*)malloc(sizeof(double) * n);
+  info = mpk_lmder(uscp_lm_fcn, &c, (int)n, 8, x, fvec, 10e-8, 10e-8, 10e-8, 5000, 100.0, &g_lm_nfev, NULL);
+  g_lm_info = info;
+  free(fvec);
+  if (info < 1 || info > 4) return 0;
+  for (a = 0; a < 8; a++) prm[a] = x[a];
   {
     const double cz = cos(x[3]), sz = sin(x[3]), cy = cos(x[4]), sy = sin(x[4]), cx = cos(x[5]), sx = sin(x[5]);
     prm[8] = x[6] * cz * cy; prm[9] = x[6] * sz * cy; prm[10] = -x[6] * sy;
@@ -952,82 +906,39 @@ static int sphere_algebraic(int dim, const double* d, size_t n, double* prm) {
   return 0;
 }
 
-static int chol_solve(double* M, const double* b, double* x, int p) {
-  int i, j, k;
-  for (j = 0; j < p; j++) {
-    double s = M[j * p + j];
-    for (k = 0; k < j; k++) s -= M[j * p + k] * M[j * p + k];
-    if (!(s > 0)) return 0;
-    M[j * p + j] = sqrt(s);
-    for (i = j + 1; i < p; i++) { double t = M[i * p + j]; for (k = 0; k < j; k++) t -= M[i * p + k] * M[j * p + k]; M[i * p + j] = t / M[j * p + j]; }
-  }
-  for (i = 0; i < p; i++) { double t = b[i]; for (k = 0; k < i; k++) t -= M[i * p + k] * x[k]; x[i] = t / M[i * p + i]; }
-  for (i = p - 1; i >= 0; i--) { double t = x[i]; for (k = i + 1; k < p; k++) t -= M[k * p + i] * x[k]; x[i] = t / M[i * p + i]; }
-  return 1;
-}
-
-/* residuals f (SphereParametersEstimator.hxx:394-409) and the normal equations of the
- * analytic Jacobian gradf (:413-431): J_i = [(c-p_i)/|p_i-c|, -1]. */
-static double sphere_cost(int dim, const double* d, size_t n, const double* x, double* JtJ, double* Jtr) {
-  int p = dim + 1, a, b2, j; size_t i; double cost = 0;
-  if (JtJ) { memset(JtJ, 0, sizeof(double) * p * p); memset(Jtr, 0, sizeof(double) * p); }
-  for (i = 0; i < n; i++) {
-    double sq = 0, sv, r, J[5];
-    for (j = 0; j < dim; j++) sq += (d[i * dim + j] - x[j]) * (d[i * dim + j] - x[j]);
+/* residuals f (SphereParametersEstimator.hxx:394-409) and the analytic Jacobian gradf (:413-431): J_i = [(c-p_i)/|p_i-c|, -1]. */
+typedef struct { const double* d; int dim; } sphere_lm_ctx;
+static int sphere_lm_fcn(void* user, int m, int n, const double* x, double* fvec, double* fjac, int ldfjac, int iflag) {
+  const sphere_lm_ctx* c = (const sphere_lm_ctx*)user;
+  const int dim = c->dim;
+  int i, j;
+  (void)n;
+  for (i = 0; i < m; i++) {
+    const double* pt = c->d + (size_t)i * dim;
+    double sq = 0, sv;
+    for (j = 0; j < dim; j++) sq += (pt[j] - x[j]) * (pt[j] - x[j]);
     sv = sqrt(sq);
-    r = sv - x[dim];
-    cost += r * r;
-    if (JtJ) {
-      for (j = 0; j < dim; j++) J[j] = (x[j] - d[i * dim + j]) / sv;
-      J[dim] = -1;
-      for (a = 0; a < p; a++) { Jtr[a] += J[a] * r; for (b2 = a; b2 < p; b2++) JtJ[a * p + b2] += J[a] * J[b2]; }
-    }
+    if (iflag == 1) fvec[i] = sv - x[dim];
+    else { for (j = 0; j < dim; j++) fjac[i + (size_t)ldfjac * j] = (x[j] - pt[j]) / sv; fjac[i + (size_t)ldfjac * dim] = -1.0; }
   }
-  if (JtJ) for (a = 0; a < p; a++) for (b2 = 0; b2 < a; b2++) JtJ[a * p + b2] = JtJ[b2 * p + a];
-  return cost;
+  return 0;
 }
 
-/* SphereParametersEstimator.hxx:310-338: vnl_levenberg_marquardt with xtol = gtol = 1e-15,
- * ftol left at VNL's default (xtol_default*0.01 = 1e-10), maxfev = 500; parameters are
- * returned only when the minimiser reports convergence. */
+/* SphereParametersEstimator.hxx:310-338: vnl_levenberg_marquardt (= MINPACK lmder, minpack_lm.h) with xtol = gtol = 10e-16,
+ * ftol left at VNL's default (xtol_default * 0.01 = 1e-10), maxfev = 500; parameters are returned only when minimize()
+ * reports success. */
 static int sphere_geometric(int dim, const double* d, size_t n, const double* init, double* prm) {
-  const double xtol = 10e-16, gtol = 10e-16, ftol = 1e-8 * 0.01;
-  const int maxfev = 500;
-  int p = dim + 1, a, evals = 1, ok = 0;
-  double x[5], xn[5], A[25], g[5], M[25], h[5], dsc[5], cost, lambda = -1, nu = 2;
+  sphere_lm_ctx c;
+  double x[5], *fvec;
+  int p = dim + 1, a, info;
+  if ((int)n < p) return 0;
+  c.d = d; c.dim = dim;
   for (a = 0; a < p; a++) x[a] = init[a];
-  cost = sphere_cost(dim, d, n, x, NULL, NULL);
-  while (evals < maxfev && !ok) {
-    double gmax = 0, fnorm = sqrt(cost);
-    int accepted = 0;
-    sphere_cost(dim, d, n, x, A, g);
-    for (a = 0; a < p; a++) { double cn = sqrt(A[a * p + a]); if (cn > 0 && fnorm > 0) { double v = fabs(g[a]) / (cn * fnorm); if (v > gmax) gmax = v; } }
-    if (gmax <= gtol || cost == 0.0) { ok = 1; break; }
-    { double dmax = 0; for (a = 0; a < p; a++) if (A[a * p + a] > dmax) dmax = A[a * p + a]; for (a = 0; a < p; a++) dsc[a] = A[a * p + a] > 1e-30 * dmax + 1e-300 ? A[a * p + a] : 1e-30 * dmax + 1e-300; }
-    if (lambda < 0) lambda = 1e-3;   /* Marquardt scaling: damping lambda * diag(J^T J), as MINPACK's mode 1 */
-    while (!accepted && evals < maxfev) {
-      double hn = 0, xnorm = 0, pred = 0, cnew, actred;
-      memcpy(M, A, sizeof(double) * p * p);
-      for (a = 0; a < p; a++) M[a * p + a] += lambda * dsc[a];
-      if (!chol_solve(M, g, h, p)) { lambda *= nu; nu *= 2; continue; }
-      for (a = 0; a < p; a++) { h[a] = -h[a]; xn[a] = x[a] + h[a]; hn += h[a] * h[a]; xnorm += x[a] * x[a]; pred += h[a] * (lambda * dsc[a] * h[a] - g[a]); }
-      cnew = sphere_cost(dim, d, n, xn, NULL, NULL); evals++;
-      actred = cost - cnew;
-      if (pred > 0 && actred > 0) {
-        double rho = actred / pred, t = 2 * rho - 1, f = 1 - t * t * t;
-        int fconv = actred <= ftol * cost && pred <= ftol * cost;
-        for (a = 0; a < p; a++) x[a] = xn[a];
-        lambda *= (f > 1.0 / 3.0 ? f : 1.0 / 3.0); nu = 2;
-        cost = cnew; accepted = 1;
-        if (fconv || sqrt(hn) <= xtol * sqrt(xnorm)) ok = 1;
-      } else {
-        if (sqrt(hn) <= xtol * sqrt(xnorm)) { ok = 1; break; }
-        if (fabs(actred) <= ftol * cost && pred <= ftol * cost) { ok = 1; break; }
-        lambda *= nu; nu *= 2;
-      }
-    }
-  }
-  if (!ok) return 0;
+  fvec = (double*)malloc(sizeof(double) * n);
+  info = mpk_lmder(sphere_lm_fcn, &c, (int)n, p, x, fvec, 1e-8 * 0.01, 10e-16, 10e-16, 500, 100.0, &g_lm_nfev, NULL);
+  g_lm_info = info;
+  free(fvec);
+  if (info < 1 || info > 4) return 0;
   for (a = 0; a < p; a++) prm[a] = x[a];
   return p;
 }

@@ -35,6 +35,8 @@ int orc_num_threads(void);
 /* estimate(): data = n>=k data in subset order; returns #params written (0 = degenerate). */
 int orc_estimate(int model, double delta, double aux, const double* data, size_t n, double* params);
 int orc_least_squares(int model, double delta, double aux, int ls_type, const double* data, size_t n, double* params);
+/* MINPACK info (1..4 = success) and number of function evaluations of the last Levenberg-Marquardt refit on this thread */
+void orc_last_lm(int* info, int* nfev);
 /* AbsoluteOrientationParametersEstimator::weightedLeastSquaresEstimate (.cxx:208-297); returns 7 or 0 */
 int orc_weighted_absor(const double* data, size_t n, const double* weights, double* params);
 /* agree() of one parameter vector against n data; returns inlier count; out[n] optional. */

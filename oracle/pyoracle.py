@@ -53,6 +53,7 @@ class Oracle:
             f("choose", ctypes.c_uint, [ctypes.c_uint, ctypes.c_uint])
             f("unrank_lex", None, [ctypes.c_uint64, ctypes.c_uint, ctypes.c_uint, _i32p])
             f("num_tries", ctypes.c_uint, [ctypes.c_double, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint])
+            f("last_lm", None, [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)])
         else:
             f("ransac", ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, _dp, ctypes.c_size_t, ctypes.c_int, ctypes.c_double, _dp, _u8p, _dp])
 
@@ -131,6 +132,12 @@ class Oracle:
         return out[:max(n, 0)].copy(), mask, frac.value
 
     # port-only helpers
+    def last_lm(self):
+        """(MINPACK info, function evaluations) of the last Levenberg-Marquardt refit."""
+        a, b = ctypes.c_int(0), ctypes.c_int(0)
+        self._last_lm(ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+
     def choose(self, n, m):
         return self._choose(n, m)
 

@@ -17,9 +17,9 @@
 //     nullvector() = last column of V; pinverse() = V W^-1 U^T.  (VNL: LINPACK dsvdc.
 //     Here: one-sided Jacobi (Hestenes).)
 //   * vnl_matrix_inverse<T> = vnl_svd<T> whose product with a vector applies pinverse().
-//   * vnl_levenberg_marquardt: minimises sum f_i(x)^2 with analytic Jacobian; returns true
-//     iff converged before max_function_evals.  (VNL: MINPACK lmder.  Here: Marquardt
-//     damping with Nielsen's update and MINPACK-style ftol/xtol/gtol tests.)
+//   * vnl_levenberg_marquardt: VNL calls MINPACK lmder (mode 1, factor 100) and returns true iff
+//     info is 1..4.  Here: the MINPACK algorithm restated step for step (oracle/minpack_lm.h)
+//     with VNL's defaults (xtol 1e-8, ftol = xtol * 0.01, gtol 1e-5, maxfev = 400 n).
 //
 // Consequence: everything in the reference that is plain `double` arithmetic (all estimate()
 // and agree() bodies for plane-3D, line, line-2D, circle, sphere, ray intersection) is
@@ -35,6 +35,8 @@
 #include <cstring>
 #include <iostream>
 #include <vector>
+
+#include "../../minpack_lm.h"
 
 template <class T> class vnl_matrix;
 
@@ -315,88 +317,63 @@ class vnl_least_squares_function {
   bool use_gradient_;
 };
 
+// vnl_levenberg_marquardt: VNL hands the problem to netlib's MINPACK.  With an analytic gradient (every functor of the
+// reference) that is lmder with mode 1 (internal scaling), factor 100; without one, lmdif (forward differences with
+// epsfcn = xtol * 0.001).  Defaults of vnl_nonlinear_minimizer: xtol 1e-8, ftol = xtol * 0.01, gtol 1e-5, and
+// vnl_levenberg_marquardt sets maxfev = 400 * unknowns.  minimize() is true iff MINPACK's info is 1..4.
+// The MINPACK algorithm itself is restated in oracle/minpack_lm.h (VNL / netlib are absent from this image).
 class vnl_levenberg_marquardt {
  public:
-  explicit vnl_levenberg_marquardt(vnl_least_squares_function& f) : f_(&f), xtol_(1e-8), ftol_(1e-8 * 0.01), gtol_(1e-5), maxfev_(400 * f.get_number_of_unknowns()), num_evals_(0) {}
+  explicit vnl_levenberg_marquardt(vnl_least_squares_function& f)
+      : f_(&f), xtol_(1e-8), ftol_(1e-8 * 0.01), gtol_(1e-5), epsfcn_(1e-8 * 0.001), maxfev_(400 * f.get_number_of_unknowns()), num_evals_(0), info_(0) {}
   void set_x_tolerance(double v) { xtol_ = v; }
   void set_f_tolerance(double v) { ftol_ = v; }
   void set_g_tolerance(double v) { gtol_ = v; }
+  void set_epsilon_function(double v) { epsfcn_ = v; }
   void set_max_function_evals(int v) { maxfev_ = v; }
   int get_num_evaluations() const { return num_evals_; }
+  int get_failure_code() const { return info_; }
   bool minimize(vnl_vector<double>& x) {
-    const unsigned p = f_->get_number_of_unknowns(), n = f_->get_number_of_residuals();
-    vnl_vector<double> fx(n), fnew(n), xnew(p);
-    vnl_matrix<double> J(n, p);
-    f_->f(x, fx); num_evals_ = 1;
-    double cost = fx.squared_magnitude();
-    double lambda = -1, nu = 2;
-    while (num_evals_ < maxfev_) {
-      if (f_->has_gradient()) f_->gradf(x, J); else numeric_jacobian(x, fx, J);
-      std::vector<double> A(size_t(p) * p, 0.0), g(p, 0.0);
-      for (unsigned i = 0; i < n; i++) { const double* Ji = J[i]; for (unsigned a = 0; a < p; a++) { g[a] += Ji[a] * fx[i]; for (unsigned b = a; b < p; b++) A[a * p + b] += Ji[a] * Ji[b]; } }
-      for (unsigned a = 0; a < p; a++) for (unsigned b = 0; b < a; b++) A[a * p + b] = A[b * p + a];
-      double gmax = 0, fnorm = std::sqrt(cost);
-      for (unsigned a = 0; a < p; a++) { double cn = std::sqrt(A[a * p + a]); if (cn > 0 && fnorm > 0) gmax = std::max(gmax, std::fabs(g[a]) / (cn * fnorm)); }
-      if (gmax <= gtol_ || cost == 0.0) return true;  // MINPACK info 4
-      // Marquardt scaling like MINPACK's mode 1: damping lambda * diag(J^T J), so that angles, scales and
-      // translations of very different magnitude are damped alike
-      std::vector<double> dsc(p);
-      { double dmax = 0; for (unsigned a = 0; a < p; a++) dmax = std::max(dmax, A[a * p + a]); for (unsigned a = 0; a < p; a++) dsc[a] = std::max(A[a * p + a], 1e-30 * dmax + 1e-300); }
-      if (lambda < 0) lambda = 1e-3;
-      bool accepted = false;
-      while (!accepted && num_evals_ < maxfev_) {
-        std::vector<double> M(A), h(p);
-        for (unsigned a = 0; a < p; a++) M[a * p + a] += lambda * dsc[a];
-        if (!chol_solve(M, g, h, p)) { lambda *= nu; nu *= 2; continue; }
-        double hn = 0, xn = 0, pred = 0;
-        for (unsigned a = 0; a < p; a++) { h[a] = -h[a]; xnew[a] = x[a] + h[a]; hn += h[a] * h[a]; xn += x[a] * x[a]; pred += h[a] * (lambda * dsc[a] * h[a] - g[a]); }
-        f_->f(xnew, fnew); ++num_evals_;
-        double cnew = fnew.squared_magnitude();
-        double actred = cost - cnew;
-        if (pred > 0 && actred > 0) {
-          double rho = actred / pred;
-          x = xnew; fx = fnew;
-          double t = 2 * rho - 1; lambda *= std::max(1.0 / 3.0, 1 - t * t * t); nu = 2;
-          bool fconv = actred <= ftol_ * cost && pred <= ftol_ * cost;
-          cost = cnew; accepted = true;
-          if (fconv) return true;                                    // info 1
-          if (std::sqrt(hn) <= xtol_ * std::sqrt(xn)) return true;  // info 2
-        } else {
-          if (std::sqrt(hn) <= xtol_ * std::sqrt(xn)) return true;  // step below resolution
-          if (std::fabs(actred) <= ftol_ * cost && pred <= ftol_ * cost) return true;
-          lambda *= nu; nu *= 2;
-          if (!(lambda < 1e300)) return true;   // the step has shrunk below resolution: stationary to rounding
-        }
-      }
-    }
-    return false;  // info 5: too many function evaluations
+    const int n = (int)f_->get_number_of_unknowns(), m = (int)f_->get_number_of_residuals();
+    if (m < n) { info_ = 0; return false; }   // VNL: "Number of unknowns(n) greater than number of data (m)"
+    std::vector<double> fvec(m);
+    int nfev = 0, njev = 0;
+    info_ = mpk_lmder(&vnl_levenberg_marquardt::callback, this, m, n, x.data_block(), fvec.data(), ftol_, xtol_, gtol_, maxfev_, 100.0, &nfev, &njev);
+    num_evals_ = nfev;
+    return info_ >= 1 && info_ <= 4;
   }
 
  private:
-  void numeric_jacobian(vnl_vector<double> const& x, vnl_vector<double> const& fx, vnl_matrix<double>& J) {
-    const unsigned p = f_->get_number_of_unknowns(), n = f_->get_number_of_residuals();
-    vnl_vector<double> xp(x), fp(n);
-    for (unsigned a = 0; a < p; a++) {
-      double h = 1.4901161193847656e-08 * std::fabs(x[a]); if (h == 0) h = 1.4901161193847656e-08;
-      xp[a] = x[a] + h; f_->f(xp, fp); ++num_evals_; xp[a] = x[a];
-      for (unsigned i = 0; i < n; i++) J(i, a) = (fp[i] - fx[i]) / h;
+  static int callback(void* user, int m, int n, const double* x, double* fvec, double* fjac, int ldfjac, int iflag) {
+    vnl_levenberg_marquardt* self = static_cast<vnl_levenberg_marquardt*>(user);
+    vnl_vector<double> vx(x, (unsigned)n);
+    if (iflag == 1) {
+      vnl_vector<double> fx((unsigned)m);
+      self->f_->f(vx, fx);
+      for (int i = 0; i < m; i++) fvec[i] = fx[i];
+    } else if (self->f_->has_gradient()) {
+      vnl_matrix<double> J((unsigned)m, (unsigned)n);
+      self->f_->gradf(vx, J);
+      for (int j = 0; j < n; j++) for (int i = 0; i < m; i++) fjac[i + (size_t)ldfjac * j] = J(i, j);
+    } else {   // forward differences (MINPACK fdjac2)
+      vnl_vector<double> f0((unsigned)m), f1((unsigned)m);
+      self->f_->f(vx, f0);
+      const double eps = std::sqrt(std::max(self->epsfcn_, 2.220446049250313e-16));
+      for (int j = 0; j < n; j++) {
+        const double t = vx[j];
+        double h = eps * std::fabs(t);
+        if (h == 0.0) h = eps;
+        vx[j] = t + h;
+        self->f_->f(vx, f1);
+        vx[j] = t;
+        for (int i = 0; i < m; i++) fjac[i + (size_t)ldfjac * j] = (f1[i] - f0[i]) / h;
+      }
     }
-  }
-  static bool chol_solve(std::vector<double>& M, std::vector<double> const& b, std::vector<double>& x, unsigned p) {
-    for (unsigned j = 0; j < p; j++) {
-      double s = M[j * p + j];
-      for (unsigned k = 0; k < j; k++) s -= M[j * p + k] * M[j * p + k];
-      if (!(s > 0)) return false;
-      M[j * p + j] = std::sqrt(s);
-      for (unsigned i = j + 1; i < p; i++) { double t = M[i * p + j]; for (unsigned k = 0; k < j; k++) t -= M[i * p + k] * M[j * p + k]; M[i * p + j] = t / M[j * p + j]; }
-    }
-    for (unsigned i = 0; i < p; i++) { double t = b[i]; for (unsigned k = 0; k < i; k++) t -= M[i * p + k] * x[k]; x[i] = t / M[i * p + i]; }
-    for (int i = int(p) - 1; i >= 0; i--) { double t = x[i]; for (unsigned k = i + 1; k < p; k++) t -= M[k * p + i] * x[k]; x[i] = t / M[i * p + i]; }
-    return true;
+    return 0;
   }
   vnl_least_squares_function* f_;
-  double xtol_, ftol_, gtol_;
-  int maxfev_, num_evals_;
+  double xtol_, ftol_, gtol_, epsfcn_;
+  int maxfev_, num_evals_, info_;
 };
 
 // Deterministic stand-in for vnl_random (only tests/examples of the reference use it).

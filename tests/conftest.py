@@ -62,3 +62,14 @@ def same_up_to_sign(a, b, idx, tol):
 # parameter entries that carry an arbitrary sign after leastSquaresEstimate
 SIGN_IDX = {"plane3": [0, 1, 2], "line2d": [0, 1], "line2": [0, 1], "line3": [0, 1, 2], "circle2": [], "sphere3": [],
             "absor": [0, 1, 2, 3], "ray": [], "pivot": [], "dense5": [], "dense6": [], "usxw": [], "uscp": [], "sphere4": [], "plane4": [0, 1, 2, 3]}
+
+
+def lm_case_is_clear(port, name, ls_type):
+    """The iterative cross-wire fit walks a flat valley: MINPACK needs hundreds to thousands of evaluations and whether its
+    1e-15 tests fire before the reference's 5000-evaluation cap (-> empty result) is decided by rounding noise
+    (tests/test_lm_cpu.py).  Parity tests on that estimator use cases where the oracle's run ends well inside the cap; call
+    this right after port.least_squares()."""
+    if name != "usxw" or ls_type != 1:
+        return True
+    info, nfev = port.last_lm()
+    return 1 <= info <= 4 and nfev <= 2500

@@ -62,6 +62,17 @@ def main():
                           -6.296891425314718e+001, -1.042139650090033e+003])
         np.savez_compressed(os.path.join(OUT, "dense_file.npz"), rows=rows, ls=ls, known_ls=known)
         print("dense file: ls", ls, "max |ls - known|", np.abs(ls - known).max())
+    # the reference's own experimental cross-wire data set (testing/SinglePointTargetUSCalibrationParametersEstimatorTest.cxx:
+    # 113-166 runs ANALYTIC then ITERATIVE least squares over testing/Data/crossWirePhantomTransformations.txt +
+    # crossWirePhantom2DPoints.txt, 54 poses, and only prints the results): what the reference returns for it
+    if not only or "usxw" in only:
+        T = np.loadtxt("/root/reference/testing/Data/crossWirePhantomTransformations.txt").reshape(-1, 3, 4)
+        q = np.loadtxt("/root/reference/testing/Data/crossWirePhantom2DPoints.txt")
+        rec = np.concatenate([T[:, :, :3].reshape(len(T), 9), T[:, :, 3], q], axis=1)
+        m = MODELS["usxw"]
+        np.savez_compressed(os.path.join(OUT, "usxw_file.npz"), data=rec, delta=5.0, ls0=ref.least_squares(m, 5.0, rec, 0),
+                            ls1=ref.least_squares(m, 5.0, rec, 1))
+        print("cross-wire file: analytic/iterative differ by", np.abs(ref.least_squares(m, 5.0, rec, 0) - ref.least_squares(m, 5.0, rec, 1)).max())
     if only:
         return
 

@@ -72,11 +72,9 @@ def test_port_matches_reference_fixture(port, name, m):
 def test_port_exhaustive_and_lsq_fixture(port, name, m):
     g = golden(name)
     for ls_type in ([0, 1] if name in ("circle2", "sphere3", "sphere4", "usxw", "uscp") else [1]):
-        # the cross-wire LM runs on vector residuals here and on the reference's scalar |e_i| residuals there:
-        # same minimum, compared at the north star's 1e-6 relative for converged Levenberg-Marquardt results
+        # Levenberg-Marquardt results: both sides run MINPACK's lmder (oracle/minpack_lm.h) on the reference's scalar residuals;
+        # the cross-wire valley is flat (hundreds of evaluations), so its end point is compared at the north star's 1e-6
         tol = 1e-6 if (name == "usxw" and ls_type == 1) else 1e-8
-        if name == "uscp" and ls_type == 1:   # the reference stops at tolerance 1e-7 (see uscp_iterative in lsqr_oracle.c):
-            tol = 1e-2                         # its stand-in minimiser returns the analytic start, a few 1e-3 from the minimiser
         prm, mask, frac, cnt, rank = port.ransac_exhaustive(m, float(g["delta"]), g["small"], ls_type=ls_type)
         assert np.array_equal(mask, g[f"ex_mask_ls{ls_type}"])
         assert frac == float(g[f"ex_fraction_ls{ls_type}"])
@@ -85,14 +83,6 @@ def test_port_exhaustive_and_lsq_fixture(port, name, m):
         _, bm = port.agree(m, float(g["delta"]), g["params"][b], g["data"])
         ls = port.least_squares(m, float(g["delta"]), g["data"][bm.astype(bool)], ls_type)
         assert same_up_to_sign(ls, g[f"lsq_ls{ls_type}"], SIGN_IDX[name], tol)
-        if name == "uscp" and ls_type == 1:   # ... and the restatement's answer is at least as good a minimum of sum |e_i|^2
-            inl = g["data"][bm.astype(bool)]
-
-            def cost(p):
-                R2 = inl[:, :9].reshape(-1, 3, 3)
-                w = np.outer(inl[:, 12], p[8:11]) + np.outer(inl[:, 13], p[11:14]) + p[0:3]
-                return float(np.sum((np.einsum("nij,nj->ni", R2, w) + inl[:, 9:12] - inl[:, 14:17]) ** 2))
-            assert cost(ls) <= cost(g[f"lsq_ls{ls_type}"]) * (1 + 1e-12)
 
 
 def test_config1_plane23(port):

@@ -11,7 +11,7 @@ minted by the reference.  Bars (BASELINE.json north_star):
 import numpy as np
 import pytest
 
-from conftest import SIGN_IDX, golden, same_up_to_sign
+from conftest import SIGN_IDX, golden, lm_case_is_clear, same_up_to_sign
 from lsqrrecipes_b200 import FP32, FP64, SAMPLE_EXHAUSTIVE, SAMPLE_LIST, SAMPLE_PARAMS, Engine, synth
 from oracle.pyoracle import INFO, MODELS
 
@@ -79,9 +79,7 @@ def test_exhaustive_compute_vs_reference_fixture(name, m):
         r = eng.ransac_exhaustive(precision=FP64)
         assert np.array_equal(r["mask"], g[f"ex_mask_ls{ls}"]), "consensus set must be bit-exact"
         assert r["fraction"] == float(g[f"ex_fraction_ls{ls}"])
-        # calibrated pointer, ITERATIVE: the reference stops its minimiser at tolerance 1e-7 (its stand-in returns the
-        # analytic start, a few 1e-3 from the minimiser the engine iterates to); see uscp_iterative in oracle/lsqr_oracle.c
-        tol = 1e-2 if (name == "uscp" and ls == 1) else REFINE_TOL
+        tol = REFINE_TOL
         assert same_up_to_sign(r["params"], g[f"ex_params_ls{ls}"], SIGN_IDX[name], tol)
         eng.close()
 
@@ -156,8 +154,13 @@ def test_crosswire_operator_interface(port):
     """SingleUnknownPointTargetUSCalibrationParametersEstimator through the Python mirror of the reference API:
     estimate() wants exactly four data (.cxx:21-22), ANALYTIC / ITERATIVE least squares, RANSAC::compute."""
     from lsqrrecipes_b200 import RANSAC, SingleUnknownPointTargetUSCalibrationParametersEstimator as Est
-    data, true = synth.crosswire(4000, seed=12)
     m = MODELS["usxw"]
+    for attempt in range(12):      # a case whose iterative fit ends well inside the reference's evaluation cap (conftest.lm_case_is_clear)
+        data, true = synth.crosswire(400, seed=12 + attempt)
+        cnt, flags = port.agree(m, 1.0, true, data)
+        port.least_squares(m, 1.0, data[flags.astype(bool)], 1)
+        if lm_case_is_clear(port, "usxw", 1):
+            break
     est = Est(1.0)
     p4, p5 = [], [1.0]
     est.estimate(data[:4], p4)
@@ -173,6 +176,7 @@ def test_crosswire_operator_interface(port):
         assert same_up_to_sign(prm, port.least_squares(m, 1.0, inl, ls_type), [], REFINE_TOL)
     assert est.agree(list(true), data[flags.astype(bool)][0]) and not est.agree(list(true), data[~flags.astype(bool)][0])
     prm, cs = [], []
+    est.setLeastSquaresType(Est.ANALYTIC)   # (compute() with the iterative refit: test_randomized_compute_end_to_end)
     frac = RANSAC.compute(prm, est, data, 0.999, cs)
     assert frac > 0.6 and len(prm) == 20 and sum(cs) == round(frac * len(data))
     assert np.abs(np.array(prm[:6]) - true[:6]).max() < 0.5 and abs(prm[9] - 0.143) < 1e-3 and abs(prm[10] - 0.139) < 1e-3
@@ -282,22 +286,30 @@ def test_circle_agree_literals():
 @pytest.mark.parametrize("name,m", ALL)
 def test_consensus_mask_and_refine_vs_oracle(port, name, m):
     D, P, k = INFO[m]
-    n = 50021
-    data, _ = synth.GENERATORS[name](n, seed=1234 + m)
     delta = synth.DELTAS[name]
-    subs = synth.random_subsets(n, k, 64, seed=5 + m)
-    c_ref, p_ref = port.score_subsets(m, delta, data, subs)
-    b = int(np.argmax(c_ref))
-    cnt_ref, mask_ref = port.agree(m, delta, p_ref[b], data)
     for ls in _ls_types(name):
+        for attempt in range(12):
+            n = 301 if (name == "usxw" and ls == 1) else 50021     # see conftest.lm_case_is_clear
+            data, _ = synth.GENERATORS[name](n, seed=1234 + m + 1000 * attempt)
+            subs = synth.random_subsets(n, k, 64, seed=5 + m)
+            c_ref, p_ref = port.score_subsets(m, delta, data, subs)
+            b = int(np.argmax(c_ref))
+            cnt_ref, mask_ref = port.agree(m, delta, p_ref[b], data)
+            want = port.least_squares(m, delta, data[mask_ref.astype(bool)], ls)
+            if lm_case_is_clear(port, name, ls):
+                break
+        else:
+            raise AssertionError("no clear Levenberg-Marquardt case found")
         eng = Engine(name, delta, ls_type=ls)
         eng.upload(data)
         cnt = eng.consensus(p_ref[b])
         assert cnt == cnt_ref
         assert np.array_equal(eng.get_mask(), mask_ref), "agree() mask must be bit-exact in fp64"
         prm = eng.refine()
-        want = port.least_squares(m, delta, data[mask_ref.astype(bool)], ls)
         assert same_up_to_sign(prm, want, SIGN_IDX[name], REFINE_TOL), (prm, want)
+        if name in ("circle2", "sphere3", "sphere4") and ls == 1:
+            # same MINPACK run: the number of function evaluations is the oracle's
+            assert eng.last_refine_stats()["lm_iterations"] == port.last_lm()[1]
         # leastSquaresEstimate() called directly on the inliers gives the same answer
         direct = eng.least_squares(data[mask_ref.astype(bool)])
         assert same_up_to_sign(direct, want, SIGN_IDX[name], REFINE_TOL)
@@ -419,16 +431,22 @@ def test_randomized_compute_end_to_end(port, name, m, precision):
     """RANSAC<T,S>::compute(parameters, estimator, data, 0.999, &consensusSet): the result must be the
     least-squares fit of a consensus set that the oracle reproduces from the chosen hypothesis."""
     D, P, k = INFO[m]
-    n = 20000
-    data, true = synth.GENERATORS[name](n, seed=2024 + m)
     delta = synth.DELTAS[name]
-    eng = Engine(name, delta)
-    eng.upload(data)
-    r = eng.ransac(0.999, precision=precision, seed=11)
+    for attempt in range(12):
+        n = 300 if name == "usxw" else 20000     # see conftest.lm_case_is_clear
+        data, true = synth.GENERATORS[name](n, seed=2024 + m + 1000 * attempt)
+        eng = Engine(name, delta)
+        eng.upload(data)
+        r = eng.ransac(0.999, precision=precision, seed=11)
+        mask = r["mask"].astype(bool)
+        want = port.least_squares(m, delta, data[mask], 1)
+        if lm_case_is_clear(port, name, 1):
+            break
+        eng.close()
+    else:
+        raise AssertionError("no clear Levenberg-Marquardt case found")
     assert r["fraction"] > 0.3 and r["tries"] >= 1
-    mask = r["mask"].astype(bool)
     assert mask.sum() == r["best_count"] and abs(r["fraction"] - mask.sum() / n) < 1e-15
-    want = port.least_squares(m, delta, data[mask], 1)
     assert same_up_to_sign(r["params"], want, SIGN_IDX[name], REFINE_TOL if precision == FP64 else 1e-4)
     # and the refined model explains the generating model's inliers
     cnt, _ = port.agree(m, delta, r["params"], data)
