@@ -382,8 +382,61 @@ class UserEstimator : public ParametersEstimator<Point2D, double> {
   virtual bool agree(std::vector<double>&, Point2D&) { return false; }
 };
 
+// std::vector<bool> filled from the packed bit mask (host only)
+static void bitsCase() {
+  std::printf("consensus set from packed bits\n");
+  for (size_t n : {size_t(0), size_t(1), size_t(31), size_t(64), size_t(1000003)}) {
+    std::vector<uint32_t> words((n + 31) / 32);
+    for (size_t w = 0; w < words.size(); w++) words[w] = static_cast<uint32_t>(rng());
+    std::vector<bool> got(5, true);
+    b200::assignBits(got, words, n);
+    bool same = got.size() == n;
+    for (size_t i = 0; same && i < n; i++) same = got[i] == (((words[i >> 5] >> (i & 31)) & 1u) != 0);
+    CHECK(same, "vector<bool> equals the bit mask");
+  }
+}
+
+// A data set large enough to be spread over every visible GPU (b200Options().multiGpuMinData): the result must be the one a
+// single GPU returns -- same consensus set, same fraction, parameters to the summation-order tolerance of the sharded refine.
+static void multiGpuCase() {
+  const int gpus = lsqr_device_count();
+  std::printf("PlaneParametersEstimator<3>, 2 M points on %d GPU(s)\n", gpus);
+  double n[3] = {0.3, -0.5, 0.81};
+  const double nn = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+  for (int i = 0; i < 3; i++) n[i] /= nn;
+  std::vector<Point3D> data(2000003);
+  for (size_t i = 0; i < data.size(); i++) {
+    Point3D p;
+    for (int j = 0; j < 3; j++) p[j] = uni(-1000, 1000);
+    if (i % 10 < 6) {
+      double s = 0;
+      for (int j = 0; j < 3; j++) s += (p[j] - 5.0) * n[j];
+      for (int j = 0; j < 3; j++) p[j] += -s * n[j] + gauss(0.4);
+    }
+    data[i] = p;
+  }
+  PlaneParametersEstimator<3> est(0.5);
+  std::vector<double> one, all;
+  std::vector<bool> cs_one, cs_all;
+  const size_t keep = b200Options().multiGpuMinData;
+  b200Options().multiGpuMinData = ~static_cast<size_t>(0);            // one GPU
+  const double f_one = RANSAC<Point3D, double>::compute(one, &est, data, 0.999, &cs_one);
+  b200Options().multiGpuMinData = keep;                               // every visible GPU
+  const double f_all = RANSAC<Point3D, double>::compute(all, &est, data, 0.999, &cs_all);
+  CHECK(one.size() == 6 && all.size() == 6, "both runs return a plane");
+  if (one.size() != 6 || all.size() != 6) return;
+  CHECK(f_one == f_all && cs_one == cs_all, "same consensus set on one GPU and on all");
+  double d = 0;
+  for (int j = 0; j < 6; j++) d = std::max(d, std::fabs(one[j] - all[j]) / std::max(1.0, std::fabs(one[j])));
+  std::printf("  fraction %.6f / %.6f, max parameter difference %.2e, multi-GPU context %s\n", f_one, f_all, d, b200::multiContext() ? "in use" : "absent (one device)");
+  CHECK(d < 1e-9, "same refined plane");
+  CHECK(gpus < 2 || (b200::multiContext() && lsqr_ctx_world(b200::multiContext()) == gpus), "the large problem ran on every visible GPU");
+}
+
 int main() {
+  bitsCase();
   if (!b200::context()) { std::printf("no GPU context: %s\n", b200LastError()); return 2; }
+  multiGpuCase();
   planeCase();
   line2dCase();
   sphereCase();

@@ -29,7 +29,10 @@ namespace lsqrRecipes {
 struct B200RansacOptions {
   int precision;        // LSQR_FP32 (default) or LSQR_FP64 for the consensus scoring
   unsigned long long seed;
-  B200RansacOptions() : precision(LSQR_FP32), seed(0) {}
+  // Data sets of at least this many elements are spread over every visible GPU (points replicated, hypotheses partitioned,
+  // refine sharded; NCCL inside the library); smaller ones stay on one device, where a call costs fewer fixed latencies.
+  size_t multiGpuMinData;
+  B200RansacOptions() : precision(LSQR_FP32), seed(0), multiGpuMinData(static_cast<size_t>(1) << 20) {}
 };
 inline B200RansacOptions& b200Options() { static B200RansacOptions o; return o; }
 
@@ -61,7 +64,7 @@ class RANSAC {
       b200::lastErrorStorage() = "this ParametersEstimator has no GPU path (b200Describe not overridden); lsqr_b200 has no CPU fallback";
       return 0;
     }
-    lsqr_ctx* ctx = b200::configured(d);
+    lsqr_ctx* ctx = b200::configured(d, data.size() >= b200Options().multiGpuMinData);
     if (!ctx) return 0;
     double probe[32];
     if (!data.empty() && paramEstimator->b200PackDatum(data[0], probe)) {
@@ -72,15 +75,15 @@ class RANSAC {
       for (size_t i = 0; i < data.size(); i++) paramEstimator->b200PackDatum(data[i], &packed[i * dim]);
       if (!b200::check(ctx, lsqr_upload(ctx, packed.data(), data.size(), sizeof(double) * dim))) return 0;
     } else if (!b200::check(ctx, lsqr_upload(ctx, data.data(), data.size(), sizeof(T)))) return 0;
-    std::vector<uint8_t> mask(consensusSet ? data.size() : 0);
     lsqr_compute_result r;
-    const int rc = exhaustive ? lsqr_ransac_exhaustive(ctx, LSQR_FP64, consensusSet ? mask.data() : NULL, &r)
-                              : lsqr_ransac(ctx, prob, b200Options().precision, b200Options().seed, consensusSet ? mask.data() : NULL, &r);
+    const int rc = exhaustive ? lsqr_ransac_exhaustive(ctx, LSQR_FP64, NULL, &r) : lsqr_ransac(ctx, prob, b200Options().precision, b200Options().seed, NULL, &r);
     if (!b200::check(ctx, rc)) return 0;
     if (r.best_count == 0) return 0;
     if (consensusSet) {
-      consensusSet->clear();
-      consensusSet->insert(consensusSet->begin(), mask.begin(), mask.end());
+      // the consensus set comes back as packed bits (1/8 of a byte mask) and goes into std::vector<bool> word by word
+      std::vector<uint32_t> words((data.size() + 31) / 32);
+      if (!b200::check(ctx, lsqr_get_mask_bits(ctx, words.data()))) return 0;
+      b200::assignBits(*consensusSet, words, data.size());
     }
     for (int i = 0; i < r.n_params; i++) parameters.push_back(static_cast<S>(r.params[i]));
     return r.fraction;

@@ -88,6 +88,24 @@ int lsqr_model_info(int model, int* dim, int* nparams, int* k);
 
 /* ---- context ---------------------------------------------------------------------- */
 int lsqr_ctx_create(lsqr_ctx** out, int device);
+/* Number of CUDA devices visible to the process (0 when there is none). */
+int lsqr_device_count(void);
+/* One context spanning `ngpus` devices of this process (ngpus <= 0: every visible device) -- SURVEY.md 8b's ctx_create(ngpus).
+ * The data are replicated on every GPU, the hypotheses of every request are partitioned by global index, the consensus set
+ * and the refine are sharded by point range; the exchange steps are native NCCL calls inside the library (one
+ * ncclAllReduce(max) on the packed 64-bit key per request, one ncclAllReduce(sum) of <= 91 doubles per refine pass, and the
+ * all-gather that replicates the uploaded points over NVLink).  Every entry point below accepts such a context and returns
+ * what a single-GPU context returns (lsqr_upload_device, lsqr_set_shard, lsqr_ctx_set_stream and lsqr_ctx_init_nccl excepted:
+ * LSQR_ERR_ARG).  The estimator's own methods (estimate / agree / least squares) run on the first device. */
+int lsqr_ctx_create_multi(lsqr_ctx** out, int ngpus);
+/* Number of GPUs / ranks behind the context (1 for lsqr_ctx_create). */
+int lsqr_ctx_world(const lsqr_ctx* ctx);
+/* One process per GPU (torchrun, MPI): rank 0 calls lsqr_nccl_unique_id, the launcher broadcasts the 128 bytes, every rank
+ * calls lsqr_ctx_init_nccl on its own single-device context.  From then on the context is rank `rank` of `world` and performs
+ * its collectives itself with ncclAllReduce / ncclAllGather on its stream; lsqr_upload fetches every world-th chunk of the
+ * host buffer (the same buffer content on every rank) and all-gathers the rest. */
+int lsqr_nccl_unique_id(void* out_id, size_t bytes /* >= 128 */);
+int lsqr_ctx_init_nccl(lsqr_ctx* ctx, const void* id, size_t bytes, int rank, int world);
 void lsqr_ctx_destroy(lsqr_ctx* ctx);
 const char* lsqr_last_error(const lsqr_ctx* ctx);
 /* Run every kernel of this context on an existing CUDA stream (cudaStream_t passed as void*). */
@@ -108,13 +126,13 @@ int lsqr_upload(lsqr_ctx* ctx, const void* aos, size_t n, size_t stride_bytes);
 /* Same, for a buffer that already lives in device memory (packed doubles, dim per record). */
 int lsqr_upload_device(lsqr_ctx* ctx, const double* dev_packed, size_t n);
 
-/* Multi-GPU sharding: this context scores hypotheses [rank*H/world, (rank+1)*H/world) of every
- * request and refines the points [rank*N/world, (rank+1)*N/world).  The two exchange steps go
- * through caller-supplied hooks operating IN PLACE on device memory (NCCL all-reduce over
- * NVLink in bench.py).  Hooks must be stream-ordered on `cuda_stream`.
- * Counts, fractions and refined parameters are global; the consensus set a rank returns (lsqr_get_mask, the mask
- * of lsqr_ransac) holds the bits of ITS point shard and zeros elsewhere -- OR the ranks' masks for the full set
- * (lsqrrecipes_b200/dist.py: full_mask). */
+/* Multi-GPU sharding with caller-supplied collectives (for launchers that own the communicator; lsqr_ctx_create_multi and
+ * lsqr_ctx_init_nccl are the native alternatives): this context scores hypotheses [rank*H/world, (rank+1)*H/world) of every
+ * request and refines the points [rank*N/world, (rank+1)*N/world) (boundaries on 32-datum words).  The two exchange steps go
+ * through the hooks, which operate IN PLACE on device memory and must be stream-ordered on `cuda_stream`.
+ * Counts, fractions and refined parameters are global.  Of the consensus set a rank writes ITS point shard only
+ * (lsqr_get_mask, lsqr_get_mask_bits, the mask of lsqr_ransac): bytes outside [begin, end) of the caller's buffer are left
+ * untouched; lsqrrecipes_b200/dist.py (full_mask) assembles the ranks' parts.  A multi-GPU group writes all parts itself. */
 typedef int (*lsqr_allreduce_max_u64_fn)(void* user, uint64_t* dev_key, void* cuda_stream);
 typedef int (*lsqr_allreduce_sum_f64_fn)(void* user, double* dev_vals, int count, void* cuda_stream);
 int lsqr_set_shard(lsqr_ctx* ctx, int rank, int world, lsqr_allreduce_max_u64_fn max_fn,
@@ -154,6 +172,9 @@ int lsqr_consensus(lsqr_ctx* ctx, const double* params, uint32_t* out_count);
  * destination (cudaHostAlloc / cudaHostRegister) receives the DMA directly; any other is filled through the
  * library's own staging buffer. */
 int lsqr_get_mask(lsqr_ctx* ctx, uint8_t* out_bytes);
+/* The same set as packed bits: datum i is bit (i & 31) of word i >> 5 (ceil(n / 32) words).  1/8 of the bytes of
+ * lsqr_get_mask; include/lsqrRecipes/RANSAC.h fills std::vector<bool> from it. */
+int lsqr_get_mask_bits(lsqr_ctx* ctx, uint32_t* out_words);
 /* leastSquaresEstimate() over the stored consensus set (RANSAC.hxx:138), or over all data
  * when use_mask == 0.  *n_params = 0 means the reference's "empty parameters" (degenerate). */
 int lsqr_refine(lsqr_ctx* ctx, int use_mask, double* out_params, int* n_params);

@@ -66,6 +66,11 @@ def load_library():
     sig = {
         "lsqr_model_info": (c.c_int, [c.c_int, c.POINTER(c.c_int), c.POINTER(c.c_int), c.POINTER(c.c_int)]),
         "lsqr_ctx_create": (c.c_int, [c.POINTER(c.c_void_p), c.c_int]),
+        "lsqr_device_count": (c.c_int, []),
+        "lsqr_ctx_create_multi": (c.c_int, [c.POINTER(c.c_void_p), c.c_int]),
+        "lsqr_ctx_world": (c.c_int, [c.c_void_p]),
+        "lsqr_nccl_unique_id": (c.c_int, [c.c_void_p, c.c_size_t]),
+        "lsqr_ctx_init_nccl": (c.c_int, [c.c_void_p, c.c_void_p, c.c_size_t, c.c_int, c.c_int]),
         "lsqr_ctx_destroy": (None, [c.c_void_p]),
         "lsqr_last_error": (c.c_char_p, [c.c_void_p]),
         "lsqr_ctx_set_stream": (c.c_int, [c.c_void_p, c.c_void_p]),
@@ -77,6 +82,7 @@ def load_library():
         "lsqr_score": (c.c_int, [c.c_void_p, c.POINTER(ScoreArgs), c.POINTER(ScoreResult)]),
         "lsqr_consensus": (c.c_int, [c.c_void_p, _dp, _u32p]),
         "lsqr_get_mask": (c.c_int, [c.c_void_p, _u8p]),
+        "lsqr_get_mask_bits": (c.c_int, [c.c_void_p, _u32p]),
         "lsqr_refine": (c.c_int, [c.c_void_p, c.c_int, _dp, c.POINTER(c.c_int)]),
         "lsqr_ransac": (c.c_int, [c.c_void_p, c.c_double, c.c_int, c.c_uint64, _u8p, c.POINTER(ComputeResult)]),
         "lsqr_ransac_exhaustive": (c.c_int, [c.c_void_p, c.c_int, _u8p, c.POINTER(ComputeResult)]),
@@ -101,6 +107,7 @@ EXPORTED_SYMBOLS = [
     "lsqr_set_estimator", "lsqr_upload", "lsqr_upload_device", "lsqr_set_shard", "lsqr_score", "lsqr_consensus", "lsqr_get_mask",
     "lsqr_refine", "lsqr_ransac", "lsqr_ransac_exhaustive", "lsqr_ransac_batch", "lsqr_estimate", "lsqr_agree", "lsqr_least_squares",
     "lsqr_microbench_fma", "lsqr_last_refine_stats", "lsqr_weighted_least_squares",
+    "lsqr_device_count", "lsqr_ctx_create_multi", "lsqr_ctx_world", "lsqr_nccl_unique_id", "lsqr_ctx_init_nccl", "lsqr_get_mask_bits",
 ]
 
 
@@ -111,14 +118,21 @@ def _ptr(a, t):
 class Engine:
     """One lsqr_ctx.  `model` is a name from MODELS or an id."""
 
-    def __init__(self, model, delta, aux=0.0, ls_type=LS_GEOMETRIC, device=0):
+    def __init__(self, model, delta, aux=0.0, ls_type=LS_GEOMETRIC, device=0, gpus=None):
+        """gpus: None -> one context on `device`; an int -> lsqr_ctx_create_multi over that many devices of this process
+        (0 = all visible), native NCCL inside the library."""
         self.lib = load_library()
         self.model = MODELS[model] if isinstance(model, str) else int(model)
         self.dim, self.n_params, self.k = MODEL_INFO[self.model]
         h = ctypes.c_void_p()
-        rc = self.lib.lsqr_ctx_create(ctypes.byref(h), device)
+        if gpus is None:
+            rc = self.lib.lsqr_ctx_create(ctypes.byref(h), device)
+            what = f"lsqr_ctx_create(device={device})"
+        else:
+            rc = self.lib.lsqr_ctx_create_multi(ctypes.byref(h), int(gpus))
+            what = f"lsqr_ctx_create_multi({gpus})"
         if rc != 0:
-            raise LsqrError(f"lsqr_ctx_create(device={device}) failed with status {rc}: no usable sm_100 CUDA device (there is no CPU fallback)")
+            raise LsqrError(f"{what} failed with status {rc}: no usable sm_100 CUDA device / NCCL (there is no CPU fallback)")
         self.h = h
         self._hooks = None
         self.n = 0
@@ -170,6 +184,20 @@ class Engine:
         self.n = n
         self._ck(self.lib.lsqr_upload_device(self.h, ctypes.c_void_p(dev_ptr), n))
 
+    @property
+    def world(self):
+        return int(self.lib.lsqr_ctx_world(self.h))
+
+    def nccl_unique_id(self):
+        buf = ctypes.create_string_buffer(128)
+        self._ck(self.lib.lsqr_nccl_unique_id(buf, 128))
+        return buf.raw
+
+    def init_nccl(self, unique_id, rank, world):
+        """One process per GPU: the library does its collectives itself (ncclAllReduce / ncclAllGather on its stream)."""
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self.lib.lsqr_ctx_init_nccl(self.h, buf, 128, int(rank), int(world)))
+
     def set_shard(self, rank, world, max_fn=None, sum_fn=None):
         mf = MAX_FN(max_fn) if max_fn else MAX_FN()
         sf = SUM_FN(sum_fn) if sum_fn else SUM_FN()
@@ -215,6 +243,12 @@ class Engine:
         m = np.zeros(self.n, dtype=np.uint8)
         self._ck(self.lib.lsqr_get_mask(self.h, _ptr(m, _u8p)))
         return m
+
+    def get_mask_bits(self):
+        """The consensus set as packed bits (datum i = bit i & 31 of word i >> 5), unpacked to one bool per datum here."""
+        w = np.zeros((self.n + 31) // 32, dtype=np.uint32)
+        self._ck(self.lib.lsqr_get_mask_bits(self.h, _ptr(w, _u32p)))
+        return np.unpackbits(w.view(np.uint8), bitorder="little")[: self.n]
 
     def refine(self, use_mask=True):
         out = np.zeros(20)

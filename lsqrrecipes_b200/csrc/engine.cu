@@ -5,14 +5,37 @@
 // sequences launches, evaluates the scalar stop rule (RANSAC.hxx:107-110) between rounds and
 // moves results.  There is no CPU fallback: every entry point fails with LSQR_ERR_CUDA when no
 // device is usable.
+//
+// Data movement of one compute() call:
+//   * upload: the caller's AoS records go to the device in chunks on a copy stream (straight from page-locked memory; from
+//     pageable memory -- std::vector<T>, the reference's only input type -- through a ring of pinned buffers filled by a few
+//     host threads) while the chunks that have landed are transposed to the SoA fp64 / fp32 working layouts on the compute
+//     stream.  With several GPUs each one fetches every world-th chunk over its own PCIe link and an NCCL all-gather over
+//     NVLink fans the round out, so the host buffer crosses PCIe once in total.
+//   * scoring round -> arg-max -> (all-reduce of the 8-byte key) -> winner re-derived on the device -> ONE small copy back
+//     (count for the stop rule, subset, parameters);
+//   * consensus set + least-squares moments in one streaming pass that also writes the caller's byte mask -> (all-reduce of
+//     the moments) -> on-device solve / Levenberg-Marquardt -> ONE copy back of parameters, count and mask.
+// Multi-GPU: points replicated, hypotheses partitioned by global index, refine sharded by point range.
+// Collectives are native NCCL calls on the context's stream (single-process group: lsqr_ctx_create_multi; one process per
+// GPU: lsqr_ctx_init_nccl), or caller-supplied hooks (lsqr_set_shard).
 #include "../../include/lsqr_b200.h"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <limits>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "engine.h"
@@ -21,26 +44,144 @@ using namespace lsqr;
 
 namespace {
 constexpr int kSmall = 1024, kSmIn = 0, kSmOut = 32, kSmLm = 64, kSmEst = 640, kSmSink = 800;   // layout of lsqr_ctx::small_dev
+
+// ---- NCCL, resolved at first use ---------------------------------------------------------------
+// The library is loaded with dlopen instead of a DT_NEEDED entry: a Python process that imports torch carries torch's own
+// libnccl.so.2 (2.28), the system has another (2.27), and whichever is mapped first serves the whole process.  Resolving
+// at the first multi-GPU call picks up the copy that is already there (RTLD_NOLOAD) and otherwise the system one.
+struct Nccl {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+Nccl& nccl() {
+  static Nccl n;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) return;
+    n.handle = h;
+#define SYM(field, name) n.field = reinterpret_cast<decltype(n.field)>(dlsym(h, name))
+    SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommInitAll, "ncclCommInitAll"); SYM(CommDestroy, "ncclCommDestroy");
+    SYM(AllReduce, "ncclAllReduce"); SYM(AllGather, "ncclAllGather"); SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    n.ok = n.GetUniqueId && n.CommInitRank && n.CommInitAll && n.CommDestroy && n.AllReduce && n.AllGather && n.GetErrorString;
+  });
+  return n;
 }
 
-namespace {
+// ---- a few host threads for pageable -> pinned staging copies ------------------------------------
+class HostCopier {
+ public:
+  explicit HostCopier(int nthreads) : n_(std::max(1, nthreads)) {
+    for (int t = 1; t < n_; t++) workers_.emplace_back([this, t] { loop(t); });
+  }
+  ~HostCopier() {
+    { std::lock_guard<std::mutex> lk(m_); stop_ = true; gen_++; }
+    cv_.notify_all();
+    for (auto& w : workers_) w.join();
+  }
+  void copy(void* dst, const void* src, size_t bytes) {
+    if (n_ == 1 || bytes < (1u << 20)) { memcpy(dst, src, bytes); return; }
+    { std::lock_guard<std::mutex> lk(m_); dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes; pending_ = n_ - 1; gen_++; }
+    cv_.notify_all();
+    slice(0);
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+  }
+
+ private:
+  void slice(int t) {
+    const size_t per = (bytes_ / n_ + 63) & ~(size_t)63, lo = std::min(bytes_, per * t), hi = (t == n_ - 1) ? bytes_ : std::min(bytes_, per * (t + 1));
+    if (hi > lo) memcpy(dst_ + lo, src_ + lo, hi - lo);
+  }
+  void loop(int t) {
+    uint64_t seen = 0;
+    for (;;) {
+      { std::unique_lock<std::mutex> lk(m_); cv_.wait(lk, [&] { return gen_ != seen; }); seen = gen_; if (stop_) return; }
+      slice(t);
+      { std::lock_guard<std::mutex> lk(m_); pending_--; }
+      done_.notify_one();
+    }
+  }
+  int n_;
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  char* dst_ = nullptr; const char* src_ = nullptr; size_t bytes_ = 0;
+  int pending_ = 0; uint64_t gen_ = 0; bool stop_ = false;
+};
+
+// ---- one worker thread per device of a single-process multi-GPU group -----------------------------
+class Workers {
+ public:
+  explicit Workers(int n) : n_(n), rc_(n, 0) {
+    for (int t = 0; t < n_; t++) threads_.emplace_back([this, t] { loop(t); });
+  }
+  ~Workers() {
+    { std::lock_guard<std::mutex> lk(m_); stop_ = true; gen_++; }
+    cv_.notify_all();
+    for (auto& w : threads_) w.join();
+  }
+  // runs fn(rank) on every worker concurrently; returns the first non-zero status
+  int run(const std::function<int(int)>& fn) {
+    { std::lock_guard<std::mutex> lk(m_); fn_ = &fn; pending_ = n_; gen_++; }
+    cv_.notify_all();
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+    for (int r : rc_) if (r) return r;
+    return 0;
+  }
+
+ private:
+  void loop(int t) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<int(int)>* fn;
+      { std::unique_lock<std::mutex> lk(m_); cv_.wait(lk, [&] { return gen_ != seen; }); seen = gen_; if (stop_) return; fn = fn_; }
+      const int rc = (*fn)(t);
+      { std::lock_guard<std::mutex> lk(m_); rc_[t] = rc; pending_--; }
+      done_.notify_one();
+    }
+  }
+  int n_;
+  std::vector<int> rc_;
+  std::vector<std::thread> threads_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<int(int)>* fn_ = nullptr;
+  int pending_ = 0; uint64_t gen_ = 0; bool stop_ = false;
+};
 
 struct DataSet {
   double* soa64 = nullptr;
   float* soa32 = nullptr;
   uint32_t* maskbits = nullptr;
+  double* center_dev = nullptr;   // kMaxDim doubles
   size_t ld = 0, cap = 0;   // cap = allocated leading dimension
   uint32_t n = 0;
   int D = 0, capD = 0;
-  double center[kMaxDim] = {0};
   bool moments_valid = false;  // rb.moments holds the LS moments of the stored consensus set
   bool mask_valid = false;
+  bool bytes_valid = false;    // ctx->mask_dev holds the consensus set of this data set, one byte per datum (own shard)
   DataView view() const {
     DataView v;
-    v.soa64 = soa64; v.soa32 = soa32; v.ld = ld; v.n = n;
-    for (int i = 0; i < kMaxDim; i++) v.center[i] = center[i];
+    v.soa64 = soa64; v.soa32 = soa32; v.ld = ld; v.n = n; v.center = center_dev;
     return v;
   }
+};
+
+struct Group {
+  std::vector<lsqr_ctx*> kids;
+  std::unique_ptr<Workers> workers;
 };
 
 }  // namespace
@@ -50,6 +191,7 @@ struct lsqr_ctx {
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;
   std::string err;
   uint64_t launches = 0;
 
@@ -67,13 +209,13 @@ struct lsqr_ctx {
   int32_t* list_dev = nullptr; size_t list_cap = 0;
   double* params_in_dev = nullptr; size_t params_in_cap = 0;
   unsigned long long* key_dev = nullptr;  // [0] key, [1] n_valid (as u32 in low half)
+  WinnerRecord* winner_dev = nullptr;
   double* small_dev = nullptr;            // kSmall doubles: parameters in @kSmIn, solve out @kSmOut, LM state @kSmLm, estimate() input @kSmEst, sink @kSmSink
-  double* center_dev = nullptr;           // kMaxDim doubles
-  double* center_partials = nullptr;      // 256 * kMaxDim
   // refine
   RefineBuffers rb{};
   // pinned host scratch
-  double* pin = nullptr;                  // 64 doubles
+  double* pin = nullptr;                  // 64 doubles, then one WinnerRecord
+  WinnerRecord* winner_pin = nullptr;
   double* weights_dev = nullptr; size_t weights_cap = 0;   // lsqr_weighted_least_squares
   double* bt_data = nullptr; size_t bt_data_cap = 0;       // lsqr_ransac_batch: packed problems, offsets, results
   uint64_t* bt_off = nullptr; size_t bt_off_cap = 0;
@@ -81,6 +223,12 @@ struct lsqr_ctx {
   uint32_t* bt_cnt = nullptr; size_t bt_cnt_cap = 0;
   uint8_t* mask_dev = nullptr; size_t mask_dev_cap = 0;   // consensus set, one byte per datum (device)
   uint8_t* mask_pin = nullptr; size_t mask_pin_cap = 0;   // pinned bounce buffer for its download
+  // upload pipeline
+  static constexpr int kRing = 4;
+  unsigned char* up_pin[kRing] = {nullptr, nullptr, nullptr, nullptr}; size_t up_pin_bytes = 0;
+  cudaEvent_t up_ev[kRing]{};             // chunk in ring slot i has been copied to the device
+  cudaEvent_t up_land[8]{};               // chunk copies landed, round-robin
+  std::unique_ptr<HostCopier> copier;
   cudaEvent_t ev[6]{};
 
   // sharding
@@ -88,6 +236,8 @@ struct lsqr_ctx {
   lsqr_allreduce_max_u64_fn max_fn = nullptr;
   lsqr_allreduce_sum_f64_fn sum_fn = nullptr;
   void* comm_user = nullptr;
+  ncclComm_t comm = nullptr;              // native collectives (lsqr_ctx_create_multi / lsqr_ctx_init_nccl)
+  Group* group = nullptr;                 // the handle returned by lsqr_ctx_create_multi: no device state of its own
 
   // stats of the last refine
   double refine_kernel_ms = 0, refine_bytes = 0;
@@ -110,6 +260,11 @@ int fail(lsqr_ctx* c, int code, const std::string& msg) {
     cudaError_t e__ = cudaGetLastError();                                                                \
     if (e__ != cudaSuccess) return fail(ctx, LSQR_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__)); \
   } while (0)
+#define CKN(call)                                                                                        \
+  do {                                                                                                   \
+    ncclResult_t r__ = (call);                                                                           \
+    if (r__ != ncclSuccess) return fail(ctx, LSQR_ERR_COMM, std::string(#call) + ": " + nccl().GetErrorString(r__)); \
+  } while (0)
 
 template <class T> int ensure(lsqr_ctx* ctx, T** p, size_t* cap, size_t want) {
   if (*cap >= want && *p) return 0;
@@ -122,8 +277,17 @@ template <class T> int ensure(lsqr_ctx* ctx, T** p, size_t* cap, size_t want) {
 
 size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
+void free_dataset(DataSet& ds) {
+  cudaFree(ds.soa64); cudaFree(ds.soa32); cudaFree(ds.maskbits); cudaFree(ds.center_dev);
+  ds = DataSet();
+}
+
 int ensure_dataset(lsqr_ctx* ctx, DataSet& ds, int D, uint32_t n) {
   const size_t ld = round_up(std::max<size_t>(n, 1), kTilePad);
+  if (!ds.center_dev) {
+    CK(cudaMalloc((void**)&ds.center_dev, sizeof(double) * kMaxDim));
+    CK(cudaMemsetAsync(ds.center_dev, 0, sizeof(double) * kMaxDim, ctx->stream));
+  }
   if (ds.cap < ld || ds.capD < D) {
     if (ds.soa64) cudaFree(ds.soa64);
     if (ds.soa32) cudaFree(ds.soa32);
@@ -136,7 +300,7 @@ int ensure_dataset(lsqr_ctx* ctx, DataSet& ds, int D, uint32_t n) {
     ds.cap = ld; ds.capD = Dc;
   }
   ds.ld = ld; ds.n = n; ds.D = D;
-  ds.moments_valid = false; ds.mask_valid = false;
+  ds.moments_valid = false; ds.mask_valid = false; ds.bytes_valid = false;
   return 0;
 }
 
@@ -156,20 +320,35 @@ int ensure_hyp(lsqr_ctx* ctx, size_t H) {
   return 0;
 }
 
-// AoS on the device -> SoA fp64 + centre + fp32 copy.
-int build_layouts(lsqr_ctx* ctx, DataSet& ds, const unsigned char* aos_dev, size_t stride) {
-  launch_ingest(ds.D, aos_dev, stride, ds.n, ds.soa64, ds.ld, ctx->stream); ctx->launches++;
-  launch_center(ctx->model, ds.soa64, ds.ld, ds.n, ctx->center_partials, ctx->center_dev, ctx->stream); ctx->launches += 2;
-  launch_make32(ds.D, ds.soa64, ctx->center_dev, ds.soa32, ds.ld, ctx->stream); ctx->launches++;
-  CKL();
-  CK(cudaMemsetAsync(ds.maskbits, 0, sizeof(uint32_t) * (ds.ld / 32), ctx->stream));
-  CK(cudaMemcpyAsync(ctx->pin, ctx->center_dev, sizeof(double) * kMaxDim, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  for (int i = 0; i < kMaxDim; i++) ds.center[i] = ctx->pin[i];
+// ---- collectives ---------------------------------------------------------------------------------
+int comm_max_u64(lsqr_ctx* ctx, unsigned long long* dev) {
+  if (ctx->world <= 1) return 0;
+  if (ctx->comm) { CKN(nccl().AllReduce(dev, dev, 1, ncclUint64, ncclMax, ctx->comm, ctx->stream)); return 0; }
+  if (!ctx->max_fn) return fail(ctx, LSQR_ERR_COMM, "sharded context without an all-reduce hook");
+  if (ctx->max_fn(ctx->comm_user, reinterpret_cast<uint64_t*>(dev), (void*)ctx->stream)) return fail(ctx, LSQR_ERR_COMM, "max all-reduce hook failed");
+  return 0;
+}
+int comm_sum_f64(lsqr_ctx* ctx, double* dev, int count) {
+  if (ctx->world <= 1) return 0;
+  if (ctx->comm) { CKN(nccl().AllReduce(dev, dev, (size_t)count, ncclDouble, ncclSum, ctx->comm, ctx->stream)); return 0; }
+  if (!ctx->sum_fn) return fail(ctx, LSQR_ERR_COMM, "sharded context without a sum all-reduce hook");
+  if (ctx->sum_fn(ctx->comm_user, dev, count, (void*)ctx->stream)) return fail(ctx, LSQR_ERR_COMM, "sum all-reduce hook failed");
   return 0;
 }
 
-int upload_to(lsqr_ctx* ctx, DataSet& ds, const void* aos, size_t n, size_t stride, bool on_device) {
+// ---- upload ----------------------------------------------------------------------------------------
+bool is_pinned(const void* p) {
+  cudaPointerAttributes attr{};
+  const bool ok = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  if (!ok) cudaGetLastError();   // an unregistered pointer is not an error here
+  return ok;
+}
+
+// AoS records, host or device -> SoA fp64 + fp32 on the device, chunk by chunk.
+//   * single context: chunk c is copied on the copy stream and transposed on the compute stream as soon as it has landed;
+//   * natively sharded context (ctx->comm): rank r copies chunks r, r + W, r + 2W, ... of the host buffer and round j of
+//     chunks [jW, (j+1)W) is completed by an in-place all-gather over NVLink before it is transposed.
+int upload_to(lsqr_ctx* ctx, DataSet& ds, const void* aos, size_t n, size_t stride, bool on_device, bool allow_sharded) {
   if (ctx->model < 0) return fail(ctx, LSQR_ERR_STATE, "lsqr_set_estimator must be called before uploading data");
   const ModelInfo mi = model_info(ctx->model);
   if (n > 0xFFFFFFF0ull) return fail(ctx, LSQR_ERR_ARG, "too many data records");
@@ -177,13 +356,71 @@ int upload_to(lsqr_ctx* ctx, DataSet& ds, const void* aos, size_t n, size_t stri
   if (n && !aos) return fail(ctx, LSQR_ERR_ARG, "null data pointer");
   CK(cudaSetDevice(ctx->device));
   if (int rc = ensure_dataset(ctx, ds, mi.D, (uint32_t)n)) return rc;
-  const unsigned char* src = static_cast<const unsigned char*>(aos);
-  if (!on_device && n) {
-    if (int rc = ensure(ctx, &ctx->staging, &ctx->staging_cap, n * stride)) return rc;
-    CK(cudaMemcpyAsync(ctx->staging, aos, n * stride, cudaMemcpyHostToDevice, ctx->stream));
-    src = ctx->staging;
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemsetAsync(ds.maskbits, 0, sizeof(uint32_t) * (ds.ld / 32), s));
+  const uint32_t N = (uint32_t)n, pad_to = (uint32_t)ds.ld;
+  const uint32_t sample = std::min<uint32_t>(N, kCenterSample);
+  if (on_device || n == 0) {
+    const unsigned char* src = static_cast<const unsigned char*>(aos);
+    launch_center_sample(ctx->model, src, stride, sample, ds.center_dev, s);
+    launch_ingest(mi.D, src, stride, 0, N, pad_to, ds.center_dev, ds.soa64, ds.soa32, ds.ld, s);
+    ctx->launches += 2;
+    CKL();
+    return LSQR_OK;
   }
-  return build_layouts(ctx, ds, src, stride);
+  const bool sharded = allow_sharded && ctx->comm != nullptr && ctx->world > 1;
+  const int W = sharded ? ctx->world : 1;
+  // chunk: at least the centre sample, ~1/8 of a rank's share, between 256 KB and 16 MB
+  size_t chunk_rec = std::max<size_t>(kCenterSample, std::min<size_t>((16u << 20) / stride, std::max<size_t>((256u << 10) / stride, (n / W + 7) / 8)));
+  chunk_rec = round_up(chunk_rec, 32);
+  const size_t chunk_bytes = chunk_rec * stride;
+  const size_t n_chunks = (n + chunk_rec - 1) / chunk_rec, rounds = (n_chunks + W - 1) / W;
+  if (int rc = ensure(ctx, &ctx->staging, &ctx->staging_cap, rounds * W * chunk_bytes)) return rc;
+  const bool pinned = is_pinned(aos);
+  if (!pinned) {
+    if (ctx->up_pin_bytes < chunk_bytes) {
+      for (int i = 0; i < lsqr_ctx::kRing; i++) { if (ctx->up_pin[i]) cudaFreeHost(ctx->up_pin[i]); ctx->up_pin[i] = nullptr; }
+      ctx->up_pin_bytes = 0;
+      for (int i = 0; i < lsqr_ctx::kRing; i++) CK(cudaMallocHost((void**)&ctx->up_pin[i], chunk_bytes));
+      ctx->up_pin_bytes = chunk_bytes;
+    }
+    CK(cudaStreamSynchronize(ctx->copy_stream));   // an earlier upload may still be reading the pinned ring
+    if (!ctx->copier) ctx->copier.reset(new HostCopier(std::min(8, std::max(1, (int)std::thread::hardware_concurrency() / 2 / std::max(1, W)))));
+  }
+  const unsigned char* host = static_cast<const unsigned char*>(aos);
+  // the copy stream must not run ahead of work still reading the staging buffer
+  CK(cudaEventRecord(ctx->up_land[7], s));
+  CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->up_land[7], 0));
+  int ring = 0, land = 0;
+  for (size_t j = 0; j < rounds; j++) {
+    const size_t g = j * W + (sharded ? ctx->rank : 0);       // the chunk this rank fetches in round j
+    const size_t lo = std::min(n, g * chunk_rec), hi = std::min(n, (g + 1) * chunk_rec);
+    if (hi > lo) {
+      const size_t bytes = (hi - lo) * stride;
+      const unsigned char* src = host + lo * stride;
+      if (!pinned) {
+        const int b = ring % lsqr_ctx::kRing;
+        if (ring >= lsqr_ctx::kRing) CK(cudaEventSynchronize(ctx->up_ev[b]));   // the copy that used this buffer has finished
+        ring++;
+        ctx->copier->copy(ctx->up_pin[b], src, bytes);
+        CK(cudaMemcpyAsync(ctx->staging + g * chunk_bytes, ctx->up_pin[b], bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->up_ev[b], ctx->copy_stream));
+      } else {
+        CK(cudaMemcpyAsync(ctx->staging + g * chunk_bytes, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+      }
+    }
+    cudaEvent_t landed = ctx->up_land[land++ % 7];
+    CK(cudaEventRecord(landed, ctx->copy_stream));
+    CK(cudaStreamWaitEvent(s, landed, 0));
+    if (sharded) CKN(nccl().AllGather(ctx->staging + g * chunk_bytes, ctx->staging + j * W * chunk_bytes, chunk_bytes, ncclUint8, ctx->comm, s));
+    if (j == 0) { launch_center_sample(ctx->model, ctx->staging, stride, sample, ds.center_dev, s); ctx->launches++; }
+    const size_t r_lo = std::min(n, j * W * chunk_rec), r_hi = std::min(n, (j + 1) * W * chunk_rec);
+    const bool last = j + 1 == rounds;
+    launch_ingest(mi.D, ctx->staging, stride, (uint32_t)r_lo, (uint32_t)(r_hi - r_lo), last ? pad_to : (uint32_t)r_hi, ds.center_dev, ds.soa64, ds.soa32, ds.ld, s);
+    ctx->launches++;
+  }
+  CKL();
+  return LSQR_OK;
 }
 
 // Number of subsets as the reference counts them (RANSAC::choose, RANSAC.hxx:254-280): the binomial
@@ -211,6 +448,7 @@ uint64_t choose_exact(uint64_t n, uint64_t k) {
 
 constexpr size_t kHypBatch = (size_t)1 << 22;
 
+// Minimal solve + consensus + arg-max of one request; the winner is re-derived on the device and fetched with one copy.
 int score_impl(lsqr_ctx* ctx, const lsqr_score_args* a, lsqr_score_result* res) {
   DataSet& ds = ctx->main;
   if (!ds.soa64) return fail(ctx, LSQR_ERR_STATE, "no data uploaded");
@@ -230,6 +468,9 @@ int score_impl(lsqr_ctx* ctx, const lsqr_score_args* a, lsqr_score_result* res) 
   CK(cudaMemsetAsync(ctx->key_dev, 0, 2 * sizeof(unsigned long long), s));
   CK(cudaEventRecord(ctx->ev[0], s));
   float cons_ms = 0.f;
+  const bool listed = a->sampler == LSQR_SAMPLE_LIST || a->sampler == LSQR_SAMPLE_PARAMS;
+  const bool one_batch = hi - lo <= kHypBatch;
+  bool timed = false;
   if (can_sample) {
     for (uint64_t b0 = lo; b0 < hi; b0 += kHypBatch) {
       const uint32_t B = (uint32_t)std::min<uint64_t>(kHypBatch, hi - b0);
@@ -252,6 +493,7 @@ int score_impl(lsqr_ctx* ctx, const lsqr_score_args* a, lsqr_score_result* res) 
       CK(cudaEventRecord(ctx->ev[2], s));
       ctx->launches += launch_consensus(ctx->model, a->precision, dv, ctx->hyp64, ctx->hyp32, ctx->hcap, B, ctx->cfg, ctx->counts, ctx->num_sms, s);
       CK(cudaEventRecord(ctx->ev[3], s));
+      timed = true;
       launch_argmax(ctx->counts, B, (uint32_t)b0, ctx->key_dev, s); ctx->launches++;
       CKL();
       if (a->out_counts) CK(cudaMemcpyAsync(a->out_counts + b0, ctx->counts, sizeof(uint32_t) * B, cudaMemcpyDeviceToHost, s));
@@ -262,31 +504,50 @@ int score_impl(lsqr_ctx* ctx, const lsqr_score_args* a, lsqr_score_result* res) 
         CK(cudaStreamSynchronize(s));
         for (uint32_t h = 0; h < B; h++) for (int j = 0; j < mi.P; j++) a->out_params[(b0 + h) * mi.P + j] = tmp[(size_t)j * B + h];
       }
-      CK(cudaEventSynchronize(ctx->ev[3]));
-      float ms = 0.f;
-      CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
-      cons_ms += ms;
+      if (!one_batch) {   // the event pair is reused by the next batch
+        CK(cudaEventSynchronize(ctx->ev[3]));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+        cons_ms += ms;
+      }
     }
   }
-  if (ctx->world > 1) {
-    if (!ctx->max_fn) return fail(ctx, LSQR_ERR_COMM, "sharded context without an all-reduce hook");
-    if (ctx->max_fn(ctx->comm_user, reinterpret_cast<uint64_t*>(ctx->key_dev), (void*)s)) return fail(ctx, LSQR_ERR_COMM, "max all-reduce hook failed");
+  if (int rc = comm_max_u64(ctx, ctx->key_dev)) return rc;
+  // the winner, on the device: index-based samplers always; listed ones when the request's list is still resident (one batch
+  // and the whole request on this rank, i.e. unsharded)
+  const bool dev_winner = !listed || (one_batch && ctx->world == 1 && can_sample && hi > lo);
+  if (dev_winner) {
+    SolveArgs wa{};
+    wa.model = ctx->model; wa.sampler = a->sampler; wa.seed = a->seed; wa.first = a->first;
+    wa.list = ctx->list_dev; wa.params_in = ctx->params_in_dev;
+    launch_winner(wa, ctx->key_dev, dv, ctx->cfg, ctx->winner_dev, s); ctx->launches++;
+    CK(cudaEventRecord(ctx->ev[1], s));
+    CKL();
+    CK(cudaMemcpyAsync(ctx->winner_pin, ctx->winner_dev, sizeof(WinnerRecord), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  } else {
+    CK(cudaEventRecord(ctx->ev[1], s));
+    CK(cudaMemcpyAsync(ctx->winner_pin, ctx->key_dev, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->winner_pin->n_valid &= 0xFFFFFFFFull;
   }
-  CK(cudaEventRecord(ctx->ev[1], s));
-  unsigned long long hk[2] = {0, 0};
-  CK(cudaMemcpyAsync(hk, ctx->key_dev, sizeof(hk), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
   float total_ms = 0.f;
   CK(cudaEventElapsedTime(&total_ms, ctx->ev[0], ctx->ev[1]));
+  if (one_batch && timed) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); cons_ms = ms; }
+  const WinnerRecord& w = *ctx->winner_pin;
   res->score_ms = total_ms; res->consensus_ms = cons_ms;
-  res->n_valid = (uint32_t)(hk[1] & 0xFFFFFFFFull);
-  res->best_count = (uint32_t)(hk[0] >> 32);
+  res->n_valid = (uint32_t)w.n_valid;
+  res->best_count = (uint32_t)(w.key >> 32);
   for (int j = 0; j < LSQR_MAX_SUBSET; j++) res->best_subset[j] = -1;
   if (res->best_count == 0) { res->best_index = 0; return LSQR_OK; }
-  const uint64_t rel = 0xFFFFFFFFull - (hk[0] & 0xFFFFFFFFull);
+  const uint64_t rel = 0xFFFFFFFFull - (w.key & 0xFFFFFFFFull);
   res->best_index = a->first + rel;
-  // Re-derive the winner's subset and parameters (same kernel, one hypothesis) so that every rank
-  // holds them regardless of which shard produced the winner.
+  if (dev_winner) {
+    for (int j = 0; j < mi.P; j++) res->best_params[j] = w.params[j];
+    for (int j = 0; j < mi.K; j++) res->best_subset[j] = w.subset[j];
+    return LSQR_OK;
+  }
+  // listed sampler whose winner's row is no longer on this device: upload that one row and solve it
   if (int rc = ensure_hyp(ctx, 1)) return rc;
   SolveArgs sa{};
   sa.model = ctx->model; sa.sampler = a->sampler; sa.seed = a->seed; sa.first = res->best_index; sa.H = 1; sa.hld = ctx->hcap;
@@ -295,7 +556,7 @@ int score_impl(lsqr_ctx* ctx, const lsqr_score_args* a, lsqr_score_result* res) 
     if (int rc = ensure(ctx, &ctx->list_dev, &ctx->list_cap, (size_t)mi.K)) return rc;
     CK(cudaMemcpyAsync(ctx->list_dev, a->subsets + rel * mi.K, sizeof(int32_t) * mi.K, cudaMemcpyHostToDevice, s));
     sa.list = ctx->list_dev;
-  } else if (a->sampler == LSQR_SAMPLE_PARAMS) {
+  } else {
     if (int rc = ensure(ctx, &ctx->params_in_dev, &ctx->params_in_cap, (size_t)mi.P)) return rc;
     CK(cudaMemcpyAsync(ctx->params_in_dev, a->params + rel * mi.P, sizeof(double) * mi.P, cudaMemcpyHostToDevice, s));
     sa.params_in = ctx->params_in_dev;
@@ -313,11 +574,7 @@ int score_impl(lsqr_ctx* ctx, const lsqr_score_args* a, lsqr_score_result* res) 
 
 int reduce_moments(lsqr_ctx* ctx, int nm) {
   launch_reduce_partials(ctx->rb, nm, ctx->stream); ctx->launches++;
-  if (ctx->world > 1) {
-    if (!ctx->sum_fn) return fail(ctx, LSQR_ERR_COMM, "sharded context without a sum all-reduce hook");
-    if (ctx->sum_fn(ctx->comm_user, ctx->rb.moments, nm, (void*)ctx->stream)) return fail(ctx, LSQR_ERR_COMM, "sum all-reduce hook failed");
-  }
-  return 0;
+  return comm_sum_f64(ctx, ctx->rb.moments, nm);
 }
 
 void shard_range(const lsqr_ctx* ctx, uint32_t n, uint32_t* begin, uint32_t* end) {
@@ -328,6 +585,28 @@ void shard_range(const lsqr_ctx* ctx, uint32_t n, uint32_t* begin, uint32_t* end
   *end = (uint32_t)std::min<uint64_t>(w1 * 32, n);
 }
 
+// Consensus set of the parameters at params_dev (device) over this rank's point shard + the least-squares moments of it,
+// enqueued only: no copy back, no synchronisation.  want_bytes: the pass also writes one byte per datum into ctx->mask_dev.
+int consensus_enqueue(lsqr_ctx* ctx, DataSet& ds, const double* params_dev, bool want_bytes) {
+  const ModelInfo mi = model_info(ctx->model);
+  cudaStream_t s = ctx->stream;
+  uint32_t b, e;
+  shard_range(ctx, ds.n, &b, &e);
+  const int nm = moments_count(ctx->model, false);
+  if (want_bytes) if (int rc = ensure(ctx, &ctx->mask_dev, &ctx->mask_dev_cap, (size_t)std::max<uint32_t>(ds.n, 1))) return rc;
+  CK(cudaEventRecord(ctx->ev[4], s));
+  ctx->rb.maskbits = ds.maskbits;
+  ctx->rb.maskbytes = want_bytes ? ctx->mask_dev : nullptr;
+  launch_mask_moments(ctx->model, ds.view(), b, e, params_dev, 1, nullptr, ctx->cfg, ctx->rb, s); ctx->launches++;
+  ctx->rb.maskbytes = nullptr;
+  CK(cudaEventRecord(ctx->ev[5], s));
+  if (int rc = reduce_moments(ctx, nm)) return rc;
+  CKL();
+  ctx->refine_bytes = (double)(e - b) * mi.D * sizeof(double) + (double)(e - b) / 8.0 + (want_bytes ? (double)(e - b) : 0.0);
+  ds.moments_valid = true; ds.mask_valid = true; ds.bytes_valid = want_bytes;
+  return LSQR_OK;
+}
+
 int consensus_impl(lsqr_ctx* ctx, DataSet& ds, const double* params, uint32_t* out_count) {
   if (!ds.soa64) return fail(ctx, LSQR_ERR_STATE, "no data uploaded");
   const ModelInfo mi = model_info(ctx->model);
@@ -335,34 +614,23 @@ int consensus_impl(lsqr_ctx* ctx, DataSet& ds, const double* params, uint32_t* o
   CK(cudaSetDevice(ctx->device));
   for (int j = 0; j < mi.P; j++) ctx->pin[32 + j] = params[j];
   CK(cudaMemcpyAsync(ctx->small_dev + kSmIn, ctx->pin + 32, sizeof(double) * mi.P, cudaMemcpyHostToDevice, s));
-  uint32_t b, e;
-  shard_range(ctx, ds.n, &b, &e);
-  const int nm = moments_count(ctx->model, false);
-  CK(cudaEventRecord(ctx->ev[4], s));
-  ctx->rb.maskbits = ds.maskbits;
-  launch_mask_moments(ctx->model, ds.view(), b, e, ctx->small_dev + kSmIn, 1, nullptr, ctx->cfg, ctx->rb, s); ctx->launches++;
-  CK(cudaEventRecord(ctx->ev[5], s));
-  if (int rc = reduce_moments(ctx, nm)) return rc;
-  CKL();
+  if (int rc = consensus_enqueue(ctx, ds, ctx->small_dev + kSmIn, false)) return rc;
   CK(cudaMemcpyAsync(ctx->pin, ctx->rb.moments, sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
   ctx->refine_kernel_ms = ms;
-  ctx->refine_bytes = (double)(e - b) * mi.D * sizeof(double) + (double)(e - b) / 8.0;
-  ds.moments_valid = true; ds.mask_valid = true;
   if (out_count) *out_count = (uint32_t)(ctx->pin[0] + 0.5);
   return LSQR_OK;
 }
 
-int refine_impl(lsqr_ctx* ctx, DataSet& ds, int use_mask, double* out_params, int* n_params) {
-  if (!ds.soa64) return fail(ctx, LSQR_ERR_STATE, "no data uploaded");
-  if (use_mask && !ds.mask_valid) return fail(ctx, LSQR_ERR_STATE, "no consensus set stored; call lsqr_consensus first");
-  const ModelInfo mi = model_info(ctx->model);
+// Least squares over the stored consensus set (or all data), enqueued; the result lands in small_dev + kSmOut
+// ([0] = number of parameters, [1..] parameters).  Levenberg-Marquardt refits synchronise once per chunk of evaluations.
+int refine_enqueue(lsqr_ctx* ctx, DataSet& ds, int use_mask) {
   cudaStream_t s = ctx->stream;
-  CK(cudaSetDevice(ctx->device));
   const DataView dv = ds.view();
   ctx->rb.maskbits = ds.maskbits;
+  ctx->rb.maskbytes = nullptr;
   uint32_t b, e;
   shard_range(ctx, ds.n, &b, &e);
   const int nm = moments_count(ctx->model, false);
@@ -375,7 +643,7 @@ int refine_impl(lsqr_ctx* ctx, DataSet& ds, int use_mask, double* out_params, in
     ds.moments_valid = false;
   }
   double* out_dev = ctx->small_dev + kSmOut;
-  // iterative refinement: geometric circle / sphere fit, iterative cross-wire calibration (ls_type 1 in both)
+  // iterative refinement: geometric circle / sphere fit, iterative ultrasound calibrations (ls_type 1 in both)
   const bool geometric = (ctx->model == CIRCLE2 || ctx->model == SPHERE3 || ctx->model == SPHERE4 || ctx->model == USXW || ctx->model == USCP) && ctx->ls_type == LSQR_LS_GEOMETRIC;
   launch_solve_moments(ctx->model, dv, ctx->rb.moments, geometric ? 1 : 0, out_dev, s); ctx->launches++;
   if (geometric) {
@@ -393,15 +661,25 @@ int refine_impl(lsqr_ctx* ctx, DataSet& ds, int use_mask, double* out_params, in
         if (int rc = reduce_moments(ctx, nlm)) return rc;
         launch_lm_update(ctx->model, ctx->rb.moments, st, s); ctx->launches++;
       }
-      CK(cudaMemcpyAsync(ctx->pin, st + lm_status_offset(), 3 * sizeof(double), cudaMemcpyDeviceToHost, s));   // status, phase, evaluations
+      CK(cudaMemcpyAsync(ctx->pin + 48, st + lm_status_offset(), 3 * sizeof(double), cudaMemcpyDeviceToHost, s));   // status, phase, evaluations
       CK(cudaStreamSynchronize(s));
-      ctx->lm_iterations = (int)ctx->pin[2];
-      if (ctx->pin[0] != 0.0) break;
+      ctx->lm_iterations = (int)ctx->pin[50];
+      if (ctx->pin[48] != 0.0) break;
     }
     launch_lm_finish(ctx->model, dv, st, out_dev, s); ctx->launches++;
   }
   CKL();
-  CK(cudaMemcpyAsync(ctx->pin, out_dev, sizeof(double) * (1 + LSQR_MAX_PARAMS), cudaMemcpyDeviceToHost, s));
+  return LSQR_OK;
+}
+
+int refine_impl(lsqr_ctx* ctx, DataSet& ds, int use_mask, double* out_params, int* n_params) {
+  if (!ds.soa64) return fail(ctx, LSQR_ERR_STATE, "no data uploaded");
+  if (use_mask && !ds.mask_valid) return fail(ctx, LSQR_ERR_STATE, "no consensus set stored; call lsqr_consensus first");
+  const ModelInfo mi = model_info(ctx->model);
+  cudaStream_t s = ctx->stream;
+  CK(cudaSetDevice(ctx->device));
+  if (int rc = refine_enqueue(ctx, ds, use_mask)) return rc;
+  CK(cudaMemcpyAsync(ctx->pin, ctx->small_dev + kSmOut, sizeof(double) * (1 + LSQR_MAX_PARAMS), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   const int np = (int)ctx->pin[0];
   if (n_params) *n_params = np;
@@ -409,176 +687,71 @@ int refine_impl(lsqr_ctx* ctx, DataSet& ds, int use_mask, double* out_params, in
   return LSQR_OK;
 }
 
-int get_mask_impl(lsqr_ctx* ctx, DataSet& ds, uint8_t* out_bytes) {
-  if (!ds.mask_valid) return fail(ctx, LSQR_ERR_STATE, "no consensus set stored");
-  if (!out_bytes || ds.n == 0) return LSQR_OK;
-  // persistent device + pinned buffers: a cudaMalloc/cudaFree pair per call costs up to 0.3 s after the
-  // thousands of launches of a large request, and a pageable destination is staged by the driver
-  if (int rc = ensure(ctx, &ctx->mask_dev, &ctx->mask_dev_cap, (size_t)ds.n)) return rc;
-  if (ctx->mask_pin_cap < ds.n) {
+// Enqueues the copy of this rank's part of the consensus set (bytes [b, e) of out_bytes; everything when unsharded) and
+// reports whether a bounce through the pinned buffer has to be finished after the synchronisation.
+int mask_download_enqueue(lsqr_ctx* ctx, DataSet& ds, uint8_t* out_bytes, bool* bounce, uint32_t* pb, uint32_t* pe) {
+  uint32_t b, e;
+  shard_range(ctx, ds.n, &b, &e);
+  *pb = b; *pe = e; *bounce = false;
+  if (!out_bytes || e <= b) return LSQR_OK;
+  if (int rc = ensure(ctx, &ctx->mask_dev, &ctx->mask_dev_cap, (size_t)std::max<uint32_t>(ds.n, 1))) return rc;
+  if (!ds.bytes_valid) { launch_expand_mask(ds.maskbits, b, e - b, ctx->mask_dev, ctx->stream); ctx->launches++; ds.bytes_valid = true; }
+  // a caller buffer that is itself page-locked takes the DMA directly; any other goes through the library's pinned buffer
+  // (persistent: a cudaMalloc/cudaFree pair per call costs up to 0.3 s after the thousands of launches of a large request)
+  const bool direct = is_pinned(out_bytes);
+  if (!direct && ctx->mask_pin_cap < ds.n) {
     if (ctx->mask_pin) cudaFreeHost(ctx->mask_pin);
     ctx->mask_pin = nullptr; ctx->mask_pin_cap = 0;
     CK(cudaMallocHost((void**)&ctx->mask_pin, ds.n));
     ctx->mask_pin_cap = ds.n;
   }
-  launch_expand_mask(ds.maskbits, ds.n, ctx->mask_dev, ctx->stream); ctx->launches++;
-  // a caller buffer that is itself page-locked takes the DMA directly
-  cudaPointerAttributes attr{};
-  const bool direct = cudaPointerGetAttributes(&attr, out_bytes) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-  if (!direct) cudaGetLastError();   // an unregistered pointer is not an error here
-  cudaError_t e1 = cudaMemcpyAsync(direct ? out_bytes : ctx->mask_pin, ctx->mask_dev, ds.n, cudaMemcpyDeviceToHost, ctx->stream);
-  cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-  if (!direct && e1 == cudaSuccess && e2 == cudaSuccess) memcpy(out_bytes, ctx->mask_pin, ds.n);
-  if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(ctx, LSQR_ERR_CUDA, "mask download failed");
+  CK(cudaMemcpyAsync((direct ? out_bytes : ctx->mask_pin) + b, ctx->mask_dev + b, e - b, cudaMemcpyDeviceToHost, ctx->stream));
+  *bounce = !direct;
   return LSQR_OK;
 }
 
-// winner -> consensus set -> least squares: RANSAC.hxx:129-138 / :175-185
+int get_mask_impl(lsqr_ctx* ctx, DataSet& ds, uint8_t* out_bytes) {
+  if (!ds.mask_valid) return fail(ctx, LSQR_ERR_STATE, "no consensus set stored");
+  if (!out_bytes || ds.n == 0) return LSQR_OK;
+  CK(cudaSetDevice(ctx->device));
+  bool bounce; uint32_t b, e;
+  if (int rc = mask_download_enqueue(ctx, ds, out_bytes, &bounce, &b, &e)) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (bounce) memcpy(out_bytes + b, ctx->mask_pin + b, e - b);
+  return LSQR_OK;
+}
+
+// winner -> consensus set -> least squares: RANSAC.hxx:129-138 / :175-185.  Everything is enqueued behind the scoring; one
+// synchronisation brings back count, parameters and the mask.
 int finish_ransac(lsqr_ctx* ctx, const lsqr_score_result& best, uint8_t* out_mask, lsqr_compute_result* res) {
   res->best_count = best.best_count; res->best_index = best.best_index;
   if (best.best_count == 0) { res->n_params = 0; res->fraction = 0.0; return LSQR_OK; }
-  uint32_t cnt = 0;
-  if (int rc = consensus_impl(ctx, ctx->main, best.best_params, &cnt)) return rc;
+  const ModelInfo mi = model_info(ctx->model);
+  cudaStream_t s = ctx->stream;
+  DataSet& ds = ctx->main;
+  for (int j = 0; j < mi.P; j++) ctx->pin[32 + j] = best.best_params[j];
+  CK(cudaMemcpyAsync(ctx->small_dev + kSmIn, ctx->pin + 32, sizeof(double) * mi.P, cudaMemcpyHostToDevice, s));
+  if (int rc = consensus_enqueue(ctx, ds, ctx->small_dev + kSmIn, out_mask != nullptr)) return rc;
+  CK(cudaMemcpyAsync(ctx->pin, ctx->rb.moments, sizeof(double), cudaMemcpyDeviceToHost, s));
+  bool bounce = false; uint32_t b = 0, e = 0;
+  if (out_mask) if (int rc = mask_download_enqueue(ctx, ds, out_mask, &bounce, &b, &e)) return rc;
+  if (int rc = refine_enqueue(ctx, ds, 1)) return rc;
+  CK(cudaMemcpyAsync(ctx->pin + 1, ctx->small_dev + kSmOut, sizeof(double) * (1 + LSQR_MAX_PARAMS), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (bounce) memcpy(out_mask + b, ctx->mask_pin + b, e - b);
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
+  ctx->refine_kernel_ms = ms;
+  const uint32_t cnt = (uint32_t)(ctx->pin[0] + 0.5);
+  const int np = (int)ctx->pin[1];
   res->best_count = cnt;
-  if (out_mask) if (int rc = get_mask_impl(ctx, ctx->main, out_mask)) return rc;
-  int np = 0;
-  if (int rc = refine_impl(ctx, ctx->main, 1, res->params, &np)) return rc;
   res->n_params = np;
-  res->fraction = (double)cnt / (double)ctx->main.n;
+  for (int j = 0; j < np && j < mi.P; j++) res->params[j] = ctx->pin[2 + j];
+  res->fraction = (double)cnt / (double)ds.n;
   return LSQR_OK;
 }
 
-}  // namespace
-
-extern "C" {
-
-int lsqr_model_info(int model, int* dim, int* nparams, int* k) {
-  if (model < 0 || model >= LSQR_NUM_MODELS) return LSQR_ERR_ARG;
-  const ModelInfo mi = model_info(model);
-  if (dim) *dim = mi.D;
-  if (nparams) *nparams = mi.P;
-  if (k) *k = mi.K;
-  return LSQR_OK;
-}
-
-int lsqr_ctx_create(lsqr_ctx** out, int device) {
-  if (!out) return LSQR_ERR_ARG;
-  *out = nullptr;
-  int count = 0;
-  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) return LSQR_ERR_CUDA;
-  lsqr_ctx* ctx = new lsqr_ctx();
-  ctx->device = device;
-  auto bail = [&](int code) { lsqr_ctx_destroy(ctx); return code; };
-  if (cudaSetDevice(device) != cudaSuccess) return bail(LSQR_ERR_CUDA);
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(LSQR_ERR_CUDA);
-  if (prop.major < 10) { fprintf(stderr, "lsqr_b200: device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major, prop.minor); return bail(LSQR_ERR_CUDA); }
-  ctx->num_sms = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(LSQR_ERR_CUDA);
-  ctx->own_stream = true;
-  ctx->rb.blocks = ctx->num_sms * mask_moments_ctas_per_sm();   // one wave of resident CTAs
-  bool ok = cudaMalloc((void**)&ctx->key_dev, 4 * sizeof(unsigned long long)) == cudaSuccess &&
-            cudaMalloc((void**)&ctx->small_dev, kSmall * sizeof(double)) == cudaSuccess &&
-            cudaMalloc((void**)&ctx->center_dev, kMaxDim * sizeof(double)) == cudaSuccess &&
-            cudaMalloc((void**)&ctx->center_partials, 256 * kMaxDim * sizeof(double)) == cudaSuccess &&
-            cudaMalloc((void**)&ctx->rb.partials, sizeof(double) * kMaxMoments * ctx->rb.blocks) == cudaSuccess &&
-            cudaMalloc((void**)&ctx->rb.moments, sizeof(double) * kMaxMoments) == cudaSuccess &&
-            cudaMallocHost((void**)&ctx->pin, 64 * sizeof(double)) == cudaSuccess;
-  for (int i = 0; ok && i < 6; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
-  if (!ok) return bail(LSQR_ERR_CUDA);
-  *out = ctx;
-  return LSQR_OK;
-}
-
-void lsqr_ctx_destroy(lsqr_ctx* ctx) {
-  if (!ctx) return;
-  cudaSetDevice(ctx->device);
-  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  for (DataSet* ds : {&ctx->main, &ctx->scratch}) { cudaFree(ds->soa64); cudaFree(ds->soa32); cudaFree(ds->maskbits); }
-  cudaFree(ctx->bt_data); cudaFree(ctx->bt_off); cudaFree(ctx->bt_prm); cudaFree(ctx->bt_cnt);
-  cudaFree(ctx->weights_dev); cudaFree(ctx->mask_dev); if (ctx->mask_pin) cudaFreeHost(ctx->mask_pin);
-  cudaFree(ctx->staging); cudaFree(ctx->subsets); cudaFree(ctx->hyp64); cudaFree(ctx->hyp32); cudaFree(ctx->counts);
-  cudaFree(ctx->list_dev); cudaFree(ctx->params_in_dev); cudaFree(ctx->key_dev); cudaFree(ctx->small_dev);
-  cudaFree(ctx->center_dev); cudaFree(ctx->center_partials); cudaFree(ctx->rb.partials); cudaFree(ctx->rb.moments);
-  if (ctx->pin) cudaFreeHost(ctx->pin);
-  for (int i = 0; i < 6; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
-  delete ctx;
-}
-
-const char* lsqr_last_error(const lsqr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-
-int lsqr_ctx_set_stream(lsqr_ctx* ctx, void* cuda_stream) {
-  if (!ctx) return LSQR_ERR_ARG;
-  if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
-  ctx->stream = (cudaStream_t)cuda_stream;
-  ctx->own_stream = false;
-  return LSQR_OK;
-}
-
-uint64_t lsqr_kernel_launches(const lsqr_ctx* ctx) { return ctx ? ctx->launches : 0; }
-
-int lsqr_set_estimator(lsqr_ctx* ctx, int model, double delta, double aux, int ls_type) {
-  if (!ctx) return LSQR_ERR_ARG;
-  if (model < 0 || model >= LSQR_NUM_MODELS) return fail(ctx, LSQR_ERR_ARG, "unknown model");
-  if (ls_type != LSQR_LS_ALGEBRAIC && ls_type != LSQR_LS_GEOMETRIC) return fail(ctx, LSQR_ERR_ARG, "bad least-squares type");  // SphereParametersEstimator.hxx:17-18
-  if (ctx->model != model) {  // layouts differ between models: the data must be uploaded again
-    for (DataSet* ds : {&ctx->main, &ctx->scratch}) { cudaFree(ds->soa64); cudaFree(ds->soa32); cudaFree(ds->maskbits); *ds = DataSet(); }
-  }
-  ctx->model = model; ctx->delta = delta; ctx->aux = aux; ctx->ls_type = ls_type;
-  // The reference keeps delta*delta for every estimator but the hypersphere, pivot and dense-system ones (e.g.
-  // PlaneParametersEstimator.hxx:16 vs SphereParametersEstimator.hxx:20), so the sign of delta is immaterial there; the device
-  // code that compares an unsquared residual (fp32 fast mode) gets |delta|.
-  const bool distance_threshold = model == LSQR_CIRCLE2 || model == LSQR_SPHERE3 || model == LSQR_SPHERE4 || model == LSQR_PIVOT ||
-                                  model == LSQR_DENSE5 || model == LSQR_DENSE6;
-  ctx->cfg.delta = distance_threshold ? delta : fabs(delta);
-  ctx->cfg.delta2 = delta * delta;
-  const double ang = aux > 0 ? aux : 0.017453292519943295769236907684886;  // RayIntersectionParametersEstimator.h:35
-  double ce = sin(ang);
-  ce *= ce;
-  ctx->cfg.cross_eps = ce;
-  ctx->main.moments_valid = false;
-  return LSQR_OK;
-}
-
-int lsqr_upload(lsqr_ctx* ctx, const void* aos, size_t n, size_t stride_bytes) {
-  if (!ctx) return LSQR_ERR_ARG;
-  return upload_to(ctx, ctx->main, aos, n, stride_bytes, false);
-}
-int lsqr_upload_device(lsqr_ctx* ctx, const double* dev_packed, size_t n) {
-  if (!ctx) return LSQR_ERR_ARG;
-  if (ctx->model < 0) return fail(ctx, LSQR_ERR_STATE, "lsqr_set_estimator must be called first");
-  return upload_to(ctx, ctx->main, dev_packed, n, sizeof(double) * model_info(ctx->model).D, true);
-}
-
-int lsqr_set_shard(lsqr_ctx* ctx, int rank, int world, lsqr_allreduce_max_u64_fn max_fn, lsqr_allreduce_sum_f64_fn sum_fn, void* user) {
-  if (!ctx) return LSQR_ERR_ARG;
-  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, LSQR_ERR_ARG, "bad rank/world");
-  if (world > 1 && (!max_fn || !sum_fn)) return fail(ctx, LSQR_ERR_ARG, "hooks required when world > 1");
-  ctx->rank = rank; ctx->world = world; ctx->max_fn = max_fn; ctx->sum_fn = sum_fn; ctx->comm_user = user;
-  return LSQR_OK;
-}
-
-int lsqr_score(lsqr_ctx* ctx, const lsqr_score_args* args, lsqr_score_result* res) {
-  if (!ctx) return LSQR_ERR_ARG;
-  return score_impl(ctx, args, res);
-}
-
-int lsqr_consensus(lsqr_ctx* ctx, const double* params, uint32_t* out_count) {
-  if (!ctx || !params) return LSQR_ERR_ARG;
-  return consensus_impl(ctx, ctx->main, params, out_count);
-}
-int lsqr_get_mask(lsqr_ctx* ctx, uint8_t* out_bytes) {
-  if (!ctx) return LSQR_ERR_ARG;
-  return get_mask_impl(ctx, ctx->main, out_bytes);
-}
-int lsqr_refine(lsqr_ctx* ctx, int use_mask, double* out_params, int* n_params) {
-  if (!ctx) return LSQR_ERR_ARG;
-  return refine_impl(ctx, ctx->main, use_mask, out_params, n_params);
-}
-
-int lsqr_ransac(lsqr_ctx* ctx, double prob, int precision, uint64_t seed, uint8_t* out_mask, lsqr_compute_result* res) {
-  if (!ctx || !res) return LSQR_ERR_ARG;
+int ransac_impl(lsqr_ctx* ctx, double prob, int precision, uint64_t seed, uint8_t* out_mask, lsqr_compute_result* res) {
   if (ctx->model < 0 || !ctx->main.soa64) return fail(ctx, LSQR_ERR_STATE, "set the estimator and upload data first");
   memset(res, 0, sizeof(*res));
   const ModelInfo mi = model_info(ctx->model);
@@ -616,8 +789,7 @@ int lsqr_ransac(lsqr_ctx* ctx, double prob, int precision, uint64_t seed, uint8_
   return rc;
 }
 
-int lsqr_ransac_exhaustive(lsqr_ctx* ctx, int precision, uint8_t* out_mask, lsqr_compute_result* res) {
-  if (!ctx || !res) return LSQR_ERR_ARG;
+int ransac_exhaustive_impl(lsqr_ctx* ctx, int precision, uint8_t* out_mask, lsqr_compute_result* res) {
   if (ctx->model < 0 || !ctx->main.soa64) return fail(ctx, LSQR_ERR_STATE, "set the estimator and upload data first");
   memset(res, 0, sizeof(*res));
   const ModelInfo mi = model_info(ctx->model);
@@ -635,17 +807,19 @@ int lsqr_ransac_exhaustive(lsqr_ctx* ctx, int precision, uint8_t* out_mask, lsqr
   return rc;
 }
 
-int lsqr_ransac_batch(lsqr_ctx* ctx, const double* data, const uint64_t* offsets, uint64_t n_problems, int exhaustive, double prob,
-                      uint32_t max_tries, uint64_t seed, double* out_params, uint32_t* out_counts, uint8_t* out_masks, double* device_ms) {
-  if (!ctx || !data || !offsets || !out_params || !out_counts) return LSQR_ERR_ARG;
+// problems [p0, p1) of a batch (offsets are absolute record offsets into `data`)
+int batch_impl(lsqr_ctx* ctx, const double* data, const uint64_t* offsets, uint64_t p0, uint64_t p1, int exhaustive, double prob, uint32_t max_tries,
+               uint64_t seed, double* out_params, uint32_t* out_counts, uint8_t* out_masks, double* device_ms) {
   if (ctx->model < 0) return fail(ctx, LSQR_ERR_STATE, "lsqr_set_estimator must be called first");
-  if (n_problems == 0) return LSQR_OK;
-  if (n_problems > 0x7FFFFFFFull) return fail(ctx, LSQR_ERR_ARG, "too many problems");
+  if (device_ms) *device_ms = 0.0;
+  if (p1 <= p0) return LSQR_OK;
+  const uint64_t np = p1 - p0;
+  if (np > 0x7FFFFFFFull) return fail(ctx, LSQR_ERR_ARG, "too many problems");
   const ModelInfo mi = model_info(ctx->model);
   CK(cudaSetDevice(ctx->device));
-  const uint64_t total = offsets[n_problems];
+  const uint64_t base = offsets[p0], total = offsets[p1] - base;
   uint32_t max_n = 1;
-  for (uint64_t b = 0; b < n_problems; b++) {
+  for (uint64_t b = p0; b < p1; b++) {
     if (offsets[b + 1] < offsets[b]) return fail(ctx, LSQR_ERR_ARG, "offsets must be non-decreasing");
     max_n = std::max<uint64_t>(max_n, offsets[b + 1] - offsets[b]);
   }
@@ -653,39 +827,350 @@ int lsqr_ransac_batch(lsqr_ctx* ctx, const double* data, const uint64_t* offsets
   cudaStream_t s = ctx->stream;
   // persistent buffers (a cudaMalloc/cudaFree set per call cost more than the kernel)
   if (int rc = ensure(ctx, &ctx->bt_data, &ctx->bt_data_cap, (size_t)std::max<uint64_t>(total, 1) * mi.D)) return rc;
-  if (int rc = ensure(ctx, &ctx->bt_off, &ctx->bt_off_cap, (size_t)n_problems + 1)) return rc;
-  if (int rc = ensure(ctx, &ctx->bt_prm, &ctx->bt_prm_cap, (size_t)n_problems * mi.P)) return rc;
-  if (int rc = ensure(ctx, &ctx->bt_cnt, &ctx->bt_cnt_cap, (size_t)n_problems)) return rc;
+  if (int rc = ensure(ctx, &ctx->bt_off, &ctx->bt_off_cap, (size_t)np + 1)) return rc;
+  if (int rc = ensure(ctx, &ctx->bt_prm, &ctx->bt_prm_cap, (size_t)np * mi.P)) return rc;
+  if (int rc = ensure(ctx, &ctx->bt_cnt, &ctx->bt_cnt_cap, (size_t)np)) return rc;
   if (out_masks) if (int rc = ensure(ctx, &ctx->mask_dev, &ctx->mask_dev_cap, (size_t)std::max<uint64_t>(total, 1))) return rc;
-  double* d_data = ctx->bt_data; uint64_t* d_off = ctx->bt_off; double* d_prm = ctx->bt_prm; uint32_t* d_cnt = ctx->bt_cnt;
-  uint8_t* d_mask = out_masks ? ctx->mask_dev : nullptr;
-  auto cleanup = [&]() {};
-#define CKB(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail(ctx, LSQR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } } while (0)
-  CKB(cudaMemcpyAsync(d_data, data, sizeof(double) * total * mi.D, cudaMemcpyHostToDevice, s));
-  CKB(cudaMemcpyAsync(d_off, offsets, sizeof(uint64_t) * (n_problems + 1), cudaMemcpyHostToDevice, s));
+  ctx->main.bytes_valid = false;   // mask_dev is shared with the consensus-set bytes
+  CK(cudaMemcpyAsync(ctx->bt_data, data + base * mi.D, sizeof(double) * total * mi.D, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->bt_off, offsets + p0, sizeof(uint64_t) * (np + 1), cudaMemcpyHostToDevice, s));
   BatchArgs ba{};
   ba.model = ctx->model; ba.exhaustive = exhaustive; ba.tries = max_tries; ba.prob = prob; ba.seed = seed;
-  ba.data = d_data; ba.offsets = d_off; ba.n_problems = (uint32_t)n_problems; ba.max_n = max_n;
-  ba.out_params = d_prm; ba.out_counts = d_cnt; ba.out_masks = d_mask;
-  CKB(cudaEventRecord(ctx->ev[0], s));
-  if (launch_batch(ba, ctx->cfg, ctx->ls_type, s) < 0) { cleanup(); return fail(ctx, LSQR_ERR_ARG, "batch launch rejected"); }
+  ba.data = ctx->bt_data; ba.offsets = ctx->bt_off; ba.n_problems = (uint32_t)np; ba.max_n = max_n; ba.base = base; ba.first_problem = p0;
+  ba.out_params = ctx->bt_prm; ba.out_counts = ctx->bt_cnt; ba.out_masks = out_masks ? ctx->mask_dev : nullptr;
+  CK(cudaEventRecord(ctx->ev[0], s));
+  if (launch_batch(ba, ctx->cfg, ctx->ls_type, s) < 0) return fail(ctx, LSQR_ERR_ARG, "batch launch rejected");
   ctx->launches++;
-  CKB(cudaEventRecord(ctx->ev[1], s));
-  CKB(cudaGetLastError());
-  CKB(cudaMemcpyAsync(out_params, d_prm, sizeof(double) * n_problems * mi.P, cudaMemcpyDeviceToHost, s));
-  CKB(cudaMemcpyAsync(out_counts, d_cnt, sizeof(uint32_t) * n_problems, cudaMemcpyDeviceToHost, s));
-  if (out_masks) CKB(cudaMemcpyAsync(out_masks, d_mask, total, cudaMemcpyDeviceToHost, s));
-  CKB(cudaStreamSynchronize(s));
+  CK(cudaEventRecord(ctx->ev[1], s));
+  CKL();
+  CK(cudaMemcpyAsync(out_params + p0 * mi.P, ctx->bt_prm, sizeof(double) * np * mi.P, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(out_counts + p0, ctx->bt_cnt, sizeof(uint32_t) * np, cudaMemcpyDeviceToHost, s));
+  if (out_masks && total) CK(cudaMemcpyAsync(out_masks + base, ctx->mask_dev, total, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
   float ms = 0.f;
-  CKB(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+  CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
   if (device_ms) *device_ms = ms;
-  cleanup();
-#undef CKB
   return LSQR_OK;
+}
+
+int create_single(lsqr_ctx** out, int device) {
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) return LSQR_ERR_CUDA;
+  lsqr_ctx* ctx = new lsqr_ctx();
+  ctx->device = device;
+  auto bail = [&](int code) { lsqr_ctx_destroy(ctx); return code; };
+  if (cudaSetDevice(device) != cudaSuccess) return bail(LSQR_ERR_CUDA);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(LSQR_ERR_CUDA);
+  if (prop.major < 10) { fprintf(stderr, "lsqr_b200: device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major, prop.minor); return bail(LSQR_ERR_CUDA); }
+  ctx->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(LSQR_ERR_CUDA);
+  ctx->own_stream = true;
+  if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(LSQR_ERR_CUDA);
+  ctx->rb.blocks = ctx->num_sms * mask_moments_ctas_per_sm();   // one wave of resident CTAs
+  bool ok = cudaMalloc((void**)&ctx->key_dev, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMalloc((void**)&ctx->winner_dev, sizeof(WinnerRecord)) == cudaSuccess &&
+            cudaMalloc((void**)&ctx->small_dev, kSmall * sizeof(double)) == cudaSuccess &&
+            cudaMalloc((void**)&ctx->rb.partials, sizeof(double) * kMaxMoments * ctx->rb.blocks) == cudaSuccess &&
+            cudaMalloc((void**)&ctx->rb.moments, sizeof(double) * kMaxMoments) == cudaSuccess &&
+            cudaMallocHost((void**)&ctx->pin, 64 * sizeof(double) + sizeof(WinnerRecord)) == cudaSuccess;
+  if (ok) ctx->winner_pin = reinterpret_cast<WinnerRecord*>(ctx->pin + 64);
+  for (int i = 0; ok && i < 6; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+  for (int i = 0; ok && i < lsqr_ctx::kRing; i++) ok = cudaEventCreateWithFlags(&ctx->up_ev[i], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < 8; i++) ok = cudaEventCreateWithFlags(&ctx->up_land[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) return bail(LSQR_ERR_CUDA);
+  *out = ctx;
+  return LSQR_OK;
+}
+
+// runs fn on every member of a group concurrently (one worker thread per device)
+int group_run(lsqr_ctx* g, const std::function<int(lsqr_ctx*, int)>& fn) {
+  Group* grp = g->group;
+  const int rc = grp->workers->run([&](int r) { return fn(grp->kids[r], r); });
+  if (rc) for (lsqr_ctx* k : grp->kids) if (!k->err.empty()) { g->err = k->err; break; }
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lsqr_model_info(int model, int* dim, int* nparams, int* k) {
+  if (model < 0 || model >= LSQR_NUM_MODELS) return LSQR_ERR_ARG;
+  const ModelInfo mi = model_info(model);
+  if (dim) *dim = mi.D;
+  if (nparams) *nparams = mi.P;
+  if (k) *k = mi.K;
+  return LSQR_OK;
+}
+
+int lsqr_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return count;
+}
+
+int lsqr_ctx_create(lsqr_ctx** out, int device) {
+  if (!out) return LSQR_ERR_ARG;
+  return create_single(out, device);
+}
+
+int lsqr_ctx_create_multi(lsqr_ctx** out, int ngpus) {
+  if (!out) return LSQR_ERR_ARG;
+  *out = nullptr;
+  const int count = lsqr_device_count();
+  if (count == 0) return LSQR_ERR_CUDA;
+  if (ngpus <= 0) ngpus = count;
+  if (ngpus > count) return LSQR_ERR_ARG;
+  if (ngpus == 1) return create_single(out, 0);
+  if (!nccl().ok) return LSQR_ERR_COMM;
+  lsqr_ctx* g = new lsqr_ctx();
+  g->group = new Group();
+  g->world = ngpus;
+  auto bail = [&](int code) { lsqr_ctx_destroy(g); return code; };
+  std::vector<int> devs(ngpus);
+  for (int r = 0; r < ngpus; r++) {
+    devs[r] = r;
+    lsqr_ctx* k = nullptr;
+    if (int rc = create_single(&k, r)) return bail(rc);
+    k->rank = r; k->world = ngpus;
+    g->group->kids.push_back(k);
+  }
+  std::vector<ncclComm_t> comms(ngpus);
+  if (nccl().CommInitAll(comms.data(), ngpus, devs.data()) != ncclSuccess) return bail(LSQR_ERR_COMM);
+  for (int r = 0; r < ngpus; r++) g->group->kids[r]->comm = comms[r];
+  g->group->workers.reset(new Workers(ngpus));
+  g->group->workers->run([&](int r) { return cudaSetDevice(g->group->kids[r]->device) == cudaSuccess ? 0 : LSQR_ERR_CUDA; });
+  *out = g;
+  return LSQR_OK;
+}
+
+int lsqr_ctx_world(const lsqr_ctx* ctx) { return ctx ? ctx->world : 0; }
+
+int lsqr_nccl_unique_id(void* out_id, size_t bytes) {
+  if (!out_id || bytes < sizeof(ncclUniqueId)) return LSQR_ERR_ARG;
+  if (!nccl().ok) return LSQR_ERR_COMM;
+  ncclUniqueId id;
+  if (nccl().GetUniqueId(&id) != ncclSuccess) return LSQR_ERR_COMM;
+  memcpy(out_id, &id, sizeof(id));
+  return LSQR_OK;
+}
+
+int lsqr_ctx_init_nccl(lsqr_ctx* ctx, const void* id_bytes, size_t bytes, int rank, int world) {
+  if (!ctx || !id_bytes || bytes < sizeof(ncclUniqueId)) return LSQR_ERR_ARG;
+  if (ctx->group) return fail(ctx, LSQR_ERR_ARG, "a multi-GPU group owns its communicators");
+  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, LSQR_ERR_ARG, "bad rank/world");
+  if (!nccl().ok) return fail(ctx, LSQR_ERR_COMM, "libnccl.so.2 not found");
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->comm) { nccl().CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  ncclUniqueId id;
+  memcpy(&id, id_bytes, sizeof(id));
+  if (world > 1) CKN(nccl().CommInitRank(&ctx->comm, world, id, rank));
+  ctx->rank = rank; ctx->world = world; ctx->max_fn = nullptr; ctx->sum_fn = nullptr;
+  return LSQR_OK;
+}
+
+void lsqr_ctx_destroy(lsqr_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->group) {
+    ctx->group->workers.reset();
+    for (lsqr_ctx* k : ctx->group->kids) lsqr_ctx_destroy(k);
+    delete ctx->group;
+    delete ctx;
+    return;
+  }
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->comm && nccl().ok) nccl().CommDestroy(ctx->comm);
+  ctx->copier.reset();
+  free_dataset(ctx->main); free_dataset(ctx->scratch);
+  cudaFree(ctx->bt_data); cudaFree(ctx->bt_off); cudaFree(ctx->bt_prm); cudaFree(ctx->bt_cnt);
+  cudaFree(ctx->weights_dev); cudaFree(ctx->mask_dev); if (ctx->mask_pin) cudaFreeHost(ctx->mask_pin);
+  for (int i = 0; i < lsqr_ctx::kRing; i++) if (ctx->up_pin[i]) cudaFreeHost(ctx->up_pin[i]);
+  cudaFree(ctx->staging); cudaFree(ctx->subsets); cudaFree(ctx->hyp64); cudaFree(ctx->hyp32); cudaFree(ctx->counts);
+  cudaFree(ctx->list_dev); cudaFree(ctx->params_in_dev); cudaFree(ctx->key_dev); cudaFree(ctx->winner_dev); cudaFree(ctx->small_dev);
+  cudaFree(ctx->rb.partials); cudaFree(ctx->rb.moments);
+  if (ctx->pin) cudaFreeHost(ctx->pin);
+  for (int i = 0; i < 6; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < lsqr_ctx::kRing; i++) if (ctx->up_ev[i]) cudaEventDestroy(ctx->up_ev[i]);
+  for (int i = 0; i < 8; i++) if (ctx->up_land[i]) cudaEventDestroy(ctx->up_land[i]);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* lsqr_last_error(const lsqr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int lsqr_ctx_set_stream(lsqr_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return LSQR_ERR_ARG;
+  if (ctx->group) return fail(ctx, LSQR_ERR_ARG, "a multi-GPU group runs on its own streams");
+  if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->own_stream = false;
+  return LSQR_OK;
+}
+
+uint64_t lsqr_kernel_launches(const lsqr_ctx* ctx) {
+  if (!ctx) return 0;
+  if (ctx->group) { uint64_t t = 0; for (const lsqr_ctx* k : ctx->group->kids) t += k->launches; return t; }
+  return ctx->launches;
+}
+
+int lsqr_set_estimator(lsqr_ctx* ctx, int model, double delta, double aux, int ls_type) {
+  if (!ctx) return LSQR_ERR_ARG;
+  if (model < 0 || model >= LSQR_NUM_MODELS) return fail(ctx, LSQR_ERR_ARG, "unknown model");
+  if (ls_type != LSQR_LS_ALGEBRAIC && ls_type != LSQR_LS_GEOMETRIC) return fail(ctx, LSQR_ERR_ARG, "bad least-squares type");  // SphereParametersEstimator.hxx:17-18
+  if (ctx->group) { ctx->model = model; return group_run(ctx, [&](lsqr_ctx* k, int) { return lsqr_set_estimator(k, model, delta, aux, ls_type); }); }
+  if (ctx->model != model) {  // layouts differ between models: the data must be uploaded again
+    cudaSetDevice(ctx->device);
+    free_dataset(ctx->main); free_dataset(ctx->scratch);
+  }
+  ctx->model = model; ctx->delta = delta; ctx->aux = aux; ctx->ls_type = ls_type;
+  // The reference keeps delta*delta for every estimator but the hypersphere, pivot and dense-system ones (e.g.
+  // PlaneParametersEstimator.hxx:16 vs SphereParametersEstimator.hxx:20), so the sign of delta is immaterial there; the device
+  // code that compares an unsquared residual (fp32 fast mode) gets |delta|.
+  const bool distance_threshold = model == LSQR_CIRCLE2 || model == LSQR_SPHERE3 || model == LSQR_SPHERE4 || model == LSQR_PIVOT ||
+                                  model == LSQR_DENSE5 || model == LSQR_DENSE6;
+  ctx->cfg.delta = distance_threshold ? delta : fabs(delta);
+  ctx->cfg.delta2 = delta * delta;
+  const double ang = aux > 0 ? aux : 0.017453292519943295769236907684886;  // RayIntersectionParametersEstimator.h:35
+  double ce = sin(ang);
+  ce *= ce;
+  ctx->cfg.cross_eps = ce;
+  ctx->main.moments_valid = false;
+  return LSQR_OK;
+}
+
+int lsqr_upload(lsqr_ctx* ctx, const void* aos, size_t n, size_t stride_bytes) {
+  if (!ctx) return LSQR_ERR_ARG;
+  if (ctx->group) return group_run(ctx, [&](lsqr_ctx* k, int) { return upload_to(k, k->main, aos, n, stride_bytes, false, true); });
+  return upload_to(ctx, ctx->main, aos, n, stride_bytes, false, true);
+}
+int lsqr_upload_device(lsqr_ctx* ctx, const double* dev_packed, size_t n) {
+  if (!ctx) return LSQR_ERR_ARG;
+  if (ctx->group) return fail(ctx, LSQR_ERR_ARG, "a device buffer belongs to one GPU; upload host memory to a multi-GPU group");
+  if (ctx->model < 0) return fail(ctx, LSQR_ERR_STATE, "lsqr_set_estimator must be called first");
+  return upload_to(ctx, ctx->main, dev_packed, n, sizeof(double) * model_info(ctx->model).D, true, false);
+}
+
+int lsqr_set_shard(lsqr_ctx* ctx, int rank, int world, lsqr_allreduce_max_u64_fn max_fn, lsqr_allreduce_sum_f64_fn sum_fn, void* user) {
+  if (!ctx) return LSQR_ERR_ARG;
+  if (ctx->group) return fail(ctx, LSQR_ERR_ARG, "a multi-GPU group shards itself");
+  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, LSQR_ERR_ARG, "bad rank/world");
+  if (world > 1 && (!max_fn || !sum_fn)) return fail(ctx, LSQR_ERR_ARG, "hooks required when world > 1");
+  if (ctx->comm && nccl().ok) { nccl().CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  ctx->rank = rank; ctx->world = world; ctx->max_fn = max_fn; ctx->sum_fn = sum_fn; ctx->comm_user = user;
+  return LSQR_OK;
+}
+
+int lsqr_score(lsqr_ctx* ctx, const lsqr_score_args* args, lsqr_score_result* res) {
+  if (!ctx) return LSQR_ERR_ARG;
+  if (ctx->group) {
+    if (!args || !res) return fail(ctx, LSQR_ERR_ARG, "null argument");
+    std::vector<lsqr_score_result> rs(ctx->world);
+    const int rc = group_run(ctx, [&](lsqr_ctx* k, int r) { return score_impl(k, args, &rs[r]); });
+    if (rc) return rc;
+    *res = rs[0];
+    uint32_t nv = 0;
+    for (const auto& r : rs) { nv += r.n_valid; res->score_ms = std::max(res->score_ms, r.score_ms); res->consensus_ms = std::max(res->consensus_ms, r.consensus_ms); }
+    res->n_valid = nv;
+    return LSQR_OK;
+  }
+  return score_impl(ctx, args, res);
+}
+
+int lsqr_consensus(lsqr_ctx* ctx, const double* params, uint32_t* out_count) {
+  if (!ctx || !params) return LSQR_ERR_ARG;
+  if (ctx->group) {
+    std::vector<uint32_t> c(ctx->world, 0);
+    const int rc = group_run(ctx, [&](lsqr_ctx* k, int r) { return consensus_impl(k, k->main, params, &c[r]); });
+    if (!rc && out_count) *out_count = c[0];
+    return rc;
+  }
+  return consensus_impl(ctx, ctx->main, params, out_count);
+}
+int lsqr_get_mask(lsqr_ctx* ctx, uint8_t* out_bytes) {
+  if (!ctx) return LSQR_ERR_ARG;
+  if (ctx->group) return group_run(ctx, [&](lsqr_ctx* k, int) { return get_mask_impl(k, k->main, out_bytes); });
+  return get_mask_impl(ctx, ctx->main, out_bytes);
+}
+int lsqr_get_mask_bits(lsqr_ctx* ctx, uint32_t* out_words) {
+  if (!ctx || !out_words) return LSQR_ERR_ARG;
+  auto one = [&](lsqr_ctx* k) -> int {
+    lsqr_ctx* ctx = k;   // for CK
+    if (!k->main.mask_valid) return fail(k, LSQR_ERR_STATE, "no consensus set stored");
+    uint32_t b, e;
+    shard_range(k, k->main.n, &b, &e);
+    if (e <= b) return LSQR_OK;
+    CK(cudaSetDevice(k->device));
+    const size_t w0 = b / 32, w1 = ((size_t)e + 31) / 32;
+    CK(cudaMemcpyAsync(out_words + w0, k->main.maskbits + w0, sizeof(uint32_t) * (w1 - w0), cudaMemcpyDeviceToHost, k->stream));
+    CK(cudaStreamSynchronize(k->stream));
+    return LSQR_OK;
+  };
+  if (ctx->group) return group_run(ctx, [&](lsqr_ctx* k, int) { return one(k); });
+  return one(ctx);
+}
+int lsqr_refine(lsqr_ctx* ctx, int use_mask, double* out_params, int* n_params) {
+  if (!ctx) return LSQR_ERR_ARG;
+  if (ctx->group) {
+    std::vector<std::vector<double>> p(ctx->world, std::vector<double>(LSQR_MAX_PARAMS, 0.0));
+    std::vector<int> np(ctx->world, 0);
+    const int rc = group_run(ctx, [&](lsqr_ctx* k, int r) { return refine_impl(k, k->main, use_mask, p[r].data(), &np[r]); });
+    if (rc) return rc;
+    if (n_params) *n_params = np[0];
+    if (out_params) for (int j = 0; j < np[0]; j++) out_params[j] = p[0][j];
+    return LSQR_OK;
+  }
+  return refine_impl(ctx, ctx->main, use_mask, out_params, n_params);
+}
+
+int lsqr_ransac(lsqr_ctx* ctx, double prob, int precision, uint64_t seed, uint8_t* out_mask, lsqr_compute_result* res) {
+  if (!ctx || !res) return LSQR_ERR_ARG;
+  if (ctx->group) {
+    std::vector<lsqr_compute_result> rs(ctx->world);
+    const int rc = group_run(ctx, [&](lsqr_ctx* k, int r) { return ransac_impl(k, prob, precision, seed, out_mask, &rs[r]); });
+    if (rc) return rc;
+    *res = rs[0];
+    for (const auto& r : rs) res->device_ms = std::max(res->device_ms, r.device_ms);
+    return LSQR_OK;
+  }
+  return ransac_impl(ctx, prob, precision, seed, out_mask, res);
+}
+
+int lsqr_ransac_exhaustive(lsqr_ctx* ctx, int precision, uint8_t* out_mask, lsqr_compute_result* res) {
+  if (!ctx || !res) return LSQR_ERR_ARG;
+  if (ctx->group) {
+    std::vector<lsqr_compute_result> rs(ctx->world);
+    const int rc = group_run(ctx, [&](lsqr_ctx* k, int r) { return ransac_exhaustive_impl(k, precision, out_mask, &rs[r]); });
+    if (rc) return rc;
+    *res = rs[0];
+    return LSQR_OK;
+  }
+  return ransac_exhaustive_impl(ctx, precision, out_mask, res);
+}
+
+int lsqr_ransac_batch(lsqr_ctx* ctx, const double* data, const uint64_t* offsets, uint64_t n_problems, int exhaustive, double prob,
+                      uint32_t max_tries, uint64_t seed, double* out_params, uint32_t* out_counts, uint8_t* out_masks, double* device_ms) {
+  if (!ctx || !data || !offsets || !out_params || !out_counts) return LSQR_ERR_ARG;
+  if (n_problems == 0) return LSQR_OK;
+  if (ctx->group) {   // independent problems: partitioned across the GPUs, no collective
+    const int W = ctx->world;
+    std::vector<double> ms(W, 0.0);
+    const int rc = group_run(ctx, [&](lsqr_ctx* k, int r) {
+      return batch_impl(k, data, offsets, n_problems * r / W, n_problems * (r + 1) / W, exhaustive, prob, max_tries, seed, out_params, out_counts, out_masks, &ms[r]);
+    });
+    if (device_ms) *device_ms = *std::max_element(ms.begin(), ms.end());
+    return rc;
+  }
+  return batch_impl(ctx, data, offsets, 0, n_problems, exhaustive, prob, max_tries, seed, out_params, out_counts, out_masks, device_ms);
 }
 
 int lsqr_estimate(lsqr_ctx* ctx, const double* packed, size_t n, double* out_params, int* n_params) {
   if (!ctx || !packed || !out_params || !n_params) return LSQR_ERR_ARG;
+  if (ctx->group) { lsqr_ctx* k = ctx->group->kids[0]; const int rc = lsqr_estimate(k, packed, n, out_params, n_params); if (rc) ctx->err = k->err; return rc; }
   if (ctx->model < 0) return fail(ctx, LSQR_ERR_STATE, "lsqr_set_estimator must be called first");
   const ModelInfo mi = model_info(ctx->model);
   *n_params = 0;
@@ -706,6 +1191,7 @@ int lsqr_estimate(lsqr_ctx* ctx, const double* packed, size_t n, double* out_par
 
 int lsqr_agree(lsqr_ctx* ctx, const double* params, const double* packed, size_t n, uint8_t* out) {
   if (!ctx || !params || !packed || !out) return LSQR_ERR_ARG;
+  if (ctx->group) { lsqr_ctx* k = ctx->group->kids[0]; const int rc = lsqr_agree(k, params, packed, n, out); if (rc) ctx->err = k->err; return rc; }
   if (ctx->model < 0) return fail(ctx, LSQR_ERR_STATE, "lsqr_set_estimator must be called first");
   if (n == 0) return LSQR_OK;
   if (n > 0xFFFFFFF0ull) return fail(ctx, LSQR_ERR_ARG, "too many data records");
@@ -726,6 +1212,7 @@ int lsqr_agree(lsqr_ctx* ctx, const double* params, const double* packed, size_t
 
 int lsqr_least_squares(lsqr_ctx* ctx, const double* packed, size_t n, double* out_params, int* n_params) {
   if (!ctx || !out_params || !n_params) return LSQR_ERR_ARG;
+  if (ctx->group) { lsqr_ctx* k = ctx->group->kids[0]; const int rc = lsqr_least_squares(k, packed, n, out_params, n_params); if (rc) ctx->err = k->err; return rc; }
   if (ctx->model < 0) return fail(ctx, LSQR_ERR_STATE, "lsqr_set_estimator must be called first");
   const ModelInfo mi = model_info(ctx->model);
   *n_params = 0;
@@ -734,7 +1221,7 @@ int lsqr_least_squares(lsqr_ctx* ctx, const double* packed, size_t n, double* ou
   // single-GPU by construction: a direct estimator call is not part of a sharded compute()
   const int world = ctx->world, rank = ctx->rank;
   ctx->world = 1; ctx->rank = 0;
-  int rc = upload_to(ctx, ctx->scratch, packed, n, sizeof(double) * mi.D, false);
+  int rc = upload_to(ctx, ctx->scratch, packed, n, sizeof(double) * mi.D, false, false);
   if (!rc) rc = refine_impl(ctx, ctx->scratch, 0, out_params, n_params);
   ctx->world = world; ctx->rank = rank;
   return rc;
@@ -742,12 +1229,13 @@ int lsqr_least_squares(lsqr_ctx* ctx, const double* packed, size_t n, double* ou
 
 int lsqr_weighted_least_squares(lsqr_ctx* ctx, const double* packed, size_t n, const double* weights, double* out_params, int* n_params) {
   if (!ctx || !out_params || !n_params || !weights) return LSQR_ERR_ARG;
+  if (ctx->group) { lsqr_ctx* k = ctx->group->kids[0]; const int rc = lsqr_weighted_least_squares(k, packed, n, weights, out_params, n_params); if (rc) ctx->err = k->err; return rc; }
   if (ctx->model != ABSOR) return fail(ctx, LSQR_ERR_ARG, "weighted least squares exists for the absolute-orientation estimator only");
   *n_params = 0;
   if (n < 3) return LSQR_OK;   // AbsoluteOrientationParametersEstimator.cxx:214-215
   const int world = ctx->world, rank = ctx->rank;
   ctx->world = 1; ctx->rank = 0;
-  int rc = upload_to(ctx, ctx->scratch, packed, n, sizeof(double) * 6, false);
+  int rc = upload_to(ctx, ctx->scratch, packed, n, sizeof(double) * 6, false, false);
   ctx->world = world; ctx->rank = rank;
   if (rc) return rc;
   cudaStream_t s = ctx->stream;
@@ -769,6 +1257,7 @@ int lsqr_weighted_least_squares(lsqr_ctx* ctx, const double* packed, size_t n, c
 
 int lsqr_microbench_fma(lsqr_ctx* ctx, int kind, int iters, double* out_fma_per_s, double* out_ms) {
   if (!ctx || kind < 0 || kind > 2 || iters <= 0) return LSQR_ERR_ARG;
+  if (ctx->group) return lsqr_microbench_fma(ctx->group->kids[0], kind, iters, out_fma_per_s, out_ms);
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   float* sink = reinterpret_cast<float*>(ctx->small_dev + kSmSink);
@@ -789,6 +1278,7 @@ int lsqr_microbench_fma(lsqr_ctx* ctx, int kind, int iters, double* out_fma_per_
 
 int lsqr_last_refine_stats(const lsqr_ctx* ctx, double* kernel_ms, double* algorithmic_bytes, int* lm_iterations) {
   if (!ctx) return LSQR_ERR_ARG;
+  if (ctx->group) return lsqr_last_refine_stats(ctx->group->kids[0], kernel_ms, algorithmic_bytes, lm_iterations);
   if (kernel_ms) *kernel_ms = ctx->refine_kernel_ms;
   if (algorithmic_bytes) *algorithmic_bytes = ctx->refine_bytes;
   if (lm_iterations) *lm_iterations = ctx->lm_iterations;

@@ -13,21 +13,32 @@ constexpr int kMaxDim = 20;           // doubles per datum, upper bound (calibra
 constexpr int kLmStateDoubles = 256;  // device scratch reserved for the Levenberg-Marquardt controller state
 constexpr int kMaxMoments = 96;  // upper bound on the doubles accumulated per thread by the refine reductions (cross-wire US calibration: 91)
 
+constexpr uint32_t kCenterSample = 16384;   // the shift c is the mean of the first min(n, kCenterSample) records
+
 // Device-resident description of the uploaded data.
 struct DataView {
   const double* soa64;  // [D][ld], padded with NaN
   const float* soa32;   // [D][ld], centred (soa64 - center), padded with NaN
   size_t ld;
   uint32_t n;
-  double center[kMaxDim];  // per-component shift used for soa32 and for the refine moments
+  const double* center; // device, kMaxDim doubles: per-component shift used for soa32 and for the refine moments
+};
+
+// What the host reads back after a scoring request: one small record, one copy.
+struct WinnerRecord {
+  unsigned long long key;      // (count << 32) | (0xFFFFFFFF - index relative to the request's first hypothesis)
+  unsigned long long n_valid;
+  int32_t subset[8];
+  double params[20];
 };
 
 // ---- k_score.cu -------------------------------------------------------------------------
-// AoS records (stride bytes, D leading doubles each) -> SoA fp64, NaN padding.
-void launch_ingest(int D, const unsigned char* aos, size_t stride, uint32_t n, double* soa64, size_t ld, cudaStream_t s);
-// Deterministic per-component mean over the n valid records -> center[D] (device).
-void launch_center(int model, const double* soa64, size_t ld, uint32_t n, double* partials, double* center_dev, cudaStream_t s);
-void launch_make32(int D, const double* soa64, const double* center_dev, float* soa32, size_t ld, cudaStream_t s);
+// c = mean of the first `count` AoS records (device buffer), per centred component -> center_dev[kMaxDim].
+void launch_center_sample(int model, const unsigned char* aos_dev, size_t stride, uint32_t count, double* center_dev, cudaStream_t s);
+// AoS records [first, first + count) (stride bytes, D leading doubles each) -> SoA fp64 and SoA fp32 of x - c; columns up to
+// pad_to are NaN-filled.
+void launch_ingest(int D, const unsigned char* aos_dev, size_t stride, uint32_t first, uint32_t count, uint32_t pad_to, const double* center_dev,
+                   double* soa64, float* soa32, size_t ld, cudaStream_t s);
 
 struct SolveArgs {
   int model, sampler;
@@ -41,6 +52,9 @@ struct SolveArgs {
   uint32_t* n_valid;      // out (atomic)
 };
 void launch_solve(const SolveArgs& a, const DataView& dv, const EstCfg& cfg, cudaStream_t s);
+// key (after arg-max / all-reduce) -> winner's subset and parameters, on the device; a.first = first hypothesis of the REQUEST,
+// a.list / a.params_in = the request's device-resident list (samplers 2, 3)
+void launch_winner(const SolveArgs& a, const unsigned long long* key_dev, const DataView& dv, const EstCfg& cfg, WinnerRecord* out, cudaStream_t s);
 void launch_hoist32(int model, const double* hyp64, size_t hld, uint32_t H, const DataView& dv, const EstCfg& cfg, float* hyp32, cudaStream_t s);
 // counts[h] (+)= |{m : agree(h, datum m)}|.  counts must be zeroed by the caller.  Returns #launches.
 int launch_consensus(int model, int precision, const DataView& dv, const double* hyp64, const float* hyp32, size_t hld, uint32_t H,
@@ -54,6 +68,7 @@ void launch_argmax(const uint32_t* counts, uint32_t H, uint32_t index_base, unsi
 // ---- k_refine.cu ------------------------------------------------------------------------
 struct RefineBuffers {
   uint32_t* maskbits;   // [ld/32]
+  uint8_t* maskbytes;   // optional [n]: mask mode 1 also writes one byte per datum (std::vector<bool> order)
   double* partials;     // [blocks][kMaxMoments]
   double* moments;      // [kMaxMoments] reduced (device)
   int blocks;
@@ -79,7 +94,8 @@ void launch_solve_weighted_absor(const DataView& dv, const double* moments, doub
 int moments_count(int model, bool lm);
 int lm_status_offset();   // index of the status word (0 run, 1 converged, 2 failed) in the LM state
 int mask_moments_ctas_per_sm();   // grid of launch_mask_moments = this x SMs (one wave)
-void launch_expand_mask(const uint32_t* bits, uint32_t n, uint8_t* bytes, cudaStream_t s);
+// bytes[i] = bit i of the consensus set, for i in [first, first + count)
+void launch_expand_mask(const uint32_t* bits, uint32_t first, uint32_t count, uint8_t* bytes, cudaStream_t s);
 
 struct BatchArgs {
   int model, exhaustive;
@@ -87,7 +103,9 @@ struct BatchArgs {
   double prob;               // desiredProbabilityForNoOutliers for the stop rule; <= 0 disables it
   uint64_t seed;
   const double* data;        // packed [total][D] on device
-  const uint64_t* offsets;   // [n_problems+1] on device
+  const uint64_t* offsets;   // [n_problems+1] on device, absolute record offsets (data[0] is record `base`)
+  uint64_t base;             // record offset of the first problem of this launch
+  uint64_t first_problem;    // global index of the first problem of this launch (the Philox counter of a problem is global)
   uint32_t n_problems;
   uint32_t max_n;            // largest problem (sizes shared memory)
   double* out_params;        // [n_problems][P]

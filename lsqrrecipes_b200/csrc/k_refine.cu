@@ -39,13 +39,6 @@ __host__ __device__ inline int n_moments(int model, bool lm) {
 }
 static_assert(kLmStateDoubles >= LM_SIZE, "engine.h: LM state buffer too small");
 
-#ifndef LSQR_MM_CTAS
-#define LSQR_MM_CTAS 2
-#endif
-#ifndef LSQR_MM_U
-#define LSQR_MM_U 8
-#endif
-int mask_moments_ctas_per_sm() { return LSQR_MM_CTAS; }
 int moments_count(int model, bool lm) { return n_moments(model, lm); }
 
 template <int M> struct Mom { static constexpr int N = 0, NLM = 0, NPLM = 1; };   // NPLM = parameters of the LM problem
@@ -74,16 +67,16 @@ template <int DIM> __device__ __forceinline__ void acc_scatter(const double* q, 
 #pragma unroll
   for (int j = 0; j < DIM; j++)
 #pragma unroll
-    for (int k = j; k < DIM; k++) acc[o++] += q[j] * q[k];
+    for (int k = j; k < DIM; k++) { acc[o] = fma(q[j], q[k], acc[o]); o++; }   // (this TU is built with -fmad=false for agree(); the sums may fuse)
 }
 template <int DIM> __device__ __forceinline__ void acc_sphere_alg(const double* q, double* acc) {
   double s = 0;
 #pragma unroll
-  for (int j = 0; j < DIM; j++) s += q[j] * q[j];
+  for (int j = 0; j < DIM; j++) s = fma(q[j], q[j], s);
   acc_scatter<DIM>(q, acc);
   int o = 1 + DIM + DIM * (DIM + 1) / 2;
 #pragma unroll
-  for (int j = 0; j < DIM; j++) acc[o++] += s * q[j];
+  for (int j = 0; j < DIM; j++) { acc[o] = fma(s, q[j], acc[o]); o++; }
   acc[o] += s;
 }
 // residual / Jacobian of SphereParametersEstimator.hxx:394-431 at x = (centre', r)
@@ -100,10 +93,10 @@ template <int DIM> __device__ __forceinline__ void acc_sphere_lm(const double* q
 #pragma unroll
   for (int a = 0; a <= DIM; a++)
 #pragma unroll
-    for (int b = a; b <= DIM; b++) acc[o++] += J[a] * J[b];
+    for (int b = a; b <= DIM; b++) { acc[o] = fma(J[a], J[b], acc[o]); o++; }
 #pragma unroll
-  for (int a = 0; a <= DIM; a++) acc[o++] += J[a] * r;
-  acc[o] += r * r;
+  for (int a = 0; a <= DIM; a++) { acc[o] = fma(J[a], r, acc[o]); o++; }
+  acc[o] = fma(r, r, acc[o]);
 }
 
 template <int M> __device__ __forceinline__ void accumulate(const double* q, double* acc);
@@ -123,7 +116,7 @@ template <> __device__ __forceinline__ void accumulate<ABSOR>(const double* q, d
 #pragma unroll
   for (int r = 0; r < 3; r++)
 #pragma unroll
-    for (int c = 0; c < 3; c++) acc[7 + r * 3 + c] += q[r] * q[3 + c];
+    for (int c = 0; c < 3; c++) acc[7 + r * 3 + c] = fma(q[r], q[3 + c], acc[7 + r * 3 + c]);
 }
 // RayIntersectionParametersEstimator.cxx:108-123
 template <> __device__ __forceinline__ void accumulate<RAY>(const double* q, double* acc) {
@@ -157,9 +150,9 @@ template <int N> __device__ __forceinline__ void acc_dense(const double* q, doub
 #pragma unroll
   for (int a = 0; a < N; a++)
 #pragma unroll
-    for (int b = a; b < N; b++) acc[o++] += q[a] * q[b];
+    for (int b = a; b < N; b++) { acc[o] = fma(q[a], q[b], acc[o]); o++; }
 #pragma unroll
-  for (int a = 0; a < N; a++) acc[o++] += q[a] * q[N];
+  for (int a = 0; a < N; a++) { acc[o] = fma(q[a], q[N], acc[o]); o++; }
 }
 template <> __device__ __forceinline__ void accumulate<DENSE5>(const double* q, double* acc) { acc_dense<5>(q, acc); }
 template <> __device__ __forceinline__ void accumulate<DENSE6>(const double* q, double* acc) { acc_dense<6>(q, acc); }
@@ -226,10 +219,10 @@ template <int NT1> __device__ __forceinline__ void acc_us_lm_rows(const double* 
 #pragma unroll
   for (int i = 0; i < NP; i++)
 #pragma unroll
-    for (int j = i; j < NP; j++) acc[o++] += J[i] * J[j];
+    for (int j = i; j < NP; j++) { acc[o] = fma(J[i], J[j], acc[o]); o++; }
 #pragma unroll
-  for (int i = 0; i < NP; i++) acc[o++] += J[i] * d;
-  acc[o] += d * d;
+  for (int i = 0; i < NP; i++) { acc[o] = fma(J[i], d, acc[o]); o++; }
+  acc[o] = fma(d, d, acc[o]);
 }
 __device__ __forceinline__ void acc_us_lm(const double* q, const double* x, double* acc) { acc_us_lm_rows<3>(q, x, x, acc); }
 
@@ -266,20 +259,71 @@ __host__ __device__ inline bool centred_comp(int model, int d) {
   }
 }
 
-// MODE 0: every datum counts; 1: evaluate agree() and write the consensus bits; 2: read stored bits.
-// HBM-bound streaming pass.  Two resident CTAs per SM (grid = 2 x SMs, one wave); every warp keeps
-// U rows of 32 data (U*D 8-byte loads per lane, ~48 registers) in flight before it touches them, so
-// that ~100 KB per SM are outstanding -- what a 6.5 TB/s stream needs at ~600 ns latency.
-// Models with more than 40 accumulators per thread (the two ultrasound calibrations: 55-91 doubles) get the whole register
-// file of an SM for one CTA; with two resident CTAs their accumulators spill to local memory.
-template <int M, bool LM> constexpr int mm_ctas() { return ((LM ? Mom<M>::NLM : Mom<M>::N) > 40) ? 1 : LSQR_MM_CTAS; }
+// ---- mbarrier / TMA-bulk helpers (SASS: SYNCS / UBLKCP) ------------------------------------
+__device__ __forceinline__ uint32_t mm_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mm_bar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mm_smem(bar)), "r"(count)); }
+__device__ __forceinline__ void mm_bar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mm_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mm_bar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mm_smem(bar)) : "memory"); }
+__device__ __forceinline__ void mm_bar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(mm_smem(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mm_tma_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(mm_smem(dst)), "l"(src), "r"(bytes),
+               "r"(mm_smem(bar))
+               : "memory");
+}
+
+// Blocking of the streaming pass: one persistent CTA per SM walks tiles of TILE data; a tile is D rows of TILE doubles in
+// shared memory, filled by D bulk copies (cp.async.bulk, one mbarrier per stage), STAGES tiles deep.  The bytes in flight per
+// SM are (STAGES - 1) tiles whatever the compute phase of the warps is -- what the register-staged version lacked
+// (profiles/r01_ncu_mask_moments_v2.txt: 25 % warps active, wait + long_scoreboard 60 %, 0.62 of HBM).
+#ifndef LSQR_MM_SMEM_KB
+#define LSQR_MM_SMEM_KB 160
+#endif
+#ifndef LSQR_MM_TILE_KB
+#define LSQR_MM_TILE_KB 24
+#endif
+#ifndef LSQR_MM_THREADS
+#define LSQR_MM_THREADS 512
+#endif
+template <int M, bool LM> struct MMCfg {
+  static constexpr int D = Model<M>::D;
+  static constexpr int NM = LM ? Mom<M>::NLM : Mom<M>::N;
+  // models with more than 40 accumulators per thread (the two ultrasound calibrations: 46-91 doubles) get the whole register
+  // file of an SM for 256 threads; everyone else runs 512 threads
+  static constexpr int THREADS = NM > 40 ? 256 : LSQR_MM_THREADS;
+  static constexpr int TILE = (D * 1024 * 8 <= LSQR_MM_TILE_KB * 1024 + 8192) ? 1024 : ((D * 512 * 8 <= LSQR_MM_TILE_KB * 1024 + 8192) ? 512 : 256);
+  static constexpr int PPT = (TILE + THREADS - 1) / THREADS;                 // data per thread per tile
+  static constexpr int TILE_BYTES = D * TILE * 8;
+  static constexpr int STAGES = (LSQR_MM_SMEM_KB * 1024 / TILE_BYTES) < 2 ? 2 : ((LSQR_MM_SMEM_KB * 1024 / TILE_BYTES) > 8 ? 8 : (LSQR_MM_SMEM_KB * 1024 / TILE_BYTES));
+  static constexpr size_t SMEM = (size_t)STAGES * TILE_BYTES;
+};
+int mask_moments_ctas_per_sm() { return 1; }
+
+// MODE 0: every datum counts; 1: evaluate agree() and write the consensus bits (and, when maskbytes != nullptr, the
+// std::vector<bool>-shaped byte per datum that the caller of compute() receives); 2: read stored bits.
+// HBM-bound: D*8 bytes read per datum, 1 bit (or 1 byte + 1 bit) written.
 template <int M, int MODE, bool LM>
-__global__ void __launch_bounds__(256, mm_ctas<M, LM>()) mask_moments_kernel(DataView dv, uint32_t begin, uint32_t end, const double* __restrict__ params_dev,
+__global__ void __launch_bounds__(MMCfg<M, LM>::THREADS, 1) mask_moments_kernel(DataView dv, uint32_t begin, uint32_t end, const double* __restrict__ params_dev,
                                                                const double* __restrict__ lm_state, EstCfg cfg, uint32_t* __restrict__ maskbits,
-                                                               double* __restrict__ partials) {
+                                                               uint8_t* __restrict__ maskbytes, double* __restrict__ partials) {
+  using C = MMCfg<M, LM>;
   constexpr int D = Model<M>::D, P = Model<M>::P, HQ = Model<M>::HQ;
-  constexpr int NM = LM ? Mom<M>::NLM : Mom<M>::N;
-  constexpr int U = D > 6 ? (LM ? 1 : 2) : (LM ? 4 : (D <= 3 ? LSQR_MM_U : 4));
+  constexpr int NM = C::NM, TILE = C::TILE, THREADS = C::THREADS, PPT = C::PPT, STAGES = C::STAGES;
+  extern __shared__ __align__(128) unsigned char mm_smem_raw[];
+  double* ring = reinterpret_cast<double*>(mm_smem_raw);                     // [STAGES][D][TILE]
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
+  __shared__ double sh[THREADS / 32][NM > 0 ? NM : 1];
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
+
   double acc[NM > 0 ? NM : 1];
 #pragma unroll
   for (int j = 0; j < NM; j++) acc[j] = 0.0;
@@ -291,41 +335,68 @@ __global__ void __launch_bounds__(256, mm_ctas<M, LM>()) mask_moments_kernel(Dat
     prepare<M>(prm, hq);
   }
   double lmx[LM ? Mom<M>::NPLM : 1] = {0};
+  bool active = true;
   if (LM) {
     // the host enqueues evaluation passes a few iterations ahead of the controller's status word: once the iteration has
     // stopped, the remaining passes are no-ops (the controller ignores the stale moments)
-    if (lm_state[LM_STATUS] != 0.0) return;
+    active = lm_state[LM_STATUS] == 0.0;
     // the phase selects the evaluation point: x or the trial point
     const int off = (lm_state[LM_PHASE] != 0.0) ? LM_TRIAL : LM_X;
 #pragma unroll
     for (int j = 0; j < Mom<M>::NPLM; j++) lmx[j] = lm_state[off + j];
   }
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  for (uint64_t base = (uint64_t)begin + (uint64_t)warp * (32 * U); base < end; base += (uint64_t)warps_total * (32 * U)) {
-    double x[U][D];
-    uint32_t stored[U];
+  // tiles [t0, t1) in units of TILE data cover [begin, end); this CTA takes t0 + blockIdx.x, + gridDim.x, ...
+  const uint32_t t0 = begin / TILE, t1 = (uint32_t)(((uint64_t)end + TILE - 1) / TILE);
+  const uint32_t first = t0 + blockIdx.x;
+  const uint32_t n_mine = (active && first < t1) ? (t1 - first + gridDim.x - 1) / gridDim.x : 0;
+  if (tid == 0) {
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      const uint64_t row = base + 32 * u;   // rows start on multiples of 32; the arrays are NaN-padded to ld >= end rounded up to 1024
-      if (row < end) {
+    for (int s = 0; s < STAGES; s++) { mm_bar_init(&full_bar[s], 1); mm_bar_init(&empty_bar[s], THREADS / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](uint32_t k) {   // tile number k of this CTA into stage k % STAGES
+    const uint32_t s = k % STAGES;
+    const size_t base = (size_t)(first + k * gridDim.x) * TILE;
+    double* dst = ring + (size_t)s * D * TILE;
+    mm_bar_expect_tx(&full_bar[s], (uint32_t)C::TILE_BYTES);
 #pragma unroll
-        for (int d = 0; d < D; d++) x[u][d] = __ldcs(dv.soa64 + (size_t)d * dv.ld + row + lane);
-        if (MODE == 2) stored[u] = maskbits[row >> 5];
+    for (int d = 0; d < D; d++) mm_tma_g2s(dst + d * TILE, dv.soa64 + (size_t)d * dv.ld + base, TILE * 8, &full_bar[s]);
+  };
+  if (tid == 0) for (uint32_t k = 0; k < (uint32_t)STAGES && k < n_mine; k++) issue(k);
+
+  for (uint32_t k = 0; k < n_mine; k++) {
+    const uint32_t s = k % STAGES, parity = (k / STAGES) & 1u;
+    const size_t base = (size_t)(first + k * gridDim.x) * TILE;
+    const double* tile = ring + (size_t)s * D * TILE;
+    mm_bar_wait(&full_bar[s], parity);
+    double x[PPT][D];
+#pragma unroll
+    for (int u = 0; u < PPT; u++) {
+      const uint32_t p = u * THREADS + tid;
+      if (PPT * THREADS == TILE || p < (uint32_t)TILE) {
+#pragma unroll
+        for (int d = 0; d < D; d++) x[u][d] = tile[d * TILE + p];
       }
     }
+    // the stage is free as soon as every warp holds its data in registers; thread 0 refills it STAGES tiles ahead
+    __syncwarp();
+    if (lane == 0) mm_bar_arrive(&empty_bar[s]);
+    if (tid == 0 && k + STAGES < n_mine) { mm_bar_wait(&empty_bar[s], parity); issue(k + STAGES); }
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      const uint64_t row = base + 32 * u, i = row + lane;
-      if (row >= end) break;
+    for (int u = 0; u < PPT; u++) {
+      const uint32_t p = u * THREADS + tid;
+      if (!(PPT * THREADS == TILE || p < (uint32_t)TILE)) break;
+      const uint64_t i = base + p, row = i - lane;      // rows of 32 data start on multiples of 32; begin is one, too
+      if (row < begin || row >= end) continue;          // warp-uniform
       bool in;
       if (MODE == 0) in = i < end;
       else if (MODE == 1) {
-        in = (i < end) && agree<M>(hq, x[u], cfg);   // NaN padding beyond n never agrees
+        in = (i < end) && agree<M>(hq, x[u], cfg);      // NaN padding beyond n never agrees
         const unsigned bits = __ballot_sync(0xffffffffu, in);
         if (lane == 0) maskbits[row >> 5] = bits;
-      } else in = (i < end) && ((stored[u] >> lane) & 1u);
+        if (maskbytes != nullptr && i < end) maskbytes[i] = in ? 1 : 0;
+      } else in = (i < end) && ((maskbits[row >> 5] >> lane) & 1u);
       if (in) {
         double q[D];
 #pragma unroll
@@ -340,32 +411,42 @@ __global__ void __launch_bounds__(256, mm_ctas<M, LM>()) mask_moments_kernel(Dat
       }
     }
   }
-  // block reduction: shuffle within warps, shared memory across the 8 warps
-  __shared__ double sh[8][kMaxMoments];
+  if (LM && !active) return;   // partials, moments and the controller state keep their values
+  // block reduction: shuffle within warps, shared memory across the warps
 #pragma unroll
   for (int j = 0; j < NM; j++) {
     double v = acc[j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) sh[threadIdx.x >> 5][j] = v;
+    if (lane == 0) sh[tid >> 5][j] = v;
   }
   __syncthreads();
-  if ((int)threadIdx.x < NM) {
+  if ((int)tid < NM) {
     double v = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) v += sh[w][threadIdx.x];
-    partials[(size_t)blockIdx.x * kMaxMoments + threadIdx.x] = v;
+    for (int w = 0; w < THREADS / 32; w++) v += sh[w][tid];
+    partials[(size_t)blockIdx.x * kMaxMoments + tid] = v;
   }
+}
+
+template <int M, int MODE, bool LM>
+static void run_mask_moments(const DataView& dv, uint32_t begin, uint32_t end, const double* params_dev, const double* lm_state, const EstCfg& cfg,
+                             const RefineBuffers& rb, cudaStream_t s) {
+  using C = MMCfg<M, LM>;
+  auto kern = mask_moments_kernel<M, MODE, LM>;
+  static bool attr_set[64] = {false};   // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM); attr_set[dev & 63] = true; }
+  kern<<<rb.blocks, C::THREADS, C::SMEM, s>>>(dv, begin, end, params_dev, lm_state, cfg, rb.maskbits, rb.maskbytes, rb.partials);
 }
 
 void launch_mask_moments(int model, const DataView& dv, uint32_t begin, uint32_t end, const double* params_dev, int mask_mode,
                          const double* lm_state, const EstCfg& cfg, const RefineBuffers& rb, cudaStream_t s) {
-  const int blocks = rb.blocks;
-#define LAUNCH(MM, MODE, LMV) mask_moments_kernel<MM, MODE, LMV><<<blocks, 256, 0, s>>>(dv, begin, end, params_dev, lm_state, cfg, rb.maskbits, rb.partials)
-#define BYMODE(MM, LMV)                                   \
-  if (mask_mode == 0) LAUNCH(MM, 0, LMV);                 \
-  else if (mask_mode == 1) LAUNCH(MM, 1, LMV);            \
-  else LAUNCH(MM, 2, LMV)
+#define BYMODE(MM, LMV)                                                                           \
+  if (mask_mode == 0) run_mask_moments<MM, 0, LMV>(dv, begin, end, params_dev, lm_state, cfg, rb, s);      \
+  else if (mask_mode == 1) run_mask_moments<MM, 1, LMV>(dv, begin, end, params_dev, lm_state, cfg, rb, s); \
+  else run_mask_moments<MM, 2, LMV>(dv, begin, end, params_dev, lm_state, cfg, rb, s)
   if (lm_state) {
     if (model == CIRCLE2) { BYMODE(CIRCLE2, true); }
     else if (model == SPHERE3) { BYMODE(SPHERE3, true); }
@@ -392,7 +473,6 @@ void launch_mask_moments(int model, const DataView& dv, uint32_t begin, uint32_t
     case PLANE4: { BYMODE(PLANE4, false); break; }
   }
 #undef BYMODE
-#undef LAUNCH
 }
 
 // Weighted Horn moments (AbsoluteOrientationParametersEstimator.cxx:217-261): sum w, sum w p1, sum w p2,
@@ -750,12 +830,12 @@ void launch_lm_finish(int model, const DataView& dv, const double* state, double
 int lm_status_offset() { return LM_STATUS; }
 
 // ---------------------------------------------------------------------------------------
-__global__ void expand_mask_kernel(const uint32_t* __restrict__ bits, uint32_t n, uint8_t* __restrict__ bytes) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) bytes[i] = (bits[i >> 5] >> (i & 31)) & 1u;
+__global__ void expand_mask_kernel(const uint32_t* __restrict__ bits, uint32_t first, uint32_t count, uint8_t* __restrict__ bytes) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count) { const uint32_t i = first + t; bytes[i] = (bits[i >> 5] >> (i & 31)) & 1u; }
 }
-void launch_expand_mask(const uint32_t* bits, uint32_t n, uint8_t* bytes, cudaStream_t s) {
-  if (n) expand_mask_kernel<<<(n + 255) / 256, 256, 0, s>>>(bits, n, bytes);
+void launch_expand_mask(const uint32_t* bits, uint32_t first, uint32_t count, uint8_t* bytes, cudaStream_t s) {
+  if (count) expand_mask_kernel<<<(count + 255) / 256, 256, 0, s>>>(bits, first, count, bytes);
 }
 
 
@@ -829,8 +909,9 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
   __shared__ int sh_ok;
 
   const uint32_t b = blockIdx.x;
-  const uint64_t off = a.offsets[b];
-  const uint32_t n = (uint32_t)(a.offsets[b + 1] - off);
+  const uint64_t off = a.offsets[b] - a.base;                 // record offset inside this launch's data
+  const uint32_t n = (uint32_t)(a.offsets[b + 1] - a.offsets[b]);
+  const uint64_t gb = a.first_problem + b;                    // global problem index: the sampler's counter does not depend on how problems are split over GPUs
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   for (uint32_t i = threadIdx.x; i < n * D; i += blockDim.x) pts[(i % D) * ldp + (i / D)] = a.data[off * D + i];
   if (threadIdx.x == 0) {
@@ -853,7 +934,7 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
     unsigned long long key = 0ull;
     if (h < sh_tries) {
       int32_t sub[K];
-      if (a.exhaustive) unrank_lex<K>(h, n, sub); else sample_subset<K>(((uint64_t)b << 32) | h, a.seed, n, sub);
+      if (a.exhaustive) unrank_lex<K>(h, n, sub); else sample_subset<K>((gb << 32) | h, a.seed, n, sub);
       double sp[K * D], prm[P], hq[HQ];
 #pragma unroll
       for (int j = 0; j < K; j++)
@@ -902,7 +983,7 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
     if (best_count > 0) {
       const unsigned long long h = 0xFFFFFFFFull - (best & 0xFFFFFFFFull);
       int32_t sub[K];
-      if (a.exhaustive) unrank_lex<K>(h, n, sub); else sample_subset<K>(((uint64_t)b << 32) | h, a.seed, n, sub);
+      if (a.exhaustive) unrank_lex<K>(h, n, sub); else sample_subset<K>((gb << 32) | h, a.seed, n, sub);
       double sp[K * D], prm[P];
       for (int j = 0; j < K; j++) for (int d = 0; d < D; d++) sp[j * D + d] = pts[d * ldp + sub[j]];
       if (estimate<M>(sp, cfg, prm)) { prepare<M>(prm, sh_prm); sh_ok = 1; }
@@ -920,14 +1001,14 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
 #pragma unroll
   for (int j = 0; j < HQ; j++) hq[j] = sh_prm[j];
   block_moments<M>(pts, n, ldp, hq, cfg, nullptr, false, 1, mask_out, sh_part, sh_mom);
-  DataView zero;
-  for (int j = 0; j < kMaxDim; j++) zero.center[j] = 0.0;
+  double zero_center[kMaxDim];
+  for (int j = 0; j < kMaxDim; j++) zero_center[j] = 0.0;
   __shared__ double sh_out[LSQR_MAX_PARAMS + 4];
   if (threadIdx.x == 0) {
     double p[LSQR_MAX_PARAMS];
     int np = 0;
     const double* m = sh_mom;
-    const double* c = zero.center;
+    const double* c = zero_center;
     switch (M) {
       case PLANE3: np = solve_scatter<3>(m, c, 0, p); break;
       case PLANE4: np = solve_scatter<4>(m, c, 0, p); break;

@@ -14,6 +14,7 @@
 // mode lives in k_fast.cu.
 // Tensor cores are deliberately unused: the contraction depth is <= 4 (BASELINE.json north_star).
 #include "engine.h"
+#include "../../include/lsqr_b200.h"
 
 #include <cstdio>
 
@@ -46,23 +47,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 }
 
 // ---------------------------------------------------------------------------------------
-// Ingest
+// Ingest: AoS records -> SoA fp64 (reference arithmetic) + SoA fp32 of x - c (fast mode), one pass, chunk by chunk so
+// that it overlaps the host-to-device copy (and, with several GPUs, the all-gather) of the chunks behind it.
 // ---------------------------------------------------------------------------------------
-__global__ void ingest_kernel(int D, const unsigned char* __restrict__ aos, size_t stride, uint32_t n, double* __restrict__ soa, size_t ld) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ld) return;
-  if (i < n) {
-    const double* rec = reinterpret_cast<const double*>(aos + i * stride);
-    for (int d = 0; d < D; d++) soa[(size_t)d * ld + i] = rec[d];
-  } else {
-    const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    for (int d = 0; d < D; d++) soa[(size_t)d * ld + i] = nan;
-  }
-}
-void launch_ingest(int D, const unsigned char* aos, size_t stride, uint32_t n, double* soa64, size_t ld, cudaStream_t s) {
-  ingest_kernel<<<(unsigned)((ld + 255) / 256), 256, 0, s>>>(D, aos, stride, n, soa64, ld);
-}
-
 // Which components are positions (get centred) for each model; directions / rotations are not.
 __host__ __device__ inline bool centred_component(int model, int d) {
   switch (model) {
@@ -75,42 +62,52 @@ __host__ __device__ inline bool centred_component(int model, int d) {
   }
 }
 
-constexpr int kCenterBlocks = 256;
-__global__ void center_partial_kernel(int D, const double* __restrict__ soa, size_t ld, uint32_t n, double* __restrict__ partials) {
+// The shift c: per-component mean of the first `count` records (count <= kCenterSample), fixed-order tree sum.  c only
+// conditions the arithmetic (fp32 copy of x - c, moments of x - c); any point near the data does, and a prefix is known
+// as soon as the first chunk has landed.
+__global__ void center_sample_kernel(int model, int D, const unsigned char* __restrict__ aos, size_t stride, uint32_t count, double* __restrict__ center) {
   __shared__ double sh[256];
-  for (int d = 0; d < D; d++) {
+  for (int d = 0; d < kMaxDim; d++) {
     double acc = 0.0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc += soa[(size_t)d * ld + i];
+    const bool on = d < D && centred_component(model, d);   // uniform
+    if (on) for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) acc += reinterpret_cast<const double*>(aos + (size_t)i * stride)[d];
     sh[threadIdx.x] = acc;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
-    if (threadIdx.x == 0) partials[(size_t)blockIdx.x * kMaxDim + d] = sh[0];
+    if (threadIdx.x == 0) {
+      double m = (on && count > 0) ? sh[0] / (double)count : 0.0;
+      if (!(m == m) || fabs(m) > 1e300) m = 0.0;
+      center[d] = m;
+    }
     __syncthreads();
   }
 }
-__global__ void center_final_kernel(int model, int D, uint32_t n, const double* __restrict__ partials, double* __restrict__ center) {
-  const int d = threadIdx.x;
-  if (d >= kMaxDim) return;
-  double acc = 0.0;
-  if (d < D && centred_component(model, d)) {
-    for (int b = 0; b < kCenterBlocks; b++) acc += partials[(size_t)b * kMaxDim + d];
-    acc = (n > 0) ? acc / (double)n : 0.0;
-    if (!(acc == acc) || fabs(acc) > 1e300) acc = 0.0;
+void launch_center_sample(int model, const unsigned char* aos_dev, size_t stride, uint32_t count, double* center_dev, cudaStream_t s) {
+  center_sample_kernel<<<1, 256, 0, s>>>(model, model_info(model).D, aos_dev, stride, count, center_dev);
+}
+
+// records [first, first + count) of the AoS buffer (record i at aos + i * stride); when pad_to > first + count the columns
+// [first + count, pad_to) are filled with NaN (padded data can never agree)
+__global__ void ingest_kernel(int D, const unsigned char* __restrict__ aos, size_t stride, uint32_t first, uint32_t count, uint32_t pad_to,
+                              const double* __restrict__ center, double* __restrict__ soa64, float* __restrict__ soa32, size_t ld) {
+  const size_t i = (size_t)first + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (size_t)first + count) {
+    const double* rec = reinterpret_cast<const double*>(aos + i * stride);
+    for (int d = 0; d < D; d++) {
+      const double v = rec[d];
+      soa64[(size_t)d * ld + i] = v;
+      soa32[(size_t)d * ld + i] = (float)(v - center[d]);
+    }
+  } else if (i < pad_to) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int d = 0; d < D; d++) { soa64[(size_t)d * ld + i] = nan; soa32[(size_t)d * ld + i] = __int_as_float(0x7fc00000); }
   }
-  center[d] = acc;
 }
-void launch_center(int model, const double* soa64, size_t ld, uint32_t n, double* partials, double* center_dev, cudaStream_t s) {
-  const int D = model_info(model).D;
-  center_partial_kernel<<<kCenterBlocks, 256, 0, s>>>(D, soa64, ld, n, partials);
-  center_final_kernel<<<1, 32, 0, s>>>(model, D, n, partials, center_dev);
-}
-__global__ void make32_kernel(int D, const double* __restrict__ soa64, const double* __restrict__ center, float* __restrict__ soa32, size_t ld) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ld) return;
-  for (int d = 0; d < D; d++) soa32[(size_t)d * ld + i] = (float)(soa64[(size_t)d * ld + i] - center[d]);
-}
-void launch_make32(int D, const double* soa64, const double* center_dev, float* soa32, size_t ld, cudaStream_t s) {
-  make32_kernel<<<(unsigned)((ld + 255) / 256), 256, 0, s>>>(D, soa64, center_dev, soa32, ld);
+void launch_ingest(int D, const unsigned char* aos_dev, size_t stride, uint32_t first, uint32_t count, uint32_t pad_to, const double* center_dev,
+                   double* soa64, float* soa32, size_t ld, cudaStream_t s) {
+  const size_t span = (size_t)(pad_to > first + count ? pad_to : first + count) - first;
+  if (span == 0) return;
+  ingest_kernel<<<(unsigned)((span + 255) / 256), 256, 0, s>>>(D, aos_dev, stride, first, count, pad_to, center_dev, soa64, soa32, ld);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -182,6 +179,46 @@ void launch_solve(const SolveArgs& a, const DataView& dv, const EstCfg& cfg, cud
   if (a.H == 0) return;
   const unsigned blocks = (a.H + 127) / 128;
 #define CALL(MM) solve_kernel<MM><<<blocks, 128, 0, s>>>(a, dv.soa64, dv.ld, dv.n, cfg)
+  LSQR_DISPATCH_MODEL(a.model, CALL)
+#undef CALL
+}
+
+// After the arg-max (and, sharded, its all-reduce): re-derives the winner's subset and parameters from the packed key ON
+// THE DEVICE -- every rank holds them whichever shard produced the winner -- and leaves key, valid count, subset and
+// parameters in one small record that the host fetches with a single copy.  The parameters also stay on the device for the
+// consensus-set pass that follows in compute().
+template <int M>
+__global__ void winner_kernel(SolveArgs a, const unsigned long long* __restrict__ key, const double* __restrict__ soa, size_t ld, uint32_t n, EstCfg cfg,
+                              WinnerRecord* __restrict__ out) {
+  constexpr int D = Model<M>::D, P = Model<M>::P, K = Model<M>::K;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const unsigned long long k = key[0];
+  out->key = k;
+  out->n_valid = key[1] & 0xFFFFFFFFull;
+  for (int j = 0; j < LSQR_MAX_SUBSET; j++) out->subset[j] = -1;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  for (int j = 0; j < LSQR_MAX_PARAMS; j++) out->params[j] = nan;
+  if ((k >> 32) == 0) return;
+  const uint64_t rel = 0xFFFFFFFFull - (k & 0xFFFFFFFFull);   // index relative to the request's first hypothesis
+  double prm[P];
+  int32_t sub[K];
+  bool ok = true;
+  if (a.sampler == 3) {
+    for (int j = 0; j < P; j++) prm[j] = a.params_in[(size_t)rel * P + j];
+    for (int j = 0; j < K; j++) sub[j] = -1;
+  } else {
+    if (a.sampler == 0) sample_subset<K>(a.first + rel, a.seed, n, sub);
+    else if (a.sampler == 1) unrank_lex<K>(a.first + rel, n, sub);
+    else for (int j = 0; j < K; j++) sub[j] = a.list[(size_t)rel * K + j];
+    double pts[K * D];
+    for (int j = 0; j < K; j++) for (int d = 0; d < D; d++) pts[j * D + d] = soa[(size_t)d * ld + (size_t)sub[j]];
+    ok = estimate<M>(pts, cfg, prm);
+  }
+  for (int j = 0; j < K; j++) out->subset[j] = sub[j];
+  if (ok) for (int j = 0; j < P; j++) out->params[j] = prm[j];
+}
+void launch_winner(const SolveArgs& a, const unsigned long long* key_dev, const DataView& dv, const EstCfg& cfg, WinnerRecord* out, cudaStream_t s) {
+#define CALL(MM) winner_kernel<MM><<<1, 32, 0, s>>>(a, key_dev, dv.soa64, dv.ld, dv.n, cfg, out)
   LSQR_DISPATCH_MODEL(a.model, CALL)
 #undef CALL
 }

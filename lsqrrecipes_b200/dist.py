@@ -124,14 +124,32 @@ def upload_replicated(engine, host, rank, world, group=None):
 
 
 def full_mask(mask, group=None):
-    """In sharded mode a rank's consensus set covers its own point shard (zeros elsewhere): OR over the ranks = the set
-    RANSAC::compute returns.  `mask`: uint8[n] from Engine.get_mask() / Engine.ransac()."""
+    """In sharded mode a rank writes only its own point shard of the consensus set (lsqr_b200.h, lsqr_set_shard): this
+    assembles the set RANSAC::compute returns on every rank.  `mask`: uint8[n] from Engine.get_mask() / Engine.ransac()."""
     import torch
     import torch.distributed as dist
 
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return mask
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi = point_shard(len(mask), rank, world)
+    mine = np.zeros_like(mask)
+    mine[lo:hi] = mask[lo:hi]
     dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
-    t = torch.from_numpy(np.ascontiguousarray(mask)).to(dev)
+    t = torch.from_numpy(mine).to(dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return t.cpu().numpy()
+
+
+def init_native(engine, rank, world, group=None):
+    """One process per GPU with the library's own NCCL communicator: rank 0 creates the unique id, torch.distributed only
+    carries its 128 bytes to the other ranks; every collective of the path is then an ncclAllReduce / ncclAllGather issued
+    by liblsqr_b200.so on its own stream (lsqr_ctx_init_nccl)."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return
+    ident = [engine.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ident, src=0, group=group)
+    engine.init_nccl(ident[0], rank, world)

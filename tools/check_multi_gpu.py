@@ -12,7 +12,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from lsqrrecipes_b200 import FP64, SAMPLE_LIST, Engine, synth  # noqa: E402
-from lsqrrecipes_b200.dist import full_mask, install_hooks, upload_replicated  # noqa: E402
+from lsqrrecipes_b200.dist import full_mask, init_native, install_hooks, upload_replicated  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -38,36 +38,43 @@ for name, n in (("plane3", 1_000_003), ("absor", 200_001), ("pivot", 50_000)):
     ok = ok and same
     print(f"rank {rank} {name}: gather == host upload: {same}", flush=True)
 # sharded requests (hypotheses partitioned over the ranks, refine moments summed over point shards) against the same
-# requests on an unsharded context: same winner, same consensus set, refit within the fp64 summation-order tolerance
+# requests on an unsharded context: same winner, same consensus set, refit within the fp64 summation-order tolerance.
+# Two ways of sharding: "native" = the library's own NCCL communicator (lsqr_ctx_init_nccl; the upload fetches every
+# world-th chunk and all-gathers the rest inside the library), "hooks" = caller-supplied torch.distributed collectives.
 from lsqrrecipes_b200 import FP32  # noqa: E402
-for name, n, H in (("plane3", 400_003, 200_000), ("sphere3", 200_001, 50_000)):
+for name, n, H in (("plane3", 400_003, 200_000), ("sphere3", 200_001, 50_000), ("circle2", 100_001, 20_000)):
     data, _ = synth.GENERATORS[name](n, seed=8)
     host = torch.from_numpy(data).pin_memory()
     out = []
-    for sharded in (False, True):
+    for mode in ("single", "native", "hooks"):
         eng = Engine(name, synth.DELTAS[name], device=local)
-        eng.set_stream(torch.cuda.current_stream().cuda_stream)
-        if sharded:
+        if mode == "hooks":
+            eng.set_stream(torch.cuda.current_stream().cuda_stream)
             install_hooks(eng, rank, world)
             upload_replicated(eng, host, rank, world)
+        elif mode == "native":
+            init_native(eng, rank, world)
+            eng.upload(data if rank % 2 else host.numpy())     # pageable on odd ranks, page-locked on even ones
         else:
             eng.upload(data)
         r = eng.score(count=H, precision=FP32, seed=11)
         cnt = eng.consensus(r["best_params"])
-        gather = full_mask if sharded else (lambda m: m)     # a rank holds the consensus bits of its own point shard
+        gather = full_mask if mode != "single" else (lambda m: m)     # a rank holds the consensus bits of its own point shard
         out.append((r["best_index"], r["best_count"], r["best_params"].copy(), cnt, gather(eng.get_mask()).copy(), eng.refine().copy()))
         c = eng.ransac(0.999, precision=FP32, seed=12)
-        out[-1] += (c["best_index"], c["fraction"], gather(c["mask"]).copy())
+        out[-1] += (c["best_index"], c["fraction"], gather(c["mask"]).copy(), c["params"].copy())
         eng.close()
-    a, b = out
-    checks = {"best_index": a[0] == b[0], "best_count": a[1] == b[1], "best_params": np.array_equal(a[2], b[2]), "consensus": a[3] == b[3],
-              "mask": np.array_equal(a[4], b[4]), "refit": np.allclose(a[5], b[5], rtol=1e-9, atol=1e-9), "compute_index": a[6] == b[6],
-              "compute_fraction": a[7] == b[7], "compute_mask": np.array_equal(a[8], b[8])}
-    same = all(checks.values())
-    if not same:
-        print(f"rank {rank} {name}: differs in {[k for k, v in checks.items() if not v]}: {a[0], a[1], a[3], a[6], a[7]} vs {b[0], b[1], b[3], b[6], b[7]}\n  {a[5]}\n  {b[5]}", flush=True)
-    ok = ok and same
-    print(f"rank {rank} {name}: sharded == unsharded: {same}", flush=True)
+    for mode, b in zip(("native", "hooks"), out[1:]):
+        a = out[0]
+        checks = {"best_index": a[0] == b[0], "best_count": a[1] == b[1], "best_params": np.array_equal(a[2], b[2]), "consensus": a[3] == b[3],
+                  "mask": np.array_equal(a[4], b[4]), "refit": a[5].shape == b[5].shape and np.allclose(a[5], b[5], rtol=1e-9, atol=1e-9),
+                  "compute_index": a[6] == b[6], "compute_fraction": a[7] == b[7], "compute_mask": np.array_equal(a[8], b[8]),
+                  "compute_params": a[9].shape == b[9].shape and np.allclose(a[9], b[9], rtol=1e-6, atol=1e-6)}
+        same = all(checks.values())
+        if not same:
+            print(f"rank {rank} {name} {mode}: differs in {[k for k, v in checks.items() if not v]}: {a[0], a[1], a[3], a[6], a[7]} vs {b[0], b[1], b[3], b[6], b[7]}\n  {a[5]}\n  {b[5]}", flush=True)
+        ok = ok and same
+        print(f"rank {rank} {name}: {mode} sharded == unsharded: {same}", flush=True)
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
