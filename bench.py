@@ -24,8 +24,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOP_PER_EVAL = {"plane3": 6, "sphere3": 8, "line2d": 4, "absor": 26}   # FFMA = 2 flop, minimal fused form
-LANEOPS_PER_EVAL = {"plane3": 3, "sphere3": 6, "line2d": 2, "absor": 15}
+# SURVEY.md 8d accounting: FMA-pipe lane-ops per evaluation in the minimal fused form with per-hypothesis constants hoisted
+# (an FFMA, FADD or FMUL each hold one lane of the pipe for one issue), and the same in flop (FFMA = 2).
+#   kD line: d FADD + 2 x (1 FMUL + (d-1) FFMA) + 1 FFMA = 3d + 1;  hypersphere: d FADD + 1 FMUL + (d-1) FFMA = 2d
+OPS_PER_EVAL = {"plane3": 3, "plane4": 4, "line2d": 2, "line2": 7, "line3": 10, "circle2": 4, "sphere3": 6, "sphere4": 8, "absor": 15, "ray": 12,
+                "pivot": 15, "dense5": 5, "dense6": 6, "usxw": 21, "uscp": 21}
+FLOP_PER_EVAL = {"plane3": 6, "plane4": 8, "line2d": 4, "line2": 10, "line3": 15, "circle2": 5, "sphere3": 8, "sphere4": 11, "absor": 26, "ray": 19,
+                 "pivot": 26, "dense5": 10, "dense6": 12, "usxw": 39, "uscp": 39}
+LANEOPS_PER_EVAL = OPS_PER_EVAL
 
 
 def parse():
@@ -34,13 +40,16 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="plane3", choices=list(FLOP_PER_EVAL))
+    ap.add_argument("--model", default="plane3", choices=["plane3", "sphere3", "line2d", "absor"])
     ap.add_argument("--points", type=int, default=10_000_000)
     ap.add_argument("--hyps", type=int, default=1_000_000, help="hypotheses per GPU")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--cpu-sample-hyps", type=int, default=0, help="hypotheses in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the secondary configurations (BASELINE.json configs[2..4], per-model scoring table)")
+    ap.add_argument("--comm", default="native", choices=["native", "hooks"],
+                    help="N > 1: collectives issued by the library itself (ncclAllReduce / ncclAllGather, lsqr_ctx_init_nccl) or torch.distributed hooks")
     return ap.parse_args()
 
 
@@ -209,6 +218,160 @@ def run_reference_arm(args):
     emit_line(line)
 
 
+def secondary_configs(device, peak_fma_per_s, hbm_peak, budget_s=75.0):
+    """BASELINE.json configs[2..4] and a per-model scoring table, time-boxed, single GPU: every number that README.md and
+    DESIGN.md quote next to the headline comes from here, i.e. from the driver's own run of this file."""
+    import torch
+    from lsqrrecipes_b200 import FP32, FP64, Engine, synth
+    t_start = time.perf_counter()
+    out = []
+
+    def left():
+        return budget_s - (time.perf_counter() - t_start)
+
+    def scoring(name, n, H, precision=FP32, reps=2, data=None):
+        if data is None:
+            data, _ = synth.GENERATORS[name](n)
+        eng = Engine(name, synth.DELTAS[name], device=device)
+        eng.upload(data)
+        eng.score(count=min(H, 131072), precision=precision, seed=1)
+        ms = [eng.score(count=H, precision=precision, seed=2 + i)["consensus_ms"] for i in range(reps)]
+        eng.close()
+        ev = float(H) * n / (min(ms) * 1e-3)
+        rec = {"model": name, "points": n, "hypotheses": H, "precision": "fp32" if precision == FP32 else "fp64", "consensus_ms": min(ms), "evals_per_s": ev}
+        if precision == FP32:
+            rec.update(ops_per_eval=OPS_PER_EVAL[name], frac=ev * OPS_PER_EVAL[name] / peak_fma_per_s,
+                       kernel="consensus_cb_kernel" if H >= 98304 else "consensus32_kernel")
+        return rec
+
+    def compute(name, n, ls_type=1, data=None):
+        """wall time of upload + RANSAC::compute(..., 0.999, &consensusSet), from page-locked and from pageable host memory"""
+        if data is None:
+            data, _ = synth.GENERATORS[name](n)
+        host = torch.from_numpy(data).pin_memory()
+        mask_pin = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
+        mask_pag = np.empty(n, dtype=np.uint8)
+        eng = Engine(name, synth.DELTAS[name], ls_type=ls_type, device=device)
+        res = {}
+        for kind, src, mask in (("pinned", host.numpy(), mask_pin), ("pageable", data, mask_pag)):
+            ms = []
+            for i in range(4):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                eng.upload_ptr(src.ctypes.data, n, data.shape[1] * 8)
+                r = eng.ransac(0.999, precision=FP32, seed=50 + i, mask_out=mask)
+                ms.append(1e3 * (time.perf_counter() - t0))
+            res[f"compute_ms_{kind}"] = float(np.median(ms[1:]))
+        st = eng.last_refine_stats()
+        eng.close()
+        res.update(model=name, points=n, tries=int(r["tries"]), inlier_fraction=float(r["fraction"]), n_params=int(len(r["params"])),
+                   lm_evaluations=int(st["lm_iterations"]), refine_pass_ms=st["kernel_ms"],
+                   refine_GBps=(st["bytes"] / (st["kernel_ms"] * 1e-3) / 1e9) if st["kernel_ms"] > 0 else None,
+                   refine_frac_of_hbm=(st["bytes"] / (st["kernel_ms"] * 1e-3) / 1e9 / hbm_peak) if st["kernel_ms"] > 0 else None)
+        return res
+
+    try:
+        # configs[2]: sphere RANSAC (4-point minimal) + Levenberg-Marquardt refine, 10 M points
+        data, _ = synth.GENERATORS["sphere3"](10_000_000)
+        rec = {"config": "configs[2] sphere3 + Levenberg-Marquardt, 10M points"}
+        rec.update(scoring("sphere3", 10_000_000, 262_144, data=data, reps=2))
+        rec.update(compute("sphere3", 10_000_000, 1, data=data))
+        out.append(rec)
+        del data
+        # configs[3]: absolute orientation over 1 M correspondences
+        data, _ = synth.GENERATORS["absor"](1_000_000)
+        rec = {"config": "configs[3] absolute orientation, 1M correspondences"}
+        rec.update(scoring("absor", 1_000_000, 1_000_000, data=data, reps=2))
+        rec.update(compute("absor", 1_000_000, 1, data=data))
+        out.append(rec)
+        # configs[1] in fp64 validation mode on a hypothesis slice
+        if left() > 20:
+            rec = {"config": "configs[1] plane3, fp64 validation mode slice"}
+            rec.update(scoring("plane3", 10_000_000, 65_536, precision=FP64, reps=1))
+            rec.update(ops_per_eval=9, note="as-written 3 DSUB + 4 DMUL + 2 DADD, no FMA (SURVEY.md 8d)")
+            out.append(rec)
+        # configs[4]: 65,536 independent small problems of 256 points, one thread block per problem
+        for name in ("line2d", "plane3"):
+            if left() < 10:
+                break
+            nprob, npts = 65_536, 256
+            rng = np.random.default_rng(17)
+            D = synth.GENERATORS[name](8, seed=1)[0].shape[1]
+            bases = [synth.GENERATORS[name](npts, seed=300 + i)[0] for i in range(64)]
+            data = np.concatenate([bases[i % 64] for i in range(nprob)]) + np.repeat(rng.uniform(-50, 50, (nprob, D)), npts, axis=0)
+            offsets = (np.arange(nprob + 1) * npts).astype(np.uint64)
+            eng = Engine(name, synth.DELTAS[name], device=device)
+            eng.ransac_batch(data[: 1024 * npts], offsets[:1025], prob=0.999, max_tries=2048, seed=1)
+            ms, wall = [], []
+            for i in range(3):
+                t0 = time.perf_counter()
+                r = eng.ransac_batch(data, offsets, prob=0.999, max_tries=2048, seed=11 + i)
+                wall.append(1e3 * (time.perf_counter() - t0))
+                ms.append(r["device_ms"])
+            eng.close()
+            out.append({"config": f"configs[4] 65536 x 256-point {name} problems, one CTA each", "model": name, "problems": nprob, "points_per_problem": npts,
+                        "kernel_ms": min(ms), "problems_per_s": nprob / (min(ms) * 1e-3), "wall_ms_pageable": float(np.median(wall)),
+                        "mean_inlier_fraction": float(r["counts"].mean() / npts)})
+        # scoring table: every estimator through the constant-bank kernel (131072 hypotheses x 1 M data)
+        table = []
+        for name in ("line2d", "line2", "line3", "circle2", "sphere4", "plane4", "ray", "pivot", "dense5", "dense6", "usxw", "uscp"):
+            if left() < 4:
+                break
+            table.append(scoring(name, 1_000_000, 131_072, reps=2))
+        out.append({"config": "scoring table: 131072 hypotheses x 1M data per estimator, fp32, frac = evals/s x SURVEY 8d lane-ops / measured FP32 lane rate",
+                    "models": table})
+    except Exception as e:  # a secondary measurement must never take the headline line down
+        out.append({"error": repr(e)})
+    return out
+
+
+def multi_gpu_parity(device, rank, world, comm):
+    """N > 1, before anything is timed: a sharded request (hypotheses partitioned over the ranks, consensus set and refine
+    sharded by point range, collectives by NCCL) must return what an unsharded context on the same GPU returns."""
+    import torch
+    import torch.distributed as dist
+    from lsqrrecipes_b200 import FP32, FP64, Engine, synth
+    from lsqrrecipes_b200.dist import full_mask, init_native, install_hooks, upload_replicated
+    checks = {}
+    for name, n, H in (("plane3", 1_000_003, 65_536), ("sphere3", 300_001, 65_536)):
+        data, _ = synth.GENERATORS[name](n, seed=8)
+        host = torch.from_numpy(data).pin_memory()
+        res = []
+        for sharded in (False, True):
+            eng = Engine(name, synth.DELTAS[name], device=device)
+            if sharded and comm == "native":
+                init_native(eng, rank, world)
+                eng.upload_ptr(host.data_ptr(), n, data.shape[1] * 8)
+            elif sharded:
+                eng.set_stream(torch.cuda.current_stream().cuda_stream)
+                install_hooks(eng, rank, world)
+                upload_replicated(eng, host, rank, world)
+            else:
+                eng.upload(data)
+            r = eng.score(count=H, precision=FP32, seed=11)
+            r64 = eng.score(count=4096, precision=FP64, seed=11)
+            cnt = eng.consensus(r["best_params"])
+            mask = eng.get_mask()
+            prm = eng.refine()
+            c = eng.ransac(0.999, precision=FP32, seed=12)
+            if sharded:
+                mask, cmask = full_mask(mask), full_mask(c["mask"])
+            else:
+                cmask = c["mask"]
+            res.append((r["best_index"], r["best_count"], r["best_params"].copy(), r64["best_index"], r64["best_count"], cnt, mask.copy(), prm.copy(),
+                        c["best_index"], c["fraction"], cmask.copy(), c["params"].copy()))
+            eng.close()
+        a, b = res
+        checks[name] = bool(a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2]) and a[3] == b[3] and a[4] == b[4] and a[5] == b[5]
+                            and np.array_equal(a[6], b[6]) and np.allclose(a[7], b[7], rtol=1e-9, atol=1e-9) and a[8] == b[8] and a[9] == b[9]
+                            and np.array_equal(a[10], b[10]) and a[11].shape == b[11].shape and np.allclose(a[11], b[11], rtol=1e-6, atol=1e-6))
+    t = torch.tensor([1 if all(checks.values()) else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return {"ok": bool(int(t.item()) == 1), "world": world, "comm": comm, "rank0": checks,
+            "what": "sharded == unsharded on every rank: fp32 and fp64 winner (index, count, parameters), consensus count and mask bit-exact, "
+                    "refit to 1e-9, compute() index / fraction / mask exact and parameters to 1e-6"}
+
+
 _JSON_FD = None
 
 
@@ -240,7 +403,7 @@ def main():
     import torch
     import torch.distributed as dist
     from lsqrrecipes_b200 import FP32, FP64, SAMPLE_PHILOX, Engine
-    from lsqrrecipes_b200.dist import install_hooks, upload_replicated
+    from lsqrrecipes_b200.dist import init_native, install_hooks, upload_replicated
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -257,10 +420,14 @@ def main():
 
     data, delta = make_data(model, N)
     host = torch.from_numpy(data).pin_memory()                 # host buffer for the e2e leg
+    parity = multi_gpu_parity(local, rank, world, args.comm) if world > 1 else None
     eng = Engine(model, delta, device=local)
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
     if world > 1:
-        install_hooks(eng, rank, world)
+        if args.comm == "native":
+            init_native(eng, rank, world)       # ncclAllReduce / ncclAllGather issued by liblsqr_b200.so itself
+        else:
+            install_hooks(eng, rank, world)
     eng.upload_ptr(host.data_ptr(), N, data.shape[1] * 8)       # untimed: inputs resident in HBM
 
     # measured pipe peaks for the roofline (same device, same moment)
@@ -331,9 +498,9 @@ def main():
     if not args.no_e2e:
         def upload_from_host():
             # N > 1: every rank needs all points; 1/world of the bytes per PCIe link, NCCL all-gather over NVLink for the rest
-            if world > 1:
+            if world > 1 and args.comm == "hooks":
                 upload_replicated(eng, host, rank, world)
-            else:
+            else:       # native: the library fetches every world-th chunk over this rank's PCIe link and all-gathers the round
                 eng.upload_ptr(host.data_ptr(), N, data.shape[1] * 8)
 
         def e2e_step(seed):
@@ -366,11 +533,25 @@ def main():
             upload_from_host()
             comp = eng.ransac(0.999, precision=precision, seed=100 + s, mask_out=mask_host)
             comp_ms.append(1e3 * (time.perf_counter() - t0))
-        tc = torch.tensor([float(np.median(comp_ms[1:]))], dtype=torch.float64, device="cuda")
+        # the same call with the reference's own container types: pageable std::vector-like memory in, pageable mask out
+        pag_ms = []
+        mask_pag = np.empty(N, dtype=np.uint8)
+        for s in range(4):
+            barrier()
+            t0 = time.perf_counter()
+            if world > 1 and args.comm == "hooks":
+                upload_replicated(eng, host, rank, world)
+            else:
+                eng.upload_ptr(data.ctypes.data, N, data.shape[1] * 8)
+            eng.ransac(0.999, precision=precision, seed=200 + s, mask_out=mask_pag)
+            pag_ms.append(1e3 * (time.perf_counter() - t0))
+        tc = torch.tensor([float(np.median(comp_ms[1:])), float(np.median(pag_ms[1:]))], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tc, op=dist.ReduceOp.MAX)
-        compute_e2e = {"ms": float(tc.item()), "desired_probability": 0.999, "tries": int(comp["tries"]), "inlier_fraction": float(comp["fraction"]),
-                       "device_ms": float(comp["device_ms"]), "n_params": int(len(comp["params"]))}
+        compute_e2e = {"ms": float(tc[0].item()), "ms_pageable": float(tc[1].item()), "desired_probability": 0.999, "tries": int(comp["tries"]),
+                       "inlier_fraction": float(comp["fraction"]), "device_ms": float(comp["device_ms"]), "n_params": int(len(comp["params"])),
+                       "what": "upload + RANSAC<T,S>::compute(parameters, estimator, data, 0.999, &consensusSet) through the C ABI, wall clock, max over ranks; "
+                               "ms: page-locked host buffers; ms_pageable: ordinary (std::vector-like) host memory for the data and the consensus set"}
         hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -399,6 +580,14 @@ def main():
         cpu = {"value": info["evals"] / info["seconds"], "unit": "evals/s", "cores": info["cores"], "kind": info["kind"],
                "sample": f"{n_hyps} hypotheses x {N} points, estimate()+agree() loop (RANSAC.hxx:217-249), OpenMP over hypotheses, {info['seconds']:.1f} s"}
 
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs and not args.no_e2e:
+        eng.close()
+        eng = None
+        del flush
+        torch.cuda.empty_cache()
+        configs = secondary_configs(local, max(ffma, ffma2), hbm_peak)
+
     if rank == 0:
         line = {
             "metric": "hypothesis x point agree() evals/sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
@@ -407,10 +596,11 @@ def main():
             "config": workload_config(model, N, Hper, world, args.precision, delta),
             "roofline": roofline, "roofline_refine": roofline_refine, "cpu_baseline": cpu, "e2e": e2e, "compute_e2e": compute_e2e,
             "gpu_launches": int(launches), "clocks": clk.summary(),
-            "best_count": int(r["best_count"]),
+            "best_count": int(r["best_count"]), "multi_gpu_parity": parity, "comm": (args.comm if world > 1 else None), "configs": configs,
         }
         emit_line(line)
-    eng.close()
+    if eng is not None:
+        eng.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -64,11 +64,11 @@ __device__ __forceinline__ f2 join(float lo, float hi) { f2 r; asm("mov.b64 %0, 
 //   PLANE3   (nx,ny,nz, delta - n.(a-c))      the kernels form s' = s + delta and test 0 <= s' < 2 delta (see count_carry)
 //   LINE2D   (nx,ny, -n.(a-c))                 |s| < delta (two FFMA2 per pair leave the ALU pipe as the limit either way; measured: the carry form is 4 % slower here)
 //   LINE2/3  (dir, a-c)
-//   CIRCLE/SPHERE (ctr-c, -m, w)  with  |d - r| < delta  <=>  |d^2 - m| < w,  m = r^2+delta^2, w = 2 r delta
+//   CIRCLE/SPHERE (ctr-c, -(r-delta)^2, 2^32 - bits(4 r delta)): t' = d^2 - (r-delta)^2, inlier <=> 0 <= t' < 4 r delta  (<=> |d - r| < delta)
 //   ABSOR    (R[9], R c1 + t - c2)
 //   RAY      (x - c)
 //   PIVOT    (tDRF, tW - c)
-//   DENSE n  (x[n], -1): a.x - b as n+1 FMAs over the (uncentred) augmented row
+//   DENSE n  (x[n], -1, delta): a.x - b + delta as n+1 FMAs over the (uncentred) augmented row
 //   USXW     (m_x R3(:,1), m_y R3(:,2), t3, t1 - c)
 //   USCP     (m_x R3(:,1), m_y R3(:,2), t3)
 template <int M> __device__ __forceinline__ void hoist32(const double* p, const double* c, const EstCfg& cfg, float* q);
@@ -91,13 +91,20 @@ template <> __device__ __forceinline__ void hoist32<LINE2>(const double* p, cons
 template <> __device__ __forceinline__ void hoist32<LINE3>(const double* p, const double* c, const EstCfg&, float* q) {
   for (int i = 0; i < 3; i++) { q[i] = (float)p[i]; q[3 + i] = (float)(p[3 + i] - c[i]); }
 }
+// |d - r| < delta  <=>  (r - delta)^2 <= d^2 < (r + delta)^2  <=>  0 <= t' < 4 r delta  with  t' = d^2 - (r - delta)^2: the chain
+// starts at -(r - delta)^2 and the datum is an inlier iff bits(t') < bits(4 r delta) as unsigned integers (count_carry; the
+// threshold is per hypothesis).  r < delta: no lower bound, t' = d^2 + 1 against (r + delta)^2 + 1.  A threshold that is not
+// positive (negative delta: SphereParametersEstimator.hxx:20 keeps its sign) is stored as 0: nothing agrees.
 template <int DIM> __device__ __forceinline__ void hoist_sphere(const double* p, const double* c, const EstCfg& cfg, float* q) {
   for (int i = 0; i < DIM; i++) q[i] = (float)(p[i] - c[i]);
   const double r = p[DIM], dl = cfg.delta;
-  double m, w;
-  if (r >= dl) { m = r * r + dl * dl; w = 2.0 * r * dl; }
-  else { const double hi = (r + dl) * (r + dl); m = (hi - 1.0) * 0.5; w = (hi + 1.0) * 0.5; }  // interval (-1, hi): d^2 >= 0 has no lower bound
-  q[DIM] = (float)(-m); q[DIM + 1] = (float)w;
+  double start, width;
+  if (r >= dl) { start = -(r - dl) * (r - dl); width = 4.0 * r * dl; }
+  else { start = 1.0; width = (r + dl) * (r + dl) + 1.0; }
+  q[DIM] = (float)start;
+  const float wf = (float)width;
+  // stored ready for count_carry: 2^32 - bits(window); 0 = nothing agrees (window not positive, or NaN)
+  q[DIM + 1] = __uint_as_float((wf > 0.0f) ? 0u - __float_as_uint(wf) : 0u);
 }
 template <> __device__ __forceinline__ void hoist32<CIRCLE2>(const double* p, const double* c, const EstCfg& cfg, float* q) { hoist_sphere<2>(p, c, cfg, q); }
 template <> __device__ __forceinline__ void hoist32<SPHERE3>(const double* p, const double* c, const EstCfg& cfg, float* q) { hoist_sphere<3>(p, c, cfg, q); }
@@ -115,12 +122,13 @@ template <> __device__ __forceinline__ void hoist32<PIVOT>(const double* p, cons
   for (int i = 0; i < 3; i++) { q[i] = (float)p[i]; q[3 + i] = (float)(p[3 + i] - c[9 + i]); }
 }
 
-template <int N> __device__ __forceinline__ void hoist_dense(const double* p, float* q) {
+template <int N> __device__ __forceinline__ void hoist_dense(const double* p, const EstCfg& cfg, float* q) {
   for (int i = 0; i < N; i++) q[i] = (float)p[i];
   q[N] = -1.0f;
+  q[N + 1] = (float)cfg.delta;   // the chain starts at +delta: s' = a.x - b + delta, inlier <=> bits(s') < bits(2 delta)
 }
-template <> __device__ __forceinline__ void hoist32<DENSE5>(const double* p, const double*, const EstCfg&, float* q) { hoist_dense<5>(p, q); }
-template <> __device__ __forceinline__ void hoist32<DENSE6>(const double* p, const double*, const EstCfg&, float* q) { hoist_dense<6>(p, q); }
+template <> __device__ __forceinline__ void hoist32<DENSE5>(const double* p, const double*, const EstCfg& cfg, float* q) { hoist_dense<5>(p, cfg, q); }
+template <> __device__ __forceinline__ void hoist32<DENSE6>(const double* p, const double*, const EstCfg& cfg, float* q) { hoist_dense<6>(p, cfg, q); }
 
 template <> __device__ __forceinline__ void hoist32<USXW>(const double* p, const double* c, const EstCfg&, float* q) {
   for (int i = 0; i < 6; i++) q[i] = (float)p[11 + i];
@@ -131,6 +139,9 @@ template <> __device__ __forceinline__ void hoist32<USCP>(const double* p, const
   for (int i = 0; i < 6; i++) q[i] = (float)p[8 + i];
   for (int i = 0; i < 3; i++) q[6 + i] = (float)p[i];
 }
+
+// slot of the per-hypothesis counting window among the hoisted constants (-1: the window is 2 delta for every hypothesis)
+template <int M> constexpr int thr_slot() { return M == CIRCLE2 ? 3 : (M == SPHERE3 ? 4 : (M == SPHERE4 ? 5 : -1)); }
 
 template <int M>
 __global__ void hoist32_kernel(const double* __restrict__ hyp64, size_t hld, uint32_t H, DataView dv, EstCfg cfg, float* __restrict__ hyp32) {
@@ -151,7 +162,7 @@ __global__ void hoist32_kernel(const double* __restrict__ hyp64, size_t hld, uin
   for (int g = 0; g < (Q + 3) / 4; g++) {
     float v[4];
 #pragma unroll
-    for (int c = 0; c < 4; c++) v[c] = (ok && 4 * g + c < Q) ? q[4 * g + c] : __int_as_float(0x7fc00000);
+    for (int c = 0; c < 4; c++) v[c] = (ok && 4 * g + c < Q) ? q[4 * g + c] : ((4 * g + c == thr_slot<M>()) ? 0.0f : __int_as_float(0x7fc00000));   // degenerate: NaN constants, empty window
     out[(size_t)g * hld + h] = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
@@ -251,19 +262,19 @@ template <> struct Eval<LINE3> {
   __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { return line_signed<3>(q, x, t); }
 };
-// d^2 - m: the sphere test |d - r| < delta becomes |d^2 - m| < w with a per-hypothesis threshold w (q[DIM + 1])
+// t' = d^2 - (r - delta)^2 (chain start q[DIM]); per-hypothesis window q[DIM + 1] = 4 r delta (see hoist_sphere)
 template <int DIM> __device__ __forceinline__ f2 sphere_t(const f2* q, const f2* x) {
-  f2 t = q[DIM];  // -m
+  f2 t = q[DIM];
 #pragma unroll
   for (int i = 0; i < DIM; i++) { const f2 w = sub2(x[i], q[i]); t = fma2(w, w, t); }
   return t;
 }
 template <int DIM> struct EvalSphere {
   static constexpr bool kHasAbsForm = true;
-  static constexpr int kThr = DIM + 1;
-  static constexpr bool kShifted = false;
+  static constexpr int kThr = DIM + 1;      // per-hypothesis window, stored as 2^32 - bits(window)
+  static constexpr bool kShifted = true;    // dist() is already the shifted residual
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return sphere_t<DIM>(q, x); }
-  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2&) { const f2 t = sphere_t<DIM>(q, x); return sub2(mul2(t, t), mul2(q[DIM + 1], q[DIM + 1])); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2&) { return sphere_t<DIM>(q, x); }
 };
 template <> struct Eval<CIRCLE2> : EvalSphere<2> {};
 template <> struct Eval<SPHERE3> : EvalSphere<3> {};
@@ -316,9 +327,10 @@ template <> struct Eval<PIVOT> {
   }
 };
 
-// |a.x - b| < delta: n+1 FMAs, the last constant is -1 (DenseLinearEquationSystemParametersEstimator.hxx:111-119)
+// |a.x - b| < delta in the shifted form: n+1 FMAs, q[N] = -1 multiplies the right-hand side, the chain starts at q[N+1] = delta
+// (DenseLinearEquationSystemParametersEstimator.hxx:111-119)
 template <int N> __device__ __forceinline__ f2 dense_dist(const f2* q, const f2* x) {
-  f2 s = mul2(q[N], x[N]);
+  f2 s = fma2(q[N], x[N], q[N + 1]);
 #pragma unroll
   for (int i = N - 1; i >= 0; i--) s = fma2(q[i], x[i], s);
   return s;
@@ -326,16 +338,16 @@ template <int N> __device__ __forceinline__ f2 dense_dist(const f2* q, const f2*
 template <> struct Eval<DENSE5> {
   static constexpr bool kHasAbsForm = true;
   static constexpr int kThr = -1;   // threshold = delta for every hypothesis
-  static constexpr bool kShifted = false;
+  static constexpr bool kShifted = true;
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return dense_dist<5>(q, x); }
-  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = sub2(dist(q, x), t.delta); return fma2(s, s, t.neg_delta2); }
 };
 template <> struct Eval<DENSE6> {
   static constexpr bool kHasAbsForm = true;
   static constexpr int kThr = -1;   // threshold = delta for every hypothesis
-  static constexpr bool kShifted = false;
+  static constexpr bool kShifted = true;
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return dense_dist<6>(q, x); }
-  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = sub2(dist(q, x), t.delta); return fma2(s, s, t.neg_delta2); }
 };
 
 // cross-wire: e = R2 (u c1 + v c2 + t3) + t2 - t1, |e|^2 - delta^2   (21 FMA-pipe operations)
@@ -385,6 +397,11 @@ template <int M> __device__ __forceinline__ float hyp_thr(const f2* q, float del
 template <int M> __device__ __forceinline__ float hyp_thr(const float* q, float delta) {
   if constexpr (Eval<M>::kThr >= 0) return q[Eval<M>::kThr];
   else return delta;
+}
+// 2^32 - bits(window) for count_carry: the window is 2 delta for every hypothesis, or the hypothesis' own (hypersphere family)
+template <int M, class Q> __device__ __forceinline__ uint32_t hyp_negk(const Q* q, uint32_t negk_delta) {
+  if constexpr (Eval<M>::kThr >= 0) return __float_as_uint(hyp_thr<M>(q, 0.f));
+  else return negk_delta;
 }
 // FSETP + predicated IADD on two residuals, written in PTX so that ptxas keeps the 2-instruction form.
 __device__ __forceinline__ void count_abs_lt(uint32_t& cnt, f2 s, float delta) {
@@ -497,7 +514,7 @@ __global__ void __launch_bounds__(THREADS) consensus32_kernel(const float* __res
         for (int u = 0; u < PPI; u++) {
           // the predicate must be the constant-bank kernel's: shifted models count through the carry chain, models with a
           // per-hypothesis threshold always take the |.| < thr form
-          if constexpr (Eval<M>::kShifted) count_carry(out[r], Eval<M>::dist(q[r], x[u]), negk);
+          if constexpr (Eval<M>::kShifted) count_carry(out[r], Eval<M>::dist(q[r], x[u]), hyp_negk<M>(q[r], negk));
           else if (Eval<M>::kHasAbsForm && (Eval<M>::kThr >= 0 || (r % 3) != 0)) count_abs_lt(cnt[r], Eval<M>::dist(q[r], x[u]), hyp_thr<M>(q[r], thr.fdelta));
           else count_sign(cnt[r], Eval<M>::signed_(q[r], x[u], thr));
         }
@@ -509,7 +526,7 @@ __global__ void __launch_bounds__(THREADS) consensus32_kernel(const float* __res
   for (int r = 0; r < R; r++) {
     const uint32_t h = hbase + r * THREADS + tid;
     // NaN padding counts as outliers; delta = 0 (bits(2 delta) = 0: no carry ever) admits nothing, like |s| < 0
-    if constexpr (Eval<M>::kShifted) cnt[r] = negk ? (t1 - t0) * (uint32_t)TILE - (uint32_t)(out[r] >> 32) : 0u;
+    if constexpr (Eval<M>::kShifted) cnt[r] = hyp_negk<M>(q[r], negk) ? (t1 - t0) * (uint32_t)TILE - (uint32_t)(out[r] >> 32) : 0u;
     if (h < H && cnt[r]) atomicAdd(&counts[h], cnt[r]);
   }
 }
@@ -603,8 +620,9 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
 #pragma unroll
       for (int j = 0; j < Q; j++) q[j] = splat(qf[r][j]);
       if constexpr (kCarry) {
+        const uint32_t nk = hyp_negk<M>(qf[r], negk);
 #pragma unroll
-        for (int u = 0; u < PPI; u++) count_carry(out[r], Eval<M>::dist(q, x[u]), negk);
+        for (int u = 0; u < PPI; u++) count_carry(out[r], Eval<M>::dist(q, x[u]), nk);
       } else if constexpr (kRaw) {
         const float th = hyp_thr<M>(qf[r], thr.fdelta);
 #pragma unroll
@@ -625,7 +643,7 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
   for (int r = 0; r < R; r++) {
     const uint32_t h = hbase + r * THREADS + tid;
     // NaN padding counts as outliers; delta = 0 (bits(2 delta) = 0: no carry ever) admits nothing, like |s| < 0
-    if constexpr (kCarry) cnt[r] = negk ? (uint32_t)(g1 - g0) * (2u * PPI) - (uint32_t)(out[r] >> 32) : 0u;
+    if constexpr (kCarry) cnt[r] = hyp_negk<M>(qf[r], negk) ? (uint32_t)(g1 - g0) * (2u * PPI) - (uint32_t)(out[r] >> 32) : 0u;
     if constexpr (kRaw) cnt[r] = cb_raw_decode(cnt[r]);
     if (h < H && cnt[r]) atomicAdd(&counts[h], cnt[r]);
   }

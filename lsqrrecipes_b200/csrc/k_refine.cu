@@ -334,6 +334,11 @@ __global__ void __launch_bounds__(MMCfg<M, LM>::THREADS, 1) mask_moments_kernel(
     for (int j = 0; j < P; j++) prm[j] = params_dev[j];
     prepare<M>(prm, hq);
   }
+  // the shift c of the centred components, once per thread (a load inside the inlier branch would put a global-memory latency
+  // on every row's critical path)
+  double ctr[D];
+#pragma unroll
+  for (int d = 0; d < D; d++) ctr[d] = centred_comp(M, d) ? dv.center[d] : 0.0;
   double lmx[LM ? Mom<M>::NPLM : 1] = {0};
   bool active = true;
   if (LM) {
@@ -400,7 +405,7 @@ __global__ void __launch_bounds__(MMCfg<M, LM>::THREADS, 1) mask_moments_kernel(
       if (in) {
         double q[D];
 #pragma unroll
-        for (int d = 0; d < D; d++) q[d] = centred_comp(M, d) ? x[u][d] - dv.center[d] : x[u][d];
+        for (int d = 0; d < D; d++) q[d] = centred_comp(M, d) ? x[u][d] - ctr[d] : x[u][d];
         if (LM) {
           if constexpr (M == CIRCLE2) acc_sphere_lm<2>(q, lmx, acc);
           if constexpr (M == SPHERE3) acc_sphere_lm<3>(q, lmx, acc);

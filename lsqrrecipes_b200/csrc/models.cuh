@@ -29,8 +29,8 @@ template <> struct Model<ABSOR>   { static constexpr int D = 6,  P = 7, K = 3, H
 template <> struct Model<RAY>     { static constexpr int D = 6,  P = 3, K = 2, HQ = 3,  Q32 = 3;  };
 template <> struct Model<PIVOT>   { static constexpr int D = 12, P = 6, K = 3, HQ = 6,  Q32 = 6;  };
 // DenseLinearEquationSystemParametersEstimator<double, n>: datum = AugmentedRow (n coefficients, right-hand side)
-template <> struct Model<DENSE5>  { static constexpr int D = 6,  P = 5, K = 5, HQ = 5,  Q32 = 6;  };
-template <> struct Model<DENSE6>  { static constexpr int D = 7,  P = 6, K = 6, HQ = 6,  Q32 = 7;  };
+template <> struct Model<DENSE5>  { static constexpr int D = 6,  P = 5, K = 5, HQ = 5,  Q32 = 7;  };
+template <> struct Model<DENSE6>  { static constexpr int D = 7,  P = 6, K = 6, HQ = 6,  Q32 = 8;  };
 // SingleUnknownPointTargetUSCalibrationParametersEstimator (cross-wire phantom): datum = [R2 (9), t2 (3), u, v],
 // parameters [t1, t3, omega_z, omega_y, omega_x, m_x, m_y, m_x R3(:,1), m_y R3(:,2), R3(:,3)]
 template <> struct Model<USXW>    { static constexpr int D = 14, P = 20, K = 4, HQ = 12, Q32 = 12; };
@@ -52,8 +52,8 @@ __host__ __device__ inline ModelInfo model_info(int m) {
     case ABSOR:   return {6, 7, 3, 12, 12};
     case RAY:     return {6, 3, 2, 3, 3};
     case PIVOT:   return {12, 6, 3, 6, 6};
-    case DENSE5:  return {6, 5, 5, 5, 6};
-    case DENSE6:  return {7, 6, 6, 6, 7};
+    case DENSE5:  return {6, 5, 5, 5, 7};
+    case DENSE6:  return {7, 6, 6, 6, 8};
     case USXW:    return {14, 20, 4, 12, 12};
     case USCP:    return {17, 17, 3, 9, 9};
     case SPHERE4: return {4, 5, 5, 5, 6};
