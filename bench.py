@@ -258,8 +258,7 @@ def secondary_configs(device, peak_fma_per_s, hbm_peak, budget_s=75.0):
             for i in range(4):
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                eng.upload_ptr(src.ctypes.data, n, data.shape[1] * 8)
-                r = eng.ransac(0.999, precision=FP32, seed=50 + i, mask_out=mask)
+                r = eng.compute(src.ctypes.data, 0.999, precision=FP32, seed=50 + i, mask_out=mask, n=n, stride_bytes=data.shape[1] * 8)
                 ms.append(1e3 * (time.perf_counter() - t0))
             res[f"compute_ms_{kind}"] = float(np.median(ms[1:]))
         st = eng.last_refine_stats()
@@ -530,8 +529,11 @@ def main():
         for s in range(4):
             barrier()
             t0 = time.perf_counter()
-            upload_from_host()
-            comp = eng.ransac(0.999, precision=precision, seed=100 + s, mask_out=mask_host)
+            if world > 1 and args.comm == "hooks":
+                upload_from_host()
+                comp = eng.ransac(0.999, precision=precision, seed=100 + s, mask_out=mask_host)
+            else:       # lsqr_compute: upload, first scoring round, consensus set and refine in one pipelined call
+                comp = eng.compute(host.data_ptr(), 0.999, precision=precision, seed=100 + s, mask_out=mask_host, n=N, stride_bytes=data.shape[1] * 8)
             comp_ms.append(1e3 * (time.perf_counter() - t0))
         # the same call with the reference's own container types: pageable std::vector-like memory in, pageable mask out
         pag_ms = []
@@ -541,16 +543,16 @@ def main():
             t0 = time.perf_counter()
             if world > 1 and args.comm == "hooks":
                 upload_replicated(eng, host, rank, world)
+                eng.ransac(0.999, precision=precision, seed=200 + s, mask_out=mask_pag)
             else:
-                eng.upload_ptr(data.ctypes.data, N, data.shape[1] * 8)
-            eng.ransac(0.999, precision=precision, seed=200 + s, mask_out=mask_pag)
+                eng.compute(data, 0.999, precision=precision, seed=200 + s, mask_out=mask_pag)
             pag_ms.append(1e3 * (time.perf_counter() - t0))
         tc = torch.tensor([float(np.median(comp_ms[1:])), float(np.median(pag_ms[1:]))], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tc, op=dist.ReduceOp.MAX)
         compute_e2e = {"ms": float(tc[0].item()), "ms_pageable": float(tc[1].item()), "desired_probability": 0.999, "tries": int(comp["tries"]),
                        "inlier_fraction": float(comp["fraction"]), "device_ms": float(comp["device_ms"]), "n_params": int(len(comp["params"])),
-                       "what": "upload + RANSAC<T,S>::compute(parameters, estimator, data, 0.999, &consensusSet) through the C ABI, wall clock, max over ranks; "
+                       "what": "RANSAC<T,S>::compute(parameters, estimator, data, 0.999, &consensusSet) through the C ABI with the data in host memory (lsqr_compute), wall clock, max over ranks; "
                                "ms: page-locked host buffers; ms_pageable: ordinary (std::vector-like) host memory for the data and the consensus set"}
         hbm_peak = None
         try:

@@ -66,17 +66,28 @@ class RANSAC {
     }
     lsqr_ctx* ctx = b200::configured(d, data.size() >= b200Options().multiGpuMinData);
     if (!ctx) return 0;
+    // the records as the engine reads them: the caller's own array when the datum's leading doubles are the engine's datum,
+    // else (members separated by padding, e.g. the ultrasound-calibration records) a packed copy made here
     double probe[32];
+    std::vector<double> packed;
+    const void* records = data.data();
+    size_t stride = sizeof(T);
     if (!data.empty() && paramEstimator->b200PackDatum(data[0], probe)) {
-      // record layout differs from the engine's datum: pack on the host, then upload packed doubles
       int dim = 0;
       lsqr_model_info(d.model, &dim, NULL, NULL);
-      std::vector<double> packed(data.size() * static_cast<size_t>(dim));
+      packed.resize(data.size() * static_cast<size_t>(dim));
       for (size_t i = 0; i < data.size(); i++) paramEstimator->b200PackDatum(data[i], &packed[i * dim]);
-      if (!b200::check(ctx, lsqr_upload(ctx, packed.data(), data.size(), sizeof(double) * dim))) return 0;
-    } else if (!b200::check(ctx, lsqr_upload(ctx, data.data(), data.size(), sizeof(T)))) return 0;
+      records = packed.data();
+      stride = sizeof(double) * dim;
+    }
     lsqr_compute_result r;
-    const int rc = exhaustive ? lsqr_ransac_exhaustive(ctx, LSQR_FP64, NULL, &r) : lsqr_ransac(ctx, prob, b200Options().precision, b200Options().seed, NULL, &r);
+    int rc;
+    if (exhaustive) {
+      if (!b200::check(ctx, lsqr_upload(ctx, records, data.size(), stride))) return 0;
+      rc = lsqr_ransac_exhaustive(ctx, LSQR_FP64, NULL, &r);
+    } else {   // upload, first scoring round, consensus set and refine in one pipelined call
+      rc = lsqr_compute(ctx, records, data.size(), stride, prob, b200Options().precision, b200Options().seed, NULL, &r);
+    }
     if (!b200::check(ctx, rc)) return 0;
     if (r.best_count == 0) return 0;
     if (consensusSet) {

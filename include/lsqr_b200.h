@@ -197,6 +197,13 @@ typedef struct lsqr_compute_result {
  * (N < k, prob outside (0,1)) returns LSQR_OK with fraction = 0, n_params = 0. */
 int lsqr_ransac(lsqr_ctx* ctx, double prob, int precision, uint64_t seed, uint8_t* out_mask_bytes,
                 lsqr_compute_result* res);
+/* The same call with the data still in host memory -- what RANSAC<T,S>::compute receives: lsqr_upload + lsqr_ransac in one
+ * pass with identical results (same hypotheses, counts, consensus set and parameters).  The minimal subsets of the first
+ * round are drawn on the host with the device's sampler and their records fetched first, so that every chunk of the data is
+ * scored against the first 256 hypotheses while the chunks behind it are still crossing PCIe (and, on a multi-GPU context,
+ * NVLink).  Invalid input (n < k, prob outside (0,1)) returns LSQR_OK with fraction = 0, n_params = 0 and uploads nothing. */
+int lsqr_compute(lsqr_ctx* ctx, const void* aos, size_t n, size_t stride_bytes, double prob, int precision, uint64_t seed,
+                 uint8_t* out_mask_bytes, lsqr_compute_result* res);
 /* The brute-force overload, RANSAC.h:111-113 / RANSAC.hxx:150-249: all C(N,k) subsets in
  * lexicographic order, first maximum wins. */
 int lsqr_ransac_exhaustive(lsqr_ctx* ctx, int precision, uint8_t* out_mask_bytes, lsqr_compute_result* res);

@@ -86,6 +86,7 @@ def load_library():
         "lsqr_refine": (c.c_int, [c.c_void_p, c.c_int, _dp, c.POINTER(c.c_int)]),
         "lsqr_ransac": (c.c_int, [c.c_void_p, c.c_double, c.c_int, c.c_uint64, _u8p, c.POINTER(ComputeResult)]),
         "lsqr_ransac_exhaustive": (c.c_int, [c.c_void_p, c.c_int, _u8p, c.POINTER(ComputeResult)]),
+        "lsqr_compute": (c.c_int, [c.c_void_p, c.c_void_p, c.c_size_t, c.c_size_t, c.c_double, c.c_int, c.c_uint64, _u8p, c.POINTER(ComputeResult)]),
         "lsqr_ransac_batch": (c.c_int, [c.c_void_p, _dp, _u64p, c.c_uint64, c.c_int, c.c_double, c.c_uint32, c.c_uint64, _dp, _u32p, _u8p, _dp]),
         "lsqr_estimate": (c.c_int, [c.c_void_p, _dp, c.c_size_t, _dp, c.POINTER(c.c_int)]),
         "lsqr_agree": (c.c_int, [c.c_void_p, _dp, _dp, c.c_size_t, _u8p]),
@@ -108,6 +109,7 @@ EXPORTED_SYMBOLS = [
     "lsqr_refine", "lsqr_ransac", "lsqr_ransac_exhaustive", "lsqr_ransac_batch", "lsqr_estimate", "lsqr_agree", "lsqr_least_squares",
     "lsqr_microbench_fma", "lsqr_last_refine_stats", "lsqr_weighted_least_squares",
     "lsqr_device_count", "lsqr_ctx_create_multi", "lsqr_ctx_world", "lsqr_nccl_unique_id", "lsqr_ctx_init_nccl", "lsqr_get_mask_bits",
+    "lsqr_compute",
 ]
 
 
@@ -266,6 +268,20 @@ class Engine:
         mask = mask_out if mask_out is not None else (np.zeros(self.n, dtype=np.uint8) if want_mask else None)
         r = ComputeResult()
         self._ck(self.lib.lsqr_ransac(self.h, float(prob), precision, seed, _ptr(mask, _u8p), ctypes.byref(r)))
+        return self._result(r, mask)
+
+    def compute(self, data, prob, precision=FP32, seed=0, want_mask=True, mask_out=None, n=None, stride_bytes=None):
+        """RANSAC<T,S>::compute with the data still on the host (lsqr_compute): upload and first scoring round overlapped.
+        data: float64 array [n, dim], or a raw host pointer (int) together with n and stride_bytes."""
+        if isinstance(data, int):
+            ptr = ctypes.c_void_p(data)
+        else:
+            d = np.ascontiguousarray(data, dtype=np.float64).reshape(-1, self.dim)
+            n, stride_bytes, ptr = d.shape[0], self.dim * 8, d.ctypes.data_as(ctypes.c_void_p)
+        self.n = n
+        mask = mask_out if mask_out is not None else (np.zeros(n, dtype=np.uint8) if want_mask else None)
+        r = ComputeResult()
+        self._ck(self.lib.lsqr_compute(self.h, ptr, n, stride_bytes, float(prob), precision, seed, _ptr(mask, _u8p), ctypes.byref(r)))
         return self._result(r, mask)
 
     def ransac_exhaustive(self, precision=FP64, want_mask=True):

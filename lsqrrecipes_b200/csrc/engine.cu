@@ -174,7 +174,13 @@ struct DataSet {
   bool bytes_valid = false;    // ctx->mask_dev holds the consensus set of this data set, one byte per datum (own shard)
   DataView view() const {
     DataView v;
-    v.soa64 = soa64; v.soa32 = soa32; v.ld = ld; v.n = n; v.center = center_dev;
+    v.soa64 = soa64; v.soa32 = soa32; v.ld = ld; v.span = ld; v.n = n; v.center = center_dev;
+    return v;
+  }
+  // columns [lo, hi) of the data set (lo a multiple of 1024); `to_end`: the view runs to the NaN-padded end of the arrays
+  DataView range(size_t lo, size_t hi, bool to_end) const {
+    DataView v = view();
+    v.soa64 = soa64 + lo; v.soa32 = soa32 + lo; v.n = (uint32_t)(hi - lo); v.span = to_end ? ld - lo : hi - lo;
     return v;
   }
 };
@@ -221,6 +227,8 @@ struct lsqr_ctx {
   uint64_t* bt_off = nullptr; size_t bt_off_cap = 0;
   double* bt_prm = nullptr; size_t bt_prm_cap = 0;
   uint32_t* bt_cnt = nullptr; size_t bt_cnt_cap = 0;
+  unsigned char* gather_dev = nullptr; size_t gather_cap = 0;        // compute(): records of the first round's minimal subsets
+  unsigned char* gather_pin = nullptr; size_t gather_pin_cap = 0;
   uint8_t* mask_dev = nullptr; size_t mask_dev_cap = 0;   // consensus set, one byte per datum (device)
   uint8_t* mask_pin = nullptr; size_t mask_pin_cap = 0;   // pinned bounce buffer for its download
   // upload pipeline
@@ -348,7 +356,10 @@ bool is_pinned(const void* p) {
 //   * single context: chunk c is copied on the copy stream and transposed on the compute stream as soon as it has landed;
 //   * natively sharded context (ctx->comm): rank r copies chunks r, r + W, r + 2W, ... of the host buffer and round j of
 //     chunks [jW, (j+1)W) is completed by an in-place all-gather over NVLink before it is transposed.
-int upload_to(lsqr_ctx* ctx, DataSet& ds, const void* aos, size_t n, size_t stride, bool on_device, bool allow_sharded) {
+// after_round(lo, hi, first, last): called after the transposition of records [lo, hi) has been enqueued (compute() scores its
+// first round of hypotheses against every range as it lands)
+using RoundFn = std::function<int(size_t, size_t, bool, bool)>;
+int upload_to(lsqr_ctx* ctx, DataSet& ds, const void* aos, size_t n, size_t stride, bool on_device, bool allow_sharded, const RoundFn* after_round = nullptr) {
   if (ctx->model < 0) return fail(ctx, LSQR_ERR_STATE, "lsqr_set_estimator must be called before uploading data");
   const ModelInfo mi = model_info(ctx->model);
   if (n > 0xFFFFFFF0ull) return fail(ctx, LSQR_ERR_ARG, "too many data records");
@@ -372,7 +383,7 @@ int upload_to(lsqr_ctx* ctx, DataSet& ds, const void* aos, size_t n, size_t stri
   const int W = sharded ? ctx->world : 1;
   // chunk: at least the centre sample, ~1/8 of a rank's share, between 256 KB and 16 MB
   size_t chunk_rec = std::max<size_t>(kCenterSample, std::min<size_t>((16u << 20) / stride, std::max<size_t>((256u << 10) / stride, (n / W + 7) / 8)));
-  chunk_rec = round_up(chunk_rec, 32);
+  chunk_rec = round_up(chunk_rec, 1024);   // rounds start on tile boundaries of every consensus kernel
   const size_t chunk_bytes = chunk_rec * stride;
   const size_t n_chunks = (n + chunk_rec - 1) / chunk_rec, rounds = (n_chunks + W - 1) / W;
   if (int rc = ensure(ctx, &ctx->staging, &ctx->staging_cap, rounds * W * chunk_bytes)) return rc;
@@ -418,9 +429,39 @@ int upload_to(lsqr_ctx* ctx, DataSet& ds, const void* aos, size_t n, size_t stri
     const bool last = j + 1 == rounds;
     launch_ingest(mi.D, ctx->staging, stride, (uint32_t)r_lo, (uint32_t)(r_hi - r_lo), last ? pad_to : (uint32_t)r_hi, ds.center_dev, ds.soa64, ds.soa32, ds.ld, s);
     ctx->launches++;
+    if (after_round) if (int rc = (*after_round)(r_lo, r_hi, j == 0, last)) return rc;
   }
   CKL();
   return LSQR_OK;
+}
+
+// ---- host copy of the device sampler (models.cuh: philox4x32_10, sample_subset) ---------------------
+// compute() draws the minimal subsets of its first round on the host so that their records can be fetched from the caller's
+// buffer ahead of the bulk upload; the indices are bit-identical to what the device draws for the same (seed, hypothesis).
+void host_philox(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+void host_sample_subset(int K, uint64_t gidx, uint64_t seed, uint32_t n, int32_t* out) {
+  uint32_t rnd[8];
+  for (int blk = 0; blk < (K > 4 ? 2 : 1); blk++) {
+    uint32_t c[4] = {(uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)blk, 0u};
+    host_philox(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    for (int i = 0; i < 4; i++) rnd[4 * blk + i] = c[i];
+  }
+  uint32_t sorted[8];
+  for (int j = 0; j < K; j++) {
+    uint32_t v = (uint32_t)(((uint64_t)rnd[j] * (uint64_t)(n - j)) >> 32);   // uniform in [0, n-j)
+    for (int i = 0; i < j; i++) if (v >= sorted[i]) v++;                       // skip taken indices, ascending
+    out[j] = (int32_t)v;
+    int pos = j;
+    for (int i = j - 1; i >= 0; i--) if (sorted[i] > v) { sorted[i + 1] = sorted[i]; pos = i; }
+    sorted[pos] = v;
+  }
 }
 
 // Number of subsets as the reference counts them (RANSAC::choose, RANSAC.hxx:254-280): the binomial
@@ -751,6 +792,8 @@ int finish_ransac(lsqr_ctx* ctx, const lsqr_score_result& best, uint8_t* out_mas
   return LSQR_OK;
 }
 
+uint64_t tries_after(uint32_t best_count, uint32_t n, int K, double numerator, unsigned int all_tries);
+
 int ransac_impl(lsqr_ctx* ctx, double prob, int precision, uint64_t seed, uint8_t* out_mask, lsqr_compute_result* res) {
   if (ctx->model < 0 || !ctx->main.soa64) return fail(ctx, LSQR_ERR_STATE, "set the estimator and upload data first");
   memset(res, 0, sizeof(*res));
@@ -776,10 +819,7 @@ int ransac_impl(lsqr_ctx* ctx, double prob, int precision, uint64_t seed, uint8_
     if (r.best_count > best.best_count) {  // strict '>' : RANSAC.hxx:100
       best = r;
       if (best.best_count == n) break;   // :104-105
-      const double denominator = log(1.0 - pow((double)best.best_count / (double)n, (double)mi.K));  // :107
-      const double t = numerator / denominator + 0.5;
-      uint64_t nt = (t >= 4294967295.0 || !(t == t)) ? 0xFFFFFFFFull : (t < 0 ? 0x80000000ull : (uint64_t)t);  // (int) cast semantics of :108
-      num_tries = std::min<uint64_t>(nt, all_tries);  // :110
+      num_tries = tries_after(best.best_count, n, mi.K, numerator, all_tries);  // :107-110
     }
     round = std::min<uint64_t>(round * 4, (uint64_t)1 << 20);
   }
@@ -804,6 +844,124 @@ int ransac_exhaustive_impl(lsqr_ctx* ctx, int precision, uint8_t* out_mask, lsqr
   res->tries = total;
   int rc = finish_ransac(ctx, r, out_mask, res);
   res->device_ms = r.score_ms + ctx->refine_kernel_ms;
+  return rc;
+}
+
+// The stop rule of RANSAC.hxx:104-110 after a new best count.
+uint64_t tries_after(uint32_t best_count, uint32_t n, int K, double numerator, unsigned int all_tries) {
+  const double denominator = log(1.0 - pow((double)best_count / (double)n, (double)K));  // :107
+  const double t = numerator / denominator + 0.5;
+  const uint64_t nt = (t >= 4294967295.0 || !(t == t)) ? 0xFFFFFFFFull : (t < 0 ? 0x80000000ull : (uint64_t)t);  // (int) cast semantics of :108
+  return std::min<uint64_t>(nt, all_tries);  // :110
+}
+
+// RANSAC<T,S>::compute with the data still on the host: lsqr_upload + lsqr_ransac in one pass, same results bit for bit.  The
+// minimal subsets of the first round (256 hypotheses, drawn on the host with the device's sampler) are fetched from the caller's
+// buffer first, solved at once, and every range of the data is scored against them as soon as it has been transposed, so
+// that when the last chunk lands only that chunk is left to score.
+int compute_impl(lsqr_ctx* ctx, const void* aos, size_t n, size_t stride, double prob, int precision, uint64_t seed, uint8_t* out_mask, lsqr_compute_result* res) {
+  if (ctx->model < 0) return fail(ctx, LSQR_ERR_STATE, "lsqr_set_estimator must be called first");
+  memset(res, 0, sizeof(*res));
+  const ModelInfo mi = model_info(ctx->model);
+  // RANSAC.hxx:16-19: fewer data than the minimal subset, or probability outside (0,1) -> return 0 (nothing is touched)
+  if (n < (size_t)mi.K || prob >= 1.0 || prob <= 0.0) return LSQR_OK;
+  if (n > 0xFFFFFFF0ull) return fail(ctx, LSQR_ERR_ARG, "too many data records");
+  if (!aos) return fail(ctx, LSQR_ERR_ARG, "null data pointer");
+  if (stride < sizeof(double) * mi.D || (stride % sizeof(double)) != 0) return fail(ctx, LSQR_ERR_ARG, "stride must be a multiple of 8 and >= 8*dim");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const uint32_t N = (uint32_t)n;
+  const double numerator = log(1.0 - prob);
+  const unsigned int all_tries = choose_ref(N, (unsigned)mi.K);  // RANSAC.hxx:41
+  const uint64_t H0 = std::min<uint64_t>(256, all_tries);         // the first round of lsqr_ransac
+  const uint64_t lo = H0 * (uint64_t)ctx->rank / (uint64_t)ctx->world, hi = H0 * (uint64_t)(ctx->rank + 1) / (uint64_t)ctx->world;
+  const uint32_t B = (uint32_t)(hi - lo);
+  // subsets of the whole round (every rank keeps the list: the winner is re-derived from it), records of this rank's share
+  std::vector<int32_t> subs((size_t)H0 * mi.K);
+  for (uint64_t h = 0; h < H0; h++) host_sample_subset(mi.K, h, seed, N, &subs[h * mi.K]);
+  if (int rc = ensure_hyp(ctx, std::max<uint32_t>(B, 1))) return rc;
+  if (int rc = ensure(ctx, &ctx->list_dev, &ctx->list_cap, (size_t)H0 * mi.K)) return rc;
+  const size_t gbytes = (size_t)std::max<uint32_t>(B, 1) * mi.K * stride;
+  if (int rc = ensure(ctx, &ctx->gather_dev, &ctx->gather_cap, gbytes)) return rc;
+  if (ctx->gather_pin_cap < gbytes + sizeof(int32_t) * H0 * mi.K) {
+    if (ctx->gather_pin) cudaFreeHost(ctx->gather_pin);
+    ctx->gather_pin = nullptr; ctx->gather_pin_cap = 0;
+    CK(cudaMallocHost((void**)&ctx->gather_pin, gbytes + sizeof(int32_t) * H0 * mi.K));
+    ctx->gather_pin_cap = gbytes + sizeof(int32_t) * H0 * mi.K;
+  }
+  const unsigned char* host = static_cast<const unsigned char*>(aos);
+  for (uint32_t h = 0; h < B; h++)
+    for (int j = 0; j < mi.K; j++) memcpy(ctx->gather_pin + ((size_t)h * mi.K + j) * stride, host + (size_t)subs[(lo + h) * mi.K + j] * stride, sizeof(double) * mi.D);
+  memcpy(ctx->gather_pin + gbytes, subs.data(), sizeof(int32_t) * H0 * mi.K);
+  CK(cudaMemsetAsync(ctx->key_dev, 0, 2 * sizeof(unsigned long long), s));
+  CK(cudaEventRecord(ctx->ev[0], s));
+  CK(cudaMemcpyAsync(ctx->gather_dev, ctx->gather_pin, gbytes, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->list_dev, ctx->gather_pin + gbytes, sizeof(int32_t) * H0 * mi.K, cudaMemcpyHostToDevice, s));
+  SolveArgs sa{};
+  sa.model = ctx->model; sa.sampler = LSQR_SAMPLE_LIST; sa.seed = seed; sa.first = lo; sa.H = B; sa.hld = ctx->hcap;
+  sa.subsets = ctx->subsets; sa.hyp64 = ctx->hyp64; sa.n_valid = reinterpret_cast<uint32_t*>(ctx->key_dev + 1);
+  sa.list = ctx->list_dev + lo * mi.K; sa.gathered = ctx->gather_dev; sa.gathered_stride = stride;
+  DataSet& ds = ctx->main;
+  const RoundFn score_range = [&](size_t r_lo, size_t r_hi, bool first, bool last) -> int {
+    if (B == 0) return 0;
+    if (first) {   // the centre is known now: hypotheses (from the fetched records) and their fp32 constants
+      DataView dv = ds.view();
+      dv.n = N;
+      launch_solve(sa, dv, ctx->cfg, s); ctx->launches++;
+      if (precision == LSQR_FP32) { launch_hoist32(ctx->model, ctx->hyp64, ctx->hcap, B, dv, ctx->cfg, ctx->hyp32, s); ctx->launches++; }
+      CK(cudaMemsetAsync(ctx->counts, 0, sizeof(uint32_t) * B, s));
+    }
+    if (r_hi > r_lo) ctx->launches += launch_consensus(ctx->model, precision, ds.range(r_lo, r_hi, last), ctx->hyp64, ctx->hyp32, ctx->hcap, B, ctx->cfg, ctx->counts, ctx->num_sms, s);
+    return 0;
+  };
+  if (int rc = upload_to(ctx, ds, aos, n, stride, false, true, &score_range)) return rc;
+  const DataView dv = ds.view();
+  if (B) { launch_argmax(ctx->counts, B, (uint32_t)lo, ctx->key_dev, s); ctx->launches++; }
+  if (int rc = comm_max_u64(ctx, ctx->key_dev)) return rc;
+  SolveArgs wa{};
+  wa.model = ctx->model; wa.sampler = LSQR_SAMPLE_LIST; wa.seed = seed; wa.first = 0; wa.list = ctx->list_dev;
+  launch_winner(wa, ctx->key_dev, dv, ctx->cfg, ctx->winner_dev, s); ctx->launches++;
+  CK(cudaEventRecord(ctx->ev[1], s));
+  CKL();
+  CK(cudaMemcpyAsync(ctx->winner_pin, ctx->winner_dev, sizeof(WinnerRecord), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  float ms0 = 0.f;
+  CK(cudaEventElapsedTime(&ms0, ctx->ev[0], ctx->ev[1]));
+  double dev_ms = ms0;   // includes the upload it overlaps
+  const WinnerRecord& w = *ctx->winner_pin;
+  lsqr_score_result best{};
+  best.best_count = (uint32_t)(w.key >> 32);
+  best.n_valid = (uint32_t)w.n_valid;
+  if (best.best_count) {
+    best.best_index = 0xFFFFFFFFull - (w.key & 0xFFFFFFFFull);
+    for (int j = 0; j < mi.P; j++) best.best_params[j] = w.params[j];
+    for (int j = 0; j < mi.K; j++) best.best_subset[j] = w.subset[j];
+  }
+  // from here on: lsqr_ransac's loop, first round done
+  uint64_t num_tries = all_tries, done = H0, round = 1024;
+  bool perfect = false;
+  if (best.best_count) {
+    if (best.best_count == N) perfect = true;   // RANSAC.hxx:104-105
+    else num_tries = tries_after(best.best_count, N, mi.K, numerator, all_tries);
+  }
+  while (!perfect && done < num_tries) {
+    lsqr_score_args a{};
+    a.sampler = LSQR_SAMPLE_PHILOX; a.precision = precision; a.seed = seed; a.first = done;
+    a.count = std::min<uint64_t>(round, num_tries - done);
+    lsqr_score_result r{};
+    if (int rc = score_impl(ctx, &a, &r)) return rc;
+    dev_ms += r.score_ms;
+    done += a.count;
+    if (r.best_count > best.best_count) {  // strict '>' : RANSAC.hxx:100
+      best = r;
+      if (best.best_count == N) break;
+      num_tries = tries_after(best.best_count, N, mi.K, numerator, all_tries);
+    }
+    round = std::min<uint64_t>(round * 4, (uint64_t)1 << 20);
+  }
+  res->tries = done;
+  int rc = finish_ransac(ctx, best, out_mask, res);
+  res->device_ms = dev_ms + ctx->refine_kernel_ms;
   return rc;
 }
 
@@ -988,6 +1146,7 @@ void lsqr_ctx_destroy(lsqr_ctx* ctx) {
   free_dataset(ctx->main); free_dataset(ctx->scratch);
   cudaFree(ctx->bt_data); cudaFree(ctx->bt_off); cudaFree(ctx->bt_prm); cudaFree(ctx->bt_cnt);
   cudaFree(ctx->weights_dev); cudaFree(ctx->mask_dev); if (ctx->mask_pin) cudaFreeHost(ctx->mask_pin);
+  cudaFree(ctx->gather_dev); if (ctx->gather_pin) cudaFreeHost(ctx->gather_pin);
   for (int i = 0; i < lsqr_ctx::kRing; i++) if (ctx->up_pin[i]) cudaFreeHost(ctx->up_pin[i]);
   cudaFree(ctx->staging); cudaFree(ctx->subsets); cudaFree(ctx->hyp64); cudaFree(ctx->hyp32); cudaFree(ctx->counts);
   cudaFree(ctx->list_dev); cudaFree(ctx->params_in_dev); cudaFree(ctx->key_dev); cudaFree(ctx->winner_dev); cudaFree(ctx->small_dev);
@@ -1138,6 +1297,20 @@ int lsqr_ransac(lsqr_ctx* ctx, double prob, int precision, uint64_t seed, uint8_
     return LSQR_OK;
   }
   return ransac_impl(ctx, prob, precision, seed, out_mask, res);
+}
+
+int lsqr_compute(lsqr_ctx* ctx, const void* aos, size_t n, size_t stride_bytes, double prob, int precision, uint64_t seed, uint8_t* out_mask,
+                 lsqr_compute_result* res) {
+  if (!ctx || !res) return LSQR_ERR_ARG;
+  if (ctx->group) {
+    std::vector<lsqr_compute_result> rs(ctx->world);
+    const int rc = group_run(ctx, [&](lsqr_ctx* k, int r) { return compute_impl(k, aos, n, stride_bytes, prob, precision, seed, out_mask, &rs[r]); });
+    if (rc) return rc;
+    *res = rs[0];
+    for (const auto& r : rs) res->device_ms = std::max(res->device_ms, r.device_ms);
+    return LSQR_OK;
+  }
+  return compute_impl(ctx, aos, n, stride_bytes, prob, precision, seed, out_mask, res);
 }
 
 int lsqr_ransac_exhaustive(lsqr_ctx* ctx, int precision, uint8_t* out_mask, lsqr_compute_result* res) {

@@ -19,8 +19,9 @@ constexpr uint32_t kCenterSample = 16384;   // the shift c is the mean of the fi
 struct DataView {
   const double* soa64;  // [D][ld], padded with NaN
   const float* soa32;   // [D][ld], centred (soa64 - center), padded with NaN
-  size_t ld;
-  uint32_t n;
+  size_t ld;            // leading dimension (stride between components)
+  size_t span;          // columns the consensus kernels walk: ld for the whole data set, fewer for a range view (multiple of 1024)
+  uint32_t n;           // valid data inside the view
   const double* center; // device, kMaxDim doubles: per-component shift used for soa32 and for the refine moments
 };
 
@@ -46,6 +47,8 @@ struct SolveArgs {
   uint32_t H;             // hypotheses in this launch
   size_t hld;             // leading dimension of the hypothesis arrays
   const int32_t* list;    // LSQR_SAMPLE_LIST: [H][K] on device
+  const unsigned char* gathered;  // optional, with `list`: the K records of every subset, AoS [H][K] records of gathered_stride bytes
+  size_t gathered_stride; //   (compute(): the minimal subsets are fetched ahead of the bulk upload)
   const double* params_in;// LSQR_SAMPLE_PARAMS: [H][P] on device
   int32_t* subsets;       // out [K][hld]
   double* hyp64;          // out [P][hld]

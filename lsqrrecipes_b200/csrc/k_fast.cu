@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(THREADS) consensus32_kernel(const float* __res
 
 template <int M, int R, int THREADS, int TILE, int PPI>
 static int run_consensus32(const DataView& dv, const float* hyp, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms, cudaStream_t s) {
-  const uint32_t tiles_total = (uint32_t)(dv.ld / TILE);
+  const uint32_t tiles_total = (uint32_t)(dv.span / TILE);
   const uint32_t hyp_blocks = (H + THREADS * R - 1) / (THREADS * R);
   uint32_t want = (uint32_t)num_sms * 16;  // ~16 work items per SM for load balance
   uint32_t chunks = (want + hyp_blocks - 1) / hyp_blocks;
@@ -719,8 +719,8 @@ static int run_consensus_cb(const DataView& dv, const float* hyp, size_t hld, ui
   };
   std::lock_guard<std::mutex> lock(g_cb_mutex[dev & 15]);
   int launches = 0;
-  for (size_t base = 0; base < dv.ld; base += cp) {
-    const uint32_t npts = (uint32_t)((dv.ld - base < cp) ? (dv.ld - base) : cp);   // ld is a multiple of 1024, cp of 16
+  for (size_t base = 0; base < dv.span; base += cp) {
+    const uint32_t npts = (uint32_t)((dv.span - base < cp) ? (dv.span - base) : cp);   // span is a multiple of 1024, cp of 16
     if (base >= dv.n) break;                                                        // only NaN padding left
     if (cudaMemcpy2DAsync(bank, sizeof(float) * cp, dv.soa32 + base, sizeof(float) * dv.ld, sizeof(float) * npts, D, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return -1;
     const uint32_t sub = pick_sub(npts);

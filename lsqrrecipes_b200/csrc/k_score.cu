@@ -142,8 +142,14 @@ __global__ void __launch_bounds__(128) solve_kernel(SolveArgs a, const double* _
     for (int j = 0; j < K; j++) {
       in_range = in_range && sub[j] >= 0 && (uint32_t)sub[j] < n;
       const size_t idx = in_range ? (size_t)sub[j] : 0;
+      if (a.gathered != nullptr) {   // the subset's records were fetched ahead of the bulk data
+        const double* rec = reinterpret_cast<const double*>(a.gathered + ((size_t)h * K + j) * a.gathered_stride);
 #pragma unroll
-      for (int d = 0; d < D; d++) pts[j * D + d] = soa[(size_t)d * ld + idx];
+        for (int d = 0; d < D; d++) pts[j * D + d] = rec[d];
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; d++) pts[j * D + d] = soa[(size_t)d * ld + idx];
+      }
     }
     ok = in_range && estimate<M>(pts, cfg, prm);
   }
@@ -303,10 +309,10 @@ __global__ void __launch_bounds__(THREADS) consensus_kernel(const typename T::re
 }
 
 template <class T, int R, int THREADS, int TILE>
-static int run_consensus(const typename T::real* soa, size_t ld, const typename T::real* hyp, size_t hld, uint32_t H, const typename T::thr_t& thr,
+static int run_consensus(const typename T::real* soa, size_t ld, size_t span, const typename T::real* hyp, size_t hld, uint32_t H, const typename T::thr_t& thr,
                          uint32_t* counts, int num_sms, cudaStream_t s) {
   using real = typename T::real;
-  const uint32_t tiles_total = (uint32_t)(ld / TILE);
+  const uint32_t tiles_total = (uint32_t)(span / TILE);
   const uint32_t hyp_blocks = (H + THREADS * R - 1) / (THREADS * R);
   // enough (hypothesis block x point chunk) work items for ~16 CTAs per SM, chunks not below 4 tiles
   uint32_t want = (uint32_t)num_sms * 16;
@@ -335,8 +341,8 @@ int launch_consensus(int model, int precision, const DataView& dv, const double*
   if (H == 0 || dv.n == 0) return 0;
   if (precision == 0) {
 #define CALL(MM)                                                                                                             \
-  if (H <= 4096) return run_consensus<Exact<MM>, 1, 128, 256>(dv.soa64, dv.ld, hyp64, hld, H, cfg, counts, num_sms, s);       \
-  return run_consensus<Exact<MM>, (Model<MM>::HQ >= 12 ? 2 : 4), 128, 256>(dv.soa64, dv.ld, hyp64, hld, H, cfg, counts, num_sms, s)
+  if (H <= 4096) return run_consensus<Exact<MM>, 1, 128, 256>(dv.soa64, dv.ld, dv.span, hyp64, hld, H, cfg, counts, num_sms, s);       \
+  return run_consensus<Exact<MM>, (Model<MM>::HQ >= 12 ? 2 : 4), 128, 256>(dv.soa64, dv.ld, dv.span, hyp64, hld, H, cfg, counts, num_sms, s)
     LSQR_DISPATCH_MODEL(model, CALL)
 #undef CALL
   } else {

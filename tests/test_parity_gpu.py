@@ -543,3 +543,34 @@ def test_python_operator_interface_mirrors_reference():
     ls = []
     est.leastSquaresEstimate(data[np.array(consensus)], ls)
     assert same_up_to_sign(ls, params, [0, 1, 2], 1e-9)
+
+
+@pytest.mark.parametrize("name", ["plane3", "line2d", "sphere3", "absor", "pivot", "uscp"])
+@pytest.mark.parametrize("precision", [FP64, FP32])
+def test_pipelined_compute_equals_upload_then_ransac(name, precision):
+    """lsqr_compute (data still on the host: first-round subsets drawn by the host copy of the Philox sampler, their records
+    fetched ahead, every chunk scored as it lands) returns exactly what lsqr_upload + lsqr_ransac return: same winner, same
+    number of tries, same consensus set, same parameters -- from pageable and from page-locked memory, for sizes below one
+    chunk and spanning many."""
+    import torch
+    for n in (5, 1000, 70_001, 1_200_003):
+        data, _ = synth.GENERATORS[name](n, seed=77 + n % 1000)
+        a = Engine(name, synth.DELTAS[name])
+        a.upload(data)
+        want = a.ransac(0.999, precision=precision, seed=21)
+        a.close()
+        b = Engine(name, synth.DELTAS[name])
+        pinned = torch.from_numpy(data).pin_memory()
+        for src in (data, pinned.numpy()):
+            got = b.compute(src, 0.999, precision=precision, seed=21)
+            assert (got["best_index"], got["best_count"], got["tries"], got["fraction"]) == (want["best_index"], want["best_count"], want["tries"], want["fraction"])
+            assert np.array_equal(got["mask"], want["mask"]) and np.array_equal(got["params"], want["params"])
+        # the data stay resident: the estimator-level calls that follow compute() see them
+        assert b.consensus(want["params"]) > 0 or len(want["params"]) == 0
+        b.close()
+    # invalid input: nothing happens (RANSAC.hxx:16-19)
+    e = Engine(name, synth.DELTAS[name])
+    r = e.compute(data[:1], 0.999)
+    assert r["fraction"] == 0.0 and len(r["params"]) == 0
+    assert e.compute(data, 1.0)["fraction"] == 0.0
+    e.close()

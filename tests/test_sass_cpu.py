@@ -48,10 +48,26 @@ def test_plane_kernel_counts_through_the_carry_chain(sass):
     assert sum(i.startswith("LDCU") for i in ins) >= 12, "constant-bank loads"
 
 
-def test_sphere_kernel_uses_the_raw_sum_form(sass):
+def test_sphere_kernel_counts_through_the_carry_chain_with_its_own_window(sass):
+    """consensus_cb_kernel<SPHERE3, 10, 128, 2>: 3 FADD2 + 3 FFMA2 per pair of residuals; the window 4 r delta is per hypothesis,
+    so the two carry-only IADD3 read it from a register (stored pre-negated by the hoist kernel: no negation in the loop)."""
     ins = _one(sass, r"consensus_cb_kernelILi5ELi10ELi128ELi2E")
-    assert sum(i.startswith("FSET.BF") for i in ins) >= 40 and sum(i.startswith("FFMA2") for i in ins) >= 60
-    assert sum(i.startswith("FADD2") for i in ins) >= 60
+    assert sum(i.startswith("FFMA2") for i in ins) >= 60 and sum(i.startswith("FADD2") for i in ins) >= 60
+    cmp_ = [i for i in ins if re.match(r"IADD3 RZ, P\d, PT, R\d+(\.reuse)?, R\d+(\.reuse)?, RZ", i)]
+    addx = [i for i in ins if re.match(r"IADD3\.X R\d+, PT, PT, RZ, RZ, R\d+, P\d, P\d", i)]
+    assert len(cmp_) >= 40 and len(addx) >= 20, (len(cmp_), len(addx))
+    assert not [i for i in ins if i.startswith(("FSET", "FSETP"))]
+    assert sum(i.startswith("IMAD.MOV R") for i in ins) == 0, "the window must not be negated inside the loop"
+
+
+def test_refine_pass_streams_through_a_tma_ring(sass):
+    """mask_moments_kernel<PLANE3, mask mode 1>: tiles arrive by cp.async.bulk (UBLKCP) on mbarriers (SYNCS), are read back
+    with LDS.64, and the moments accumulate with DFMA; no global load of the centre inside the loop (two LDG at most, ahead of it)."""
+    ins = _one(sass, r"mask_moments_kernelILi0ELi1ELb0E")
+    assert any(i.startswith("UBLKCP") for i in ins) and any("SYNCS.PHASECHK" in i for i in ins)
+    assert sum(i.startswith("LDS.64") for i in ins) >= 6 and sum(i.startswith("DFMA") for i in ins) >= 12
+    first_wait = next(k for k, i in enumerate(ins) if "SYNCS.PHASECHK" in i)
+    assert not [i for i in ins[first_wait:] if i.startswith("LDG") and ".64" in i], "per-row global loads inside the streaming loop"
 
 
 def test_shared_memory_kernel_is_fed_by_tma(sass):

@@ -64,8 +64,11 @@ def full_pag(i):
     eng.ransac(0.999, precision=FP32, seed=i, mask_out=mask_pag)
 
 
-print("compute() pinned   ms", med(full_pin))
-print("compute() pageable ms", med(full_pag))
+print("upload + ransac pinned   ms", med(full_pin))
+print("upload + ransac pageable ms", med(full_pag))
+print("lsqr_compute pinned   ms", med(lambda i: eng.compute(host.data_ptr(), 0.999, precision=FP32, seed=i, mask_out=mask_pin, n=N, stride_bytes=stride)))
+print("lsqr_compute pageable ms", med(lambda i: eng.compute(data, 0.999, precision=FP32, seed=i, mask_out=mask_pag)))
+print("lsqr_compute pinned, no mask ms", med(lambda i: eng.compute(host.data_ptr(), 0.999, precision=FP32, seed=i, want_mask=False, n=N, stride_bytes=stride)))
 st = eng.last_refine_stats()
 print("refine kernel", st)
 eng.close()
