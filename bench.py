@@ -218,7 +218,7 @@ def run_reference_arm(args):
     emit_line(line)
 
 
-def secondary_configs(device, peak_fma_per_s, hbm_peak, budget_s=75.0):
+def secondary_configs(device, peak_fma_per_s, hbm_peak, budget_s=90.0):
     """BASELINE.json configs[2..4] and a per-model scoring table, time-boxed, single GPU: every number that README.md and
     DESIGN.md quote next to the headline comes from here, i.e. from the driver's own run of this file."""
     import torch
@@ -316,8 +316,8 @@ def secondary_configs(device, peak_fma_per_s, hbm_peak, budget_s=75.0):
         for name in ("line2d", "line2", "line3", "circle2", "sphere4", "plane4", "ray", "pivot", "dense5", "dense6", "usxw", "uscp"):
             if left() < 4:
                 break
-            table.append(scoring(name, 1_000_000, 131_072, reps=2))
-        out.append({"config": "scoring table: 131072 hypotheses x 1M data per estimator, fp32, frac = evals/s x SURVEY 8d lane-ops / measured FP32 lane rate",
+            table.append(scoring(name, 1_000_000, 1_048_576, reps=1))
+        out.append({"config": "scoring table: 1M hypotheses x 1M data per estimator, fp32, frac = evals/s x SURVEY 8d lane-ops / measured FP32 lane rate",
                     "models": table})
     except Exception as e:  # a secondary measurement must never take the headline line down
         out.append({"error": repr(e)})

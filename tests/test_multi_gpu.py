@@ -52,6 +52,11 @@ def test_native_multi_gpu_context_matches_single_gpu():
         ra, rb = one.ransac(0.999, precision=FP32, seed=12), many.ransac(0.999, precision=FP32, seed=12)
         assert (ra["best_index"], ra["fraction"], ra["tries"]) == (rb["best_index"], rb["fraction"], rb["tries"])
         assert np.array_equal(ra["mask"], rb["mask"]) and np.allclose(ra["params"], rb["params"], rtol=1e-9, atol=1e-9)
+        # lsqr_compute: the pipelined call with the data on the host (interleaved chunk upload + all-gather inside the library)
+        ca, cb = one.compute(data, 0.999, precision=FP32, seed=12), many.compute(data, 0.999, precision=FP32, seed=12)
+        assert (ca["best_index"], ca["fraction"], ca["tries"]) == (ra["best_index"], ra["fraction"], ra["tries"]) == (cb["best_index"], cb["fraction"], cb["tries"])
+        assert np.array_equal(ca["mask"], ra["mask"]) and np.array_equal(cb["mask"], ra["mask"])
+        assert np.array_equal(ca["params"], ra["params"]) and np.allclose(cb["params"], ra["params"], rtol=1e-9, atol=1e-9)
         one.close()
         many.close()
     # batched small problems: partitioned over the GPUs, no collective, same answers

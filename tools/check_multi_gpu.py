@@ -62,6 +62,9 @@ for name, n, H in (("plane3", 400_003, 200_000), ("sphere3", 200_001, 50_000), (
         gather = full_mask if mode != "single" else (lambda m: m)     # a rank holds the consensus bits of its own point shard
         out.append((r["best_index"], r["best_count"], r["best_params"].copy(), cnt, gather(eng.get_mask()).copy(), eng.refine().copy()))
         c = eng.ransac(0.999, precision=FP32, seed=12)
+        if mode == "native":   # and the pipelined one-call form gives the same answer
+            c2 = eng.compute(data, 0.999, precision=FP32, seed=12)
+            assert (c2["best_index"], c2["fraction"], c2["tries"]) == (c["best_index"], c["fraction"], c["tries"]) and np.array_equal(full_mask(c2["mask"]), full_mask(c["mask"]))
         out[-1] += (c["best_index"], c["fraction"], gather(c["mask"]).copy(), c["params"].copy())
         eng.close()
     for mode, b in zip(("native", "hooks"), out[1:]):

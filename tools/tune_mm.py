@@ -10,7 +10,8 @@ from lsqrrecipes_b200 import api  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "plane3"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000_000
-for lib in sorted(glob.glob(os.path.join(ROOT, "tools/bin/variants/lib_mm_*.so"))) + [api.lib_path()]:
+libs = [api.lib_path()] if os.environ.get("TUNE_MM_ONLY_SHIPPED") else sorted(glob.glob(os.path.join(ROOT, "tools/bin/variants/lib_mm_*.so"))) + [api.lib_path()]
+for lib in libs:
     if os.fork() == 0:
         api.lib_path = lambda lib=lib: lib
         from lsqrrecipes_b200 import FP32, Engine, synth
