@@ -235,6 +235,10 @@ int lsqr_weighted_least_squares(lsqr_ctx* ctx, const double* packed, size_t n, c
  * packed fp32x2 (kind 1) or fp64 (kind 2) pipe on the context's device.  Used by bench.py
  * to state the consensus kernel's roofline against a MEASURED pipe peak. */
 int lsqr_microbench_fma(lsqr_ctx* ctx, int kind, int iters, double* out_fma_per_s, double* out_ms);
+/* The consensus-set + moments pass (mask_moments_kernel) for `params`, `reps` launches back to back between two CUDA events
+ * on the context's stream: average duration of a launch and the bytes one launch has to move (8 dim bytes per datum read,
+ * 1 bit written).  bench.py's roofline_refine. */
+int lsqr_bench_refine_pass(lsqr_ctx* ctx, const double* params, int reps, double* ms_per_pass, double* algorithmic_bytes);
 /* Time of the last refine's streaming moment kernel and the bytes it had to read. */
 int lsqr_last_refine_stats(const lsqr_ctx* ctx, double* kernel_ms, double* algorithmic_bytes, int* lm_iterations);
 

@@ -94,6 +94,7 @@ def load_library():
         "lsqr_weighted_least_squares": (c.c_int, [c.c_void_p, _dp, c.c_size_t, _dp, _dp, c.POINTER(c.c_int)]),
         "lsqr_microbench_fma": (c.c_int, [c.c_void_p, c.c_int, c.c_int, _dp, _dp]),
         "lsqr_last_refine_stats": (c.c_int, [c.c_void_p, _dp, _dp, c.POINTER(c.c_int)]),
+        "lsqr_bench_refine_pass": (c.c_int, [c.c_void_p, _dp, c.c_int, _dp, _dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -109,7 +110,7 @@ EXPORTED_SYMBOLS = [
     "lsqr_refine", "lsqr_ransac", "lsqr_ransac_exhaustive", "lsqr_ransac_batch", "lsqr_estimate", "lsqr_agree", "lsqr_least_squares",
     "lsqr_microbench_fma", "lsqr_last_refine_stats", "lsqr_weighted_least_squares",
     "lsqr_device_count", "lsqr_ctx_create_multi", "lsqr_ctx_world", "lsqr_nccl_unique_id", "lsqr_ctx_init_nccl", "lsqr_get_mask_bits",
-    "lsqr_compute",
+    "lsqr_compute", "lsqr_bench_refine_pass",
 ]
 
 
@@ -341,6 +342,14 @@ class Engine:
         ms = ctypes.c_double(0)
         self._ck(self.lib.lsqr_microbench_fma(self.h, kind, iters, ctypes.byref(v), ctypes.byref(ms)))
         return v.value, ms.value
+
+    def bench_refine_pass(self, params, reps=16):
+        """Average duration (ms) of one consensus-set + moments launch over `reps` back-to-back launches, and its bytes."""
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        ms = ctypes.c_double(0)
+        b = ctypes.c_double(0)
+        self._ck(self.lib.lsqr_bench_refine_pass(self.h, _ptr(p, _dp), int(reps), ctypes.byref(ms), ctypes.byref(b)))
+        return {"ms_per_pass": ms.value, "bytes": b.value}
 
     def last_refine_stats(self):
         ms = ctypes.c_double(0)

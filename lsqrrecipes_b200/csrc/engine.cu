@@ -1449,6 +1449,35 @@ int lsqr_microbench_fma(lsqr_ctx* ctx, int kind, int iters, double* out_fma_per_
   return LSQR_OK;
 }
 
+int lsqr_bench_refine_pass(lsqr_ctx* ctx, const double* params, int reps, double* ms_per_pass, double* algorithmic_bytes) {
+  if (!ctx || !params || reps <= 0) return LSQR_ERR_ARG;
+  if (ctx->group) return lsqr_bench_refine_pass(ctx->group->kids[0], params, reps, ms_per_pass, algorithmic_bytes);
+  DataSet& ds = ctx->main;
+  if (ctx->model < 0 || !ds.soa64) return fail(ctx, LSQR_ERR_STATE, "set the estimator and upload data first");
+  const ModelInfo mi = model_info(ctx->model);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  for (int j = 0; j < mi.P; j++) ctx->pin[32 + j] = params[j];
+  CK(cudaMemcpyAsync(ctx->small_dev + kSmIn, ctx->pin + 32, sizeof(double) * mi.P, cudaMemcpyHostToDevice, s));
+  uint32_t b, e;
+  shard_range(ctx, ds.n, &b, &e);
+  ctx->rb.maskbits = ds.maskbits;
+  ctx->rb.maskbytes = nullptr;
+  launch_mask_moments(ctx->model, ds.view(), b, e, ctx->small_dev + kSmIn, 1, nullptr, ctx->cfg, ctx->rb, s);   // warm-up
+  CK(cudaEventRecord(ctx->ev[4], s));
+  for (int i = 0; i < reps; i++) launch_mask_moments(ctx->model, ds.view(), b, e, ctx->small_dev + kSmIn, 1, nullptr, ctx->cfg, ctx->rb, s);
+  CK(cudaEventRecord(ctx->ev[5], s));
+  ctx->launches += (uint64_t)reps + 1;
+  CKL();
+  CK(cudaStreamSynchronize(s));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
+  if (ms_per_pass) *ms_per_pass = (double)ms / reps;
+  if (algorithmic_bytes) *algorithmic_bytes = (double)(e - b) * mi.D * sizeof(double) + (double)(e - b) / 8.0;
+  ds.moments_valid = false; ds.mask_valid = true; ds.bytes_valid = false;
+  return LSQR_OK;
+}
+
 int lsqr_last_refine_stats(const lsqr_ctx* ctx, double* kernel_ms, double* algorithmic_bytes, int* lm_iterations) {
   if (!ctx) return LSQR_ERR_ARG;
   if (ctx->group) return lsqr_last_refine_stats(ctx->group->kids[0], kernel_ms, algorithmic_bytes, lm_iterations);

@@ -58,9 +58,9 @@ template <> struct Mom<DENSE6>  { static constexpr int N = 28, NLM = 0, NPLM = 1
 template <> struct Mom<USXW>    { static constexpr int N = 91, NLM = 79, NPLM = 11; };
 template <> struct Mom<USCP>    { static constexpr int N = 55, NLM = 46, NPLM = 8; };
 
-// q = centred datum.  acc[0] counts.
+// q = centred datum.  acc[0] is the inlier count: the callers add it (the streaming pass feeds zeros for data outside the
+// consensus set instead of branching, so only the count must know).
 template <int DIM> __device__ __forceinline__ void acc_scatter(const double* q, double* acc) {
-  acc[0] += 1.0;
   int o = 1;
 #pragma unroll
   for (int j = 0; j < DIM; j++) acc[o++] += q[j];
@@ -110,7 +110,6 @@ template <> __device__ __forceinline__ void accumulate<SPHERE3>(const double* q,
 template <> __device__ __forceinline__ void accumulate<SPHERE4>(const double* q, double* acc) { acc_sphere_alg<4>(q, acc); }
 // AbsoluteOrientationParametersEstimator.cxx:134-166: sums of both point sets and of p1 p2^T
 template <> __device__ __forceinline__ void accumulate<ABSOR>(const double* q, double* acc) {
-  acc[0] += 1.0;
 #pragma unroll
   for (int j = 0; j < 6; j++) acc[1 + j] += q[j];
 #pragma unroll
@@ -121,7 +120,6 @@ template <> __device__ __forceinline__ void accumulate<ABSOR>(const double* q, d
 // RayIntersectionParametersEstimator.cxx:108-123
 template <> __device__ __forceinline__ void accumulate<RAY>(const double* q, double* acc) {
   const double* n = q + 3;
-  acc[0] += 1.0;
   acc[1] += n[0] * n[0]; acc[2] += n[0] * n[1]; acc[3] += n[0] * n[2];
   acc[4] += n[1] * n[1]; acc[5] += n[1] * n[2]; acc[6] += n[2] * n[2];
   const double s = n[0] * q[0] + n[1] * q[1] + n[2] * q[2];
@@ -129,7 +127,6 @@ template <> __device__ __forceinline__ void accumulate<RAY>(const double* q, dou
 }
 // Normal equations of the rows [R | -I] x = -t (PivotCalibrationParametersEstimator.cxx:77-83)
 template <> __device__ __forceinline__ void accumulate<PIVOT>(const double* q, double* acc) {
-  acc[0] += 1.0;
   int o = 1;
 #pragma unroll
   for (int a = 0; a < 3; a++)
@@ -145,7 +142,6 @@ template <> __device__ __forceinline__ void accumulate<PIVOT>(const double* q, d
 
 // Normal equations of the rows a.x = b (DenseLinearEquationSystemParametersEstimator.hxx:64-96)
 template <int N> __device__ __forceinline__ void acc_dense(const double* q, double* acc) {
-  acc[0] += 1.0;
   int o = 1;
 #pragma unroll
   for (int a = 0; a < N; a++)
@@ -159,7 +155,6 @@ template <> __device__ __forceinline__ void accumulate<DENSE6>(const double* q, 
 
 // Normal equations of the rows [u R2, v R2, R2, -I] x = -t2 (SinglePointTargetUSCalibrationParametersEstimator.cxx:137-189)
 template <> __device__ __forceinline__ void accumulate<USXW>(const double* q, double* acc) {
-  acc[0] += 1.0;
   const double u = q[12], v = q[13];
 #pragma unroll
   for (int r = 0; r < 3; r++) {
@@ -228,7 +223,6 @@ __device__ __forceinline__ void acc_us_lm(const double* q, const double* x, doub
 
 // Normal equations of the rows [u R2, v R2, R2] x = p - t2 (SinglePointTargetUSCalibrationParametersEstimator.cxx:806-846)
 template <> __device__ __forceinline__ void accumulate<USCP>(const double* q, double* acc) {
-  acc[0] += 1.0;
   const double u = q[12], v = q[13];
 #pragma unroll
   for (int r = 0; r < 3; r++) {
@@ -300,11 +294,17 @@ template <int M, bool LM> struct MMCfg {
   // models with more than 40 accumulators per thread (the two ultrasound calibrations: 46-91 doubles) get the whole register
   // file of an SM for 256 threads; everyone else runs 512 threads
   static constexpr int THREADS = NM > 40 ? 256 : LSQR_MM_THREADS;
-  static constexpr int TILE = (D * 1024 * 8 <= LSQR_MM_TILE_KB * 1024 + 8192) ? 1024 : ((D * 512 * 8 <= LSQR_MM_TILE_KB * 1024 + 8192) ? 512 : 256);
+  static constexpr int kTileCap = LSQR_MM_TILE_KB * 1024 + 8192;
+  static constexpr int TILE = (D * 2048 * 8 <= kTileCap) ? 2048 : (D * 1024 * 8 <= kTileCap) ? 1024 : ((D * 512 * 8 <= kTileCap) ? 512 : 256);
   static constexpr int PPT = (TILE + THREADS - 1) / THREADS;                 // data per thread per tile
   static constexpr int TILE_BYTES = D * TILE * 8;
-  static constexpr int STAGES = (LSQR_MM_SMEM_KB * 1024 / TILE_BYTES) < 2 ? 2 : ((LSQR_MM_SMEM_KB * 1024 / TILE_BYTES) > 8 ? 8 : (LSQR_MM_SMEM_KB * 1024 / TILE_BYTES));
+  static constexpr int kFit = LSQR_MM_SMEM_KB * 1024 / TILE_BYTES;
+  static constexpr int STAGES = kFit >= 8 ? 8 : (kFit >= 4 ? 4 : 2);         // a power of two: stage and phase are shifts and masks
   static constexpr size_t SMEM = (size_t)STAGES * TILE_BYTES;
+  // light moment sets are accumulated without a branch (zeros for data outside the consensus set): the rows of a tile are
+  // then independent straight-line chains that the scheduler interleaves; Levenberg-Marquardt rows (sqrt, division) and the
+  // 46-91-term calibration rows stay behind a branch
+  static constexpr bool BRANCHLESS = !LM && NM <= 32;
 };
 int mask_moments_ctas_per_sm() { return 1; }
 
@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(MMCfg<M, LM>::THREADS, 1) mask_moments_kernel(
   using C = MMCfg<M, LM>;
   constexpr int D = Model<M>::D, P = Model<M>::P, HQ = Model<M>::HQ;
   constexpr int NM = C::NM, TILE = C::TILE, THREADS = C::THREADS, PPT = C::PPT, STAGES = C::STAGES;
+  constexpr bool kFullTile = PPT * THREADS == TILE;
   extern __shared__ __align__(128) unsigned char mm_smem_raw[];
   double* ring = reinterpret_cast<double*>(mm_smem_raw);                     // [STAGES][D][TILE]
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
@@ -334,8 +335,8 @@ __global__ void __launch_bounds__(MMCfg<M, LM>::THREADS, 1) mask_moments_kernel(
     for (int j = 0; j < P; j++) prm[j] = params_dev[j];
     prepare<M>(prm, hq);
   }
-  // the shift c of the centred components, once per thread (a load inside the inlier branch would put a global-memory latency
-  // on every row's critical path)
+  // the shift c of the centred components, once per thread (a load inside the loop would put a global-memory latency on every
+  // row's critical path)
   double ctr[D];
 #pragma unroll
   for (int d = 0; d < D; d++) ctr[d] = centred_comp(M, d) ? dv.center[d] : 0.0;
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(MMCfg<M, LM>::THREADS, 1) mask_moments_kernel(
   }
   __syncthreads();
   auto issue = [&](uint32_t k) {   // tile number k of this CTA into stage k % STAGES
-    const uint32_t s = k % STAGES;
+    const uint32_t s = k & (STAGES - 1);
     const size_t base = (size_t)(first + k * gridDim.x) * TILE;
     double* dst = ring + (size_t)s * D * TILE;
     mm_bar_expect_tx(&full_bar[s], (uint32_t)C::TILE_BYTES);
@@ -370,16 +371,62 @@ __global__ void __launch_bounds__(MMCfg<M, LM>::THREADS, 1) mask_moments_kernel(
   };
   if (tid == 0) for (uint32_t k = 0; k < (uint32_t)STAGES && k < n_mine; k++) issue(k);
 
+  // one tile: `checked` tiles straddle begin / end (at most two per launch) and test every row against the range
+  auto process = [&](const double (&x)[PPT][D], uint32_t base, bool checked) {
+    bool in[PPT], rowok[PPT];
+#pragma unroll
+    for (int u = 0; u < PPT; u++) {
+      const uint32_t p = u * THREADS + tid, i = base + p, row = i - lane;      // rows of 32 data start on multiples of 32
+      rowok[u] = (kFullTile || p < (uint32_t)TILE) && (!checked || (row >= begin && row < end));   // warp-uniform
+      const bool valid = rowok[u] && (!checked || i < end);
+      if (MODE == 0) in[u] = valid;
+      else if (MODE == 1) in[u] = valid && agree<M>(hq, x[u], cfg);   // NaN padding beyond n never agrees
+      else in[u] = valid && ((maskbits[row >> 5] >> lane) & 1u);
+    }
+    if (MODE == 1) {
+#pragma unroll
+      for (int u = 0; u < PPT; u++) {
+        const uint32_t p = u * THREADS + tid, i = base + p;
+        const unsigned bits = __ballot_sync(0xffffffffu, in[u]);
+        if (rowok[u]) {
+          if (lane == 0) maskbits[(i - lane) >> 5] = bits;
+          if (maskbytes != nullptr && i < end) maskbytes[i] = in[u] ? 1 : 0;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PPT; u++) {
+      if constexpr (C::BRANCHLESS) {
+        double q[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) q[d] = in[u] ? x[u][d] - ctr[d] : 0.0;
+        acc[0] += in[u] ? 1.0 : 0.0;
+        accumulate<M>(q, acc);
+      } else if (in[u]) {
+        double q[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) q[d] = x[u][d] - ctr[d];
+        if (LM) {
+          if constexpr (M == CIRCLE2) acc_sphere_lm<2>(q, lmx, acc);
+          if constexpr (M == SPHERE3) acc_sphere_lm<3>(q, lmx, acc);
+          if constexpr (M == SPHERE4) acc_sphere_lm<4>(q, lmx, acc);
+          if constexpr (M == USXW) acc_us_lm(q, lmx, acc);
+          if constexpr (M == USCP) acc_uscp_lm(q, lmx, acc);
+        } else { acc[0] += 1.0; accumulate<M>(q, acc); }
+      }
+    }
+  };
+
   for (uint32_t k = 0; k < n_mine; k++) {
-    const uint32_t s = k % STAGES, parity = (k / STAGES) & 1u;
-    const size_t base = (size_t)(first + k * gridDim.x) * TILE;
+    const uint32_t s = k & (STAGES - 1), parity = (k / STAGES) & 1u;
+    const uint32_t base = (first + k * gridDim.x) * (uint32_t)TILE;
     const double* tile = ring + (size_t)s * D * TILE;
     mm_bar_wait(&full_bar[s], parity);
     double x[PPT][D];
 #pragma unroll
     for (int u = 0; u < PPT; u++) {
       const uint32_t p = u * THREADS + tid;
-      if (PPT * THREADS == TILE || p < (uint32_t)TILE) {
+      if (kFullTile || p < (uint32_t)TILE) {
 #pragma unroll
         for (int d = 0; d < D; d++) x[u][d] = tile[d * TILE + p];
       }
@@ -388,33 +435,8 @@ __global__ void __launch_bounds__(MMCfg<M, LM>::THREADS, 1) mask_moments_kernel(
     __syncwarp();
     if (lane == 0) mm_bar_arrive(&empty_bar[s]);
     if (tid == 0 && k + STAGES < n_mine) { mm_bar_wait(&empty_bar[s], parity); issue(k + STAGES); }
-#pragma unroll
-    for (int u = 0; u < PPT; u++) {
-      const uint32_t p = u * THREADS + tid;
-      if (!(PPT * THREADS == TILE || p < (uint32_t)TILE)) break;
-      const uint64_t i = base + p, row = i - lane;      // rows of 32 data start on multiples of 32; begin is one, too
-      if (row < begin || row >= end) continue;          // warp-uniform
-      bool in;
-      if (MODE == 0) in = i < end;
-      else if (MODE == 1) {
-        in = (i < end) && agree<M>(hq, x[u], cfg);      // NaN padding beyond n never agrees
-        const unsigned bits = __ballot_sync(0xffffffffu, in);
-        if (lane == 0) maskbits[row >> 5] = bits;
-        if (maskbytes != nullptr && i < end) maskbytes[i] = in ? 1 : 0;
-      } else in = (i < end) && ((maskbits[row >> 5] >> lane) & 1u);
-      if (in) {
-        double q[D];
-#pragma unroll
-        for (int d = 0; d < D; d++) q[d] = centred_comp(M, d) ? x[u][d] - ctr[d] : x[u][d];
-        if (LM) {
-          if constexpr (M == CIRCLE2) acc_sphere_lm<2>(q, lmx, acc);
-          if constexpr (M == SPHERE3) acc_sphere_lm<3>(q, lmx, acc);
-          if constexpr (M == SPHERE4) acc_sphere_lm<4>(q, lmx, acc);
-          if constexpr (M == USXW) acc_us_lm(q, lmx, acc);
-          if constexpr (M == USCP) acc_uscp_lm(q, lmx, acc);
-        } else accumulate<M>(q, acc);
-      }
-    }
+    const bool checked = base < begin || (uint64_t)base + TILE > end;   // CTA-uniform
+    if (checked) process(x, base, true); else process(x, base, false);
   }
   if (LM && !active) return;   // partials, moments and the controller state keep their values
   // block reduction: shuffle within warps, shared memory across the warps
@@ -882,7 +904,7 @@ __device__ void block_moments(const double* pts, uint32_t n, uint32_t ldp, const
         if constexpr (M == CIRCLE2) acc_sphere_lm<2>(x, lmx, acc);
         if constexpr (M == SPHERE3) acc_sphere_lm<3>(x, lmx, acc);
         if constexpr (M == SPHERE4) acc_sphere_lm<4>(x, lmx, acc);
-      } else accumulate<M>(x, acc);
+      } else { acc[0] += 1.0; accumulate<M>(x, acc); }
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
