@@ -344,6 +344,9 @@ int comm_sum_f64(lsqr_ctx* ctx, double* dev, int count) {
   return 0;
 }
 
+// threads for staging copies between pageable and pinned memory: most of the cores, shared between the devices of a group
+int host_copy_threads(int W) { return std::min(12, std::max(1, ((int)std::thread::hardware_concurrency() * 3 / 4) / std::max(1, W))); }
+
 // ---- upload ----------------------------------------------------------------------------------------
 bool is_pinned(const void* p) {
   cudaPointerAttributes attr{};
@@ -381,13 +384,15 @@ int upload_to(lsqr_ctx* ctx, DataSet& ds, const void* aos, size_t n, size_t stri
   }
   const bool sharded = allow_sharded && ctx->comm != nullptr && ctx->world > 1;
   const int W = sharded ? ctx->world : 1;
-  // chunk: at least the centre sample, ~1/8 of a rank's share, between 256 KB and 16 MB
-  size_t chunk_rec = std::max<size_t>(kCenterSample, std::min<size_t>((16u << 20) / stride, std::max<size_t>((256u << 10) / stride, (n / W + 7) / 8)));
+  const bool pinned = is_pinned(aos);
+  // chunk: at least the centre sample, ~1/8 of a rank's share, between 256 KB and 16 MB (4 MB from pageable memory: the first
+  // copy cannot start before the first chunk has been staged)
+  const size_t chunk_cap = pinned ? (16u << 20) : (4u << 20);
+  size_t chunk_rec = std::max<size_t>(kCenterSample, std::min<size_t>(chunk_cap / stride, std::max<size_t>((256u << 10) / stride, (n / W + 7) / 8)));
   chunk_rec = round_up(chunk_rec, 1024);   // rounds start on tile boundaries of every consensus kernel
   const size_t chunk_bytes = chunk_rec * stride;
   const size_t n_chunks = (n + chunk_rec - 1) / chunk_rec, rounds = (n_chunks + W - 1) / W;
   if (int rc = ensure(ctx, &ctx->staging, &ctx->staging_cap, rounds * W * chunk_bytes)) return rc;
-  const bool pinned = is_pinned(aos);
   if (!pinned) {
     if (ctx->up_pin_bytes < chunk_bytes) {
       for (int i = 0; i < lsqr_ctx::kRing; i++) { if (ctx->up_pin[i]) cudaFreeHost(ctx->up_pin[i]); ctx->up_pin[i] = nullptr; }
@@ -396,7 +401,7 @@ int upload_to(lsqr_ctx* ctx, DataSet& ds, const void* aos, size_t n, size_t stri
       ctx->up_pin_bytes = chunk_bytes;
     }
     CK(cudaStreamSynchronize(ctx->copy_stream));   // an earlier upload may still be reading the pinned ring
-    if (!ctx->copier) ctx->copier.reset(new HostCopier(std::min(8, std::max(1, (int)std::thread::hardware_concurrency() / 2 / std::max(1, W)))));
+    if (!ctx->copier) ctx->copier.reset(new HostCopier(host_copy_threads(W)));
   }
   const unsigned char* host = static_cast<const unsigned char*>(aos);
   // the copy stream must not run ahead of work still reading the staging buffer
@@ -728,6 +733,14 @@ int refine_impl(lsqr_ctx* ctx, DataSet& ds, int use_mask, double* out_params, in
   return LSQR_OK;
 }
 
+// pinned -> pageable copy of a result, by the staging threads when it is large
+void host_copy(lsqr_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes >= (1u << 20)) {
+    if (!ctx->copier) ctx->copier.reset(new HostCopier(host_copy_threads(ctx->world > 1 && ctx->comm ? ctx->world : 1)));
+    ctx->copier->copy(dst, src, bytes);
+  } else memcpy(dst, src, bytes);
+}
+
 // Enqueues the copy of this rank's part of the consensus set (bytes [b, e) of out_bytes; everything when unsharded) and
 // reports whether a bounce through the pinned buffer has to be finished after the synchronisation.
 int mask_download_enqueue(lsqr_ctx* ctx, DataSet& ds, uint8_t* out_bytes, bool* bounce, uint32_t* pb, uint32_t* pe) {
@@ -758,7 +771,7 @@ int get_mask_impl(lsqr_ctx* ctx, DataSet& ds, uint8_t* out_bytes) {
   bool bounce; uint32_t b, e;
   if (int rc = mask_download_enqueue(ctx, ds, out_bytes, &bounce, &b, &e)) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
-  if (bounce) memcpy(out_bytes + b, ctx->mask_pin + b, e - b);
+  if (bounce) host_copy(ctx, out_bytes + b, ctx->mask_pin + b, e - b);
   return LSQR_OK;
 }
 
@@ -779,7 +792,7 @@ int finish_ransac(lsqr_ctx* ctx, const lsqr_score_result& best, uint8_t* out_mas
   if (int rc = refine_enqueue(ctx, ds, 1)) return rc;
   CK(cudaMemcpyAsync(ctx->pin + 1, ctx->small_dev + kSmOut, sizeof(double) * (1 + LSQR_MAX_PARAMS), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
-  if (bounce) memcpy(out_mask + b, ctx->mask_pin + b, e - b);
+  if (bounce) host_copy(ctx, out_mask + b, ctx->mask_pin + b, e - b);
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
   ctx->refine_kernel_ms = ms;

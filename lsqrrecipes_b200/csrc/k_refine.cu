@@ -278,12 +278,13 @@ __device__ __forceinline__ void mm_tma_g2s(void* dst, const void* src, uint32_t 
 // Blocking of the streaming pass: one persistent CTA per SM walks tiles of TILE data; a tile is D rows of TILE doubles in
 // shared memory, filled by D bulk copies (cp.async.bulk, one mbarrier per stage), STAGES tiles deep.  The bytes in flight per
 // SM are (STAGES - 1) tiles whatever the compute phase of the warps is -- what the register-staged version lacked
-// (profiles/r01_ncu_mask_moments_v2.txt: 25 % warps active, wait + long_scoreboard 60 %, 0.62 of HBM).
+// (profiles/r01_ncu_mask_moments_v2.txt: 25 % warps active, wait + long_scoreboard 60 %, 0.62 of HBM).  Tiles of ~48 KB
+// (2048 3-D points: four rows of 32 per thread, interleaved) x 4 stages measured best (profiles/r02_tune_mm.txt).
 #ifndef LSQR_MM_SMEM_KB
-#define LSQR_MM_SMEM_KB 160
+#define LSQR_MM_SMEM_KB 208
 #endif
 #ifndef LSQR_MM_TILE_KB
-#define LSQR_MM_TILE_KB 24
+#define LSQR_MM_TILE_KB 48
 #endif
 #ifndef LSQR_MM_THREADS
 #define LSQR_MM_THREADS 512
@@ -299,7 +300,7 @@ template <int M, bool LM> struct MMCfg {
   static constexpr int PPT = (TILE + THREADS - 1) / THREADS;                 // data per thread per tile
   static constexpr int TILE_BYTES = D * TILE * 8;
   static constexpr int kFit = LSQR_MM_SMEM_KB * 1024 / TILE_BYTES;
-  static constexpr int STAGES = kFit >= 8 ? 8 : (kFit >= 4 ? 4 : 2);         // a power of two: stage and phase are shifts and masks
+  static constexpr int STAGES = kFit >= 8 ? 8 : (kFit >= 2 ? kFit : 2);      // stage and phase are carried as counters, no division
   static constexpr size_t SMEM = (size_t)STAGES * TILE_BYTES;
   // light moment sets are accumulated without a branch (zeros for data outside the consensus set): the rows of a tile are
   // then independent straight-line chains that the scheduler interleaves; Levenberg-Marquardt rows (sqrt, division) and the
@@ -325,6 +326,28 @@ __global__ void __launch_bounds__(MMCfg<M, LM>::THREADS, 1) mask_moments_kernel(
   __shared__ double sh[THREADS / 32][NM > 0 ? NM : 1];
   const uint32_t tid = threadIdx.x, lane = tid & 31;
 
+  // LM passes are enqueued a few evaluations ahead of the controller's status word: once the iteration has stopped, the
+  // remaining passes are no-ops (the controller ignores the stale moments)
+  const bool active = !LM || lm_state[LM_STATUS] == 0.0;
+  // tiles [t0, t1) in units of TILE data cover [begin, end); this CTA takes t0 + blockIdx.x, + gridDim.x, ...
+  const uint32_t t0 = begin / TILE, t1 = (uint32_t)(((uint64_t)end + TILE - 1) / TILE);
+  const uint32_t first = t0 + blockIdx.x;
+  const uint32_t n_mine = (active && first < t1) ? (t1 - first + gridDim.x - 1) / gridDim.x : 0;
+  auto issue = [&](uint32_t k, uint32_t s) {   // tile number k of this CTA into stage s
+    const size_t base = (size_t)(first + k * gridDim.x) * TILE;
+    double* dst = ring + (size_t)s * D * TILE;
+    mm_bar_expect_tx(&full_bar[s], (uint32_t)C::TILE_BYTES);
+#pragma unroll
+    for (int d = 0; d < D; d++) mm_tma_g2s(dst + d * TILE, dv.soa64 + (size_t)d * dv.ld + base, TILE * 8, &full_bar[s]);
+  };
+  // the first tiles are on their way before anything else is set up
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) { mm_bar_init(&full_bar[s], 1); mm_bar_init(&empty_bar[s], THREADS / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (uint32_t k = 0; k < (uint32_t)STAGES && k < n_mine; k++) issue(k, k);
+  }
+
   double acc[NM > 0 ? NM : 1];
 #pragma unroll
   for (int j = 0; j < NM; j++) acc[j] = 0.0;
@@ -341,35 +364,13 @@ __global__ void __launch_bounds__(MMCfg<M, LM>::THREADS, 1) mask_moments_kernel(
 #pragma unroll
   for (int d = 0; d < D; d++) ctr[d] = centred_comp(M, d) ? dv.center[d] : 0.0;
   double lmx[LM ? Mom<M>::NPLM : 1] = {0};
-  bool active = true;
   if (LM) {
-    // the host enqueues evaluation passes a few iterations ahead of the controller's status word: once the iteration has
-    // stopped, the remaining passes are no-ops (the controller ignores the stale moments)
-    active = lm_state[LM_STATUS] == 0.0;
     // the phase selects the evaluation point: x or the trial point
     const int off = (lm_state[LM_PHASE] != 0.0) ? LM_TRIAL : LM_X;
 #pragma unroll
     for (int j = 0; j < Mom<M>::NPLM; j++) lmx[j] = lm_state[off + j];
   }
-  // tiles [t0, t1) in units of TILE data cover [begin, end); this CTA takes t0 + blockIdx.x, + gridDim.x, ...
-  const uint32_t t0 = begin / TILE, t1 = (uint32_t)(((uint64_t)end + TILE - 1) / TILE);
-  const uint32_t first = t0 + blockIdx.x;
-  const uint32_t n_mine = (active && first < t1) ? (t1 - first + gridDim.x - 1) / gridDim.x : 0;
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; s++) { mm_bar_init(&full_bar[s], 1); mm_bar_init(&empty_bar[s], THREADS / 32); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  auto issue = [&](uint32_t k) {   // tile number k of this CTA into stage k % STAGES
-    const uint32_t s = k & (STAGES - 1);
-    const size_t base = (size_t)(first + k * gridDim.x) * TILE;
-    double* dst = ring + (size_t)s * D * TILE;
-    mm_bar_expect_tx(&full_bar[s], (uint32_t)C::TILE_BYTES);
-#pragma unroll
-    for (int d = 0; d < D; d++) mm_tma_g2s(dst + d * TILE, dv.soa64 + (size_t)d * dv.ld + base, TILE * 8, &full_bar[s]);
-  };
-  if (tid == 0) for (uint32_t k = 0; k < (uint32_t)STAGES && k < n_mine; k++) issue(k);
+  __syncthreads();   // barriers initialised before anyone waits on them
 
   // one tile: `checked` tiles straddle begin / end (at most two per launch) and test every row against the range
   auto process = [&](const double (&x)[PPT][D], uint32_t base, bool checked) {
@@ -417,8 +418,8 @@ __global__ void __launch_bounds__(MMCfg<M, LM>::THREADS, 1) mask_moments_kernel(
     }
   };
 
+  uint32_t s = 0, parity = 0;
   for (uint32_t k = 0; k < n_mine; k++) {
-    const uint32_t s = k & (STAGES - 1), parity = (k / STAGES) & 1u;
     const uint32_t base = (first + k * gridDim.x) * (uint32_t)TILE;
     const double* tile = ring + (size_t)s * D * TILE;
     mm_bar_wait(&full_bar[s], parity);
@@ -434,7 +435,10 @@ __global__ void __launch_bounds__(MMCfg<M, LM>::THREADS, 1) mask_moments_kernel(
     // the stage is free as soon as every warp holds its data in registers; thread 0 refills it STAGES tiles ahead
     __syncwarp();
     if (lane == 0) mm_bar_arrive(&empty_bar[s]);
-    if (tid == 0 && k + STAGES < n_mine) { mm_bar_wait(&empty_bar[s], parity); issue(k + STAGES); }
+    if (tid == 0 && k + STAGES < n_mine) { mm_bar_wait(&empty_bar[s], parity); issue(k + STAGES, s); }
+    const uint32_t s_next = (s + 1 == (uint32_t)STAGES) ? 0u : s + 1;
+    parity ^= (s_next == 0u) ? 1u : 0u;
+    s = s_next;
     const bool checked = base < begin || (uint64_t)base + TILE > end;   // CTA-uniform
     if (checked) process(x, base, true); else process(x, base, false);
   }

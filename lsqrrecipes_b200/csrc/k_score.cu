@@ -65,25 +65,41 @@ __host__ __device__ inline bool centred_component(int model, int d) {
 // The shift c: per-component mean of the first `count` records (count <= kCenterSample), fixed-order tree sum.  c only
 // conditions the arithmetic (fp32 copy of x - c, moments of x - c); any point near the data does, and a prefix is known
 // as soon as the first chunk has landed.
-__global__ void center_sample_kernel(int model, int D, const unsigned char* __restrict__ aos, size_t stride, uint32_t count, double* __restrict__ center) {
-  __shared__ double sh[256];
+__global__ void __launch_bounds__(1024) center_sample_kernel(int model, int D, const unsigned char* __restrict__ aos, size_t stride, uint32_t count, double* __restrict__ center) {
+  __shared__ double sh[32][kMaxDim];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double acc[kMaxDim];
+#pragma unroll
+  for (int d = 0; d < kMaxDim; d++) acc[d] = 0.0;
+  // a thread reads whole records (the D doubles of one record share cache lines); 16 records per thread for the full sample
+#pragma unroll 4
+  for (uint32_t i = tid; i < count; i += blockDim.x) {
+    const double* rec = reinterpret_cast<const double*>(aos + (size_t)i * stride);
+#pragma unroll
+    for (int d = 0; d < kMaxDim; d++) if (d < D) acc[d] += rec[d];
+  }
+  // fixed-order tree: lanes, then warps
+#pragma unroll
   for (int d = 0; d < kMaxDim; d++) {
-    double acc = 0.0;
-    const bool on = d < D && centred_component(model, d);   // uniform
-    if (on) for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) acc += reinterpret_cast<const double*>(aos + (size_t)i * stride)[d];
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
-    if (threadIdx.x == 0) {
-      double m = (on && count > 0) ? sh[0] / (double)count : 0.0;
+    double v = acc[d];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[warp][d] = v;
+  }
+  __syncthreads();
+  if (tid < kMaxDim) {
+    const int d = (int)tid;
+    double m = 0.0;
+    if (d < D && centred_component(model, d) && count > 0) {
+      for (uint32_t w = 0; w < (blockDim.x >> 5); w++) m += sh[w][d];
+      m /= (double)count;
       if (!(m == m) || fabs(m) > 1e300) m = 0.0;
-      center[d] = m;
     }
-    __syncthreads();
+    center[d] = m;
   }
 }
 void launch_center_sample(int model, const unsigned char* aos_dev, size_t stride, uint32_t count, double* center_dev, cudaStream_t s) {
-  center_sample_kernel<<<1, 256, 0, s>>>(model, model_info(model).D, aos_dev, stride, count, center_dev);
+  center_sample_kernel<<<1, 1024, 0, s>>>(model, model_info(model).D, aos_dev, stride, count, center_dev);
 }
 
 // records [first, first + count) of the AoS buffer (record i at aos + i * stride); when pad_to > first + count the columns
