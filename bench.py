@@ -26,10 +26,13 @@ sys.path.insert(0, ROOT)
 
 # SURVEY.md 8d accounting: FMA-pipe lane-ops per evaluation in the minimal fused form with per-hypothesis constants hoisted
 # (an FFMA, FADD or FMUL each hold one lane of the pipe for one issue), and the same in flop (FFMA = 2).
-#   kD line: d FADD + 2 x (1 FMUL + (d-1) FFMA) + 1 FFMA = 3d + 1;  hypersphere: d FADD + 1 FMUL + (d-1) FFMA = 2d
-OPS_PER_EVAL = {"plane3": 3, "plane4": 4, "line2d": 2, "line2": 7, "line3": 10, "circle2": 4, "sphere3": 6, "sphere4": 8, "absor": 15, "ray": 12,
+#   hypersphere: d FADD + 1 FMUL + (d-1) FFMA = 2d.  kD line: SURVEY charges 3d + 1 (d FADD + 2 x (1 FMUL + (d-1) FFMA) + 1 FFMA,
+#   the |v|^2 - (v.n)^2 form, which cancels catastrophically in fp32 for coordinates of +-1000); the kernel issues FEWER
+#   operations in a form that does not cancel -- d = 2: the 2-D line form on the perpendicular, 2 FFMA; d = 3: the Pluecker form
+#   |x X n - m|^2, 9 FFMA -- and the fraction is charged with what it issues.
+OPS_PER_EVAL = {"plane3": 3, "plane4": 4, "line2d": 2, "line2": 2, "line3": 9, "circle2": 4, "sphere3": 6, "sphere4": 8, "absor": 15, "ray": 12,
                 "pivot": 15, "dense5": 5, "dense6": 6, "usxw": 21, "uscp": 21}
-FLOP_PER_EVAL = {"plane3": 6, "plane4": 8, "line2d": 4, "line2": 10, "line3": 15, "circle2": 5, "sphere3": 8, "sphere4": 11, "absor": 26, "ray": 19,
+FLOP_PER_EVAL = {"plane3": 6, "plane4": 8, "line2d": 4, "line2": 4, "line3": 18, "circle2": 5, "sphere3": 8, "sphere4": 11, "absor": 26, "ray": 19,
                  "pivot": 26, "dense5": 10, "dense6": 12, "usxw": 39, "uscp": 39}
 LANEOPS_PER_EVAL = OPS_PER_EVAL
 

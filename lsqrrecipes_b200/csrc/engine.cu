@@ -377,7 +377,7 @@ int upload_to(lsqr_ctx* ctx, DataSet& ds, const void* aos, size_t n, size_t stri
   if (on_device || n == 0) {
     const unsigned char* src = static_cast<const unsigned char*>(aos);
     launch_center_sample(ctx->model, src, stride, sample, ds.center_dev, s);
-    launch_ingest(mi.D, src, stride, 0, N, pad_to, ds.center_dev, ds.soa64, ds.soa32, ds.ld, s);
+    launch_ingest(ctx->model, src, stride, 0, N, pad_to, ds.center_dev, ds.soa64, ds.soa32, ds.ld, s);
     ctx->launches += 2;
     CKL();
     return LSQR_OK;
@@ -432,7 +432,7 @@ int upload_to(lsqr_ctx* ctx, DataSet& ds, const void* aos, size_t n, size_t stri
     if (j == 0) { launch_center_sample(ctx->model, ctx->staging, stride, sample, ds.center_dev, s); ctx->launches++; }
     const size_t r_lo = std::min(n, j * W * chunk_rec), r_hi = std::min(n, (j + 1) * W * chunk_rec);
     const bool last = j + 1 == rounds;
-    launch_ingest(mi.D, ctx->staging, stride, (uint32_t)r_lo, (uint32_t)(r_hi - r_lo), last ? pad_to : (uint32_t)r_hi, ds.center_dev, ds.soa64, ds.soa32, ds.ld, s);
+    launch_ingest(ctx->model, ctx->staging, stride, (uint32_t)r_lo, (uint32_t)(r_hi - r_lo), last ? pad_to : (uint32_t)r_hi, ds.center_dev, ds.soa64, ds.soa32, ds.ld, s);
     ctx->launches++;
     if (after_round) if (int rc = (*after_round)(r_lo, r_hi, j == 0, last)) return rc;
   }

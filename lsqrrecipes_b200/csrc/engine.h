@@ -38,7 +38,7 @@ struct WinnerRecord {
 void launch_center_sample(int model, const unsigned char* aos_dev, size_t stride, uint32_t count, double* center_dev, cudaStream_t s);
 // AoS records [first, first + count) (stride bytes, D leading doubles each) -> SoA fp64 and SoA fp32 of x - c; columns up to
 // pad_to are NaN-filled.
-void launch_ingest(int D, const unsigned char* aos_dev, size_t stride, uint32_t first, uint32_t count, uint32_t pad_to, const double* center_dev,
+void launch_ingest(int model, const unsigned char* aos_dev, size_t stride, uint32_t first, uint32_t count, uint32_t pad_to, const double* center_dev,
                    double* soa64, float* soa32, size_t ld, cudaStream_t s);
 
 struct SolveArgs {

@@ -54,6 +54,7 @@ struct f2 { unsigned long long v; };
 __device__ __forceinline__ f2 splat(float a) { f2 r; asm("mov.b64 %0, {%1, %1};" : "=l"(r.v) : "f"(a)); return r; }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 __device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 __device__ __forceinline__ void halves(f2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
 __device__ __forceinline__ f2 join(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
@@ -63,13 +64,14 @@ __device__ __forceinline__ f2 join(float lo, float hi) { f2 r; asm("mov.b64 %0, 
 // (positions are stored as x - c in fp32) and the thresholds:
 //   PLANE3   (nx,ny,nz, delta - n.(a-c))      the kernels form s' = s + delta and test 0 <= s' < 2 delta (see count_carry)
 //   LINE2D   (nx,ny, -n.(a-c))                 |s| < delta (two FFMA2 per pair leave the ALU pipe as the limit either way; measured: the carry form is 4 % slower here)
-//   LINE2/3  (dir, a-c)
+//   LINE2    (n_perp, -n_perp.(a-c))            the 2-D line form on the perpendicular of the unit direction
+//   LINE3    3 x (n_k, -n_j, -((a-c) x n)_i)    Pluecker form
 //   CIRCLE/SPHERE (ctr-c, -(r-delta)^2, 2^32 - bits(4 r delta)): t' = d^2 - (r-delta)^2, inlier <=> 0 <= t' < 4 r delta  (<=> |d - r| < delta)
 //   ABSOR    (R[9], R c1 + t - c2)
 //   RAY      (x - c)
-//   PIVOT    (tDRF, tW - c)
+//   PIVOT    (tDRF, -(tW - c))
 //   DENSE n  (x[n], -1, delta): a.x - b + delta as n+1 FMAs over the (uncentred) augmented row
-//   USXW     (m_x R3(:,1), m_y R3(:,2), t3, t1 - c)
+//   USXW     (m_x R3(:,1), m_y R3(:,2), t3, -(t1 - c))
 //   USCP     (m_x R3(:,1), m_y R3(:,2), t3)
 template <int M> __device__ __forceinline__ void hoist32(const double* p, const double* c, const EstCfg& cfg, float* q);
 template <> __device__ __forceinline__ void hoist32<PLANE3>(const double* p, const double* c, const EstCfg& cfg, float* q) {
@@ -85,11 +87,26 @@ template <> __device__ __forceinline__ void hoist32<LINE2D>(const double* p, con
   q[0] = (float)p[0]; q[1] = (float)p[1];
   q[2] = (float)(-(p[0] * (p[2] - c[0]) + p[1] * (p[3] - c[1])));
 }
+// kD lines (LineParametersEstimator.hxx:135-150: |v - (v.n) n|^2 < delta^2 with v = x - a).  The fast mode takes the direction as
+// the unit vector it is for every hypothesis estimate() produces (it is re-normalised here, a no-op then), which makes the
+// rejection |v x n| in 3-D and |n_perp . v| in 2-D:
+//   d = 2: the 2-D line form, s = n_perp . x - n_perp . (a - c)                                        2 FMA per datum
+//   d = 3: Pluecker form, w = x X n - (a - c) X n, every component two FMAs on a hoisted constant:      6 + 3 FMA per datum
+// instead of the 9 / 12 operations of the literal form.  The validation mode keeps the literal form (models.cuh).
 template <> __device__ __forceinline__ void hoist32<LINE2>(const double* p, const double* c, const EstCfg&, float* q) {
-  q[0] = (float)p[0]; q[1] = (float)p[1]; q[2] = (float)(p[2] - c[0]); q[3] = (float)(p[3] - c[1]);
+  const double inv = 1.0 / sqrt(p[0] * p[0] + p[1] * p[1]);
+  const double px = -p[1] * inv, py = p[0] * inv;
+  q[0] = (float)px; q[1] = (float)py;
+  q[2] = (float)(-(px * (p[2] - c[0]) + py * (p[3] - c[1])));
 }
 template <> __device__ __forceinline__ void hoist32<LINE3>(const double* p, const double* c, const EstCfg&, float* q) {
-  for (int i = 0; i < 3; i++) { q[i] = (float)p[i]; q[3 + i] = (float)(p[3 + i] - c[i]); }
+  const double inv = 1.0 / sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+  const double n[3] = {p[0] * inv, p[1] * inv, p[2] * inv}, a[3] = {p[3] - c[0], p[4] - c[1], p[5] - c[2]};
+  // w_i = x_j n_k - x_k n_j - (a_j n_k - a_k n_j)   with (i, j, k) cyclic: constants (n_k, -n_j, -m_i) per component
+  for (int i = 0; i < 3; i++) {
+    const int j = (i + 1) % 3, k = (i + 2) % 3;
+    q[3 * i] = (float)n[k]; q[3 * i + 1] = (float)(-n[j]); q[3 * i + 2] = (float)(-(a[j] * n[k] - a[k] * n[j]));
+  }
 }
 // |d - r| < delta  <=>  (r - delta)^2 <= d^2 < (r + delta)^2  <=>  0 <= t' < 4 r delta  with  t' = d^2 - (r - delta)^2: the chain
 // starts at -(r - delta)^2 and the datum is an inlier iff bits(t') < bits(4 r delta) as unsigned integers (count_carry; the
@@ -119,7 +136,7 @@ template <> __device__ __forceinline__ void hoist32<RAY>(const double* p, const 
   for (int i = 0; i < 3; i++) q[i] = (float)(p[i] - c[i]);
 }
 template <> __device__ __forceinline__ void hoist32<PIVOT>(const double* p, const double* c, const EstCfg&, float* q) {
-  for (int i = 0; i < 3; i++) { q[i] = (float)p[i]; q[3 + i] = (float)(p[3 + i] - c[9 + i]); }
+  for (int i = 0; i < 3; i++) { q[i] = (float)p[i]; q[3 + i] = (float)(-(p[3 + i] - c[9 + i])); }   // the chain starts at -(tW - c)
 }
 
 template <int N> __device__ __forceinline__ void hoist_dense(const double* p, const EstCfg& cfg, float* q) {
@@ -132,7 +149,7 @@ template <> __device__ __forceinline__ void hoist32<DENSE6>(const double* p, con
 
 template <> __device__ __forceinline__ void hoist32<USXW>(const double* p, const double* c, const EstCfg&, float* q) {
   for (int i = 0; i < 6; i++) q[i] = (float)p[11 + i];
-  for (int i = 0; i < 3; i++) { q[6 + i] = (float)p[3 + i]; q[9 + i] = (float)(p[i] - c[9 + i]); }
+  for (int i = 0; i < 3; i++) { q[6 + i] = (float)p[3 + i]; q[9 + i] = (float)(-(p[i] - c[9 + i])); }   // the chain starts at -(t1 - c)
 }
 
 template <> __device__ __forceinline__ void hoist32<USCP>(const double* p, const double*, const EstCfg&, float* q) {
@@ -235,32 +252,30 @@ template <> struct Eval<LINE2D> {
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return fma2(q[0], x[0], fma2(q[1], x[1], q[2])); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
 };
-template <int DIM> __device__ __forceinline__ f2 line_signed(const f2* q, const f2* x, const Thr2& t) {
-  f2 v[DIM], vn;
-#pragma unroll
-  for (int i = 0; i < DIM; i++) v[i] = sub2(x[i], q[DIM + i]);
-  vn = mul2(v[0], q[0]);
-#pragma unroll
-  for (int i = 1; i < DIM; i++) vn = fma2(v[i], q[i], vn);
-  const f2 nvn = sub2(splat(0.f), vn);
-  f2 g = t.neg_delta2;
-#pragma unroll
-  for (int i = 0; i < DIM; i++) { const f2 w = fma2(nvn, q[i], v[i]); g = fma2(w, w, g); }
-  return g;
-}
-template <> struct Eval<LINE2> {
-  static constexpr bool kHasAbsForm = false;
+// Every instruction below takes at most ONE datum operand: in the constant-bank kernel the data are uniform registers and an
+// FFMA2 / FADD2 encodes a single uniform source -- a second one forces ptxas to fetch the datum with LDC into ordinary
+// registers (indexed constant loads, a quarter of the throughput: measured on the pivot estimator, 0.7 -> 2.3 T evals/s).
+template <> struct Eval<LINE2> {     // the 2-D line form on the perpendicular (see hoist32<LINE2>)
+  static constexpr bool kHasAbsForm = true;
   static constexpr int kThr = -1;
   static constexpr bool kShifted = false;
-  __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
-  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { return line_signed<2>(q, x, t); }
+  __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return fma2(q[0], x[0], fma2(q[1], x[1], q[2])); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = dist(q, x); return fma2(s, s, t.neg_delta2); }
 };
-template <> struct Eval<LINE3> {
+template <> struct Eval<LINE3> {     // Pluecker form: |x X n - m|^2 - delta^2 (see hoist32<LINE3>)
   static constexpr bool kHasAbsForm = false;
   static constexpr int kThr = -1;
   static constexpr bool kShifted = false;
   __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
-  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { return line_signed<3>(q, x, t); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) {
+    f2 g = t.neg_delta2;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const f2 w = fma2(x[(i + 1) % 3], q[3 * i], fma2(x[(i + 2) % 3], q[3 * i + 1], q[3 * i + 2]));
+      g = fma2(w, w, g);
+    }
+    return g;
+  }
 };
 // t' = d^2 - (r - delta)^2 (chain start q[DIM]); per-hypothesis window q[DIM + 1] = 4 r delta (see hoist_sphere)
 template <int DIM> __device__ __forceinline__ f2 sphere_t(const f2* q, const f2* x) {
@@ -320,7 +335,7 @@ template <> struct Eval<PIVOT> {
     f2 g = t.neg_delta2;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-      const f2 d = sub2(fma2(x[3 * i], q[0], fma2(x[3 * i + 1], q[1], fma2(x[3 * i + 2], q[2], x[9 + i]))), q[3 + i]);
+      const f2 d = add2(fma2(q[0], x[3 * i], fma2(q[1], x[3 * i + 1], fma2(q[2], x[3 * i + 2], q[3 + i]))), x[9 + i]);
       g = fma2(d, d, g);
     }
     return g;
@@ -363,14 +378,14 @@ template <> struct Eval<USXW> {
     f2 g = t.neg_delta2;
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-      const f2 e = sub2(fma2(x[3 * r], w[0], fma2(x[3 * r + 1], w[1], fma2(x[3 * r + 2], w[2], x[9 + r]))), q[9 + r]);
+      const f2 e = add2(fma2(x[3 * r], w[0], fma2(x[3 * r + 1], w[1], fma2(x[3 * r + 2], w[2], q[9 + r]))), x[9 + r]);
       g = fma2(e, e, g);
     }
     return g;
   }
 };
 
-// calibrated pointer: e = R2 (u c1 + v c2 + t3) + t2 - p
+// calibrated pointer: e = R2 (u c1 + v c2 + t3) + (t2 - p); the difference t2 - p is formed in fp64 when the fp32 copy is written
 template <> struct Eval<USCP> {
   static constexpr bool kHasAbsForm = false;
   static constexpr int kThr = -1;
@@ -383,7 +398,7 @@ template <> struct Eval<USCP> {
     f2 g = t.neg_delta2;
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-      const f2 e = sub2(fma2(x[3 * r], w[0], fma2(x[3 * r + 1], w[1], fma2(x[3 * r + 2], w[2], x[9 + r]))), x[14 + r]);
+      const f2 e = add2(fma2(x[3 * r], w[0], fma2(x[3 * r + 1], w[1], mul2(x[3 * r + 2], w[2]))), x[9 + r]);   // rows 9..11 of the fp32 copy hold t2 - p (ingest_kernel)
       g = fma2(e, e, g);
     }
     return g;
@@ -649,41 +664,44 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
   }
 }
 
-// Hypotheses per thread / point pairs per iteration of the constant-bank kernel (128 threads), from the sweep in
-// profiles/r01_tune_cb_sweep_models.txt.  Few hypotheses per thread (R = 4, 5) on a model with few operations per datum
-// make the uniform constant loads (D per point pair) the limit: 3-8x slower, see the plane4 / dense5 columns there.
+// Hypotheses per thread (R) / point pairs per iteration (PPI) of the constant-bank kernel (128 threads), from the sweeps in
+// profiles/r01_tune_cb_sweep_models.txt and profiles/r02_tune_cb_blocking.txt.  Two things decide them:
+//   * few hypotheses per thread on a model with few operations per datum make the uniform constant loads (D per point pair)
+//     the limit: 3-8x slower, see the plane4 / dense5 columns of the first sweep;
+//   * ptxas fetches the data with LDCU into uniform registers only when a loaded pair has enough consumers in the loop body;
+//     below that it falls back to indexed LDC.64 into ordinary registers, which an SM sub-partition sustains at about one
+//     per 38 cycles (pivot at R = 6, PPI = 1: 12 LDC.64 per 90 FFMA2, 0.70 T evals/s; at R = 8, PPI = 2 the same body
+//     uses LDCU).  tests/test_sass_cpu.py pins "no LDC c[0x3] in the loop" for every model.
 #ifndef LSQR_CB_THREADS
 #define LSQR_CB_THREADS 128
 #endif
 #ifndef LSQR_CB_R_PLANE
 #define LSQR_CB_R_PLANE 10
 #endif
-#ifdef LSQR_CB_SWEEP_R   // R&D builds (tools/build_variants.sh): one blocking for every model that can take it
-template <int M> struct BlockCB { static constexpr int R = LSQR_CB_SWEEP_R, PPI = LSQR_CB_SWEEP_PPI; };
-template <> struct BlockCB<PIVOT> { static constexpr int R = 6, PPI = 1; };
-template <> struct BlockCB<USXW> { static constexpr int R = 4, PPI = 1; };
-template <> struct BlockCB<USCP> { static constexpr int R = 4, PPI = 1; };
-#else
-template <int M> struct BlockCB { static constexpr int R = 8, PPI = 2; };
 #ifndef LSQR_CB_PPI_PLANE
 #define LSQR_CB_PPI_PLANE 4
 #endif
-template <> struct BlockCB<PLANE3> { static constexpr int R = LSQR_CB_R_PLANE, PPI = LSQR_CB_PPI_PLANE; };
-template <> struct BlockCB<LINE2D> { static constexpr int R = 10, PPI = 4; };
-template <> struct BlockCB<LINE2> { static constexpr int R = 6, PPI = 4; };
-template <> struct BlockCB<LINE3> { static constexpr int R = 8, PPI = 2; };
-template <> struct BlockCB<CIRCLE2> { static constexpr int R = 12, PPI = 2; };
-template <> struct BlockCB<SPHERE3> { static constexpr int R = 10, PPI = 2; };
-template <> struct BlockCB<ABSOR> { static constexpr int R = 4, PPI = 4; };
-template <> struct BlockCB<RAY> { static constexpr int R = 8, PPI = 4; };
-template <> struct BlockCB<PIVOT> { static constexpr int R = 6, PPI = 1; };
-template <> struct BlockCB<DENSE5> { static constexpr int R = 8, PPI = 4; };
-template <> struct BlockCB<DENSE6> { static constexpr int R = 8, PPI = 4; };
-template <> struct BlockCB<USXW> { static constexpr int R = 4, PPI = 1; };
-template <> struct BlockCB<USCP> { static constexpr int R = 4, PPI = 1; };
-template <> struct BlockCB<SPHERE4> { static constexpr int R = 8, PPI = 4; };
-template <> struct BlockCB<PLANE4> { static constexpr int R = 8, PPI = 4; };
+constexpr int cb_blocking(int m, bool want_r) {
+#ifdef LSQR_CB_OVR_MODEL      // R&D builds (tools/build_variants.sh): override one model
+  if (m == LSQR_CB_OVR_MODEL) return want_r ? LSQR_CB_OVR_R : LSQR_CB_OVR_PPI;
 #endif
+  int r = 8, ppi = 2;
+  switch (m) {
+    case PLANE3: r = LSQR_CB_R_PLANE; ppi = LSQR_CB_PPI_PLANE; break;
+    case LINE2D: case LINE2: r = 16; ppi = 4; break;
+    case LINE3: r = 8; ppi = 2; break;
+    case CIRCLE2: r = 12; ppi = 2; break;
+    case SPHERE3: r = 10; ppi = 2; break;
+    case ABSOR: r = 4; ppi = 4; break;
+    case RAY: r = 8; ppi = 4; break;
+    case PIVOT: r = 8; ppi = 2; break;
+    case DENSE5: case DENSE6: case SPHERE4: case PLANE4: r = 8; ppi = 4; break;
+    case USXW: case USCP: r = 4; ppi = 2; break;
+    default: break;
+  }
+  return want_r ? r : ppi;
+}
+template <int M> struct BlockCB { static constexpr int R = cb_blocking(M, true), PPI = cb_blocking(M, false); };
 
 template <int M>
 static int run_consensus_cb(const DataView& dv, const float* hyp, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms, cudaStream_t s) {

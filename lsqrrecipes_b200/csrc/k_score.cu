@@ -104,7 +104,8 @@ void launch_center_sample(int model, const unsigned char* aos_dev, size_t stride
 
 // records [first, first + count) of the AoS buffer (record i at aos + i * stride); when pad_to > first + count the columns
 // [first + count, pad_to) are filled with NaN (padded data can never agree)
-__global__ void ingest_kernel(int D, const unsigned char* __restrict__ aos, size_t stride, uint32_t first, uint32_t count, uint32_t pad_to,
+// (calibrated-pointer ultrasound records: rows 9..11 of the fp32 copy hold t2 - p, formed in fp64, rows 14..16 are unused)
+__global__ void ingest_kernel(int model, int D, const unsigned char* __restrict__ aos, size_t stride, uint32_t first, uint32_t count, uint32_t pad_to,
                               const double* __restrict__ center, double* __restrict__ soa64, float* __restrict__ soa32, size_t ld) {
   const size_t i = (size_t)first + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < (size_t)first + count) {
@@ -112,18 +113,20 @@ __global__ void ingest_kernel(int D, const unsigned char* __restrict__ aos, size
     for (int d = 0; d < D; d++) {
       const double v = rec[d];
       soa64[(size_t)d * ld + i] = v;
-      soa32[(size_t)d * ld + i] = (float)(v - center[d]);
+      float f = (float)(v - center[d]);
+      if (model == USCP && d >= 9) f = (d < 12) ? (float)(v - rec[d + 5]) : (d >= 14 ? 0.0f : f);
+      soa32[(size_t)d * ld + i] = f;
     }
   } else if (i < pad_to) {
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     for (int d = 0; d < D; d++) { soa64[(size_t)d * ld + i] = nan; soa32[(size_t)d * ld + i] = __int_as_float(0x7fc00000); }
   }
 }
-void launch_ingest(int D, const unsigned char* aos_dev, size_t stride, uint32_t first, uint32_t count, uint32_t pad_to, const double* center_dev,
+void launch_ingest(int model, const unsigned char* aos_dev, size_t stride, uint32_t first, uint32_t count, uint32_t pad_to, const double* center_dev,
                    double* soa64, float* soa32, size_t ld, cudaStream_t s) {
   const size_t span = (size_t)(pad_to > first + count ? pad_to : first + count) - first;
   if (span == 0) return;
-  ingest_kernel<<<(unsigned)((span + 255) / 256), 256, 0, s>>>(D, aos_dev, stride, first, count, pad_to, center_dev, soa64, soa32, ld);
+  ingest_kernel<<<(unsigned)((span + 255) / 256), 256, 0, s>>>(model, model_info(model).D, aos_dev, stride, first, count, pad_to, center_dev, soa64, soa32, ld);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -21,8 +21,8 @@ enum : int { PLANE3 = 0, LINE2D = 1, LINE2 = 2, LINE3 = 3, CIRCLE2 = 4, SPHERE3 
 template <int M> struct Model;
 template <> struct Model<PLANE3>  { static constexpr int D = 3,  P = 6, K = 3, HQ = 6,  Q32 = 4;  };
 template <> struct Model<LINE2D>  { static constexpr int D = 2,  P = 4, K = 2, HQ = 4,  Q32 = 3;  };
-template <> struct Model<LINE2>   { static constexpr int D = 2,  P = 4, K = 2, HQ = 4,  Q32 = 4;  };
-template <> struct Model<LINE3>   { static constexpr int D = 3,  P = 6, K = 2, HQ = 6,  Q32 = 6;  };
+template <> struct Model<LINE2>   { static constexpr int D = 2,  P = 4, K = 2, HQ = 4,  Q32 = 3;  };
+template <> struct Model<LINE3>   { static constexpr int D = 3,  P = 6, K = 2, HQ = 6,  Q32 = 9;  };
 template <> struct Model<CIRCLE2> { static constexpr int D = 2,  P = 3, K = 3, HQ = 3,  Q32 = 4;  };
 template <> struct Model<SPHERE3> { static constexpr int D = 3,  P = 4, K = 4, HQ = 4,  Q32 = 5;  };
 template <> struct Model<ABSOR>   { static constexpr int D = 6,  P = 7, K = 3, HQ = 12, Q32 = 12; };
@@ -45,8 +45,8 @@ __host__ __device__ inline ModelInfo model_info(int m) {
   switch (m) {
     case PLANE3:  return {3, 6, 3, 6, 4};
     case LINE2D:  return {2, 4, 2, 4, 3};
-    case LINE2:   return {2, 4, 2, 4, 4};
-    case LINE3:   return {3, 6, 2, 6, 6};
+    case LINE2:   return {2, 4, 2, 4, 3};
+    case LINE3:   return {3, 6, 2, 6, 9};
     case CIRCLE2: return {2, 3, 3, 3, 4};
     case SPHERE3: return {3, 4, 4, 4, 5};
     case ABSOR:   return {6, 7, 3, 12, 12};

@@ -61,6 +61,9 @@ def test_fp32_mode_vs_fp64_mode_131072_hypotheses_x_10m_points(plane10m):
     assert np.all(diff[ok] <= (hi - lo)[ok]), "an fp32 decision differs outside the rounding band of the threshold"
     assert np.all(c32[~ok] == 0) and np.all(c64[~ok] == 0)
     # ... and the band is narrow: it holds a vanishing share of the data, so do the differences
-    assert (hi - lo)[ok].sum() <= 2e-3 * c64[ok].sum()
+    # (data spread evenly over the slab of half-width delta put 2 band / delta of the count inside the band; the synthetic
+    # inliers are denser near the plane than at the threshold, so that is an upper estimate -- allow it once over)
+    assert band <= 1e-6 * np.abs(data).max(), "the band must stay within the north star's 1e-6 of the coordinate scale"
+    assert (hi - lo)[ok].sum() <= 4 * band / delta * c64[ok].sum()
     assert diff[ok].sum() <= 2e-5 * c64[ok].sum()
     assert int(np.argmax(c32)) == int(np.argmax(c64)) or abs(int(c32.max()) - int(c64.max())) <= int((hi - lo)[int(np.argmax(c64))])

@@ -74,3 +74,16 @@ def test_shared_memory_kernel_is_fed_by_tma(sass):
     ins = _one(sass, r"consensus32_kernelILi0ELi9ELi256ELi512ELi2E")
     assert any(i.startswith("UBLKCP") for i in ins), "cp.async.bulk (TMA) must be present"
     assert any("SYNCS" in i for i in ins), "mbarrier wait"
+
+
+@pytest.mark.parametrize("model", range(15))
+def test_constant_bank_kernels_read_their_points_through_uniform_registers(sass, model):
+    """Every consensus_cb_kernel<M>: the points of the launch come out of the constant bank with LDCU (uniform registers) and
+    never with an indexed LDC into ordinary registers -- ptxas falls back to that when a loaded pair has too few consumers in
+    the loop body or an instruction names two data operands, and an SM sub-partition sustains only about one LDC.64 per 38
+    cycles (the pivot estimator ran at 0.28 of the FP32 pipe that way, k_fast.cu BlockCB)."""
+    ins = _one(sass, rf"consensus_cb_kernelILi{model}ELi\d+ELi128ELi\dE")
+    assert not [i for i in ins if re.match(r"LDC(\.\d+)? R\d+, c\[0x3\]", i)], "indexed constant loads of the data"
+    assert sum(i.startswith("LDCU.64") or i.startswith("LDCU.128") for i in ins) >= 4
+    packed = [i for i in ins if i.startswith(("FFMA2", "FADD2", "FMUL2"))]
+    assert sum("UR" in i for i in packed) >= len(packed) // 2, "most packed operations take their datum from a uniform register"
