@@ -34,6 +34,16 @@ OPS_PER_EVAL = {"plane3": 3, "plane4": 4, "line2d": 2, "line2": 2, "line3": 9, "
                 "pivot": 15, "dense5": 5, "dense6": 6, "usxw": 21, "uscp": 21}
 FLOP_PER_EVAL = {"plane3": 6, "plane4": 8, "line2d": 4, "line2": 4, "line3": 18, "circle2": 5, "sphere3": 8, "sphere4": 11, "absor": 26, "ray": 19,
                  "pivot": 26, "dense5": 10, "dense6": 12, "usxw": 39, "uscp": 39}
+# the wider template space: hyperplane d FFMA, hypersphere 2d, dense system n, kD line in the literal
+# form 4d (d FADD + d FFMA + d FFMA + d FFMA; the |v|^2 - (v.n)^2 form SURVEY counts, 3d + 1, cancels in fp32)
+for _d in (2, 5, 6, 7, 8):
+    OPS_PER_EVAL[f"plane{_d}"], FLOP_PER_EVAL[f"plane{_d}"] = _d, 2 * _d
+for _d in (5, 6, 7, 8):
+    OPS_PER_EVAL[f"sphere{_d}"], FLOP_PER_EVAL[f"sphere{_d}"] = 2 * _d, 3 * _d - 1
+for _d in (4, 5, 6, 7, 8):
+    OPS_PER_EVAL[f"line{_d}"], FLOP_PER_EVAL[f"line{_d}"] = 4 * _d, 7 * _d - 1
+for _n in (2, 3, 4, 7, 8):
+    OPS_PER_EVAL[f"dense{_n}"], FLOP_PER_EVAL[f"dense{_n}"] = _n, 2 * _n
 LANEOPS_PER_EVAL = OPS_PER_EVAL
 
 
@@ -221,7 +231,7 @@ def run_reference_arm(args):
     emit_line(line)
 
 
-def secondary_configs(device, peak_fma_per_s, hbm_peak, budget_s=90.0):
+def secondary_configs(device, peak_fma_per_s, hbm_peak, budget_s=110.0):
     """BASELINE.json configs[2..4] and a per-model scoring table, time-boxed, single GPU: every number that README.md and
     DESIGN.md quote next to the headline comes from here, i.e. from the driver's own run of this file."""
     import torch
@@ -322,6 +332,14 @@ def secondary_configs(device, peak_fma_per_s, hbm_peak, budget_s=90.0):
             table.append(scoring(name, 1_000_000, 1_048_576, reps=1))
         out.append({"config": "scoring table: 1M hypotheses x 1M data per estimator, fp32, frac = evals/s x SURVEY 8d lane-ops / measured FP32 lane rate",
                     "models": table})
+        # the dimension-templated estimators at the ends of the instantiated range (2..8)
+        table = []
+        for name in ("plane2", "plane8", "sphere8", "line4", "line8", "dense2", "dense8"):
+            if left() < 4:
+                break
+            table.append(scoring(name, 1_000_000, 1_048_576, reps=1))
+        out.append({"config": "scoring table, template space: PlaneParametersEstimator<2, 8>, SphereParametersEstimator<8>, LineParametersEstimator<4, 8>, "
+                              "DenseLinearEquationSystemParametersEstimator<double, 2 / 8>, 1M hypotheses x 1M data, fp32", "models": table})
     except Exception as e:  # a secondary measurement must never take the headline line down
         out.append({"error": repr(e)})
     return out

@@ -184,6 +184,102 @@ static void fourDCase() {
   }
 }
 
+// The rest of the reference's template space: the same class templates at other dimensions.
+template <unsigned int DIM> static void templateSpaceCase() {
+  typedef Point<double, DIM> PointND;
+  std::printf("PlaneParametersEstimator<%u>, SphereParametersEstimator<%u>, LineParametersEstimator<%u>, DenseLinearEquationSystemParametersEstimator<double,%u>\n", DIM, DIM, DIM, DIM);
+  std::vector<double> prm;
+  // hyperplane
+  double n[DIM], a[DIM], nn = 0;
+  for (unsigned j = 0; j < DIM; j++) { n[j] = uni(0, 1); nn += n[j] * n[j]; a[j] = uni(-500, 500); }
+  nn = std::sqrt(nn);
+  for (unsigned j = 0; j < DIM; j++) n[j] /= nn;
+  std::vector<PointND> pdata;
+  for (int i = 0; i < 20000; i++) {
+    PointND p;
+    double t = 0;
+    for (unsigned j = 0; j < DIM; j++) { p[j] = uni(-1000, 1000); t += (p[j] - a[j]) * n[j]; }
+    if (i % 10 < 8) for (unsigned j = 0; j < DIM; j++) p[j] += -t * n[j] + gauss(0.2);
+    pdata.push_back(p);
+  }
+  PlaneParametersEstimator<DIM> pl(0.5);
+  const double pfrac = RANSAC<PointND, double>::compute(prm, &pl, pdata, 0.999);
+  CHECK(prm.size() == 2 * DIM && pfrac > 0.7, "hyperplane RANSAC");
+  if (prm.size() == 2 * DIM) {
+    double dot = 0, off = 0;
+    for (unsigned j = 0; j < DIM; j++) { dot += prm[j] * n[j]; off += (prm[DIM + j] - a[j]) * n[j]; }
+    std::printf("  hyperplane: fraction %.4f  |n.n_true| %.8f  offset %.4g\n", pfrac, std::fabs(dot), off);
+    CHECK(std::fabs(std::fabs(dot) - 1) < 1e-6 && std::fabs(off) < 0.05, "refined hyperplane matches the generating one");
+  }
+  // hypersphere
+  double c[DIM];
+  const double r = uni(100, 500);
+  for (unsigned j = 0; j < DIM; j++) c[j] = uni(-500, 500);
+  std::vector<PointND> sdata;
+  for (int i = 0; i < 20000; i++) {
+    PointND p;
+    double u[DIM], un = 0;
+    for (unsigned j = 0; j < DIM; j++) { u[j] = gauss(1.0); un += u[j] * u[j]; }
+    un = std::sqrt(un);
+    for (unsigned j = 0; j < DIM; j++) p[j] = (i % 10 < 8) ? c[j] + r * u[j] / un + gauss(0.2) : uni(-1000, 1000);
+    sdata.push_back(p);
+  }
+  SphereParametersEstimator<DIM> sph(0.5);
+  const double sfrac = RANSAC<PointND, double>::compute(prm, &sph, sdata, 0.999);
+  CHECK(prm.size() == DIM + 1 && sfrac > 0.4, "hypersphere RANSAC, geometric LS");
+  if (prm.size() == DIM + 1) {
+    double e = std::fabs(prm[DIM] - r);
+    for (unsigned j = 0; j < DIM; j++) e += std::fabs(prm[j] - c[j]);
+    std::printf("  hypersphere: fraction %.4f  |error|_1 %.4g\n", sfrac, e);
+    CHECK(e < 0.5, "refined hypersphere matches the generating one");
+  }
+  // line
+  std::vector<PointND> ldata;
+  for (int i = 0; i < 20000; i++) {
+    PointND p;
+    const double t = uni(-1000, 1000);
+    for (unsigned j = 0; j < DIM; j++) p[j] = (i % 10 < 7) ? a[j] + t * n[j] + gauss(0.1) : uni(-1000, 1000);
+    ldata.push_back(p);
+  }
+  LineParametersEstimator<DIM> ln(0.5);
+  const double lfrac = RANSAC<PointND, double>::compute(prm, &ln, ldata, 0.999);
+  CHECK(prm.size() == 2 * DIM && lfrac > 0.6, "line RANSAC");
+  if (prm.size() == 2 * DIM) {
+    double dot = 0;
+    for (unsigned j = 0; j < DIM; j++) dot += prm[j] * n[j];
+    std::printf("  line: fraction %.4f  |dir.dir_true| %.8f\n", lfrac, std::fabs(dot));
+    CHECK(std::fabs(std::fabs(dot) - 1) < 1e-6, "refined direction matches the generating one");
+  }
+  // dense system of DIM unknowns
+  double x[DIM];
+  for (unsigned j = 0; j < DIM; j++) x[j] = uni(-100, 100);
+  std::vector<AugmentedRow<double, DIM> > rows;
+  for (int i = 0; i < 4000; i++) {
+    double row[DIM + 1];
+    row[DIM] = gauss(0.03);
+    for (unsigned j = 0; j < DIM; j++) { row[j] = uni(-100, 100); row[DIM] += row[j] * x[j]; }
+    if (i % 10 >= 8) row[DIM] += uni(5, 5000);
+    rows.push_back(AugmentedRow<double, DIM>(row));
+  }
+  DenseLinearEquationSystemParametersEstimator<double, DIM> de(0.2);
+  const double dfrac = RANSAC<AugmentedRow<double, DIM>, double>::compute(prm, &de, rows, 0.999);
+  CHECK(prm.size() == DIM && dfrac > 0.75, "linear system RANSAC");
+  if (prm.size() == DIM) {
+    double e = 0;
+    for (unsigned j = 0; j < DIM; j++) e += std::fabs(prm[j] - x[j]);
+    std::printf("  dense: fraction %.4f  |error|_1 %.4g\n", dfrac, e);
+    CHECK(e < 1e-3, "solution recovered");
+  }
+}
+// a dimension the engine does not instantiate: compiles, and fails the reference's way (0, empty parameters) with a reason
+static void beyondTemplateSpaceCase() {
+  typedef Point<double, 9> Point9D;
+  std::vector<Point9D> pts(64);
+  PlaneParametersEstimator<9> pl(0.5);
+  std::vector<double> prm(1, 1.0);
+  CHECK((RANSAC<Point9D, double>::compute(prm, &pl, pts, 0.9) == 0.0) && prm.empty(), "dimension 9: no GPU path -> 0 and empty parameters");
+}
+
 static void absorCase() {
   std::printf("AbsoluteOrientationParametersEstimator\n");
   Frame T(uni(-1000, 1000), uni(-1000, 1000), uni(-1000, 1000), 0.5, 0.5, -0.5, 0.5, true);
@@ -444,6 +540,10 @@ int main() {
   line2dCase();
   sphereCase();
   fourDCase();
+  templateSpaceCase<2>();
+  templateSpaceCase<5>();
+  templateSpaceCase<8>();
+  beyondTemplateSpaceCase();
   absorCase();
   rayCase();
   pivotCase();

@@ -4,10 +4,10 @@
 // values <= EPS dropped and fails on rank < n (.hxx:17-49); leastSquaresEstimate() does the same over
 // all rows (:64-96); agree() is |a.x - b| < delta (:111-119).
 //
-// The engine instantiates n = 5 and n = 6, the two sizes the reference's test and example use
-// (testing/DenseLinearEquationSystemParametersEstimatorTest.cxx:44,157,
-// examples/linearEquationSystemSolver.cxx).  Other n have no GPU path: b200Describe() returns false
-// and RANSAC::compute reports failure the reference's way (empty parameters, 0).
+// The engine instantiates n = 2..8 (the reference's test and example use 5 and 6,
+// testing/DenseLinearEquationSystemParametersEstimatorTest.cxx:44,157, examples/linearEquationSystemSolver.cxx).
+// Larger n have no GPU path: b200Describe() returns false and RANSAC::compute reports failure the
+// reference's way (empty parameters, 0).
 #ifndef LSQR_B200_DENSE_LINEAR_EQUATION_SYSTEM_PARAMETERS_ESTIMATOR_H
 #define LSQR_B200_DENSE_LINEAR_EQUATION_SYSTEM_PARAMETERS_ESTIMATOR_H
 #include <cstring>
@@ -74,7 +74,9 @@ class DenseLinearEquationSystemParametersEstimator : public B200Estimator<Augmen
   virtual bool b200Describe(B200EstimatorDesc& d) const {
     // the engine's arithmetic is double; rows must be n+1 packed doubles
     if (sizeof(T) != sizeof(double) || sizeof(AugmentedRow<T, n>) != (n + 1) * sizeof(double)) return false;
-    if (n == 5) d.model = LSQR_DENSE5; else if (n == 6) d.model = LSQR_DENSE6; else return false;
+    const int m = lsqr_model_dense(n);
+    if (m < 0) return false;
+    d.model = m;
     d.delta = delta;
     return true;
   }

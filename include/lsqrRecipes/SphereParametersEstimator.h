@@ -2,7 +2,8 @@
 // Hypersphere (p-c)^T(p-c) = r^2, parameters [c, r]; Cramer minimal solvers for the circle
 // (.hxx:80-109) and the sphere (:115-163), agree :255-264 (a distance against delta), algebraic
 // least squares :267-307, geometric least squares by Levenberg-Marquardt :310-338.
-// GPU path for dimension 2, 3 and 4 (4 goes through the N-D pseudo-inverse solver, :169-202).
+// GPU path for dimensions 2..8 (4 and above go through the N-D pseudo-inverse solver, :169-202); higher dimensions compile
+// and report "no GPU path" at run time (b200Describe returns false).
 #ifndef LSQR_B200_SPHERE_PARAMETERS_ESTIMATOR_H
 #define LSQR_B200_SPHERE_PARAMETERS_ESTIMATOR_H
 #include <exception>
@@ -14,7 +15,7 @@ namespace lsqrRecipes {
 
 template <unsigned int dimension>
 class SphereParametersEstimator : public B200Estimator<Point<double, dimension> > {
-  static_assert(dimension >= 2 && dimension <= 4, "lsqr_b200 accelerates SphereParametersEstimator<2>, <3> and <4>");
+  static_assert(dimension >= 2, "a hypersphere needs at least two dimensions");
   typedef Point<double, dimension> PointT;
 
  public:
@@ -43,7 +44,9 @@ class SphereParametersEstimator : public B200Estimator<Point<double, dimension> 
     lsType = keep;
   }
   virtual bool b200Describe(B200EstimatorDesc& d) const {
-    d.model = (dimension == 2) ? LSQR_CIRCLE2 : (dimension == 3 ? LSQR_SPHERE3 : LSQR_SPHERE4);
+    const int m = lsqr_model_sphere(dimension);
+    if (m < 0) return false;
+    d.model = m;
     d.delta = delta;
     d.lsType = (lsType == ALGEBRAIC) ? LSQR_LS_ALGEBRAIC : LSQR_LS_GEOMETRIC;
     return true;

@@ -52,7 +52,13 @@ typedef enum lsqr_model {
                      * datum = 17 doubles [R2 row-major, t2, u, v, p]; ls_type as for LSQR_USXW */
   LSQR_SPHERE4 = 13, /* SphereParametersEstimator<4>: the generic-dimension minimal solver (pseudo-inverse, rank test)   SphereParametersEstimator.hxx:169-202 */
   LSQR_PLANE4 = 14,  /* PlaneParametersEstimator<4>: the generic-dimension minimal solver (null space of [p_i, -1])   PlaneParametersEstimator.hxx:70-108 */
-  LSQR_NUM_MODELS = 15
+  /* the rest of the reference's template space: same code paths, one id per instantiation */
+  LSQR_PLANE2 = 15,  /* PlaneParametersEstimator<2> (a 2-D line through the generic null-space branch) */
+  LSQR_PLANE5 = 16, LSQR_PLANE6 = 17, LSQR_PLANE7 = 18, LSQR_PLANE8 = 19,       /* PlaneParametersEstimator<5..8> */
+  LSQR_SPHERE5 = 20, LSQR_SPHERE6 = 21, LSQR_SPHERE7 = 22, LSQR_SPHERE8 = 23,   /* SphereParametersEstimator<5..8> */
+  LSQR_LINE4 = 24, LSQR_LINE5 = 25, LSQR_LINE6 = 26, LSQR_LINE7 = 27, LSQR_LINE8 = 28,   /* LineParametersEstimator<4..8> */
+  LSQR_DENSE2 = 29, LSQR_DENSE3 = 30, LSQR_DENSE4 = 31, LSQR_DENSE7 = 32, LSQR_DENSE8 = 33,   /* DenseLinearEquationSystemParametersEstimator<double, 2..4, 7, 8> */
+  LSQR_NUM_MODELS = 34
 } lsqr_model;
 
 typedef enum lsqr_status {
@@ -79,12 +85,22 @@ typedef enum lsqr_sampler {
 typedef enum lsqr_ls_type { LSQR_LS_ALGEBRAIC = 0, LSQR_LS_GEOMETRIC = 1 } lsqr_ls_type;
 
 #define LSQR_MAX_PARAMS 20
-#define LSQR_MAX_SUBSET 6
+#define LSQR_MAX_SUBSET 10
 
 /* ---- model table ------------------------------------------------------------------ */
 /* dim = doubles per datum, nparams = length of the parameter vector, k = numForEstimate()
  * (ParametersEstimator.h:61). */
 int lsqr_model_info(int model, int* dim, int* nparams, int* k);
+
+/* Model id of a dimension-templated estimator of the reference, or -1 when the engine does not instantiate that dimension:
+ * PlaneParametersEstimator<d> (PlaneParametersEstimator.h:24), SphereParametersEstimator<d> (SphereParametersEstimator.h:24) and
+ * LineParametersEstimator<d> (LineParametersEstimator.h:35) for d = 2..8, DenseLinearEquationSystemParametersEstimator<double, n>
+ * (DenseLinearEquationSystemParametersEstimator.h:149) for n = 2..8.  What a binding of those class templates calls once,
+ * in the constructor, in the place of the reference's compile-time `dimension`. */
+int lsqr_model_plane(unsigned dimension);
+int lsqr_model_sphere(unsigned dimension);
+int lsqr_model_line(unsigned dimension);
+int lsqr_model_dense(unsigned n);
 
 /* ---- context ---------------------------------------------------------------------- */
 int lsqr_ctx_create(lsqr_ctx** out, int device);

@@ -11,6 +11,19 @@ MODELS = {"plane3": 0, "line2d": 1, "line2": 2, "line3": 3, "circle2": 4, "spher
 # model id -> (dim, n_params, k)  (lsqr_model_info)
 MODEL_INFO = {0: (3, 6, 3), 1: (2, 4, 2), 2: (2, 4, 2), 3: (3, 6, 2), 4: (2, 3, 3), 5: (3, 4, 4), 6: (6, 7, 3), 7: (6, 3, 2), 8: (12, 6, 3),
               9: (6, 5, 5), 10: (7, 6, 6), 11: (14, 20, 4), 12: (17, 17, 3), 13: (4, 5, 5), 14: (4, 8, 4)}
+# the rest of the reference's template space (include/lsqr_b200.h: LSQR_PLANE2 ... LSQR_DENSE8)
+for _d, _id in ((2, 15), (5, 16), (6, 17), (7, 18), (8, 19)):
+    MODELS[f"plane{_d}"] = _id
+    MODEL_INFO[_id] = (_d, 2 * _d, _d)
+for _d in range(5, 9):
+    MODELS[f"sphere{_d}"] = 20 + _d - 5
+    MODEL_INFO[20 + _d - 5] = (_d, _d + 1, _d + 1)
+for _d in range(4, 9):
+    MODELS[f"line{_d}"] = 24 + _d - 4
+    MODEL_INFO[24 + _d - 4] = (_d, 2 * _d, 2)
+for _n, _id in ((2, 29), (3, 30), (4, 31), (7, 32), (8, 33)):
+    MODELS[f"dense{_n}"] = _id
+    MODEL_INFO[_id] = (_n + 1, _n, _n)
 FP64, FP32 = 0, 1
 SAMPLE_PHILOX, SAMPLE_EXHAUSTIVE, SAMPLE_LIST, SAMPLE_PARAMS = 0, 1, 2, 3
 LS_ALGEBRAIC, LS_GEOMETRIC = 0, 1
@@ -32,7 +45,7 @@ class ScoreArgs(ctypes.Structure):
 
 class ScoreResult(ctypes.Structure):
     _fields_ = [("best_index", ctypes.c_uint64), ("best_count", ctypes.c_uint32), ("n_valid", ctypes.c_uint32),
-                ("best_subset", ctypes.c_int32 * 6), ("best_params", ctypes.c_double * 20),
+                ("best_subset", ctypes.c_int32 * 10), ("best_params", ctypes.c_double * 20),
                 ("score_ms", ctypes.c_double), ("consensus_ms", ctypes.c_double)]
 
 
@@ -65,6 +78,8 @@ def load_library():
     c = ctypes
     sig = {
         "lsqr_model_info": (c.c_int, [c.c_int, c.POINTER(c.c_int), c.POINTER(c.c_int), c.POINTER(c.c_int)]),
+        "lsqr_model_plane": (c.c_int, [c.c_uint]), "lsqr_model_sphere": (c.c_int, [c.c_uint]), "lsqr_model_line": (c.c_int, [c.c_uint]),
+        "lsqr_model_dense": (c.c_int, [c.c_uint]),
         "lsqr_ctx_create": (c.c_int, [c.POINTER(c.c_void_p), c.c_int]),
         "lsqr_device_count": (c.c_int, []),
         "lsqr_ctx_create_multi": (c.c_int, [c.POINTER(c.c_void_p), c.c_int]),
@@ -110,7 +125,7 @@ EXPORTED_SYMBOLS = [
     "lsqr_refine", "lsqr_ransac", "lsqr_ransac_exhaustive", "lsqr_ransac_batch", "lsqr_estimate", "lsqr_agree", "lsqr_least_squares",
     "lsqr_microbench_fma", "lsqr_last_refine_stats", "lsqr_weighted_least_squares",
     "lsqr_device_count", "lsqr_ctx_create_multi", "lsqr_ctx_world", "lsqr_nccl_unique_id", "lsqr_ctx_init_nccl", "lsqr_get_mask_bits",
-    "lsqr_compute", "lsqr_bench_refine_pass",
+    "lsqr_compute", "lsqr_bench_refine_pass", "lsqr_model_plane", "lsqr_model_sphere", "lsqr_model_line", "lsqr_model_dense",
 ]
 
 

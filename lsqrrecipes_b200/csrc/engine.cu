@@ -322,7 +322,7 @@ int ensure_hyp(lsqr_ctx* ctx, size_t H) {
   ctx->subsets = nullptr; ctx->hyp64 = nullptr; ctx->hyp32 = nullptr; ctx->counts = nullptr; ctx->hcap = 0;
   CK(cudaMalloc((void**)&ctx->subsets, sizeof(int32_t) * LSQR_MAX_SUBSET * want));
   CK(cudaMalloc((void**)&ctx->hyp64, sizeof(double) * LSQR_MAX_PARAMS * want));
-  CK(cudaMalloc((void**)&ctx->hyp32, sizeof(float) * 12 * want));
+  CK(cudaMalloc((void**)&ctx->hyp32, sizeof(float) * 16 * want));   // up to four float4 groups per hypothesis (8-D line: 16 constants)
   CK(cudaMalloc((void**)&ctx->counts, sizeof(uint32_t) * want));
   ctx->hcap = want;
   return 0;
@@ -452,13 +452,13 @@ void host_philox(uint32_t c[4], uint32_t k0, uint32_t k1) {
   }
 }
 void host_sample_subset(int K, uint64_t gidx, uint64_t seed, uint32_t n, int32_t* out) {
-  uint32_t rnd[8];
-  for (int blk = 0; blk < (K > 4 ? 2 : 1); blk++) {
+  uint32_t rnd[4 * ((LSQR_MAX_SUBSET + 3) / 4)];
+  for (int blk = 0; blk < (K + 3) / 4; blk++) {
     uint32_t c[4] = {(uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)blk, 0u};
     host_philox(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     for (int i = 0; i < 4; i++) rnd[4 * blk + i] = c[i];
   }
-  uint32_t sorted[8];
+  uint32_t sorted[LSQR_MAX_SUBSET];
   for (int j = 0; j < K; j++) {
     uint32_t v = (uint32_t)(((uint64_t)rnd[j] * (uint64_t)(n - j)) >> 32);   // uniform in [0, n-j)
     for (int i = 0; i < j; i++) if (v >= sorted[i]) v++;                       // skip taken indices, ascending
@@ -690,7 +690,7 @@ int refine_enqueue(lsqr_ctx* ctx, DataSet& ds, int use_mask) {
   }
   double* out_dev = ctx->small_dev + kSmOut;
   // iterative refinement: geometric circle / sphere fit, iterative ultrasound calibrations (ls_type 1 in both)
-  const bool geometric = (ctx->model == CIRCLE2 || ctx->model == SPHERE3 || ctx->model == SPHERE4 || ctx->model == USXW || ctx->model == USCP) && ctx->ls_type == LSQR_LS_GEOMETRIC;
+  const bool geometric = (model_family(ctx->model) == FAM_SPHERE || ctx->model == USXW || ctx->model == USCP) && ctx->ls_type == LSQR_LS_GEOMETRIC;
   launch_solve_moments(ctx->model, dv, ctx->rb.moments, geometric ? 1 : 0, out_dev, s); ctx->launches++;
   if (geometric) {
     // SphereParametersEstimator.hxx:224-230: algebraic fit as the start, then Levenberg-Marquardt.
@@ -1003,24 +1003,72 @@ int batch_impl(lsqr_ctx* ctx, const double* data, const uint64_t* offsets, uint6
   if (int rc = ensure(ctx, &ctx->bt_cnt, &ctx->bt_cnt_cap, (size_t)np)) return rc;
   if (out_masks) if (int rc = ensure(ctx, &ctx->mask_dev, &ctx->mask_dev_cap, (size_t)std::max<uint64_t>(total, 1))) return rc;
   ctx->main.bytes_valid = false;   // mask_dev is shared with the consensus-set bytes
-  CK(cudaMemcpyAsync(ctx->bt_data, data + base * mi.D, sizeof(double) * total * mi.D, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(ctx->bt_off, offsets + p0, sizeof(uint64_t) * (np + 1), cudaMemcpyHostToDevice, s));
-  BatchArgs ba{};
-  ba.model = ctx->model; ba.exhaustive = exhaustive; ba.tries = max_tries; ba.prob = prob; ba.seed = seed;
-  ba.data = ctx->bt_data; ba.offsets = ctx->bt_off; ba.n_problems = (uint32_t)np; ba.max_n = max_n; ba.base = base; ba.first_problem = p0;
-  ba.out_params = ctx->bt_prm; ba.out_counts = ctx->bt_cnt; ba.out_masks = out_masks ? ctx->mask_dev : nullptr;
-  CK(cudaEventRecord(ctx->ev[0], s));
-  if (launch_batch(ba, ctx->cfg, ctx->ls_type, s) < 0) return fail(ctx, LSQR_ERR_ARG, "batch launch rejected");
-  ctx->launches++;
-  CK(cudaEventRecord(ctx->ev[1], s));
+  // The problems go up in chunks of whole problems (~16 MB from page-locked memory, ~4 MB through the pinned staging ring from
+  // pageable memory, as lsqr_upload does) on the copy stream; each chunk's problems are solved as soon as it has landed, so the
+  // kernel hides behind the copy of the chunks that follow (65 536 x 256 3-D points: 403 MB of upload against 2.3 ms of kernel).
+  const size_t rec_bytes = (size_t)mi.D * sizeof(double);
+  const bool pinned = is_pinned(data + base * mi.D);
+  const uint64_t chunk_rec = std::max<uint64_t>((pinned ? (16u << 20) : (4u << 20)) / rec_bytes, 1);
+  const size_t ring_bytes = (size_t)(chunk_rec + max_n) * rec_bytes;
+  if (!pinned) {
+    if (ctx->up_pin_bytes < ring_bytes) {
+      for (int i = 0; i < lsqr_ctx::kRing; i++) { if (ctx->up_pin[i]) cudaFreeHost(ctx->up_pin[i]); ctx->up_pin[i] = nullptr; }
+      ctx->up_pin_bytes = 0;
+      for (int i = 0; i < lsqr_ctx::kRing; i++) CK(cudaMallocHost((void**)&ctx->up_pin[i], ring_bytes));
+      ctx->up_pin_bytes = ring_bytes;
+    }
+    CK(cudaStreamSynchronize(ctx->copy_stream));   // an earlier upload may still be reading the pinned ring
+    if (!ctx->copier) ctx->copier.reset(new HostCopier(host_copy_threads(ctx->world > 1 && ctx->comm ? ctx->world : 1)));
+  }
+  CK(cudaEventRecord(ctx->up_land[7], s));           // the copy stream must not run ahead of work still reading bt_data
+  CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->up_land[7], 0));
+  std::vector<cudaEvent_t> tev;                      // kernel time = sum over the chunks' launches
+  int ring = 0, land = 0;
+  for (uint64_t q0 = p0; q0 < p1;) {
+    uint64_t q1 = q0 + 1;
+    while (q1 < p1 && offsets[q1 + 1] - offsets[q0] <= chunk_rec) q1++;
+    const uint64_t rec0 = offsets[q0] - base, nrec = offsets[q1] - offsets[q0];
+    if (nrec) {
+      const double* src = data + offsets[q0] * mi.D;
+      double* dst = ctx->bt_data + rec0 * mi.D;
+      if (!pinned) {
+        const int b = ring % lsqr_ctx::kRing;
+        if (ring >= lsqr_ctx::kRing) CK(cudaEventSynchronize(ctx->up_ev[b]));   // the copy that used this buffer has finished
+        ring++;
+        ctx->copier->copy(ctx->up_pin[b], src, nrec * rec_bytes);
+        CK(cudaMemcpyAsync(dst, ctx->up_pin[b], nrec * rec_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->up_ev[b], ctx->copy_stream));
+      } else {
+        CK(cudaMemcpyAsync(dst, src, nrec * rec_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+      }
+      cudaEvent_t landed = ctx->up_land[land++ % 7];
+      CK(cudaEventRecord(landed, ctx->copy_stream));
+      CK(cudaStreamWaitEvent(s, landed, 0));
+    }
+    BatchArgs ba{};
+    ba.model = ctx->model; ba.exhaustive = exhaustive; ba.tries = max_tries; ba.prob = prob; ba.seed = seed;
+    ba.data = ctx->bt_data + rec0 * mi.D; ba.offsets = ctx->bt_off + (q0 - p0); ba.n_problems = (uint32_t)(q1 - q0); ba.max_n = max_n;
+    ba.base = offsets[q0]; ba.first_problem = q0;
+    ba.out_params = ctx->bt_prm + (q0 - p0) * mi.P; ba.out_counts = ctx->bt_cnt + (q0 - p0); ba.out_masks = out_masks ? ctx->mask_dev + rec0 : nullptr;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); tev.push_back(e0);
+    CK(cudaEventCreate(&e1)); tev.push_back(e1);
+    CK(cudaEventRecord(e0, s));
+    if (launch_batch(ba, ctx->cfg, ctx->ls_type, s) < 0) { for (cudaEvent_t e : tev) cudaEventDestroy(e); return fail(ctx, LSQR_ERR_ARG, "batch launch rejected"); }
+    ctx->launches++;
+    CK(cudaEventRecord(e1, s));
+    q0 = q1;
+  }
   CKL();
   CK(cudaMemcpyAsync(out_params + p0 * mi.P, ctx->bt_prm, sizeof(double) * np * mi.P, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(out_counts + p0, ctx->bt_cnt, sizeof(uint32_t) * np, cudaMemcpyDeviceToHost, s));
   if (out_masks && total) CK(cudaMemcpyAsync(out_masks + base, ctx->mask_dev, total, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
-  float ms = 0.f;
-  CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
-  if (device_ms) *device_ms = ms;
+  double total_ms = 0.0;
+  for (size_t i = 0; i + 1 < tev.size(); i += 2) { float ms = 0.f; if (cudaEventElapsedTime(&ms, tev[i], tev[i + 1]) == cudaSuccess) total_ms += ms; }
+  for (cudaEvent_t e : tev) cudaEventDestroy(e);
+  if (device_ms) *device_ms = total_ms;
   return LSQR_OK;
 }
 
@@ -1067,6 +1115,10 @@ int group_run(lsqr_ctx* g, const std::function<int(lsqr_ctx*, int)>& fn) {
 
 extern "C" {
 
+int lsqr_model_plane(unsigned d) { return d == 3 ? LSQR_PLANE3 : d == 4 ? LSQR_PLANE4 : d == 2 ? LSQR_PLANE2 : (d >= 5 && d <= 8) ? (int)(LSQR_PLANE5 + d - 5) : -1; }
+int lsqr_model_sphere(unsigned d) { return d == 2 ? LSQR_CIRCLE2 : d == 3 ? LSQR_SPHERE3 : d == 4 ? LSQR_SPHERE4 : (d >= 5 && d <= 8) ? (int)(LSQR_SPHERE5 + d - 5) : -1; }
+int lsqr_model_line(unsigned d) { return d == 2 ? LSQR_LINE2 : d == 3 ? LSQR_LINE3 : (d >= 4 && d <= 8) ? (int)(LSQR_LINE4 + d - 4) : -1; }
+int lsqr_model_dense(unsigned n) { return n == 5 ? LSQR_DENSE5 : n == 6 ? LSQR_DENSE6 : (n >= 2 && n <= 4) ? (int)(LSQR_DENSE2 + n - 2) : (n == 7 || n == 8) ? (int)(LSQR_DENSE7 + n - 7) : -1; }
 int lsqr_model_info(int model, int* dim, int* nparams, int* k) {
   if (model < 0 || model >= LSQR_NUM_MODELS) return LSQR_ERR_ARG;
   const ModelInfo mi = model_info(model);
@@ -1203,8 +1255,7 @@ int lsqr_set_estimator(lsqr_ctx* ctx, int model, double delta, double aux, int l
   // The reference keeps delta*delta for every estimator but the hypersphere, pivot and dense-system ones (e.g.
   // PlaneParametersEstimator.hxx:16 vs SphereParametersEstimator.hxx:20), so the sign of delta is immaterial there; the device
   // code that compares an unsquared residual (fp32 fast mode) gets |delta|.
-  const bool distance_threshold = model == LSQR_CIRCLE2 || model == LSQR_SPHERE3 || model == LSQR_SPHERE4 || model == LSQR_PIVOT ||
-                                  model == LSQR_DENSE5 || model == LSQR_DENSE6;
+  const bool distance_threshold = model_family(model) == FAM_SPHERE || model_family(model) == FAM_DENSE || model == LSQR_PIVOT;
   ctx->cfg.delta = distance_threshold ? delta : fabs(delta);
   ctx->cfg.delta2 = delta * delta;
   const double ang = aux > 0 ? aux : 0.017453292519943295769236907684886;  // RayIntersectionParametersEstimator.h:35

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "../../include/lsqr_b200.h"
 #include "models.cuh"
 
 namespace lsqr {
@@ -29,8 +30,8 @@ struct DataView {
 struct WinnerRecord {
   unsigned long long key;      // (count << 32) | (0xFFFFFFFF - index relative to the request's first hypothesis)
   unsigned long long n_valid;
-  int32_t subset[8];
-  double params[20];
+  int32_t subset[LSQR_MAX_SUBSET];
+  double params[LSQR_MAX_PARAMS];
 };
 
 // ---- k_score.cu -------------------------------------------------------------------------

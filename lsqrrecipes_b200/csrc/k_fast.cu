@@ -78,11 +78,14 @@ template <> __device__ __forceinline__ void hoist32<PLANE3>(const double* p, con
   q[0] = (float)p[0]; q[1] = (float)p[1]; q[2] = (float)p[2];
   q[3] = (float)(cfg.delta - (p[0] * (p[3] - c[0]) + p[1] * (p[4] - c[1]) + p[2] * (p[5] - c[2])));   // shifted residual s + delta
 }
-template <> __device__ __forceinline__ void hoist32<PLANE4>(const double* p, const double* c, const EstCfg& cfg, float* q) {
+template <int DIM> __device__ __forceinline__ void hoist_plane_nd(const double* p, const double* c, const EstCfg& cfg, float* q) {
   double s = 0;
-  for (int i = 0; i < 4; i++) { q[i] = (float)p[i]; s += p[i] * (p[4 + i] - c[i]); }
-  q[4] = (float)(cfg.delta - s);
+  for (int i = 0; i < DIM; i++) { q[i] = (float)p[i]; s += p[i] * (p[DIM + i] - c[i]); }
+  q[DIM] = (float)(cfg.delta - s);
 }
+#define LSQR_DEF_(ID, DIM) template <> __device__ __forceinline__ void hoist32<ID>(const double* p, const double* c, const EstCfg& cfg, float* q) { hoist_plane_nd<DIM>(p, c, cfg, q); }
+LSQR_PLANE_ND_LIST(LSQR_DEF_)
+#undef LSQR_DEF_
 template <> __device__ __forceinline__ void hoist32<LINE2D>(const double* p, const double* c, const EstCfg&, float* q) {
   q[0] = (float)p[0]; q[1] = (float)p[1];
   q[2] = (float)(-(p[0] * (p[2] - c[0]) + p[1] * (p[3] - c[1])));
@@ -108,6 +111,13 @@ template <> __device__ __forceinline__ void hoist32<LINE3>(const double* p, cons
     q[3 * i] = (float)n[k]; q[3 * i + 1] = (float)(-n[j]); q[3 * i + 2] = (float)(-(a[j] * n[k] - a[k] * n[j]));
   }
 }
+// d >= 4: the literal form, constants (n, a - c)
+template <int DIM> __device__ __forceinline__ void hoist_line_nd(const double* p, const double* c, float* q) {
+  for (int i = 0; i < DIM; i++) { q[i] = (float)p[i]; q[DIM + i] = (float)(p[DIM + i] - c[i]); }
+}
+#define LSQR_DEF_(ID, DIM) template <> __device__ __forceinline__ void hoist32<ID>(const double* p, const double* c, const EstCfg&, float* q) { hoist_line_nd<DIM>(p, c, q); }
+LSQR_DEF_(LINE4, 4) LSQR_DEF_(LINE5, 5) LSQR_DEF_(LINE6, 6) LSQR_DEF_(LINE7, 7) LSQR_DEF_(LINE8, 8)
+#undef LSQR_DEF_
 // |d - r| < delta  <=>  (r - delta)^2 <= d^2 < (r + delta)^2  <=>  0 <= t' < 4 r delta  with  t' = d^2 - (r - delta)^2: the chain
 // starts at -(r - delta)^2 and the datum is an inlier iff bits(t') < bits(4 r delta) as unsigned integers (count_carry; the
 // threshold is per hypothesis).  r < delta: no lower bound, t' = d^2 + 1 against (r + delta)^2 + 1.  A threshold that is not
@@ -123,9 +133,9 @@ template <int DIM> __device__ __forceinline__ void hoist_sphere(const double* p,
   // stored ready for count_carry: 2^32 - bits(window); 0 = nothing agrees (window not positive, or NaN)
   q[DIM + 1] = __uint_as_float((wf > 0.0f) ? 0u - __float_as_uint(wf) : 0u);
 }
-template <> __device__ __forceinline__ void hoist32<CIRCLE2>(const double* p, const double* c, const EstCfg& cfg, float* q) { hoist_sphere<2>(p, c, cfg, q); }
-template <> __device__ __forceinline__ void hoist32<SPHERE3>(const double* p, const double* c, const EstCfg& cfg, float* q) { hoist_sphere<3>(p, c, cfg, q); }
-template <> __device__ __forceinline__ void hoist32<SPHERE4>(const double* p, const double* c, const EstCfg& cfg, float* q) { hoist_sphere<4>(p, c, cfg, q); }
+#define LSQR_DEF_(ID, DIM) template <> __device__ __forceinline__ void hoist32<ID>(const double* p, const double* c, const EstCfg& cfg, float* q) { hoist_sphere<DIM>(p, c, cfg, q); }
+LSQR_SPHERE_ALL_LIST(LSQR_DEF_)
+#undef LSQR_DEF_
 template <> __device__ __forceinline__ void hoist32<ABSOR>(const double* p, const double* c, const EstCfg&, float* q) {
   double R[9];
   quat_to_rot(p[0], p[1], p[2], p[3], R);
@@ -144,8 +154,9 @@ template <int N> __device__ __forceinline__ void hoist_dense(const double* p, co
   q[N] = -1.0f;
   q[N + 1] = (float)cfg.delta;   // the chain starts at +delta: s' = a.x - b + delta, inlier <=> bits(s') < bits(2 delta)
 }
-template <> __device__ __forceinline__ void hoist32<DENSE5>(const double* p, const double*, const EstCfg& cfg, float* q) { hoist_dense<5>(p, cfg, q); }
-template <> __device__ __forceinline__ void hoist32<DENSE6>(const double* p, const double*, const EstCfg& cfg, float* q) { hoist_dense<6>(p, cfg, q); }
+#define LSQR_DEF_(ID, N) template <> __device__ __forceinline__ void hoist32<ID>(const double* p, const double*, const EstCfg& cfg, float* q) { hoist_dense<N>(p, cfg, q); }
+LSQR_DENSE_N_LIST(LSQR_DEF_)
+#undef LSQR_DEF_
 
 template <> __device__ __forceinline__ void hoist32<USXW>(const double* p, const double* c, const EstCfg&, float* q) {
   for (int i = 0; i < 6; i++) q[i] = (float)p[11 + i];
@@ -158,7 +169,7 @@ template <> __device__ __forceinline__ void hoist32<USCP>(const double* p, const
 }
 
 // slot of the per-hypothesis counting window among the hoisted constants (-1: the window is 2 delta for every hypothesis)
-template <int M> constexpr int thr_slot() { return M == CIRCLE2 ? 3 : (M == SPHERE3 ? 4 : (M == SPHERE4 ? 5 : -1)); }
+template <int M> constexpr int thr_slot() { return model_family(M) == FAM_SPHERE ? model_dim(M) + 1 : -1; }
 
 template <int M>
 __global__ void hoist32_kernel(const double* __restrict__ hyp64, size_t hld, uint32_t H, DataView dv, EstCfg cfg, float* __restrict__ hyp32) {
@@ -198,26 +209,6 @@ __device__ __forceinline__ void load_hyp32(const float* __restrict__ hyp, size_t
   }
 }
 
-#define LSQR_DISPATCH_MODEL(model, CALL)      \
-  switch (model) {                            \
-    case PLANE3: { CALL(PLANE3); break; }     \
-    case LINE2D: { CALL(LINE2D); break; }     \
-    case LINE2: { CALL(LINE2); break; }       \
-    case LINE3: { CALL(LINE3); break; }       \
-    case CIRCLE2: { CALL(CIRCLE2); break; }   \
-    case SPHERE3: { CALL(SPHERE3); break; }   \
-    case ABSOR: { CALL(ABSOR); break; }       \
-    case RAY: { CALL(RAY); break; }           \
-    case PIVOT: { CALL(PIVOT); break; }       \
-    case DENSE5: { CALL(DENSE5); break; }     \
-    case DENSE6: { CALL(DENSE6); break; }     \
-    case USXW: { CALL(USXW); break; }         \
-    case USCP: { CALL(USCP); break; }         \
-    case SPHERE4: { CALL(SPHERE4); break; }   \
-    case PLANE4: { CALL(PLANE4); break; }     \
-    default: break;                           \
-  }
-
 void launch_hoist32(int model, const double* hyp64, size_t hld, uint32_t H, const DataView& dv, const EstCfg& cfg, float* hyp32, cudaStream_t s) {
   if (H == 0) return;
   const unsigned blocks = (H + 255) / 256;
@@ -238,13 +229,21 @@ template <> struct Eval<PLANE3> {
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return fma2(q[0], x[0], fma2(q[1], x[1], fma2(q[2], x[2], q[3]))); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = sub2(dist(q, x), t.delta); return fma2(s, s, t.neg_delta2); }
 };
-template <> struct Eval<PLANE4> {
+template <int DIM> struct EvalPlaneND {
   static constexpr bool kHasAbsForm = true;
   static constexpr int kThr = -1;
   static constexpr bool kShifted = true;   // dist() is s + delta (the hoisted constant carries the shift)
-  __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return fma2(q[0], x[0], fma2(q[1], x[1], fma2(q[2], x[2], fma2(q[3], x[3], q[4])))); }
+  __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) {
+    f2 s = q[DIM];
+#pragma unroll
+    for (int i = DIM - 1; i >= 0; i--) s = fma2(q[i], x[i], s);
+    return s;
+  }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = sub2(dist(q, x), t.delta); return fma2(s, s, t.neg_delta2); }
 };
+#define LSQR_DEF_(ID, DIM) template <> struct Eval<ID> : EvalPlaneND<DIM> {};
+LSQR_PLANE_ND_LIST(LSQR_DEF_)
+#undef LSQR_DEF_
 template <> struct Eval<LINE2D> {
   static constexpr bool kHasAbsForm = true;
   static constexpr int kThr = -1;
@@ -277,6 +276,31 @@ template <> struct Eval<LINE3> {     // Pluecker form: |x X n - m|^2 - delta^2 (
     return g;
   }
 };
+// d >= 4: the literal form of LineParametersEstimator.hxx:135-150, v = x - a, w = v - (v.n) n, |w|^2 - delta^2: 4d operations
+template <int DIM> struct EvalLineND {
+  static constexpr bool kHasAbsForm = false;
+  static constexpr int kThr = -1;
+  static constexpr bool kShifted = false;
+  __device__ static __forceinline__ f2 dist(const f2*, const f2*) { return splat(0.f); }
+  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) {
+    f2 v[DIM];
+#pragma unroll
+    for (int i = 0; i < DIM; i++) v[i] = sub2(x[i], q[DIM + i]);
+    f2 vn = mul2(v[0], q[0]);
+#pragma unroll
+    for (int i = 1; i < DIM; i++) vn = fma2(v[i], q[i], vn);
+    const f2 nvn = sub2(splat(0.f), vn);
+    f2 g = t.neg_delta2;
+#pragma unroll
+    for (int i = 0; i < DIM; i++) { const f2 w = fma2(nvn, q[i], v[i]); g = fma2(w, w, g); }
+    return g;
+  }
+};
+template <> struct Eval<LINE4> : EvalLineND<4> {};
+template <> struct Eval<LINE5> : EvalLineND<5> {};
+template <> struct Eval<LINE6> : EvalLineND<6> {};
+template <> struct Eval<LINE7> : EvalLineND<7> {};
+template <> struct Eval<LINE8> : EvalLineND<8> {};
 // t' = d^2 - (r - delta)^2 (chain start q[DIM]); per-hypothesis window q[DIM + 1] = 4 r delta (see hoist_sphere)
 template <int DIM> __device__ __forceinline__ f2 sphere_t(const f2* q, const f2* x) {
   f2 t = q[DIM];
@@ -291,9 +315,9 @@ template <int DIM> struct EvalSphere {
   __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return sphere_t<DIM>(q, x); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2&) { return sphere_t<DIM>(q, x); }
 };
-template <> struct Eval<CIRCLE2> : EvalSphere<2> {};
-template <> struct Eval<SPHERE3> : EvalSphere<3> {};
-template <> struct Eval<SPHERE4> : EvalSphere<4> {};
+#define LSQR_DEF_(ID, DIM) template <> struct Eval<ID> : EvalSphere<DIM> {};
+LSQR_SPHERE_ALL_LIST(LSQR_DEF_)
+#undef LSQR_DEF_
 template <> struct Eval<ABSOR> {
   static constexpr bool kHasAbsForm = false;
   static constexpr int kThr = -1;
@@ -350,20 +374,16 @@ template <int N> __device__ __forceinline__ f2 dense_dist(const f2* q, const f2*
   for (int i = N - 1; i >= 0; i--) s = fma2(q[i], x[i], s);
   return s;
 }
-template <> struct Eval<DENSE5> {
+template <int N> struct EvalDense {
   static constexpr bool kHasAbsForm = true;
   static constexpr int kThr = -1;   // threshold = delta for every hypothesis
   static constexpr bool kShifted = true;
-  __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return dense_dist<5>(q, x); }
+  __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return dense_dist<N>(q, x); }
   __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = sub2(dist(q, x), t.delta); return fma2(s, s, t.neg_delta2); }
 };
-template <> struct Eval<DENSE6> {
-  static constexpr bool kHasAbsForm = true;
-  static constexpr int kThr = -1;   // threshold = delta for every hypothesis
-  static constexpr bool kShifted = true;
-  __device__ static __forceinline__ f2 dist(const f2* q, const f2* x) { return dense_dist<6>(q, x); }
-  __device__ static __forceinline__ f2 signed_(const f2* q, const f2* x, const Thr2& t) { const f2 s = sub2(dist(q, x), t.delta); return fma2(s, s, t.neg_delta2); }
-};
+#define LSQR_DEF_(ID, N) template <> struct Eval<ID> : EvalDense<N> {};
+LSQR_DENSE_N_LIST(LSQR_DEF_)
+#undef LSQR_DEF_
 
 // cross-wire: e = R2 (u c1 + v c2 + t3) + t2 - t1, |e|^2 - delta^2   (21 FMA-pipe operations)
 template <> struct Eval<USXW> {
@@ -688,7 +708,7 @@ constexpr int cb_blocking(int m, bool want_r) {
   int r = 8, ppi = 2;
   switch (m) {
     case PLANE3: r = LSQR_CB_R_PLANE; ppi = LSQR_CB_PPI_PLANE; break;
-    case LINE2D: case LINE2: r = 16; ppi = 4; break;
+    case LINE2D: case LINE2: case PLANE2: r = 16; ppi = 4; break;
     case LINE3: r = 8; ppi = 2; break;
     case CIRCLE2: r = 12; ppi = 2; break;
     case SPHERE3: r = 10; ppi = 2; break;
@@ -697,7 +717,14 @@ constexpr int cb_blocking(int m, bool want_r) {
     case PIVOT: r = 8; ppi = 2; break;
     case DENSE5: case DENSE6: case SPHERE4: case PLANE4: r = 8; ppi = 4; break;
     case USXW: case USCP: r = 4; ppi = 2; break;
-    default: break;
+    default:   // the wider template space: hypotheses per thread bounded by the registers their constants take
+      switch (model_family(m)) {
+        case FAM_PLANE: case FAM_DENSE: r = model_dim(m) <= 4 ? 10 : 8; ppi = model_dim(m) <= 6 ? 4 : 2; break;
+        case FAM_SPHERE: r = 8; ppi = model_dim(m) <= 6 ? 4 : 2; break;
+        case FAM_LINE: r = model_dim(m) <= 5 ? 6 : 4; ppi = 2; break;
+        default: break;
+      }
+      break;
   }
   return want_r ? r : ppi;
 }
@@ -752,22 +779,16 @@ static int run_consensus_cb(const DataView& dv, const float* hyp, size_t hld, ui
 
 // Register blocking per model: R hypotheses per thread sized so that 2*Q32*R duplicated constants
 // plus the point pairs stay below ~128 registers at 256 threads.
-template <int M> struct Block32 { static constexpr int R = 6, PPI = 2; };
-template <> struct Block32<PLANE3> { static constexpr int R = 9, PPI = 2; };
-template <> struct Block32<LINE2D> { static constexpr int R = 9, PPI = 2; };
-template <> struct Block32<LINE2> { static constexpr int R = 8, PPI = 2; };
-template <> struct Block32<LINE3> { static constexpr int R = 6, PPI = 2; };
-template <> struct Block32<CIRCLE2> { static constexpr int R = 8, PPI = 2; };
-template <> struct Block32<SPHERE3> { static constexpr int R = 8, PPI = 2; };
-template <> struct Block32<ABSOR> { static constexpr int R = 3, PPI = 1; };
-template <> struct Block32<RAY> { static constexpr int R = 8, PPI = 1; };
-template <> struct Block32<PIVOT> { static constexpr int R = 4, PPI = 1; };
-template <> struct Block32<DENSE5> { static constexpr int R = 6, PPI = 2; };
-template <> struct Block32<DENSE6> { static constexpr int R = 6, PPI = 2; };
-template <> struct Block32<USXW> { static constexpr int R = 3, PPI = 1; };
-template <> struct Block32<USCP> { static constexpr int R = 3, PPI = 1; };
-template <> struct Block32<SPHERE4> { static constexpr int R = 6, PPI = 2; };
-template <> struct Block32<PLANE4> { static constexpr int R = 8, PPI = 2; };
+constexpr int block32_r(int m) {
+  switch (m) {
+    case PLANE3: case LINE2D: return 9;
+    case LINE2: case CIRCLE2: case SPHERE3: case RAY: case PLANE4: return 8;
+    case ABSOR: case USXW: case USCP: return 3;
+    case PIVOT: return 4;
+    default: { const int q = model_info(m).Q32; return q <= 8 ? 6 : (q <= 10 ? 5 : (q <= 12 ? 4 : 3)); }
+  }
+}
+template <int M> struct Block32 { static constexpr int R = block32_r(M), PPI = (M == ABSOR || M == RAY || M == PIVOT || M == USXW || M == USCP) ? 1 : 2; };
 
 int launch_consensus32(int model, const DataView& dv, const float* hyp32, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms,
                        cudaStream_t s) {

@@ -57,8 +57,7 @@ __host__ __device__ inline bool centred_component(int model, int d) {
     case PIVOT: return d >= 9;
     case USXW: return d >= 9 && d < 12;       // t2; rotation entries and pixel coordinates stay
     case USCP: return false;                  // t2 and p enter as p - t2 with no free translation to absorb a shift
-    case DENSE5: case DENSE6: return false;   // rows of a linear system: a shift would change the solution
-    default: return true;
+    default: return model_family(model) != FAM_DENSE;   // rows of a linear system: a shift would change the solution
   }
 }
 
@@ -179,26 +178,6 @@ __global__ void __launch_bounds__(128) solve_kernel(SolveArgs a, const double* _
   const unsigned ballot = __ballot_sync(__activemask(), ok);
   if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1) && ballot) atomicAdd(a.n_valid, __popc(ballot));
 }
-
-#define LSQR_DISPATCH_MODEL(model, CALL)      \
-  switch (model) {                            \
-    case PLANE3: { CALL(PLANE3); break; }     \
-    case LINE2D: { CALL(LINE2D); break; }     \
-    case LINE2: { CALL(LINE2); break; }       \
-    case LINE3: { CALL(LINE3); break; }       \
-    case CIRCLE2: { CALL(CIRCLE2); break; }   \
-    case SPHERE3: { CALL(SPHERE3); break; }   \
-    case ABSOR: { CALL(ABSOR); break; }       \
-    case RAY: { CALL(RAY); break; }           \
-    case PIVOT: { CALL(PIVOT); break; }       \
-    case DENSE5: { CALL(DENSE5); break; }     \
-    case DENSE6: { CALL(DENSE6); break; }     \
-    case USXW: { CALL(USXW); break; }         \
-    case USCP: { CALL(USCP); break; }         \
-    case SPHERE4: { CALL(SPHERE4); break; }   \
-    case PLANE4: { CALL(PLANE4); break; }     \
-    default: break;                           \
-  }
 
 void launch_solve(const SolveArgs& a, const DataView& dv, const EstCfg& cfg, cudaStream_t s) {
   if (a.H == 0) return;

@@ -14,53 +14,74 @@
 
 namespace lsqr {
 
-enum : int { PLANE3 = 0, LINE2D = 1, LINE2 = 2, LINE3 = 3, CIRCLE2 = 4, SPHERE3 = 5, ABSOR = 6, RAY = 7, PIVOT = 8, DENSE5 = 9, DENSE6 = 10, USXW = 11, USCP = 12, SPHERE4 = 13, PLANE4 = 14, NUM_MODELS = 15 };
+enum : int { PLANE3 = 0, LINE2D = 1, LINE2 = 2, LINE3 = 3, CIRCLE2 = 4, SPHERE3 = 5, ABSOR = 6, RAY = 7, PIVOT = 8, DENSE5 = 9, DENSE6 = 10, USXW = 11, USCP = 12, SPHERE4 = 13, PLANE4 = 14,
+              // the rest of the reference's template space: hyperplanes, hyperspheres and lines up to dimension 8, dense systems of 2..8 unknowns
+              PLANE2 = 15, PLANE5 = 16, PLANE6 = 17, PLANE7 = 18, PLANE8 = 19, SPHERE5 = 20, SPHERE6 = 21, SPHERE7 = 22, SPHERE8 = 23,
+              LINE4 = 24, LINE5 = 25, LINE6 = 26, LINE7 = 27, LINE8 = 28, DENSE2 = 29, DENSE3 = 30, DENSE4 = 31, DENSE7 = 32, DENSE8 = 33, NUM_MODELS = 34 };
+
+// The dimension-templated estimators of the reference as X-macro lists (model id, dimension).  PLANE_ND: the generic branch of
+// PlaneParametersEstimator<d> (every d but 3); SPHERE_ND: SphereParametersEstimator<d>::estimateND (every d but 2, 3);
+// LINE_ND: LineParametersEstimator<d>; DENSE_N: DenseLinearEquationSystemParametersEstimator<double, n>.
+#define LSQR_PLANE_ND_LIST(X) X(PLANE2, 2) X(PLANE4, 4) X(PLANE5, 5) X(PLANE6, 6) X(PLANE7, 7) X(PLANE8, 8)
+#define LSQR_SPHERE_ND_LIST(X) X(SPHERE4, 4) X(SPHERE5, 5) X(SPHERE6, 6) X(SPHERE7, 7) X(SPHERE8, 8)
+#define LSQR_SPHERE_ALL_LIST(X) X(CIRCLE2, 2) X(SPHERE3, 3) LSQR_SPHERE_ND_LIST(X)
+#define LSQR_LINE_ND_LIST(X) X(LINE2, 2) X(LINE3, 3) X(LINE4, 4) X(LINE5, 5) X(LINE6, 6) X(LINE7, 7) X(LINE8, 8)
+#define LSQR_DENSE_N_LIST(X) X(DENSE2, 2) X(DENSE3, 3) X(DENSE4, 4) X(DENSE5, 5) X(DENSE6, 6) X(DENSE7, 7) X(DENSE8, 8)
+// every model id, for the dispatch switches
+#define LSQR_ALL_MODELS(X)                                                                                                    \
+  X(PLANE3) X(LINE2D) X(LINE2) X(LINE3) X(CIRCLE2) X(SPHERE3) X(ABSOR) X(RAY) X(PIVOT) X(DENSE5) X(DENSE6) X(USXW) X(USCP) X(SPHERE4) \
+  X(PLANE4) X(PLANE2) X(PLANE5) X(PLANE6) X(PLANE7) X(PLANE8) X(SPHERE5) X(SPHERE6) X(SPHERE7) X(SPHERE8) X(LINE4) X(LINE5) X(LINE6)  \
+  X(LINE7) X(LINE8) X(DENSE2) X(DENSE3) X(DENSE4) X(DENSE7) X(DENSE8)
+#define LSQR_DISPATCH_CASE_(MM) case MM: { CALL(MM); break; }
+// switch (model) over every id; the caller defines CALL(MM) around it
+#define LSQR_DISPATCH_MODEL(model, CALL_UNUSED) switch (model) { LSQR_ALL_MODELS(LSQR_DISPATCH_CASE_) default: break; }
+
+// family and dimension of a model id (dimension: space dimension, or the number of unknowns of a dense system)
+enum : int { FAM_OTHER = 0, FAM_PLANE = 1, FAM_SPHERE = 2, FAM_LINE = 3, FAM_DENSE = 4 };
+__host__ __device__ constexpr int model_family(int m) {
+  return (m == PLANE3 || m == PLANE4 || m == PLANE2 || (m >= PLANE5 && m <= PLANE8)) ? FAM_PLANE
+       : (m == CIRCLE2 || m == SPHERE3 || m == SPHERE4 || (m >= SPHERE5 && m <= SPHERE8)) ? FAM_SPHERE
+       : (m == LINE2 || m == LINE3 || (m >= LINE4 && m <= LINE8)) ? FAM_LINE
+       : (m == DENSE5 || m == DENSE6 || (m >= DENSE2 && m <= DENSE8)) ? FAM_DENSE : FAM_OTHER;
+}
+__host__ __device__ constexpr int model_dim(int m) {
+  return m == PLANE3 ? 3 : m == PLANE4 ? 4 : m == PLANE2 ? 2 : (m >= PLANE5 && m <= PLANE8) ? m - PLANE5 + 5
+       : m == CIRCLE2 ? 2 : m == SPHERE3 ? 3 : m == SPHERE4 ? 4 : (m >= SPHERE5 && m <= SPHERE8) ? m - SPHERE5 + 5
+       : m == LINE2 ? 2 : m == LINE3 ? 3 : (m >= LINE4 && m <= LINE8) ? m - LINE4 + 4
+       : m == DENSE5 ? 5 : m == DENSE6 ? 6 : (m >= DENSE2 && m <= DENSE4) ? m - DENSE2 + 2 : (m == DENSE7 || m == DENSE8) ? m - DENSE7 + 7 : 0;
+}
 
 // dim = doubles per datum, P = parameters, K = minimal subset, HQ = doubles of a prepared
 // fp64 hypothesis, Q32 = floats of a hoisted fp32 hypothesis.
-template <int M> struct Model;
-template <> struct Model<PLANE3>  { static constexpr int D = 3,  P = 6, K = 3, HQ = 6,  Q32 = 4;  };
-template <> struct Model<LINE2D>  { static constexpr int D = 2,  P = 4, K = 2, HQ = 4,  Q32 = 3;  };
-template <> struct Model<LINE2>   { static constexpr int D = 2,  P = 4, K = 2, HQ = 4,  Q32 = 3;  };
-template <> struct Model<LINE3>   { static constexpr int D = 3,  P = 6, K = 2, HQ = 6,  Q32 = 9;  };
-template <> struct Model<CIRCLE2> { static constexpr int D = 2,  P = 3, K = 3, HQ = 3,  Q32 = 4;  };
-template <> struct Model<SPHERE3> { static constexpr int D = 3,  P = 4, K = 4, HQ = 4,  Q32 = 5;  };
-template <> struct Model<ABSOR>   { static constexpr int D = 6,  P = 7, K = 3, HQ = 12, Q32 = 12; };
-template <> struct Model<RAY>     { static constexpr int D = 6,  P = 3, K = 2, HQ = 3,  Q32 = 3;  };
-template <> struct Model<PIVOT>   { static constexpr int D = 12, P = 6, K = 3, HQ = 6,  Q32 = 6;  };
-// DenseLinearEquationSystemParametersEstimator<double, n>: datum = AugmentedRow (n coefficients, right-hand side)
-template <> struct Model<DENSE5>  { static constexpr int D = 6,  P = 5, K = 5, HQ = 5,  Q32 = 7;  };
-template <> struct Model<DENSE6>  { static constexpr int D = 7,  P = 6, K = 6, HQ = 6,  Q32 = 8;  };
-// SingleUnknownPointTargetUSCalibrationParametersEstimator (cross-wire phantom): datum = [R2 (9), t2 (3), u, v],
-// parameters [t1, t3, omega_z, omega_y, omega_x, m_x, m_y, m_x R3(:,1), m_y R3(:,2), R3(:,3)]
-template <> struct Model<USXW>    { static constexpr int D = 14, P = 20, K = 4, HQ = 12, Q32 = 12; };
-// CalibratedPointerTargetUSCalibrationParametersEstimator: datum = [R2 (9), t2 (3), u, v, p (3)],
-// parameters [t3, omega_z, omega_y, omega_x, m_x, m_y, m_x R3(:,1), m_y R3(:,2), R3(:,3)]
-template <> struct Model<USCP>    { static constexpr int D = 17, P = 17, K = 3, HQ = 9,  Q32 = 9;  };
-template <> struct Model<SPHERE4> { static constexpr int D = 4,  P = 5, K = 5, HQ = 5,  Q32 = 6;  };
-template <> struct Model<PLANE4>  { static constexpr int D = 4,  P = 8, K = 4, HQ = 8,  Q32 = 5;  };
-
 struct ModelInfo { int D, P, K, HQ, Q32; };
-__host__ __device__ inline ModelInfo model_info(int m) {
+__host__ __device__ constexpr ModelInfo model_info(int m) {
+  const int d = model_dim(m);
+  switch (model_family(m)) {
+    case FAM_PLANE:  return {d, 2 * d, d, 2 * d, d + 1};
+    case FAM_SPHERE: return {d, d + 1, d + 1, d + 1, d + 2};
+    case FAM_LINE:   return {d, 2 * d, 2, 2 * d, d == 2 ? 3 : (d == 3 ? 9 : 2 * d)};   // fp32: 2-D form, Pluecker form, literal form (k_fast.cu)
+    // DenseLinearEquationSystemParametersEstimator<double, n>: datum = AugmentedRow (n coefficients, right-hand side)
+    case FAM_DENSE:  return {d + 1, d, d, d, d + 2};
+    default: break;
+  }
   switch (m) {
-    case PLANE3:  return {3, 6, 3, 6, 4};
     case LINE2D:  return {2, 4, 2, 4, 3};
-    case LINE2:   return {2, 4, 2, 4, 3};
-    case LINE3:   return {3, 6, 2, 6, 9};
-    case CIRCLE2: return {2, 3, 3, 3, 4};
-    case SPHERE3: return {3, 4, 4, 4, 5};
     case ABSOR:   return {6, 7, 3, 12, 12};
     case RAY:     return {6, 3, 2, 3, 3};
     case PIVOT:   return {12, 6, 3, 6, 6};
-    case DENSE5:  return {6, 5, 5, 5, 7};
-    case DENSE6:  return {7, 6, 6, 6, 8};
+    // SingleUnknownPointTargetUSCalibrationParametersEstimator (cross-wire phantom): datum = [R2 (9), t2 (3), u, v],
+    // parameters [t1, t3, omega_z, omega_y, omega_x, m_x, m_y, m_x R3(:,1), m_y R3(:,2), R3(:,3)]
     case USXW:    return {14, 20, 4, 12, 12};
+    // CalibratedPointerTargetUSCalibrationParametersEstimator: datum = [R2 (9), t2 (3), u, v, p (3)],
+    // parameters [t3, omega_z, omega_y, omega_x, m_x, m_y, m_x R3(:,1), m_y R3(:,2), R3(:,3)]
     case USCP:    return {17, 17, 3, 9, 9};
-    case SPHERE4: return {4, 5, 5, 5, 6};
-    case PLANE4:  return {4, 8, 4, 8, 5};
   }
   return {0, 0, 0, 0, 0};
 }
+template <int M> struct Model {
+  static constexpr int D = model_info(M).D, P = model_info(M).P, K = model_info(M).K, HQ = model_info(M).HQ, Q32 = model_info(M).Q32;
+  static constexpr int FAM = model_family(M), DIM = model_dim(M);
+};
 
 // Thresholds of one estimator instance (what the reference keeps in private members).
 struct EstCfg {
@@ -262,8 +283,9 @@ template <int DIM> __device__ inline bool estimate_line(const double* d, const E
   for (int i = 0; i < DIM; i++) prm[i] /= dir_norm;
   return true;
 }
-template <> __device__ inline bool estimate<LINE2>(const double* d, const EstCfg& c, double* prm) { return estimate_line<2>(d, c, prm); }
-template <> __device__ inline bool estimate<LINE3>(const double* d, const EstCfg& c, double* prm) { return estimate_line<3>(d, c, prm); }
+#define LSQR_DEF_(ID, DIM) template <> __device__ inline bool estimate<ID>(const double* d, const EstCfg& c, double* prm) { return estimate_line<DIM>(d, c, prm); }
+LSQR_LINE_ND_LIST(LSQR_DEF_)
+#undef LSQR_DEF_
 
 // SphereParametersEstimator.hxx:80-109
 template <> __device__ inline bool estimate<CIRCLE2>(const double* d, const EstCfg&, double* prm) {
@@ -384,8 +406,9 @@ template <int N> __device__ inline bool estimate_dense(const double* d, double* 
   for (int i = 0; i < N; i++) { for (int j = 0; j < N; j++) A[i * N + j] = d[i * (N + 1) + j]; b[i] = d[i * (N + 1) + N]; }
   return pinv_solve<N, N>(A, b, kEps, prm) >= N;
 }
-template <> __device__ inline bool estimate<DENSE5>(const double* d, const EstCfg&, double* prm) { return estimate_dense<5>(d, prm); }
-template <> __device__ inline bool estimate<DENSE6>(const double* d, const EstCfg&, double* prm) { return estimate_dense<6>(d, prm); }
+#define LSQR_DEF_(ID, N) template <> __device__ inline bool estimate<ID>(const double* d, const EstCfg&, double* prm) { return estimate_dense<N>(d, prm); }
+LSQR_DENSE_N_LIST(LSQR_DEF_)
+#undef LSQR_DEF_
 
 // R <- U V^T of its SVD (closest rotation in the Frobenius norm, SinglePointTargetUSCalibrationParametersEstimator
 // .cxx:226-229), as the orthogonal polar factor R (R^T R)^(-1/2).
@@ -467,31 +490,37 @@ template <> __device__ inline bool estimate<USXW>(const double* d, const EstCfg&
 }
 
 // PlaneParametersEstimator.hxx:70-108 (every dimension other than 3): [n, d] spans the null space of [p_i, -1]
-template <> __device__ inline bool estimate<PLANE4>(const double* d, const EstCfg&, double* prm) {
-  double A[4 * 5], x[5];
-  for (int i = 0; i < 4; i++) { for (int j = 0; j < 4; j++) A[i * 5 + j] = d[i * 4 + j]; A[i * 5 + 4] = -1; }
-  if (null_vector<4, 5>(A, kEps, x) < 4) return false;
+template <int DIM> __device__ inline bool estimate_plane_nd(const double* d, double* prm) {
+  double A[DIM * (DIM + 1)], x[DIM + 1];
+  for (int i = 0; i < DIM; i++) { for (int j = 0; j < DIM; j++) A[i * (DIM + 1) + j] = d[i * DIM + j]; A[i * (DIM + 1) + DIM] = -1; }
+  if (null_vector<DIM, DIM + 1>(A, kEps, x) < DIM) return false;
   double norm = 0;
-  for (int i = 0; i < 4; i++) norm += x[i] * x[i];
+  for (int i = 0; i < DIM; i++) norm += x[i] * x[i];
   norm = 1.0 / sqrt(norm);
-  for (int i = 0; i < 4; i++) { prm[i] = x[i] * norm; prm[4 + i] = d[i]; }
+  for (int i = 0; i < DIM; i++) { prm[i] = x[i] * norm; prm[DIM + i] = d[i]; }
   return true;
 }
+#define LSQR_DEF_(ID, DIM) template <> __device__ inline bool estimate<ID>(const double* d, const EstCfg&, double* prm) { return estimate_plane_nd<DIM>(d, prm); }
+LSQR_PLANE_ND_LIST(LSQR_DEF_)
+#undef LSQR_DEF_
 
 // SphereParametersEstimator.hxx:169-202 (estimateND, every dimension other than 2 and 3): rows p0 - p_i, pseudo-inverse
 // with singular values <= EPS zeroed; rank < dim means the points lie in a hyperplane.
-template <> __device__ inline bool estimate<SPHERE4>(const double* d, const EstCfg&, double* prm) {
-  double A[16], b[4], x[4];
-  for (int i = 0; i < 4; i++) {
+template <int DIM> __device__ inline bool estimate_sphere_nd(const double* d, double* prm) {
+  double A[DIM * DIM], b[DIM], x[DIM];
+  for (int i = 0; i < DIM; i++) {
     b[i] = 0.0;
-    for (int j = 0; j < 4; j++) { A[i * 4 + j] = d[j] - d[(i + 1) * 4 + j]; b[i] += A[i * 4 + j] * (d[j] + d[(i + 1) * 4 + j]); }
+    for (int j = 0; j < DIM; j++) { A[i * DIM + j] = d[j] - d[(i + 1) * DIM + j]; b[i] += A[i * DIM + j] * (d[j] + d[(i + 1) * DIM + j]); }
   }
-  if (pinv_solve<4, 4>(A, b, kSphereEps, x) < 4) return false;
+  if (pinv_solve<DIM, DIM>(A, b, kSphereEps, x) < DIM) return false;
   double rSquared = 0.0;
-  for (int i = 0; i < 4; i++) { prm[i] = x[i] * 0.5; rSquared += (d[i] - prm[i]) * (d[i] - prm[i]); }
-  prm[4] = sqrt(rSquared);
+  for (int i = 0; i < DIM; i++) { prm[i] = x[i] * 0.5; rSquared += (d[i] - prm[i]) * (d[i] - prm[i]); }
+  prm[DIM] = sqrt(rSquared);
   return true;
 }
+#define LSQR_DEF_(ID, DIM) template <> __device__ inline bool estimate<ID>(const double* d, const EstCfg&, double* prm) { return estimate_sphere_nd<DIM>(d, prm); }
+LSQR_SPHERE_ND_LIST(LSQR_DEF_)
+#undef LSQR_DEF_
 
 // SinglePointTargetUSCalibrationParametersEstimator.cxx:789-920 with three data: rows [u R2, v R2, R2] x = p - t2,
 // singular values <= FLT_EPSILON zeroed, rank < 9 fails.
@@ -547,12 +576,15 @@ template <> __device__ __forceinline__ bool agree<PLANE3>(const double* h, const
   for (int i = 0; i < 3; i++) sd += h[i] * (x[i] - h[3 + i]);
   return (sd * sd) < cfg.delta2;
 }
-template <> __device__ __forceinline__ bool agree<PLANE4>(const double* h, const double* x, const EstCfg& cfg) {
+template <int DIM> __device__ __forceinline__ bool agree_plane_nd(const double* h, const double* x, const EstCfg& cfg) {
   double sd = 0;
 #pragma unroll
-  for (int i = 0; i < 4; i++) sd += h[i] * (x[i] - h[4 + i]);
+  for (int i = 0; i < DIM; i++) sd += h[i] * (x[i] - h[DIM + i]);
   return (sd * sd) < cfg.delta2;
 }
+#define LSQR_DEF_(ID, DIM) template <> __device__ __forceinline__ bool agree<ID>(const double* h, const double* x, const EstCfg& c) { return agree_plane_nd<DIM>(h, x, c); }
+LSQR_PLANE_ND_LIST(LSQR_DEF_)
+#undef LSQR_DEF_
 // Line2DParametersEstimator.cxx:119-123
 template <> __device__ __forceinline__ bool agree<LINE2D>(const double* h, const double* x, const EstCfg& cfg) {
   const double sd = h[0] * (x[0] - h[2]) + h[1] * (x[1] - h[3]);
@@ -567,19 +599,36 @@ template <int DIM> __device__ __forceinline__ bool agree_line(const double* h, c
   for (int i = 0; i < DIM; i++) ds += (v[i] - v_dot_n * h[i]) * (v[i] - v_dot_n * h[i]);
   return ds < cfg.delta2;
 }
-template <> __device__ __forceinline__ bool agree<LINE2>(const double* h, const double* x, const EstCfg& c) { return agree_line<2>(h, x, c); }
-template <> __device__ __forceinline__ bool agree<LINE3>(const double* h, const double* x, const EstCfg& c) { return agree_line<3>(h, x, c); }
-// SphereParametersEstimator.hxx:255-264 (a distance against delta, not squared)
+#define LSQR_DEF_(ID, DIM) template <> __device__ __forceinline__ bool agree<ID>(const double* h, const double* x, const EstCfg& c) { return agree_line<DIM>(h, x, c); }
+LSQR_LINE_ND_LIST(LSQR_DEF_)
+#undef LSQR_DEF_
+// SphereParametersEstimator.hxx:255-264 (a distance against delta, not squared): |sqrt(dl) - r| < delta.
+// The square root (a ~20-instruction sequence on the FP64 pipe) decides nothing for a datum whose squared distance is clear
+// of both (r - delta)^2 and (r + delta)^2 by more than any rounding of the reference's expression could move it (1e-9
+// relative, against a few ulp = 4e-16); only data inside those two slivers take the reference's expression literally.  The
+// decision is the reference's for every datum -- the streaming refine pass of the sphere went from 0.61 to the plane's
+// fraction of HBM bandwidth with this, the FP64 validation kernel of the sphere by the share of the square root.
 template <int DIM> __device__ __forceinline__ bool agree_sphere(const double* h, const double* x, const EstCfg& cfg) {
   double dl = 0;
 #pragma unroll
   for (int i = 0; i < DIM; i++) dl += ((x[i] - h[i]) * (x[i] - h[i]));
-  dl = fabs(sqrt(dl) - h[DIM]);
+  const double r = h[DIM], hi = r + cfg.delta, lo = r - cfg.delta;
+  if (cfg.delta > 0.0 && r > 0.0) {      // (NaN or non-positive radius / threshold: literal path)
+    constexpr double kUp = 1.0 + 1e-9, kDn = 1.0 - 1e-9;   // margins of 5e-10 (r +- delta) on sqrt(dl): >> the ~4e-16 r the roundings can move
+    const double hi2 = hi * hi;
+    if (dl > hi2 * kUp) return false;                       // sqrt(dl) > r + delta for sure
+    if (lo > 1e-3 * r) {                                    // (a radius within 0.1 % of delta: the margin on r - delta would not cover its own rounding)
+      const double lo2 = lo * lo;
+      if (dl < lo2 * kDn) return false;                     // sqrt(dl) < r - delta for sure
+      if (dl < hi2 * kDn && dl > lo2 * kUp) return true;    // strictly between
+    }
+  }
+  dl = fabs(sqrt(dl) - r);
   return dl < cfg.delta;
 }
-template <> __device__ __forceinline__ bool agree<CIRCLE2>(const double* h, const double* x, const EstCfg& c) { return agree_sphere<2>(h, x, c); }
-template <> __device__ __forceinline__ bool agree<SPHERE3>(const double* h, const double* x, const EstCfg& c) { return agree_sphere<3>(h, x, c); }
-template <> __device__ __forceinline__ bool agree<SPHERE4>(const double* h, const double* x, const EstCfg& c) { return agree_sphere<4>(h, x, c); }
+#define LSQR_DEF_(ID, DIM) template <> __device__ __forceinline__ bool agree<ID>(const double* h, const double* x, const EstCfg& c) { return agree_sphere<DIM>(h, x, c); }
+LSQR_SPHERE_ALL_LIST(LSQR_DEF_)
+#undef LSQR_DEF_
 // AbsoluteOrientationParametersEstimator.cxx:316-327 with Frame::apply, common/Frame.cxx:229-248
 template <> __device__ __forceinline__ bool agree<ABSOR>(const double* h, const double* x, const EstCfg& cfg) {
   const double qx = h[0] * x[0] + h[1] * x[1] + h[2] * x[2] + h[9];
@@ -650,8 +699,9 @@ template <int N> __device__ __forceinline__ bool agree_dense(const double* h, co
   sum -= x[N];
   return fabs(sum) < cfg.delta;
 }
-template <> __device__ __forceinline__ bool agree<DENSE5>(const double* h, const double* x, const EstCfg& c) { return agree_dense<5>(h, x, c); }
-template <> __device__ __forceinline__ bool agree<DENSE6>(const double* h, const double* x, const EstCfg& c) { return agree_dense<6>(h, x, c); }
+#define LSQR_DEF_(ID, N) template <> __device__ __forceinline__ bool agree<ID>(const double* h, const double* x, const EstCfg& c) { return agree_dense<N>(h, x, c); }
+LSQR_DENSE_N_LIST(LSQR_DEF_)
+#undef LSQR_DEF_
 
 // ---------------------------------------------------------------------------------------
 // Subset generation
@@ -674,11 +724,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 // in draw order, RANSAC.hxx:56-68).  Draw j picks uniformly among the n-j indices not yet taken.
 template <int K>
 __device__ __forceinline__ void sample_subset(uint64_t gidx, uint64_t seed, uint32_t n, int32_t* out) {
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  uint32_t rnd[K > 4 ? 8 : 4] = {r.x, r.y, r.z, r.w};
-  if constexpr (K > 4) {   // second counter block for the 5th..8th draw
-    const uint4 r2 = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), 1u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    rnd[4] = r2.x; rnd[5] = r2.y; rnd[6] = r2.z; rnd[7] = r2.w;
+  constexpr int NB = (K + 3) / 4;   // one counter block per four draws
+  uint32_t rnd[4 * NB];
+#pragma unroll
+  for (int blk = 0; blk < NB; blk++) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)blk, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    rnd[4 * blk] = r.x; rnd[4 * blk + 1] = r.y; rnd[4 * blk + 2] = r.z; rnd[4 * blk + 3] = r.w;
   }
   uint32_t sorted[K];
 #pragma unroll

@@ -60,22 +60,22 @@ class ParametersEstimator:
 
 
 class PlaneParametersEstimator(ParametersEstimator):
-    """PlaneParametersEstimator<dimension> for dimension 3 or 4 (PlaneParametersEstimator.h:24-91)."""
+    """PlaneParametersEstimator<dimension> for dimension 2..8 (PlaneParametersEstimator.h:24-91)."""
 
     def __init__(self, delta, dimension=3):
-        if dimension not in (3, 4):
-            raise NotImplementedError("hyperplanes are accelerated for d = 3, 4")
-        self._model = "plane3" if dimension == 3 else "plane4"
+        if not 2 <= dimension <= 8:
+            raise NotImplementedError("hyperplanes are accelerated for d = 2..8")
+        self._model = f"plane{dimension}"
         super().__init__(dimension, delta)
 
 
 class LineParametersEstimator(ParametersEstimator):
-    """LineParametersEstimator<dimension> for dimension 2 or 3 (LineParametersEstimator.h:35-100)."""
+    """LineParametersEstimator<dimension> for dimension 2..8 (LineParametersEstimator.h:35-100)."""
 
     def __init__(self, delta, dimension=3):
-        if dimension not in (2, 3):
-            raise NotImplementedError("kD lines are accelerated for d = 2, 3")
-        self._model = "line2" if dimension == 2 else "line3"
+        if not 2 <= dimension <= 8:
+            raise NotImplementedError("kD lines are accelerated for d = 2..8")
+        self._model = f"line{dimension}"
         super().__init__(2, delta)
 
 
@@ -88,15 +88,15 @@ class Line2DParametersEstimator(ParametersEstimator):
 
 
 class SphereParametersEstimator(ParametersEstimator):
-    """SphereParametersEstimator<dimension> for dimension 2 (circle), 3 or 4 (SphereParametersEstimator.h:29-190)."""
+    """SphereParametersEstimator<dimension> for dimension 2 (circle) .. 8 (SphereParametersEstimator.h:29-190)."""
     ALGEBRAIC, GEOMETRIC = api.LS_ALGEBRAIC, api.LS_GEOMETRIC
 
     def __init__(self, delta, lsType=api.LS_GEOMETRIC, dimension=3):
         if lsType not in (self.ALGEBRAIC, self.GEOMETRIC):
             raise ValueError("lsType must be ALGEBRAIC or GEOMETRIC")  # SphereParametersEstimator.hxx:17-18 throws
-        if dimension not in (2, 3, 4):
-            raise NotImplementedError("hyperspheres are accelerated for d = 2, 3, 4")
-        self._model = {2: "circle2", 3: "sphere3", 4: "sphere4"}[dimension]
+        if not 2 <= dimension <= 8:
+            raise NotImplementedError("hyperspheres are accelerated for d = 2..8")
+        self._model = "circle2" if dimension == 2 else f"sphere{dimension}"
         super().__init__(dimension + 1, delta, ls_type=lsType)
 
     def setLeastSquaresType(self, lsType):
@@ -149,12 +149,12 @@ class PivotCalibrationEstimator(ParametersEstimator):
 
 
 class DenseLinearEquationSystemParametersEstimator(ParametersEstimator):
-    """DenseLinearEquationSystemParametersEstimator<double, n> (n = 5 or 6); datum = AugmentedRow as n+1 doubles
+    """DenseLinearEquationSystemParametersEstimator<double, n> (n = 2..8); datum = AugmentedRow as n+1 doubles
     [a_0..a_{n-1}, b]; parameters = the solution x (DenseLinearEquationSystemParametersEstimator.hxx:17-119)."""
 
     def __init__(self, delta, n):
-        if n not in (5, 6):
-            raise ValueError("dense linear systems are instantiated for n = 5 and n = 6 (the sizes the reference exercises)")
+        if not 2 <= n <= 8:
+            raise ValueError("dense linear systems are instantiated for n = 2..8 (the reference exercises 5 and 6)")
         self._model = f"dense{n}"
         super().__init__(n, delta)
 

@@ -250,8 +250,20 @@ GENERATORS = {
     "usxw": lambda n, seed=SEED: crosswire(n, seed=seed),
     "uscp": lambda n, seed=SEED: calibrated_pointer(n, seed=seed),
 }
+# the wider template space: fewer outliers as the minimal subset grows (0.8^9 = 13 % all-inlier subsets for the 8-D sphere)
+for _d in (2, 5, 6, 7, 8):
+    GENERATORS[f"plane{_d}"] = lambda n, seed=SEED, _d=_d: plane(n, seed=seed, dim=_d, outlier_frac=0.4 if _d == 2 else 0.2)
+for _d in (5, 6, 7, 8):
+    GENERATORS[f"sphere{_d}"] = lambda n, seed=SEED, _d=_d: sphere(n, _d, seed=seed, outlier_frac=0.2)
+for _d in (4, 5, 6, 7, 8):
+    GENERATORS[f"line{_d}"] = lambda n, seed=SEED, _d=_d: line(n, _d, seed=seed, sigma=0.1)   # the distance to a line grows like sigma sqrt(d - 1)
+for _n in (2, 3, 4, 7, 8):
+    GENERATORS[f"dense{_n}"] = lambda n, seed=SEED, _n=_n: dense_rows(n, _n, seed=seed, outlier_frac=0.3 if _n <= 4 else 0.2)
 DELTAS = {"plane3": 0.5, "line2d": 0.5, "line2": 0.5, "line3": 0.5, "circle2": 0.5, "sphere3": 0.5, "absor": 2.0, "ray": 1.0, "pivot": 1.0,
           "dense5": 0.2, "dense6": 0.2, "usxw": 1.0, "uscp": 1.0, "sphere4": 0.5, "plane4": 0.5}
+for _name in GENERATORS:
+    if _name not in DELTAS:
+        DELTAS[_name] = 0.2 if _name.startswith("dense") else 0.5
 
 
 def random_subsets(n, k, H, seed=SEED):

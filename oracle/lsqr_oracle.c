@@ -22,7 +22,32 @@
 #include <omp.h>
 #endif
 
-enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10, M_USXW = 11, M_USCP = 12, M_SPHERE4 = 13, M_PLANE4 = 14 };
+enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10, M_USXW = 11, M_USCP = 12, M_SPHERE4 = 13, M_PLANE4 = 14,
+       /* the rest of the reference's template space: PlaneParametersEstimator<2, 5..8>, SphereParametersEstimator<5..8>,
+        * LineParametersEstimator<4..8>, DenseLinearEquationSystemParametersEstimator<double, 2..4, 7, 8> */
+       M_PLANE2 = 15, M_PLANE5 = 16, M_PLANE8 = 19, M_SPHERE5 = 20, M_SPHERE8 = 23, M_LINE4 = 24, M_LINE8 = 28, M_DENSE2 = 29, M_DENSE4 = 31, M_DENSE7 = 32, M_DENSE8 = 33, M_COUNT = 34 };
+#define MAXD 9   /* doubles per datum of the dimension-templated estimators (8-unknown dense row) */
+
+/* Family and dimension of a dimension-templated estimator: every branch below that depends on `dimension` in the reference
+ * takes it from here.  F_NONE: one of the fixed-size estimators. */
+enum { F_NONE = 0, F_PLANE_ND, F_SPHERE_ND, F_LINE, F_DENSE };
+static int family(int model, int* dim) {
+  int d = 0, f = F_NONE;
+  if (model == M_PLANE4) { f = F_PLANE_ND; d = 4; }
+  else if (model == M_PLANE2) { f = F_PLANE_ND; d = 2; }
+  else if (model >= M_PLANE5 && model <= M_PLANE8) { f = F_PLANE_ND; d = model - M_PLANE5 + 5; }
+  else if (model == M_SPHERE4) { f = F_SPHERE_ND; d = 4; }
+  else if (model >= M_SPHERE5 && model <= M_SPHERE8) { f = F_SPHERE_ND; d = model - M_SPHERE5 + 5; }
+  else if (model == M_LINE2) { f = F_LINE; d = 2; }
+  else if (model == M_LINE3) { f = F_LINE; d = 3; }
+  else if (model >= M_LINE4 && model <= M_LINE8) { f = F_LINE; d = model - M_LINE4 + 4; }
+  else if (model == M_DENSE5) { f = F_DENSE; d = 5; }
+  else if (model == M_DENSE6) { f = F_DENSE; d = 6; }
+  else if (model >= M_DENSE2 && model <= M_DENSE4) { f = F_DENSE; d = model - M_DENSE2 + 2; }
+  else if (model == M_DENSE7 || model == M_DENSE8) { f = F_DENSE; d = model - M_DENSE7 + 7; }
+  if (dim) *dim = d;
+  return f;
+}
 
 /* common/Epsilon.h:19 */
 static const double EPS = 2.220446049250313e-016;
@@ -34,7 +59,15 @@ static const double FRAME_HALF_PI = 3.14159265358979323846 / 2.0;
 
 int orc_model_info(int model, int* D, int* P, int* k) {
   static const int tab[15][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}, {6, 5, 5}, {7, 6, 6}, {14, 20, 4}, {17, 17, 3}, {4, 5, 5}, {4, 8, 4}};
-  if (model < 0 || model > 14) return -1;
+  int d;
+  if (model < 0 || model >= M_COUNT) return -1;
+  switch (model > 14 ? family(model, &d) : F_NONE) {
+    case F_PLANE_ND: *D = d; *P = 2 * d; *k = d; return 0;
+    case F_SPHERE_ND: *D = d; *P = d + 1; *k = d + 1; return 0;
+    case F_LINE: *D = d; *P = 2 * d; *k = 2; return 0;
+    case F_DENSE: *D = d + 1; *P = d; *k = d; return 0;
+    default: break;
+  }
   *D = tab[model][0]; *P = tab[model][1]; *k = tab[model][2];
   return 0;
 }
@@ -133,7 +166,7 @@ static int pinv_solve(int m, int n, const double* Ain, const double* b, double t
  * singular values (descending, the trailing n-m zero) and an n x n V; nullvector() is V's last column.  Same
  * one-sided Jacobi as pinv_solve, run on the columns of the wide matrix. */
 static int null_vector(int m, int n, const double* Ain, double tol, double* x) {
-  double A[6 * 7], V[7 * 7], w[7];
+  double A[MAXD * MAXD], V[MAXD * MAXD], w[MAXD];
   int i, j, k, p, q, sweep, rank = 0, last = 0;
   memcpy(A, Ain, sizeof(double) * (size_t)m * n);
   for (i = 0; i < n; i++) for (j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0 : 0.0;
@@ -351,7 +384,7 @@ static int triad(const double* P0, const double* P1, const double* P2, double Rm
  * the k x (k+1) matrix [p_i, -1]; rank < k -> linearly dependent points; the normal is scaled to unit length, the point
  * on the plane is the first datum */
 static int plane_nd_estimate(int dim, const double* d, double* prm) {
-  double A[6 * 7], x[7], norm = 0;
+  double A[MAXD * MAXD], x[MAXD], norm = 0;
   int i, j;
   for (i = 0; i < dim; i++) { for (j = 0; j < dim; j++) A[i * (dim + 1) + j] = d[i * dim + j]; A[i * (dim + 1) + dim] = -1; }
   if (null_vector(dim, dim + 1, A, EPS, x) < dim) return 0;
@@ -365,7 +398,7 @@ static int plane_nd_estimate(int dim, const double* d, double* prm) {
 /* SphereParametersEstimator.hxx:169-202 (estimateND, dimensions other than 2 and 3): rows p0 - p_i, pseudo-inverse with
  * singular values <= EPS zeroed, rank < dim -> coplanar points */
 static int sphere_nd_estimate(int dim, const double* d, double* prm) {
-  double A[36], b[6] = {0, 0, 0, 0, 0, 0}, x[6], rSquared = 0.0;
+  double A[MAXD * MAXD], b[MAXD] = {0}, x[MAXD], rSquared = 0.0;
   int i, j, rank;
   for (i = 0; i < dim; i++)
     for (j = 0; j < dim; j++) { A[i * dim + j] = d[j] - d[(i + 1) * dim + j]; b[i] += A[i * dim + j] * (d[j] + d[(i + 1) * dim + j]); }
@@ -742,6 +775,16 @@ int orc_estimate(int model, double delta, double aux, const double* data, size_t
   int D, P, k;
   if (orc_model_info(model, &D, &P, &k)) return -1;
   if (n < (size_t)k) return 0;
+  if (model > 14) {   /* the wider template space: the same generic bodies, `dimension` from the model id */
+    int dim;
+    switch (family(model, &dim)) {
+      case F_PLANE_ND: return plane_nd_estimate(dim, data, params);
+      case F_SPHERE_ND: return sphere_nd_estimate(dim, data, params);
+      case F_LINE: return line_estimate(dim, data, delta * delta, params);
+      case F_DENSE: return dense_solve(dim, data, (size_t)dim, params);
+      default: return -1;
+    }
+  }
   switch (model) {
     case M_PLANE3: return plane3_estimate(data, params);
     case M_LINE2D: return line2d_estimate(data, delta * delta, params);
@@ -767,6 +810,35 @@ int orc_estimate(int model, double delta, double aux, const double* data, size_t
 /* ------------------------------------------------------------------------------------ */
 
 static int agree1(int model, double delta, const double* prm, const double* x) {
+  if (model > 14) {
+    int dim, i;
+    switch (family(model, &dim)) {
+      case F_PLANE_ND: { /* PlaneParametersEstimator.hxx:196-203 */
+        double sd = 0;
+        for (i = 0; i < dim; i++) sd += prm[i] * (x[i] - prm[dim + i]);
+        return (sd * sd) < delta * delta;
+      }
+      case F_LINE: { /* LineParametersEstimator.hxx:135-150 */
+        double v[MAXD], vDotN = 0.0, ds = 0.0;
+        for (i = 0; i < dim; i++) { v[i] = x[i] - prm[dim + i]; vDotN += v[i] * prm[i]; }
+        for (i = 0; i < dim; i++) ds += (v[i] - vDotN * prm[i]) * (v[i] - vDotN * prm[i]);
+        return ds < delta * delta;
+      }
+      case F_SPHERE_ND: { /* SphereParametersEstimator.hxx:255-264 */
+        double dl = 0;
+        for (i = 0; i < dim; i++) dl += ((x[i] - prm[i]) * (x[i] - prm[i]));
+        dl = fabs(sqrt(dl) - prm[dim]);
+        return dl < delta;
+      }
+      case F_DENSE: { /* DenseLinearEquationSystemParametersEstimator.hxx:111-119 */
+        double sum = 0.0;
+        for (i = 0; i < dim; i++) sum += x[i] * prm[i];
+        sum -= x[dim];
+        return fabs(sum) < delta;
+      }
+      default: return 0;
+    }
+  }
   switch (model) {
     case M_PLANE3:
     case M_PLANE4: { /* PlaneParametersEstimator.hxx:196-203 */
@@ -847,7 +919,7 @@ int orc_agree(int model, double delta, double aux, const double* params, int np,
 /* PlaneParametersEstimator.hxx:129-172 (col=0: smallest eigenvalue) and
  * LineParametersEstimator.hxx:68-111 (col=dim-1: largest) share the covariance build. */
 static int cov_eig_estimate(int dim, int col, const double* d, size_t n, double* prm) {
-  double mean[4] = {0, 0, 0, 0}, cov[16] = {0}, meanMat[16], V[16], ev[4], sqrtN = sqrt((double)n);
+  double mean[MAXD] = {0}, cov[MAXD * MAXD] = {0}, meanMat[MAXD * MAXD], V[MAXD * MAXD], ev[MAXD], sqrtN = sqrt((double)n);
   size_t i; int j, k;
   for (i = 0; i < n; i++) for (j = 0; j < dim; j++) mean[j] += d[i * dim + j];
   for (j = 0; j < dim; j++) mean[j] /= sqrtN;
@@ -890,7 +962,7 @@ static int line2d_lsq(const double* d, size_t n, double* prm) {
 static int sphere_algebraic(int dim, const double* d, size_t n, double* prm) {
   int cols = dim + 1, j, rank;
   size_t i;
-  double x[5], rSquared;
+  double x[MAXD], rSquared;
   double* A = (double*)malloc(sizeof(double) * n * cols);
   double* b = (double*)calloc(n, sizeof(double));
   for (i = 0; i < n; i++) {
@@ -929,7 +1001,7 @@ static int sphere_lm_fcn(void* user, int m, int n, const double* x, double* fvec
  * reports success. */
 static int sphere_geometric(int dim, const double* d, size_t n, const double* init, double* prm) {
   sphere_lm_ctx c;
-  double x[5], *fvec;
+  double x[MAXD], *fvec;
   int p = dim + 1, a, info;
   if ((int)n < p) return 0;
   c.d = d; c.dim = dim;
@@ -945,7 +1017,7 @@ static int sphere_geometric(int dim, const double* d, size_t n, const double* in
 
 /* SphereParametersEstimator.hxx:209-232 */
 static int sphere_lsq(int dim, int ls_type, const double* d, size_t n, double* prm) {
-  double init[5];
+  double init[MAXD];
   if (ls_type == 0) return sphere_algebraic(dim, d, n, prm);
   if (!sphere_algebraic(dim, d, n, init)) return 0;
   return sphere_geometric(dim, d, n, init, prm);
@@ -1023,6 +1095,16 @@ int orc_least_squares(int model, double delta, double aux, int ls_type, const do
   (void)delta; (void)aux;
   if (orc_model_info(model, &D, &P, &k)) return -1;
   if (n < (size_t)k && model != M_RAY) return 0; /* ray LS has no size guard (:100-144) */
+  if (model > 14) {
+    int dim;
+    switch (family(model, &dim)) {
+      case F_PLANE_ND: return cov_eig_estimate(dim, 0, data, n, params);          /* PlaneParametersEstimator.hxx:129-172 */
+      case F_LINE: return cov_eig_estimate(dim, dim - 1, data, n, params);        /* LineParametersEstimator.hxx:68-111 */
+      case F_SPHERE_ND: return sphere_lsq(dim, ls_type, data, n, params);
+      case F_DENSE: return dense_solve(dim, data, n, params);
+      default: return -1;
+    }
+  }
   switch (model) {
     case M_PLANE3: return cov_eig_estimate(3, 0, data, n, params);
     case M_PLANE4: return cov_eig_estimate(4, 0, data, n, params);
@@ -1050,7 +1132,7 @@ int orc_least_squares(int model, double delta, double aux, int ls_type, const do
 /* RANSAC.hxx:217-249 body for one subset (full scoring, no early exit). */
 static uint32_t score_one(int model, int D, int k, double delta, double aux, const double* data, size_t n,
                           const int32_t* sub, double* prm, int* nprm) {
-  double pts[6 * 17];
+  double pts[10 * 17];   /* up to 9 data (8-D hypersphere) of up to 17 doubles */
   int j; size_t m; uint32_t c = 0;
   for (j = 0; j < k; j++) memcpy(pts + j * D, data + (size_t)sub[j] * D, sizeof(double) * D);
   *nprm = orc_estimate(model, delta, aux, pts, (size_t)k, prm);
@@ -1122,7 +1204,7 @@ unsigned int orc_num_tries(double prob, unsigned int votes, unsigned int n, unsi
 int orc_ransac_exhaustive(int model, double delta, double aux, int ls_type, const double* data, size_t n,
                           double* params, uint8_t* mask, double* fraction, uint32_t* best_count, uint64_t* best_rank) {
   int D, P, k, np = 0, j;
-  int32_t sub[6];
+  int32_t sub[10];
   uint32_t best = 0; uint64_t rank = 0, brank = 0; double bprm[20], prm[20];
   size_t m, nin = 0;
   double* inl;

@@ -22,6 +22,20 @@ MODELS = {"plane3": 0, "line2d": 1, "line2": 2, "line3": 3, "circle2": 4, "spher
 # model -> (D doubles per datum, P params, k minimal subset)
 INFO = {0: (3, 6, 3), 1: (2, 4, 2), 2: (2, 4, 2), 3: (3, 6, 2), 4: (2, 3, 3), 5: (3, 4, 4), 6: (6, 7, 3), 7: (6, 3, 2), 8: (12, 6, 3),
         9: (6, 5, 5), 10: (7, 6, 6), 11: (14, 20, 4), 12: (17, 17, 3), 13: (4, 5, 5), 14: (4, 8, 4)}
+# the rest of the reference's template space: PlaneParametersEstimator<2, 5..8>, SphereParametersEstimator<5..8>,
+# LineParametersEstimator<4..8>, DenseLinearEquationSystemParametersEstimator<double, 2..4, 7, 8> (ids as in lsqr_oracle.c)
+for _d, _id in ((2, 15), (5, 16), (6, 17), (7, 18), (8, 19)):
+    MODELS[f"plane{_d}"] = _id
+    INFO[_id] = (_d, 2 * _d, _d)
+for _d in range(5, 9):
+    MODELS[f"sphere{_d}"] = 20 + _d - 5
+    INFO[20 + _d - 5] = (_d, _d + 1, _d + 1)
+for _d in range(4, 9):
+    MODELS[f"line{_d}"] = 24 + _d - 4
+    INFO[24 + _d - 4] = (_d, 2 * _d, 2)
+for _n, _id in ((2, 29), (3, 30), (4, 31), (7, 32), (8, 33)):
+    MODELS[f"dense{_n}"] = _id
+    INFO[_id] = (_n + 1, _n, _n)
 
 
 def lib_path(kind):

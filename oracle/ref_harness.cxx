@@ -37,7 +37,10 @@
 
 using namespace lsqrRecipes;
 
-enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10, M_USXW = 11, M_USCP = 12, M_SPHERE4 = 13, M_PLANE4 = 14 };
+enum { M_PLANE3 = 0, M_LINE2D = 1, M_LINE2 = 2, M_LINE3 = 3, M_CIRCLE2 = 4, M_SPHERE3 = 5, M_ABSOR = 6, M_RAY = 7, M_PIVOT = 8, M_DENSE5 = 9, M_DENSE6 = 10, M_USXW = 11, M_USCP = 12, M_SPHERE4 = 13, M_PLANE4 = 14,
+       // further instantiations of the reference's dimension-templated estimators (ids of lsqr_oracle.c / include/lsqr_b200.h)
+       M_PLANE2 = 15, M_PLANE5 = 16, M_PLANE6 = 17, M_PLANE7 = 18, M_PLANE8 = 19, M_SPHERE5 = 20, M_SPHERE6 = 21, M_SPHERE7 = 22, M_SPHERE8 = 23,
+       M_LINE4 = 24, M_LINE5 = 25, M_LINE6 = 26, M_LINE7 = 27, M_LINE8 = 28, M_DENSE2 = 29, M_DENSE3 = 30, M_DENSE4 = 31, M_DENSE7 = 32, M_DENSE8 = 33, M_COUNT = 34 };
 
 namespace {
 
@@ -120,6 +123,14 @@ template <class F> int dispatch(const Cfg& c, F& f) {
     case M_PIVOT: { PivotCalibrationEstimator e(c.delta); return f(&e, (Frame*)0); }
     case M_DENSE5: { DenseLinearEquationSystemParametersEstimator<double, 5> e(c.delta); return f(&e, (AugmentedRow<double, 5>*)0); }
     case M_DENSE6: { DenseLinearEquationSystemParametersEstimator<double, 6> e(c.delta); return f(&e, (AugmentedRow<double, 6>*)0); }
+#define REF_PLANE(ID, DIM) case ID: { PlaneParametersEstimator<DIM> e(c.delta); return f(&e, (Point<double, DIM>*)0); }
+    REF_PLANE(M_PLANE2, 2) REF_PLANE(M_PLANE5, 5) REF_PLANE(M_PLANE6, 6) REF_PLANE(M_PLANE7, 7) REF_PLANE(M_PLANE8, 8)
+#define REF_SPHERE(ID, DIM) case ID: { SphereParametersEstimator<DIM> e(c.delta, c.ls_type == 0 ? SphereParametersEstimator<DIM>::ALGEBRAIC : SphereParametersEstimator<DIM>::GEOMETRIC); return f(&e, (Point<double, DIM>*)0); }
+    REF_SPHERE(M_SPHERE5, 5) REF_SPHERE(M_SPHERE6, 6) REF_SPHERE(M_SPHERE7, 7) REF_SPHERE(M_SPHERE8, 8)
+#define REF_LINE(ID, DIM) case ID: { LineParametersEstimator<DIM> e(c.delta); return f(&e, (Point<double, DIM>*)0); }
+    REF_LINE(M_LINE4, 4) REF_LINE(M_LINE5, 5) REF_LINE(M_LINE6, 6) REF_LINE(M_LINE7, 7) REF_LINE(M_LINE8, 8)
+#define REF_DENSE(ID, N) case ID: { DenseLinearEquationSystemParametersEstimator<double, N> e(c.delta); return f(&e, (AugmentedRow<double, N>*)0); }
+    REF_DENSE(M_DENSE2, 2) REF_DENSE(M_DENSE3, 3) REF_DENSE(M_DENSE4, 4) REF_DENSE(M_DENSE7, 7) REF_DENSE(M_DENSE8, 8)
     case M_USXW: {
       SingleUnknownPointTargetUSCalibrationParametersEstimator e(c.delta, c.ls_type == 0 ? SingleUnknownPointTargetUSCalibrationParametersEstimator::ANALYTIC
                                                                                          : SingleUnknownPointTargetUSCalibrationParametersEstimator::ITERATIVE);
@@ -205,7 +216,11 @@ extern "C" {
 
 int ref_model_info(int model, int* D, int* P, int* k) {
   static const int tab[15][3] = {{3, 6, 3}, {2, 4, 2}, {2, 4, 2}, {3, 6, 2}, {2, 3, 3}, {3, 4, 4}, {6, 7, 3}, {6, 3, 2}, {12, 6, 3}, {6, 5, 5}, {7, 6, 6}, {14, 20, 4}, {17, 17, 3}, {4, 5, 5}, {4, 8, 4}};
-  if (model < 0 || model > 14) return -1;
+  if (model < 0 || model >= M_COUNT) return -1;
+  if (model >= M_PLANE2 && model <= M_PLANE8) { const int d = model == M_PLANE2 ? 2 : model - M_PLANE5 + 5; *D = d; *P = 2 * d; *k = d; return 0; }
+  if (model >= M_SPHERE5 && model <= M_SPHERE8) { const int d = model - M_SPHERE5 + 5; *D = d; *P = d + 1; *k = d + 1; return 0; }
+  if (model >= M_LINE4 && model <= M_LINE8) { const int d = model - M_LINE4 + 4; *D = d; *P = 2 * d; *k = 2; return 0; }
+  if (model >= M_DENSE2 && model <= M_DENSE8) { const int n = model <= M_DENSE4 ? model - M_DENSE2 + 2 : model - M_DENSE7 + 7; *D = n + 1; *P = n; *k = n; return 0; }
   *D = tab[model][0]; *P = tab[model][1]; *k = tab[model][2];
   return 0;
 }

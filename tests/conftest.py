@@ -59,9 +59,45 @@ def same_up_to_sign(a, b, idx, tol):
     return bool(np.all(np.abs(a - b) <= tol * scale))
 
 
-# parameter entries that carry an arbitrary sign after leastSquaresEstimate
-SIGN_IDX = {"plane3": [0, 1, 2], "line2d": [0, 1], "line2": [0, 1], "line3": [0, 1, 2], "circle2": [], "sphere3": [],
-            "absor": [0, 1, 2, 3], "ray": [], "pivot": [], "dense5": [], "dense6": [], "usxw": [], "uscp": [], "sphere4": [], "plane4": [0, 1, 2, 3]}
+def model_family(name):
+    """('plane' | 'sphere' | 'line' | 'dense' | None, dimension) of a dimension-templated estimator name."""
+    import re
+    if name == "circle2":
+        return "sphere", 2
+    m = re.fullmatch(r"(plane|sphere|line|dense)(\d)", name)
+    return (m.group(1), int(m.group(2))) if m else (None, 0)
+
+
+class _SignIdx(dict):
+    """parameter entries that carry an arbitrary sign after leastSquaresEstimate: hyperplane normals, line directions, quaternions"""
+
+    def __missing__(self, name):
+        fam, d = model_family(name)
+        return list(range(d)) if fam in ("plane", "line") else []
+
+
+SIGN_IDX = _SignIdx({"line2d": [0, 1], "absor": [0, 1, 2, 3]})
+
+
+def is_sphere(name):
+    return model_family(name)[0] == "sphere"
+
+
+def ls_types(name):
+    """least-squares variants of an estimator: algebraic / geometric hypersphere, analytic / iterative ultrasound calibration"""
+    return [0, 1] if (is_sphere(name) or name in ("usxw", "uscp")) else [1]
+
+
+def pinv_tol(name):
+    """None where estimate() is plain double arithmetic in the reference (bit-exact parity); else the rounding-level tolerance of
+    the minimal solvers that go through a pseudo-inverse / null vector (VNL's SVD there, one-sided Jacobi here), which scales
+    with the conditioning of the minimal system (the 9x9 / 12x12 calibration systems of random subsets reach 1e7)."""
+    fam, d = model_family(name)
+    if name == "pivot" or fam == "dense" or (fam == "plane" and d != 3):
+        return 1e-9 if d <= 6 else 1e-8
+    if name in ("usxw", "uscp") or (fam == "sphere" and d >= 4):
+        return 1e-6
+    return None
 
 
 def lm_case_is_clear(port, name, ls_type):

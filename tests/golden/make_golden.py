@@ -37,11 +37,12 @@ def main():
         data, true = synth.GENERATORS[name](n, seed=synth.SEED + m)
         subsets = synth.random_subsets(n, k, 400, seed=synth.SEED + 100 + m)
         counts, params = ref.score_subsets(m, delta, data, subsets)
-        # exhaustive RANSAC::compute on a smaller problem (C(28,4) = 20475 subsets at most)
-        ns = 28
+        # exhaustive RANSAC::compute on a smaller problem (C(28,4) = 20475 subsets at most; the larger minimal subsets of
+        # the wider template space get fewer data so that C(ns, k) stays below 20000)
+        ns = 28 if (k <= 4 or m <= 14) else {5: 20, 6: 18, 7: 16, 8: 16, 9: 16}[k]
         small, _ = synth.GENERATORS[name](ns, seed=synth.SEED + 200 + m)
         fx = {"data": data, "delta": delta, "subsets": subsets, "counts": counts, "params": params, "true": true, "small": small}
-        for ls_type in ([0, 1] if name in ("circle2", "sphere3", "sphere4", "usxw", "uscp") else [1]):
+        for ls_type in ([0, 1] if (name.startswith(("circle", "sphere")) or name in ("usxw", "uscp")) else [1]):
             prm, mask, frac, cnt, _ = ref.ransac_exhaustive(m, delta, small, ls_type=ls_type)
             fx[f"ex_params_ls{ls_type}"] = prm
             fx[f"ex_mask_ls{ls_type}"] = mask

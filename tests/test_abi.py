@@ -34,6 +34,12 @@ def test_model_table_matches_reference_shapes():
         assert lib.lsqr_model_info(m, ctypes.byref(d), ctypes.byref(p), ctypes.byref(k)) == 0
         assert (d.value, p.value, k.value) == api.MODEL_INFO[m]
     assert lib.lsqr_model_info(99, None, None, None) != 0
+    # the dimension-templated estimators: ids by dimension, -1 outside the instantiated range
+    for d in range(2, 9):
+        assert lib.lsqr_model_plane(d) == api.MODELS[f"plane{d}"] and lib.lsqr_model_line(d) == api.MODELS[f"line{d}"]
+        assert lib.lsqr_model_sphere(d) == api.MODELS["circle2" if d == 2 else f"sphere{d}"] and lib.lsqr_model_dense(d) == api.MODELS[f"dense{d}"]
+    assert [f(9) for f in (lib.lsqr_model_plane, lib.lsqr_model_sphere, lib.lsqr_model_line, lib.lsqr_model_dense)] == [-1] * 4
+    assert lib.lsqr_model_plane(1) == -1 and lib.lsqr_model_dense(1) == -1
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -102,7 +108,11 @@ def test_estimator_mirrors_keep_the_reference_contracts():
         assert api.MODEL_INFO[api.MODELS[est._model]][2] == k
     with pytest.raises(ValueError):
         L.SphereParametersEstimator(0.5, lsType=7)
-    for bad in (lambda: L.PlaneParametersEstimator(0.5, dimension=5), lambda: L.SphereParametersEstimator(0.5, dimension=5),
-                lambda: L.LineParametersEstimator(0.5, dimension=4), lambda: L.DenseLinearEquationSystemParametersEstimator(0.5, 7)):
+    # the template space of the dimensioned estimators: 2..8, minimal subsets d / d + 1 / 2 / n
+    for d in range(2, 9):
+        assert L.PlaneParametersEstimator(0.5, dimension=d).numForEstimate() == d and L.SphereParametersEstimator(0.5, dimension=d).numForEstimate() == d + 1
+        assert L.LineParametersEstimator(0.5, dimension=d).numForEstimate() == 2 and L.DenseLinearEquationSystemParametersEstimator(0.5, d).numForEstimate() == d
+    for bad in (lambda: L.PlaneParametersEstimator(0.5, dimension=9), lambda: L.SphereParametersEstimator(0.5, dimension=9),
+                lambda: L.LineParametersEstimator(0.5, dimension=9), lambda: L.DenseLinearEquationSystemParametersEstimator(0.5, 9)):
         with pytest.raises((NotImplementedError, ValueError)):
             bad()

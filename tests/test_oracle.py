@@ -5,15 +5,11 @@ No GPU involved."""
 import numpy as np
 import pytest
 
-from conftest import SIGN_IDX, golden, same_up_to_sign
+from conftest import SIGN_IDX, golden, ls_types, pinv_tol, same_up_to_sign
 from lsqrrecipes_b200 import synth
 from oracle.pyoracle import INFO, MODELS
 
 ALL = list(MODELS.items())
-PINV_MODELS = ("pivot", "dense5", "dense6", "usxw", "uscp", "sphere4", "plane4")   # estimate() goes through a pseudo-inverse: rounding-level, not bit-exact
-# ... where "rounding level" scales with the conditioning of the minimal system (the 9x9 / 12x12 calibration systems of
-# random subsets reach 1e7)
-PINV_TOL = {"pivot": 1e-9, "dense5": 1e-9, "dense6": 1e-9, "usxw": 1e-6, "uscp": 1e-6, "sphere4": 1e-6, "plane4": 1e-9}
 
 
 # ---- the reference's own literal test vectors -------------------------------------------
@@ -62,8 +58,8 @@ def test_port_matches_reference_fixture(port, name, m):
     counts, params = port.score_subsets(m, float(g["delta"]), g["data"], g["subsets"])
     assert np.array_equal(counts, g["counts"]), "per-hypothesis inlier counts must be bit-exact"
     assert np.array_equal(np.isnan(params), np.isnan(g["params"])), "same degenerate subsets"
-    if name in PINV_MODELS:  # 9x6 / n x n pseudo-inverse goes through the SVD stand-in: rounding-level agreement
-        assert np.allclose(np.nan_to_num(params), np.nan_to_num(g["params"]), rtol=PINV_TOL[name], atol=PINV_TOL[name])
+    if pinv_tol(name):  # 9x6 / n x n pseudo-inverse goes through the SVD stand-in: rounding-level agreement
+        assert np.allclose(np.nan_to_num(params), np.nan_to_num(g["params"]), rtol=pinv_tol(name), atol=pinv_tol(name))
     else:
         assert np.array_equal(np.nan_to_num(params), np.nan_to_num(g["params"])), "estimate() must be bit-exact"
 
@@ -71,7 +67,7 @@ def test_port_matches_reference_fixture(port, name, m):
 @pytest.mark.parametrize("name,m", ALL)
 def test_port_exhaustive_and_lsq_fixture(port, name, m):
     g = golden(name)
-    for ls_type in ([0, 1] if name in ("circle2", "sphere3", "sphere4", "usxw", "uscp") else [1]):
+    for ls_type in ls_types(name):
         # Levenberg-Marquardt results: both sides run MINPACK's lmder (oracle/minpack_lm.h) on the reference's scalar residuals;
         # the cross-wire valley is flat (hundreds of evaluations), so its end point is compared at the north star's 1e-6
         tol = 1e-6 if (name == "usxw" and ls_type == 1) else 1e-8
@@ -110,8 +106,8 @@ def test_port_matches_reference_live(port, ref, name, m):
     c2, p2 = ref.score_subsets(m, delta, data, subs)
     assert np.array_equal(c1, c2)
     assert np.array_equal(np.isnan(p1), np.isnan(p2))
-    if name in PINV_MODELS:
-        assert np.allclose(np.nan_to_num(p1), np.nan_to_num(p2), rtol=PINV_TOL[name], atol=PINV_TOL[name])
+    if pinv_tol(name):
+        assert np.allclose(np.nan_to_num(p1), np.nan_to_num(p2), rtol=pinv_tol(name), atol=pinv_tol(name))
     else:
         assert np.array_equal(np.nan_to_num(p1), np.nan_to_num(p2))
 

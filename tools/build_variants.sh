@@ -15,5 +15,5 @@ for cfg in "$@"; do
     -DLSQR_CB_MINBLOCKS=$1 -DLSQR_CB_R_PLANE=$2 -DLSQR_CB_THREADS=$4 -DLSQR_CB_PPI_PLANE=$ppi $sweep -Xptxas -v -c k_fast.cu -o /tmp/kf_$tag.o 2>&1 \
     | grep -A2 "consensus_cb_kernelILi0E" | grep -E "Used|spill" | tr '\n' ' '
   echo " <- $tag"
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../tools/bin/variants/lib_$tag.so build/engine.o build/k_score.o /tmp/kf_$tag.o build/k_refine.o build/k_bench.o -cudart shared
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../tools/bin/variants/lib_$tag.so build/engine.o build/k_score.o /tmp/kf_$tag.o build/k_refine.o build/k_batch.o build/k_bench.o -cudart shared
 done
