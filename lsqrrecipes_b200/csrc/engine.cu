@@ -1010,7 +1010,7 @@ int batch_impl(lsqr_ctx* ctx, const double* data, const uint64_t* offsets, uint6
   const size_t rec_bytes = (size_t)mi.D * sizeof(double);
   const bool pinned = is_pinned(data + base * mi.D);
   const uint64_t chunk_rec = std::max<uint64_t>((pinned ? (16u << 20) : (4u << 20)) / rec_bytes, 1);
-  const size_t ring_bytes = (size_t)(chunk_rec + max_n) * rec_bytes;
+  const size_t ring_bytes = (size_t)chunk_rec * rec_bytes;
   if (!pinned) {
     if (ctx->up_pin_bytes < ring_bytes) {
       for (int i = 0; i < lsqr_ctx::kRing; i++) { if (ctx->up_pin[i]) cudaFreeHost(ctx->up_pin[i]); ctx->up_pin[i] = nullptr; }
@@ -1025,23 +1025,29 @@ int batch_impl(lsqr_ctx* ctx, const double* data, const uint64_t* offsets, uint6
   CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->up_land[7], 0));
   std::vector<cudaEvent_t> tev;                      // kernel time = sum over the chunks' launches
   int ring = 0, land = 0;
+  // copies go in pieces of chunk_rec records; a launch covers the problems of ~32 MB of them (several thousand small problems:
+  // enough thread blocks to fill the GPU -- launches of one copy piece each, ~650 blocks, tripled the kernel time)
+  const uint64_t launch_rec = std::max<uint64_t>(chunk_rec, (32u << 20) / rec_bytes);
   for (uint64_t q0 = p0; q0 < p1;) {
     uint64_t q1 = q0 + 1;
-    while (q1 < p1 && offsets[q1 + 1] - offsets[q0] <= chunk_rec) q1++;
+    while (q1 < p1 && offsets[q1 + 1] - offsets[q0] <= launch_rec) q1++;
     const uint64_t rec0 = offsets[q0] - base, nrec = offsets[q1] - offsets[q0];
-    if (nrec) {
-      const double* src = data + offsets[q0] * mi.D;
-      double* dst = ctx->bt_data + rec0 * mi.D;
+    for (uint64_t c0 = 0; c0 < nrec; c0 += chunk_rec) {
+      const uint64_t cn = std::min<uint64_t>(chunk_rec, nrec - c0);
+      const double* src = data + (offsets[q0] + c0) * mi.D;
+      double* dst = ctx->bt_data + (rec0 + c0) * mi.D;
       if (!pinned) {
         const int b = ring % lsqr_ctx::kRing;
         if (ring >= lsqr_ctx::kRing) CK(cudaEventSynchronize(ctx->up_ev[b]));   // the copy that used this buffer has finished
         ring++;
-        ctx->copier->copy(ctx->up_pin[b], src, nrec * rec_bytes);
-        CK(cudaMemcpyAsync(dst, ctx->up_pin[b], nrec * rec_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        ctx->copier->copy(ctx->up_pin[b], src, cn * rec_bytes);
+        CK(cudaMemcpyAsync(dst, ctx->up_pin[b], cn * rec_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
         CK(cudaEventRecord(ctx->up_ev[b], ctx->copy_stream));
       } else {
-        CK(cudaMemcpyAsync(dst, src, nrec * rec_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaMemcpyAsync(dst, src, cn * rec_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
       }
+    }
+    if (nrec) {
       cudaEvent_t landed = ctx->up_land[land++ % 7];
       CK(cudaEventRecord(landed, ctx->copy_stream));
       CK(cudaStreamWaitEvent(s, landed, 0));

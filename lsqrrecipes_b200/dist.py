@@ -5,13 +5,14 @@ by global index (rank r owns [r*H/W, (r+1)*H/W); Philox counters and lexicograph
 global, so results do not depend on W), and exactly two exchange steps:
   1. one all-reduce(MAX) on the packed 64-bit key (count << 32) | (0xFFFFFFFF - index): largest
      count wins, ties go to the smallest index -- the strict '>' of RANSAC.hxx:100,245;
-  2. one all-reduce(SUM) of <= 32 doubles per refine pass (per LM iteration for the sphere):
+  2. one all-reduce(SUM) of <= 91 doubles per refine pass (per LM evaluation for the iterative fits):
      the least-squares moments of the point shards.
 Both run in place on device memory through the hooks of lsqr_set_shard.  Replicating the points is the one bulk
 transfer: `upload_replicated` moves 1/W of the host buffer over each GPU's PCIe link and lets an NCCL all-gather over
 NVLink / NVSwitch fan it out, instead of W full uploads competing for the host's memory bandwidth.  The helpers below are
 pure functions so that the N>1 logic is testable with gloo on CPU.
 """
+import contextlib
 import ctypes
 
 import numpy as np
@@ -62,10 +63,16 @@ def install_hooks(engine, rank, world, group=None):
     import torch
     import torch.distributed as dist
 
+    def on(stream):
+        # the hook contract is "stream-ordered on the stream handed in": make it torch's current stream for the collective, so
+        # that NCCL's own stream waits for it and it waits for NCCL (a null handle means the legacy default stream)
+        return torch.cuda.stream(torch.cuda.ExternalStream(int(stream))) if stream else contextlib.nullcontext()
+
     def max_hook(user, dev_key, stream):
         try:
-            t = torch.as_tensor(_DevArray(dev_key, 1, "<i8"), device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            with on(stream):
+                t = torch.as_tensor(_DevArray(dev_key, 1, "<i8"), device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
             return 0
         except Exception as e:  # never raise across the C ABI
             print("max all-reduce hook failed:", e)
@@ -73,8 +80,9 @@ def install_hooks(engine, rank, world, group=None):
 
     def sum_hook(user, dev_vals, count, stream):
         try:
-            t = torch.as_tensor(_DevArray(dev_vals, count, "<f8"), device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            with on(stream):
+                t = torch.as_tensor(_DevArray(dev_vals, count, "<f8"), device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
             return 0
         except Exception as e:
             print("sum all-reduce hook failed:", e)
