@@ -113,9 +113,9 @@ class ClockSampler:
 
 
 def load_traffic():
-    """DRAM bytes per launch from the committed ncu --set full captures (profiles/r01_traffic.json)."""
+    """DRAM bytes per launch from the committed ncu --set full captures (profiles/r02_traffic.json)."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
     except Exception:
         return {}
 

@@ -1264,6 +1264,7 @@ int lsqr_set_estimator(lsqr_ctx* ctx, int model, double delta, double aux, int l
   const bool distance_threshold = model_family(model) == FAM_SPHERE || model_family(model) == FAM_DENSE || model == LSQR_PIVOT;
   ctx->cfg.delta = distance_threshold ? delta : fabs(delta);
   ctx->cfg.delta2 = delta * delta;
+  { unsigned long long b = 0; const double d2 = ctx->cfg.delta2; if (d2 == d2) memcpy(&b, &d2, sizeof(b)); ctx->cfg.delta2_bits = b; }   // below_delta2 (models.cuh)
   const double ang = aux > 0 ? aux : 0.017453292519943295769236907684886;  // RayIntersectionParametersEstimator.h:35
   double ce = sin(ang);
   ce *= ce;

@@ -13,13 +13,16 @@
 //   * Small requests (adaptive RANSAC rounds, tests) take consensus32_kernel: point tiles staged by TMA bulk copies into a
 //     2-deep shared-memory ring (as in k_score.cu), pairs through LDS.128.
 //   * Counting, three ALU instructions per two residuals in the hot kernel:
-//       - plane / 4-D hyperplane: CARRY CHAIN (count_carry) -- the hoisted constant carries +delta, the residual arrives as
-//         s' = s + delta, inlier <=> bits(s') < bits(2 delta) unsigned; two carry-only IADD3 and one IADD3.X with the two
-//         predicates as carry-ins, one register operand each;
-//       - 2-D line, dense systems, hypersphere family (|d^2 - m| < w, per-hypothesis w): two FSET.BF and one three-input
-//         IADD3 on their raw words (count_abs_lt4_raw, decoded by cb_raw_decode);
-//       - vector residuals (lines, absolute orientation, ray, pivot, ultrasound): the FMA chain starts at -delta^2, so
-//         the SIGN BIT of the sum is the decision and LEA.HI adds it (count_sign).
+//       - hyperplanes, dense systems, hypersphere family: CARRY CHAIN (count_carry) -- the residual arrives shifted (the hoisted
+//         constant carries +delta; hypersphere: t' = d^2 - (r - delta)^2), inlier <=> bits(s') < bits(window) unsigned (window 2 delta,
+//         or the hypothesis' own 4 r delta); two carry-only IADD3 and one IADD3.X with the two predicates as carry-ins, one
+//         register operand each;
+//       - 2-D lines (Line2D, Line<2>): two FFMA2 per pair leave the ALU pipe as the limit of any 3-ALU count, so of every four
+//         point pairs two are tested as |s| < delta (two FSET.BF and one three-input IADD3 on their raw words,
+//         count_abs_lt4_raw, decoded by cb_raw_decode) and two through the sign of s^2 - delta^2 (one more FFMA2, LEA.HI):
+//         5 + 5 pipe slots per two pairs instead of 4 + 6;
+//       - vector residuals (lines of 3 and more dimensions, absolute orientation, ray, pivot, ultrasound): the FMA chain starts
+//         at -delta^2, so the SIGN BIT of the sum is the decision and LEA.HI adds it (count_sign).
 //     Both kernels evaluate the same predicate per model, so their counts are bit-identical (tested).
 // Tensor cores are deliberately unused: contraction depth <= 4 (BASELINE.json north_star).
 #include "engine.h"
@@ -536,7 +539,10 @@ __global__ void __launch_bounds__(THREADS) consensus32_kernel(const float* __res
       f2 x[PPI][D];
 #pragma unroll
       for (int d = 0; d < D; d++) {
-        if constexpr (PPI == 2) {
+        if constexpr (PPI == 4) {
+          const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(tl + d * TILE + i), w = *reinterpret_cast<const ulonglong2*>(tl + d * TILE + i + 4);
+          x[0][d].v = v.x; x[1][d].v = v.y; x[2][d].v = w.x; x[3][d].v = w.y;
+        } else if constexpr (PPI == 2) {
           const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(tl + d * TILE + i);
           x[0][d].v = v.x; x[1][d].v = v.y;
         } else {
@@ -547,10 +553,11 @@ __global__ void __launch_bounds__(THREADS) consensus32_kernel(const float* __res
       for (int r = 0; r < R; r++) {
 #pragma unroll
         for (int u = 0; u < PPI; u++) {
-          // the predicate must be the constant-bank kernel's: shifted models count through the carry chain, models with a
-          // per-hypothesis threshold always take the |.| < thr form
+          // the predicate must be the constant-bank kernel's for every (hypothesis, datum): shifted models count through the
+          // carry chain; the 2-D lines take |s| < delta for the first two point pairs of every group of four and the sign of
+          // s^2 - delta^2 for the other two (kMixed, see consensus_cb_kernel); vector residuals the sign of the sum
           if constexpr (Eval<M>::kShifted) count_carry(out[r], Eval<M>::dist(q[r], x[u]), hyp_negk<M>(q[r], negk));
-          else if (Eval<M>::kHasAbsForm && (Eval<M>::kThr >= 0 || (r % 3) != 0)) count_abs_lt(cnt[r], Eval<M>::dist(q[r], x[u]), hyp_thr<M>(q[r], thr.fdelta));
+          else if (Eval<M>::kHasAbsForm && (u & 2) == 0) count_abs_lt(cnt[r], Eval<M>::dist(q[r], x[u]), hyp_thr<M>(q[r], thr.fdelta));
           else count_sign(cnt[r], Eval<M>::signed_(q[r], x[u], thr));
         }
       }
@@ -615,12 +622,12 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
   const int tid = threadIdx.x;
   const uint32_t hbase = blockIdx.x * (THREADS * R);
   float qf[R][Q];
-  uint32_t cnt[R];
+  uint32_t cnt[R], sgn[R];     // sgn: the sign-counted half of the mixed form
   unsigned long long out[R];   // kShifted models: outliers in the high word (count_carry)
 #pragma unroll
   for (int r = 0; r < R; r++) {
     load_hyp32<Q>(hyp, hld, hbase + r * THREADS + tid, H, qf[r]);
-    cnt[r] = 0;
+    cnt[r] = 0; sgn[r] = 0;
     out[r] = 0ull;
   }
   const uint32_t negk = 0u - __float_as_uint(2.0f * delta);   // 2^32 - bits(2 delta)
@@ -631,7 +638,8 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
   const int g0 = (int)(p0 / (2 * PPI)), g1 = (int)(p1 / (2 * PPI));
   // raw-sum counting (count_abs_lt4_raw) holds 9 bits: the host keeps sub <= kCbRawMaxSub points per CTA
   constexpr bool kCarry = Eval<M>::kShifted;
-  constexpr bool kRaw = Eval<M>::kHasAbsForm && PPI >= 2 && !kCarry;
+  constexpr bool kRaw = Eval<M>::kHasAbsForm && !kCarry;
+  static_assert(!kRaw || PPI % 4 == 0, "the mixed count alternates in groups of four point pairs");
   // points of group g (2*PPI points) from the constant bank: uniform loads, the values live in uniform registers
   auto load_group = [&](f2 (&x)[PPI][D], int g) {
 #pragma unroll
@@ -659,9 +667,16 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
 #pragma unroll
         for (int u = 0; u < PPI; u++) count_carry(out[r], Eval<M>::dist(q, x[u]), nk);
       } else if constexpr (kRaw) {
+        // kMixed: of every four point pairs two are tested as |s| < delta (2 FFMA2 + 3 ALU instructions per pair: ALU-bound on
+        // its own) and two through the sign of s^2 - delta^2 (3 FFMA2 + 2 ALU: FMA-bound on its own); together 5 + 5 pipe slots
+        // per two pairs instead of 4 + 6
         const float th = hyp_thr<M>(qf[r], thr.fdelta);
 #pragma unroll
-        for (int u = 0; u < PPI; u += 2) count_abs_lt4_raw(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), th);
+        for (int u = 0; u < PPI; u += 4) {
+          count_abs_lt4_raw(cnt[r], Eval<M>::dist(q, x[u]), Eval<M>::dist(q, x[u + 1]), th);
+          count_sign(sgn[r], Eval<M>::signed_(q, x[u + 2], thr));
+          count_sign(sgn[r], Eval<M>::signed_(q, x[u + 3], thr));
+        }
       } else {
 #pragma unroll
         for (int u = 0; u < PPI; u++) count_sign(cnt[r], Eval<M>::signed_(q, x[u], thr));
@@ -679,7 +694,7 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
     const uint32_t h = hbase + r * THREADS + tid;
     // NaN padding counts as outliers; delta = 0 (bits(2 delta) = 0: no carry ever) admits nothing, like |s| < 0
     if constexpr (kCarry) cnt[r] = hyp_negk<M>(qf[r], negk) ? (uint32_t)(g1 - g0) * (2u * PPI) - (uint32_t)(out[r] >> 32) : 0u;
-    if constexpr (kRaw) cnt[r] = cb_raw_decode(cnt[r]);
+    if constexpr (kRaw) cnt[r] = cb_raw_decode(cnt[r]) + sgn[r];
     if (h < H && cnt[r]) atomicAdd(&counts[h], cnt[r]);
   }
 }
@@ -708,7 +723,8 @@ constexpr int cb_blocking(int m, bool want_r) {
   int r = 8, ppi = 2;
   switch (m) {
     case PLANE3: r = LSQR_CB_R_PLANE; ppi = LSQR_CB_PPI_PLANE; break;
-    case LINE2D: case LINE2: case PLANE2: r = 16; ppi = 4; break;
+    case LINE2D: case LINE2: r = 14; ppi = 4; break;   // two counters per hypothesis (mixed count): 16 would spill
+    case PLANE2: r = 16; ppi = 4; break;
     case LINE3: r = 8; ppi = 2; break;
     case CIRCLE2: r = 12; ppi = 2; break;
     case SPHERE3: r = 10; ppi = 2; break;
@@ -748,7 +764,7 @@ static int run_consensus_cb(const DataView& dv, const float* hyp, size_t hld, ui
   const uint32_t hyp_blocks = (H + THREADS * R - 1) / (THREADS * R);
   const uint32_t slots = (uint32_t)num_sms * (uint32_t)occ[dev & 15];
   // sub-chunks per launch: fill the last wave (the launches of one request serialise on the bank)
-  constexpr bool kRaw = Eval<M>::kHasAbsForm && PPI >= 2 && !Eval<M>::kShifted;
+  constexpr bool kRaw = Eval<M>::kHasAbsForm && !Eval<M>::kShifted;
   auto pick_sub = [&](uint32_t npts) {
     uint32_t best_sub = kRaw ? std::min(npts, kCbRawMaxSub) : npts; double best_eff = 0.0;
     for (uint32_t nsub = 1; nsub <= 64; nsub++) {
@@ -788,7 +804,7 @@ constexpr int block32_r(int m) {
     default: { const int q = model_info(m).Q32; return q <= 8 ? 6 : (q <= 10 ? 5 : (q <= 12 ? 4 : 3)); }
   }
 }
-template <int M> struct Block32 { static constexpr int R = block32_r(M), PPI = (M == ABSOR || M == RAY || M == PIVOT || M == USXW || M == USCP) ? 1 : 2; };
+template <int M> struct Block32 { static constexpr int R = block32_r(M), PPI = (M == ABSOR || M == RAY || M == PIVOT || M == USXW || M == USCP) ? 1 : ((M == LINE2D || M == LINE2) ? 4 : 2); };
 
 int launch_consensus32(int model, const DataView& dv, const float* hyp32, size_t hld, uint32_t H, const EstCfg& cfg, uint32_t* counts, int num_sms,
                        cudaStream_t s) {

@@ -88,6 +88,7 @@ struct EstCfg {
   double delta;      // SphereParametersEstimator.h / PivotCalibrationParametersEstimator.h: compared against a distance
   double delta2;     // delta*delta, e.g. PlaneParametersEstimator.hxx:17 -- compared against a squared distance
   double cross_eps;  // RayIntersectionParametersEstimator.cxx:14-15: sin(minimalAngularDeviation)^2
+  unsigned long long delta2_bits;   // bit pattern of delta2, 0 when delta2 is NaN (below_delta2)
 };
 
 constexpr double kEps = 2.220446049250313e-016;      // common/Epsilon.h:19
@@ -569,35 +570,38 @@ template <> __device__ __forceinline__ void prepare<USCP>(const double* prm, dou
 
 template <int M> __device__ __forceinline__ bool agree(const double* hq, const double* x, const EstCfg& cfg);
 
+// `v < deltaSquared` for a v that is a square or a sum of squares (v >= +0, +inf or NaN), decided on the integer ALU:
+// non-negative doubles order like their bit patterns, a NaN (either sign) has a larger pattern than any finite or infinite
+// threshold, and a NaN threshold (delta2_bits = 0) admits nothing -- the same truth table as the reference's double compare,
+// without a DSETP on the FP64 pipe, which is the pipe that bounds the validation kernel (11 -> 9 FP64 instructions per plane
+// evaluation together with the leading `0 +` of the reference's accumulation loops, which cannot change a square: the only
+// value it alters is the sign of a zero).
+__device__ __forceinline__ bool below_delta2(double v, const EstCfg& cfg) { return (unsigned long long)__double_as_longlong(v) < cfg.delta2_bits; }
+
 // PlaneParametersEstimator.hxx:196-203
-template <> __device__ __forceinline__ bool agree<PLANE3>(const double* h, const double* x, const EstCfg& cfg) {
-  double sd = 0;
-#pragma unroll
-  for (int i = 0; i < 3; i++) sd += h[i] * (x[i] - h[3 + i]);
-  return (sd * sd) < cfg.delta2;
-}
 template <int DIM> __device__ __forceinline__ bool agree_plane_nd(const double* h, const double* x, const EstCfg& cfg) {
-  double sd = 0;
+  double sd = h[0] * (x[0] - h[DIM]);
 #pragma unroll
-  for (int i = 0; i < DIM; i++) sd += h[i] * (x[i] - h[DIM + i]);
-  return (sd * sd) < cfg.delta2;
+  for (int i = 1; i < DIM; i++) sd += h[i] * (x[i] - h[DIM + i]);
+  return below_delta2(sd * sd, cfg);
 }
+template <> __device__ __forceinline__ bool agree<PLANE3>(const double* h, const double* x, const EstCfg& cfg) { return agree_plane_nd<3>(h, x, cfg); }
 #define LSQR_DEF_(ID, DIM) template <> __device__ __forceinline__ bool agree<ID>(const double* h, const double* x, const EstCfg& c) { return agree_plane_nd<DIM>(h, x, c); }
 LSQR_PLANE_ND_LIST(LSQR_DEF_)
 #undef LSQR_DEF_
 // Line2DParametersEstimator.cxx:119-123
 template <> __device__ __forceinline__ bool agree<LINE2D>(const double* h, const double* x, const EstCfg& cfg) {
   const double sd = h[0] * (x[0] - h[2]) + h[1] * (x[1] - h[3]);
-  return (sd * sd) < cfg.delta2;
+  return below_delta2(sd * sd, cfg);
 }
 // LineParametersEstimator.hxx:135-150
 template <int DIM> __device__ __forceinline__ bool agree_line(const double* h, const double* x, const EstCfg& cfg) {
-  double v[DIM], v_dot_n = 0.0, ds = 0.0;
+  double v[DIM], v_dot_n, ds;
 #pragma unroll
-  for (int i = 0; i < DIM; i++) { v[i] = x[i] - h[DIM + i]; v_dot_n += v[i] * h[i]; }
+  for (int i = 0; i < DIM; i++) { v[i] = x[i] - h[DIM + i]; v_dot_n = i ? v_dot_n + v[i] * h[i] : v[i] * h[i]; }
 #pragma unroll
-  for (int i = 0; i < DIM; i++) ds += (v[i] - v_dot_n * h[i]) * (v[i] - v_dot_n * h[i]);
-  return ds < cfg.delta2;
+  for (int i = 0; i < DIM; i++) { const double w = v[i] - v_dot_n * h[i]; ds = i ? ds + w * w : w * w; }
+  return below_delta2(ds, cfg);
 }
 #define LSQR_DEF_(ID, DIM) template <> __device__ __forceinline__ bool agree<ID>(const double* h, const double* x, const EstCfg& c) { return agree_line<DIM>(h, x, c); }
 LSQR_LINE_ND_LIST(LSQR_DEF_)
@@ -635,7 +639,7 @@ template <> __device__ __forceinline__ bool agree<ABSOR>(const double* h, const 
   const double qy = h[3] * x[0] + h[4] * x[1] + h[5] * x[2] + h[10];
   const double qz = h[6] * x[0] + h[7] * x[1] + h[8] * x[2] + h[11];
   const double dx = qx - x[3], dy = qy - x[4], dz = qz - x[5];
-  return (dx * dx + dy * dy + dz * dz) < cfg.delta2;
+  return below_delta2(dx * dx + dy * dy + dz * dz, cfg);
 }
 // RayIntersectionParametersEstimator.cxx:164-179
 template <> __device__ __forceinline__ bool agree<RAY>(const double* h, const double* x, const EstCfg& cfg) {
@@ -644,7 +648,7 @@ template <> __device__ __forceinline__ bool agree<RAY>(const double* h, const do
   const double dx = h[0] - p[0] - t * n[0];
   const double dy = h[1] - p[1] - t * n[1];
   const double dz = h[2] - p[2] - t * n[2];
-  return t >= 0 && (dx * dx + dy * dy + dz * dz < cfg.delta2);
+  return t >= 0 && below_delta2(dx * dx + dy * dy + dz * dz, cfg);
 }
 // PivotCalibrationParametersEstimator.cxx:108-123 (Frame::apply then Vector::l2Norm, common/Vector.h:134-139)
 template <> __device__ __forceinline__ bool agree<PIVOT>(const double* h, const double* x, const EstCfg& cfg) {
@@ -672,7 +676,7 @@ template <> __device__ __forceinline__ bool agree<USXW>(const double* h, const d
     err[i] = (M0 * u + M1 * v + M3) - h[9 + i];
   }
   s = err[0] * err[0] + err[1] * err[1] + err[2] * err[2];
-  return s < cfg.delta2;
+  return below_delta2(s, cfg);
 }
 
 // SinglePointTargetUSCalibrationParametersEstimator.cxx:726-761: the same product, compared with the measured pointer tip
@@ -688,7 +692,7 @@ template <> __device__ __forceinline__ bool agree<USCP>(const double* h, const d
     err[i] = (M0 * u + M1 * v + M3) - x[14 + i];
   }
   const double s = err[0] * err[0] + err[1] * err[1] + err[2] * err[2];
-  return s < cfg.delta2;
+  return below_delta2(s, cfg);
 }
 
 // DenseLinearEquationSystemParametersEstimator.hxx:111-119

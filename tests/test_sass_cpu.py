@@ -76,7 +76,7 @@ def test_shared_memory_kernel_is_fed_by_tma(sass):
     assert any("SYNCS" in i for i in ins), "mbarrier wait"
 
 
-@pytest.mark.parametrize("model", range(15))
+@pytest.mark.parametrize("model", range(34))
 def test_constant_bank_kernels_read_their_points_through_uniform_registers(sass, model):
     """Every consensus_cb_kernel<M>: the points of the launch come out of the constant bank with LDCU (uniform registers) and
     never with an indexed LDC into ordinary registers -- ptxas falls back to that when a loaded pair has too few consumers in
@@ -86,4 +86,15 @@ def test_constant_bank_kernels_read_their_points_through_uniform_registers(sass,
     assert not [i for i in ins if re.match(r"LDC(\.\d+)? R\d+, c\[0x3\]", i)], "indexed constant loads of the data"
     assert sum(i.startswith("LDCU.64") or i.startswith("LDCU.128") for i in ins) >= 4
     packed = [i for i in ins if i.startswith(("FFMA2", "FADD2", "FMUL2"))]
-    assert sum("UR" in i for i in packed) >= len(packed) // 2, "most packed operations take their datum from a uniform register"
+    # (the literal kD-line form of d >= 4 touches the datum in one of its four operations per component, everything else in two or more)
+    assert sum("UR" in i for i in packed) >= len(packed) // (5 if 24 <= model <= 28 else 2), "packed operations take their datum from a uniform register"
+
+
+def test_fp64_validation_kernel_compares_on_the_integer_alu(sass):
+    """consensus_kernel<Exact<PLANE3>, 4, 128, 256>: nine FP64-pipe instructions per evaluation (5 DADD + 4 DMUL as the reference
+    writes them, minus the leading `0 +`), the threshold test as a 64-bit integer compare (ISETP + ISETP.EX) -- no DSETP."""
+    ins = _one(sass, r"consensus_kernelINS_5ExactILi0EEELi4ELi128ELi256E")
+    assert not [i for i in ins if i.startswith("DSETP")], "the squared-distance compare must not occupy the FP64 pipe"
+    assert sum(i.startswith("DADD") for i in ins) == 40 and sum(i.startswith("DMUL") for i in ins) == 32   # 8 evaluations per iteration
+    assert not [i for i in ins if i.startswith("DFMA")], "validation mode must not contract (the reference is built without FMA)"
+    assert sum(".EX" in i and i.startswith("ISETP") for i in ins) >= 8
