@@ -9,7 +9,8 @@
 
 namespace lsqr {
 
-constexpr int kTilePad = 1024;   // leading dimension of the SoA point arrays is a multiple of this
+constexpr int kTilePad = 2048;   // leading dimension of the SoA point arrays is a multiple of this: the largest tile any kernel fetches with one bulk copy per row
+                                 // (mask_moments_kernel: 2048 data; with 1024 the last tile of the last row read past the allocation -- found by memcheck)
 constexpr int kMaxDim = 20;           // doubles per datum, upper bound (calibrated-pointer US calibration: 17)
 constexpr int kLmStateDoubles = 256;  // device scratch reserved for the Levenberg-Marquardt controller state
 constexpr int kMaxMoments = 96;  // upper bound on the doubles accumulated per thread by the refine reductions (cross-wire US calibration: 91)

@@ -62,6 +62,7 @@ template <int M, bool LM> struct MMCfg {
   static constexpr int THREADS = NM > 40 ? 256 : LSQR_MM_THREADS;
   static constexpr int kTileCap = LSQR_MM_TILE_KB * 1024 + 8192;
   static constexpr int TILE = (D * 2048 * 8 <= kTileCap) ? 2048 : (D * 1024 * 8 <= kTileCap) ? 1024 : ((D * 512 * 8 <= kTileCap) ? 512 : 256);
+  static_assert(kTilePad % TILE == 0, "a tile must never straddle the end of a row (rows are kTilePad-padded)");
   static constexpr int PPT = (TILE + THREADS - 1) / THREADS;                 // data per thread per tile
   static constexpr int TILE_BYTES = D * TILE * 8;
   static constexpr int kFit = LSQR_MM_SMEM_KB * 1024 / TILE_BYTES;

@@ -61,6 +61,7 @@ class Oracle:
         f("agree", ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_double, _dp, ctypes.c_int, _dp, ctypes.c_size_t, _u8p])
         f("score_subsets", ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_double, _dp, ctypes.c_size_t, _i32p, ctypes.c_size_t, _u32p, _dp, ctypes.c_int])
         f("num_threads", ctypes.c_int, [])
+        f("model_info", ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)])
         f("weighted_absor", ctypes.c_int, [_dp, ctypes.c_size_t, _dp, _dp])
         if kind == "port":
             f("ransac_exhaustive", ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, _dp, ctypes.c_size_t, _dp, _u8p, _dp, _u32p, ctypes.POINTER(ctypes.c_uint64)])
@@ -70,6 +71,13 @@ class Oracle:
             f("last_lm", None, [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)])
         else:
             f("ransac", ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, _dp, ctypes.c_size_t, ctypes.c_int, ctypes.c_double, _dp, _u8p, _dp])
+
+    def model_info(self, model):
+        """(D, P, k) as the C side has them, or None for an unknown id."""
+        d, p, k = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        if self._model_info(model, ctypes.byref(d), ctypes.byref(p), ctypes.byref(k)) != 0:
+            return None
+        return d.value, p.value, k.value
 
     def _fn(self, name, res, args):
         fn = getattr(self.lib, self.pfx + name)

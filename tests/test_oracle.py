@@ -160,3 +160,13 @@ def test_choose_unrank_and_stop_rule(port):
     # log(1-0.999)/log(1-0.6^3) = 28.4 -> 28
     assert port.num_tries(0.999, 60, 100, 3, 161700) == 28
     assert port.num_tries(0.999, 100, 100, 3, 161700) == 0
+
+
+def test_model_tables_agree_everywhere(port, ref):
+    """One id space: the Python tables of the oracle and of the engine binding, the C restatement and the reference harness
+    describe every model with the same (doubles per datum, parameters, minimal subset)."""
+    from lsqrrecipes_b200 import api
+    assert MODELS == api.MODELS and len(MODELS) == 34
+    for name, m in MODELS.items():
+        assert INFO[m] == api.MODEL_INFO[m] == port.model_info(m) == ref.model_info(m), name
+    assert port.model_info(34) is None and ref.model_info(34) is None and port.model_info(-1) is None

@@ -531,6 +531,25 @@ def test_batched_small_problems_vs_oracle(port, name):
     eng.close()
 
 
+def test_batched_problems_cross_copy_pieces_and_launches(port):
+    """lsqr_ransac_batch uploads in pieces (4 MB from pageable memory) and launches per ~32 MB of problems: 100 000 copies of one
+    16-point problem (38 MB) in exhaustive mode must all return the oracle's answer for that problem, whichever piece and launch
+    they travelled in; the same from page-locked memory (16 MB pieces)."""
+    import torch
+    per, nprob = 16, 100_000
+    one, _ = synth.GENERATORS["plane3"](per, seed=9)
+    prm, mask, frac, cnt, rank = port.ransac_exhaustive(MODELS["plane3"], 0.5, one, ls_type=1)
+    data = np.tile(one, (nprob, 1))
+    offsets = (np.arange(nprob + 1) * per).astype(np.uint64)
+    eng = Engine("plane3", 0.5)
+    for src in (data, torch.from_numpy(data).pin_memory().numpy()):
+        out = eng.ransac_batch(src, offsets, exhaustive=True, want_masks=True)
+        assert np.all(out["counts"] == cnt)
+        assert np.array_equal(out["masks"].reshape(nprob, per), np.tile(mask, (nprob, 1)))
+        assert np.all(np.abs(out["params"] - out["params"][0]) == 0) and same_up_to_sign(out["params"][0], prm, SIGN_IDX["plane3"], REFINE_TOL)
+    eng.close()
+
+
 def test_python_operator_interface_mirrors_reference():
     """Reads like examples/planeEstimation.cxx:112-118."""
     from lsqrrecipes_b200 import PlaneParametersEstimator, RANSAC
