@@ -24,7 +24,8 @@
 //       - vector residuals (lines of 3 and more dimensions, absolute orientation, ray, pivot, ultrasound): the FMA chain starts
 //         at -delta^2, so the SIGN BIT of the sum is the decision and LEA.HI adds it (count_sign).
 //     Both kernels evaluate the same predicate per model, so their counts are bit-identical (tested).
-// Tensor cores are deliberately unused: contraction depth <= 4 (BASELINE.json north_star).
+// Tensor cores are deliberately unused: contraction depth <= 8 (BASELINE.json north_star: <= 4 for its estimators), and
+// TF32 / bf16 operands would destroy a residual of 0.5 on coordinates of 1000.
 #include "engine.h"
 
 #include <mutex>

@@ -3,6 +3,7 @@
 #   check      GPU parity tests, smoke, the bench line, single-launch refine timings per estimator      (one GPU)
 #   evidence   ncu --set full captures of the shipped kernels at the bench configuration + launch list  (one GPU)
 #   sanitize   compute-sanitizer memcheck over every model and entry point (tools/sanitize_smoke.py)     (one GPU)
+#   racecheck  compute-sanitizer racecheck over a subset of the models (shared-memory hazards)             (one GPU)
 #   multi N    multi-GPU tests, reference arm and bench under torchrun, compute() on the group, C++ demo (gpurun --gpus N)
 # Everything lands in gpurun_out/<tag>/ (text only: ncu reports are summarised on the box, gpurun carries back <= 64 MiB).
 set -u
@@ -40,6 +41,10 @@ evidence)
 sanitize)
   timeout 1700 compute-sanitizer --tool memcheck --error-exitcode 7 python tools/sanitize_smoke.py --big > $OUT/memcheck.log 2>&1
   echo "memcheck rc=$?"; tail -8 $OUT/memcheck.log
+  ;;
+racecheck)
+  SMOKE_MODELS="plane3 sphere3 line2d absor uscp sphere8 dense5" timeout 1700 compute-sanitizer --tool racecheck --error-exitcode 7 python tools/sanitize_smoke.py > $OUT/racecheck.log 2>&1
+  echo "racecheck rc=$?"; grep -c "hazard" $OUT/racecheck.log; tail -5 $OUT/racecheck.log
   ;;
 multi)
   echo "== pytest multi gpu" | tee $OUT/pytest.log

@@ -10,7 +10,10 @@ sys.path.insert(0, ROOT)
 from lsqrrecipes_b200 import FP32, FP64, SAMPLE_EXHAUSTIVE, Engine, MODELS, synth  # noqa: E402
 
 big = "--big" in sys.argv
+only = os.environ.get("SMOKE_MODELS", "").split()          # e.g. SMOKE_MODELS="plane3 sphere3" for the slower racecheck
 for name in MODELS:
+    if only and name not in only:
+        continue
     n = 3000
     data, true = synth.GENERATORS[name](n, seed=5)
     for ls in ([0, 1] if (name.startswith(("circle", "sphere")) or name in ("usxw", "uscp")) else [1]):
