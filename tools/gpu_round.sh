@@ -42,6 +42,14 @@ sanitize)
   timeout 1700 compute-sanitizer --tool memcheck --error-exitcode 7 python tools/sanitize_smoke.py --big > $OUT/memcheck.log 2>&1
   echo "memcheck rc=$?"; tail -8 $OUT/memcheck.log
   ;;
+profile_cb)   # ncu --set full of the constant-bank kernel for the models named in $CB_MODELS (default: the ones furthest from the pipe)
+  for mdl in ${CB_MODELS:-uscp usxw ray circle2}; do
+    timeout 300 ncu --set full --clock-control none --import-source on -k regex:consensus_cb -s 3 -c 1 -o $OUT/cb_$mdl python tools/tune_cb.py $mdl 1000000 262144 > $OUT/ncu_cb_$mdl.log 2>&1; echo "$mdl rc=$?"
+    python tools/ncu_summary.py $OUT/cb_$mdl.ncu-rep > $OUT/cb_$mdl.txt 2>&1
+    ncu -i $OUT/cb_$mdl.ncu-rep --page source --csv 2>/dev/null | head -400 > $OUT/cb_${mdl}_source.csv
+    rm -f $OUT/cb_$mdl.ncu-rep
+  done
+  ;;
 racecheck)
   SMOKE_MODELS="plane3 sphere3 line2d absor uscp sphere8 dense5" timeout 1700 compute-sanitizer --tool racecheck --error-exitcode 7 python tools/sanitize_smoke.py > $OUT/racecheck.log 2>&1
   echo "racecheck rc=$?"; grep -c "hazard" $OUT/racecheck.log; tail -5 $OUT/racecheck.log
