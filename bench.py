@@ -197,6 +197,39 @@ def reference_compute_ms(model, data, delta, prob=0.999, budget_s=60.0):
                     "the number of tries is time-seeded (RANSAC.hxx:44)"}
 
 
+def reference_compute_configs(budget_s=45.0):
+    """SURVEY.md 8d, CPU baseline (i): the reference's own RANSAC<T,S>::compute, one thread as shipped, on BASELINE.json
+    configs[2..4] -- sphere + Levenberg-Marquardt, absolute orientation, and a host loop over small problems (the reference's
+    analogue of the batched mode) -- with N reduced where the full size would not fit the time box, stated per entry."""
+    from lsqrrecipes_b200 import synth
+    pyoracle, orc, kind = _oracle()
+    if kind != "ref":
+        return None
+    out, t_all = [], time.perf_counter()
+
+    def one(name, n, what):
+        data, _ = synth.GENERATORS[name](n)
+        t0 = time.perf_counter()
+        prm, mask, frac = orc.ransac_random(pyoracle.MODELS[name], synth.DELTAS[name], data, 0.999)
+        return {"config": what, "model": name, "points": n, "ms": 1e3 * (time.perf_counter() - t0), "inlier_fraction": float(frac), "n_params": int(len(prm)), "threads": 1}
+
+    out.append(one("sphere3", 1_000_000, "configs[2] sphere3 + Levenberg-Marquardt, N reduced from 10 M to 1 M points"))
+    if time.perf_counter() - t_all < budget_s:
+        out.append(one("absor", 1_000_000, "configs[3] absolute orientation, 1M correspondences"))
+    for name in ("line2d", "plane3"):
+        if time.perf_counter() - t_all > budget_s:
+            break
+        nprob, npts = 256, 256
+        probs = [synth.GENERATORS[name](npts, seed=300 + i)[0] for i in range(64)]
+        t0 = time.perf_counter()
+        for i in range(nprob):
+            orc.ransac_random(pyoracle.MODELS[name], synth.DELTAS[name], probs[i % 64], 0.999)
+        dt = time.perf_counter() - t0
+        out.append({"config": f"configs[4] host loop of RANSAC::compute over {nprob} of the 65536 x 256-point {name} problems", "model": name, "problems": nprob,
+                    "points_per_problem": npts, "ms_per_problem": 1e3 * dt / nprob, "problems_per_s": nprob / dt, "threads": 1})
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -216,6 +249,7 @@ def run_reference_arm(args):
     total = time.perf_counter() - t_all
     value = info["evals"] * args.steps / sum(times)
     comp = None if args.no_e2e else reference_compute_ms(args.model, data, delta)
+    comp_configs = None if (args.no_e2e or args.no_configs) else reference_compute_configs()
     line = {
         "impl": "reference", "metric": "hypothesis x point agree() evals/sec", "value": value, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
@@ -225,7 +259,7 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": info["cores"], "kind": info["kind"],
                          "sample": f"{n_hyps} hypotheses x {args.points} points per step, estimate()+agree() loop of RANSAC.hxx:217-249, OpenMP over hypotheses"},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "compute_e2e": comp,
+        "compute_e2e": comp, "configs": comp_configs,
         "gpu_launches": 0, "wall_s": total,
     }
     emit_line(line)
