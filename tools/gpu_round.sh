@@ -50,6 +50,9 @@ profile_cb)   # ncu --set full of the constant-bank kernel for the models named 
     rm -f $OUT/cb_$mdl.ncu-rep
   done
   ;;
+sweep_cb)     # times the blocking variants of tools/build_variants.sh against the shipped library, per model in $CB_MODELS
+  for mdl in ${CB_MODELS:-uscp usxw ray circle2 sphere3}; do timeout 300 python tools/tune_cb.py $mdl 1000000 262144 2>&1 | grep "T evals" | tee -a $OUT/sweep_cb.txt; done
+  ;;
 racecheck)
   SMOKE_MODELS="plane3 sphere3 line2d absor uscp sphere8 dense5" timeout 1700 compute-sanitizer --tool racecheck --error-exitcode 7 python tools/sanitize_smoke.py > $OUT/racecheck.log 2>&1
   echo "racecheck rc=$?"; grep -c "hazard" $OUT/racecheck.log; tail -5 $OUT/racecheck.log

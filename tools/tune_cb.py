@@ -13,7 +13,7 @@ from lsqrrecipes_b200 import api  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else "plane3"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 H = int(sys.argv[3]) if len(sys.argv) > 3 else 1_000_000
-libs = sorted(glob.glob(os.path.join(ROOT, "tools/bin/variants/lib_*.so"))) + [api.lib_path()]
+libs = sorted(glob.glob(os.path.join(ROOT, f"tools/bin/variants/lib_m{api.MODELS[name]}_*.so"))) + [api.lib_path()]   # tools/build_variants.sh "<id> <R> <PPI>"
 pid = os.fork() if False else None
 for lib in libs:
     # one subprocess per variant: ctypes cannot unload a library
