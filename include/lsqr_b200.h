@@ -229,10 +229,12 @@ int lsqr_ransac_exhaustive(lsqr_ctx* ctx, int precision, uint8_t* out_mask_bytes
  * back; `offsets` [n_problems+1] in records.  exhaustive != 0 enumerates all C(n,k) subsets
  * of each problem (RANSAC.hxx:150-249); otherwise rounds of Philox hypotheses with the stop
  * rule of RANSAC.hxx:107-110 for `prob` (prob <= 0: exactly max_tries hypotheses), capped at
- * max_tries.  Outputs per problem: params [n_problems][P] (NaN row = empty), counts
+ * max_tries, scored in `precision` (LSQR_FP32: the fast forms on an fp32 copy of the points relative to the problem's
+ * first point; exhaustive mode always scores in fp64).  Minimal solves, the winner's consensus set, its count and the
+ * refine are fp64 in every mode.  Outputs per problem: params [n_problems][P] (NaN row = empty), counts
  * [n_problems], optional masks (bytes, same indexing as data). */
 int lsqr_ransac_batch(lsqr_ctx* ctx, const double* data, const uint64_t* offsets, uint64_t n_problems,
-                      int exhaustive, double prob, uint32_t max_tries, uint64_t seed,
+                      int exhaustive, double prob, uint32_t max_tries, uint64_t seed, int precision,
                       double* out_params, uint32_t* out_counts, uint8_t* out_masks, double* device_ms);
 
 /* ---- the estimator's own methods, for callers that use them directly ---------------- */

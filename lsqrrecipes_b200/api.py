@@ -102,7 +102,7 @@ def load_library():
         "lsqr_ransac": (c.c_int, [c.c_void_p, c.c_double, c.c_int, c.c_uint64, _u8p, c.POINTER(ComputeResult)]),
         "lsqr_ransac_exhaustive": (c.c_int, [c.c_void_p, c.c_int, _u8p, c.POINTER(ComputeResult)]),
         "lsqr_compute": (c.c_int, [c.c_void_p, c.c_void_p, c.c_size_t, c.c_size_t, c.c_double, c.c_int, c.c_uint64, _u8p, c.POINTER(ComputeResult)]),
-        "lsqr_ransac_batch": (c.c_int, [c.c_void_p, _dp, _u64p, c.c_uint64, c.c_int, c.c_double, c.c_uint32, c.c_uint64, _dp, _u32p, _u8p, _dp]),
+        "lsqr_ransac_batch": (c.c_int, [c.c_void_p, _dp, _u64p, c.c_uint64, c.c_int, c.c_double, c.c_uint32, c.c_uint64, c.c_int, _dp, _u32p, _u8p, _dp]),
         "lsqr_estimate": (c.c_int, [c.c_void_p, _dp, c.c_size_t, _dp, c.POINTER(c.c_int)]),
         "lsqr_agree": (c.c_int, [c.c_void_p, _dp, _dp, c.c_size_t, _u8p]),
         "lsqr_least_squares": (c.c_int, [c.c_void_p, _dp, c.c_size_t, _dp, c.POINTER(c.c_int)]),
@@ -306,7 +306,7 @@ class Engine:
         self._ck(self.lib.lsqr_ransac_exhaustive(self.h, precision, _ptr(mask, _u8p), ctypes.byref(r)))
         return self._result(r, mask)
 
-    def ransac_batch(self, data, offsets, exhaustive=False, prob=0.999, max_tries=1024, seed=0, want_masks=False):
+    def ransac_batch(self, data, offsets, exhaustive=False, prob=0.999, max_tries=1024, seed=0, want_masks=False, precision=FP64):
         d = np.ascontiguousarray(data, dtype=np.float64).reshape(-1, self.dim)
         off = np.ascontiguousarray(offsets, dtype=np.uint64)
         nprob = len(off) - 1
@@ -315,7 +315,7 @@ class Engine:
         masks = np.zeros(d.shape[0], dtype=np.uint8) if want_masks else None
         ms = ctypes.c_double(0)
         self._ck(self.lib.lsqr_ransac_batch(self.h, _ptr(d, _dp), _ptr(off, _u64p), nprob, 1 if exhaustive else 0, float(prob),
-                                            int(max_tries), seed, _ptr(prm, _dp), _ptr(cnt, _u32p), _ptr(masks, _u8p), ctypes.byref(ms)))
+                                            int(max_tries), seed, int(precision), _ptr(prm, _dp), _ptr(cnt, _u32p), _ptr(masks, _u8p), ctypes.byref(ms)))
         return {"params": prm, "counts": cnt, "masks": masks, "device_ms": ms.value}
 
     # -- the estimator's own methods ---------------------------------------------------

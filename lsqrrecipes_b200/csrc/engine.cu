@@ -980,7 +980,7 @@ int compute_impl(lsqr_ctx* ctx, const void* aos, size_t n, size_t stride, double
 
 // problems [p0, p1) of a batch (offsets are absolute record offsets into `data`)
 int batch_impl(lsqr_ctx* ctx, const double* data, const uint64_t* offsets, uint64_t p0, uint64_t p1, int exhaustive, double prob, uint32_t max_tries,
-               uint64_t seed, double* out_params, uint32_t* out_counts, uint8_t* out_masks, double* device_ms) {
+               uint64_t seed, int precision, double* out_params, uint32_t* out_counts, uint8_t* out_masks, double* device_ms) {
   if (ctx->model < 0) return fail(ctx, LSQR_ERR_STATE, "lsqr_set_estimator must be called first");
   if (device_ms) *device_ms = 0.0;
   if (p1 <= p0) return LSQR_OK;
@@ -994,7 +994,8 @@ int batch_impl(lsqr_ctx* ctx, const double* data, const uint64_t* offsets, uint6
     if (offsets[b + 1] < offsets[b]) return fail(ctx, LSQR_ERR_ARG, "offsets must be non-decreasing");
     max_n = std::max<uint64_t>(max_n, offsets[b + 1] - offsets[b]);
   }
-  if ((size_t)max_n * mi.D * sizeof(double) > 200 * 1024) return fail(ctx, LSQR_ERR_ARG, "a problem does not fit in shared memory; use lsqr_ransac for large problems");
+  const bool use32 = precision == LSQR_FP32 && !exhaustive;   // fp32 scoring keeps an fp32 copy of the points next to the fp64 one
+  if ((size_t)max_n * mi.D * (sizeof(double) + (use32 ? sizeof(float) : 0)) + 16 > 200 * 1024) return fail(ctx, LSQR_ERR_ARG, "a problem does not fit in shared memory; use lsqr_ransac for large problems");
   cudaStream_t s = ctx->stream;
   // persistent buffers (a cudaMalloc/cudaFree set per call cost more than the kernel)
   if (int rc = ensure(ctx, &ctx->bt_data, &ctx->bt_data_cap, (size_t)std::max<uint64_t>(total, 1) * mi.D)) return rc;
@@ -1053,7 +1054,7 @@ int batch_impl(lsqr_ctx* ctx, const double* data, const uint64_t* offsets, uint6
       CK(cudaStreamWaitEvent(s, landed, 0));
     }
     BatchArgs ba{};
-    ba.model = ctx->model; ba.exhaustive = exhaustive; ba.tries = max_tries; ba.prob = prob; ba.seed = seed;
+    ba.model = ctx->model; ba.exhaustive = exhaustive; ba.precision = use32 ? 1 : 0; ba.tries = max_tries; ba.prob = prob; ba.seed = seed;
     ba.data = ctx->bt_data + rec0 * mi.D; ba.offsets = ctx->bt_off + (q0 - p0); ba.n_problems = (uint32_t)(q1 - q0); ba.max_n = max_n;
     ba.base = offsets[q0]; ba.first_problem = q0;
     ba.out_params = ctx->bt_prm + (q0 - p0) * mi.P; ba.out_counts = ctx->bt_cnt + (q0 - p0); ba.out_masks = out_masks ? ctx->mask_dev + rec0 : nullptr;
@@ -1397,19 +1398,20 @@ int lsqr_ransac_exhaustive(lsqr_ctx* ctx, int precision, uint8_t* out_mask, lsqr
 }
 
 int lsqr_ransac_batch(lsqr_ctx* ctx, const double* data, const uint64_t* offsets, uint64_t n_problems, int exhaustive, double prob,
-                      uint32_t max_tries, uint64_t seed, double* out_params, uint32_t* out_counts, uint8_t* out_masks, double* device_ms) {
+                      uint32_t max_tries, uint64_t seed, int precision, double* out_params, uint32_t* out_counts, uint8_t* out_masks, double* device_ms) {
   if (!ctx || !data || !offsets || !out_params || !out_counts) return LSQR_ERR_ARG;
+  if (precision != LSQR_FP64 && precision != LSQR_FP32) return fail(ctx, LSQR_ERR_ARG, "bad precision");
   if (n_problems == 0) return LSQR_OK;
   if (ctx->group) {   // independent problems: partitioned across the GPUs, no collective
     const int W = ctx->world;
     std::vector<double> ms(W, 0.0);
     const int rc = group_run(ctx, [&](lsqr_ctx* k, int r) {
-      return batch_impl(k, data, offsets, n_problems * r / W, n_problems * (r + 1) / W, exhaustive, prob, max_tries, seed, out_params, out_counts, out_masks, &ms[r]);
+      return batch_impl(k, data, offsets, n_problems * r / W, n_problems * (r + 1) / W, exhaustive, prob, max_tries, seed, precision, out_params, out_counts, out_masks, &ms[r]);
     });
     if (device_ms) *device_ms = *std::max_element(ms.begin(), ms.end());
     return rc;
   }
-  return batch_impl(ctx, data, offsets, 0, n_problems, exhaustive, prob, max_tries, seed, out_params, out_counts, out_masks, device_ms);
+  return batch_impl(ctx, data, offsets, 0, n_problems, exhaustive, prob, max_tries, seed, precision, out_params, out_counts, out_masks, device_ms);
 }
 
 int lsqr_estimate(lsqr_ctx* ctx, const double* packed, size_t n, double* out_params, int* n_params) {

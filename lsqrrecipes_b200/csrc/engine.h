@@ -104,6 +104,7 @@ void launch_expand_mask(const uint32_t* bits, uint32_t first, uint32_t count, ui
 
 struct BatchArgs {
   int model, exhaustive;
+  int precision;             // randomized mode: 0 = fp64 scoring, 1 = fp32 scoring (exhaustive mode is always fp64)
   uint32_t tries;            // cap on hypotheses per problem (randomized mode)
   double prob;               // desiredProbabilityForNoOutliers for the stop rule; <= 0 disables it
   uint64_t seed;

@@ -1,5 +1,6 @@
 // Batched small problems (BASELINE.json configs[4]): one thread block per problem, see the comment above batch_kernel.
 #include "refine_common.cuh"
+#include "fast_forms.cuh"
 
 namespace lsqr {
 
@@ -7,9 +8,12 @@ namespace lsqr {
 // Batched small problems: one thread block per problem (BASELINE.json config 5; in the
 // reference this is a host loop of RANSAC<T,S>::compute calls).  Everything -- subset
 // generation, minimal solve, consensus, arg-max, consensus set, least-squares refine -- happens
-// inside the block with the problem's points resident in shared memory, in fp64 reference
-// arithmetic.  Exhaustive mode enumerates all C(n,k) subsets (RANSAC.hxx:150-249); otherwise
-// rounds of blockDim.x Philox hypotheses with the stop rule of RANSAC.hxx:107-110 between rounds.
+// inside the block with the problem's points resident in shared memory.  Exhaustive mode enumerates all C(n,k)
+// subsets (RANSAC.hxx:150-249) in fp64 reference arithmetic (bit-comparable with the reference's brute-force driver);
+// otherwise rounds of Philox hypotheses with the stop rule of RANSAC.hxx:107-110 between rounds, scored in fp64 or -- precision
+// LSQR_FP32, what the large-problem path does -- in the fp32 forms of fast_forms.cuh on an fp32 copy of the points relative to the
+// problem's first point, two data per packed operation.  Minimal solves, the winner's consensus set, its count and the refine
+// are fp64 in every mode, so the returned mask / count / parameters are exact for the chosen hypothesis.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, unsigned long long* sh) {
 #pragma unroll
@@ -76,6 +80,21 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
   const uint64_t gb = a.first_problem + b;                    // global problem index: the sampler's counter does not depend on how problems are split over GPUs
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   for (uint32_t i = threadIdx.x; i < n * D; i += blockDim.x) pts[(i % D) * ldp + (i / D)] = a.data[off * D + i];
+  // fp32 scoring: the problem's points relative to its first point (centred components only), padded to an even count with NaN
+  const bool use32 = a.precision == 1 && !a.exhaustive;
+  const uint32_t ldf = (ldp + 1u) & ~1u;
+  float* ptsf = reinterpret_cast<float*>(pts + (size_t)D * ldp);   // [D][ldf]
+  __shared__ double sh_ctr[kMaxDim];
+  if (use32) {
+    __syncthreads();
+    if (threadIdx.x < (uint32_t)kMaxDim) sh_ctr[threadIdx.x] = (threadIdx.x < (uint32_t)D && n > 0 && centred_comp(M, (int)threadIdx.x)) ? pts[threadIdx.x * ldp] : 0.0;
+    __syncthreads();
+    const uint32_t npad = (n + 1u) & ~1u;
+    for (uint32_t i = threadIdx.x; i < npad * D; i += blockDim.x) {
+      const uint32_t d = i / npad, j = i % npad;
+      ptsf[d * ldf + j] = (j < n) ? (float)(pts[d * ldp + j] - sh_ctr[d]) : __int_as_float(0x7fc00000);
+    }
+  }
   if (threadIdx.x == 0) {
     sh_best = 0ull;
     unsigned long long all = 0xFFFFFFFFull;  // RANSAC::choose saturates at UINT_MAX (RANSAC.hxx:254-280)
@@ -104,7 +123,34 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
         for (int d = 0; d < D; d++) sp[j * D + d] = pts[d * ldp + sub[j]];
       const bool ok = estimate<M>(sp, cfg, prm);   // the same for all G threads of a hypothesis
       uint32_t c = 0;
-      if (ok) {
+      if (ok && use32) {
+        if constexpr (M != USXW && M != USCP) {   // (the ultrasound calibrations have no batched mode)
+          constexpr int Q = Model<M>::Q32;
+          double ctr[kMaxDim];
+#pragma unroll
+          for (int d = 0; d < kMaxDim; d++) ctr[d] = sh_ctr[d];
+          float qf[Q];
+          hoist32<M>(prm, ctr, cfg, qf);
+          f2 q[Q];
+#pragma unroll
+          for (int j = 0; j < Q; j++) q[j] = splat(qf[j]);
+          Thr2 thr;
+          thr.delta = splat((float)cfg.delta); thr.neg_delta2 = splat(-(float)cfg.delta2); thr.fdelta = (float)cfg.delta;
+          const uint32_t negk = hyp_negk<M>(qf, 0u - __float_as_uint(2.0f * (float)cfg.delta));   // 2^32 - bits(window)
+          unsigned long long out = 0ull;
+          uint32_t pairs = 0;
+          for (uint32_t i = 2 * sub_lane; i < n; i += 2 * G) {
+            f2 x[D];
+#pragma unroll
+            for (int d = 0; d < D; d++) x[d].v = *reinterpret_cast<const unsigned long long*>(ptsf + d * ldf + i);
+            if constexpr (Eval<M>::kShifted) count_carry(out, Eval<M>::dist(q, x), negk);
+            else if constexpr (Eval<M>::kHasAbsForm) count_abs_lt(c, Eval<M>::dist(q, x), hyp_thr<M>(qf, thr.fdelta));
+            else count_sign(c, Eval<M>::signed_(q, x, thr));
+            pairs++;
+          }
+          if constexpr (Eval<M>::kShifted) c = negk ? 2u * pairs - (uint32_t)(out >> 32) : 0u;   // outliers were counted (NaN padding among them)
+        }
+      } else if (ok) {
         prepare<M>(prm, hq);
         for (uint32_t i = sub_lane; i < n; i += G) {
           double x[D];
@@ -163,6 +209,7 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
 #pragma unroll
   for (int j = 0; j < HQ; j++) hq[j] = sh_prm[j];
   block_moments<M>(pts, n, ldp, hq, cfg, nullptr, false, 1, mask_out, sh_part, sh_mom);
+  if (use32 && threadIdx.x == 0) a.out_counts[b] = (uint32_t)sh_mom[0];   // the fp64 count of the winner's consensus set (the fp32 count chose it)
   double zero_center[kMaxDim];
   for (int j = 0; j < kMaxDim; j++) zero_center[j] = 0.0;
   __shared__ double sh_out[LSQR_MAX_PARAMS + 4];
@@ -218,7 +265,8 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
 int launch_batch(const BatchArgs& a, const EstCfg& cfg, int ls_type, cudaStream_t s) {
   if (a.n_problems == 0) return 0;
   const int D = model_info(a.model).D;
-  const size_t smem = (size_t)D * a.max_n * sizeof(double);
+  const bool use32 = a.precision == 1 && !a.exhaustive;
+  const size_t smem = (size_t)D * a.max_n * sizeof(double) + (use32 ? (size_t)D * ((a.max_n + 1u) & ~1u) * sizeof(float) : 0);
   if (smem > 200 * 1024) return -1;
   const int threads = a.exhaustive ? 256 : 64;
   const uint32_t group = a.exhaustive ? 1u : 2u;

@@ -531,6 +531,45 @@ def test_batched_small_problems_vs_oracle(port, name):
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["line2d", "plane3", "sphere3", "line3", "absor", "dense5", "plane6", "sphere5"])
+def test_batched_small_problems_fp32_scoring(port, name):
+    """Randomized batched mode with fp32 scoring (what the large-problem path does): the fast forms choose the hypothesis, everything
+    returned is fp64 -- the consensus set is agree() of the winner in reference arithmetic, the count is its size, the parameters
+    its least-squares fit -- and the consensus reached is what fp64 scoring reaches (same sampler, same stop rule)."""
+    m = MODELS[name]
+    D, P, k = INFO[m]
+    delta = synth.DELTAS[name]
+    nprob = 48
+    sizes = [150 + (37 * i) % 107 for i in range(nprob)]      # odd and even sizes: the fp32 copy is padded to a pair
+    sizes[3] = 1
+    sizes[5] = k
+    chunks = [synth.GENERATORS[name](max(s, k + 1), seed=700 + i)[0][:s] + (0.0 if name.startswith("dense") else 40.0 * i) for i, s in enumerate(sizes)]
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    data = np.concatenate(chunks)
+    eng = Engine(name, delta, ls_type=1)
+    o32 = eng.ransac_batch(data, offsets, prob=0.999, max_tries=2048, seed=5, want_masks=True, precision=FP32)
+    again = eng.ransac_batch(data, offsets, prob=0.999, max_tries=2048, seed=5, want_masks=True, precision=FP32)
+    o64 = eng.ransac_batch(data, offsets, prob=0.999, max_tries=2048, seed=5, want_masks=True, precision=FP64)
+    eng.close()
+    assert np.array_equal(o32["counts"], again["counts"]) and np.array_equal(o32["masks"], again["masks"])
+    assert np.array_equal(np.nan_to_num(o32["params"]), np.nan_to_num(again["params"]))
+    for i, ch in enumerate(chunks):
+        mask = o32["masks"][int(offsets[i]):int(offsets[i + 1])].astype(bool)
+        assert mask.sum() == o32["counts"][i], "the count is the fp64 size of the returned consensus set"
+        if sizes[i] < k or o32["counts"][i] == 0:
+            assert np.isnan(o32["params"][i]).all() or o32["counts"][i] >= k
+            continue
+        want = port.least_squares(m, delta, ch[mask], 1)
+        if len(want) == 0:
+            assert np.isnan(o32["params"][i]).all()
+        else:
+            assert same_up_to_sign(o32["params"][i], want, SIGN_IDX[name], REFINE_TOL), (i, o32["params"][i], want)
+    big = [i for i, s in enumerate(sizes) if s > 4 * k]
+    # same hypotheses, same stop rule: the two precisions agree on the winner except where fp32 rounding reorders near-ties
+    close = np.abs(o32["counts"][big].astype(np.int64) - o64["counts"][big].astype(np.int64)) <= np.maximum(2, 0.02 * o64["counts"][big])
+    assert close.mean() > 0.9, (o32["counts"][big], o64["counts"][big])
+
+
 def test_batched_problems_cross_copy_pieces_and_launches(port):
     """lsqr_ransac_batch uploads in pieces (4 MB from pageable memory) and launches per ~32 MB of problems: 100 000 copies of one
     16-point problem (38 MB) in exhaustive mode must all return the oracle's answer for that problem, whichever piece and launch

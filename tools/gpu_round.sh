@@ -50,6 +50,10 @@ profile_cb)   # ncu --set full of the constant-bank kernel for the models named 
     rm -f $OUT/cb_$mdl.ncu-rep
   done
   ;;
+batch)        # the batched path only: its GPU tests and the batch probe
+  timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_full_size_gpu.py -m gpu -q -k "batch" 2>&1 | tail -30 | tee $OUT/pytest_batch.log
+  timeout 300 python tools/batch_probe.py 2>&1 | tail -20 | tee $OUT/batch_probe.txt
+  ;;
 sweep_cb)     # times the blocking variants of tools/build_variants.sh against the shipped library, per model in $CB_MODELS
   for mdl in ${CB_MODELS:-uscp usxw ray circle2 sphere3}; do timeout 300 python tools/tune_cb.py $mdl 1000000 262144 2>&1 | grep "T evals" | tee -a $OUT/sweep_cb.txt; done
   ;;
