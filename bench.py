@@ -547,6 +547,7 @@ def main():
     n_kernel_launches = -(-N // tr["points_per_launch"]) if cb_match else None
     roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": tr["bytes_per_launch"] if cb_match else None,
+                "traffic_note": tr.get("step_level") if cb_match else None,
                 "kernel": "consensus_cb_kernel" if (precision == FP32 and Hper >= 98304) else "consensus_kernel", "kernel_ms": kern_ms,
                 "launches_per_step": n_kernel_launches,
                 "algorithmic_flop_per_launch": (float(Hper) * tr["points_per_launch"] * FLOP_PER_EVAL[model]) if cb_match else None,
