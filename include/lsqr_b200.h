@@ -71,7 +71,11 @@ typedef enum lsqr_status {
 
 typedef enum lsqr_precision {
   LSQR_FP64 = 0, /* validation mode: the reference's operation order, no FMA contraction; bit-exact counts */
-  LSQR_FP32 = 1  /* fast mode: hoisted constants, fused multiply-add */
+  LSQR_FP32 = 1  /* fast mode: hoisted constants, fused multiply-add.  Decisions differ from LSQR_FP64 only for data within the fp32
+                  * rounding band of the threshold.  The kD-line estimators are scored through the perpendicular (d = 2) / the Pluecker
+                  * moment (d = 3) of the direction, which is taken as the unit vector estimate() returns (it is re-normalised; imported
+                  * parameter vectors with a non-unit direction are scored as their normalised line, where LSQR_FP64 evaluates the
+                  * reference's expression literally, LineParametersEstimator.hxx:135-150). */
 } lsqr_precision;
 
 typedef enum lsqr_sampler {
