@@ -277,3 +277,23 @@ def random_subsets(n, k, H, seed=SEED):
             break
         s[bad] = rng.integers(0, n, size=(int(bad.sum()), k))
     return np.ascontiguousarray(s, dtype=np.int32)
+
+
+def degenerate_pool(name, n=48, seed=SEED):
+    """A data pool whose random minimal subsets are often DEGENERATE the way the reference's estimate() bodies test for:
+    repeated records, records that are exact copies up to a scale or a shift along one axis (collinear / coplanar / rank-
+    deficient subsets), all-zero records -- next to ordinary data, so that valid and invalid subsets are mixed."""
+    rng = np.random.default_rng(seed)
+    data, _ = GENERATORS[name](n, seed=seed)
+    d = data.shape[1]
+    q = n // 4
+    data[q:2 * q] = data[0]                                            # copies of one record
+    if d > 8:                                                           # frames (rotation + translation + ...): only repetition keeps a record meaningful
+        return np.ascontiguousarray(data[rng.permutation(n)])
+    base, step = data[1].copy(), np.zeros(d)
+    step[0] = 1.0
+    for i in range(2 * q, 3 * q):                                      # records on one axis-parallel line through record 1
+        data[i] = base + step * float(i - 2 * q)
+    data[3 * q] = 0.0                                                   # an all-zero record
+    data[3 * q + 1] = 2.0 * data[2]                                     # a scaled copy
+    return np.ascontiguousarray(data[rng.permutation(n)])

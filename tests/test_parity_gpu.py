@@ -64,6 +64,33 @@ def test_fp64_counts_bit_exact_vs_oracle_large(port, name, m):
 
 
 @pytest.mark.parametrize("name,m", ALL)
+def test_degenerate_subsets_are_rejected_like_the_oracle(port, name, m):
+    """Minimal subsets with repeated, collinear, scaled and all-zero records (synth.degenerate_pool; the oracle is pinned to the
+    reference on the same pools in tests/test_oracle.py): the device solvers reject exactly the subsets the oracle rejects
+    (a rejected hypothesis counts as a try and scores nothing, RANSAC.hxx:87-88), agree on the rest, and the arg-max ignores the
+    rejected ones."""
+    D, P, k = INFO[m]
+    data = synth.degenerate_pool(name, seed=31 + m)
+    subs = synth.random_subsets(len(data), k, 600, seed=7 + m)
+    delta = synth.DELTAS[name]
+    c_ref, p_ref = port.score_subsets(m, delta, data, subs)
+    eng = Engine(name, delta)
+    eng.upload(data)
+    r = eng.score(sampler=SAMPLE_LIST, subsets=subs, precision=FP64, want_counts=True, want_params=True)
+    bad = np.isnan(p_ref[:, 0])
+    assert bad.any() and not bad.all()
+    assert np.array_equal(np.isnan(r["params"][:, 0]), bad), "same subsets rejected"
+    assert r["n_valid"] == int((~bad).sum()) and np.all(r["counts"][bad] == 0)
+    if pinv_tol(name) is None:
+        assert np.array_equal(np.nan_to_num(r["params"]), np.nan_to_num(p_ref)) and np.array_equal(r["counts"], c_ref)
+        assert r["best_index"] == int(np.argmax(c_ref))
+    # the fp32 fast mode rejects the same subsets (the minimal solve is fp64 in both modes)
+    r32 = eng.score(sampler=SAMPLE_LIST, subsets=subs, precision=FP32, want_counts=True)
+    assert np.all(r32["counts"][bad] == 0) and r32["n_valid"] == r["n_valid"]
+    eng.close()
+
+
+@pytest.mark.parametrize("name,m", ALL)
 def test_exhaustive_compute_vs_reference_fixture(name, m):
     """RANSAC<T,S>::compute, brute-force overload (RANSAC.hxx:150-249), on the fixture's small problem."""
     g = golden(name)
