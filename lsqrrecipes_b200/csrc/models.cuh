@@ -513,7 +513,7 @@ template <int DIM> __device__ inline bool estimate_sphere_nd(const double* d, do
     b[i] = 0.0;
     for (int j = 0; j < DIM; j++) { A[i * DIM + j] = d[j] - d[(i + 1) * DIM + j]; b[i] += A[i * DIM + j] * (d[j] + d[(i + 1) * DIM + j]); }
   }
-  if (pinv_solve<DIM, DIM>(A, b, kSphereEps, x) < DIM) return false;
+  if (pinv_solve<DIM, DIM>(A, b, kEps, x) < DIM) return false;   // EPS of common/Epsilon.h here (:189), not the SPHERE_EPS of the 2-D / 3-D determinant tests
   double rSquared = 0.0;
   for (int i = 0; i < DIM; i++) { prm[i] = x[i] * 0.5; rSquared += (d[i] - prm[i]) * (d[i] - prm[i]); }
   prm[DIM] = sqrt(rSquared);

@@ -50,6 +50,12 @@ profile_cb)   # ncu --set full of the constant-bank kernel for the models named 
     rm -f $OUT/cb_$mdl.ncu-rep
   done
   ;;
+run)          # an arbitrary command: CMD="python tools/..."
+  timeout 900 bash -c "$CMD" 2>&1 | tail -60 | tee $OUT/run.log
+  ;;
+only)         # a subset of the GPU tests: K="<pytest -k expression>"
+  timeout 900 python -m pytest tests -m gpu -q -k "${K:-degenerate}" 2>&1 | tail -40 | tee $OUT/pytest_only.log
+  ;;
 batch)        # the batched path only: its GPU tests and the batch probe
   timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_full_size_gpu.py -m gpu -q -k "batch" 2>&1 | tail -30 | tee $OUT/pytest_batch.log
   timeout 300 python tools/batch_probe.py 2>&1 | tail -20 | tee $OUT/batch_probe.txt
