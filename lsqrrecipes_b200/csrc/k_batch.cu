@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
           if constexpr (Eval<M>::kShifted) c = negk ? 2u * pairs - (uint32_t)(out >> 32) : 0u;   // outliers were counted (NaN padding among them)
         }
       } else if (ok) {
-        prepare<M>(prm, hq);
+        prepare<M>(prm, cfg, hq);
         for (uint32_t i = sub_lane; i < n; i += G) {
           double x[D];
 #pragma unroll
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256) batch_kernel(BatchArgs a, EstCfg cfg, int
       if (a.exhaustive) unrank_lex<K>(h, n, sub); else sample_subset<K>((gb << 32) | h, a.seed, n, sub);
       double sp[K * D], prm[P];
       for (int j = 0; j < K; j++) for (int d = 0; d < D; d++) sp[j * D + d] = pts[d * ldp + sub[j]];
-      if (estimate<M>(sp, cfg, prm)) { prepare<M>(prm, sh_prm); sh_ok = 1; }
+      if (estimate<M>(sp, cfg, prm)) { prepare<M>(prm, cfg, sh_prm); sh_ok = 1; }
     }
   }
   __syncthreads();

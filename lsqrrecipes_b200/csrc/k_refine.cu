@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(MMCfg<M, LM>::THREADS, 1) mask_moments_kernel(
     double prm[P];
 #pragma unroll
     for (int j = 0; j < P; j++) prm[j] = params_dev[j];
-    prepare<M>(prm, hq);
+    prepare<M>(prm, cfg, hq);
   }
   // the shift c of the centred components, once per thread (a load inside the loop would put a global-memory latency on every
   // row's critical path)

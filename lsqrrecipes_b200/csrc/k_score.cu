@@ -232,7 +232,7 @@ template <int M> struct Exact {
   using real = double;
   using thr_t = EstCfg;
   static constexpr int D = Model<M>::D, NIN = Model<M>::P, HQ = Model<M>::HQ, UNR = 2;
-  __device__ static __forceinline__ void load(const double* raw, double* hq) { prepare<M>(raw, hq); }
+  __device__ static __forceinline__ void load(const double* raw, const EstCfg& t, double* hq) { prepare<M>(raw, t, hq); }
   __device__ static __forceinline__ bool test(const double* hq, const double* x, const EstCfg& t) { return agree<M>(hq, x, t); }
 };
 template <class T, int R, int THREADS, int TILE>
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(THREADS) consensus_kernel(const typename T::re
     real raw[T::NIN];
 #pragma unroll
     for (int j = 0; j < T::NIN; j++) raw[j] = (h < H) ? hyp[(size_t)j * hld + h] : (real)NAN;
-    T::load(raw, hq[r]);
+    T::load(raw, thr, hq[r]);
     cnt[r] = 0;
   }
 
@@ -334,13 +334,17 @@ static int run_consensus(const typename T::real* soa, size_t ld, size_t span, co
   return 1;
 }
 
+// hypotheses per thread of the fp64 validation kernel (models with up to 11 prepared doubles per hypothesis)
+#ifndef LSQR_FP64_R
+#define LSQR_FP64_R 4
+#endif
 int launch_consensus(int model, int precision, const DataView& dv, const double* hyp64, const float* hyp32, size_t hld, uint32_t H,
                      const EstCfg& cfg, uint32_t* counts, int num_sms, cudaStream_t s) {
   if (H == 0 || dv.n == 0) return 0;
   if (precision == 0) {
 #define CALL(MM)                                                                                                             \
   if (H <= 4096) return run_consensus<Exact<MM>, 1, 128, 256>(dv.soa64, dv.ld, dv.span, hyp64, hld, H, cfg, counts, num_sms, s);       \
-  return run_consensus<Exact<MM>, (Model<MM>::HQ >= 12 ? 2 : 4), 128, 256>(dv.soa64, dv.ld, dv.span, hyp64, hld, H, cfg, counts, num_sms, s)
+  return run_consensus<Exact<MM>, (Model<MM>::HQ >= 12 ? 2 : LSQR_FP64_R), 128, 256>(dv.soa64, dv.ld, dv.span, hyp64, hld, H, cfg, counts, num_sms, s)
     LSQR_DISPATCH_MODEL(model, CALL)
 #undef CALL
   } else {
@@ -406,7 +410,7 @@ __global__ void agree_many_kernel(const double* __restrict__ params, const doubl
   double prm[P], hq[HQ], x[D];
 #pragma unroll
   for (int j = 0; j < P; j++) prm[j] = params[j];
-  prepare<M>(prm, hq);
+  prepare<M>(prm, cfg, hq);
 #pragma unroll
   for (int d = 0; d < D; d++) x[d] = packed[(size_t)i * D + d];
   out[i] = agree<M>(hq, x, cfg) ? 1 : 0;

@@ -58,7 +58,7 @@ __host__ __device__ constexpr ModelInfo model_info(int m) {
   const int d = model_dim(m);
   switch (model_family(m)) {
     case FAM_PLANE:  return {d, 2 * d, d, 2 * d, d + 1};
-    case FAM_SPHERE: return {d, d + 1, d + 1, d + 1, d + 2};
+    case FAM_SPHERE: return {d, d + 1, d + 1, d + 5, d + 2};   // prepared: centre, radius and four squared-distance thresholds (prepare_sphere)
     case FAM_LINE:   return {d, 2 * d, 2, 2 * d, d == 2 ? 3 : (d == 3 ? 9 : 2 * d)};   // fp32: 2-D form, Pluecker form, literal form (k_fast.cu)
     // DenseLinearEquationSystemParametersEstimator<double, n>: datum = AugmentedRow (n coefficients, right-hand side)
     case FAM_DENSE:  return {d + 1, d, d, d, d + 2};
@@ -543,17 +543,17 @@ template <> __device__ inline bool estimate<USCP>(const double* d, const EstCfg&
 // ---------------------------------------------------------------------------------------
 // agree(): prepare once per hypothesis, test once per (hypothesis, datum)
 // ---------------------------------------------------------------------------------------
-template <int M> __device__ __forceinline__ void prepare(const double* prm, double* hq) {
+template <int M> __device__ __forceinline__ void prepare(const double* prm, const EstCfg&, double* hq) {
 #pragma unroll
   for (int i = 0; i < Model<M>::P; i++) hq[i] = prm[i];
 }
-template <> __device__ __forceinline__ void prepare<ABSOR>(const double* prm, double* hq) {
+template <> __device__ __forceinline__ void prepare<ABSOR>(const double* prm, const EstCfg&, double* hq) {
   quat_to_rot(prm[0], prm[1], prm[2], prm[3], hq);
   hq[9] = prm[4]; hq[10] = prm[5]; hq[11] = prm[6];
 }
 
 // cross-wire: the twelve entries agree() reads -- m_x R3(:,1), m_y R3(:,2), t3, t1
-template <> __device__ __forceinline__ void prepare<USXW>(const double* prm, double* hq) {
+template <> __device__ __forceinline__ void prepare<USXW>(const double* prm, const EstCfg&, double* hq) {
 #pragma unroll
   for (int i = 0; i < 6; i++) hq[i] = prm[11 + i];
 #pragma unroll
@@ -561,7 +561,7 @@ template <> __device__ __forceinline__ void prepare<USXW>(const double* prm, dou
 }
 
 // calibrated pointer: m_x R3(:,1), m_y R3(:,2), t3
-template <> __device__ __forceinline__ void prepare<USCP>(const double* prm, double* hq) {
+template <> __device__ __forceinline__ void prepare<USCP>(const double* prm, const EstCfg&, double* hq) {
 #pragma unroll
   for (int i = 0; i < 6; i++) hq[i] = prm[8 + i];
 #pragma unroll
@@ -609,25 +609,42 @@ LSQR_LINE_ND_LIST(LSQR_DEF_)
 // SphereParametersEstimator.hxx:255-264 (a distance against delta, not squared): |sqrt(dl) - r| < delta.
 // The square root (a ~20-instruction sequence on the FP64 pipe) decides nothing for a datum whose squared distance is clear
 // of both (r - delta)^2 and (r + delta)^2 by more than any rounding of the reference's expression could move it (1e-9
-// relative, against a few ulp = 4e-16); only data inside those two slivers take the reference's expression literally.  The
-// decision is the reference's for every datum -- the streaming refine pass of the sphere went from 0.61 to the plane's
-// fraction of HBM bandwidth with this, the FP64 validation kernel of the sphere by the share of the square root.
-template <int DIM> __device__ __forceinline__ bool agree_sphere(const double* h, const double* x, const EstCfg& cfg) {
-  double dl = 0;
+// relative on the squared distance = 5e-10 (r +- delta) on the distance, against the few ulp = 4e-16 r the roundings can move
+// it); only data inside those two slivers take the reference's expression literally.  The decision is the reference's for
+// every datum.  The four thresholds are prepared once per hypothesis (prepare_sphere) as bit patterns: the squared distance is
+// a sum of squares (>= +0, +inf or NaN), so it orders like its bits and the tests run on the integer ALU:
+//   bits(dl) > OUT_HI or < OUT_LO : surely outside (NaN and +inf included);   IN_LO < bits(dl) < IN_HI : surely inside.
+// A threshold that must not fire is all-ones (never exceeded) or zero (nothing below it): delta <= 0 or NaN, r <= 0 or NaN
+// disable all four, a radius within 0.1 % of delta (where the margin on r - delta would not cover its own rounding) the
+// three that involve r - delta.  hq = [centre (DIM), r, OUT_HI, OUT_LO, IN_HI, IN_LO].
+template <int DIM> __device__ __forceinline__ void prepare_sphere(const double* prm, const EstCfg& cfg, double* hq) {
 #pragma unroll
-  for (int i = 0; i < DIM; i++) dl += ((x[i] - h[i]) * (x[i] - h[i]));
-  const double r = h[DIM], hi = r + cfg.delta, lo = r - cfg.delta;
-  if (cfg.delta > 0.0 && r > 0.0) {      // (NaN or non-positive radius / threshold: literal path)
-    constexpr double kUp = 1.0 + 1e-9, kDn = 1.0 - 1e-9;   // margins of 5e-10 (r +- delta) on sqrt(dl): >> the ~4e-16 r the roundings can move
-    const double hi2 = hi * hi;
-    if (dl > hi2 * kUp) return false;                       // sqrt(dl) > r + delta for sure
-    if (lo > 1e-3 * r) {                                    // (a radius within 0.1 % of delta: the margin on r - delta would not cover its own rounding)
-      const double lo2 = lo * lo;
-      if (dl < lo2 * kDn) return false;                     // sqrt(dl) < r - delta for sure
-      if (dl < hi2 * kDn && dl > lo2 * kUp) return true;    // strictly between
+  for (int i = 0; i <= DIM; i++) hq[i] = prm[i];
+  const double r = prm[DIM], hi = r + cfg.delta, lo = r - cfg.delta;
+  constexpr double kUp = 1.0 + 1e-9, kDn = 1.0 - 1e-9;
+  long long out_hi = -1LL, out_lo = 0, in_hi = 0, in_lo = -1LL;
+  if (cfg.delta > 0.0 && r > 0.0 && hi < 1e150) {
+    out_hi = __double_as_longlong(hi * hi * kUp);
+    if (lo > 1e-3 * r) {
+      out_lo = __double_as_longlong(lo * lo * kDn);
+      in_hi = __double_as_longlong(hi * hi * kDn);
+      in_lo = __double_as_longlong(lo * lo * kUp);
     }
   }
-  dl = fabs(sqrt(dl) - r);
+  hq[DIM + 1] = __longlong_as_double(out_hi); hq[DIM + 2] = __longlong_as_double(out_lo);
+  hq[DIM + 3] = __longlong_as_double(in_hi); hq[DIM + 4] = __longlong_as_double(in_lo);
+}
+#define LSQR_DEF_(ID, DIM) template <> __device__ __forceinline__ void prepare<ID>(const double* prm, const EstCfg& cfg, double* hq) { prepare_sphere<DIM>(prm, cfg, hq); }
+LSQR_SPHERE_ALL_LIST(LSQR_DEF_)
+#undef LSQR_DEF_
+template <int DIM> __device__ __forceinline__ bool agree_sphere(const double* h, const double* x, const EstCfg& cfg) {
+  double dl = (x[0] - h[0]) * (x[0] - h[0]);      // (the reference's leading `0 +` cannot change a non-negative term)
+#pragma unroll
+  for (int i = 1; i < DIM; i++) dl += ((x[i] - h[i]) * (x[i] - h[i]));
+  const unsigned long long b = (unsigned long long)__double_as_longlong(dl);
+  if (b > (unsigned long long)__double_as_longlong(h[DIM + 1]) || b < (unsigned long long)__double_as_longlong(h[DIM + 2])) return false;
+  if (b < (unsigned long long)__double_as_longlong(h[DIM + 3]) && b > (unsigned long long)__double_as_longlong(h[DIM + 4])) return true;
+  dl = fabs(sqrt(dl) - h[DIM]);
   return dl < cfg.delta;
 }
 #define LSQR_DEF_(ID, DIM) template <> __device__ __forceinline__ bool agree<ID>(const double* h, const double* x, const EstCfg& c) { return agree_sphere<DIM>(h, x, c); }
