@@ -641,9 +641,12 @@ template <int DIM> __device__ __forceinline__ bool agree_sphere(const double* h,
   double dl = (x[0] - h[0]) * (x[0] - h[0]);      // (the reference's leading `0 +` cannot change a non-negative term)
 #pragma unroll
   for (int i = 1; i < DIM; i++) dl += ((x[i] - h[i]) * (x[i] - h[i]));
-  const unsigned long long b = (unsigned long long)__double_as_longlong(dl);
-  if (b > (unsigned long long)__double_as_longlong(h[DIM + 1]) || b < (unsigned long long)__double_as_longlong(h[DIM + 2])) return false;
-  if (b < (unsigned long long)__double_as_longlong(h[DIM + 3]) && b > (unsigned long long)__double_as_longlong(h[DIM + 4])) return true;
+  // only the HIGH words are compared (one 32-bit compare per threshold instead of two chained ones: the integer ALU would
+  // otherwise bound the kernel): a strictly larger / smaller high word implies the 64-bit relation, equal high words -- a sliver
+  // of 2^-20 relative around a threshold -- fall through to the literal expression
+  const unsigned b = (unsigned)__double2hiint(dl);
+  if (b > (unsigned)__double2hiint(h[DIM + 1]) || b < (unsigned)__double2hiint(h[DIM + 2])) return false;
+  if (b < (unsigned)__double2hiint(h[DIM + 3]) && b > (unsigned)__double2hiint(h[DIM + 4])) return true;
   dl = fabs(sqrt(dl) - h[DIM]);
   return dl < cfg.delta;
 }
