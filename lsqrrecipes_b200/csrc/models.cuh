@@ -678,6 +678,12 @@ template <> __device__ __forceinline__ bool agree<PIVOT>(const double* h, const 
   const double rx = qx - h[3], ry = qy - h[4], rz = qz - h[5];
   double s = 0;
   s += rx * rx; s += ry * ry; s += rz * rz;
+  // sqrt(s) < delta is decided by s against delta^2 wherever s is clear of it by more than the roundings of the literal
+  // expression can matter (1e-9 relative against a few ulp); the square root is taken only inside that sliver
+  if (cfg.delta > 0.0) {
+    if (s < cfg.delta2 * (1.0 - 1e-9)) return true;
+    if (s > cfg.delta2 * (1.0 + 1e-9)) return false;
+  }
   return sqrt(s) < cfg.delta;
 }
 
