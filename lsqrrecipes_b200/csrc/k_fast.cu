@@ -314,7 +314,8 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
 }
 
 // Hypotheses per thread (R) / point pairs per iteration (PPI) of the constant-bank kernel (128 threads), from the sweeps in
-// profiles/r01_tune_cb_sweep_models.txt and profiles/r02_tune_cb_blocking.txt.  Two things decide them:
+// profiles/r01_tune_cb_sweep_models.txt and profiles/r02_tune_cb_blocking.txt (the plane's 12 x 8 -- sixteen points per iteration --
+// is 4.6 % faster than the 10 x 4 it replaced: half the loop overhead per point).  Two things decide them:
 //   * few hypotheses per thread on a model with few operations per datum make the uniform constant loads (D per point pair)
 //     the limit: 3-8x slower, see the plane4 / dense5 columns of the first sweep;
 //   * ptxas fetches the data with LDCU into uniform registers only when a loaded pair has enough consumers in the loop body;
@@ -325,10 +326,10 @@ __global__ void __launch_bounds__(THREADS, LSQR_CB_MINBLOCKS) consensus_cb_kerne
 #define LSQR_CB_THREADS 128
 #endif
 #ifndef LSQR_CB_R_PLANE
-#define LSQR_CB_R_PLANE 10
+#define LSQR_CB_R_PLANE 12
 #endif
 #ifndef LSQR_CB_PPI_PLANE
-#define LSQR_CB_PPI_PLANE 4
+#define LSQR_CB_PPI_PLANE 8
 #endif
 constexpr int cb_blocking(int m, bool want_r) {
 #ifdef LSQR_CB_OVR_MODEL      // R&D builds (tools/build_variants.sh): override one model
@@ -337,9 +338,10 @@ constexpr int cb_blocking(int m, bool want_r) {
   int r = 8, ppi = 2;
   switch (m) {
     case PLANE3: r = LSQR_CB_R_PLANE; ppi = LSQR_CB_PPI_PLANE; break;
-    case LINE2D: case LINE2: r = 14; ppi = 4; break;   // two counters per hypothesis (mixed count): 16 would spill
+    case LINE2D: case LINE2: r = 12; ppi = 8; break;   // two counters per hypothesis (mixed count): 16 x 4 spills, 12 x 8 measured 2.5 % over 14 x 4
     case PLANE2: r = 16; ppi = 4; break;
-    case LINE3: r = 8; ppi = 2; break;
+    case LINE3: r = 8; ppi = 4; break;
+    case DENSE2: r = 10; ppi = 8; break;
     case CIRCLE2: r = 12; ppi = 2; break;
     case SPHERE3: r = 10; ppi = 2; break;
     case ABSOR: r = 4; ppi = 4; break;

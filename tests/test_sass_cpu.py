@@ -35,17 +35,17 @@ def _one(funcs, pattern):
 
 
 def test_plane_kernel_counts_through_the_carry_chain(sass):
-    """consensus_cb_kernel<PLANE3, 10, 128, 4>: per pair of residuals 3 FFMA2 with a uniform-register point operand, two IADD3 that
+    """consensus_cb_kernel<PLANE3, 12, 128, 8>: per pair of residuals 3 FFMA2 with a uniform-register point operand, two IADD3 that
     write only a carry predicate and one IADD3.X that consumes two predicates; no FSET / FSETP / LEA.HI in the loop."""
-    ins = _one(sass, r"consensus_cb_kernelILi0ELi10ELi128ELi4E")
+    ins = _one(sass, r"consensus_cb_kernelILi0ELi12ELi128ELi8E")
     ffma2 = [i for i in ins if i.startswith("FFMA2")]
-    assert len(ffma2) >= 120 and sum("UR" in i for i in ffma2) >= 120, "points must come as uniform-register operands"
+    assert len(ffma2) >= 288 and sum("UR" in i for i in ffma2) >= 288, "points must come as uniform-register operands"
     cmp_ = [i for i in ins if re.match(r"IADD3 RZ, P\d, PT, R\d+, UR\d+, RZ", i)]
     addx = [i for i in ins if re.match(r"IADD3\.X R\d+, PT, PT, RZ, RZ, R\d+, P\d, P\d", i)]
-    assert len(cmp_) >= 80 and len(addx) >= 40, (len(cmp_), len(addx))
+    assert len(cmp_) >= 192 and len(addx) >= 96, (len(cmp_), len(addx))
     assert not [i for i in ins if i.startswith(("FSET", "FSETP"))]          # no float compare left in this kernel
     assert sum(i.startswith("LEA.HI") for i in ins) <= 2                    # (index arithmetic outside the loop)
-    assert sum(i.startswith("LDCU") for i in ins) >= 12, "constant-bank loads"
+    assert sum(i.startswith("LDCU") for i in ins) >= 24, "constant-bank loads"
 
 
 def test_sphere_kernel_counts_through_the_carry_chain_with_its_own_window(sass):
