@@ -43,6 +43,7 @@
 using namespace lsqr;
 
 namespace {
+constexpr size_t kAgreeZeroCopy = 16;   // lsqr_agree: up to this many data are read by the kernel straight from page-locked host memory
 constexpr int kSmall = 1024, kSmIn = 0, kSmOut = 32, kSmLm = 64, kSmEst = 640, kSmSink = 800;   // layout of lsqr_ctx::small_dev
 
 // ---- NCCL, resolved at first use ---------------------------------------------------------------
@@ -231,6 +232,7 @@ struct lsqr_ctx {
   unsigned char* gather_pin = nullptr; size_t gather_pin_cap = 0;
   uint8_t* mask_dev = nullptr; size_t mask_dev_cap = 0;   // consensus set, one byte per datum (device)
   uint8_t* mask_pin = nullptr; size_t mask_pin_cap = 0;   // pinned bounce buffer for its download
+  double* agree_pin = nullptr;                            // lsqr_agree on a handful of data: zero-copy parameters, data and answers
   // upload pipeline
   static constexpr int kRing = 4;
   unsigned char* up_pin[kRing] = {nullptr, nullptr, nullptr, nullptr}; size_t up_pin_bytes = 0;
@@ -1217,7 +1219,7 @@ void lsqr_ctx_destroy(lsqr_ctx* ctx) {
   ctx->copier.reset();
   free_dataset(ctx->main); free_dataset(ctx->scratch);
   cudaFree(ctx->bt_data); cudaFree(ctx->bt_off); cudaFree(ctx->bt_prm); cudaFree(ctx->bt_cnt);
-  cudaFree(ctx->weights_dev); cudaFree(ctx->mask_dev); if (ctx->mask_pin) cudaFreeHost(ctx->mask_pin);
+  cudaFree(ctx->weights_dev); cudaFree(ctx->mask_dev); if (ctx->mask_pin) cudaFreeHost(ctx->mask_pin); if (ctx->agree_pin) cudaFreeHost(ctx->agree_pin);
   cudaFree(ctx->gather_dev); if (ctx->gather_pin) cudaFreeHost(ctx->gather_pin);
   for (int i = 0; i < lsqr_ctx::kRing; i++) if (ctx->up_pin[i]) cudaFreeHost(ctx->up_pin[i]);
   cudaFree(ctx->staging); cudaFree(ctx->subsets); cudaFree(ctx->hyp64); cudaFree(ctx->hyp32); cudaFree(ctx->counts);
@@ -1444,6 +1446,20 @@ int lsqr_agree(lsqr_ctx* ctx, const double* params, const double* packed, size_t
   const ModelInfo mi = model_info(ctx->model);
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
+  if (n <= kAgreeZeroCopy) {
+    // a handful of data (the reference's examples call agree() datum by datum): parameters and data go into a small page-locked
+    // buffer that the kernel reads in place and answers into (unified addressing) -- one launch and one synchronisation, no copies
+    if (!ctx->agree_pin) CK(cudaMallocHost((void**)&ctx->agree_pin, sizeof(double) * (LSQR_MAX_PARAMS + kAgreeZeroCopy * kMaxDim) + kAgreeZeroCopy));
+    double* hp = ctx->agree_pin;
+    uint8_t* ho = reinterpret_cast<uint8_t*>(hp + LSQR_MAX_PARAMS + kAgreeZeroCopy * kMaxDim);
+    memcpy(hp, params, sizeof(double) * mi.P);
+    memcpy(hp + LSQR_MAX_PARAMS, packed, sizeof(double) * n * mi.D);
+    launch_agree_many(ctx->model, hp, hp + LSQR_MAX_PARAMS, (uint32_t)n, ctx->cfg, ho, s); ctx->launches++;
+    CKL();
+    CK(cudaStreamSynchronize(s));
+    memcpy(out, ho, n);
+    return LSQR_OK;
+  }
   if (int rc = ensure(ctx, &ctx->staging, &ctx->staging_cap, n * mi.D * sizeof(double) + n)) return rc;
   double* d_in = reinterpret_cast<double*>(ctx->staging);
   uint8_t* d_out = ctx->staging + n * mi.D * sizeof(double);
