@@ -197,3 +197,33 @@ def test_port_matches_reference_on_degenerate_subsets(port, ref, name, m):
     else:
         assert np.array_equal(np.nan_to_num(p1), np.nan_to_num(p2))
         assert np.array_equal(c1, c2)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_port_matches_reference_across_seeds_and_thresholds(port, ref, seed):
+    """Every model on fresh data with a threshold drawn per seed (tight thresholds put many data near the decision boundary):
+    counts bit-exact, estimate() bit-exact where the reference's arithmetic is plain double, least squares over the best
+    consensus set within 1e-8 (1e-6 for the cross-wire valley)."""
+    rng = np.random.default_rng(1000 + seed)
+    for name, m in ALL:
+        D, P, k = INFO[m]
+        n = 160
+        data, _ = synth.GENERATORS[name](n, seed=5000 + 37 * seed + m)
+        delta = synth.DELTAS[name] * float(rng.choice([0.25, 1.0, 3.0]))
+        subs = synth.random_subsets(n, k, 120, seed=seed + m)
+        c1, p1 = port.score_subsets(m, delta, data, subs)
+        c2, p2 = ref.score_subsets(m, delta, data, subs)
+        assert np.array_equal(np.isnan(p1), np.isnan(p2)), name
+        if pinv_tol(name) is None:
+            assert np.array_equal(np.nan_to_num(p1), np.nan_to_num(p2)) and np.array_equal(c1, c2), name
+        else:
+            assert np.allclose(np.nan_to_num(p1), np.nan_to_num(p2), rtol=pinv_tol(name), atol=pinv_tol(name)), name
+            # counts of the pseudo-inverse models: identical on identical parameter vectors
+            b = int(np.argmax(c2))
+            assert port.agree(m, delta, p2[b], data)[0] == ref.agree(m, delta, p2[b], data)[0] == c2[b], name
+        b = int(np.argmax(c2))
+        _, mask = ref.agree(m, delta, p2[b], data)
+        inl = data[mask.astype(bool)]
+        if len(inl) >= max(k, 4) and name != "usxw":
+            a, r = port.least_squares(m, delta, inl, 0), ref.least_squares(m, delta, inl, 0)
+            assert same_up_to_sign(a, r, SIGN_IDX[name], 1e-8), name
