@@ -26,6 +26,12 @@ def test_reference_arm_prints_one_json_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port", "ref") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the second half of the metric: the reference's own RANSAC<T,S>::compute, one thread as shipped (only oracle/_ref has it)
+    if cb["kind"] == "reference":
+        assert d["compute_e2e"]["ms"] > 0 and d["compute_e2e"]["threads"] == 1 and d["compute_e2e"]["points"] == 20000
+        kinds = [c["model"] for c in d["configs"]]
+        assert kinds == ["sphere3", "absor", "line2d", "plane3"] and all(c["threads"] == 1 for c in d["configs"])
+        assert d["configs"][0]["ms"] > 0 and d["configs"][2]["problems_per_s"] > 0
 
 
 def test_reference_arm_other_ranks_exit_quietly():
